@@ -1,0 +1,307 @@
+"""Oracle (torch-CPU, fp32) restatement of the reference's embedding-extraction forward.
+
+TEST INFRASTRUCTURE ONLY -- see ``oracle/__init__.py``.  Layout follows the reference:
+activations are ``(B, C, T)`` (time contiguous), features arrive as ``(T, F)``.
+
+The arithmetic goes through the same ATen CPU ops the reference calls (``F.pad`` +
+``weight*mask`` + ``F.conv1d`` including the masked taps, ``F.batch_norm`` in eval
+mode ...), so timing this file on host cores is a faithful stand-in for "the
+reference's CPU PyTorch path" (``bench.py`` ``cpu_baseline``, kind ``"port"``).
+Parity is pinned by ``tests/golden/*.npz`` produced from the imported reference.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-5  # torch.nn.BatchNorm1d default, used everywhere in the reference
+
+
+# --------------------------------------------------------------------------------------
+# Layer restatements
+# --------------------------------------------------------------------------------------
+def context_span(context):
+    """left/right/total context exactly as TdnnAffine.__init__ computes them
+    (pytorch/libs/nnet/components.py:50-53)."""
+    left = context[0] if context[0] < 0 else 0
+    right = context[-1] if context[-1] > 0 else 0
+    return left, right, right - left + 1
+
+
+def tdnn_affine(x, weight, bias, context):
+    """TdnnAffine.forward, pytorch/libs/nnet/components.py:107-149.
+
+    x (B, Cin, T); weight (Cout, Cin, tot_context) *including* the masked taps; zero pad
+    (-left, right) (:117); taps not in ``context`` are multiplied by 0 (:133-138); dense
+    conv1d, stride 1 (:147)."""
+    left, right, tot = context_span(context)
+    assert weight.shape[2] == tot, (weight.shape, context)
+    x = F.pad(x, (-left, right), mode="constant", value=0.0)
+    if len(context) != tot:
+        mask = torch.tensor([[[1.0 if i in context else 0.0 for i in range(left, right + 1)]]],
+                            dtype=weight.dtype)
+        weight = weight * mask
+    return F.conv1d(x, weight, bias, stride=1, padding=0, dilation=1, groups=1)
+
+
+def batchnorm_eval(x, sd, prefix):
+    """BatchNorm1d in eval mode (running stats, eps 1e-5); affine optional
+    (components.py:374-378; ECAPA fc2 uses affine=False, runEcapaXvector_online.py:243-247)."""
+    w = sd.get(prefix + ".weight")
+    b = sd.get(prefix + ".bias")
+    return F.batch_norm(x, sd[prefix + ".running_mean"], sd[prefix + ".running_var"], w, b,
+                        training=False, momentum=0.0, eps=BN_EPS)
+
+
+def relu_bn_tdnn_layer(x, sd, prefix, context, relu=True, bn=True):
+    """ReluBatchNormTdnnLayer.forward = affine -> ReLU -> BatchNorm (order: ReLU first),
+    components.py:410-431, :434-461."""
+    y = tdnn_affine(x, sd[prefix + ".affine.weight"], sd[prefix + ".affine.bias"], context)
+    if relu:
+        y = F.relu(y)
+    if bn:
+        y = batchnorm_eval(y, sd, prefix + ".batchnorm")
+    return y
+
+
+def statistics_pooling(x, eps=1.0e-10):
+    """StatisticsPooling.forward, no-lengths branch, pytorch/libs/nnet/pooling.py:58-67:
+    mean over T; biased variance sum((x-mean)^2)/T; std = sqrt(clamp(var, eps)); cat."""
+    counts = x.shape[2]
+    mean = x.mean(dim=2, keepdim=True)
+    var = torch.sum((x - mean) ** 2, dim=2, keepdim=True) / counts
+    std = torch.sqrt(var.clamp(min=eps))
+    return torch.cat((mean, std), dim=1)
+
+
+# --------------------------------------------------------------------------------------
+# Standard x-vector (pytorch/model/xvector.py)
+# --------------------------------------------------------------------------------------
+XVECTOR_LAYERS = (  # name, context  (xvector.py:26-33)
+    ("tdnn1", [-2, -1, 0, 1, 2]),
+    ("tdnn2", [-2, 0, 2]),
+    ("tdnn3", [-3, 0, 3]),
+    ("tdnn4", [0]),
+    ("tdnn5", [0]),
+)
+
+
+def xvector_forward(sd, x, extracted_embedding="far", return_intermediates=False):
+    """Xvector.extract_embedding body, pytorch/model/xvector.py:84-98.  x (B, F, T)."""
+    inter = OrderedDict()
+    for name, ctx in XVECTOR_LAYERS:
+        x = relu_bn_tdnn_layer(x, sd, name, ctx)
+        inter[name] = x
+    x = statistics_pooling(x)
+    inter["stats"] = x
+    if extracted_embedding == "far":
+        x = tdnn_affine(x, sd["tdnn6.affine.weight"], sd["tdnn6.affine.bias"], [0])
+    elif extracted_embedding == "near":
+        x = relu_bn_tdnn_layer(x, sd, "tdnn6", [0])
+        x = tdnn_affine(x, sd["tdnn7.affine.weight"], sd["tdnn7.affine.bias"], [0])
+    else:
+        raise TypeError("Expected far or near position, but got {}".format(extracted_embedding))
+    return (x, inter) if return_intermediates else x
+
+
+# --------------------------------------------------------------------------------------
+# ECAPA-TDNN c1024 (pytorch/model/ecapa_tdnn_xvector.py)
+# --------------------------------------------------------------------------------------
+def res2net_block(x, sd, prefix, dilation, scale=8):
+    """Res2NetBlock.forward, ecapa_tdnn_xvector.py:61-75 (context from :50-51)."""
+    ctx = [-dilation, 0, dilation]
+    spx = torch.chunk(x, scale, dim=1)
+    y = [spx[0]]
+    sp = None
+    for i in range(scale - 1):
+        sp = spx[i + 1] if i == 0 else sp + spx[i + 1]
+        sp = relu_bn_tdnn_layer(sp, sd, "{}.blocks.{}".format(prefix, i), ctx)
+        y.append(sp)
+    return torch.cat(y, dim=1)
+
+
+def se_connect(x, sd, prefix):
+    """SE_Connect.forward, ecapa_tdnn_xvector.py:97-111: avgpool(T) -> conv1x1 -> ReLU ->
+    conv1x1 -> sigmoid; x * gate."""
+    s = x.mean(dim=2, keepdim=True)
+    s = F.relu(F.conv1d(s, sd[prefix + ".se.1.weight"], sd[prefix + ".se.1.bias"]))
+    s = torch.sigmoid(F.conv1d(s, sd[prefix + ".se.3.weight"], sd[prefix + ".se.3.bias"]))
+    return x * s
+
+
+def se_res2block(x, sd, prefix, dilation):
+    """SE_Res2Block.forward, ecapa_tdnn_xvector.py:139-149 (in==out so no shortcut conv)."""
+    residual = x
+    x = relu_bn_tdnn_layer(x, sd, prefix + ".conv_relu_bn1", [0])
+    x = res2net_block(x, sd, prefix + ".res2net_block", dilation)
+    x = relu_bn_tdnn_layer(x, sd, prefix + ".conv_relu_bn2", [0])
+    x = se_connect(x, sd, prefix + ".se")
+    return x + residual
+
+
+def attentive_stats_pool(x, sd, prefix="stats"):
+    """AttentiveStatsPool.forward with time_attention=True, ecapa_tdnn_xvector.py:173-188.
+    global std uses torch.var default (unbiased) + 1e-5 (:177-178); attention =
+    conv -> ReLU -> BN -> tanh -> conv -> softmax over T (:164-171)."""
+    g_mean = torch.mean(x, dim=2, keepdim=True).expand_as(x)
+    g_std = torch.sqrt(torch.var(x, dim=-1, keepdim=True) + 1e-5).expand_as(x)
+    x_in = torch.cat((x, g_mean, g_std), dim=1)
+    a = F.conv1d(x_in, sd[prefix + ".attention.0.weight"], sd[prefix + ".attention.0.bias"])
+    a = F.relu(a)
+    a = batchnorm_eval(a, sd, prefix + ".attention.2")
+    a = torch.tanh(a)
+    a = F.conv1d(a, sd[prefix + ".attention.4.weight"], sd[prefix + ".attention.4.bias"])
+    alpha = torch.softmax(a, dim=2)
+    mean = torch.sum(alpha * x, dim=2)
+    residuals = torch.sum(alpha * (x ** 2), dim=2) - mean ** 2
+    std = torch.sqrt(residuals.clamp(min=1e-5))
+    return torch.cat([mean, std], dim=1)
+
+
+def ecapa_forward(sd, x, extracted_embedding="near", fc2_relu=False, return_intermediates=False):
+    """ECAPA_TDNN.extract_embedding body, ecapa_tdnn_xvector.py:403-426 with the canonical
+    c1024 parameters of pytorch/launcher/runEcapaXvector_online.py:221-263 (fc1=False; fc2
+    nonlinearity '' and BN affine=False -> ``fc2_relu=False`` and no fc2.batchnorm.weight
+    key).  ``fc2_relu=True`` reproduces the blueprint's constructor defaults (:219-224)."""
+    inter = OrderedDict()
+    x = relu_bn_tdnn_layer(x, sd, "layer1", [-2, -1, 0, 1, 2])
+    inter["layer1"] = x
+    x1 = se_res2block(x, sd, "layer2", 2)
+    x2 = se_res2block(x + x1, sd, "layer3", 3)
+    x3 = se_res2block(x + x1 + x2, sd, "layer4", 4)
+    inter["layer2"], inter["layer3"], inter["layer4"] = x1, x2, x3
+    x = torch.cat([x1, x2, x3], dim=1)
+    x = relu_bn_tdnn_layer(x, sd, "mfa", [0])
+    inter["mfa"] = x
+    x = attentive_stats_pool(x, sd, "stats")
+    inter["stats"] = x
+    x = batchnorm_eval(x, sd, "bn_stats")
+    x = x.unsqueeze(2)
+    if extracted_embedding == "near_affine":
+        x = tdnn_affine(x, sd["fc2.affine.weight"], sd["fc2.affine.bias"], [0])
+    elif extracted_embedding == "near":
+        x = relu_bn_tdnn_layer(x, sd, "fc2", [0], relu=fc2_relu)
+    else:
+        raise TypeError("Expected far or near position, but got {}".format(extracted_embedding))
+    return (x, inter) if return_intermediates else x
+
+
+# --------------------------------------------------------------------------------------
+# Whole-utterance wrapper
+# --------------------------------------------------------------------------------------
+def extract_embedding(forward_fn, feats, max_chunk=10000):
+    """for_extract_embedding wrapper, pytorch/libs/nnet/framework.py:18-52.
+
+    feats: (T, F) float32 ndarray -> (1, F, T); num_split = ceil(T/maxChunk);
+    split_size = T // num_split; the last chunk takes the remainder; embedding =
+    sum(len_i * emb_i) / T; returns a 1-D CPU tensor."""
+    with torch.no_grad():
+        x = torch.tensor(feats).unsqueeze(0).transpose(1, 2)
+        num_frames = x.shape[2]
+        num_split = (num_frames + max_chunk - 1) // max_chunk
+        split_size = num_frames // num_split
+        offset = 0
+        stats = 0.0
+        for _ in range(num_split - 1):
+            stats = stats + split_size * forward_fn(x[:, :, offset:offset + split_size])
+            offset += split_size
+        last = forward_fn(x[:, :, offset:])
+        emb = (stats + (num_frames - offset) * last) / num_frames
+        return torch.squeeze(emb.transpose(1, 2))
+
+
+# --------------------------------------------------------------------------------------
+# Seeded synthetic checkpoints (shapes = the reference constructors'; make_golden.py
+# asserts key-for-key equality with the imported reference's state_dict()).
+# --------------------------------------------------------------------------------------
+def _affine_entries(prefix, cin, cout, context, key_style="tdnn"):
+    _, _, tot = context_span(context)
+    if key_style == "tdnn":
+        return [(prefix + ".affine.weight", (cout, cin, tot), ("w", cin * len(context))),
+                (prefix + ".affine.bias", (cout,), ("b", 0))]
+    return [(prefix + ".weight", (cout, cin, tot), ("w", cin)), (prefix + ".bias", (cout,), ("b", 0))]
+
+
+def _bn_entries(prefix, c, affine=True):
+    out = []
+    if affine:
+        out += [(prefix + ".weight", (c,), ("gamma", 0)), (prefix + ".bias", (c,), ("beta", 0))]
+    out += [(prefix + ".running_mean", (c,), ("rmean", 0)), (prefix + ".running_var", (c,), ("rvar", 0)),
+            (prefix + ".num_batches_tracked", (), ("nbt", 0))]
+    return out
+
+
+def xvector_spec(inputs_dim):
+    """Keys/shapes of Xvector(inputs_dim, N, training=False).state_dict() (xvector.py:26-33)."""
+    spec = []
+    dims = [(inputs_dim, 512), (512, 512), (512, 512), (512, 512), (512, 1500)]
+    for (name, ctx), (cin, cout) in zip(XVECTOR_LAYERS, dims):
+        spec += _affine_entries(name, cin, cout, ctx) + _bn_entries(name + ".batchnorm", cout)
+    spec += _affine_entries("tdnn6", 3000, 512, [0]) + _bn_entries("tdnn6.batchnorm", 512)
+    spec += _affine_entries("tdnn7", 512, 512, [0]) + _bn_entries("tdnn7.batchnorm", 512)
+    return spec
+
+
+def ecapa_spec(inputs_dim, channels=1024, embd_dim=192, mfa_conv=1536, hidden=128,
+               fc2_bn_affine=False, scale=8, se_bottleneck=128):
+    """Keys/shapes of ECAPA_TDNN(inputs_dim, N, training=False, <canonical params>).state_dict()
+    (ecapa_tdnn_xvector.py:259-332)."""
+    spec = _affine_entries("layer1", inputs_dim, channels, [-2, -1, 0, 1, 2]) + \
+        _bn_entries("layer1.batchnorm", channels)
+    width = channels // scale
+    for li, d in (("layer2", 2), ("layer3", 3), ("layer4", 4)):
+        spec += _affine_entries(li + ".conv_relu_bn1", channels, channels, [0]) + \
+            _bn_entries(li + ".conv_relu_bn1.batchnorm", channels)
+        for i in range(scale - 1):
+            p = "{}.res2net_block.blocks.{}".format(li, i)
+            spec += _affine_entries(p, width, width, [-d, 0, d]) + _bn_entries(p + ".batchnorm", width)
+        spec += _affine_entries(li + ".conv_relu_bn2", channels, channels, [0]) + \
+            _bn_entries(li + ".conv_relu_bn2.batchnorm", channels)
+        spec += _affine_entries(li + ".se.se.1", channels, se_bottleneck, [0], "conv") + \
+            _affine_entries(li + ".se.se.3", se_bottleneck, channels, [0], "conv")
+    spec += _affine_entries("mfa", 3 * channels, mfa_conv, [0]) + _bn_entries("mfa.batchnorm", mfa_conv)
+    spec += _affine_entries("stats.attention.0", 3 * mfa_conv, hidden, [0], "conv") + \
+        _bn_entries("stats.attention.2", hidden) + \
+        _affine_entries("stats.attention.4", hidden, mfa_conv, [0], "conv")
+    spec += _bn_entries("bn_stats", 2 * mfa_conv)
+    spec += _affine_entries("fc2", 2 * mfa_conv, embd_dim, [0]) + \
+        _bn_entries("fc2.batchnorm", embd_dim, affine=fc2_bn_affine)
+    return spec
+
+
+def make_state_dict(spec, seed):
+    """Seeded synthetic checkpoint: He-scaled weights on *all* stored taps (masked taps get
+    garbage on purpose), randomised BN statistics so that a folded or
+    mis-ordered BN/ReLU epilogue cannot hide."""
+    rng = np.random.RandomState(seed)
+    sd = OrderedDict()
+    for key, shape, (kind, fan_in) in spec:
+        if kind == "w":
+            v = rng.standard_normal(shape).astype(np.float32) * np.float32(math.sqrt(2.0 / fan_in))
+        elif kind == "b":
+            v = (0.1 * rng.standard_normal(shape)).astype(np.float32)
+        elif kind == "gamma":
+            v = rng.uniform(0.5, 1.5, shape).astype(np.float32)
+        elif kind == "beta":
+            v = (0.1 * rng.standard_normal(shape)).astype(np.float32)
+        elif kind == "rmean":
+            v = rng.uniform(0.1, 0.6, shape).astype(np.float32)
+        elif kind == "rvar":
+            v = rng.uniform(0.5, 1.5, shape).astype(np.float32)
+        elif kind == "nbt":
+            sd[key] = torch.tensor(1000, dtype=torch.long)
+            continue
+        else:
+            raise ValueError(kind)
+        sd[key] = torch.from_numpy(v)
+    return sd
+
+
+def synthetic_feats(num_utts, num_frames, feat_dim, seed):
+    """N(0,1) frames, (num_utts, T, F) float32 (CMN-like zero mean)."""
+    rng = np.random.RandomState(seed)
+    return rng.standard_normal((num_utts, num_frames, feat_dim)).astype(np.float32)

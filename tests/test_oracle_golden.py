@@ -1,0 +1,130 @@
+"""Pin the CPU oracle against fixtures produced by the imported reference
+(tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nnet as onn
+from oracle import scoring as osc
+
+RTOL = 2e-5  # oracle and reference run the same ATen ops; only thread/blocking order differs
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+@pytest.mark.parametrize("dim,seed", [(23, 101), (80, 102)])
+def test_xvector_embeddings(golden, dim, seed):
+    g = golden("xvector")
+    sd = onn.make_state_dict(onn.xvector_spec(dim), seed)
+    feats = onn.synthetic_feats(4, 200, dim, seed + 1000)
+    for pos in ("far", "near"):
+        emb = np.stack([onn.extract_embedding(lambda x: onn.xvector_forward(sd, x, pos), feats[i]).numpy()
+                        for i in range(4)])
+        assert emb.shape == (4, 512)
+        assert rel(emb, g["xv{}_{}_emb".format(dim, pos)]) < RTOL
+
+
+@pytest.mark.parametrize("dim,seed", [(23, 101), (80, 102)])
+def test_xvector_layers_and_edges(golden, dim, seed):
+    g = golden("xvector")
+    sd = onn.make_state_dict(onn.xvector_spec(dim), seed)
+    x = torch.from_numpy(onn.synthetic_feats(2, 50, dim, seed + 2000)).transpose(1, 2)
+    with torch.no_grad():
+        _, inter = onn.xvector_forward(sd, x, "far", return_intermediates=True)
+    for name, v in inter.items():
+        ref = g["xv{}_inter_{}".format(dim, name)]
+        got = v.numpy() if v.shape[2] == 1 else v.numpy()[:, :8]
+        assert rel(got, ref) < RTOL, name
+        assert abs(np.abs(v.numpy()).mean() - g["xv{}_absmean_{}".format(dim, name)]) < 1e-4
+    for T in (1, 3, 7):
+        f = onn.synthetic_feats(1, T, dim, seed + 3000 + T)[0]
+        e = onn.extract_embedding(lambda x: onn.xvector_forward(sd, x, "far"), f).numpy()
+        assert rel(e, g["xv{}_far_T{}".format(dim, T)]) < RTOL
+
+
+def test_xvector_chunked(golden):
+    g = golden("xvector")
+    sd = onn.make_state_dict(onn.xvector_spec(23), 101)
+    f = onn.synthetic_feats(1, 10050, 23, 4242)[0]
+    e = onn.extract_embedding(lambda x: onn.xvector_forward(sd, x, "far"), f).numpy()
+    assert rel(e, g["xv23_far_T10050"]) < RTOL
+    # chunking changes the answer: a single pass must differ measurably
+    e1 = onn.extract_embedding(lambda x: onn.xvector_forward(sd, x, "far"), f, max_chunk=10 ** 9).numpy()
+    assert rel(e1, g["xv23_far_T10050"]) > 1e-6
+
+
+def test_ecapa(golden):
+    g = golden("ecapa")
+    sd = onn.make_state_dict(onn.ecapa_spec(80), 201)
+    feats = onn.synthetic_feats(2, 300, 80, 1201)
+    for pos in ("near", "near_affine"):
+        emb = np.stack([onn.extract_embedding(lambda x: onn.ecapa_forward(sd, x, pos), feats[i]).numpy()
+                        for i in range(2)])
+        assert rel(emb, g["ecapa80_{}_emb".format(pos)]) < RTOL
+    x = torch.from_numpy(onn.synthetic_feats(2, 60, 80, 2201)).transpose(1, 2)
+    with torch.no_grad():
+        _, inter = onn.ecapa_forward(sd, x, "near", return_intermediates=True)
+        h = inter["layer1"]
+        r1 = onn.relu_bn_tdnn_layer(h, sd, "layer2.conv_relu_bn1", [0])
+        r2 = onn.res2net_block(r1, sd, "layer2.res2net_block", 2)
+        r3 = onn.relu_bn_tdnn_layer(r2, sd, "layer2.conv_relu_bn2", [0])
+        r4 = onn.se_connect(r3, sd, "layer2.se")
+        inter.update(l2_bn1=r1, l2_res2=r2, l2_bn2=r3, l2_se=r4)
+        inter["stats"] = inter["stats"].unsqueeze(2)
+        inter["bn_stats"] = onn.batchnorm_eval(inter["stats"].squeeze(2), sd, "bn_stats").unsqueeze(2)
+    for name, v in inter.items():
+        ref = g["ecapa80_inter_" + name]
+        got = v.numpy() if v.shape[2] == 1 else v.numpy()[:, :8]
+        assert rel(got, ref) < RTOL, name
+    sd2 = onn.make_state_dict(onn.ecapa_spec(80, fc2_bn_affine=True), 202)
+    for T in (2, 40):
+        f = onn.synthetic_feats(1, T, 80, 3201 + T)[0]
+        e = onn.extract_embedding(lambda x: onn.ecapa_forward(sd2, x, "near", fc2_relu=True), f).numpy()
+        assert rel(e, g["ecapa80_default_T{}".format(T)]) < RTOL
+
+
+def test_plda(golden):
+    g = golden("scoring")
+    within = osc.plda_smooth_within(g["plda_within"])
+    G, L, c, k = osc.plda_calculate_var(g["plda_between"], within, g["plda_mean"])
+    assert rel(G, g["plda_gamma"]) < 1e-12 and rel(L, g["plda_lambda"]) < 1e-12 and rel(c, g["plda_c"]) < 1e-12
+    E, T = g["plda_E"], g["plda_T"]
+    S = osc.plda_score_matrix(E, T, G, L, c, k)
+    assert rel(S, g["plda_S"]) < 1e-12
+    assert abs(osc.plda_score_pair(E[3].reshape(-1, 1), T[4].reshape(-1, 1), G, L, c, k) - g["plda_S"][3, 4]) < 1e-10
+
+
+def _eer_scores(seed):
+    rng = np.random.RandomState(seed)
+    tar = rng.standard_normal(2000) + 2.0
+    non = rng.standard_normal(50000)
+    scores = np.concatenate([tar, non])
+    labels = np.concatenate([np.ones(2000, dtype=np.int64), np.zeros(50000, dtype=np.int64)])
+    perm = rng.permutation(scores.shape[0])
+    return scores[perm], labels[perm]
+
+
+def test_eer_definitions(golden):
+    g = golden("scoring")
+    scores, labels = _eer_scores(int(g["eer_scores_seed"]))
+    eb, tb = osc.eer_bosaris_like(scores, labels)
+    assert abs(eb - g["eer_bosaris"]) < 1e-12 and abs(tb - g["eer_bosaris_thr"]) < 1e-12
+    ed, td = osc.eer_det_interp(scores, labels)
+    assert abs(ed - g["eer_det"]) < 1e-12 and abs(td - g["eer_det_thr"]) < 1e-9
+    assert abs(osc.min_dcf(scores, labels, 0.01) - g["mindcf_det"]) < 1e-12
+    ek, _ = osc.eer_kaldi(scores, labels)  # unpinned definition: sanity only
+    assert abs(ek - eb) < 2e-3
+
+
+def test_length_norm_and_means():
+    emb, lab = osc.synthetic_speakers(7, 5, 16, 11)
+    n = osc.length_norm(emb)
+    assert np.allclose(np.linalg.norm(n, axis=1), 1.0, atol=1e-6)
+    m, cnt = osc.speaker_mean(emb, lab, 7)
+    assert np.all(cnt == 5) and np.allclose(m[2], emb[lab == 2].mean(0), atol=1e-6)
+    gm = osc.global_mean(emb)
+    assert np.allclose(osc.subtract_global_mean(emb, gm).mean(0), 0, atol=1e-6)
