@@ -1,0 +1,82 @@
+"""ctypes binding of libxvb200.so (C ABI: include/xvb200.h).  No fallback: if the shared library
+is missing or a call fails, an exception is raised."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libxvb200.so")
+
+RELU, BN = 1, 2
+MAX_TAPS = 16
+
+
+class XvbError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "asv_subtools_b200: native library {} not found -- build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (make -C asv_subtools_b200/csrc). "
+            "There is no Python/CPU fallback.".format(LIB_PATH))
+    return C.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+_p = C.c_void_p
+_i = C.c_int
+_i64 = C.c_int64
+_f = C.c_float
+_ip = C.POINTER(C.c_int)
+
+# name -> (restype, argtypes); every symbol declared in include/xvb200.h must appear here
+SIGNATURES = {
+    "xvb_version": (_i, []),
+    "xvb_last_error": (C.c_char_p, []),
+    "xvb_device_check": (_i, []),
+    "xvb_split_f32": (_i, [_p, _i64, _i, _i64, _p, _p, _i64, _p]),
+    "xvb_packed_weight_elems": (_i64, [_i, _i, _i]),
+    "xvb_pack_tdnn_weight": (_i, [_p, _i, _i, _i, _i, _ip, _i, _p, _p, _p]),
+    "xvb_tdnn_affine": (_i, [_p, _p, _i64, _p, _p, _p, _p, _p, _i, _ip, _i, _p, _p, _i64, _p, _i64, _i, _i, _i, _i, _p]),
+    "xvb_tdnn_affine_simt": (_i, [_p, _i64, _p, _i, _i, _p, _p, _p, _i, _ip, _i, _p, _i64, _i, _i, _i, _i, _p]),
+    "xvb_stats_pool": (_i, [_p, _i64, _i, _i, _i, _f, _p, _p, _p, _i64, _p]),
+    "xvb_center_length_norm": (_i, [_p, _p, _p, _i64, _i, _p]),
+    "xvb_column_mean": (_i, [_p, _i64, _i, _p, _p]),
+    "xvb_cosine_trials": (_i, [_p, _p, _i, _p, _p, _i64, _p, _p]),
+    "xvb_cosine_matrix": (_i, [_p, _i64, _p, _i64, _i, _p, _i64, _p]),
+    "xvb_plda_terms": (_i, [_p, _i64, _i, _p, _p, _p, _p]),
+    "xvb_plda_matrix": (_i, [_p, _i64, _p, _i64, _i, _p, _p, _p, _p, _i64, _p]),
+    "xvb_extractor_create": (_i, [C.POINTER(_p), _i]),
+    "xvb_extractor_add_frame_layer": (_i, [_p, _i, _ip, _i, _p, _p, _p, _p, _i]),
+    "xvb_extractor_add_segment_layer": (_i, [_p, _i, _p, _p, _p, _p, _i]),
+    "xvb_extractor_finalize": (_i, [_p, _f]),
+    "xvb_extractor_embed_dim": (_i, [_p]),
+    "xvb_extractor_extract": (_i, [_p, _p, _i, _i, _p, _p]),
+    "xvb_extractor_extract_host": (_i, [_p, _p, _i, _i, _p, _p]),
+    "xvb_extractor_set_profiling": (_i, [_p, _i]),
+    "xvb_extractor_kernel_times": (_i, [_p, C.POINTER(C.c_float), _i]),
+    "xvb_extractor_last_launches": (_i, [_p]),
+    "xvb_extractor_debug_f32": (_p, [_p, _i]),
+    "xvb_extractor_destroy": (None, [_p]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)  # AttributeError here == the .so does not export what the header declares
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def last_error():
+    return lib.xvb_last_error().decode("utf-8", "replace")
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise XvbError("{} failed (rc={}): {}".format(what or "libxvb200 call", rc, last_error()))
+
+
+def int_array(values):
+    arr = (C.c_int * len(values))(*[int(v) for v in values])
+    return arr

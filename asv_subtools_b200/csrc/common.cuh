@@ -1,0 +1,66 @@
+// Shared host-side helpers: error reporting, launch counting, bf16 split helpers.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/xvb200.h"
+
+namespace xvb {
+
+// thread-local last error message (xvb_last_error)
+void set_error(const char* fmt, ...);
+// counts kernels launched by this library on this thread (xvb_extractor_last_launches)
+extern thread_local long g_launches;
+
+#define XVB_CHECK_ARG(cond, ...)        \
+  do {                                  \
+    if (!(cond)) {                      \
+      ::xvb::set_error(__VA_ARGS__);    \
+      return XVB_EINVAL;                \
+    }                                   \
+  } while (0)
+
+#define XVB_CUDA(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      ::xvb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return XVB_ECUDA;                                                                        \
+    }                                                                                          \
+  } while (0)
+
+#define XVB_LAUNCH_CHECK()                                                              \
+  do {                                                                                  \
+    ::xvb::g_launches++;                                                                \
+    cudaError_t _e = cudaGetLastError();                                                \
+    if (_e != cudaSuccess) {                                                            \
+      ::xvb::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return XVB_ECUDA;                                                                 \
+    }                                                                                   \
+  } while (0)
+
+int require_sm100();  // XVB_OK or XVB_ENODEVICE (cached per device)
+int sm_count();
+
+// fp32 -> (hi, lo) bf16 split: hi = rn(x), lo = rn(x - hi)
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// tdnn_gemm.cu: the tcgen05 layer with the optional per-frame bias used by PLDA scoring.
+int tdnn_affine_impl(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, const uint16_t* w_hi,
+                     const uint16_t* w_lo, const float* bias, const float* bn_scale, const float* bn_shift,
+                     const float* row_bias, int flags, const int* context_host, int ntaps, uint16_t* y_hi,
+                     uint16_t* y_lo, int64_t ldy, float* y_f32, int64_t ldyf, int B, int T, int Cin, int Cout,
+                     void* stream);
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+}  // namespace xvb

@@ -1,0 +1,314 @@
+// Whole-model extractor for the TDNN x-vector family: frame-level TDNN layers -> statistics
+// pooling -> segment-level affine layers.  Owns packed weights and workspace on the current device.
+// Stands in for Xvector.extract_embedding (pytorch/model/xvector.py:77-98) on a whole batch of
+// equal-length utterances and for the "load weights, run extraction without Python" role of the
+// reference's C++ runtime (runtime/bin/extractor_main.cc, runtime/speaker/torch_asv_model.cc).
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace xvb {
+
+struct Layer {
+  int Cin = 0, Cout = 0, ntaps = 0, flags = 0;
+  int ctx[XVB_MAX_TAPS] = {0};
+  uint16_t* w_hi = nullptr;
+  uint16_t* w_lo = nullptr;
+  float* bias = nullptr;
+  float* scale = nullptr;
+  float* shift = nullptr;
+};
+
+template <typename T>
+static int dev_alloc(T** p, size_t n) {
+  XVB_CUDA(cudaMalloc((void**)p, n * sizeof(T)));
+  return XVB_OK;
+}
+
+}  // namespace xvb
+
+using namespace xvb;
+
+struct xvb_extractor {
+  int feat_dim = 0, ldf = 0;
+  bool finalized = false;
+  float pooling_eps = 1e-10f;
+  std::vector<Layer> frame, segment;
+  // workspace
+  long long cap_frames = 0;
+  int cap_B = 0;
+  uint16_t* in_hi = nullptr; uint16_t* in_lo = nullptr;        // (B,T,ldf)
+  uint16_t* act_hi[2] = {nullptr, nullptr};                    // ping-pong (B,T,max_c)
+  uint16_t* act_lo[2] = {nullptr, nullptr};
+  float* last_f32 = nullptr;                                   // (B,T,C_last)
+  float* stats = nullptr;                                      // (B,2*C_last)
+  uint16_t* stats_hi = nullptr; uint16_t* stats_lo = nullptr;
+  uint16_t* seg_hi[2] = {nullptr, nullptr}; uint16_t* seg_lo[2] = {nullptr, nullptr};  // (B,max_seg_c)
+  float* h_feats = nullptr; float* h_emb = nullptr;            // device staging for *_host
+  size_t h_feats_cap = 0, h_emb_cap = 0;
+  int max_c = 0, max_seg_c = 0;
+  int last_launches = 0;
+  // optional per-kernel CUDA-event timing on the launching stream (bench.py roofline)
+  bool profiling = false;
+  std::vector<cudaEvent_t> events;
+  int events_used = 0;
+  cudaStream_t events_stream = nullptr;
+
+  int mark(cudaStream_t s) {
+    if (!profiling) return XVB_OK;
+    if (events_used == (int)events.size()) {
+      cudaEvent_t e;
+      XVB_CUDA(cudaEventCreate(&e));
+      events.push_back(e);
+    }
+    XVB_CUDA(cudaEventRecord(events[events_used++], s));
+    return XVB_OK;
+  }
+
+  void free_ws() {
+    cudaFree(in_hi); cudaFree(in_lo);
+    for (int i = 0; i < 2; ++i) { cudaFree(act_hi[i]); cudaFree(act_lo[i]); cudaFree(seg_hi[i]); cudaFree(seg_lo[i]); }
+    cudaFree(last_f32); cudaFree(stats); cudaFree(stats_hi); cudaFree(stats_lo);
+    in_hi = in_lo = nullptr; last_f32 = stats = nullptr; stats_hi = stats_lo = nullptr;
+    for (int i = 0; i < 2; ++i) act_hi[i] = act_lo[i] = seg_hi[i] = seg_lo[i] = nullptr;
+    cap_frames = 0; cap_B = 0;
+  }
+};
+
+static int upload_layer(Layer& L, int Cin, int Cout, const int* ctx, int ntaps, const float* w_host,
+                        const float* bias_host, const float* scale_host, const float* shift_host, int flags) {
+  XVB_CHECK_ARG(ntaps >= 1 && ntaps <= XVB_MAX_TAPS && ctx && w_host, "add layer: bad taps/weights");
+  XVB_CHECK_ARG(!(flags & XVB_BN) || (scale_host && shift_host), "add layer: XVB_BN without scale/shift");
+  for (int i = 1; i < ntaps; ++i) XVB_CHECK_ARG(ctx[i] > ctx[i - 1], "add layer: context must be strictly increasing");
+  // left/right/total context exactly as TdnnAffine.__init__ (components.py:50-53)
+  const int left = ctx[0] < 0 ? ctx[0] : 0;
+  const int right = ctx[ntaps - 1] > 0 ? ctx[ntaps - 1] : 0;
+  const int tot = right - left + 1;
+  L.Cin = Cin; L.Cout = Cout; L.ntaps = ntaps; L.flags = flags;
+  for (int i = 0; i < ntaps; ++i) L.ctx[i] = ctx[i];
+  const size_t wn = (size_t)Cout * Cin * tot;
+  float* w_dev = nullptr;
+  int rc = dev_alloc(&w_dev, wn);
+  if (rc) return rc;
+  XVB_CUDA(cudaMemcpy(w_dev, w_host, wn * sizeof(float), cudaMemcpyHostToDevice));
+  const size_t pn = (size_t)xvb_packed_weight_elems(Cout, Cin, ntaps);
+  if ((rc = dev_alloc(&L.w_hi, pn))) return rc;
+  if ((rc = dev_alloc(&L.w_lo, pn))) return rc;
+  rc = xvb_pack_tdnn_weight(w_dev, Cout, Cin, tot, left, ctx, ntaps, L.w_hi, L.w_lo, nullptr);
+  if (rc) return rc;
+  XVB_CUDA(cudaDeviceSynchronize());
+  cudaFree(w_dev);
+  auto up = [&](float** d, const float* h) -> int {
+    if (!h) return XVB_OK;
+    int r = dev_alloc(d, (size_t)Cout);
+    if (r) return r;
+    XVB_CUDA(cudaMemcpy(*d, h, (size_t)Cout * sizeof(float), cudaMemcpyHostToDevice));
+    return XVB_OK;
+  };
+  if ((rc = up(&L.bias, bias_host))) return rc;
+  if (flags & XVB_BN) {
+    if ((rc = up(&L.scale, scale_host))) return rc;
+    if ((rc = up(&L.shift, shift_host))) return rc;
+  }
+  return XVB_OK;
+}
+
+extern "C" int xvb_extractor_create(xvb_extractor_t** out, int feat_dim) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  XVB_CHECK_ARG(out && feat_dim > 0, "xvb_extractor_create: bad arguments");
+  xvb_extractor* h = new xvb_extractor();
+  h->feat_dim = feat_dim;
+  h->ldf = (int)round_up(feat_dim, 8);
+  *out = h;
+  return XVB_OK;
+}
+
+extern "C" int xvb_extractor_add_frame_layer(xvb_extractor_t* h, int Cout, const int* context_host, int ntaps,
+                                             const float* w_host, const float* bias_host, const float* bn_scale_host,
+                                             const float* bn_shift_host, int flags) {
+  XVB_CHECK_ARG(h && !h->finalized, "xvb_extractor_add_frame_layer: null or finalized extractor");
+  XVB_CHECK_ARG(h->segment.empty(), "xvb_extractor_add_frame_layer: frame layers must precede segment layers");
+  const int Cin = h->frame.empty() ? h->feat_dim : h->frame.back().Cout;
+  Layer L;
+  int rc = upload_layer(L, Cin, Cout, context_host, ntaps, w_host, bias_host, bn_scale_host, bn_shift_host, flags);
+  if (rc) return rc;
+  h->frame.push_back(L);
+  return XVB_OK;
+}
+
+extern "C" int xvb_extractor_add_segment_layer(xvb_extractor_t* h, int Cout, const float* w_host, const float* bias_host,
+                                               const float* bn_scale_host, const float* bn_shift_host, int flags) {
+  XVB_CHECK_ARG(h && !h->finalized && !h->frame.empty(), "xvb_extractor_add_segment_layer: need frame layers first");
+  const int Cin = h->segment.empty() ? 2 * h->frame.back().Cout : h->segment.back().Cout;
+  const int ctx0 = 0;
+  Layer L;
+  int rc = upload_layer(L, Cin, Cout, &ctx0, 1, w_host, bias_host, bn_scale_host, bn_shift_host, flags);
+  if (rc) return rc;
+  h->segment.push_back(L);
+  return XVB_OK;
+}
+
+extern "C" int xvb_extractor_finalize(xvb_extractor_t* h, float pooling_eps) {
+  XVB_CHECK_ARG(h && !h->frame.empty() && !h->segment.empty(), "xvb_extractor_finalize: need >=1 frame and >=1 segment layer");
+  h->max_c = 0;
+  for (size_t i = 0; i + 1 < h->frame.size(); ++i) {
+    XVB_CHECK_ARG(h->frame[i].Cout % 8 == 0, "frame layer %d: Cout=%d must be a multiple of 8", (int)i, h->frame[i].Cout);
+    if (h->frame[i].Cout > h->max_c) h->max_c = h->frame[i].Cout;
+  }
+  XVB_CHECK_ARG(h->frame.back().Cout % 4 == 0, "last frame layer: Cout=%d must be a multiple of 4", h->frame.back().Cout);
+  h->max_seg_c = 0;
+  for (size_t i = 0; i + 1 < h->segment.size(); ++i) {
+    XVB_CHECK_ARG(h->segment[i].Cout % 8 == 0, "segment layer %d: Cout must be a multiple of 8", (int)i);
+    if (h->segment[i].Cout > h->max_seg_c) h->max_seg_c = h->segment[i].Cout;
+  }
+  XVB_CHECK_ARG(h->segment.back().Cout % 4 == 0, "last segment layer: Cout must be a multiple of 4");
+  h->pooling_eps = pooling_eps;
+  h->finalized = true;
+  return XVB_OK;
+}
+
+extern "C" int xvb_extractor_embed_dim(const xvb_extractor_t* h) {
+  return (h && !h->segment.empty()) ? h->segment.back().Cout : XVB_ESTATE;
+}
+
+static int reserve(xvb_extractor* h, int B, int T) {
+  const long long frames = (long long)B * T;
+  if (frames <= h->cap_frames && B <= h->cap_B) return XVB_OK;
+  const long long nf = frames > h->cap_frames ? frames : h->cap_frames;
+  const int nb = B > h->cap_B ? B : h->cap_B;
+  h->free_ws();
+  int rc;
+  if ((rc = dev_alloc(&h->in_hi, (size_t)nf * h->ldf))) return rc;
+  if ((rc = dev_alloc(&h->in_lo, (size_t)nf * h->ldf))) return rc;
+  if (h->max_c > 0)
+    for (int i = 0; i < 2; ++i) {
+      if ((rc = dev_alloc(&h->act_hi[i], (size_t)nf * h->max_c))) return rc;
+      if ((rc = dev_alloc(&h->act_lo[i], (size_t)nf * h->max_c))) return rc;
+    }
+  const int cl = h->frame.back().Cout;
+  if ((rc = dev_alloc(&h->last_f32, (size_t)nf * cl))) return rc;
+  if ((rc = dev_alloc(&h->stats, (size_t)nb * 2 * cl))) return rc;
+  if ((rc = dev_alloc(&h->stats_hi, (size_t)nb * 2 * cl))) return rc;
+  if ((rc = dev_alloc(&h->stats_lo, (size_t)nb * 2 * cl))) return rc;
+  if (h->max_seg_c > 0)
+    for (int i = 0; i < 2; ++i) {
+      if ((rc = dev_alloc(&h->seg_hi[i], (size_t)nb * h->max_seg_c))) return rc;
+      if ((rc = dev_alloc(&h->seg_lo[i], (size_t)nb * h->max_seg_c))) return rc;
+    }
+  h->cap_frames = nf;
+  h->cap_B = nb;
+  return XVB_OK;
+}
+
+extern "C" int xvb_extractor_extract(xvb_extractor_t* h, const float* feats, int B, int T, float* emb, void* stream) {
+  XVB_CHECK_ARG(h && h->finalized, "xvb_extractor_extract: extractor not finalized");
+  XVB_CHECK_ARG(feats && emb && B > 0 && T > 0, "xvb_extractor_extract: bad arguments");
+  int rc = reserve(h, B, T);
+  if (rc) return rc;
+  const long before = g_launches;
+  cudaStream_t cs = (cudaStream_t)stream;
+  h->events_used = 0;
+  h->events_stream = cs;
+  if ((rc = h->mark(cs))) return rc;
+  // 1. stage the frame matrix as split planes (framework.py:28-33 staging)
+  rc = xvb_split_f32(feats, (int64_t)B * T, h->feat_dim, h->feat_dim, h->in_hi, h->in_lo, h->ldf, stream);
+  if (rc) return rc;
+  if ((rc = h->mark(cs))) return rc;
+  // 2. frame-level TDNN stack (xvector.py:85-89)
+  const uint16_t* x_hi = h->in_hi;
+  const uint16_t* x_lo = h->in_lo;
+  int64_t ldx = h->ldf;
+  for (size_t i = 0; i < h->frame.size(); ++i) {
+    const Layer& L = h->frame[i];
+    const bool last = i + 1 == h->frame.size();
+    uint16_t* y_hi = last ? nullptr : h->act_hi[i & 1];
+    uint16_t* y_lo = last ? nullptr : h->act_lo[i & 1];
+    rc = xvb_tdnn_affine(x_hi, x_lo, ldx, L.w_hi, L.w_lo, L.bias, L.scale, L.shift, L.flags, L.ctx, L.ntaps, y_hi, y_lo,
+                         L.Cout, last ? h->last_f32 : nullptr, L.Cout, B, T, L.Cin, L.Cout, stream);
+    if (rc) return rc;
+    if ((rc = h->mark(cs))) return rc;
+    x_hi = y_hi; x_lo = y_lo; ldx = L.Cout;
+  }
+  // 3. statistics pooling (xvector.py:90, pooling.py:58-67)
+  const int cl = h->frame.back().Cout;
+  rc = xvb_stats_pool(h->last_f32, cl, B, T, cl, h->pooling_eps, h->stats, h->stats_hi, h->stats_lo, 2 * cl, stream);
+  if (rc) return rc;
+  if ((rc = h->mark(cs))) return rc;
+  // 4. segment-level layers (xvector.py:92-96)
+  x_hi = h->stats_hi; x_lo = h->stats_lo; ldx = 2 * cl;
+  for (size_t i = 0; i < h->segment.size(); ++i) {
+    const Layer& L = h->segment[i];
+    const bool last = i + 1 == h->segment.size();
+    uint16_t* y_hi = last ? nullptr : h->seg_hi[i & 1];
+    uint16_t* y_lo = last ? nullptr : h->seg_lo[i & 1];
+    rc = xvb_tdnn_affine(x_hi, x_lo, ldx, L.w_hi, L.w_lo, L.bias, L.scale, L.shift, L.flags, L.ctx, 1, y_hi, y_lo, L.Cout,
+                         last ? emb : nullptr, L.Cout, B, 1, L.Cin, L.Cout, stream);
+    if (rc) return rc;
+    if ((rc = h->mark(cs))) return rc;
+    x_hi = y_hi; x_lo = y_lo; ldx = L.Cout;
+  }
+  h->last_launches = (int)(g_launches - before);
+  return XVB_OK;
+}
+
+extern "C" int xvb_extractor_extract_host(xvb_extractor_t* h, const float* feats_host, int B, int T, float* emb_host,
+                                          void* stream) {
+  XVB_CHECK_ARG(h && h->finalized && feats_host && emb_host && B > 0 && T > 0, "xvb_extractor_extract_host: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t nf = (size_t)B * T * h->feat_dim, ne = (size_t)B * h->segment.back().Cout;
+  if (nf > h->h_feats_cap) {
+    cudaFree(h->h_feats);
+    int rc = dev_alloc(&h->h_feats, nf);
+    if (rc) return rc;
+    h->h_feats_cap = nf;
+  }
+  if (ne > h->h_emb_cap) {
+    cudaFree(h->h_emb);
+    int rc = dev_alloc(&h->h_emb, ne);
+    if (rc) return rc;
+    h->h_emb_cap = ne;
+  }
+  XVB_CUDA(cudaMemcpyAsync(h->h_feats, feats_host, nf * sizeof(float), cudaMemcpyHostToDevice, s));
+  int rc = xvb_extractor_extract(h, h->h_feats, B, T, h->h_emb, stream);
+  if (rc) return rc;
+  XVB_CUDA(cudaMemcpyAsync(emb_host, h->h_emb, ne * sizeof(float), cudaMemcpyDeviceToHost, s));
+  XVB_CUDA(cudaStreamSynchronize(s));
+  return XVB_OK;
+}
+
+extern "C" int xvb_extractor_set_profiling(xvb_extractor_t* h, int enable) {
+  XVB_CHECK_ARG(h, "xvb_extractor_set_profiling: null extractor");
+  h->profiling = enable != 0;
+  h->events_used = 0;
+  return XVB_OK;
+}
+
+extern "C" int xvb_extractor_kernel_times(xvb_extractor_t* h, float* ms_host, int max_n) {
+  XVB_CHECK_ARG(h && ms_host, "xvb_extractor_kernel_times: null argument");
+  if (h->events_used < 2) return 0;
+  XVB_CUDA(cudaEventSynchronize(h->events[h->events_used - 1]));
+  int n = h->events_used - 1;
+  if (n > max_n) n = max_n;
+  for (int i = 0; i < n; ++i) XVB_CUDA(cudaEventElapsedTime(&ms_host[i], h->events[i], h->events[i + 1]));
+  return n;
+}
+
+extern "C" int xvb_extractor_last_launches(const xvb_extractor_t* h) { return h ? h->last_launches : XVB_ESTATE; }
+
+extern "C" const float* xvb_extractor_debug_f32(const xvb_extractor_t* h, int which) {
+  if (!h) return nullptr;
+  return which < 0 ? h->stats : h->last_f32;
+}
+
+extern "C" void xvb_extractor_destroy(xvb_extractor_t* h) {
+  if (!h) return;
+  h->free_ws();
+  for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+  cudaFree(h->h_feats); cudaFree(h->h_emb);
+  for (auto* v : {&h->frame, &h->segment})
+    for (Layer& L : *v) { cudaFree(L.w_hi); cudaFree(L.w_lo); cudaFree(L.bias); cudaFree(L.scale); cudaFree(L.shift); }
+  delete h;
+}

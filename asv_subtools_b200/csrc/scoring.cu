@@ -1,0 +1,203 @@
+// Back-end scoring kernels: embedding pre-processing (score/process.sh `submean`/`norm`/`getmean`),
+// cosine (score/score.sh:82-97) and two-covariance PLDA (score/pyplda/gaussian-plda-scoring.py:23-50).
+// The score matrices are dense contractions and ride on the tcgen05 layer kernel of tdnn_gemm.cu
+// (enroll rows = "frames" with T=1, test rows = output channels); the per-row pieces are
+// bandwidth-bound warp kernels.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace xvb {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// one warp per row: y = (x - mean) / ||x - mean||
+__global__ void center_length_norm_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                          float* __restrict__ y, long long rows, int D) {
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + row * D;
+  float ss = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    const float v = xr[c] - (mean ? mean[c] : 0.f);
+    ss = fmaf(v, v, ss);
+  }
+  ss = warp_sum(ss);
+  const float inv = 1.0f / sqrtf(ss);
+  for (int c = lane; c < D; c += 32) y[row * D + c] = (xr[c] - (mean ? mean[c] : 0.f)) * inv;
+}
+
+// partial[g, c] = sum over rows r = g, g+G, ... of x[r, c]   (thread = column, coalesced)
+__global__ void column_partial_kernel(const float* __restrict__ x, long long rows, int D, double* __restrict__ partial) {
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    double s = 0.0;
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x) s += (double)x[r * D + c];
+    partial[(long long)blockIdx.x * D + c] = s;
+  }
+}
+__global__ void column_final_kernel(const double* __restrict__ partial, int G, long long rows, int D,
+                                    float* __restrict__ mean) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  double s = 0.0;
+  for (int g = 0; g < G; ++g) s += partial[(long long)g * D + c];
+  mean[c] = (float)(s / (double)rows);
+}
+
+// one warp per trial
+__global__ void cosine_trials_kernel(const float* __restrict__ e, const float* __restrict__ t, int D,
+                                     const int32_t* __restrict__ te, const int32_t* __restrict__ tt,
+                                     long long n, float* __restrict__ scores) {
+  const long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const float* a = e + (long long)te[i] * D;
+  const float* b = t + (long long)tt[i] * D;
+  float s = 0.f;
+  for (int c = lane; c < D; c += 32) s = fmaf(a[c], b[c], s);
+  s = warp_sum(s);
+  if (lane == 0) scores[i] = s;
+}
+
+// term[i] = <y_i, x_i> + <x_i, c>   (y = x G computed by the GEMM)
+__global__ void plda_rowterm_kernel(const float* __restrict__ x, const float* __restrict__ y, long long ldy,
+                                    const float* __restrict__ c, long long rows, int D, float* __restrict__ term) {
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float s = 0.f;
+  for (int k = lane; k < D; k += 32) {
+    const float xv = x[row * D + k];
+    s = fmaf(xv, y[row * ldy + k] + c[k], s);
+  }
+  s = warp_sum(s);
+  if (lane == 0) term[row] = s;
+}
+
+struct TempBuf {  // stream-ordered scratch
+  void* p = nullptr;
+  cudaStream_t s;
+  explicit TempBuf(cudaStream_t st) : s(st) {}
+  int alloc(size_t bytes) {
+    XVB_CUDA(cudaMallocAsync(&p, bytes, s));
+    return XVB_OK;
+  }
+  ~TempBuf() { if (p) cudaFreeAsync(p, s); }
+};
+
+// out (Ne, Nt) = A (Ne, D) . Bm (Nt, D)^T  [+ row_bias[i] + col_bias[j]] through the tcgen05 layer.
+static int matmul_nt(const float* A, int64_t Ne, const float* Bm, int64_t Nt, int D, const float* row_bias,
+                     const float* col_bias, float* out, int64_t ldo, uint16_t* out_hi, uint16_t* out_lo,
+                     int64_t ldplane, cudaStream_t s) {
+  const int64_t ldp = round_up(D, 16);
+  TempBuf ta(s), tb(s);
+  int rc = ta.alloc((size_t)Ne * ldp * 2 * 2);
+  if (rc) return rc;
+  rc = tb.alloc((size_t)Nt * ldp * 2 * 2);
+  if (rc) return rc;
+  uint16_t* a_hi = (uint16_t*)ta.p;
+  uint16_t* a_lo = a_hi + Ne * ldp;
+  uint16_t* b_hi = (uint16_t*)tb.p;
+  uint16_t* b_lo = b_hi + Nt * ldp;
+  rc = xvb_split_f32(A, Ne, D, D, a_hi, a_lo, ldp, s);
+  if (rc) return rc;
+  rc = xvb_split_f32(Bm, Nt, D, D, b_hi, b_lo, ldp, s);
+  if (rc) return rc;
+  const int ctx0 = 0;
+  return tdnn_affine_impl(a_hi, a_lo, ldp, b_hi, b_lo, col_bias, nullptr, nullptr, row_bias, 0, &ctx0, 1, out_hi,
+                          out_lo, ldplane, out, ldo, (int)Ne, 1, D, (int)Nt, s);
+}
+
+}  // namespace xvb
+
+using namespace xvb;
+
+extern "C" int xvb_center_length_norm(const float* x, const float* mean, float* y, int64_t rows, int D, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  XVB_CHECK_ARG(x && y && rows > 0 && D > 0, "xvb_center_length_norm: bad arguments");
+  const long long threads = rows * 32;
+  center_length_norm_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, mean, y, rows, D);
+  XVB_LAUNCH_CHECK();
+  return XVB_OK;
+}
+
+extern "C" int xvb_column_mean(const float* x, int64_t rows, int D, float* mean, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  XVB_CHECK_ARG(x && mean && rows > 0 && D > 0, "xvb_column_mean: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  int G = sm_count() * 4;
+  if (G > rows) G = (int)rows;
+  TempBuf t(s);
+  rc = t.alloc((size_t)G * D * sizeof(double));
+  if (rc) return rc;
+  column_partial_kernel<<<G, D < 512 ? ((D + 31) / 32) * 32 : 512, 0, s>>>(x, rows, D, (double*)t.p);
+  XVB_LAUNCH_CHECK();
+  column_final_kernel<<<(D + 127) / 128, 128, 0, s>>>((const double*)t.p, G, rows, D, mean);
+  XVB_LAUNCH_CHECK();
+  return XVB_OK;
+}
+
+extern "C" int xvb_cosine_trials(const float* enroll, const float* test, int D, const int32_t* trial_e,
+                                 const int32_t* trial_t, int64_t num_trials, float* scores, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  XVB_CHECK_ARG(enroll && test && trial_e && trial_t && scores && D > 0, "xvb_cosine_trials: bad arguments");
+  if (num_trials == 0) return XVB_OK;
+  const long long threads = num_trials * 32;
+  cosine_trials_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(enroll, test, D, trial_e,
+                                                                                          trial_t, num_trials, scores);
+  XVB_LAUNCH_CHECK();
+  return XVB_OK;
+}
+
+extern "C" int xvb_cosine_matrix(const float* enroll, int64_t Ne, const float* test, int64_t Nt, int D, float* S,
+                                 int64_t lds, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  XVB_CHECK_ARG(enroll && test && S && Ne > 0 && Nt > 0 && D > 0, "xvb_cosine_matrix: bad arguments");
+  XVB_CHECK_ARG(Nt % 4 == 0 && lds % 4 == 0 && lds >= Nt, "xvb_cosine_matrix: Nt and lds must be multiples of 4");
+  XVB_CHECK_ARG(Ne < (1ll << 31) && Nt < (1ll << 31), "xvb_cosine_matrix: too many rows for one call");
+  return matmul_nt(enroll, Ne, test, Nt, D, nullptr, nullptr, S, lds, nullptr, nullptr, 0, (cudaStream_t)stream);
+}
+
+extern "C" int xvb_plda_terms(const float* x, int64_t rows, int D, const float* gamma, const float* c, float* term,
+                              void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  XVB_CHECK_ARG(x && gamma && c && term && rows > 0 && D > 0 && D % 4 == 0, "xvb_plda_terms: bad arguments (D%%4==0)");
+  cudaStream_t s = (cudaStream_t)stream;
+  TempBuf y(s);
+  rc = y.alloc((size_t)rows * D * sizeof(float));
+  if (rc) return rc;
+  // y = x . Gamma^T; Gamma is symmetric (sum of inverses of symmetric matrices), so this is x Gamma.
+  rc = matmul_nt(x, rows, gamma, D, D, nullptr, nullptr, (float*)y.p, D, nullptr, nullptr, 0, s);
+  if (rc) return rc;
+  const long long threads = rows * 32;
+  plda_rowterm_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(x, (const float*)y.p, D, c, rows, D, term);
+  XVB_LAUNCH_CHECK();
+  return XVB_OK;
+}
+
+extern "C" int xvb_plda_matrix(const float* enroll, int64_t Ne, const float* test, int64_t Nt, int D, const float* L2,
+                               const float* row, const float* col, float* S, int64_t lds, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  XVB_CHECK_ARG(enroll && test && L2 && S && Ne > 0 && Nt > 0 && D > 0 && D % 4 == 0, "xvb_plda_matrix: bad arguments (D%%4==0)");
+  XVB_CHECK_ARG(Nt % 4 == 0 && lds % 4 == 0 && lds >= Nt, "xvb_plda_matrix: Nt and lds must be multiples of 4");
+  cudaStream_t s = (cudaStream_t)stream;
+  TempBuf el(s);
+  rc = el.alloc((size_t)Ne * D * sizeof(float));
+  if (rc) return rc;
+  // E' = E . L2   (L2 = Lambda + Lambda^T is symmetric, so E L2 = E L2^T)
+  rc = matmul_nt(enroll, Ne, L2, D, D, nullptr, nullptr, (float*)el.p, D, nullptr, nullptr, 0, s);
+  if (rc) return rc;
+  return matmul_nt((const float*)el.p, Ne, test, Nt, D, row, col, S, lds, nullptr, nullptr, 0, s);
+}

@@ -1,0 +1,76 @@
+"""Parameter containers mirroring pytorch/libs/nnet/components.py (TdnnAffine :20-165,
+ReluBatchNormTdnnLayer :434-461).  They hold parameters under the reference's state_dict keys;
+the forward arithmetic lives in csrc/tdnn_gemm.cu (tcgen05) and is driven by the owning model."""
+import numpy as np
+import torch
+
+
+class TdnnAffine(torch.nn.Module):
+    """y = splice(w * x, context) + b.  Same constructor contract as the reference
+    (components.py:30-97): `weight` is (output_dim, input_dim, tot_context) *including* the taps
+    that `context` skips; only stride=1, groups=1, pad=True, no weight/feature normalisation is
+    supported on the B200 path (the two target blueprints use nothing else)."""
+
+    def __init__(self, input_dim, output_dim, context=[0], bias=True, pad=True, stride=1, groups=1,
+                 norm_w=False, norm_f=False):
+        super().__init__()
+        for i in range(len(context) - 1):
+            if context[i] >= context[i + 1]:
+                raise ValueError("Context tuple {} is invalid, such as the order.".format(context))
+        if stride != 1 or groups != 1 or not pad or norm_w or norm_f:
+            raise NotImplementedError("B200 TdnnAffine supports stride=1, groups=1, pad=True, norm_w/f=False only")
+        self.input_dim, self.output_dim, self.context = input_dim, output_dim, list(context)
+        self.bool_bias = bias
+        self.left_context = context[0] if context[0] < 0 else 0
+        self.right_context = context[-1] if context[-1] > 0 else 0
+        self.tot_context = self.right_context - self.left_context + 1
+        self.weight = torch.nn.Parameter(torch.empty(output_dim, input_dim, self.tot_context))
+        self.bias = torch.nn.Parameter(torch.empty(output_dim)) if bias else None
+        torch.nn.init.normal_(self.weight, 0.0, 0.01)  # components.py:99-104
+        if self.bias is not None:
+            torch.nn.init.constant_(self.bias, 0.0)
+
+    def extra_repr(self):
+        return "{}, {}, context={}, bias={}".format(self.input_dim, self.output_dim, self.context, self.bool_bias)
+
+
+class ReluBatchNormTdnnLayer(torch.nn.Module):
+    """affine -> ReLU -> BatchNorm1d (eval), the reference's default "relu-bn" order
+    (components.py:347-431).  Options accepted like the reference's **options; only the ones the
+    extraction path depends on are interpreted: nonlinearity ('relu' or ''), bn, bn_params.affine."""
+
+    def __init__(self, input_dim, output_dim, context=[0], affine_type="tdnn", **options):
+        super().__init__()
+        if affine_type != "tdnn":
+            raise NotImplementedError("only affine_type='tdnn' is supported")
+        if options.get("bn-relu", False) or options.get("ln_replace", False):
+            raise NotImplementedError("bn-relu / LayerNorm variants are not on the B200 path")
+        nonlin = options.get("nonlinearity", "relu")
+        if nonlin not in ("relu", "", None, False):
+            raise NotImplementedError("nonlinearity {!r} is not on the B200 path".format(nonlin))
+        self.relu = nonlin == "relu"
+        self.affine = TdnnAffine(input_dim, output_dim, context=context, bias=options.get("bias", True))
+        self.batchnorm = None
+        if options.get("bn", True):
+            bn_params = {"momentum": 0.1, "affine": True, "track_running_stats": True}
+            bn_params.update(options.get("bn_params", {}))
+            self.batchnorm = torch.nn.BatchNorm1d(output_dim, **bn_params)
+
+    def folded_bn(self):
+        """eval-mode BatchNorm as (scale, shift) float32 arrays: y = x*scale + shift with
+        scale = gamma / sqrt(running_var + eps), shift = beta - running_mean*scale."""
+        return fold_batchnorm(self.batchnorm)
+
+
+def fold_batchnorm(bn):
+    if bn is None:
+        return None, None
+    var = bn.running_var.detach().double().cpu().numpy()
+    mean = bn.running_mean.detach().double().cpu().numpy()
+    scale = 1.0 / np.sqrt(var + bn.eps)
+    if bn.weight is not None:
+        scale = scale * bn.weight.detach().double().cpu().numpy()
+    shift = -mean * scale
+    if bn.bias is not None:
+        shift = shift + bn.bias.detach().double().cpu().numpy()
+    return scale.astype(np.float32), shift.astype(np.float32)

@@ -1,0 +1,127 @@
+"""`TopVirtualNnet` plugin base + whole-utterance wrapper, mirroring
+pytorch/libs/nnet/framework.py (for_extract_embedding :12-55, TopVirtualNnet :61-186).
+
+Contract kept: `Cls(inputs_dim, num_targets, **params)` with `init()`,
+`load_state_dict(strict=False)` on the reference's keys, `.cuda()/.cpu()/.eval()`,
+`extract_embedding(feats[T,F] float32 ndarray) -> 1-D CPU float32 tensor`, the `maxChunk`
+splitting rule.  What is new: `extract_embedding_batch()` for equal-length utterances."""
+import numpy as np
+import torch
+
+
+def for_extract_embedding(maxChunk=10000, isMatrix=True):
+    """Decorator with the reference's semantics (framework.py:18-52).  The wrapped function
+    receives a channel-contiguous CUDA tensor (1, frames, feat_dim) and returns (1, D)."""
+
+    def wrapper(function):
+        def _wrapper(self, input):
+            train_status = self.training
+            self.eval()
+            with torch.no_grad():
+                x = torch.as_tensor(np.asarray(input) if not isinstance(input, torch.Tensor) else input)
+                if not isMatrix:
+                    # reference layout (1, F, T) -> (T, F)
+                    x = x[0].transpose(0, 1)
+                if x.dtype != torch.float32:
+                    # the reference fails on float64 features
+                    raise TypeError("extract_embedding expects float32 features, got {}".format(x.dtype))
+                x = x.to(self.device_for_extraction(), non_blocking=True).contiguous()
+                num_frames = x.shape[0]
+                num_split = (num_frames + maxChunk - 1) // maxChunk
+                split_size = num_frames // num_split
+                offset = 0
+                acc = None
+                for _ in range(num_split - 1):
+                    e = function(self, x[offset:offset + split_size].unsqueeze(0))
+                    acc = split_size * e if acc is None else acc + split_size * e
+                    offset += split_size
+                last = function(self, x[offset:].unsqueeze(0))
+                emb = (num_frames - offset) * last if acc is None else acc + (num_frames - offset) * last
+                emb = emb / num_frames
+                if train_status:
+                    self.train()
+                return torch.squeeze(emb).cpu()
+
+        return _wrapper
+
+    return wrapper
+
+
+class TopVirtualNnet(torch.nn.Module):
+    """Top-level plugin base.  Subclasses implement `init(...)` (build the parameter containers)
+    and `build_extractor()` (hand the current parameters to the native library)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        name = type(self).__name__
+        args_str = ",".join(repr(a) for a in args)
+        kwargs_str = ",".join("{}={!r}".format(k, v) for k, v in kwargs.items())
+        self.model_creation = "{}({})".format(name, ",".join(s for s in (args_str, kwargs_str) if s))
+        self.loss = None
+        self.use_step = False
+        self.transform_keys = []
+        self.rename_transform_keys = {}
+        self._extractor = None
+        self.init(*args, **kwargs)
+
+    def init(self, *args, **kwargs):
+        raise NotImplementedError
+
+    def get_model_creation(self):
+        return self.model_creation
+
+    # ---- native extractor lifecycle ------------------------------------------------------
+    def build_extractor(self):
+        raise NotImplementedError
+
+    def invalidate(self):
+        if self._extractor is not None:
+            self._extractor.close()
+        self._extractor = None
+
+    def extractor(self):
+        if self._extractor is None:
+            self._extractor = self.build_extractor()
+        return self._extractor
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
+        self.invalidate()
+        return out
+
+    def _apply(self, fn, *a, **kw):  # .cuda()/.cpu()/.to(): packed weights live on one device
+        out = super()._apply(fn, *a, **kw)
+        self.invalidate()
+        return out
+
+    def device_for_extraction(self):
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("asv_subtools_b200 has no CPU path: move the model to a B200 with .cuda() "
+                               "(extract_embeddings.py --use-gpu true)")
+        return dev
+
+    def load_transform_state_dict(self, state_dict):
+        keep = {self.rename_transform_keys.get(k, k): v for k, v in state_dict.items()
+                if k.split(".")[0] in self.transform_keys or k in self.transform_keys}
+        self.load_state_dict(keep, strict=False)
+        return self
+
+    # ---- extraction surface ----------------------------------------------------------------
+    @for_extract_embedding(maxChunk=10000, isMatrix=True)
+    def extract_embedding(self, inputs):
+        """inputs (1, frames, feat_dim) CUDA float32 -> (1, D)."""
+        return self.extractor().extract(inputs)
+
+    def extract_embedding_batch(self, feats):
+        """Equal-length utterances in one call: feats (B, T, F) float32 (CUDA tensor, CPU tensor or
+        ndarray; T <= maxChunk) -> (B, D) CUDA tensor.  Same arithmetic as B calls of
+        extract_embedding()."""
+        with torch.no_grad():
+            x = torch.as_tensor(feats)
+            if x.dtype != torch.float32:
+                raise TypeError("extract_embedding_batch expects float32 features")
+            if x.shape[1] > 10000:
+                raise ValueError("T > maxChunk: use extract_embedding() per utterance")
+            x = x.to(self.device_for_extraction(), non_blocking=True).contiguous()
+            return self.extractor().extract(x)

@@ -1,0 +1,278 @@
+"""Thin Python wrappers over the C ABI for torch CUDA tensors (device memory + streams are the
+only things torch is used for).  Frame matrices are channel-contiguous ``(B, T, C)``."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import BN, RELU, check, int_array, lib  # noqa: F401
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _req(t, dtype, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise TypeError("{} must be a contiguous CUDA tensor of dtype {}".format(name, dtype))
+    return t
+
+
+class SplitPlanes:
+    """fp32 tensor stored as two bf16 planes hi = bf16(x), lo = bf16(x - hi); last dim padded to `ld`."""
+
+    def __init__(self, hi, lo, channels):
+        self.hi, self.lo, self.channels = hi, lo, channels
+
+    @property
+    def ld(self):
+        return self.hi.shape[-1]
+
+    def float(self):
+        return (self.hi.float() + self.lo.float())[..., :self.channels]
+
+
+def split_f32(x, ld=None):
+    """(rows..., C) fp32 -> SplitPlanes with row pitch ld (default round_up(C, 8))."""
+    x = _req(x, torch.float32, "x")
+    c = x.shape[-1]
+    ld = ld or (c + 7) // 8 * 8
+    rows = x.numel() // c
+    hi = torch.empty(x.shape[:-1] + (ld,), dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty_like(hi)
+    check(lib.xvb_split_f32(_ptr(x), rows, c, c, _ptr(hi), _ptr(lo), ld, _stream()), "xvb_split_f32")
+    return SplitPlanes(hi, lo, c)
+
+
+def context_span(context):
+    """left/right/total context as TdnnAffine.__init__ (components.py:50-53)."""
+    left = context[0] if context[0] < 0 else 0
+    right = context[-1] if context[-1] > 0 else 0
+    return left, right, right - left + 1
+
+
+def pack_tdnn_weight(weight, context):
+    """Reference weight (Cout, Cin, tot_context) fp32 CUDA -> packed K-major SplitPlanes."""
+    weight = _req(weight, torch.float32, "weight")
+    cout, cin, tot = weight.shape
+    left, _, tot_expected = context_span(context)
+    if tot != tot_expected:
+        raise ValueError("weight kernel size {} does not match context {}".format(tot, context))
+    n = lib.xvb_packed_weight_elems(cout, cin, len(context))
+    hi = torch.empty(n, dtype=torch.bfloat16, device=weight.device)
+    lo = torch.empty_like(hi)
+    check(lib.xvb_pack_tdnn_weight(_ptr(weight), cout, cin, tot, left, int_array(context), len(context), _ptr(hi),
+                                   _ptr(lo), _stream()), "xvb_pack_tdnn_weight")
+    return SplitPlanes(hi.view(cout, -1), lo.view(cout, -1), cin)
+
+
+def tdnn_affine(x, w, cout, context, bias=None, bn_scale=None, bn_shift=None, relu=False, out_planes=True,
+                out_f32=False):
+    """x: SplitPlanes (B, T, ld).  Returns (SplitPlanes | None, fp32 tensor | None)."""
+    b, t, ldx = x.hi.shape
+    flags = (RELU if relu else 0) | (BN if bn_scale is not None else 0)
+    dev = x.hi.device
+    y = None
+    yf = None
+    if out_planes:
+        y = SplitPlanes(torch.empty(b, t, cout, dtype=torch.bfloat16, device=dev),
+                        torch.empty(b, t, cout, dtype=torch.bfloat16, device=dev), cout)
+    if out_f32:
+        yf = torch.empty(b, t, cout, dtype=torch.float32, device=dev)
+    check(lib.xvb_tdnn_affine(_ptr(x.hi), _ptr(x.lo), ldx, _ptr(w.hi), _ptr(w.lo), _ptr(bias), _ptr(bn_scale),
+                              _ptr(bn_shift), flags, int_array(context), len(context),
+                              _ptr(y.hi) if y else None, _ptr(y.lo) if y else None, cout, _ptr(yf), cout,
+                              b, t, x.channels, cout, _stream()), "xvb_tdnn_affine")
+    return y, yf
+
+
+def tdnn_affine_simt(x, weight, context, bias=None, bn_scale=None, bn_shift=None, relu=False):
+    """fp32 CUDA-core cross-check: x (B,T,Cin) fp32, weight (Cout,Cin,tot) as in the reference."""
+    x = _req(x, torch.float32, "x")
+    weight = _req(weight, torch.float32, "weight")
+    b, t, cin = x.shape
+    cout, _, tot = weight.shape
+    left, _, _ = context_span(context)
+    flags = (RELU if relu else 0) | (BN if bn_scale is not None else 0)
+    y = torch.empty(b, t, cout, dtype=torch.float32, device=x.device)
+    check(lib.xvb_tdnn_affine_simt(_ptr(x), cin, _ptr(weight), tot, left, _ptr(bias), _ptr(bn_scale), _ptr(bn_shift),
+                                   flags, int_array(context), len(context), _ptr(y), cout, b, t, cin, cout, _stream()),
+          "xvb_tdnn_affine_simt")
+    return y
+
+
+def stats_pool(x, eps=1e-10, planes=False):
+    """x (B,T,C) fp32 -> (B,2C) fp32 [, SplitPlanes]  (pooling.py:58-67)."""
+    x = _req(x, torch.float32, "x")
+    b, t, c = x.shape
+    out = torch.empty(b, 2 * c, dtype=torch.float32, device=x.device)
+    hi = lo = None
+    if planes:
+        hi = torch.empty(b, 2 * c, dtype=torch.bfloat16, device=x.device)
+        lo = torch.empty_like(hi)
+    check(lib.xvb_stats_pool(_ptr(x), c, b, t, c, eps, _ptr(out), _ptr(hi), _ptr(lo), 2 * c, _stream()),
+          "xvb_stats_pool")
+    return (out, SplitPlanes(hi, lo, 2 * c)) if planes else out
+
+
+# ------------------------------------------------------------------ scoring
+def center_length_norm(x, mean=None):
+    x = _req(x, torch.float32, "x")
+    y = torch.empty_like(x)
+    check(lib.xvb_center_length_norm(_ptr(x), _ptr(mean), _ptr(y), x.shape[0], x.shape[1], _stream()),
+          "xvb_center_length_norm")
+    return y
+
+
+def column_mean(x):
+    x = _req(x, torch.float32, "x")
+    m = torch.empty(x.shape[1], dtype=torch.float32, device=x.device)
+    check(lib.xvb_column_mean(_ptr(x), x.shape[0], x.shape[1], _ptr(m), _stream()), "xvb_column_mean")
+    return m
+
+
+def cosine_trials(enroll, test, trial_e, trial_t):
+    enroll = _req(enroll, torch.float32, "enroll")
+    test = _req(test, torch.float32, "test")
+    trial_e = _req(trial_e, torch.int32, "trial_e")
+    trial_t = _req(trial_t, torch.int32, "trial_t")
+    s = torch.empty(trial_e.shape[0], dtype=torch.float32, device=enroll.device)
+    check(lib.xvb_cosine_trials(_ptr(enroll), _ptr(test), enroll.shape[1], _ptr(trial_e), _ptr(trial_t),
+                                trial_e.shape[0], _ptr(s), _stream()), "xvb_cosine_trials")
+    return s
+
+
+def cosine_matrix(enroll, test):
+    enroll = _req(enroll, torch.float32, "enroll")
+    test = _req(test, torch.float32, "test")
+    s = torch.empty(enroll.shape[0], test.shape[0], dtype=torch.float32, device=enroll.device)
+    check(lib.xvb_cosine_matrix(_ptr(enroll), enroll.shape[0], _ptr(test), test.shape[0], enroll.shape[1], _ptr(s),
+                                test.shape[0], _stream()), "xvb_cosine_matrix")
+    return s
+
+
+def plda_terms(x, gamma, c):
+    x = _req(x, torch.float32, "x")
+    term = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    check(lib.xvb_plda_terms(_ptr(x), x.shape[0], x.shape[1], _ptr(_req(gamma, torch.float32, "gamma")),
+                             _ptr(_req(c, torch.float32, "c")), _ptr(term), _stream()), "xvb_plda_terms")
+    return term
+
+
+def plda_matrix(enroll, test, l2, row, col):
+    enroll = _req(enroll, torch.float32, "enroll")
+    test = _req(test, torch.float32, "test")
+    s = torch.empty(enroll.shape[0], test.shape[0], dtype=torch.float32, device=enroll.device)
+    check(lib.xvb_plda_matrix(_ptr(enroll), enroll.shape[0], _ptr(test), test.shape[0], enroll.shape[1],
+                              _ptr(_req(l2, torch.float32, "l2")), _ptr(row), _ptr(col), _ptr(s), test.shape[0],
+                              _stream()), "xvb_plda_matrix")
+    return s
+
+
+# ------------------------------------------------------------------ whole-model extractor
+class Extractor:
+    """Owner of a native xvb_extractor_t (packed weights + workspace on the current device)."""
+
+    def __init__(self, feat_dim):
+        self._h = C.c_void_p()
+        check(lib.xvb_extractor_create(C.byref(self._h), int(feat_dim)), "xvb_extractor_create")
+        self.feat_dim = int(feat_dim)
+        self._keep = []
+
+    @staticmethod
+    def _np(a):
+        if a is None:
+            return None, None
+        a = np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+        return a, a.ctypes.data_as(C.c_void_p)
+
+    def add_frame_layer(self, weight, bias, context, bn_scale=None, bn_shift=None, relu=True):
+        w, wp = self._np(weight)
+        b, bp = self._np(bias)
+        s, sp = self._np(bn_scale)
+        t, tp = self._np(bn_shift)
+        flags = (RELU if relu else 0) | (BN if bn_scale is not None else 0)
+        check(lib.xvb_extractor_add_frame_layer(self._h, w.shape[0], int_array(context), len(context), wp, bp, sp, tp,
+                                                flags), "xvb_extractor_add_frame_layer")
+
+    def add_segment_layer(self, weight, bias, bn_scale=None, bn_shift=None, relu=False):
+        w, wp = self._np(weight)
+        b, bp = self._np(bias)
+        s, sp = self._np(bn_scale)
+        t, tp = self._np(bn_shift)
+        flags = (RELU if relu else 0) | (BN if bn_scale is not None else 0)
+        check(lib.xvb_extractor_add_segment_layer(self._h, w.shape[0], wp, bp, sp, tp, flags),
+              "xvb_extractor_add_segment_layer")
+
+    def finalize(self, pooling_eps=1e-10):
+        check(lib.xvb_extractor_finalize(self._h, pooling_eps), "xvb_extractor_finalize")
+        self.embed_dim = lib.xvb_extractor_embed_dim(self._h)
+
+    def extract(self, feats):
+        """feats (B,T,F) fp32 CUDA -> (B,D) fp32 CUDA, asynchronous on the current stream."""
+        feats = _req(feats, torch.float32, "feats")
+        b, t, f = feats.shape
+        if f != self.feat_dim:
+            raise ValueError("expected feature dim {}, got {}".format(self.feat_dim, f))
+        emb = torch.empty(b, self.embed_dim, dtype=torch.float32, device=feats.device)
+        check(lib.xvb_extractor_extract(self._h, _ptr(feats), b, t, _ptr(emb), _stream()), "xvb_extractor_extract")
+        return emb
+
+    def extract_host(self, feats_np):
+        """feats (B,T,F) float32 host array -> (B,D) float32 host array (H2D + D2H inside the call)."""
+        feats_np = np.ascontiguousarray(feats_np, dtype=np.float32)
+        b, t, f = feats_np.shape
+        if f != self.feat_dim:
+            raise ValueError("expected feature dim {}, got {}".format(self.feat_dim, f))
+        emb = np.empty((b, self.embed_dim), dtype=np.float32)
+        check(lib.xvb_extractor_extract_host(self._h, feats_np.ctypes.data_as(C.c_void_p), b, t,
+                                             emb.ctypes.data_as(C.c_void_p), _stream()), "xvb_extractor_extract_host")
+        return emb
+
+    def extract_host_into(self, feats_ptr, b, t, emb_ptr):
+        check(lib.xvb_extractor_extract_host(self._h, C.c_void_p(feats_ptr), b, t, C.c_void_p(emb_ptr), _stream()),
+              "xvb_extractor_extract_host")
+
+    def set_profiling(self, enable):
+        check(lib.xvb_extractor_set_profiling(self._h, 1 if enable else 0), "xvb_extractor_set_profiling")
+
+    def kernel_times_ms(self):
+        """Durations (ms) of the kernels of the last extract call, launch order (needs set_profiling)."""
+        buf = (C.c_float * 64)()
+        n = lib.xvb_extractor_kernel_times(self._h, buf, 64)
+        if n < 0:
+            check(n, "xvb_extractor_kernel_times")
+        return [float(buf[i]) for i in range(n)]
+
+    @property
+    def last_launches(self):
+        return lib.xvb_extractor_last_launches(self._h)
+
+    def debug_f32(self, which, shape):
+        """View of an internal fp32 buffer of the last call (which=-1: pooled stats, 0: last frame layer)."""
+        ptr = lib.xvb_extractor_debug_f32(self._h, which)
+        if not ptr:
+            raise _lib.XvbError("no debug buffer")
+
+        class _DevPtr:  # zero-copy view through the CUDA array interface
+            __cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False),
+                                        "version": 2}
+
+        torch.cuda.synchronize()
+        return torch.as_tensor(_DevPtr(), device="cuda").clone()
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib.xvb_extractor_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec of x-vector extraction (80-d fbank, 200-frame chunks, batch 256 per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one pass of the hot path (split -> tdnn1..5 -> stats pooling -> tdnn6.affine) over one
+batch of 256 x 200 x 80 synthetic frames per GPU (BASELINE.json configs[1]).  One process per GPU;
+under torchrun the ranks only share a barrier and a MAX-reduce of the device time (utterances shard
+with no data-path collective -> weak scaling).  Rank 0 prints ONE JSON line.
+
+  value     : whole-job frames/s with the inputs resident in HBM (CUDA events, max over ranks)
+  e2e       : same through the C-ABI host-buffer call (pinned host feats -> H2D -> extract -> D2H)
+  roofline  : the tcgen05 TDNN GEMM -- algorithmic FLOPs (5 630 976 FLOP/frame) / summed
+              per-launch CUDA-event durations, against the measured bf16 peak (MEASURED_PEAKS.json);
+              the kernel executes 3 bf16 MMAs per algorithmic MAC (bf16x3 split), reported too
+  cpu_baseline : the oracle port of the reference's CPU PyTorch path on this box's host cores
+
+`--impl reference` times that CPU port alone (the reference is Python/torch and cannot travel to
+the GPU box; the oracle restates it op for op, pinned by tests/golden).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B, T, F, D = 256, 200, 80, 512
+FLOP_PER_FRAME = 5630976          # 2*(2 807 808 MAC/frame) + 2*1 536 000/200
+GEMM_FLOP_PER_STEP = FLOP_PER_FRAME * B * T
+POOL_BYTES_PER_STEP = 1212000 * B  # 4*(C*T + 2C) B/utt, C=1500, T=200
+NUM_INPUT_BATCHES = 8             # rotate 8 x 16.4 MB inputs; activations per step ~1.1 GB >> 126 MB L2
+METRIC = "frames/sec x-vector extraction (80-d fbank)"
+UNIT = "frames/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"],
+                "bf16_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clock/throttle sampling during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.lines:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                mhz = float(parts[0])
+                smax = float(parts[1])
+            except ValueError:
+                continue
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                sm.append(mhz)
+                for n, v in zip(names, parts[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        if not sm:  # region shorter than the sampling period: take whatever we have
+            sm = [float(l.split(",")[0]) for _, l in self.lines if l and l.split(",")[0].strip().replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_checkpoint():
+    from oracle import nnet as onn  # synthetic seeded weights of the BASELINE architecture (no datasets here)
+    return onn.make_state_dict(onn.xvector_spec(F), 102)
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_port_frames_per_s(sd, budget_s, sample_utts, threads):
+    """Oracle port of the reference's CPU PyTorch path on a bounded sample of the same workload:
+    (i) batched forward (most favourable to the reference), (ii) the reference's literal
+    one-utterance-per-call extract_embedding loop."""
+    from oracle import nnet as onn
+    torch.set_num_threads(threads)
+    feats = onn.synthetic_feats(sample_utts, T, F, 1024)
+    x = torch.from_numpy(feats).transpose(1, 2).contiguous()
+    with torch.no_grad():
+        onn.xvector_forward(sd, x[:8], "far")  # warm-up
+        n, t0 = 0, time.perf_counter()
+        while True:
+            onn.xvector_forward(sd, x, "far")
+            n += 1
+            if time.perf_counter() - t0 > budget_s * 0.6:
+                break
+        batched = n * sample_utts * T / (time.perf_counter() - t0)
+        m, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < budget_s * 0.4:
+            onn.extract_embedding(lambda z: onn.xvector_forward(sd, z, "far"), feats[m % sample_utts])
+            m += 1
+        per_utt = m * T / (time.perf_counter() - t0)
+    return batched, per_utt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sd = make_checkpoint()
+    from oracle import nnet as onn
+    torch.set_num_threads(threads)
+    sample_utts = 64
+    x = torch.from_numpy(onn.synthetic_feats(sample_utts, T, F, 1024)).transpose(1, 2).contiguous()
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 3))):
+            onn.xvector_forward(sd, x, "far")
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            onn.xvector_forward(sd, x, "far")
+        dt = time.perf_counter() - t0
+    value = args.steps * sample_utts * T / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "x-vector TDNN, 80-d fbank, 200-frame chunks (BASELINE configs[1])",
+                   "sample": "{} utterances x {} frames per step, batched forward".format(sample_utts, T)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "{} steps x {} utts x {} frames, oracle port (torch CPU ops incl. masked taps) of "
+                                   "the reference forward, batched".format(args.steps, sample_utts, T)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_native(args, rank, world, local_rank):
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from asv_subtools_b200.model.xvector import Xvector
+    sd = make_checkpoint()
+    model = Xvector(F, 10, training=False, extracted_embedding="far")
+    model.load_state_dict(sd, strict=True)
+    model.cuda().eval()
+    ex = model.extractor()
+
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1024 + rank)  # the reference's own seed (runXvector.py:176)
+    batches = [torch.randn(B, T, F, device=dev, generator=gen) for _ in range(NUM_INPUT_BATCHES)]
+    host = [torch.empty(B, T, F, dtype=torch.float32).pin_memory() for _ in range(2)]
+    for h, d in zip(host, batches):
+        h.copy_(d.cpu())
+    host_out = torch.empty(B, D, dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---- device-resident throughput -----------------------------------------------------------
+    for i in range(args.warmup):
+        ex.extract(batches[i % NUM_INPUT_BATCHES])
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.time()
+    e0.record()
+    for i in range(args.steps):
+        out = ex.extract(batches[i % NUM_INPUT_BATCHES])
+    e1.record()
+    barrier()
+    wall1 = time.time()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = ex.last_launches * args.steps
+    assert torch.isfinite(out).all()
+
+    # ---- end to end through the host-buffer C-ABI call ----------------------------------------
+    for i in range(min(args.warmup, 3)):
+        ex.extract_host_into(host[i % 2].data_ptr(), B, T, host_out.data_ptr())
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        ex.extract_host_into(host[i % 2].data_ptr(), B, T, host_out.data_ptr())
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop(wall0, time.time()) if sampler else None
+
+    # ---- per-kernel CUDA-event times (roofline) -------------------------------------------------
+    ex.set_profiling(True)
+    per = []
+    for i in range(max(3, min(args.steps, 10))):
+        ex.extract(batches[i % NUM_INPUT_BATCHES])
+        per.append(ex.kernel_times_ms())
+    ex.set_profiling(False)
+    per = np.median(np.array(per), axis=0)  # [split, tdnn1..5, pool, tdnn6]
+    names = ["split"] + ["tdnn%d" % (i + 1) for i in range(5)] + ["stats_pool", "tdnn6.affine"]
+    gemm_ms = float(per[1:6].sum() + per[7])
+    pool_ms = float(per[6])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    frames = B * T * args.steps * world
+    value = frames / (ms * 1e-3)
+    achieved = GEMM_FLOP_PER_STEP / (gemm_ms * 1e-3) / 1e12
+    pool_gbs = POOL_BYTES_PER_STEP / (pool_ms * 1e-3) / 1e9
+    cpu_batched, cpu_per_utt = cpu_port_frames_per_s(sd, 16.0, 64, os.cpu_count() or 1)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (bf16x3 split operands on tcgen05, fp32 accumulate in TMEM)", "data": "synthetic",
+        "config": {"workload": "x-vector TDNN (pytorch/model/xvector.py), 80-d fbank, 200-frame chunks, "
+                               "batch 256 per GPU, extracted_embedding=far (BASELINE configs[1])",
+                   "batch_per_gpu": B, "frames_per_utt": T, "feat_dim": F, "parallelism": "utterance-sharded x%d" % world,
+                   "l2_policy": "inputs rotate over %d batches; ~1.1 GB of activations per step >> 126 MB L2" % NUM_INPUT_BATCHES,
+                   "weights": "seeded synthetic checkpoint of the reference architecture"},
+        "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": B * T * F * 4, "d2h_bytes_per_step": B * D * 4,
+                "api": "xvb_extractor_extract_host (pinned host feats in, host embeddings out)"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "tdnn_gemm_bf16x3_kernel (6 launches/step)",
+                     "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / pk["bf16_sustained"], "traffic": None,
+                     "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)",
+                     "algorithmic_flop_per_launch_avg": GEMM_FLOP_PER_STEP / 6,
+                     "executed_tflops": 3 * achieved, "executed_frac": 3 * achieved / pk["bf16_sustained"],
+                     "note": "3 bf16 MMAs per algorithmic MAC (hi*hi + lo*hi + hi*lo) to hold 1e-4 parity",
+                     "gemm_ms_per_step": gemm_ms},
+        "roofline_stats_pool": {"bound": "hbm", "kernel": "stats_pool_kernel", "achieved": pool_gbs,
+                                "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": pool_gbs / pk["hbm_gbs"],
+                                "traffic": None, "ms": pool_ms, "peak_source": pk["src"]},
+        "kernel_ms": {n: float(v) for n, v in zip(names, per)},
+        "cpu_baseline": {"value": cpu_batched, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                         "sample": "64 utts x 200 frames batched forward for ~10 s (most favourable to the reference); "
+                                   "the reference's literal batch-1 extract_embedding loop: %.0f frames/s" % cpu_per_utt,
+                         "per_utterance_value": cpu_per_utt},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no GPU visible -- the native arm has no CPU fallback")
+        run_native(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

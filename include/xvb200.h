@@ -1,0 +1,178 @@
+/*
+ * xvb200.h -- C ABI of libxvb200.so, the B200 (sm_100a) x-vector extraction / back-end scoring
+ * library that stands in for the hot path of Snowdar/asv-subtools.
+ *
+ * The reference has no native FFI for this path: its "kernels" are ATen calls issued from
+ * Python.  The entry points below are therefore what a ctypes stub in the
+ * reference tree would bind to replace those calls; each one cites the reference code whose
+ * arithmetic it takes over (paths relative to the reference root).  INTEGRATION.md shows the
+ * stub.  Conventions:
+ *
+ *   - plain C, no C++/torch types; every pointer is a raw device pointer unless the name ends
+ *     in _host; sizes are explicit; nothing is allocated behind the caller's back except by
+ *     the xvb_extractor_* object, which owns its packed weights and workspace;
+ *   - every function returns 0 on success or a negative XVB_E* code; xvb_last_error() gives
+ *     the message (thread-local);
+ *   - device functions are asynchronous on the caller-supplied cudaStream_t (passed as void*);
+ *   - frame matrices are channel-contiguous "(B, T, C)" (the reference is (B, C, T); Kaldi
+ *     features arrive as (T, F), so no transpose is needed on the way in);
+ *   - "split planes": an fp32 tensor stored as two bf16 tensors hi = bf16(x), lo = bf16(x-hi)
+ *     (same bytes as fp32).  The tcgen05 GEMM consumes them as x*w ~= hi*whi + lo*whi + hi*wlo
+ *     with fp32 accumulation in TMEM (|error| <= ~3 * 2^-18 |x w| per product), which is what
+ *     keeps the stack within the 1e-4 parity budget at bf16 tensor-core rate.
+ *
+ * There is no CPU fallback anywhere in this library: on a machine without an sm_100 device
+ * every compute entry point fails with XVB_ENODEVICE.
+ */
+#ifndef XVB200_H_
+#define XVB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XVB_VERSION 100
+
+/* error codes */
+#define XVB_OK 0
+#define XVB_EINVAL (-1)    /* bad argument (shape, alignment, null pointer) */
+#define XVB_ECUDA (-2)     /* a CUDA runtime/driver call failed; see xvb_last_error() */
+#define XVB_ENODEVICE (-3) /* no sm_100 GPU visible */
+#define XVB_ESTATE (-4)    /* object used in the wrong state (e.g. extract before finalize) */
+
+/* epilogue flags for xvb_tdnn_affine* (order is fixed: +bias -> ReLU -> BN affine) */
+#define XVB_RELU 1 /* components.py:410-416 (_relu_bn_forward): ReLU first ... */
+#define XVB_BN 2   /* ... then eval-mode BatchNorm folded to y*scale[c] + shift[c] */
+
+#define XVB_MAX_TAPS 16
+
+int xvb_version(void);
+const char* xvb_last_error(void);
+/* 0 if the current device is sm_100 (B200); XVB_ENODEVICE otherwise. */
+int xvb_device_check(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Frame-matrix staging
+ * ------------------------------------------------------------------------------------------- */
+
+/* fp32 (rows, C) with row pitch ldx  ->  split planes (rows, ldp); columns [C, ldp) are zeroed.
+ * Replaces the torch.tensor(input)/unsqueeze/transpose staging of for_extract_embedding,
+ * pytorch/libs/nnet/framework.py:28-33.  ldp % 8 == 0. */
+int xvb_split_f32(const float* x, int64_t rows, int C, int64_t ldx, uint16_t* hi, uint16_t* lo, int64_t ldp,
+                  void* stream);
+
+/* Pack a TdnnAffine weight.  w: (Cout, Cin, tot_context) fp32 exactly as stored in the
+ * reference state_dict, *including* the masked taps (pytorch/libs/nnet/components.py:62,
+ * :78-83); only the taps listed in context[] are kept (the weight*mask of :133-138).
+ * Output planes are K-major (Cout, ntaps*cin_p16) with cin_p16 = round_up(Cin,16) and
+ * K index = tap*cin_p16 + c.  Size in elements: xvb_packed_weight_elems(). */
+int64_t xvb_packed_weight_elems(int Cout, int Cin, int ntaps);
+int xvb_pack_tdnn_weight(const float* w, int Cout, int Cin, int tot_context, int left_context, const int* context_host,
+                         int ntaps, uint16_t* w_hi, uint16_t* w_lo, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * TDNN layer:  y[b,t,:] = epilogue( bias + sum_{c in context} W_c . x[b,t+c,:] ),  x = 0 outside
+ * [0,T) -- TdnnAffine.forward (components.py:107-149) fused with ReLU/BatchNorm of
+ * _BaseActivationBatchNorm (components.py:410-431).
+ *
+ * xvb_tdnn_affine: tcgen05 (bf16x3 split, fp32 accumulate in TMEM) GEMM with M = B*T frames,
+ * K = ntaps*Cin, N = Cout; the context splice is done by TMA (3-D tensor map (C,T,B), time
+ * coordinate offset per tap, out-of-bounds zero fill == F.pad).  Outputs: split planes
+ * (y_hi,y_lo; may be NULL) and/or fp32 (y_f32; may be NULL).  Requirements: ldx % 8 == 0,
+ * ldy % 8 == 0 and Cout % 8 == 0 when planes are written, ldyf % 4 == 0 and Cout % 4 == 0 when
+ * fp32 is written; pointers 16-byte aligned.
+ * ------------------------------------------------------------------------------------------- */
+int xvb_tdnn_affine(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, const uint16_t* w_hi,
+                    const uint16_t* w_lo, const float* bias, const float* bn_scale, const float* bn_shift, int flags,
+                    const int* context_host, int ntaps, uint16_t* y_hi, uint16_t* y_lo, int64_t ldy, float* y_f32,
+                    int64_t ldyf, int B, int T, int Cin, int Cout, void* stream);
+
+/* Same layer on CUDA cores in plain fp32 straight from the *unpacked* reference weight
+ * (Cout, Cin, tot_context).  Slow; exists so the tensor-core path and the weight packer can
+ * be cross-checked on the device and for shapes the tcgen05 path rejects. */
+int xvb_tdnn_affine_simt(const float* x, int64_t ldx, const float* w, int tot_context, int left_context,
+                         const float* bias, const float* bn_scale, const float* bn_shift, int flags,
+                         const int* context_host, int ntaps, float* y, int64_t ldy, int B, int T, int Cin, int Cout,
+                         void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Statistics pooling: StatisticsPooling.forward, no-lengths branch
+ * (pytorch/libs/nnet/pooling.py:58-67): out[b, 0:C] = mean_t x, out[b, C:2C] =
+ * sqrt(max(sum_t (x-mean)^2 / T, eps)).  x: (B, T, C) fp32 pitch ldx (ldx % 4 == 0, C % 4 == 0).
+ * One HBM read of x.  out: (B, 2C) fp32; out_hi/out_lo (optional, pitch ldo % 8 == 0) receive
+ * the same values as split planes for the following segment-level GEMM.
+ * ------------------------------------------------------------------------------------------- */
+int xvb_stats_pool(const float* x, int64_t ldx, int B, int T, int C, float eps, float* out, uint16_t* out_hi,
+                   uint16_t* out_lo, int64_t ldo, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Back-end scoring
+ * ------------------------------------------------------------------------------------------- */
+
+/* y = (x - mean) / ||x - mean||_2 per row.  mean may be NULL.  Covers `submean` + `norm` of
+ * score/process.sh:181-203 (ivector-subtract-global-mean, ivector-normalize-length
+ * --scaleup=false). */
+int xvb_center_length_norm(const float* x, const float* mean, float* y, int64_t rows, int D, void* stream);
+
+/* Column mean of (rows, D): `getmean`, score/process.sh:169-179 (ivector-mean). */
+int xvb_column_mean(const float* x, int64_t rows, int D, float* mean, void* stream);
+
+/* Per-trial dot products: score/score.sh:82-97 (ivector-compute-dot-products).
+ * scores[i] = <enroll[trial_e[i]], test[trial_t[i]]>. */
+int xvb_cosine_trials(const float* enroll, const float* test, int D, const int32_t* trial_e, const int32_t* trial_t,
+                      int64_t num_trials, float* scores, void* stream);
+
+/* All-pairs score matrix S (Ne, Nt) = enroll . test^T (BASELINE config 4). */
+int xvb_cosine_matrix(const float* enroll, int64_t Ne, const float* test, int64_t Nt, int D, float* S, int64_t lds,
+                      void* stream);
+
+/* Two-covariance PLDA, score/pyplda/gaussian-plda-scoring.py:23-29 in matrix form:
+ * S[i,j] = e_i^T L2 t_j + row[i] + col[j],  L2 = Lambda + Lambda^T (D,D) fp32,
+ * row = diag(E G E^T) + E c, col likewise (see xvb_plda_terms). */
+int xvb_plda_terms(const float* x, int64_t rows, int D, const float* gamma, const float* c, float* term, void* stream);
+int xvb_plda_matrix(const float* enroll, int64_t Ne, const float* test, int64_t Nt, int D, const float* L2,
+                    const float* row, const float* col, float* S, int64_t lds, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Whole-model extractor (x-vector TDNN family): owns packed weights + workspace on the current
+ * device; replaces Xvector.extract_embedding (pytorch/model/xvector.py:77-98) for a whole batch
+ * of equal-length utterances, and the model-loading role of runtime/ (torch_asv_model.cc:8-17).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct xvb_extractor xvb_extractor_t;
+
+int xvb_extractor_create(xvb_extractor_t** out, int feat_dim);
+/* Append a frame-level layer (before pooling) / a segment-level layer (after pooling).
+ * w_host: (Cout, Cin, tot_context) fp32 host; bias_host (Cout) or NULL; bn_scale_host/
+ * bn_shift_host (Cout) or NULL (folded eval BatchNorm); flags: XVB_RELU | XVB_BN. */
+int xvb_extractor_add_frame_layer(xvb_extractor_t* h, int Cout, const int* context_host, int ntaps,
+                                  const float* w_host, const float* bias_host, const float* bn_scale_host,
+                                  const float* bn_shift_host, int flags);
+int xvb_extractor_add_segment_layer(xvb_extractor_t* h, int Cout, const float* w_host, const float* bias_host,
+                                    const float* bn_scale_host, const float* bn_shift_host, int flags);
+int xvb_extractor_finalize(xvb_extractor_t* h, float pooling_eps);
+int xvb_extractor_embed_dim(const xvb_extractor_t* h);
+/* feats (B, T, feat_dim) fp32 on the device -> emb (B, embed_dim) fp32 on the device. */
+int xvb_extractor_extract(xvb_extractor_t* h, const float* feats, int B, int T, float* emb, void* stream);
+/* Same through host buffers (H2D of feats, D2H of emb inside; synchronises the stream). */
+int xvb_extractor_extract_host(xvb_extractor_t* h, const float* feats_host, int B, int T, float* emb_host,
+                               void* stream);
+/* Per-kernel timing with CUDA events recorded on the launching stream around every kernel of
+ * the next extract calls.  xvb_extractor_kernel_times() waits for the last call and returns the
+ * number of kernels n (<= max_n) and their durations in ms, in launch order: split, frame layers,
+ * stats pooling, segment layers. */
+int xvb_extractor_set_profiling(xvb_extractor_t* h, int enable);
+int xvb_extractor_kernel_times(xvb_extractor_t* h, float* ms_host, int max_n);
+/* Number of kernels the last extract call launched (bench.py's gpu_launches). */
+int xvb_extractor_last_launches(const xvb_extractor_t* h);
+/* Device pointer/pitch of a frame layer's fp32 output from the last call (debug/tests; only
+ * the last frame layer keeps fp32), or the pooled statistics (layer = -1). */
+const float* xvb_extractor_debug_f32(const xvb_extractor_t* h, int which);
+void xvb_extractor_destroy(xvb_extractor_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XVB200_H_ */

@@ -1,0 +1,214 @@
+"""Parity tests proper: every CUDA kernel, called through the C ABI, against the CPU oracle on the
+same seeded inputs.  Needs a B200 (`-m gpu`)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nnet as onn
+
+pytestmark = pytest.mark.gpu
+
+# bf16x3 split GEMM: per-product error <= ~3*2^-18; measured as max|d| / max|ref| per tensor.
+GEMM_TOL = 3e-5
+EMB_TOL = 1e-4  # north-star tolerance for embeddings (fp32, relative to the largest component)
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from asv_subtools_b200 import ops as _ops
+    assert torch.cuda.is_available()
+    return _ops
+
+
+def _layer_inputs(B, T, Cin, Cout, context, seed, bn=True):
+    rng = np.random.RandomState(seed)
+    left, right, tot = onn.context_span(context)
+    x = rng.standard_normal((B, T, Cin)).astype(np.float32)
+    w = (rng.standard_normal((Cout, Cin, tot)) * np.sqrt(2.0 / (Cin * len(context)))).astype(np.float32)
+    b = (0.1 * rng.standard_normal(Cout)).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, Cout).astype(np.float32) if bn else None
+    shift = (0.1 * rng.standard_normal(Cout)).astype(np.float32) if bn else None
+    return x, w, b, scale, shift
+
+
+def _oracle_layer(x, w, b, scale, shift, context, relu):
+    with torch.no_grad():
+        y = onn.tdnn_affine(torch.from_numpy(x).transpose(1, 2), torch.from_numpy(w), torch.from_numpy(b), context)
+        if relu:
+            y = torch.relu(y)
+        if scale is not None:
+            y = y * torch.from_numpy(scale)[None, :, None] + torch.from_numpy(shift)[None, :, None]
+    return y.transpose(1, 2).contiguous().numpy()
+
+
+def test_split_planes(ops):
+    x = torch.randn(37, 23, device="cuda") * 3
+    p = ops.split_f32(x)
+    assert p.hi.shape == (37, 24) and p.hi.dtype == torch.bfloat16
+    back = p.float()
+    assert rel(back.cpu().numpy(), x.cpu().numpy()) < 2.0 ** -16
+    assert torch.all(p.hi[:, 23] == 0) and torch.all(p.lo[:, 23] == 0)
+
+
+def test_pack_weight_drops_masked_taps(ops):
+    rng = np.random.RandomState(0)
+    w = rng.standard_normal((40, 24, 7)).astype(np.float32)  # context [-3,0,3]: taps 1,2,4,5 are garbage
+    p = ops.pack_tdnn_weight(torch.from_numpy(w).cuda(), [-3, 0, 3])
+    got = p.float().cpu().numpy().reshape(40, 3, 32)[:, :, :24]
+    want = np.stack([w[:, :, 0], w[:, :, 3], w[:, :, 6]], axis=1)
+    assert rel(got, want) < 2.0 ** -16
+    assert np.all(p.hi.float().cpu().numpy().reshape(40, 3, 32)[:, :, 24:] == 0)
+
+
+@pytest.mark.parametrize("B,T,Cin,Cout,context,relu", [
+    (2, 19, 24, 64, [-2, -1, 0, 1, 2], True),
+    (1, 5, 16, 32, [-3, 0, 3], False),
+])
+def test_simt_layer_vs_oracle(ops, B, T, Cin, Cout, context, relu):
+    x, w, b, scale, shift = _layer_inputs(B, T, Cin, Cout, context, 3)
+    y = ops.tdnn_affine_simt(torch.from_numpy(x).cuda(), torch.from_numpy(w).cuda(), context,
+                             torch.from_numpy(b).cuda(), torch.from_numpy(scale).cuda(),
+                             torch.from_numpy(shift).cuda(), relu=relu)
+    assert rel(y.cpu().numpy(), _oracle_layer(x, w, b, scale, shift, context, relu)) < 1e-5
+
+
+GEMM_CASES = [
+    # B, T, Cin, Cout, context, relu, f32-out   (M tiles / N tiles / K tails exercised)
+    (2, 50, 24, 512, [-2, -1, 0, 1, 2], True, False),   # tdnn1, 23->24-dim MFCC: partial K step
+    (3, 37, 80, 512, [-2, -1, 0, 1, 2], True, False),   # tdnn1, 80-dim fbank: 64+16 channel blocks, ragged T
+    (2, 40, 512, 512, [-2, 0, 2], True, False),         # tdnn2: masked taps dropped
+    (1, 7, 512, 512, [-3, 0, 3], True, False),          # tdnn3: T < context span, padding dominates
+    (5, 16, 512, 512, [0], True, False),                # tdnn4
+    (2, 33, 512, 1500, [0], True, True),                # tdnn5: N tail (1500 = 5*256+220), fp32 out
+    (9, 1, 3000, 512, [0], False, True),                # tdnn6.affine: segment level, M=B rows, narrow N tiles
+    (200, 8, 128, 128, [-2, 0, 2], True, False),        # Res2Net-shaped block, >148 tiles -> persistent loop
+    (16, 200, 512, 512, [-2, 0, 2], True, False),       # Tb=8 x Bb=16 tiling of the BASELINE shape
+]
+
+
+@pytest.mark.parametrize("B,T,Cin,Cout,context,relu,f32out", GEMM_CASES)
+def test_tdnn_gemm_vs_oracle(ops, B, T, Cin, Cout, context, relu, f32out):
+    x, w, b, scale, shift = _layer_inputs(B, T, Cin, Cout, context, 11)
+    xp = ops.split_f32(torch.from_numpy(x).cuda())
+    wp = ops.pack_tdnn_weight(torch.from_numpy(w).cuda(), context)
+    y, yf = ops.tdnn_affine(xp, wp, Cout, context, torch.from_numpy(b).cuda(), torch.from_numpy(scale).cuda(),
+                            torch.from_numpy(shift).cuda(), relu=relu, out_planes=not f32out, out_f32=f32out)
+    torch.cuda.synchronize()
+    got = (yf if f32out else y.float()).cpu().numpy()
+    ref = _oracle_layer(x, w, b, scale, shift, context, relu)
+    assert got.shape == ref.shape
+    assert np.all(np.isfinite(got))
+    assert rel(got, ref) < GEMM_TOL
+    # device-side cross-check against the fp32 CUDA-core layer reading the *unpacked* weight
+    simt = ops.tdnn_affine_simt(torch.from_numpy(x).cuda(), torch.from_numpy(w).cuda(), context,
+                                torch.from_numpy(b).cuda(), torch.from_numpy(scale).cuda(),
+                                torch.from_numpy(shift).cuda(), relu=relu).cpu().numpy()
+    assert rel(got, simt) < GEMM_TOL
+
+
+def test_tdnn_gemm_zero_padding_is_exact(ops):
+    """Linearity/padding property: frames outside [0,T) contribute exactly nothing, and utterances
+    never leak into each other: an all-zero utterance next to a non-zero one stays at relu(bias)."""
+    B, T, Cin, Cout, context = 4, 20, 64, 64, [-3, 0, 3]
+    x, w, b, _, _ = _layer_inputs(B, T, Cin, Cout, context, 5, bn=False)
+    x[1] = 0
+    xp = ops.split_f32(torch.from_numpy(x).cuda())
+    wp = ops.pack_tdnn_weight(torch.from_numpy(w).cuda(), context)
+    _, yf = ops.tdnn_affine(xp, wp, Cout, context, torch.from_numpy(b).cuda(), relu=True, out_planes=False, out_f32=True)
+    got = yf.cpu().numpy()
+    assert np.array_equal(got[1], np.broadcast_to(np.maximum(b, 0), (T, Cout)))
+
+
+@pytest.mark.parametrize("B,T,C", [(3, 200, 1500), (2, 1, 1500), (2, 7, 512), (1, 1000, 128), (4, 64, 4)])
+def test_stats_pool_vs_oracle(ops, B, T, C):
+    rng = np.random.RandomState(21)
+    x = (rng.standard_normal((B, T, C)) * rng.uniform(0.1, 3.0, (1, 1, C)) + rng.standard_normal((1, 1, C))).astype(np.float32)
+    out, planes = ops.stats_pool(torch.from_numpy(x).cuda(), planes=True)
+    with torch.no_grad():
+        ref = onn.statistics_pooling(torch.from_numpy(x).transpose(1, 2)).squeeze(2).numpy()
+    assert rel(out.cpu().numpy(), ref) < 2e-6
+    assert rel(planes.float().cpu().numpy(), ref) < 2.0 ** -16
+
+
+def test_stats_pool_constant_input_clamps_to_eps(ops):
+    x = torch.full((2, 50, 8), 3.25, device="cuda")
+    out = ops.stats_pool(x, eps=1e-10).cpu().numpy()
+    assert np.allclose(out[:, :8], 3.25) and np.allclose(out[:, 8:], 1e-5, rtol=1e-3)  # sqrt(clamp(0, 1e-10))
+
+
+# ---------------------------------------------------------------- whole model vs golden fixtures
+def _model(dim, seed, pos):
+    from asv_subtools_b200.model.xvector import Xvector
+    sd = onn.make_state_dict(onn.xvector_spec(dim), seed)
+    m = Xvector(dim, 10, training=False, extracted_embedding=pos)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda().eval(), sd
+
+
+@pytest.mark.parametrize("dim,seed", [(23, 101), (80, 102)])
+@pytest.mark.parametrize("pos", ["far", "near"])
+def test_xvector_embeddings_match_reference_golden(golden, dim, seed, pos):
+    g = golden("xvector")
+    m, _ = _model(dim, seed, pos)
+    feats = onn.synthetic_feats(4, 200, dim, seed + 1000)
+    ref = g["xv{}_{}_emb".format(dim, pos)]
+    single = np.stack([m.extract_embedding(feats[i]).numpy() for i in range(4)])
+    batch = m.extract_embedding_batch(feats).cpu().numpy()
+    assert single.shape == (4, 512) and single.dtype == np.float32
+    for i in range(4):
+        assert rel(single[i], ref[i]) < EMB_TOL
+        assert rel(batch[i], ref[i]) < EMB_TOL
+        cos = np.dot(batch[i], ref[i]) / (np.linalg.norm(batch[i]) * np.linalg.norm(ref[i]))
+        assert cos > 1 - 1e-6
+
+
+@pytest.mark.parametrize("dim,seed", [(23, 101), (80, 102)])
+def test_xvector_edge_lengths(golden, dim, seed):
+    g = golden("xvector")
+    m, _ = _model(dim, seed, "far")
+    for T in (1, 3, 7):
+        f = onn.synthetic_feats(1, T, dim, seed + 3000 + T)[0]
+        assert rel(m.extract_embedding(f).numpy(), g["xv{}_far_T{}".format(dim, T)]) < EMB_TOL
+
+
+def test_xvector_chunked_long_utterance(golden):
+    g = golden("xvector")
+    m, _ = _model(23, 101, "far")
+    f = onn.synthetic_feats(1, 10050, 23, 4242)[0]
+    assert rel(m.extract_embedding(f).numpy(), g["xv23_far_T10050"]) < EMB_TOL
+
+
+def test_xvector_intermediates(golden):
+    """Pooled statistics of the native extractor against the reference's own layer outputs."""
+    g = golden("xvector")
+    m, _ = _model(80, 102, "far")
+    feats = onn.synthetic_feats(2, 50, 80, 102 + 2000)
+    m.extract_embedding_batch(feats)
+    stats = m.extractor().debug_f32(-1, (2, 3000)).cpu().numpy()
+    assert rel(stats, g["xv80_inter_stats"][:, :, 0]) < EMB_TOL
+    last = m.extractor().debug_f32(0, (2, 50, 1500)).cpu().numpy()
+    assert rel(last.transpose(0, 2, 1)[:, :8], g["xv80_inter_tdnn5"]) < EMB_TOL
+
+
+def test_host_buffer_path_matches_device_path():
+    m, _ = _model(80, 102, "far")
+    feats = onn.synthetic_feats(8, 200, 80, 77)
+    a = m.extract_embedding_batch(feats).cpu().numpy()
+    b = m.extractor().extract_host(feats)
+    assert np.array_equal(a, b)
+
+
+def test_no_cpu_path():
+    from asv_subtools_b200.model.xvector import Xvector
+    m = Xvector(23, 10, training=False)
+    with pytest.raises(RuntimeError):
+        m.extract_embedding(np.zeros((10, 23), dtype=np.float32))
+    m.cuda()
+    with pytest.raises(TypeError):
+        m.extract_embedding(np.zeros((10, 23), dtype=np.float64))
