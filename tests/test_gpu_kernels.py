@@ -60,10 +60,11 @@ def test_pack_weight_drops_masked_taps(ops):
     rng = np.random.RandomState(0)
     w = rng.standard_normal((40, 24, 7)).astype(np.float32)  # context [-3,0,3]: taps 1,2,4,5 are garbage
     p = ops.pack_tdnn_weight(torch.from_numpy(w).cuda(), [-3, 0, 3])
-    got = p.float().cpu().numpy().reshape(40, 3, 32)[:, :, :24]
+    assert p.hi.shape == (40, 3 * 32)  # K index = tap*cin_p16 + c, cin_p16 = 32
+    full = (p.hi.float() + p.lo.float()).cpu().numpy().reshape(40, 3, 32)
     want = np.stack([w[:, :, 0], w[:, :, 3], w[:, :, 6]], axis=1)
-    assert rel(got, want) < 2.0 ** -16
-    assert np.all(p.hi.float().cpu().numpy().reshape(40, 3, 32)[:, :, 24:] == 0)
+    assert rel(full[:, :, :24], want) < 2.0 ** -16
+    assert np.all(full[:, :, 24:] == 0)
 
 
 @pytest.mark.parametrize("B,T,Cin,Cout,context,relu", [
