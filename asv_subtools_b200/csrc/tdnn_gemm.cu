@@ -21,6 +21,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -31,7 +33,10 @@ namespace xvb {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                      // bf16 elements = one 128-byte swizzle row
 constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB per plane per stage
-constexpr int kNumThreads = 192;
+constexpr int kNumEpiWarps = 8;                  // two groups of 4 warps, each group covers all 128 TMEM lanes
+constexpr int kNumThreads = 64 + kNumEpiWarps * 32;
+constexpr int kSlabBytes = 16384;                // TMA-store staging: bf16 hi(8K)+lo(8K) or one fp32 slab
+constexpr int kParamBytes = 3 * 256 * 4;         // bias/scale/shift for one 256-wide tile
 
 struct TdnnGemmParams {
   int B, T, Cin, Cout;
@@ -50,30 +55,42 @@ struct TdnnGemmParams {
   long long ldyf;
 };
 
-template <int BLOCK_N>
+// kCta = 1: one CTA per 128 x BLOCK_N tile.  kCta = 2: a CTA pair (cluster of 2, tcgen05
+// cta_group::2) per 256 x BLOCK_N tile -- each CTA stages its own 128 A rows and HALF of the
+// weight tile, so operand traffic per MMA flop drops by a third and a third stage fits.
+template <int BLOCK_N, int kCta>
 struct GemmCfg {
-  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kBRows = BLOCK_N / kCta;   // weight rows staged by one CTA
+  static constexpr int kBBytes = kBRows * kBlockK * 2;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 6 ? 6 : (200 * 1024) / kStageBytes;
+  static constexpr int kStages = (192 * 1024) / kStageBytes > 6 ? 6 : (192 * 1024) / kStageBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // two accumulator stages
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kSlabBytes + 2 * kParamBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
   static_assert(kStages >= 2, "need at least a double-buffered operand pipeline");
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int kCta>
 __global__ void __launch_bounds__(kNumThreads, 1)
 tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                         const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
-                        const __grid_constant__ TdnnGemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N>;
+                        const __grid_constant__ CUtensorMap map_y_hi, const __grid_constant__ CUtensorMap map_y_lo,
+                        const __grid_constant__ CUtensorMap map_y_f32, const __grid_constant__ TdnnGemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N, kCta>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kBBytes = Cfg::kBBytes;
   constexpr int kStageBytes = Cfg::kStageBytes;
+  const uint32_t cta_rank = kCta == 2 ? cluster_ctarank() : 0;  // rank 0 = leader (issues the MMAs)
+  const int tile_first = kCta == 2 ? blockIdx.x >> 1 : blockIdx.x;
+  const int tile_step = kCta == 2 ? gridDim.x >> 1 : gridDim.x;
 
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint8_t* slab_base = smem + kStages * kStageBytes;                     // 16 KB, 1024-aligned
+  float* param_base = reinterpret_cast<float*>(slab_base + kSlabBytes);  // 2 x [3][256] floats
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(slab_base + kSlabBytes + 2 * kParamBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
@@ -88,16 +105,17 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     tma_prefetch_desc(&map_w_hi);
     tma_prefetch_desc(&map_w_lo);
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&full_bar[i], kCta);   // leader's barrier: one producer arrival per CTA + all TMA bytes
+      mbar_init(&empty_bar[i], 1);     // per CTA, released by (multicast) tcgen05.commit
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 128);
+      mbar_init(&tmem_full_bar[i], 1);                          // per CTA, (multicast) commit
+      mbar_init(&tmem_empty_bar[i], kCta * kNumEpiWarps * 32);  // leader's: every epilogue thread of the pair
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<1>(tmem_ptr_smem, Cfg::kTmemCols);
+  if constexpr (kCta == 2) cluster_sync();  // peer barriers initialised before anyone signals them
+  if (warp == 1) tmem_alloc<kCta>(tmem_ptr_smem, Cfg::kTmemCols);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -110,21 +128,31 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.num_n_blk, n_blk = tile % p.num_n_blk;
-        const int b0 = (m_blk / p.num_t_blk) * p.Bb, t0 = (m_blk % p.num_t_blk) * p.Tb;
-        const int n0 = n_blk * BLOCK_N;
+      for (int tile = tile_first; tile < p.num_tiles; tile += tile_step) {
+        const int m_blk = (tile / p.num_n_blk) * kCta + (int)cta_rank, n_blk = tile % p.num_n_blk;
+        const int b0 = (m_blk / p.num_t_blk) * p.Bb, t0 = (m_blk % p.num_t_blk) * p.Tb;  // may be fully out of
+        const int n0 = n_blk * BLOCK_N + (int)cta_rank * Cfg::kBRows;                     // range: TMA zero-fills
         for (int tap = 0; tap < p.ntaps; ++tap) {
           const int tt = t0 + p.ctx[tap];
           for (int cb = 0; cb < p.num_cblk; ++cb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* s = smem + stage * kStageBytes;
-            mbar_expect_tx(&full_bar[stage], kStageBytes);
-            tma_load_3d(s, &map_a_hi, &full_bar[stage], cb * kBlockK, tt, b0);
-            tma_load_3d(s + kABytes, &map_a_lo, &full_bar[stage], cb * kBlockK, tt, b0);
             const int kw = tap * p.cin_p16 + cb * kBlockK;
-            tma_load_2d(s + 2 * kABytes, &map_w_hi, &full_bar[stage], kw, n0);
-            tma_load_2d(s + 2 * kABytes + kBBytes, &map_w_lo, &full_bar[stage], kw, n0);
+            if constexpr (kCta == 1) {
+              mbar_expect_tx(&full_bar[stage], kStageBytes);
+              tma_load_3d(s, &map_a_hi, &full_bar[stage], cb * kBlockK, tt, b0);
+              tma_load_3d(s + kABytes, &map_a_lo, &full_bar[stage], cb * kBlockK, tt, b0);
+              tma_load_2d(s + 2 * kABytes, &map_w_hi, &full_bar[stage], kw, n0);
+              tma_load_2d(s + 2 * kABytes + kBBytes, &map_w_lo, &full_bar[stage], kw, n0);
+            } else {
+              // both CTAs' bytes complete on the LEADER's barrier (peer-bit-masked address)
+              if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes);
+              else mbar_arrive_cluster(&full_bar[stage], 0);
+              tma_load_3d_2sm(s, &map_a_hi, &full_bar[stage], cb * kBlockK, tt, b0);
+              tma_load_3d_2sm(s + kABytes, &map_a_lo, &full_bar[stage], cb * kBlockK, tt, b0);
+              tma_load_2d_2sm(s + 2 * kABytes, &map_w_hi, &full_bar[stage], kw, n0);
+              tma_load_2d_2sm(s + 2 * kABytes + kBBytes, &map_w_lo, &full_bar[stage], kw, n0);
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -133,12 +161,13 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     __syncwarp();
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N);
+    // (leader CTA only: one thread drives the tensor cores of both SMs of a pair)
+    if (cta_rank == 0 && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM * kCta, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile_first; tile < p.num_tiles; tile += tile_step, ++it) {
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tcgen05_fence_after();
@@ -157,93 +186,150 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
           const uint64_t db_lo = make_kmajor_desc<128>(sa + 2 * kABytes + kBBytes);
           for (int s = 0; s < nsteps; ++s) {
             const uint64_t koff = (uint64_t)(s * 32 >> 4);  // 16 bf16 = 32 bytes along K inside the swizzle row
-            umma_bf16<1>(tmem_d, da_lo + koff, db_hi + koff, idesc, accumulate);
+            umma_bf16<kCta>(tmem_d, da_lo + koff, db_hi + koff, idesc, accumulate);
             accumulate = 1;
-            umma_bf16<1>(tmem_d, da_hi + koff, db_lo + koff, idesc, 1);
-            umma_bf16<1>(tmem_d, da_hi + koff, db_hi + koff, idesc, 1);
+            umma_bf16<kCta>(tmem_d, da_hi + koff, db_lo + koff, idesc, 1);
+            umma_bf16<kCta>(tmem_d, da_hi + koff, db_hi + koff, idesc, 1);
           }
-          umma_commit<1>(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          umma_commit<kCta>(&empty_bar[stage]);  // frees the smem slot (in both CTAs) once these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit<1>(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        umma_commit<kCta>(&tmem_full_bar[acc]);  // accumulator complete -> epilogue (of both CTAs)
       }
     }
     __syncwarp();
   } else {
     // ================================ epilogue ====================================
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    // 8 warps: warp -> TMEM lane quarter q = warp & 3 (hardware rule) and column half h = (warp-2)>>2;
+    // a thread owns one accumulator row and 16 of the 32 columns of every chunk.  Per chunk:
+    // tcgen05.ld (prefetched one chunk ahead) -> +bias -> ReLU -> BN (parameters broadcast from
+    // smem) -> split -> swizzled 16 KB smem slab -> one thread issues the TMA store, which clips
+    // ragged T / B / Cout for free and writes full lines.
+    const int ew = warp - 2;
+    const int half = ew >> 2;
+    const int q = warp & 3;
     const int row = q * 32 + lane;
+    const int etid = threadIdx.x - 64;  // 0..255
+    const bool leader = etid == 0;
     const bool relu = (p.flags & XVB_RELU) != 0;
     const bool bn = (p.flags & XVB_BN) != 0;
+    const bool planes = p.y_hi != nullptr;
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile_first; tile < p.num_tiles; tile += tile_step, ++it) {
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-      const int m_blk = tile / p.num_n_blk, n_blk = tile % p.num_n_blk;
-      const int b = (m_blk / p.num_t_blk) * p.Bb + row / p.Tb;
-      const int t = (m_blk % p.num_t_blk) * p.Tb + row % p.Tb;
+      const int m_blk = (tile / p.num_n_blk) * kCta + (int)cta_rank, n_blk = tile % p.num_n_blk;
+      const int b0 = (m_blk / p.num_t_blk) * p.Bb, t0 = (m_blk % p.num_t_blk) * p.Tb;
+      const int b = b0 + row / p.Tb, t = t0 + row % p.Tb;
       const bool valid = (b < p.B) && (t < p.T);
-      const long long frame = (long long)b * p.T + t;
       const int n0 = n_blk * BLOCK_N;
-      const float rbias = (p.row_bias && valid) ? __ldg(p.row_bias + frame) : 0.f;
+      const float rbias = (p.row_bias && valid) ? __ldg(p.row_bias + (long long)b * p.T + t) : 0.f;
+      // stage this tile's per-column parameters (double-buffered by accumulator stage; the
+      // barrier also orders reuse: nobody can be two tiles ahead of the slowest epilogue thread)
+      float* prm = param_base + acc * (3 * 256);
+      if (etid < BLOCK_N) {
+        const int c = n0 + etid;
+        const bool in = c < p.Cout;
+        prm[etid] = (in && p.bias) ? __ldg(p.bias + c) : 0.f;
+        prm[256 + etid] = (in && bn) ? __ldg(p.scale + c) : 1.f;
+        prm[512 + etid] = (in && bn) ? __ldg(p.shift + c) : 0.f;
+      }
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+      int nch = (p.Cout - n0 + 31) >> 5;
+      nch = nch > BLOCK_N / 32 ? BLOCK_N / 32 : nch;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
-#pragma unroll 1
-      for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
-        const int n = n0 + ch * 32;
-        if (n >= p.Cout) break;  // warp-uniform
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + ch * 32, v);
-        tmem_ld_wait();
-        float f[32];
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + half * 16;
+
+      auto process = [&](uint32_t (&v)[16], int ch) {
+        const int pc = ch * 32 + half * 16;
+        const float4* pb = reinterpret_cast<const float4*>(prm + pc);
+        const float4* ps = reinterpret_cast<const float4*>(prm + 256 + pc);
+        const float4* pt = reinterpret_cast<const float4*>(prm + 512 + pc);
+        float f[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int c = n + j;
-          float x = __uint_as_float(v[j]) + rbias;
-          if (c < p.Cout) {
-            if (p.bias) x += __ldg(p.bias + c);
-            if (relu) x = fmaxf(x, 0.f);
-            if (bn) x = fmaf(x, __ldg(p.scale + c), __ldg(p.shift + c));
-          }
-          f[j] = x;
+        for (int g = 0; g < 4; ++g) {
+          const float4 bb = pb[g], ss = ps[g], tt = pt[g];
+          float x0 = __uint_as_float(v[4 * g + 0]) + rbias + bb.x;
+          float x1 = __uint_as_float(v[4 * g + 1]) + rbias + bb.y;
+          float x2 = __uint_as_float(v[4 * g + 2]) + rbias + bb.z;
+          float x3 = __uint_as_float(v[4 * g + 3]) + rbias + bb.w;
+          if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+          f[4 * g + 0] = fmaf(x0, ss.x, tt.x);
+          f[4 * g + 1] = fmaf(x1, ss.y, tt.y);
+          f[4 * g + 2] = fmaf(x2, ss.z, tt.z);
+          f[4 * g + 3] = fmaf(x3, ss.w, tt.w);
         }
-        if (valid) {
-          if (p.y_f32) {
-            float* dst = p.y_f32 + frame * p.ldyf + n;
+        // the previous TMA store must have finished reading the slab
+        if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (planes) {
+          // two slabs of 64-byte rows (SWIZZLE_64B): 16-byte chunk c of row r sits at c ^ ((r>>1)&3)
+          uint8_t* sh = slab_base + row * 64;
+          uint8_t* sl = slab_base + 8192 + row * 64;
+          const int sw = (row >> 1) & 3;
 #pragma unroll
-            for (int g = 0; g < 8; ++g)
-              if (n + g * 4 < p.Cout)
-                *reinterpret_cast<float4*>(dst + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
-          }
-          if (p.y_hi) {
-            __nv_bfloat16* dh = p.y_hi + frame * p.ldy + n;
-            __nv_bfloat16* dl = p.y_lo + frame * p.ldy + n;
+          for (int g = 0; g < 2; ++g) {
+            uint32_t h[4], l[4];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (n + g * 8 < p.Cout) {
-                uint32_t h[4], l[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  __nv_bfloat16 h0, l0, h1, l1;
-                  split_bf16(f[g * 8 + 2 * k], h0, l0);
-                  split_bf16(f[g * 8 + 2 * k + 1], h1, l1);
-                  h[k] = pack_bf16x2(h0, h1);
-                  l[k] = pack_bf16x2(l0, l1);
-                }
-                *reinterpret_cast<uint4*>(dh + g * 8) = make_uint4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<uint4*>(dl + g * 8) = make_uint4(l[0], l[1], l[2], l[3]);
-              }
+            for (int k = 0; k < 4; ++k) {
+              __nv_bfloat16 h0, l0, h1, l1;
+              split_bf16(f[g * 8 + 2 * k], h0, l0);
+              split_bf16(f[g * 8 + 2 * k + 1], h1, l1);
+              h[k] = pack_bf16x2(h0, h1);
+              l[k] = pack_bf16x2(l0, l1);
             }
+            const int c = half * 2 + g;
+            *reinterpret_cast<uint4*>(sh + ((c ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(sl + ((c ^ sw) << 4)) = make_uint4(l[0], l[1], l[2], l[3]);
+          }
+        } else {
+          // one slab of 128-byte rows (SWIZZLE_128B): chunk c of row r sits at c ^ (r & 7)
+          uint8_t* sf = slab_base + row * 128;
+          const int sw = row & 7;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int c = half * 4 + g;
+            *reinterpret_cast<float4*>(sf + ((c ^ sw) << 4)) = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
           }
         }
+        fence_proxy_async();
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (leader) {
+          const int n = n0 + ch * 32;
+          if (planes) {
+            tma_store_3d(&map_y_hi, slab_base, n, t0, b0);
+            tma_store_3d(&map_y_lo, slab_base + 8192, n, t0, b0);
+          } else {
+            tma_store_3d(&map_y_f32, slab_base, n, t0, b0);
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      };
+
+      uint32_t va[16], vb[16];
+      int ch = 0;
+      tmem_ld_32x16(trow, va);
+      while (ch < nch) {
+        tmem_ld_wait();
+        if (ch + 1 < nch) tmem_ld_32x16(trow + (ch + 1) * 32, vb);
+        process(va, ch);
+        if (++ch >= nch) break;
+        tmem_ld_wait();
+        if (ch + 1 < nch) tmem_ld_32x16(trow + (ch + 1) * 32, va);
+        process(vb, ch);
+        ++ch;
       }
       tcgen05_fence_before();
-      mbar_arrive(&tmem_empty_bar[acc]);
+      if constexpr (kCta == 1) mbar_arrive(&tmem_empty_bar[acc]);
+      else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);  // the leader's barrier counts both CTAs' epilogues
     }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
   }
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<1>(tmem_base, Cfg::kTmemCols);
+  if constexpr (kCta == 2) cluster_sync();  // nobody leaves while the pair still reads its smem / barriers
+  if (warp == 1) tmem_dealloc<kCta>(tmem_base, Cfg::kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -296,6 +382,16 @@ static int make_weight_map(CUtensorMap* m, const void* base, long long K, int Co
   return XVB_OK;
 }
 
+// XVB_GEMM_CTA=1 forces single-CTA tiles, =2 (default) uses CTA pairs for the big layers.
+static int gemm_cta_mode() {
+  static int mode = 0;
+  if (mode == 0) {
+    const char* e = getenv("XVB_GEMM_CTA");
+    mode = (e && e[0] == '1') ? 1 : 2;
+  }
+  return mode;
+}
+
 // Pick the (Tb, Bb) factorisation of the 128-row M tile with the fewest padded rows.
 static void choose_m_tile(int B, int T, int* Tb_out, int* Bb_out) {
   long long best = -1;
@@ -309,26 +405,70 @@ static void choose_m_tile(int B, int T, int* Tb_out, int* Bb_out) {
   *Bb_out = 128 / bt;
 }
 
-template <int BLOCK_N>
+// Output tensor map: (Cout, T, B) with row pitch ld elements of `esize` bytes; box = 32 columns x
+// Tb x Bb; 64-byte rows (bf16) use SWIZZLE_64B, 128-byte rows (fp32) SWIZZLE_128B.
+static int make_out_map(CUtensorMap* m, const void* base, int esize, int C, int T, int B, long long ld, int Tb, int Bb) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return XVB_ECUDA; }
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * esize, (cuuint64_t)ld * esize * (cuuint64_t)T};
+  cuuint32_t box[3] = {32u, (cuuint32_t)Tb, (cuuint32_t)Bb};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   esize == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(output map C=%d T=%d B=%d ld=%lld) failed: %d", C, T, B, ld, (int)r); return XVB_ECUDA; }
+  return XVB_OK;
+}
+
+template <int BLOCK_N, int kCta>
 static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const void* w_hi, const void* w_lo,
                        TdnnGemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, kCta>;
   CUtensorMap mw_hi, mw_lo;
   const long long K = (long long)p.ntaps * p.cin_p16;
-  int rc = make_weight_map(&mw_hi, w_hi, K, p.Cout, BLOCK_N);
+  int rc = make_weight_map(&mw_hi, w_hi, K, p.Cout, Cfg::kBRows);
   if (rc) return rc;
-  rc = make_weight_map(&mw_lo, w_lo, K, p.Cout, BLOCK_N);
+  rc = make_weight_map(&mw_lo, w_lo, K, p.Cout, Cfg::kBRows);
   if (rc) return rc;
   p.num_n_blk = (p.Cout + BLOCK_N - 1) / BLOCK_N;
-  p.num_tiles = p.num_t_blk * p.num_b_blk * p.num_n_blk;
+  const int num_m_units = (p.num_t_blk * p.num_b_blk + kCta - 1) / kCta;  // 128-row blocks, or pairs of them
+  p.num_tiles = num_m_units * p.num_n_blk;
   static bool attr_set = false;
   if (!attr_set) {
-    XVB_CUDA(cudaFuncSetAttribute(tdnn_gemm_bf16x3_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    XVB_CUDA(cudaFuncSetAttribute(tdnn_gemm_bf16x3_kernel<BLOCK_N, kCta>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  tdnn_gemm_bf16x3_kernel<BLOCK_N><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
+  CUtensorMap my_hi, my_lo, my_f32;
+  if (p.y_hi) {
+    if ((rc = make_out_map(&my_hi, p.y_hi, 2, p.Cout, p.T, p.B, p.ldy, p.Tb, p.Bb))) return rc;
+    if ((rc = make_out_map(&my_lo, p.y_lo, 2, p.Cout, p.T, p.B, p.ldy, p.Tb, p.Bb))) return rc;
+  } else {
+    my_hi = mw_hi; my_lo = mw_lo;  // unused
+  }
+  if (p.y_f32) {
+    if ((rc = make_out_map(&my_f32, p.y_f32, 4, p.Cout, p.T, p.B, p.ldyf, p.Tb, p.Bb))) return rc;
+  } else {
+    my_f32 = mw_hi;  // unused
+  }
+  const int units = sm_count() / kCta;  // CTAs (kCta=1) or CTA pairs (kCta=2) resident at once
+  const int grid = (p.num_tiles < units ? p.num_tiles : units) * kCta;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCta;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  XVB_CUDA(cudaLaunchKernelEx(&cfg, tdnn_gemm_bf16x3_kernel<BLOCK_N, kCta>, ma_hi, ma_lo, mw_hi, mw_lo, my_hi, my_lo,
+                              my_f32, p));
   XVB_LAUNCH_CHECK();
   return XVB_OK;
 }
@@ -349,7 +489,7 @@ int xvb::tdnn_affine_impl(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ld
   XVB_CHECK_ARG(ntaps >= 1 && ntaps <= XVB_MAX_TAPS && context_host, "xvb_tdnn_affine: ntaps=%d out of range", ntaps);
   XVB_CHECK_ARG(ldx % 8 == 0 && ldx >= Cin, "xvb_tdnn_affine: ldx=%lld must be a multiple of 8 and >= Cin", (long long)ldx);
   XVB_CHECK_ARG((y_hi != nullptr) == (y_lo != nullptr), "xvb_tdnn_affine: y_hi/y_lo must both be set or both NULL");
-  XVB_CHECK_ARG(y_hi || y_f32, "xvb_tdnn_affine: no output requested");
+  XVB_CHECK_ARG((y_hi != nullptr) != (y_f32 != nullptr), "xvb_tdnn_affine: request exactly one of plane output / fp32 output");
   if (y_hi) XVB_CHECK_ARG(ldy % 8 == 0 && Cout % 8 == 0 && ldy >= Cout, "xvb_tdnn_affine: plane output needs ldy%%8==0, Cout%%8==0");
   if (y_f32) XVB_CHECK_ARG(ldyf % 4 == 0 && Cout % 4 == 0 && ldyf >= Cout, "xvb_tdnn_affine: fp32 output needs ldyf%%4==0, Cout%%4==0");
   XVB_CHECK_ARG(!(flags & XVB_BN) || (bn_scale && bn_shift), "xvb_tdnn_affine: XVB_BN without scale/shift");
@@ -384,10 +524,15 @@ int xvb::tdnn_affine_impl(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ld
   // segment-level layers (M = B rows) so that more SMs get a tile.
   const long long m_tiles = (long long)p.num_t_blk * p.num_b_blk;
   const int sms = sm_count();
-  if (Cout >= 256 && m_tiles * ((Cout + 255) / 256) >= sms) return launch_gemm<256>(ma_hi, ma_lo, w_hi, w_lo, p, s);
-  if (Cout >= 128 && m_tiles * ((Cout + 127) / 128) >= sms) return launch_gemm<128>(ma_hi, ma_lo, w_hi, w_lo, p, s);
-  if (Cout >= 64 && m_tiles * ((Cout + 63) / 64) >= sms / 2) return launch_gemm<64>(ma_hi, ma_lo, w_hi, w_lo, p, s);
-  return launch_gemm<32>(ma_hi, ma_lo, w_hi, w_lo, p, s);
+  const int mode = gemm_cta_mode();
+  if (mode == 2 && Cout >= 256 && m_tiles * ((Cout + 255) / 256) >= sms)
+    return launch_gemm<256, 2>(ma_hi, ma_lo, w_hi, w_lo, p, s);
+  if (mode == 2 && Cout >= 128 && m_tiles * ((Cout + 127) / 128) >= sms)
+    return launch_gemm<128, 2>(ma_hi, ma_lo, w_hi, w_lo, p, s);
+  if (Cout >= 256 && m_tiles * ((Cout + 255) / 256) >= sms) return launch_gemm<256, 1>(ma_hi, ma_lo, w_hi, w_lo, p, s);
+  if (Cout >= 128 && m_tiles * ((Cout + 127) / 128) >= sms) return launch_gemm<128, 1>(ma_hi, ma_lo, w_hi, w_lo, p, s);
+  if (Cout >= 64 && m_tiles * ((Cout + 63) / 64) >= sms / 2) return launch_gemm<64, 1>(ma_hi, ma_lo, w_hi, w_lo, p, s);
+  return launch_gemm<32, 1>(ma_hi, ma_lo, w_hi, w_lo, p, s);
 }
 
 extern "C" int xvb_tdnn_affine(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, const uint16_t* w_hi,
