@@ -45,6 +45,8 @@ SIGNATURES = {
     "xvb_center_length_norm": (_i, [_p, _p, _p, _i64, _i, _p]),
     "xvb_column_mean": (_i, [_p, _i64, _i, _p, _p]),
     "xvb_cosine_trials": (_i, [_p, _p, _i, _p, _p, _i64, _p, _p]),
+    "xvb_bilinear_trials": (_i, [_p, _p, _i, _p, _p, _i64, _p, _p, _p, _p]),
+    "xvb_project": (_i, [_p, _i64, _i, _p, _i, _p, _p]),
     "xvb_cosine_matrix": (_i, [_p, _i64, _p, _i64, _i, _p, _i64, _p]),
     "xvb_plda_terms": (_i, [_p, _i64, _i, _p, _p, _p, _p]),
     "xvb_plda_matrix": (_i, [_p, _i64, _p, _i64, _i, _p, _p, _p, _p, _i64, _p]),

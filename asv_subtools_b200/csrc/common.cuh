@@ -1,5 +1,6 @@
 // Shared host-side helpers: error reporting, launch counting, bf16 split helpers.
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdarg.h>
@@ -60,6 +61,10 @@ int tdnn_affine_impl(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, co
                      const float* row_bias, int flags, const int* context_host, int ntaps, uint16_t* y_hi,
                      uint16_t* y_lo, int64_t ldy, float* y_f32, int64_t ldyf, int B, int T, int Cin, int Cout,
                      void* stream);
+
+// tdnn_gemm.cu: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda).
+int make_tensor_map(CUtensorMap* m, const void* base, int esize, int rank, const unsigned long long* dims,
+                    const unsigned long long* strides_bytes, const unsigned* box, int swizzle_bytes);
 
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 

@@ -3,106 +3,124 @@
 //   mean[b,c] = (1/T) sum_t x[b,t,c];  std[b,c] = sqrt(max((1/T) sum_t (x-mean)^2, eps))
 //
 // HBM-bound: x (B,T,C) fp32 is read exactly once.  A CTA owns one utterance x one 128-channel
-// slab; each of its 8 warps streams every 8th frame (32 lanes x float4 = 512 contiguous bytes per
-// frame) in register chunks of kRows frames.  Within a chunk the variance is the true two-pass
-// sum (x - chunk_mean)^2 on registers; chunks and warps are merged with Chan's parallel update,
-// which is algebraically the reference's two-pass result without a second trip to memory.
+// slab.  The slab (up to 200 frames x 512 B = 100 KB) is pulled into shared memory by TMA in
+// 40-frame boxes, each with its own mbarrier, so ~100 KB per CTA (two CTAs per SM) are in flight
+// without costing registers, and the reduction starts on the first box while the rest lands.
+// With the slab on chip the statistics are the reference's literal two passes: pass 1 the mean,
+// pass 2 sum((x - mean)^2).  Utterances longer than one slab are processed slab by slab and merged
+// with Chan's parallel-variance update (algebraically the same two-pass result).
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace xvb {
 
 constexpr int kPoolWarps = 8;
-constexpr int kPoolRows = 8;  // frames held in registers per warp per chunk (8 x float4 = 32 regs)
+constexpr int kPoolBoxRows = 40;                 // frames per TMA box (20 KB)
+constexpr int kPoolSlabRows = 200;               // 5 boxes resident: 100 KB -> two CTAs per SM
+constexpr int kPoolNumBars = (kPoolSlabRows + kPoolBoxRows - 1) / kPoolBoxRows;
+constexpr int kPoolSmemBytes = kPoolNumBars * kPoolBoxRows * 128 * 4 + kPoolWarps * 128 * 4 + 128;
 
-struct Moments {  // running count / mean / M2 for 4 channels
-  float n;
-  float mean[4];
-  float m2[4];
-};
+__global__ void __launch_bounds__(kPoolWarps * 32, 2)
+stats_pool_tma_kernel(const __grid_constant__ CUtensorMap map_x, int T, int C, float eps, float* __restrict__ out,
+                      __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, long long ldo) {
+  extern __shared__ __align__(128) uint8_t pool_smem[];
+  float* slab = reinterpret_cast<float*>(pool_smem);                                  // [rows][128]
+  float* scratch = slab + kPoolNumBars * kPoolBoxRows * 128;                          // [warps][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + kPoolWarps * 128);           // [kPoolNumBars]
 
-__device__ __forceinline__ void chan_merge(Moments& a, float nb, const float (&mb)[4], const float (&m2b)[4]) {
-  if (nb == 0.f) return;
-  const float tot = a.n + nb;
-  const float wb = nb / tot;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float d = mb[k] - a.mean[k];
-    a.mean[k] = fmaf(d, wb, a.mean[k]);
-    a.m2[k] += m2b[k] + d * d * a.n * wb;
-  }
-  a.n = tot;
-}
-
-__global__ void __launch_bounds__(kPoolWarps * 32)
-stats_pool_kernel(const float* __restrict__ x, long long ldx, int T, int C, float eps, float* __restrict__ out,
-                  __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, long long ldo) {
   const int b = blockIdx.y;
-  const int c = blockIdx.x * 128 + (threadIdx.x & 31) * 4;
-  const int warp = threadIdx.x >> 5;
-  const bool active = c < C;  // C % 4 == 0, so a float4 is all-in or all-out
-  const float* xb = x + (long long)b * T * ldx + c;
+  const int c0 = blockIdx.x * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = c0 + lane * 4;
+  const bool active = c < C;  // C % 4 == 0
 
-  Moments acc{};
-  for (int t0 = warp; t0 < T; t0 += kPoolWarps * kPoolRows) {
-    float4 v[kPoolRows];
-    int cnt = 0;
-#pragma unroll
-    for (int r = 0; r < kPoolRows; ++r) {
-      const int t = t0 + r * kPoolWarps;
-      if (t < T) {
-        if (active) v[r] = __ldcs(reinterpret_cast<const float4*>(xb + (long long)t * ldx));  // streaming: read once
-        ++cnt;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_x);
+    for (int i = 0; i < kPoolNumBars; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  float run_n = 0.f;
+  float4 run_mean = make_float4(0.f, 0.f, 0.f, 0.f), run_m2 = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint32_t phase = 0;
+  for (int t_base = 0; t_base < T; t_base += kPoolSlabRows, phase ^= 1) {
+    const int rows = min(kPoolSlabRows, T - t_base);
+    const int nbox = (rows + kPoolBoxRows - 1) / kPoolBoxRows;
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < nbox; ++i) {
+        mbar_expect_tx(&bars[i], kPoolBoxRows * 128 * 4);  // OOB rows/channels are zero-filled but counted
+        tma_load_3d(slab + i * kPoolBoxRows * 128, &map_x, &bars[i], c0, t_base + i * kPoolBoxRows, b);
       }
     }
-    if (!active) continue;
-    float s[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int r = 0; r < kPoolRows; ++r)
-      if (r < cnt) { s[0] += v[r].x; s[1] += v[r].y; s[2] += v[r].z; s[3] += v[r].w; }
-    const float inv = 1.f / (float)cnt;
-    float m[4] = {s[0] * inv, s[1] * inv, s[2] * inv, s[3] * inv};
-    float q[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int r = 0; r < kPoolRows; ++r)
-      if (r < cnt) {
-        float d;
-        d = v[r].x - m[0]; q[0] = fmaf(d, d, q[0]);
-        d = v[r].y - m[1]; q[1] = fmaf(d, d, q[1]);
-        d = v[r].z - m[2]; q[2] = fmaf(d, d, q[2]);
-        d = v[r].w - m[3]; q[3] = fmaf(d, d, q[3]);
+    // ---- pass 1: mean (rows strided over warps; start as soon as a box has landed)
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < nbox; ++i) {
+      mbar_wait(&bars[i], phase);
+      const int r_end = min(rows, (i + 1) * kPoolBoxRows);
+#pragma unroll 4
+      for (int r = i * kPoolBoxRows + warp; r < r_end; r += kPoolWarps) {
+        const float4 v = *reinterpret_cast<const float4*>(slab + r * 128 + lane * 4);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
       }
-    chan_merge(acc, (float)cnt, m, q);
+    }
+    *reinterpret_cast<float4*>(scratch + warp * 128 + lane * 4) = s;
+    __syncthreads();
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < kPoolWarps; ++w) {
+      const float4 v = *reinterpret_cast<const float4*>(scratch + w * 128 + lane * 4);
+      m.x += v.x; m.y += v.y; m.z += v.z; m.w += v.w;
+    }
+    const float inv = 1.f / (float)rows;
+    m.x *= inv; m.y *= inv; m.z *= inv; m.w *= inv;
+    __syncthreads();
+    // ---- pass 2: sum (x - mean)^2 from the on-chip slab
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int r = warp; r < rows; r += kPoolWarps) {
+      const float4 v = *reinterpret_cast<const float4*>(slab + r * 128 + lane * 4);
+      float d;
+      d = v.x - m.x; q.x = fmaf(d, d, q.x);
+      d = v.y - m.y; q.y = fmaf(d, d, q.y);
+      d = v.z - m.z; q.z = fmaf(d, d, q.z);
+      d = v.w - m.w; q.w = fmaf(d, d, q.w);
+    }
+    *reinterpret_cast<float4*>(scratch + warp * 128 + lane * 4) = q;
+    __syncthreads();
+    float4 m2 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < kPoolWarps; ++w) {
+      const float4 v = *reinterpret_cast<const float4*>(scratch + w * 128 + lane * 4);
+      m2.x += v.x; m2.y += v.y; m2.z += v.z; m2.w += v.w;
+    }
+    __syncthreads();  // scratch and slab are free again
+    // ---- Chan merge of this slab into the running statistics (every thread keeps a copy)
+    const float nb = (float)rows, tot = run_n + nb, wb = nb / tot, cross = run_n * wb;
+    float d;
+    d = m.x - run_mean.x; run_mean.x = fmaf(d, wb, run_mean.x); run_m2.x += m2.x + d * d * cross;
+    d = m.y - run_mean.y; run_mean.y = fmaf(d, wb, run_mean.y); run_m2.y += m2.y + d * d * cross;
+    d = m.z - run_mean.z; run_mean.z = fmaf(d, wb, run_mean.z); run_m2.z += m2.z + d * d * cross;
+    d = m.w - run_mean.w; run_mean.w = fmaf(d, wb, run_mean.w); run_m2.w += m2.w + d * d * cross;
+    run_n = tot;
   }
 
-  __shared__ float sh_n[kPoolWarps][32];
-  __shared__ float sh_mean[kPoolWarps][32][4];
-  __shared__ float sh_m2[kPoolWarps][32][4];
-  const int lane = threadIdx.x & 31;
-  sh_n[warp][lane] = acc.n;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) { sh_mean[warp][lane][k] = acc.mean[k]; sh_m2[warp][lane][k] = acc.m2[k]; }
-  __syncthreads();
   if (warp == 0 && active) {
-    Moments tot{};
-    for (int w = 0; w < kPoolWarps; ++w) {
-      float mb[4], qb[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { mb[k] = sh_mean[w][lane][k]; qb[k] = sh_m2[w][lane][k]; }
-      chan_merge(tot, sh_n[w][lane], mb, qb);
-    }
-    float sd[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) sd[k] = sqrtf(fmaxf(tot.m2[k] / (float)T, eps));  // biased var, clamp(min=eps)
+    const float invT = 1.f / (float)T;
+    float sd[4] = {sqrtf(fmaxf(run_m2.x * invT, eps)), sqrtf(fmaxf(run_m2.y * invT, eps)),
+                   sqrtf(fmaxf(run_m2.z * invT, eps)), sqrtf(fmaxf(run_m2.w * invT, eps))};  // biased var, clamp
+    float mu[4] = {run_mean.x, run_mean.y, run_mean.z, run_mean.w};
     float* ob = out + (long long)b * 2 * C;
-    *reinterpret_cast<float4*>(ob + c) = make_float4(tot.mean[0], tot.mean[1], tot.mean[2], tot.mean[3]);
+    *reinterpret_cast<float4*>(ob + c) = make_float4(mu[0], mu[1], mu[2], mu[3]);
     *reinterpret_cast<float4*>(ob + C + c) = make_float4(sd[0], sd[1], sd[2], sd[3]);
     if (out_hi) {
       __nv_bfloat16 h[8], l[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { split_bf16(tot.mean[k], h[k], l[k]); split_bf16(sd[k], h[4 + k], l[4 + k]); }
+      for (int k = 0; k < 4; ++k) { split_bf16(mu[k], h[k], l[k]); split_bf16(sd[k], h[4 + k], l[4 + k]); }
       __nv_bfloat16* oh = out_hi + (long long)b * ldo;
       __nv_bfloat16* ol = out_lo + (long long)b * ldo;
       *reinterpret_cast<uint2*>(oh + c) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
@@ -127,9 +145,20 @@ extern "C" int xvb_stats_pool(const float* x, int64_t ldx, int B, int T, int C, 
   if (out_hi) XVB_CHECK_ARG(ldo >= 2 * C && ldo % 4 == 0, "xvb_stats_pool: ldo=%lld too small / unaligned", (long long)ldo);
   XVB_CHECK_ARG(((uintptr_t)x | (uintptr_t)out) % 16 == 0 && ((uintptr_t)out_hi | (uintptr_t)out_lo) % 8 == 0, "xvb_stats_pool: unaligned pointer");
   XVB_CHECK_ARG(B <= 65535, "xvb_stats_pool: B=%d exceeds grid.y", B);
+  CUtensorMap map;
+  const unsigned long long dims[3] = {(unsigned long long)C, (unsigned long long)T, (unsigned long long)B};
+  const unsigned long long strides[2] = {(unsigned long long)ldx * 4, (unsigned long long)ldx * 4 * (unsigned long long)T};
+  const unsigned box[3] = {128u, (unsigned)kPoolBoxRows, 1u};
+  rc = make_tensor_map(&map, x, 4, 3, dims, strides, box, 0);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    XVB_CUDA(cudaFuncSetAttribute(stats_pool_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoolSmemBytes));
+    attr_set = true;
+  }
   dim3 grid((C + 127) / 128, B);
-  stats_pool_kernel<<<grid, kPoolWarps * 32, 0, (cudaStream_t)stream>>>(
-      x, ldx, T, C, eps, out, reinterpret_cast<__nv_bfloat16*>(out_hi), reinterpret_cast<__nv_bfloat16*>(out_lo), ldo);
+  stats_pool_tma_kernel<<<grid, kPoolWarps * 32, kPoolSmemBytes, (cudaStream_t)stream>>>(
+      map, T, C, eps, out, reinterpret_cast<__nv_bfloat16*>(out_hi), reinterpret_cast<__nv_bfloat16*>(out_lo), ldo);
   XVB_LAUNCH_CHECK();
   return XVB_OK;
 }

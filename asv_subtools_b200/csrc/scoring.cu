@@ -50,9 +50,10 @@ __global__ void column_final_kernel(const double* __restrict__ partial, int G, l
   mean[c] = (float)(s / (double)rows);
 }
 
-// one warp per trial
+// one warp per trial: <e[te], t[tt]> (+ row[te] + col[tt] for PLDA)
 __global__ void cosine_trials_kernel(const float* __restrict__ e, const float* __restrict__ t, int D,
                                      const int32_t* __restrict__ te, const int32_t* __restrict__ tt,
+                                     const float* __restrict__ row, const float* __restrict__ col,
                                      long long n, float* __restrict__ scores) {
   const long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -62,7 +63,7 @@ __global__ void cosine_trials_kernel(const float* __restrict__ e, const float* _
   float s = 0.f;
   for (int c = lane; c < D; c += 32) s = fmaf(a[c], b[c], s);
   s = warp_sum(s);
-  if (lane == 0) scores[i] = s;
+  if (lane == 0) scores[i] = s + (row ? row[te[i]] : 0.f) + (col ? col[tt[i]] : 0.f);
 }
 
 // term[i] = <y_i, x_i> + <x_i, c>   (y = x G computed by the GEMM)
@@ -145,17 +146,32 @@ extern "C" int xvb_column_mean(const float* x, int64_t rows, int D, float* mean,
   return XVB_OK;
 }
 
-extern "C" int xvb_cosine_trials(const float* enroll, const float* test, int D, const int32_t* trial_e,
-                                 const int32_t* trial_t, int64_t num_trials, float* scores, void* stream) {
+extern "C" int xvb_bilinear_trials(const float* enroll, const float* test, int D, const int32_t* trial_e,
+                                   const int32_t* trial_t, int64_t num_trials, const float* row_term,
+                                   const float* col_term, float* scores, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
-  XVB_CHECK_ARG(enroll && test && trial_e && trial_t && scores && D > 0, "xvb_cosine_trials: bad arguments");
+  XVB_CHECK_ARG(enroll && test && trial_e && trial_t && scores && D > 0, "xvb_bilinear_trials: bad arguments");
   if (num_trials == 0) return XVB_OK;
   const long long threads = num_trials * 32;
-  cosine_trials_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(enroll, test, D, trial_e,
-                                                                                          trial_t, num_trials, scores);
+  cosine_trials_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      enroll, test, D, trial_e, trial_t, row_term, col_term, num_trials, scores);
   XVB_LAUNCH_CHECK();
   return XVB_OK;
+}
+
+extern "C" int xvb_cosine_trials(const float* enroll, const float* test, int D, const int32_t* trial_e,
+                                 const int32_t* trial_t, int64_t num_trials, float* scores, void* stream) {
+  return xvb_bilinear_trials(enroll, test, D, trial_e, trial_t, num_trials, nullptr, nullptr, scores, stream);
+}
+
+// y (rows, Dout) = x (rows, D) . M^T, M (Dout, D) -- the small projections of the back-end
+// (E' = E.(Lambda+Lambda^T) for PLDA; LDA/whitening transforms of score/process.sh:205-265).
+extern "C" int xvb_project(const float* x, int64_t rows, int D, const float* M, int Dout, float* y, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  XVB_CHECK_ARG(x && M && y && rows > 0 && D > 0 && Dout > 0 && Dout % 4 == 0, "xvb_project: bad arguments (Dout%%4==0)");
+  return matmul_nt(x, rows, M, Dout, D, nullptr, nullptr, y, Dout, nullptr, nullptr, 0, (cudaStream_t)stream);
 }
 
 extern "C" int xvb_cosine_matrix(const float* enroll, int64_t Ne, const float* test, int64_t Nt, int D, float* S,

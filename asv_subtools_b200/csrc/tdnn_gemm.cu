@@ -352,6 +352,24 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+// Generic tiled tensor map (exported for pooling.cu).  esize 2 -> bf16, 4 -> fp32; swizzle_bytes 0/64/128.
+int make_tensor_map(CUtensorMap* m, const void* base, int esize, int rank, const unsigned long long* dims,
+                    const unsigned long long* strides_bytes, const unsigned* box, int swizzle_bytes) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return XVB_ECUDA; }
+  cuuint64_t d[5], st[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                               : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = enc(m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank,
+                   const_cast<void*>(base), d, st, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(rank %d) failed: %d", rank, (int)r); return XVB_ECUDA; }
+  return XVB_OK;
+}
+
 // (C, T, B) bf16 frame matrix with row pitch ld; box = 64 channels x Tb frames x Bb utterances.
 static int make_frame_map(CUtensorMap* m, const void* base, int C, int T, int B, long long ld, int Tb, int Bb) {
   PFN_encodeTiled enc = get_encode();

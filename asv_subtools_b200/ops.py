@@ -147,6 +147,27 @@ def cosine_trials(enroll, test, trial_e, trial_t):
     return s
 
 
+def bilinear_trials(enroll, test, trial_e, trial_t, row_term=None, col_term=None):
+    enroll = _req(enroll, torch.float32, "enroll")
+    test = _req(test, torch.float32, "test")
+    trial_e = _req(trial_e, torch.int32, "trial_e")
+    trial_t = _req(trial_t, torch.int32, "trial_t")
+    s = torch.empty(trial_e.shape[0], dtype=torch.float32, device=enroll.device)
+    check(lib.xvb_bilinear_trials(_ptr(enroll), _ptr(test), enroll.shape[1], _ptr(trial_e), _ptr(trial_t),
+                                  trial_e.shape[0], _ptr(row_term), _ptr(col_term), _ptr(s), _stream()),
+          "xvb_bilinear_trials")
+    return s
+
+
+def project(x, m):
+    """x (rows, D) . m^T with m (Dout, D) -> (rows, Dout)."""
+    x = _req(x, torch.float32, "x")
+    m = _req(m, torch.float32, "m")
+    y = torch.empty(x.shape[0], m.shape[0], dtype=torch.float32, device=x.device)
+    check(lib.xvb_project(_ptr(x), x.shape[0], x.shape[1], _ptr(m), m.shape[0], _ptr(y), _stream()), "xvb_project")
+    return y
+
+
 def cosine_matrix(enroll, test):
     enroll = _req(enroll, torch.float32, "enroll")
     test = _req(test, torch.float32, "test")

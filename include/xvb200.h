@@ -125,6 +125,18 @@ int xvb_column_mean(const float* x, int64_t rows, int D, float* mean, void* stre
 int xvb_cosine_trials(const float* enroll, const float* test, int D, const int32_t* trial_e, const int32_t* trial_t,
                       int64_t num_trials, float* scores, void* stream);
 
+/* Per-trial bilinear scores with optional per-row / per-column terms:
+ * scores[i] = <enroll[te[i]], test[tt[i]]> + row_term[te[i]] + col_term[tt[i]]  (terms may be NULL).
+ * With enroll := E.(Lambda+Lambda^T) and the xvb_plda_terms() vectors this is PLDAScoring
+ * (score/pyplda/gaussian-plda-scoring.py:23-29) for each listed trial (main loop :78-84). */
+int xvb_bilinear_trials(const float* enroll, const float* test, int D, const int32_t* trial_e, const int32_t* trial_t,
+                        int64_t num_trials, const float* row_term, const float* col_term, float* scores, void* stream);
+
+/* y (rows, Dout) = x (rows, D) . M^T with M (Dout, D) row-major, Dout % 4 == 0: the small
+ * projections of the back-end (PLDA's E.(Lambda+Lambda^T); `lda`/`whiten` transforms applied by
+ * ivector-transform in score/process.sh:205-233).  Runs on the tcgen05 layer kernel. */
+int xvb_project(const float* x, int64_t rows, int D, const float* M, int Dout, float* y, void* stream);
+
 /* All-pairs score matrix S (Ne, Nt) = enroll . test^T (BASELINE config 4). */
 int xvb_cosine_matrix(const float* enroll, int64_t Ne, const float* test, int64_t Nt, int D, float* S, int64_t lds,
                       void* stream);

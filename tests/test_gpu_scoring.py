@@ -1,0 +1,177 @@
+"""Back-end scoring parity on the GPU: pre-processing, cosine, PLDA and "EER identical to 3
+decimals" against the oracle / golden fixtures, plus the CLI twins end to end."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nnet as onn
+from oracle import scoring as osc
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from asv_subtools_b200 import ops as _ops
+    return _ops
+
+
+def cuda(a, dtype=np.float32):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).cuda()
+
+
+def test_center_length_norm_and_column_mean(ops):
+    emb, _ = osc.synthetic_speakers(50, 7, 192, 3)
+    emb = emb * 3 + 0.7
+    mean = ops.column_mean(cuda(emb))
+    assert rel(mean.cpu().numpy(), osc.global_mean(emb)) < 1e-6
+    y = ops.center_length_norm(cuda(emb), mean)
+    ref = osc.length_norm(osc.subtract_global_mean(emb, osc.global_mean(emb)))
+    assert rel(y.cpu().numpy(), ref) < 1e-6
+    y2 = ops.center_length_norm(cuda(emb))
+    assert rel(y2.cpu().numpy(), osc.length_norm(emb)) < 1e-6
+
+
+def test_cosine_trials_and_matrix(ops):
+    e, _ = osc.synthetic_speakers(40, 3, 512, 4)
+    t, _ = osc.synthetic_speakers(30, 4, 512, 5)
+    e, t = osc.length_norm(e), osc.length_norm(t)
+    rng = np.random.RandomState(0)
+    te = rng.randint(0, e.shape[0], 500).astype(np.int32)
+    tt = rng.randint(0, t.shape[0], 500).astype(np.int32)
+    s = ops.cosine_trials(cuda(e), cuda(t), cuda(te, np.int32), cuda(tt, np.int32))
+    assert np.max(np.abs(s.cpu().numpy() - osc.cosine_trials(e, t, te, tt))) < 2e-6
+    S = ops.cosine_matrix(cuda(e), cuda(t))
+    assert S.shape == (120, 120)
+    assert np.max(np.abs(S.cpu().numpy() - osc.cosine_matrix(e, t))) < 2e-5  # bf16x3 GEMM, |s| <= 1
+
+
+def test_plda_matches_reference_golden(golden):
+    from asv_subtools_b200.score.backend import PldaModel
+    g = golden("scoring")
+    m = PldaModel(g["plda_mean"], g["plda_within"], g["plda_between"])
+    assert rel(m.gamma, g["plda_gamma"]) < 1e-12 and rel(m.lam, g["plda_lambda"]) < 1e-12
+    assert rel(m.c, g["plda_c"].reshape(-1)) < 1e-12
+    E, T = cuda(g["plda_E"]), cuda(g["plda_T"][:8])   # Nt % 4 == 0 for the matrix form
+    S = m.score_matrix(E, T).cpu().numpy()
+    assert rel(S, g["plda_S"][:, :8]) < 5e-5
+    te = np.repeat(np.arange(12), 9).astype(np.int32)
+    tt = np.tile(np.arange(9), 12).astype(np.int32)
+    s = m.score_trials(E, cuda(g["plda_T"]), cuda(te, np.int32), cuda(tt, np.int32)).cpu().numpy()
+    assert rel(s.reshape(12, 9), g["plda_S"]) < 5e-5
+
+
+def _trials(lab_e, lab_t, rng, n):
+    te = rng.randint(0, lab_e.shape[0], n).astype(np.int32)
+    tt = rng.randint(0, lab_t.shape[0], n).astype(np.int32)
+    # make ~10% of the trials targets
+    k = n // 10
+    for i in range(k):
+        cand = np.flatnonzero(lab_t == lab_e[te[i]])
+        tt[i] = cand[rng.randint(cand.size)]
+    return te, tt, (lab_e[te] == lab_t[tt]).astype(np.int64)
+
+
+def test_eer_identical_to_three_decimals_cosine_and_plda(ops):
+    """North-star criterion on synthetic trials: EER(new scores) == EER(reference-arithmetic scores)
+    to 3 decimals (in %), under each in-repo EER definition."""
+    from asv_subtools_b200.score import metrics
+    from asv_subtools_b200.score.backend import PldaModel
+    emb, lab = osc.synthetic_speakers(300, 8, 192, 21, noise=1.6)
+    rng = np.random.RandomState(9)
+    te, tt, y = _trials(lab, lab, rng, 200000)
+    # --- cosine with submean + norm (score/process.sh + score.sh)
+    ref_x = osc.length_norm(osc.subtract_global_mean(emb, osc.global_mean(emb)))
+    ref_s = osc.cosine_trials(ref_x, ref_x, te, tt)
+    x = cuda(emb)
+    xn = ops.center_length_norm(x, ops.column_mean(x))
+    s = ops.cosine_trials(xn, xn, cuda(te, np.int32), cuda(tt, np.int32)).cpu().numpy()
+    for name, fn_ref, fn_new in (("bosaris", osc.eer_bosaris_like, metrics.eer_bosaris),
+                                 ("det", osc.eer_det_interp, metrics.eer_det)):
+        e_ref, e_new = fn_ref(ref_s, y)[0], fn_new(s, y)[0]
+        assert 0.01 < e_ref < 0.3, e_ref
+        assert round(e_ref * 100, 3) == round(e_new * 100, 3), (name, e_ref, e_new)
+    # --- PLDA with a synthetic two-covariance model
+    d = emb.shape[1]
+    a = rng.standard_normal((d, d))
+    within = a @ a.T / d * 2.0 + np.eye(d)
+    between = np.eye(d) * 1.0 + 0.05 * (a + a.T) / np.sqrt(d)
+    between = between @ between.T
+    mean = emb.mean(0).astype(np.float64).reshape(-1, 1)
+    G, L, c, k = osc.plda_calculate_var(between, osc.plda_smooth_within(within), mean)
+    row = np.einsum("ij,jk,ik->i", emb.astype(np.float64), G, emb.astype(np.float64)) + emb.astype(np.float64) @ c.reshape(-1)
+    ref_p = np.einsum("ij,jk,ik->i", emb[te].astype(np.float64), L + L.T, emb[tt].astype(np.float64)) + row[te] + row[tt]
+    m = PldaModel(mean, within, between)
+    p = m.score_trials(x, x, cuda(te, np.int32), cuda(tt, np.int32)).cpu().numpy()
+    assert rel(p, ref_p) < 1e-4
+    for fn_ref, fn_new in ((osc.eer_bosaris_like, metrics.eer_bosaris), (osc.eer_det_interp, metrics.eer_det)):
+        assert round(fn_ref(ref_p, y)[0] * 100, 3) == round(fn_new(p, y)[0] * 100, 3)
+
+
+def test_extract_and_score_clis_end_to_end(tmp_path):
+    """feats.ark + checkpoint + nnet.config -> extract CLI -> xvector.ark -> cosine CLI -> EER CLI,
+    compared with the oracle running the reference arithmetic on the same files."""
+    from asv_subtools_b200 import kaldi_io
+    dim, n_spk, per = 24, 12, 4
+    sd = onn.make_state_dict(onn.xvector_spec(dim), 31)
+    torch.save(sd, str(tmp_path / "final.params"))
+    bp = os.path.join(ROOT, "asv_subtools_b200", "model", "xvector.py")
+    (tmp_path / "nnet.config").write_text(
+        'model_blueprint;{}\nmodel_creation;"Xvector({},10,training=False,extracted_embedding=""far"")"\n'.format(bp, dim))
+    rng = np.random.RandomState(1)
+    spk_dir = rng.standard_normal((n_spk, dim)).astype(np.float32)
+    feats, labels = {}, {}
+    for s in range(n_spk):
+        for u in range(per):
+            T = [60, 60, 75, 90][u]
+            key = "spk{:02d}-utt{}".format(s, u)
+            feats[key] = (rng.standard_normal((T, dim)) + 0.8 * spk_dir[s]).astype(np.float32)
+            labels[key] = s
+    with open(tmp_path / "feats.ark", "wb") as f:
+        for k, v in feats.items():
+            kaldi_io.write_mat(f, v, key=k)
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-m", "asv_subtools_b200.pipeline.extract_embeddings", "--nnet-config",
+                        str(tmp_path / "nnet.config"), "--batch-size", "8", str(tmp_path / "final.params"),
+                        "ark:" + str(tmp_path / "feats.ark"), "ark:" + str(tmp_path / "xvector.ark")],
+                       capture_output=True, text=True, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("Process utterance for key") == len(feats)
+    got = dict(kaldi_io.read_vec_flt_ark(str(tmp_path / "xvector.ark")))
+    assert set(got) == set(feats)
+    ref = {}
+    for k, v in feats.items():
+        ref[k] = onn.extract_embedding(lambda x: onn.xvector_forward(sd, x, "far"), v).numpy()
+        assert got[k].dtype == np.float32 and rel(got[k], ref[k]) < 1e-4
+    keys = sorted(feats)
+    with open(tmp_path / "trials", "w") as f:
+        for a in keys[::3]:
+            for b in keys:
+                f.write("{} {} {}\n".format(a, b, "target" if labels[a] == labels[b] else "nontarget"))
+    r = subprocess.run([sys.executable, "-m", "asv_subtools_b200.score.cosine", "--norm", str(tmp_path / "trials"),
+                        str(tmp_path / "xvector.ark"), str(tmp_path / "xvector.ark"), str(tmp_path / "cos.score")],
+                       capture_output=True, text=True, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stdout + r.stderr
+    r = subprocess.run([sys.executable, "-m", "asv_subtools_b200.score.compute_eer", str(tmp_path / "trials"),
+                        str(tmp_path / "cos.score")], capture_output=True, text=True, env=env, cwd=ROOT)
+    assert r.returncode == 0 and "EER%" in r.stdout, r.stdout + r.stderr
+    eer_cli = float(r.stdout.split("EER%")[1].split()[0])
+    X = osc.length_norm(np.stack([ref[k] for k in keys]))
+    idx = {k: i for i, k in enumerate(keys)}
+    s, y = [], []
+    for line in open(tmp_path / "trials"):
+        a, b, l = line.split()
+        s.append(float(X[idx[a]].astype(np.float64) @ X[idx[b]].astype(np.float64)))
+        y.append(1 if l == "target" else 0)
+    assert round(osc.eer_bosaris_like(s, y)[0] * 100, 3) == round(eer_cli, 3)

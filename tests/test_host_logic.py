@@ -1,0 +1,146 @@
+"""Host-side logic that needs no GPU: metrics vs golden, CLI plumbing (nnet.config, blueprint
+loading, bucketing), the extract_embedding chunk rule, world-size-2 sharding under gloo."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from asv_subtools_b200.pipeline import extract_embeddings as cli
+from asv_subtools_b200.score import metrics
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _eer_scores(seed):
+    rng = np.random.RandomState(seed)
+    tar = rng.standard_normal(2000) + 2.0
+    non = rng.standard_normal(50000)
+    scores = np.concatenate([tar, non])
+    labels = np.concatenate([np.ones(2000, dtype=np.int64), np.zeros(50000, dtype=np.int64)])
+    perm = rng.permutation(scores.shape[0])
+    return scores[perm], labels[perm]
+
+
+def test_metrics_match_reference_golden(golden):
+    g = golden("scoring")
+    s, lab = _eer_scores(int(g["eer_scores_seed"]))
+    e, t = metrics.eer_bosaris(s, lab)
+    assert abs(e - g["eer_bosaris"]) < 1e-12 and abs(t - g["eer_bosaris_thr"]) < 1e-12
+    e, t = metrics.eer_det(s, lab)
+    assert abs(e - g["eer_det"]) < 1e-12 and abs(t - g["eer_det_thr"]) < 1e-9
+    assert abs(metrics.min_dcf(s, lab, 0.01) - g["mindcf_det"]) < 1e-12
+    strs = np.where(lab == 1, "target", "nontarget")
+    assert metrics.eer_bosaris(s, strs)[0] == metrics.eer_bosaris(s, lab)[0]
+
+
+def test_metrics_match_oracle_on_ties_and_small_sets():
+    from oracle import scoring as osc
+    rng = np.random.RandomState(5)
+    for n in (40, 400):
+        s = np.round(rng.standard_normal(n) + np.repeat([1.0, 0.0], n // 2), 1)  # heavy ties
+        lab = np.repeat([1, 0], n // 2)
+        assert metrics.eer_bosaris(s, lab) == pytest.approx(osc.eer_bosaris_like(s, lab))
+        assert metrics.eer_det(s, lab) == pytest.approx(osc.eer_det_interp(s, lab))
+        assert metrics.eer_kaldi(s, lab) == pytest.approx(osc.eer_kaldi(s, lab))
+
+
+def test_nnet_config_and_blueprint_loading(tmp_path):
+    cfg = tmp_path / "nnet.config"
+    bp = os.path.join(ROOT, "asv_subtools_b200", "model", "xvector.py")
+    # the exact layout pandas.to_csv(header=None, sep=";") writes in utils.write_nnet_config
+    cfg.write_text('model_blueprint;{}\nmodel_creation;"Xvector(23,10,training=False,extracted_embedding=""near"")"\n'.format(bp))
+    blueprint, creation = cli.read_nnet_config(str(cfg))
+    assert blueprint == bp and creation == 'Xvector(23,10,training=False,extracted_embedding="near")'
+    m = cli.create_model_from_py(blueprint, creation)
+    assert type(m).__name__ == "Xvector" and m.extracted_embedding == "near"
+    with pytest.raises(TypeError):
+        cli.create_model_from_py(str(tmp_path / "missing.py"), creation)
+
+
+class FakeModel:
+    """Stands in for a blueprint: embedding = [T, mean(feats)] so routing can be checked on CPU."""
+    calls = []
+
+    def extract_embedding(self, feats):
+        FakeModel.calls.append(("single", feats.shape[0]))
+        return torch.tensor([feats.shape[0], float(feats.mean())])
+
+    def extract_embedding_batch(self, x):
+        FakeModel.calls.append(("batch", x.shape))
+        return torch.stack([torch.tensor([f.shape[0], float(f.mean())]) for f in x])
+
+
+def test_extract_stream_buckets_by_length_and_shards():
+    rng = np.random.RandomState(0)
+    lens = [200] * 5 + [300] * 3 + [10001] + [200] * 2
+    utts = [("u{}".format(i), rng.standard_normal((t, 4)).astype(np.float32)) for i, t in enumerate(lens)]
+    out = {}
+    FakeModel.calls = []
+    n = cli.extract_stream(FakeModel(), iter(utts), lambda k, v: out.__setitem__(k, v), batch_size=4, log=lambda s: None)
+    assert n == len(utts) and set(out) == {k for k, _ in utts}
+    for k, f in utts:
+        assert out[k][0] == f.shape[0] and abs(out[k][1] - f.mean()) < 1e-6
+    kinds = [c[0] for c in FakeModel.calls]
+    assert kinds.count("single") == 1                      # only the >maxChunk utterance
+    assert ("batch", (4, 200, 4)) in FakeModel.calls       # a full bucket
+    out2 = {}
+    cli.extract_stream(FakeModel(), iter(utts), lambda k, v: out2.__setitem__(k, v), batch_size=4, shard=(1, 2), log=lambda s: None)
+    assert set(out2) == {"u{}".format(i) for i in range(1, len(utts), 2)}
+    with pytest.raises(TypeError):
+        cli.extract_stream(FakeModel(), iter([("d", np.zeros((3, 4)))]), lambda k, v: None, log=lambda s: None)
+
+
+def test_chunk_rule_matches_reference_wrapper():
+    """for_extract_embedding (framework.py:34-47): the split sizes the plugin base uses."""
+    from asv_subtools_b200.nnet.framework import for_extract_embedding
+
+    seen = []
+
+    class M(torch.nn.Module):
+        training = False
+
+        def __init__(self):
+            super().__init__()
+            self.p = torch.nn.Parameter(torch.zeros(1))
+
+        def device_for_extraction(self):
+            return torch.device("cpu")
+
+        @for_extract_embedding(maxChunk=100, isMatrix=True)
+        def extract_embedding(self, x):
+            seen.append(x.shape[1])
+            return x.mean(dim=1)
+
+    feats = np.arange(250 * 3, dtype=np.float32).reshape(250, 3)
+    e = M().extract_embedding(feats)
+    assert seen == [83, 83, 84]                            # num_split=3, split=83, remainder to the last chunk
+    assert torch.allclose(e, torch.from_numpy(feats.mean(0)), rtol=1e-6)
+
+
+@pytest.mark.timeout(120)
+def test_world_size_2_gloo_sharding_and_gather(tmp_path):
+    """N>1 host logic on CPU: two gloo ranks shard utterances i % 2, all_gather their (fake)
+    embeddings and both end with the same, correctly ordered table."""
+    script = tmp_path / "w.py"
+    script.write_text('''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from asv_subtools_b200.parallel import shard_indices, all_gather_embeddings
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+n, d = 11, 4
+idx = shard_indices(n, r, w)
+local = torch.stack([torch.full((d,), float(i)) for i in idx])
+full = all_gather_embeddings(local, n, r, w)
+assert full.shape == (n, d) and torch.equal(full[:, 0], torch.arange(n, dtype=torch.float32)), full
+print("rank", r, "ok")
+dist.destroy_process_group()
+''' % ROOT)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29617", str(script)],
+                         capture_output=True, text=True, timeout=110)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2
