@@ -6,7 +6,20 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libxvb200.so")
 
-RELU, BN = 1, 2
+RELU, BN, SIGMOID, TANH = 1, 2, 4, 8
+
+
+class TdnnArgs(C.Structure):
+    """xvb_tdnn_args_t (include/xvb200.h)."""
+    _fields_ = [("x_hi", C.c_void_p), ("x_lo", C.c_void_p), ("ldx", C.c_int64),
+                ("x2_hi", C.c_void_p), ("x2_lo", C.c_void_p), ("ldx2", C.c_int64),
+                ("w_hi", C.c_void_p), ("w_lo", C.c_void_p),
+                ("bias", C.c_void_p), ("bn_scale", C.c_void_p), ("bn_shift", C.c_void_p),
+                ("row_bias", C.c_void_p), ("utt_bias", C.c_void_p), ("ld_utt_bias", C.c_int64),
+                ("flags", C.c_int), ("context_host", C.POINTER(C.c_int)), ("ntaps", C.c_int),
+                ("y_hi", C.c_void_p), ("y_lo", C.c_void_p), ("ldy", C.c_int64),
+                ("y_f32", C.c_void_p), ("ldyf", C.c_int64),
+                ("B", C.c_int), ("T", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int)]
 MAX_TAPS = 16
 
 
@@ -42,6 +55,11 @@ SIGNATURES = {
     "xvb_tdnn_affine": (_i, [_p, _p, _i64, _p, _p, _p, _p, _p, _i, _ip, _i, _p, _p, _i64, _p, _i64, _i, _i, _i, _i, _p]),
     "xvb_tdnn_affine_simt": (_i, [_p, _i64, _p, _i, _i, _p, _p, _p, _i, _ip, _i, _p, _i64, _i, _i, _i, _i, _p]),
     "xvb_stats_pool": (_i, [_p, _i64, _i, _i, _i, _f, _p, _p, _p, _i64, _p]),
+    "xvb_stats_pool_ex": (_i, [_p, _i64, _i, _i, _i, _f, _i, _p, _p, _p, _i64, _p]),
+    "xvb_tdnn_affine_ex": (_i, [_p, _p]),
+    "xvb_plane_mean": (_i, [_p, _p, _i64, _i, _i, _i, _p, _p, _p, _i64, _p]),
+    "xvb_se_apply": (_i, [_p, _p, _i64, _p, _p, _i64, _p, _p, _p, _i64, _p, _p, _i64, _i, _i, _i, _p]),
+    "xvb_attn_stats_pool": (_i, [_p, _i64, _p, _i64, _i, _i, _i, _f, _p, _p, _p, _i64, _p]),
     "xvb_center_length_norm": (_i, [_p, _p, _p, _i64, _i, _p]),
     "xvb_column_mean": (_i, [_p, _i64, _i, _p, _p]),
     "xvb_cosine_trials": (_i, [_p, _p, _i, _p, _p, _i64, _p, _p]),

@@ -55,12 +55,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
-// tdnn_gemm.cu: the tcgen05 layer with the optional per-frame bias used by PLDA scoring.
-int tdnn_affine_impl(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, const uint16_t* w_hi,
-                     const uint16_t* w_lo, const float* bias, const float* bn_scale, const float* bn_shift,
-                     const float* row_bias, int flags, const int* context_host, int ntaps, uint16_t* y_hi,
-                     uint16_t* y_lo, int64_t ldy, float* y_f32, int64_t ldyf, int B, int T, int Cin, int Cout,
-                     void* stream);
+// tdnn_gemm.cu: the tcgen05 layer behind xvb_tdnn_affine / xvb_tdnn_affine_ex.
+int tdnn_affine_impl(const xvb_tdnn_args_t& args, void* stream);
 
 // tdnn_gemm.cu: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda).
 int make_tensor_map(CUtensorMap* m, const void* base, int esize, int rank, const unsigned long long* dims,

@@ -1,0 +1,268 @@
+// ECAPA-TDNN specific bandwidth-bound kernels (pytorch/model/ecapa_tdnn_xvector.py):
+//   * plane_mean      : mean over time of a split-plane tensor (SE_Connect's AdaptiveAvgPool1d, :100)
+//   * se_apply        : out = z * gate[b] + in  (+ next = in + out)   (SE_Connect :109-111, SE_Res2Block :149,
+//                       and the dense residual sums x+x1, x+x1+x2 of ECAPA_TDNN.extract_embedding :405-408)
+//   * attn_stats_pool : softmax over time + weighted mean / std (AttentiveStatsPool.forward :183-188) as a
+//                       single streaming pass with an online softmax (running max + rescaled sums)
+// All the dense contractions of the model run on the tcgen05 layer kernel (tdnn_gemm.cu).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace xvb {
+
+__device__ __forceinline__ void unpack8(const uint4& h, const uint4& l, float (&f)[8]) {
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    f[2 * k] = __uint_as_float(hw[k] << 16) + __uint_as_float(lw[k] << 16);
+    f[2 * k + 1] = __uint_as_float(hw[k] & 0xffff0000u) + __uint_as_float(lw[k] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ void pack8(const float (&f)[8], uint4& h, uint4& l) {
+  uint32_t hw[4], lw[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(f[2 * k], h0, l0);
+    split_bf16(f[2 * k + 1], h1, l1);
+    hw[k] = pack_bf16x2(h0, h1);
+    lw[k] = pack_bf16x2(l0, l1);
+  }
+  h = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+  l = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
+
+// ---------------------------------------------------------------- mean over T of planes
+constexpr int kPmWarps = 8;
+__global__ void __launch_bounds__(kPmWarps * 32)
+plane_mean_kernel(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __restrict__ xl, long long ldx, int T, int C,
+                  float* __restrict__ out, __nv_bfloat16* __restrict__ oh, __nv_bfloat16* __restrict__ ol, long long ldo) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + lane * 8;
+  const bool active = c < C;  // C % 8 == 0
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (active) {
+    const long long base = (long long)b * T * ldx + c;
+    for (int t = warp; t < T; t += kPmWarps) {
+      const uint4 h = *reinterpret_cast<const uint4*>(xh + base + (long long)t * ldx);
+      const uint4 l = *reinterpret_cast<const uint4*>(xl + base + (long long)t * ldx);
+      float f[8];
+      unpack8(h, l, f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += f[k];
+    }
+  }
+  __shared__ float sh[kPmWarps][32][8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sh[warp][lane][k] = acc[k];
+  __syncthreads();
+  if (warp == 0 && active) {
+    float m[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float s = 0.f;
+      for (int w = 0; w < kPmWarps; ++w) s += sh[w][lane][k];
+      m[k] = s / (float)T;
+    }
+    if (out) {
+      float* o = out + (long long)b * C + c;
+      *reinterpret_cast<float4*>(o) = make_float4(m[0], m[1], m[2], m[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(m[4], m[5], m[6], m[7]);
+    }
+    if (oh) {
+      uint4 h, l;
+      pack8(m, h, l);
+      *reinterpret_cast<uint4*>(oh + (long long)b * ldo + c) = h;
+      *reinterpret_cast<uint4*>(ol + (long long)b * ldo + c) = l;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- SE gate + residual (+ running sum)
+__global__ void se_apply_kernel(const __nv_bfloat16* __restrict__ zh, const __nv_bfloat16* __restrict__ zl, long long ldz,
+                                const __nv_bfloat16* __restrict__ ih, const __nv_bfloat16* __restrict__ il, long long ldi,
+                                const float* __restrict__ gate, __nv_bfloat16* __restrict__ oh,
+                                __nv_bfloat16* __restrict__ ol, long long ldo, __nv_bfloat16* __restrict__ nh,
+                                __nv_bfloat16* __restrict__ nl, long long ldn, long long frames, int T, int C) {
+  const int groups = C / 8;
+  const long long total = frames * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long fr = i / groups;
+    const int c = (int)(i % groups) * 8;
+    const long long b = fr / T;
+    float z[8], x[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(zh + fr * ldz + c), *reinterpret_cast<const uint4*>(zl + fr * ldz + c), z);
+    unpack8(*reinterpret_cast<const uint4*>(ih + fr * ldi + c), *reinterpret_cast<const uint4*>(il + fr * ldi + c), x);
+    const float4 g0 = *reinterpret_cast<const float4*>(gate + b * C + c);
+    const float4 g1 = *reinterpret_cast<const float4*>(gate + b * C + c + 4);
+    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = z[k] * g[k] + x[k];   // mul then add: the reference's two roundings
+    uint4 h, l;
+    pack8(o, h, l);
+    *reinterpret_cast<uint4*>(oh + fr * ldo + c) = h;
+    *reinterpret_cast<uint4*>(ol + fr * ldo + c) = l;
+    if (nh) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] += x[k];
+      pack8(o, h, l);
+      *reinterpret_cast<uint4*>(nh + fr * ldn + c) = h;
+      *reinterpret_cast<uint4*>(nl + fr * ldn + c) = l;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- attentive statistics pooling
+constexpr int kApWarps = 8;
+constexpr int kApRows = 4;
+
+struct Online {  // per channel: running max and rescaled sums of e, e*x, e*x^2
+  float m, s0, s1, s2;
+};
+__device__ __forceinline__ void online_add(Online& o, float l, float x) {
+  const float mn = fmaxf(o.m, l);
+  const float sc = expf(o.m - mn), e = expf(l - mn);
+  o.s0 = fmaf(o.s0, sc, e);
+  o.s1 = fmaf(o.s1, sc, e * x);
+  o.s2 = fmaf(o.s2, sc, e * x * x);
+  o.m = mn;
+}
+__device__ __forceinline__ void online_merge(Online& a, const Online& b) {
+  const float mn = fmaxf(a.m, b.m);
+  const float sa = expf(a.m - mn), sb = expf(b.m - mn);
+  a.s0 = a.s0 * sa + b.s0 * sb;
+  a.s1 = a.s1 * sa + b.s1 * sb;
+  a.s2 = a.s2 * sa + b.s2 * sb;
+  a.m = mn;
+}
+
+__global__ void __launch_bounds__(kApWarps * 32)
+attn_stats_pool_kernel(const float* __restrict__ logits, long long ldl, const float* __restrict__ x, long long ldx, int T,
+                       int C, float floor_, float* __restrict__ out, __nv_bfloat16* __restrict__ oh,
+                       __nv_bfloat16* __restrict__ ol, long long ldo) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + lane * 4;
+  const bool active = c < C;
+  Online st[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) st[k] = {-INFINITY, 0.f, 0.f, 0.f};
+  if (active) {
+    const float* lb = logits + (long long)b * T * ldl + c;
+    const float* xb = x + (long long)b * T * ldx + c;
+    for (int t0 = warp; t0 < T; t0 += kApWarps * kApRows) {
+      float4 lv[kApRows], xv[kApRows];
+#pragma unroll
+      for (int r = 0; r < kApRows; ++r) {
+        const int t = t0 + r * kApWarps;
+        if (t < T) {
+          lv[r] = __ldcs(reinterpret_cast<const float4*>(lb + (long long)t * ldl));
+          xv[r] = __ldcs(reinterpret_cast<const float4*>(xb + (long long)t * ldx));
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < kApRows; ++r) {
+        if (t0 + r * kApWarps < T) {
+          online_add(st[0], lv[r].x, xv[r].x);
+          online_add(st[1], lv[r].y, xv[r].y);
+          online_add(st[2], lv[r].z, xv[r].z);
+          online_add(st[3], lv[r].w, xv[r].w);
+        }
+      }
+    }
+  }
+  __shared__ Online sh[kApWarps][32][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sh[warp][lane][k] = st[k];
+  __syncthreads();
+  if (warp == 0 && active) {
+    float mu[4], sd[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      Online a = sh[0][lane][k];
+      for (int w = 1; w < kApWarps; ++w)
+        if (sh[w][lane][k].s0 > 0.f) online_merge(a, sh[w][lane][k]);
+      mu[k] = a.s1 / a.s0;
+      sd[k] = sqrtf(fmaxf(a.s2 / a.s0 - mu[k] * mu[k], floor_));   // residuals.clamp(min=1e-5), :186-187
+    }
+    float* ob = out + (long long)b * 2 * C;
+    *reinterpret_cast<float4*>(ob + c) = make_float4(mu[0], mu[1], mu[2], mu[3]);
+    *reinterpret_cast<float4*>(ob + C + c) = make_float4(sd[0], sd[1], sd[2], sd[3]);
+    if (oh) {
+      __nv_bfloat16 h[8], l[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { split_bf16(mu[k], h[k], l[k]); split_bf16(sd[k], h[4 + k], l[4 + k]); }
+      __nv_bfloat16* ph = oh + (long long)b * ldo;
+      __nv_bfloat16* pl = ol + (long long)b * ldo;
+      *reinterpret_cast<uint2*>(ph + c) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+      *reinterpret_cast<uint2*>(pl + c) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+      *reinterpret_cast<uint2*>(ph + C + c) = make_uint2(pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+      *reinterpret_cast<uint2*>(pl + C + c) = make_uint2(pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+    }
+  }
+}
+
+}  // namespace xvb
+
+using namespace xvb;
+
+extern "C" int xvb_plane_mean(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, int B, int T, int C, float* out,
+                              uint16_t* out_hi, uint16_t* out_lo, int64_t ldo, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  XVB_CHECK_ARG(x_hi && x_lo && (out || out_hi), "xvb_plane_mean: null pointer");
+  XVB_CHECK_ARG(B > 0 && T > 0 && C > 0 && C % 8 == 0 && ldx % 8 == 0 && ldx >= C && B <= 65535, "xvb_plane_mean: need C%%8==0, ldx%%8==0");
+  XVB_CHECK_ARG((out_hi != nullptr) == (out_lo != nullptr), "xvb_plane_mean: out_hi/out_lo must both be set or both NULL");
+  if (out_hi) XVB_CHECK_ARG(ldo % 8 == 0 && ldo >= C, "xvb_plane_mean: ldo must be a multiple of 8 and >= C");
+  dim3 grid((C + 255) / 256, B);
+  plane_mean_kernel<<<grid, kPmWarps * 32, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x_hi), reinterpret_cast<const __nv_bfloat16*>(x_lo), ldx, T, C, out,
+      reinterpret_cast<__nv_bfloat16*>(out_hi), reinterpret_cast<__nv_bfloat16*>(out_lo), ldo);
+  XVB_LAUNCH_CHECK();
+  return XVB_OK;
+}
+
+extern "C" int xvb_se_apply(const uint16_t* z_hi, const uint16_t* z_lo, int64_t ldz, const uint16_t* in_hi,
+                            const uint16_t* in_lo, int64_t ldin, const float* gate, uint16_t* out_hi, uint16_t* out_lo,
+                            int64_t ldout, uint16_t* next_hi, uint16_t* next_lo, int64_t ldnext, int B, int T, int C,
+                            void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  XVB_CHECK_ARG(z_hi && z_lo && in_hi && in_lo && gate && out_hi && out_lo, "xvb_se_apply: null pointer");
+  XVB_CHECK_ARG((next_hi != nullptr) == (next_lo != nullptr), "xvb_se_apply: next_hi/next_lo must both be set or both NULL");
+  XVB_CHECK_ARG(B > 0 && T > 0 && C > 0 && C % 8 == 0 && ldz % 8 == 0 && ldin % 8 == 0 && ldout % 8 == 0 &&
+                    (!next_hi || ldnext % 8 == 0), "xvb_se_apply: C and all pitches must be multiples of 8");
+  const long long frames = (long long)B * T;
+  const long long total = frames * (C / 8);
+  long long g = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 32;
+  if (g > cap) g = cap;
+  se_apply_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(z_hi), reinterpret_cast<const __nv_bfloat16*>(z_lo), ldz,
+      reinterpret_cast<const __nv_bfloat16*>(in_hi), reinterpret_cast<const __nv_bfloat16*>(in_lo), ldin, gate,
+      reinterpret_cast<__nv_bfloat16*>(out_hi), reinterpret_cast<__nv_bfloat16*>(out_lo), ldout,
+      reinterpret_cast<__nv_bfloat16*>(next_hi), reinterpret_cast<__nv_bfloat16*>(next_lo), ldnext, frames, T, C);
+  XVB_LAUNCH_CHECK();
+  return XVB_OK;
+}
+
+extern "C" int xvb_attn_stats_pool(const float* logits, int64_t ldl, const float* x, int64_t ldx, int B, int T, int C,
+                                   float floor_, float* out, uint16_t* out_hi, uint16_t* out_lo, int64_t ldo,
+                                   void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  XVB_CHECK_ARG(logits && x && out, "xvb_attn_stats_pool: null pointer");
+  XVB_CHECK_ARG(B > 0 && T > 0 && C > 0 && C % 4 == 0 && ldl % 4 == 0 && ldx % 4 == 0 && ldl >= C && ldx >= C && B <= 65535,
+                "xvb_attn_stats_pool: need C%%4==0 and pitches %%4==0");
+  XVB_CHECK_ARG((out_hi != nullptr) == (out_lo != nullptr), "xvb_attn_stats_pool: out_hi/out_lo must both be set or both NULL");
+  if (out_hi) XVB_CHECK_ARG(ldo % 4 == 0 && ldo >= 2 * C, "xvb_attn_stats_pool: ldo too small / unaligned");
+  dim3 grid((C + 127) / 128, B);
+  attn_stats_pool_kernel<<<grid, kApWarps * 32, 0, (cudaStream_t)stream>>>(
+      logits, ldl, x, ldx, T, C, floor_, out, reinterpret_cast<__nv_bfloat16*>(out_hi),
+      reinterpret_cast<__nv_bfloat16*>(out_lo), ldo);
+  XVB_LAUNCH_CHECK();
+  return XVB_OK;
+}

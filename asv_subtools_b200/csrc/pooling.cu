@@ -25,7 +25,7 @@ constexpr int kPoolNumBars = (kPoolSlabRows + kPoolBoxRows - 1) / kPoolBoxRows;
 constexpr int kPoolSmemBytes = kPoolNumBars * kPoolBoxRows * 128 * 4 + kPoolWarps * 128 * 4 + 128;
 
 __global__ void __launch_bounds__(kPoolWarps * 32, 2)
-stats_pool_tma_kernel(const __grid_constant__ CUtensorMap map_x, int T, int C, float eps, float* __restrict__ out,
+stats_pool_tma_kernel(const __grid_constant__ CUtensorMap map_x, int T, int C, float eps, int mode, float* __restrict__ out,
                       __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, long long ldo) {
   extern __shared__ __align__(128) uint8_t pool_smem[];
   float* slab = reinterpret_cast<float*>(pool_smem);                                  // [rows][128]
@@ -110,9 +110,16 @@ stats_pool_tma_kernel(const __grid_constant__ CUtensorMap map_x, int T, int C, f
   }
 
   if (warp == 0 && active) {
-    const float invT = 1.f / (float)T;
-    float sd[4] = {sqrtf(fmaxf(run_m2.x * invT, eps)), sqrtf(fmaxf(run_m2.y * invT, eps)),
-                   sqrtf(fmaxf(run_m2.z * invT, eps)), sqrtf(fmaxf(run_m2.w * invT, eps))};  // biased var, clamp
+    float sd[4];
+    if (mode == 0) {  // StatisticsPooling: sqrt(clamp(biased var, eps))  (pooling.py:62-66)
+      const float invT = 1.f / (float)T;
+      sd[0] = sqrtf(fmaxf(run_m2.x * invT, eps)); sd[1] = sqrtf(fmaxf(run_m2.y * invT, eps));
+      sd[2] = sqrtf(fmaxf(run_m2.z * invT, eps)); sd[3] = sqrtf(fmaxf(run_m2.w * invT, eps));
+    } else {          // ECAPA global context: sqrt(unbiased var + eps)  (ecapa_tdnn_xvector.py:177-178; T=1 -> NaN as there)
+      const float invT1 = 1.f / (float)(T - 1);
+      sd[0] = sqrtf(run_m2.x * invT1 + eps); sd[1] = sqrtf(run_m2.y * invT1 + eps);
+      sd[2] = sqrtf(run_m2.z * invT1 + eps); sd[3] = sqrtf(run_m2.w * invT1 + eps);
+    }
     float mu[4] = {run_mean.x, run_mean.y, run_mean.z, run_mean.w};
     float* ob = out + (long long)b * 2 * C;
     *reinterpret_cast<float4*>(ob + c) = make_float4(mu[0], mu[1], mu[2], mu[3]);
@@ -137,9 +144,15 @@ using namespace xvb;
 
 extern "C" int xvb_stats_pool(const float* x, int64_t ldx, int B, int T, int C, float eps, float* out, uint16_t* out_hi,
                               uint16_t* out_lo, int64_t ldo, void* stream) {
+  return xvb_stats_pool_ex(x, ldx, B, T, C, eps, 0, out, out_hi, out_lo, ldo, stream);
+}
+
+extern "C" int xvb_stats_pool_ex(const float* x, int64_t ldx, int B, int T, int C, float eps, int mode, float* out,
+                                 uint16_t* out_hi, uint16_t* out_lo, int64_t ldo, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
   XVB_CHECK_ARG(x && out, "xvb_stats_pool: null pointer");
+  XVB_CHECK_ARG(mode == 0 || mode == 1, "xvb_stats_pool_ex: mode must be 0 (biased, clamp) or 1 (unbiased, +eps)");
   XVB_CHECK_ARG(B > 0 && T > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0 && ldx >= C, "xvb_stats_pool: need C%%4==0, ldx%%4==0 (C=%d ldx=%lld)", C, (long long)ldx);
   XVB_CHECK_ARG((out_hi != nullptr) == (out_lo != nullptr), "xvb_stats_pool: out_hi/out_lo must both be set or both NULL");
   if (out_hi) XVB_CHECK_ARG(ldo >= 2 * C && ldo % 4 == 0, "xvb_stats_pool: ldo=%lld too small / unaligned", (long long)ldo);
@@ -158,7 +171,7 @@ extern "C" int xvb_stats_pool(const float* x, int64_t ldx, int B, int T, int C, 
   }
   dim3 grid((C + 127) / 128, B);
   stats_pool_tma_kernel<<<grid, kPoolWarps * 32, kPoolSmemBytes, (cudaStream_t)stream>>>(
-      map, T, C, eps, out, reinterpret_cast<__nv_bfloat16*>(out_hi), reinterpret_cast<__nv_bfloat16*>(out_lo), ldo);
+      map, T, C, eps, mode, out, reinterpret_cast<__nv_bfloat16*>(out_hi), reinterpret_cast<__nv_bfloat16*>(out_lo), ldo);
   XVB_LAUNCH_CHECK();
   return XVB_OK;
 }

@@ -111,8 +111,12 @@ static int matmul_nt(const float* A, int64_t Ne, const float* Bm, int64_t Nt, in
   rc = xvb_split_f32(Bm, Nt, D, D, b_hi, b_lo, ldp, s);
   if (rc) return rc;
   const int ctx0 = 0;
-  return tdnn_affine_impl(a_hi, a_lo, ldp, b_hi, b_lo, col_bias, nullptr, nullptr, row_bias, 0, &ctx0, 1, out_hi,
-                          out_lo, ldplane, out, ldo, (int)Ne, 1, D, (int)Nt, s);
+  xvb_tdnn_args_t g{};
+  g.x_hi = a_hi; g.x_lo = a_lo; g.ldx = ldp; g.w_hi = b_hi; g.w_lo = b_lo;
+  g.bias = col_bias; g.row_bias = row_bias; g.context_host = &ctx0; g.ntaps = 1;
+  g.y_hi = out_hi; g.y_lo = out_lo; g.ldy = ldplane; g.y_f32 = out; g.ldyf = ldo;
+  g.B = (int)Ne; g.T = 1; g.Cin = D; g.Cout = (int)Nt;
+  return tdnn_affine_impl(g, s);
 }
 
 }  // namespace xvb

@@ -48,6 +48,9 @@ struct TdnnGemmParams {
   const float* scale;
   const float* shift;
   const float* row_bias;  // per-frame additive term (PLDA row term), may be NULL
+  const float* utt_bias;  // per-utterance x column additive term (B, ld_utt), may be NULL
+  long long ld_utt;
+  int num_src;            // 1, or 2: a second A source accumulated with the same weights (W.(x + x2))
   __nv_bfloat16* y_hi;
   __nv_bfloat16* y_lo;
   long long ldy;
@@ -74,6 +77,7 @@ struct GemmCfg {
 template <int BLOCK_N, int kCta>
 __global__ void __launch_bounds__(kNumThreads, 1)
 tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                        const __grid_constant__ CUtensorMap map_a2_hi, const __grid_constant__ CUtensorMap map_a2_lo,
                         const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                         const __grid_constant__ CUtensorMap map_y_hi, const __grid_constant__ CUtensorMap map_y_lo,
                         const __grid_constant__ CUtensorMap map_y_f32, const __grid_constant__ TdnnGemmParams p) {
@@ -121,7 +125,7 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int num_kblk = p.ntaps * p.num_cblk;
+  const int num_kblk = p.num_src * p.ntaps * p.num_cblk;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -132,6 +136,9 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
         const int m_blk = (tile / p.num_n_blk) * kCta + (int)cta_rank, n_blk = tile % p.num_n_blk;
         const int b0 = (m_blk / p.num_t_blk) * p.Bb, t0 = (m_blk % p.num_t_blk) * p.Tb;  // may be fully out of
         const int n0 = n_blk * BLOCK_N + (int)cta_rank * Cfg::kBRows;                     // range: TMA zero-fills
+        for (int src = 0; src < p.num_src; ++src) {
+        const CUtensorMap* ma_hi = src == 0 ? &map_a_hi : &map_a2_hi;
+        const CUtensorMap* ma_lo = src == 0 ? &map_a_lo : &map_a2_lo;
         for (int tap = 0; tap < p.ntaps; ++tap) {
           const int tt = t0 + p.ctx[tap];
           for (int cb = 0; cb < p.num_cblk; ++cb) {
@@ -140,21 +147,22 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
             const int kw = tap * p.cin_p16 + cb * kBlockK;
             if constexpr (kCta == 1) {
               mbar_expect_tx(&full_bar[stage], kStageBytes);
-              tma_load_3d(s, &map_a_hi, &full_bar[stage], cb * kBlockK, tt, b0);
-              tma_load_3d(s + kABytes, &map_a_lo, &full_bar[stage], cb * kBlockK, tt, b0);
+              tma_load_3d(s, ma_hi, &full_bar[stage], cb * kBlockK, tt, b0);
+              tma_load_3d(s + kABytes, ma_lo, &full_bar[stage], cb * kBlockK, tt, b0);
               tma_load_2d(s + 2 * kABytes, &map_w_hi, &full_bar[stage], kw, n0);
               tma_load_2d(s + 2 * kABytes + kBBytes, &map_w_lo, &full_bar[stage], kw, n0);
             } else {
               // both CTAs' bytes complete on the LEADER's barrier (peer-bit-masked address)
               if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes);
               else mbar_arrive_cluster(&full_bar[stage], 0);
-              tma_load_3d_2sm(s, &map_a_hi, &full_bar[stage], cb * kBlockK, tt, b0);
-              tma_load_3d_2sm(s + kABytes, &map_a_lo, &full_bar[stage], cb * kBlockK, tt, b0);
+              tma_load_3d_2sm(s, ma_hi, &full_bar[stage], cb * kBlockK, tt, b0);
+              tma_load_3d_2sm(s + kABytes, ma_lo, &full_bar[stage], cb * kBlockK, tt, b0);
               tma_load_2d_2sm(s + 2 * kABytes, &map_w_hi, &full_bar[stage], kw, n0);
               tma_load_2d_2sm(s + 2 * kABytes + kBBytes, &map_w_lo, &full_bar[stage], kw, n0);
             }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
+        }
         }
       }
     }
@@ -213,7 +221,10 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     const bool leader = etid == 0;
     const bool relu = (p.flags & XVB_RELU) != 0;
     const bool bn = (p.flags & XVB_BN) != 0;
+    const bool act_sigmoid = (p.flags & XVB_SIGMOID) != 0;
+    const bool act_tanh = (p.flags & XVB_TANH) != 0;
     const bool planes = p.y_hi != nullptr;
+    const bool f32o = p.y_f32 != nullptr;
     uint32_t it = 0;
     for (int tile = tile_first; tile < p.num_tiles; tile += tile_step, ++it) {
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
@@ -223,6 +234,7 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
       const bool valid = (b < p.B) && (t < p.T);
       const int n0 = n_blk * BLOCK_N;
       const float rbias = (p.row_bias && valid) ? __ldg(p.row_bias + (long long)b * p.T + t) : 0.f;
+      const float* ub = (p.utt_bias && valid) ? p.utt_bias + (long long)b * p.ld_utt + n0 + half * 16 : nullptr;
       // stage this tile's per-column parameters (double-buffered by accumulator stage; the
       // barrier also orders reuse: nobody can be two tiles ahead of the slowest epilogue thread)
       float* prm = param_base + acc * (3 * 256);
@@ -249,20 +261,26 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const float4 bb = pb[g], ss = ps[g], tt = pt[g];
-          float x0 = __uint_as_float(v[4 * g + 0]) + rbias + bb.x;
-          float x1 = __uint_as_float(v[4 * g + 1]) + rbias + bb.y;
-          float x2 = __uint_as_float(v[4 * g + 2]) + rbias + bb.z;
-          float x3 = __uint_as_float(v[4 * g + 3]) + rbias + bb.w;
+          float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ub && n0 + pc + 4 * g < p.Cout) u = __ldg(reinterpret_cast<const float4*>(ub + ch * 32) + g);
+          float x0 = __uint_as_float(v[4 * g + 0]) + rbias + bb.x + u.x;
+          float x1 = __uint_as_float(v[4 * g + 1]) + rbias + bb.y + u.y;
+          float x2 = __uint_as_float(v[4 * g + 2]) + rbias + bb.z + u.z;
+          float x3 = __uint_as_float(v[4 * g + 3]) + rbias + bb.w + u.w;
           if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
-          f[4 * g + 0] = fmaf(x0, ss.x, tt.x);
-          f[4 * g + 1] = fmaf(x1, ss.y, tt.y);
-          f[4 * g + 2] = fmaf(x2, ss.z, tt.z);
-          f[4 * g + 3] = fmaf(x3, ss.w, tt.w);
+          x0 = fmaf(x0, ss.x, tt.x); x1 = fmaf(x1, ss.y, tt.y); x2 = fmaf(x2, ss.z, tt.z); x3 = fmaf(x3, ss.w, tt.w);
+          if (act_tanh) { x0 = tanhf(x0); x1 = tanhf(x1); x2 = tanhf(x2); x3 = tanhf(x3); }
+          if (act_sigmoid) {
+            x0 = 1.f / (1.f + expf(-x0)); x1 = 1.f / (1.f + expf(-x1));
+            x2 = 1.f / (1.f + expf(-x2)); x3 = 1.f / (1.f + expf(-x3));
+          }
+          f[4 * g + 0] = x0; f[4 * g + 1] = x1; f[4 * g + 2] = x2; f[4 * g + 3] = x3;
         }
-        // the previous TMA store must have finished reading the slab
-        if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int n = n0 + ch * 32;
         if (planes) {
+          // the previous TMA store must have finished reading the slab
+          if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
           // two slabs of 64-byte rows (SWIZZLE_64B): 16-byte chunk c of row r sits at c ^ ((r>>1)&3)
           uint8_t* sh = slab_base + row * 64;
           uint8_t* sl = slab_base + 8192 + row * 64;
@@ -282,7 +300,17 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
             *reinterpret_cast<uint4*>(sh + ((c ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
             *reinterpret_cast<uint4*>(sl + ((c ^ sw) << 4)) = make_uint4(l[0], l[1], l[2], l[3]);
           }
-        } else {
+          fence_proxy_async();
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          if (leader) {
+            tma_store_3d(&map_y_hi, slab_base, n, t0, b0);
+            tma_store_3d(&map_y_lo, slab_base + 8192, n, t0, b0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        if (f32o) {
+          if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
           // one slab of 128-byte rows (SWIZZLE_128B): chunk c of row r sits at c ^ (r & 7)
           uint8_t* sf = slab_base + row * 128;
           const int sw = row & 7;
@@ -291,18 +319,12 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
             const int c = half * 4 + g;
             *reinterpret_cast<float4*>(sf + ((c ^ sw) << 4)) = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
           }
-        }
-        fence_proxy_async();
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-        if (leader) {
-          const int n = n0 + ch * 32;
-          if (planes) {
-            tma_store_3d(&map_y_hi, slab_base, n, t0, b0);
-            tma_store_3d(&map_y_lo, slab_base + 8192, n, t0, b0);
-          } else {
+          fence_proxy_async();
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          if (leader) {
             tma_store_3d(&map_y_f32, slab_base, n, t0, b0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       };
 
@@ -441,8 +463,9 @@ static int make_out_map(CUtensorMap* m, const void* base, int esize, int C, int 
 }
 
 template <int BLOCK_N, int kCta>
-static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const void* w_hi, const void* w_lo,
-                       TdnnGemmParams& p, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& ma2_hi,
+                       const CUtensorMap& ma2_lo, const void* w_hi, const void* w_lo, TdnnGemmParams& p,
+                       cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, kCta>;
   CUtensorMap mw_hi, mw_lo;
   const long long K = (long long)p.ntaps * p.cin_p16;
@@ -485,8 +508,8 @@ static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  XVB_CUDA(cudaLaunchKernelEx(&cfg, tdnn_gemm_bf16x3_kernel<BLOCK_N, kCta>, ma_hi, ma_lo, mw_hi, mw_lo, my_hi, my_lo,
-                              my_f32, p));
+  XVB_CUDA(cudaLaunchKernelEx(&cfg, tdnn_gemm_bf16x3_kernel<BLOCK_N, kCta>, ma_hi, ma_lo, ma2_hi, ma2_lo, mw_hi, mw_lo,
+                              my_hi, my_lo, my_f32, p));
   XVB_LAUNCH_CHECK();
   return XVB_OK;
 }
@@ -495,26 +518,28 @@ static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const
 
 using namespace xvb;
 
-int xvb::tdnn_affine_impl(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, const uint16_t* w_hi,
-                          const uint16_t* w_lo, const float* bias, const float* bn_scale, const float* bn_shift,
-                          const float* row_bias, int flags, const int* context_host, int ntaps, uint16_t* y_hi,
-                          uint16_t* y_lo, int64_t ldy, float* y_f32, int64_t ldyf, int B, int T, int Cin, int Cout,
-                          void* stream) {
+int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
-  XVB_CHECK_ARG(x_hi && x_lo && w_hi && w_lo, "xvb_tdnn_affine: null operand pointer");
+  const int B = a.B, T = a.T, Cin = a.Cin, Cout = a.Cout, ntaps = a.ntaps;
+  XVB_CHECK_ARG(a.x_hi && a.x_lo && a.w_hi && a.w_lo, "xvb_tdnn_affine: null operand pointer");
   XVB_CHECK_ARG(B > 0 && T > 0 && Cin > 0 && Cout > 0, "xvb_tdnn_affine: bad shape B=%d T=%d Cin=%d Cout=%d", B, T, Cin, Cout);
-  XVB_CHECK_ARG(ntaps >= 1 && ntaps <= XVB_MAX_TAPS && context_host, "xvb_tdnn_affine: ntaps=%d out of range", ntaps);
-  XVB_CHECK_ARG(ldx % 8 == 0 && ldx >= Cin, "xvb_tdnn_affine: ldx=%lld must be a multiple of 8 and >= Cin", (long long)ldx);
-  XVB_CHECK_ARG((y_hi != nullptr) == (y_lo != nullptr), "xvb_tdnn_affine: y_hi/y_lo must both be set or both NULL");
-  XVB_CHECK_ARG((y_hi != nullptr) != (y_f32 != nullptr), "xvb_tdnn_affine: request exactly one of plane output / fp32 output");
-  if (y_hi) XVB_CHECK_ARG(ldy % 8 == 0 && Cout % 8 == 0 && ldy >= Cout, "xvb_tdnn_affine: plane output needs ldy%%8==0, Cout%%8==0");
-  if (y_f32) XVB_CHECK_ARG(ldyf % 4 == 0 && Cout % 4 == 0 && ldyf >= Cout, "xvb_tdnn_affine: fp32 output needs ldyf%%4==0, Cout%%4==0");
-  XVB_CHECK_ARG(!(flags & XVB_BN) || (bn_scale && bn_shift), "xvb_tdnn_affine: XVB_BN without scale/shift");
-  XVB_CHECK_ARG(((uintptr_t)x_hi | (uintptr_t)x_lo | (uintptr_t)w_hi | (uintptr_t)w_lo | (uintptr_t)y_hi |
-                 (uintptr_t)y_lo | (uintptr_t)y_f32) % 16 == 0, "xvb_tdnn_affine: pointers must be 16-byte aligned");
+  XVB_CHECK_ARG(ntaps >= 1 && ntaps <= XVB_MAX_TAPS && a.context_host, "xvb_tdnn_affine: ntaps=%d out of range", ntaps);
+  XVB_CHECK_ARG(a.ldx % 8 == 0 && a.ldx >= Cin, "xvb_tdnn_affine: ldx=%lld must be a multiple of 8 and >= Cin", (long long)a.ldx);
+  XVB_CHECK_ARG((a.x2_hi != nullptr) == (a.x2_lo != nullptr), "xvb_tdnn_affine: x2_hi/x2_lo must both be set or both NULL");
+  if (a.x2_hi) XVB_CHECK_ARG(a.ldx2 % 8 == 0 && a.ldx2 >= Cin, "xvb_tdnn_affine: ldx2=%lld must be a multiple of 8 and >= Cin", (long long)a.ldx2);
+  XVB_CHECK_ARG((a.y_hi != nullptr) == (a.y_lo != nullptr), "xvb_tdnn_affine: y_hi/y_lo must both be set or both NULL");
+  XVB_CHECK_ARG(a.y_hi || a.y_f32, "xvb_tdnn_affine: no output requested");
+  if (a.y_hi) XVB_CHECK_ARG(a.ldy % 8 == 0 && a.ldy >= Cout, "xvb_tdnn_affine: plane output needs ldy%%8==0 and ldy>=Cout");
+  if (a.y_f32) XVB_CHECK_ARG(a.ldyf % 4 == 0 && a.ldyf >= Cout, "xvb_tdnn_affine: fp32 output needs ldyf%%4==0 and ldyf>=Cout");
+  XVB_CHECK_ARG(!(a.flags & XVB_BN) || (a.bn_scale && a.bn_shift), "xvb_tdnn_affine: XVB_BN without scale/shift");
+  if (a.utt_bias) XVB_CHECK_ARG(a.ld_utt_bias % 4 == 0 && a.ld_utt_bias >= Cout && Cout % 4 == 0 && (uintptr_t)a.utt_bias % 16 == 0,
+                                "xvb_tdnn_affine: utt_bias needs ld%%4==0, Cout%%4==0, 16-byte alignment");
+  XVB_CHECK_ARG(((uintptr_t)a.x_hi | (uintptr_t)a.x_lo | (uintptr_t)a.x2_hi | (uintptr_t)a.x2_lo | (uintptr_t)a.w_hi |
+                 (uintptr_t)a.w_lo | (uintptr_t)a.y_hi | (uintptr_t)a.y_lo | (uintptr_t)a.y_f32) % 16 == 0,
+                "xvb_tdnn_affine: pointers must be 16-byte aligned");
   for (int i = 1; i < ntaps; ++i)
-    XVB_CHECK_ARG(context_host[i] > context_host[i - 1], "xvb_tdnn_affine: context must be strictly increasing (components.py:34-36)");
+    XVB_CHECK_ARG(a.context_host[i] > a.context_host[i - 1], "xvb_tdnn_affine: context must be strictly increasing (components.py:34-36)");
 
   TdnnGemmParams p{};
   p.B = B; p.T = T; p.Cin = Cin; p.Cout = Cout;
@@ -524,33 +549,46 @@ int xvb::tdnn_affine_impl(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ld
   p.ntaps = ntaps;
   p.cin_p16 = (int)round_up(Cin, 16);
   p.num_cblk = (Cin + kBlockK - 1) / kBlockK;
-  for (int i = 0; i < ntaps; ++i) p.ctx[i] = context_host[i];
-  p.flags = flags;
-  p.bias = bias; p.scale = bn_scale; p.shift = bn_shift; p.row_bias = row_bias;
-  p.y_hi = reinterpret_cast<__nv_bfloat16*>(y_hi);
-  p.y_lo = reinterpret_cast<__nv_bfloat16*>(y_lo);
-  p.ldy = ldy; p.y_f32 = y_f32; p.ldyf = ldyf;
+  for (int i = 0; i < ntaps; ++i) p.ctx[i] = a.context_host[i];
+  p.flags = a.flags;
+  p.bias = a.bias; p.scale = a.bn_scale; p.shift = a.bn_shift; p.row_bias = a.row_bias;
+  p.utt_bias = a.utt_bias; p.ld_utt = a.ld_utt_bias;
+  p.num_src = a.x2_hi ? 2 : 1;
+  p.y_hi = reinterpret_cast<__nv_bfloat16*>(a.y_hi);
+  p.y_lo = reinterpret_cast<__nv_bfloat16*>(a.y_lo);
+  p.ldy = a.ldy; p.y_f32 = a.y_f32; p.ldyf = a.ldyf;
 
-  CUtensorMap ma_hi, ma_lo;
-  rc = make_frame_map(&ma_hi, x_hi, Cin, T, B, ldx, p.Tb, p.Bb);
-  if (rc) return rc;
-  rc = make_frame_map(&ma_lo, x_lo, Cin, T, B, ldx, p.Tb, p.Bb);
-  if (rc) return rc;
+  CUtensorMap ma_hi, ma_lo, ma2_hi, ma2_lo;
+  if ((rc = make_frame_map(&ma_hi, a.x_hi, Cin, T, B, a.ldx, p.Tb, p.Bb))) return rc;
+  if ((rc = make_frame_map(&ma_lo, a.x_lo, Cin, T, B, a.ldx, p.Tb, p.Bb))) return rc;
+  if (a.x2_hi) {
+    if ((rc = make_frame_map(&ma2_hi, a.x2_hi, Cin, T, B, a.ldx2, p.Tb, p.Bb))) return rc;
+    if ((rc = make_frame_map(&ma2_lo, a.x2_lo, Cin, T, B, a.ldx2, p.Tb, p.Bb))) return rc;
+  } else {
+    ma2_hi = ma_hi; ma2_lo = ma_lo;  // unused
+  }
 
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  // Wide N tiles when there are enough M tiles to fill the machine, narrow ones for the
-  // segment-level layers (M = B rows) so that more SMs get a tile.
+  // Wide N tiles (CTA pairs) when there are enough M tiles to fill the machine, narrow ones for
+  // the segment-level layers (M = B rows) so that more SMs get a tile.
   const long long m_tiles = (long long)p.num_t_blk * p.num_b_blk;
   const int sms = sm_count();
   const int mode = gemm_cta_mode();
+  const void* w_hi = a.w_hi;
+  const void* w_lo = a.w_lo;
   if (mode == 2 && Cout >= 256 && m_tiles * ((Cout + 255) / 256) >= sms)
-    return launch_gemm<256, 2>(ma_hi, ma_lo, w_hi, w_lo, p, s);
+    return launch_gemm<256, 2>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
   if (mode == 2 && Cout >= 128 && m_tiles * ((Cout + 127) / 128) >= sms)
-    return launch_gemm<128, 2>(ma_hi, ma_lo, w_hi, w_lo, p, s);
-  if (Cout >= 256 && m_tiles * ((Cout + 255) / 256) >= sms) return launch_gemm<256, 1>(ma_hi, ma_lo, w_hi, w_lo, p, s);
-  if (Cout >= 128 && m_tiles * ((Cout + 127) / 128) >= sms) return launch_gemm<128, 1>(ma_hi, ma_lo, w_hi, w_lo, p, s);
-  if (Cout >= 64 && m_tiles * ((Cout + 63) / 64) >= sms / 2) return launch_gemm<64, 1>(ma_hi, ma_lo, w_hi, w_lo, p, s);
-  return launch_gemm<32, 1>(ma_hi, ma_lo, w_hi, w_lo, p, s);
+    return launch_gemm<128, 2>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
+  if (Cout >= 256 && m_tiles * ((Cout + 255) / 256) >= sms) return launch_gemm<256, 1>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
+  if (Cout >= 128 && m_tiles * ((Cout + 127) / 128) >= sms) return launch_gemm<128, 1>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
+  if (Cout >= 64 && m_tiles * ((Cout + 63) / 64) >= sms / 2) return launch_gemm<64, 1>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
+  return launch_gemm<32, 1>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
+}
+
+extern "C" int xvb_tdnn_affine_ex(const xvb_tdnn_args_t* args, void* stream) {
+  XVB_CHECK_ARG(args, "xvb_tdnn_affine_ex: null args");
+  return tdnn_affine_impl(*args, stream);
 }
 
 extern "C" int xvb_tdnn_affine(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, const uint16_t* w_hi,
@@ -558,6 +596,11 @@ extern "C" int xvb_tdnn_affine(const uint16_t* x_hi, const uint16_t* x_lo, int64
                                int flags, const int* context_host, int ntaps, uint16_t* y_hi, uint16_t* y_lo,
                                int64_t ldy, float* y_f32, int64_t ldyf, int B, int T, int Cin, int Cout,
                                void* stream) {
-  return tdnn_affine_impl(x_hi, x_lo, ldx, w_hi, w_lo, bias, bn_scale, bn_shift, nullptr, flags, context_host, ntaps,
-                          y_hi, y_lo, ldy, y_f32, ldyf, B, T, Cin, Cout, stream);
+  xvb_tdnn_args_t a{};
+  a.x_hi = x_hi; a.x_lo = x_lo; a.ldx = ldx; a.w_hi = w_hi; a.w_lo = w_lo;
+  a.bias = bias; a.bn_scale = bn_scale; a.bn_shift = bn_shift; a.flags = flags;
+  a.context_host = context_host; a.ntaps = ntaps;
+  a.y_hi = y_hi; a.y_lo = y_lo; a.ldy = ldy; a.y_f32 = y_f32; a.ldyf = ldyf;
+  a.B = B; a.T = T; a.Cin = Cin; a.Cout = Cout;
+  return tdnn_affine_impl(a, stream);
 }

@@ -1,0 +1,254 @@
+# -*- coding:utf-8 -*-
+"""ECAPA-TDNN (SE-Res2Block + attentive statistics pooling) blueprint for the B200 path -- drop-in
+for pytorch/model/ecapa_tdnn_xvector.py.
+
+Same constructor signature, creation string and state_dict keys as the reference
+(`layerN.conv_relu_bn1.affine.weight`, `layerN.res2net_block.blocks.i.affine.weight` (128,128,2d+1
+with the masked taps), `layerN.se.se.1/3.weight`, `mfa.*`, `stats.attention.0/2/4.*`,
+`bn_stats.*`, `fc2.*`; ecapa_tdnn_xvector.py:201-357) and the same `extract_embedding()` semantics
+(:403-426).  Every contraction runs on the tcgen05 layer kernel; what the reference does with
+chunk/cat/expand copies is expressed through channel-slice views instead:
+
+  * Res2Net (:61-75): block i reads chunk i+1 of the 1024-channel tensor and, for i>=1, the previous
+    block's output as a SECOND A source accumulated into the same TMEM accumulator
+    (W.(sp + spx[i+1]) = W.sp + W.spx[i+1]) -- no add kernel, no chunk/cat copies;
+  * SE (:97-111) = plane_mean -> two M=B GEMMs (ReLU, sigmoid epilogues) -> se_apply, which also
+    writes the block output straight into its slot of the (B,T,3072) MFA input and the running sum
+    x+x1(+x2) that feeds the next block (:405-409);
+  * attentive pooling (:173-188): the (B,4608,T) concat is never built -- the time-constant
+    [mean,std] part of the first conv becomes a per-utterance bias (a (B,3072)x(3072,128) GEMM),
+    the softmax over T and the weighted moments are one streaming online-softmax pass;
+  * bn_stats (:412) is folded into fc2's weights at build time.
+"""
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+
+from asv_subtools_b200 import ops  # noqa: E402
+from asv_subtools_b200.nnet import ReluBatchNormTdnnLayer, TopVirtualNnet  # noqa: E402
+from asv_subtools_b200.nnet.components import fold_batchnorm  # noqa: E402
+
+
+def _merge(defaults, given):
+    """The subset of utils.assign_params_dict (utils.py:319-356) the blueprint needs: recursive
+    override of known keys."""
+    out = dict(defaults)
+    for k, v in (given or {}).items():
+        if k in out and isinstance(out[k], dict) and isinstance(v, dict):
+            out[k] = _merge(out[k], v)
+        else:
+            out[k] = v
+    return out
+
+
+class Res2NetBlock(nn.Module):
+    def __init__(self, in_channels, out_channels, scale=8, kernel_size=3, dilation=1, bn_params={}):
+        super().__init__()
+        assert in_channels % scale == 0 and out_channels % scale == 0 and scale > 1
+        width = in_channels // scale
+        half = kernel_size // 2
+        self.context = [i for i in range(-half * dilation, half * dilation + 1, dilation)]
+        self.blocks = nn.ModuleList([ReluBatchNormTdnnLayer(width, out_channels // scale, self.context, **bn_params)
+                                     for _ in range(scale - 1)])
+        self.scale = scale
+        self.width = width
+
+
+class SE_Connect(nn.Module):
+    def __init__(self, channels, bottleneck=128):
+        super().__init__()
+        self.se = nn.Sequential(nn.AdaptiveAvgPool1d(1), nn.Conv1d(channels, bottleneck, kernel_size=1), nn.ReLU(),
+                                nn.Conv1d(bottleneck, channels, kernel_size=1), nn.Sigmoid())
+
+
+class SE_Res2Block(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size=3, dilation=1, scale=8, bn_params={}):
+        super().__init__()
+        if in_channels != out_channels:
+            raise NotImplementedError("B200 SE_Res2Block implements in_channels == out_channels (no shortcut conv)")
+        width = int(math.floor(in_channels / scale))
+        self.conv_relu_bn1 = ReluBatchNormTdnnLayer(in_channels, width * scale, **bn_params)
+        self.res2net_block = Res2NetBlock(width * scale, width * scale, scale=scale, kernel_size=kernel_size,
+                                          dilation=dilation, bn_params=bn_params)
+        self.conv_relu_bn2 = ReluBatchNormTdnnLayer(in_channels, width * scale, **bn_params)
+        self.se = SE_Connect(out_channels)
+        self.shortcut = None
+
+
+class AttentiveStatsPool(nn.Module):
+    def __init__(self, in_dim, bottleneck_dim=128, time_attention=False, bn={}):
+        super().__init__()
+        if not time_attention:
+            raise NotImplementedError("B200 AttentiveStatsPool implements time_attention=True (the c1024 recipe)")
+        self.in_dim, self.time_attention = in_dim, time_attention
+        self.attention = nn.Sequential(nn.Conv1d(in_dim * 3, bottleneck_dim, kernel_size=1), nn.ReLU(),
+                                       nn.BatchNorm1d(bottleneck_dim, **bn), nn.Tanh(),
+                                       nn.Conv1d(bottleneck_dim, in_dim, kernel_size=1), nn.Softmax(dim=2))
+
+
+class ECAPA_TDNN(TopVirtualNnet):
+    def init(self, inputs_dim, num_targets, aug_dropout=0., tail_dropout=0., training=True,
+             extracted_embedding="near", mixup=False, mixup_alpha=1.0, pooling="ecpa-attentive", pooling_params={},
+             ecapa_params={}, fc1=False, fc1_params={}, fc2_params={},
+             margin_loss=True, margin_loss_params={}, use_step=False, step_params={}, transfer_from="softmax_loss"):
+        default_ecapa = {"channels": 1024, "embd_dim": 192, "mfa_conv": 1536,
+                         "bn_params": {"momentum": 0.5, "affine": True, "track_running_stats": True}}
+        default_pool = {"hidden_size": 128, "time_attention": True, "stddev": True}
+        default_fc = {"nonlinearity": "relu", "nonlinearity_params": {"inplace": True}, "bn-relu": False, "bn": True,
+                      "bn_params": {"momentum": 0.5, "affine": True, "track_running_stats": True}}
+        if pooling != "ecpa-attentive":
+            raise NotImplementedError("B200 ECAPA implements pooling='ecpa-attentive' (the reference default)")
+        if fc1:
+            raise NotImplementedError("B200 ECAPA implements fc1=False (the c1024 recipe)")
+        ecapa_params = _merge(default_ecapa, ecapa_params)
+        pooling_params = _merge(default_pool, pooling_params)
+        fc2_params = _merge(default_fc, fc2_params)
+        self.inputs_dim = inputs_dim
+        self.use_step, self.step_params = use_step, step_params
+        self.extracted_embedding = extracted_embedding
+        self.embd_dim = ecapa_params["embd_dim"]
+        channels, mfa_conv = ecapa_params["channels"], ecapa_params["mfa_conv"]
+        self.layer1 = ReluBatchNormTdnnLayer(inputs_dim, channels, [-2, -1, 0, 1, 2], **ecapa_params)
+        self.layer2 = SE_Res2Block(channels, channels, kernel_size=3, dilation=2, scale=8, bn_params=ecapa_params)
+        self.layer3 = SE_Res2Block(channels, channels, kernel_size=3, dilation=3, scale=8, bn_params=ecapa_params)
+        self.layer4 = SE_Res2Block(channels, channels, kernel_size=3, dilation=4, scale=8, bn_params=ecapa_params)
+        self.mfa = ReluBatchNormTdnnLayer(channels * 3, mfa_conv, **ecapa_params)
+        self.stats = AttentiveStatsPool(mfa_conv, pooling_params["hidden_size"], pooling_params["time_attention"])
+        self.bn_stats = nn.BatchNorm1d(mfa_conv * 2, **ecapa_params["bn_params"])
+        self.fc1 = None
+        self.fc2 = ReluBatchNormTdnnLayer(mfa_conv * 2, self.embd_dim, **fc2_params)
+        self.transform_keys = ["layer1", "layer2", "layer3", "layer4", "stats", "mfa", "bn_stats", "fc1", "fc2", "loss"]
+        if margin_loss and transfer_from == "softmax_loss":
+            self.rename_transform_keys = {"loss.affine.weight": "loss.weight"}
+
+    def build_extractor(self):
+        if self.extracted_embedding not in ("near", "near_affine"):
+            if self.extracted_embedding == "far":
+                raise AssertionError("extracted_embedding='far' needs fc1 (ecapa_tdnn_xvector.py:415-416)")
+            raise TypeError("Expected far or near position, but got {}".format(self.extracted_embedding))
+        return EcapaExtractor(self, self.device_for_extraction())
+
+
+class _Layer:
+    """Device-side packed parameters of one TDNN / 1x1-conv layer."""
+
+    def __init__(self, weight, bias, context, bn=None, relu=False, device=None, scale_shift=None):
+        w = weight.detach().float().to(device).contiguous()
+        self.context = list(context)
+        self.w = ops.pack_tdnn_weight(w, self.context)
+        self.cout = w.shape[0]
+        self.bias = bias.detach().float().to(device).contiguous() if bias is not None else None
+        self.relu = relu
+        scale, shift = scale_shift if scale_shift is not None else fold_batchnorm(bn)
+        self.scale = torch.from_numpy(scale).to(device) if scale is not None else None
+        self.shift = torch.from_numpy(shift).to(device) if shift is not None else None
+
+    def run(self, x, **kw):
+        ops.tdnn_affine_ex(x, self.w, self.cout, self.context, bias=self.bias, bn_scale=self.scale, bn_shift=self.shift,
+                           relu=self.relu, **kw)
+
+
+class EcapaExtractor:
+    """Packed weights on one device + the launch sequence of ECAPA_TDNN.extract_embedding (:403-426)."""
+
+    def __init__(self, m, device):
+        self.device = device
+        self.feat_dim = m.inputs_dim
+        self.ldf = (m.inputs_dim + 7) // 8 * 8
+        self.last_launches = 0
+
+        def tdnn(layer):
+            return _Layer(layer.affine.weight, layer.affine.bias, layer.affine.context, bn=layer.batchnorm,
+                          relu=layer.relu, device=device)
+
+        self.layer1 = tdnn(m.layer1)
+        self.blocks = []
+        for blk in (m.layer2, m.layer3, m.layer4):
+            self.blocks.append({
+                "bn1": tdnn(blk.conv_relu_bn1),
+                "res": [tdnn(b) for b in blk.res2net_block.blocks],
+                "width": blk.res2net_block.width,
+                "bn2": tdnn(blk.conv_relu_bn2),
+                "se1": _Layer(blk.se.se[1].weight, blk.se.se[1].bias, [0], relu=True, device=device),
+                "se2": _Layer(blk.se.se[3].weight, blk.se.se[3].bias, [0], device=device),
+            })
+        self.channels = m.layer1.affine.output_dim
+        self.mfa = tdnn(m.mfa)
+        att = m.stats.attention
+        c = m.stats.in_dim
+        w0 = att[0].weight.detach().float()
+        self.att_x = _Layer(w0[:, :c].contiguous(), None, [0], bn=att[2], relu=True, device=device)
+        self.att_gs = _Layer(w0[:, c:].contiguous(), att[0].bias, [0], device=device)  # [mean | std] columns
+        self.att2 = _Layer(att[4].weight, att[4].bias, [0], device=device)
+        self.mfa_dim = c
+        # bn_stats folded into fc2: W' = W diag(s), b' = W t + b
+        s, t = fold_batchnorm(m.bn_stats)
+        w = m.fc2.affine.weight.detach().double().cpu().numpy()[:, :, 0]
+        b = m.fc2.affine.bias.detach().double().cpu().numpy()
+        w2 = torch.from_numpy((w * s.astype(np.float64)[None, :]).astype(np.float32)).unsqueeze(2)
+        b2 = torch.from_numpy((w @ t.astype(np.float64) + b).astype(np.float32))
+        full = m.extracted_embedding == "near"
+        self.fc2 = _Layer(w2, b2, [0], relu=full and m.fc2.relu, device=device,
+                          scale_shift=fold_batchnorm(m.fc2.batchnorm) if full else (None, None))
+        self.embed_dim = m.embd_dim
+
+    def extract(self, feats):
+        """feats (B,T,F) fp32 CUDA -> (B, embd_dim) fp32 CUDA (asynchronous on the current stream)."""
+        if feats.shape[2] != self.feat_dim:
+            raise ValueError("expected feature dim {}, got {}".format(self.feat_dim, feats.shape[2]))
+        B, T, _ = feats.shape
+        dev, C = feats.device, self.channels
+        P = ops.SplitPlanes
+        xin = ops.split_f32(feats, ld=self.ldf)
+        X = P.empty((B, T, C), dev)
+        self.layer1.run(xin, y=X)
+        H, R, Z = P.empty((B, T, C), dev), P.empty((B, T, C), dev), P.empty((B, T, C), dev)
+        N = P.empty((B, T, C), dev)
+        CAT = P.empty((B, T, 3 * C), dev)
+        gate = torch.empty(B, 1, C, dtype=torch.float32, device=dev)
+        s1 = P.empty((B, 1, self.blocks[0]["se1"].cout), dev)
+        cur = X
+        for li, blk in enumerate(self.blocks):
+            w = blk["width"]
+            blk["bn1"].run(cur, y=H)
+            R.hi[:, :, :w].copy_(H.hi[:, :, :w])       # chunk 0 passes through (ecapa_tdnn_xvector.py:63-64)
+            R.lo[:, :, :w].copy_(H.lo[:, :, :w])
+            for i, layer in enumerate(blk["res"]):
+                layer.run(H.slice(w * (i + 1), w * (i + 2)), x2=R.slice(w * i, w * (i + 1)) if i >= 1 else None,
+                          y=R.slice(w * (i + 1), w * (i + 2)))
+            blk["bn2"].run(R, y=Z)
+            _, zm = ops.plane_mean(Z)
+            blk["se1"].run(zm, y=s1)
+            blk["se2"].run(s1, sigmoid=True, y_f32=gate)
+            last = li + 1 == len(self.blocks)
+            ops.se_apply(Z, cur, gate.view(B, C), CAT.slice(C * li, C * (li + 1)), None if last else N)
+            cur = N
+        D = self.mfa_dim
+        M = P.empty((B, T, D), dev)
+        MF = torch.empty(B, T, D, dtype=torch.float32, device=dev)
+        self.mfa.run(CAT, y=M, y_f32=MF)
+        _, gp = ops.stats_pool_ex(MF, 1e-5, 1, planes=True)          # global mean | sqrt(var_unbiased + 1e-5)
+        ub = torch.empty(B, 1, self.att_gs.cout, dtype=torch.float32, device=dev)
+        self.att_gs.run(gp, y_f32=ub)
+        A1 = P.empty((B, T, self.att_x.cout), dev)
+        self.att_x.run(M, utt_bias=ub.view(B, -1), tanh=True, y=A1)
+        LOG = torch.empty(B, T, D, dtype=torch.float32, device=dev)
+        self.att2.run(A1, y_f32=LOG)
+        _, pp = ops.attn_stats_pool(LOG, MF, 1e-5, planes=True)
+        emb = torch.empty(B, 1, self.embed_dim, dtype=torch.float32, device=dev)
+        self.fc2.run(pp, y_f32=emb)
+        return emb.view(B, self.embed_dim)
+
+    def close(self):
+        pass
+
+
+# Test.
+if __name__ == "__main__":
+    print(ECAPA_TDNN(80, 10, training=False))

@@ -6,7 +6,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import BN, RELU, check, int_array, lib  # noqa: F401
+from ._lib import BN, RELU, SIGMOID, TANH, TdnnArgs, check, int_array, lib  # noqa: F401
 
 
 def _stream():
@@ -31,10 +31,22 @@ class SplitPlanes:
 
     @property
     def ld(self):
-        return self.hi.shape[-1]
+        """Row pitch in elements (a channel slice keeps the pitch of the tensor it was cut from)."""
+        return self.hi.stride(-2) if self.hi.dim() >= 2 else self.hi.shape[-1]
 
     def float(self):
         return (self.hi.float() + self.lo.float())[..., :self.channels]
+
+    def slice(self, c0, c1):
+        """Channel slice [c0, c1) as a view (c0 must keep 16-byte alignment: c0 % 8 == 0)."""
+        if c0 % 8:
+            raise ValueError("channel slices must start at a multiple of 8")
+        return SplitPlanes(self.hi[..., c0:c1], self.lo[..., c0:c1], c1 - c0)
+
+    @staticmethod
+    def empty(shape, device):
+        return SplitPlanes(torch.empty(shape, dtype=torch.bfloat16, device=device),
+                           torch.empty(shape, dtype=torch.bfloat16, device=device), shape[-1])
 
 
 def split_f32(x, ld=None):
@@ -89,6 +101,82 @@ def tdnn_affine(x, w, cout, context, bias=None, bn_scale=None, bn_shift=None, re
                               _ptr(y.hi) if y else None, _ptr(y.lo) if y else None, cout, _ptr(yf), cout,
                               b, t, x.channels, cout, _stream()), "xvb_tdnn_affine")
     return y, yf
+
+
+def tdnn_affine_ex(x, w, cout, context, x2=None, bias=None, bn_scale=None, bn_shift=None, utt_bias=None, row_bias=None,
+                   relu=False, tanh=False, sigmoid=False, y=None, y_f32=None):
+    """Full form of the tcgen05 layer (xvb_tdnn_affine_ex).  x / x2: SplitPlanes (B,T,*) (views
+    allowed); y: SplitPlanes to write (view allowed) and/or y_f32: fp32 (B,T,>=cout) tensor."""
+    b, t = x.hi.shape[0], x.hi.shape[1]
+    a = TdnnArgs()
+    a.x_hi, a.x_lo, a.ldx = x.hi.data_ptr(), x.lo.data_ptr(), x.ld
+    if x2 is not None:
+        a.x2_hi, a.x2_lo, a.ldx2 = x2.hi.data_ptr(), x2.lo.data_ptr(), x2.ld
+    a.w_hi, a.w_lo = w.hi.data_ptr(), w.lo.data_ptr()
+    keep = []
+    for name, v in (("bias", bias), ("bn_scale", bn_scale), ("bn_shift", bn_shift), ("row_bias", row_bias)):
+        if v is not None:
+            setattr(a, name, _req(v, torch.float32, name).data_ptr())
+    if utt_bias is not None:
+        a.utt_bias, a.ld_utt_bias = _req(utt_bias, torch.float32, "utt_bias").data_ptr(), utt_bias.shape[-1]
+    a.flags = (RELU if relu else 0) | (BN if bn_scale is not None else 0) | (TANH if tanh else 0) | \
+        (SIGMOID if sigmoid else 0)
+    ctx = int_array(context)
+    keep.append(ctx)
+    a.context_host, a.ntaps = ctx, len(context)
+    if y is not None:
+        a.y_hi, a.y_lo, a.ldy = y.hi.data_ptr(), y.lo.data_ptr(), y.ld
+    if y_f32 is not None:
+        if y_f32.dtype != torch.float32 or not y_f32.is_cuda:
+            raise TypeError("y_f32 must be a CUDA float32 tensor")
+        a.y_f32, a.ldyf = y_f32.data_ptr(), y_f32.stride(-2)
+    a.B, a.T, a.Cin, a.Cout = b, t, x.channels, cout
+    check(lib.xvb_tdnn_affine_ex(C.byref(a), _stream()), "xvb_tdnn_affine_ex")
+
+
+def plane_mean(x, planes=True):
+    """Mean over T of SplitPlanes (B,T,C) -> (fp32 (B,C), SplitPlanes (B,1,C) | None)."""
+    b, t, c = x.hi.shape[0], x.hi.shape[1], x.channels
+    out = torch.empty(b, c, dtype=torch.float32, device=x.hi.device)
+    op = SplitPlanes.empty((b, 1, c), x.hi.device) if planes else None
+    check(lib.xvb_plane_mean(x.hi.data_ptr(), x.lo.data_ptr(), x.ld, b, t, c, _ptr(out),
+                             op.hi.data_ptr() if op else None, op.lo.data_ptr() if op else None, c, _stream()),
+          "xvb_plane_mean")
+    return out, op
+
+
+def se_apply(z, xin, gate, out, nxt=None):
+    """out = z * gate[b] + xin ; nxt = xin + out   (all SplitPlanes (B,T,C), views allowed)."""
+    b, t, c = z.hi.shape[0], z.hi.shape[1], z.channels
+    gate = _req(gate, torch.float32, "gate")
+    check(lib.xvb_se_apply(z.hi.data_ptr(), z.lo.data_ptr(), z.ld, xin.hi.data_ptr(), xin.lo.data_ptr(), xin.ld,
+                           _ptr(gate), out.hi.data_ptr(), out.lo.data_ptr(), out.ld,
+                           nxt.hi.data_ptr() if nxt else None, nxt.lo.data_ptr() if nxt else None,
+                           nxt.ld if nxt else 0, b, t, c, _stream()), "xvb_se_apply")
+
+
+def stats_pool_ex(x, eps, mode, planes=False):
+    """mode 0: StatisticsPooling; mode 1: ECAPA global context (unbiased var + eps)."""
+    x = _req(x, torch.float32, "x")
+    b, t, c = x.shape
+    out = torch.empty(b, 2 * c, dtype=torch.float32, device=x.device)
+    op = SplitPlanes.empty((b, 1, 2 * c), x.device) if planes else None
+    check(lib.xvb_stats_pool_ex(_ptr(x), c, b, t, c, eps, mode, _ptr(out), op.hi.data_ptr() if op else None,
+                                op.lo.data_ptr() if op else None, 2 * c, _stream()), "xvb_stats_pool_ex")
+    return (out, op) if planes else out
+
+
+def attn_stats_pool(logits, x, floor=1e-5, planes=False):
+    """softmax over T of logits (B,T,C) -> weighted mean/std of x (B,T,C): (B,2C)."""
+    logits = _req(logits, torch.float32, "logits")
+    x = _req(x, torch.float32, "x")
+    b, t, c = x.shape
+    out = torch.empty(b, 2 * c, dtype=torch.float32, device=x.device)
+    op = SplitPlanes.empty((b, 1, 2 * c), x.device) if planes else None
+    check(lib.xvb_attn_stats_pool(_ptr(logits), c, _ptr(x), c, b, t, c, floor, _ptr(out),
+                                  op.hi.data_ptr() if op else None, op.lo.data_ptr() if op else None, 2 * c, _stream()),
+          "xvb_attn_stats_pool")
+    return (out, op) if planes else out
 
 
 def tdnn_affine_simt(x, weight, context, bias=None, bn_scale=None, bn_shift=None, relu=False):

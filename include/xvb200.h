@@ -46,6 +46,8 @@ extern "C" {
 /* epilogue flags for xvb_tdnn_affine* (order is fixed: +bias -> ReLU -> BN affine) */
 #define XVB_RELU 1 /* components.py:410-416 (_relu_bn_forward): ReLU first ... */
 #define XVB_BN 2   /* ... then eval-mode BatchNorm folded to y*scale[c] + shift[c] */
+#define XVB_SIGMOID 4 /* ... then sigmoid (SE gate, ecapa_tdnn_xvector.py:97-106) */
+#define XVB_TANH 8    /* ... then tanh (attention bottleneck, ecapa_tdnn_xvector.py:164-168) */
 
 #define XVB_MAX_TAPS 16
 
@@ -81,14 +83,37 @@ int xvb_pack_tdnn_weight(const float* w, int Cout, int Cin, int tot_context, int
  * xvb_tdnn_affine: tcgen05 (bf16x3 split, fp32 accumulate in TMEM) GEMM with M = B*T frames,
  * K = ntaps*Cin, N = Cout; the context splice is done by TMA (3-D tensor map (C,T,B), time
  * coordinate offset per tap, out-of-bounds zero fill == F.pad).  Outputs: split planes
- * (y_hi,y_lo; may be NULL) and/or fp32 (y_f32; may be NULL).  Requirements: ldx % 8 == 0,
- * ldy % 8 == 0 and Cout % 8 == 0 when planes are written, ldyf % 4 == 0 and Cout % 4 == 0 when
- * fp32 is written; pointers 16-byte aligned.
+ * (y_hi,y_lo; may be NULL) and/or fp32 (y_f32; may be NULL); the TMA store clips ragged T / B /
+ * Cout.  Requirements: ldx % 8 == 0, ldy % 8 == 0, ldyf % 4 == 0; pointers 16-byte aligned.
  * ------------------------------------------------------------------------------------------- */
 int xvb_tdnn_affine(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, const uint16_t* w_hi,
                     const uint16_t* w_lo, const float* bias, const float* bn_scale, const float* bn_shift, int flags,
                     const int* context_host, int ntaps, uint16_t* y_hi, uint16_t* y_lo, int64_t ldy, float* y_f32,
                     int64_t ldyf, int B, int T, int Cin, int Cout, void* stream);
+
+/* Extended form of the same kernel (everything xvb_tdnn_affine does, plus what ECAPA-TDNN and the
+ * PLDA scorer need).  Zero-initialise the struct; unused pointers stay NULL.
+ *   x2_*      : second A source with the same shape; computes W.(x + x2) by accumulating both
+ *               sources into the same TMEM accumulator (Res2Net "sp + spx[i+1]",
+ *               pytorch/model/ecapa_tdnn_xvector.py:66-71) -- no elementwise pass, no extra launch;
+ *   row_bias  : per frame (B*T) additive term (PLDA row term);
+ *   utt_bias  : per utterance x column (B, Cout) additive term, pitch ld_utt_bias (the
+ *               time-constant [mean,std] part of AttentiveStatsPool's first conv, :173-180);
+ *   both plane and fp32 outputs may be requested together. */
+typedef struct xvb_tdnn_args {
+  const uint16_t* x_hi; const uint16_t* x_lo; int64_t ldx;
+  const uint16_t* x2_hi; const uint16_t* x2_lo; int64_t ldx2;
+  const uint16_t* w_hi; const uint16_t* w_lo;
+  const float* bias; const float* bn_scale; const float* bn_shift;
+  const float* row_bias;
+  const float* utt_bias; int64_t ld_utt_bias;
+  int flags;
+  const int* context_host; int ntaps;
+  uint16_t* y_hi; uint16_t* y_lo; int64_t ldy;
+  float* y_f32; int64_t ldyf;
+  int B, T, Cin, Cout;
+} xvb_tdnn_args_t;
+int xvb_tdnn_affine_ex(const xvb_tdnn_args_t* args, void* stream);
 
 /* Same layer on CUDA cores in plain fp32 straight from the *unpacked* reference weight
  * (Cout, Cin, tot_context).  Slow; exists so the tensor-core path and the weight packer can
@@ -107,6 +132,33 @@ int xvb_tdnn_affine_simt(const float* x, int64_t ldx, const float* w, int tot_co
  * ------------------------------------------------------------------------------------------- */
 int xvb_stats_pool(const float* x, int64_t ldx, int B, int T, int C, float eps, float* out, uint16_t* out_hi,
                    uint16_t* out_lo, int64_t ldo, void* stream);
+
+/* mode 0 = xvb_stats_pool; mode 1 = the global context of ECAPA's AttentiveStatsPool
+ * (pytorch/model/ecapa_tdnn_xvector.py:175-178): std = sqrt(unbiased_var + eps). */
+int xvb_stats_pool_ex(const float* x, int64_t ldx, int B, int T, int C, float eps, int mode, float* out,
+                      uint16_t* out_hi, uint16_t* out_lo, int64_t ldo, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ECAPA-TDNN pieces that are not contractions (pytorch/model/ecapa_tdnn_xvector.py)
+ * ------------------------------------------------------------------------------------------- */
+
+/* Mean over time of a split-plane tensor (B,T,C) -> (B,C) fp32 and/or planes: the
+ * AdaptiveAvgPool1d(1) of SE_Connect (:100).  C % 8 == 0. */
+int xvb_plane_mean(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, int B, int T, int C, float* out,
+                   uint16_t* out_hi, uint16_t* out_lo, int64_t ldo, void* stream);
+
+/* out = z * gate[b,:] + in  and optionally next = in + out, all split planes (B,T,C): the SE
+ * scaling + residual of SE_Res2Block.forward (:109-111, :149) fused with the running sums
+ * x+x1, x+x1+x2 of ECAPA_TDNN.extract_embedding (:405-408).  gate: (B,C) fp32. */
+int xvb_se_apply(const uint16_t* z_hi, const uint16_t* z_lo, int64_t ldz, const uint16_t* in_hi, const uint16_t* in_lo,
+                 int64_t ldin, const float* gate, uint16_t* out_hi, uint16_t* out_lo, int64_t ldout, uint16_t* next_hi,
+                 uint16_t* next_lo, int64_t ldnext, int B, int T, int C, void* stream);
+
+/* AttentiveStatsPool.forward tail (:183-188): alpha = softmax_T(logits); mean = sum alpha x;
+ * std = sqrt(max(sum alpha x^2 - mean^2, floor)); out (B,2C) = [mean | std].  One streaming pass
+ * over logits and x (both (B,T,C) fp32) with an online softmax. */
+int xvb_attn_stats_pool(const float* logits, int64_t ldl, const float* x, int64_t ldx, int B, int T, int C, float floor_,
+                        float* out, uint16_t* out_hi, uint16_t* out_lo, int64_t ldo, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Back-end scoring

@@ -62,3 +62,27 @@ def test_model_blueprint_contract_on_cpu():
     assert m.extracted_embedding == "near" and hasattr(m, "extract_embedding")
     with pytest.raises(RuntimeError):                     # no CPU path
         m.extract_embedding(onn.synthetic_feats(1, 10, 23, 0)[0])
+
+
+def test_ecapa_blueprint_contract_on_cpu():
+    """ECAPA plugin surface: canonical c1024 creation string -> the reference's keys and shapes."""
+    from asv_subtools_b200.model.ecapa_tdnn_xvector import ECAPA_TDNN
+    from oracle import nnet as onn
+    canon = dict(training=False, extracted_embedding="near",
+                 ecapa_params={"channels": 1024, "embd_dim": 192, "mfa_conv": 1536,
+                               "bn_params": {"momentum": 0.5, "affine": True, "track_running_stats": True}},
+                 pooling="ecpa-attentive", pooling_params={"hidden_size": 128, "time_attention": True, "stddev": True},
+                 fc1=False, fc2_params={"nonlinearity": "", "nonlinearity_params": {"inplace": True}, "bn-relu": False,
+                                        "bn": True, "bn_params": {"momentum": 0.5, "affine": False,
+                                                                  "track_running_stats": True}})
+    m = ECAPA_TDNN(80, 10, **canon)
+    spec = {k: tuple(s) for k, s, _ in onn.ecapa_spec(80)}
+    sd = m.state_dict()
+    assert set(sd) == set(spec), set(sd) ^ set(spec)
+    for k, v in sd.items():
+        assert tuple(v.shape) == spec[k], k
+    m.load_state_dict(onn.make_state_dict(onn.ecapa_spec(80), 201), strict=True)
+    assert not m.fc2.relu and m.fc2.batchnorm.weight is None
+    d = ECAPA_TDNN(80, 10, training=False)                # blueprint defaults: fc2 = affine + ReLU + affine BN
+    assert d.fc2.relu and set(d.state_dict()) == {k for k, _, _ in onn.ecapa_spec(80, fc2_bn_affine=True)}
+    assert d.layer3.res2net_block.context == [-3, 0, 3] and d.layer4.res2net_block.blocks[0].affine.weight.shape == (128, 128, 9)

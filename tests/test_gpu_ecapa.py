@@ -1,0 +1,163 @@
+"""ECAPA-TDNN on the GPU: every new epilogue/kernel against the oracle, then the whole model
+against the golden fixtures produced by the reference."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nnet as onn
+
+pytestmark = pytest.mark.gpu
+TOL = 3e-5
+EMB_TOL = 1e-4
+
+CANON = dict(training=False,
+             ecapa_params={"channels": 1024, "embd_dim": 192, "mfa_conv": 1536,
+                           "bn_params": {"momentum": 0.5, "affine": True, "track_running_stats": True}},
+             pooling="ecpa-attentive", pooling_params={"hidden_size": 128, "time_attention": True, "stddev": True},
+             fc1=False, fc2_params={"nonlinearity": "", "nonlinearity_params": {"inplace": True}, "bn-relu": False,
+                                    "bn": True, "bn_params": {"momentum": 0.5, "affine": False,
+                                                              "track_running_stats": True}})
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from asv_subtools_b200 import ops as _ops
+    return _ops
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+
+def test_second_source_and_channel_slices(ops):
+    """Res2Net step: y = relu_bn(W.(a[:, :, 128:256] + r[:, :, 0:128])) written into a slice of a wider tensor."""
+    rng = np.random.RandomState(1)
+    B, T, d = 3, 50, 3
+    a = rng.standard_normal((B, T, 1024)).astype(np.float32)
+    r = rng.standard_normal((B, T, 1024)).astype(np.float32)
+    w = (rng.standard_normal((128, 128, 2 * d + 1)) * 0.05).astype(np.float32)
+    b = rng.standard_normal(128).astype(np.float32) * 0.1
+    sc = rng.uniform(0.5, 1.5, 128).astype(np.float32)
+    sh = rng.standard_normal(128).astype(np.float32) * 0.1
+    ctx = [-d, 0, d]
+    ap, rp = ops.split_f32(cu(a)), ops.split_f32(cu(r))
+    out = ops.SplitPlanes(torch.zeros(B, T, 1024, dtype=torch.bfloat16, device="cuda"),
+                          torch.zeros(B, T, 1024, dtype=torch.bfloat16, device="cuda"), 1024)
+    wp = ops.pack_tdnn_weight(cu(w), ctx)
+    ops.tdnn_affine_ex(ap.slice(128, 256), wp, 128, ctx, x2=rp.slice(0, 128), bias=cu(b), bn_scale=cu(sc),
+                       bn_shift=cu(sh), relu=True, y=out.slice(256, 384))
+    got = out.float().cpu().numpy()
+    with torch.no_grad():
+        x = torch.from_numpy(a[:, :, 128:256] + r[:, :, 0:128]).transpose(1, 2)
+        ref = torch.relu(onn.tdnn_affine(x, torch.from_numpy(w), torch.from_numpy(b), ctx))
+        ref = (ref * torch.from_numpy(sc)[None, :, None] + torch.from_numpy(sh)[None, :, None]).transpose(1, 2).numpy()
+    assert rel(got[:, :, 256:384], ref) < TOL
+    assert np.all(got[:, :, :256] == 0) and np.all(got[:, :, 384:] == 0)   # nothing outside the slice was touched
+
+
+def test_utt_bias_tanh_sigmoid_and_dual_output(ops):
+    rng = np.random.RandomState(2)
+    B, T, Cin, Cout = 5, 37, 192, 128
+    x = rng.standard_normal((B, T, Cin)).astype(np.float32)
+    w = (rng.standard_normal((Cout, Cin, 1)) / np.sqrt(Cin)).astype(np.float32)
+    ub = rng.standard_normal((B, Cout)).astype(np.float32)
+    sc = rng.uniform(0.5, 1.5, Cout).astype(np.float32)
+    sh = rng.standard_normal(Cout).astype(np.float32) * 0.1
+    xp, wp = ops.split_f32(cu(x)), ops.pack_tdnn_weight(cu(w), [0])
+    y = ops.SplitPlanes.empty((B, T, Cout), "cuda")
+    yf = torch.empty(B, T, Cout, device="cuda")
+    ops.tdnn_affine_ex(xp, wp, Cout, [0], utt_bias=cu(ub), bn_scale=cu(sc), bn_shift=cu(sh), relu=True, tanh=True,
+                       y=y, y_f32=yf)
+    pre = np.einsum("btc,nc->btn", x.astype(np.float64), w[:, :, 0].astype(np.float64)) + ub[:, None, :]
+    ref = np.tanh(np.maximum(pre, 0) * sc + sh)
+    assert rel(yf.cpu().numpy(), ref) < TOL and rel(y.float().cpu().numpy(), ref) < TOL
+    ops.tdnn_affine_ex(xp, wp, Cout, [0], sigmoid=True, y_f32=yf)
+    ref = 1 / (1 + np.exp(-np.einsum("btc,nc->btn", x.astype(np.float64), w[:, :, 0].astype(np.float64))))
+    assert rel(yf.cpu().numpy(), ref) < TOL
+
+
+def test_plane_mean_and_se_apply(ops):
+    rng = np.random.RandomState(3)
+    B, T, C = 4, 61, 1024
+    z = rng.standard_normal((B, T, C)).astype(np.float32)
+    xin = rng.standard_normal((B, T, C)).astype(np.float32)
+    g = rng.uniform(0, 1, (B, C)).astype(np.float32)
+    zp, ip = ops.split_f32(cu(z)), ops.split_f32(cu(xin))
+    m, mp = ops.plane_mean(zp)
+    assert rel(m.cpu().numpy(), z.mean(1)) < 1e-5 and rel(mp.float().cpu().numpy()[:, 0], z.mean(1)) < 1e-5
+    cat = ops.SplitPlanes.empty((B, T, 3 * C), "cuda")
+    nxt = ops.SplitPlanes.empty((B, T, C), "cuda")
+    ops.se_apply(zp, ip, cu(g), cat.slice(C, 2 * C), nxt)
+    ref = z * g[:, None, :] + xin
+    assert rel(cat.float().cpu().numpy()[:, :, C:2 * C], ref) < 1e-5
+    assert rel(nxt.float().cpu().numpy(), xin + ref) < 1e-5
+    ops.se_apply(zp, nxt, cu(g), cat.slice(0, C), nxt)          # in place: next = in + out over the same buffer
+    assert rel(cat.float().cpu().numpy()[:, :, :C], z * g[:, None, :] + (xin + ref)) < 1e-5
+
+
+def test_global_context_stats_and_attentive_pool(ops):
+    rng = np.random.RandomState(4)
+    B, T, C = 3, 77, 1536
+    x = (rng.standard_normal((B, T, C)) * 2 + 0.3).astype(np.float32)
+    logits = (rng.standard_normal((B, T, C)) * 3).astype(np.float32)
+    g = ops.stats_pool_ex(cu(x), 1e-5, 1).cpu().numpy()
+    xt = torch.from_numpy(x).transpose(1, 2)
+    assert rel(g[:, :C], xt.mean(2).numpy()) < 2e-6
+    assert rel(g[:, C:], torch.sqrt(torch.var(xt, dim=-1) + 1e-5).numpy()) < 2e-6
+    out, pl = ops.attn_stats_pool(cu(logits), cu(x), 1e-5, planes=True)
+    alpha = torch.softmax(torch.from_numpy(logits).transpose(1, 2), dim=2)
+    mean = torch.sum(alpha * xt, dim=2)
+    std = torch.sqrt((torch.sum(alpha * xt ** 2, dim=2) - mean ** 2).clamp(min=1e-5))
+    ref = torch.cat([mean, std], dim=1).numpy()
+    assert rel(out.cpu().numpy(), ref) < 5e-6
+    assert rel(pl.float().cpu().numpy()[:, 0], ref) < 2e-5
+
+
+def _model(pos, seed=201, default_fc2=False):
+    from asv_subtools_b200.model.ecapa_tdnn_xvector import ECAPA_TDNN
+    if default_fc2:
+        sd = onn.make_state_dict(onn.ecapa_spec(80, fc2_bn_affine=True), seed)
+        m = ECAPA_TDNN(80, 10, training=False)
+    else:
+        sd = onn.make_state_dict(onn.ecapa_spec(80), seed)
+        m = ECAPA_TDNN(80, 10, extracted_embedding=pos, **CANON)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda().eval(), sd
+
+
+@pytest.mark.parametrize("pos", ["near", "near_affine"])
+def test_ecapa_embeddings_match_reference_golden(golden, pos):
+    g = golden("ecapa")
+    m, _ = _model(pos)
+    feats = onn.synthetic_feats(2, 300, 80, 1201)
+    ref = g["ecapa80_{}_emb".format(pos)]
+    batch = m.extract_embedding_batch(feats).cpu().numpy()
+    single = np.stack([m.extract_embedding(feats[i]).numpy() for i in range(2)])
+    for i in range(2):
+        assert rel(batch[i], ref[i]) < EMB_TOL and rel(single[i], ref[i]) < EMB_TOL
+        assert np.dot(batch[i], ref[i]) / (np.linalg.norm(batch[i]) * np.linalg.norm(ref[i])) > 1 - 1e-6
+
+
+def test_ecapa_default_fc2_and_short_utterances(golden):
+    g = golden("ecapa")
+    m, _ = _model("near", seed=202, default_fc2=True)
+    for T in (2, 40):
+        f = onn.synthetic_feats(1, T, 80, 3201 + T)[0]
+        assert rel(m.extract_embedding(f).numpy(), g["ecapa80_default_T{}".format(T)]) < EMB_TOL
+
+
+def test_ecapa_vs_oracle_batch():
+    """A batch shape with ragged tiles (B=5, T=83) straight against the oracle."""
+    m, sd = _model("near")
+    feats = onn.synthetic_feats(5, 83, 80, 555)
+    got = m.extract_embedding_batch(feats).cpu().numpy()
+    with torch.no_grad():
+        ref = onn.ecapa_forward(sd, torch.from_numpy(feats).transpose(1, 2), "near").squeeze(2).numpy()
+    for i in range(5):
+        assert rel(got[i], ref[i]) < EMB_TOL

@@ -4,7 +4,7 @@
 TAG=${1:-r01}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_gpu.txt
-for MODE in 1 2; do
+for MODE in ${MODES:-2}; do
   XVB_GEMM_CTA=$MODE timeout 900 python -m pytest tests -m gpu -q > gpurun_out/${TAG}_pytest_gpu_cta$MODE.log 2>&1; echo "pytest(cta=$MODE) rc=$?"
   tail -12 gpurun_out/${TAG}_pytest_gpu_cta$MODE.log
   XVB_GEMM_CTA=$MODE timeout 300 python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench_cta$MODE.json 2> gpurun_out/${TAG}_bench_cta$MODE.err; echo "bench(cta=$MODE) rc=$?"
@@ -18,6 +18,7 @@ except Exception as e:
     print("bench parse failed", e); print(open("gpurun_out/${TAG}_bench_cta$MODE.err").read()[-2000:])
 PY
 done
+timeout 300 python tools/bench_ecapa.py 10 > gpurun_out/${TAG}_ecapa_bench.json 2> gpurun_out/${TAG}_ecapa_bench.err; echo "ecapa bench rc=$?"; cat gpurun_out/${TAG}_ecapa_bench.json; tail -3 gpurun_out/${TAG}_ecapa_bench.err
 timeout 300 python __graft_entry__.py smoke > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/${TAG}_smoke.log
 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; cat gpurun_out/${TAG}_bench.json; tail -5 gpurun_out/${TAG}_bench.err
 if [ -z "$2" ]; then
