@@ -95,10 +95,11 @@ def test_plane_mean_and_se_apply(ops):
     nxt = ops.SplitPlanes.empty((B, T, C), "cuda")
     ops.se_apply(zp, ip, cu(g), cat.slice(C, 2 * C), nxt)
     ref = z * g[:, None, :] + xin
-    assert rel(cat.float().cpu().numpy()[:, :, C:2 * C], ref) < 1e-5
-    assert rel(nxt.float().cpu().numpy(), xin + ref) < 1e-5
+    # split planes carry ~2^-17 relative precision per stored tensor
+    assert rel(cat.float().cpu().numpy()[:, :, C:2 * C], ref) < TOL
+    assert rel(nxt.float().cpu().numpy(), xin + ref) < TOL
     ops.se_apply(zp, nxt, cu(g), cat.slice(0, C), nxt)          # in place: next = in + out over the same buffer
-    assert rel(cat.float().cpu().numpy()[:, :, :C], z * g[:, None, :] + (xin + ref)) < 1e-5
+    assert rel(cat.float().cpu().numpy()[:, :, :C], z * g[:, None, :] + (xin + ref)) < TOL
 
 
 def test_global_context_stats_and_attentive_pool(ops):
