@@ -63,6 +63,7 @@ SIGNATURES = {
     "xvb_center_length_norm": (_i, [_p, _p, _p, _i64, _i, _p]),
     "xvb_column_mean": (_i, [_p, _i64, _i, _p, _p]),
     "xvb_cosine_trials": (_i, [_p, _p, _i, _p, _p, _i64, _p, _p]),
+    "xvb_speaker_mean": (_i, [_p, _i, _p, _p, _i, _p, _p]),
     "xvb_bilinear_trials": (_i, [_p, _p, _i, _p, _p, _i64, _p, _p, _p, _p]),
     "xvb_project": (_i, [_p, _i64, _i, _p, _i, _p, _p]),
     "xvb_cosine_matrix": (_i, [_p, _i64, _p, _i64, _i, _p, _i64, _p]),
@@ -75,6 +76,8 @@ SIGNATURES = {
     "xvb_extractor_embed_dim": (_i, [_p]),
     "xvb_extractor_extract": (_i, [_p, _p, _i, _i, _p, _p]),
     "xvb_extractor_extract_host": (_i, [_p, _p, _i, _i, _p, _p]),
+    "xvb_extractor_submit_host": (_i, [_p, _p, _i, _i, _p, _i, _p]),
+    "xvb_extractor_wait": (_i, [_p, _i]),
     "xvb_extractor_set_profiling": (_i, [_p, _i]),
     "xvb_extractor_kernel_times": (_i, [_p, C.POINTER(C.c_float), _i]),
     "xvb_extractor_last_launches": (_i, [_p]),

@@ -48,6 +48,12 @@ struct xvb_extractor {
   uint16_t* seg_hi[2] = {nullptr, nullptr}; uint16_t* seg_lo[2] = {nullptr, nullptr};  // (B,max_seg_c)
   float* h_feats = nullptr; float* h_emb = nullptr;            // device staging for *_host
   size_t h_feats_cap = 0, h_emb_cap = 0;
+  // double-buffered pipelined host path (submit/wait): H2D of batch i+1 overlaps the stack of batch i
+  float* p_feats[2] = {nullptr, nullptr}; float* p_emb[2] = {nullptr, nullptr};
+  size_t p_feats_cap[2] = {0, 0}, p_emb_cap[2] = {0, 0};
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  bool slot_busy[2] = {false, false};
   int max_c = 0, max_seg_c = 0;
   int last_launches = 0;
   // optional per-kernel CUDA-event timing on the launching stream (bench.py roofline)
@@ -279,6 +285,52 @@ extern "C" int xvb_extractor_extract_host(xvb_extractor_t* h, const float* feats
   return XVB_OK;
 }
 
+extern "C" int xvb_extractor_submit_host(xvb_extractor_t* h, const float* feats_host, int B, int T, float* emb_host,
+                                         int slot, void* stream) {
+  XVB_CHECK_ARG(h && h->finalized && feats_host && emb_host && B > 0 && T > 0 && (slot == 0 || slot == 1),
+                "xvb_extractor_submit_host: bad arguments (slot must be 0 or 1)");
+  XVB_CHECK_ARG(!h->slot_busy[slot], "xvb_extractor_submit_host: slot %d still in flight (call xvb_extractor_wait)", slot);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!h->copy_stream) {
+    XVB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      XVB_CUDA(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+      XVB_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+    }
+  }
+  const size_t nf = (size_t)B * T * h->feat_dim, ne = (size_t)B * h->segment.back().Cout;
+  if (nf > h->p_feats_cap[slot]) {
+    cudaFree(h->p_feats[slot]);
+    int rc = dev_alloc(&h->p_feats[slot], nf);
+    if (rc) return rc;
+    h->p_feats_cap[slot] = nf;
+  }
+  if (ne > h->p_emb_cap[slot]) {
+    cudaFree(h->p_emb[slot]);
+    int rc = dev_alloc(&h->p_emb[slot], ne);
+    if (rc) return rc;
+    h->p_emb_cap[slot] = ne;
+  }
+  // the copy engine fills this slot while the compute stream still works on the other one
+  XVB_CUDA(cudaMemcpyAsync(h->p_feats[slot], feats_host, nf * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream));
+  XVB_CUDA(cudaEventRecord(h->ev_h2d[slot], h->copy_stream));
+  XVB_CUDA(cudaStreamWaitEvent(s, h->ev_h2d[slot], 0));
+  int rc = xvb_extractor_extract(h, h->p_feats[slot], B, T, h->p_emb[slot], stream);
+  if (rc) return rc;
+  XVB_CUDA(cudaMemcpyAsync(emb_host, h->p_emb[slot], ne * sizeof(float), cudaMemcpyDeviceToHost, s));
+  XVB_CUDA(cudaEventRecord(h->ev_done[slot], s));
+  h->slot_busy[slot] = true;
+  return XVB_OK;
+}
+
+extern "C" int xvb_extractor_wait(xvb_extractor_t* h, int slot) {
+  XVB_CHECK_ARG(h && (slot == 0 || slot == 1), "xvb_extractor_wait: bad arguments");
+  if (!h->slot_busy[slot]) return XVB_OK;
+  XVB_CUDA(cudaEventSynchronize(h->ev_done[slot]));
+  h->slot_busy[slot] = false;
+  return XVB_OK;
+}
+
 extern "C" int xvb_extractor_set_profiling(xvb_extractor_t* h, int enable) {
   XVB_CHECK_ARG(h, "xvb_extractor_set_profiling: null extractor");
   h->profiling = enable != 0;
@@ -307,6 +359,12 @@ extern "C" void xvb_extractor_destroy(xvb_extractor_t* h) {
   if (!h) return;
   h->free_ws();
   for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(h->p_feats[i]); cudaFree(h->p_emb[i]);
+    if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
+    if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+  }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   cudaFree(h->h_feats); cudaFree(h->h_emb);
   for (auto* v : {&h->frame, &h->segment})
     for (Layer& L : *v) { cudaFree(L.w_hi); cudaFree(L.w_lo); cudaFree(L.bias); cudaFree(L.scale); cudaFree(L.shift); }

@@ -50,6 +50,18 @@ __global__ void column_final_kernel(const double* __restrict__ partial, int G, l
   mean[c] = (float)(s / (double)rows);
 }
 
+// one CTA per speaker: mean of its member rows (CSR lists), thread = column
+__global__ void speaker_mean_kernel(const float* __restrict__ x, int D, const int32_t* __restrict__ offsets,
+                                    const int32_t* __restrict__ members, float* __restrict__ out) {
+  const int s = blockIdx.x;
+  const int beg = offsets[s], end = offsets[s + 1];
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    double acc = 0.0;
+    for (int i = beg; i < end; ++i) acc += (double)x[(long long)members[i] * D + c];
+    out[(long long)s * D + c] = end > beg ? (float)(acc / (double)(end - beg)) : 0.f;
+  }
+}
+
 // one warp per trial: <e[te], t[tt]> (+ row[te] + col[tt] for PLDA)
 __global__ void cosine_trials_kernel(const float* __restrict__ e, const float* __restrict__ t, int D,
                                      const int32_t* __restrict__ te, const int32_t* __restrict__ tt,
@@ -146,6 +158,16 @@ extern "C" int xvb_column_mean(const float* x, int64_t rows, int D, float* mean,
   column_partial_kernel<<<G, D < 512 ? ((D + 31) / 32) * 32 : 512, 0, s>>>(x, rows, D, (double*)t.p);
   XVB_LAUNCH_CHECK();
   column_final_kernel<<<(D + 127) / 128, 128, 0, s>>>((const double*)t.p, G, rows, D, mean);
+  XVB_LAUNCH_CHECK();
+  return XVB_OK;
+}
+
+extern "C" int xvb_speaker_mean(const float* x, int D, const int32_t* offsets, const int32_t* members, int num_spk,
+                                float* out, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  XVB_CHECK_ARG(x && offsets && members && out && D > 0 && num_spk > 0, "xvb_speaker_mean: bad arguments");
+  speaker_mean_kernel<<<num_spk, D < 256 ? ((D + 31) / 32) * 32 : 256, 0, (cudaStream_t)stream>>>(x, D, offsets, members, out);
   XVB_LAUNCH_CHECK();
   return XVB_OK;
 }

@@ -235,6 +235,18 @@ def cosine_trials(enroll, test, trial_e, trial_t):
     return s
 
 
+def speaker_mean(x, spk2rows):
+    """x (N,D) fp32 CUDA; spk2rows: list of row-index lists (spk2utt order) -> ((S,D) means, num_utts)."""
+    x = _req(x, torch.float32, "x")
+    counts = np.array([len(r) for r in spk2rows], dtype=np.int32)
+    offsets = torch.from_numpy(np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)).to(x.device)
+    members = torch.from_numpy(np.concatenate([np.asarray(r, dtype=np.int32) for r in spk2rows])).to(x.device)
+    out = torch.empty(len(spk2rows), x.shape[1], dtype=torch.float32, device=x.device)
+    check(lib.xvb_speaker_mean(_ptr(x), x.shape[1], _ptr(offsets), _ptr(members), len(spk2rows), _ptr(out), _stream()),
+          "xvb_speaker_mean")
+    return out, counts
+
+
 def bilinear_trials(enroll, test, trial_e, trial_t, row_term=None, col_term=None):
     enroll = _req(enroll, torch.float32, "enroll")
     test = _req(test, torch.float32, "test")
@@ -342,6 +354,14 @@ class Extractor:
         check(lib.xvb_extractor_extract_host(self._h, feats_np.ctypes.data_as(C.c_void_p), b, t,
                                              emb.ctypes.data_as(C.c_void_p), _stream()), "xvb_extractor_extract_host")
         return emb
+
+    def submit_host(self, feats_ptr, b, t, emb_ptr, slot):
+        """Pipelined host path: queue batch `slot` (0/1); pair with wait(slot)."""
+        check(lib.xvb_extractor_submit_host(self._h, C.c_void_p(feats_ptr), b, t, C.c_void_p(emb_ptr), slot, _stream()),
+              "xvb_extractor_submit_host")
+
+    def wait(self, slot):
+        check(lib.xvb_extractor_wait(self._h, slot), "xvb_extractor_wait")
 
     def extract_host_into(self, feats_ptr, b, t, emb_ptr):
         check(lib.xvb_extractor_extract_host(self._h, C.c_void_p(feats_ptr), b, t, C.c_void_p(emb_ptr), _stream()),

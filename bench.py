@@ -38,6 +38,9 @@ FLOP_PER_FRAME = 5630976          # 2*(2 807 808 MAC/frame) + 2*
 GEMM_FLOP_PER_STEP = FLOP_PER_FRAME * B * T
 POOL_BYTES_PER_STEP = 1212000 * B  # 4*(C*T + 2C) B/utt, C=1500, T=200
 NUM_INPUT_BATCHES = 8             # rotate 8 x 16.4 MB inputs; activations per step ~1.1 GB >> 126 MB L2
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
+NCU_GEMM_TRAFFIC_BYTES_PER_LAUNCH = int((68.4 + 174.0 + 178.2 + 163.7 + 359.8 + 9.3) * 1e6 / 6)
+NCU_POOL_TRAFFIC_BYTES_PER_LAUNCH = int((307.2 + 8.3) * 1e6)
 METRIC = "frames/sec x-vector extraction (80-d fbank)"
 UNIT = "frames/s"
 
@@ -215,15 +218,25 @@ def run_native(args, rank, world, local_rank):
     assert torch.isfinite(out).all()
 
     # ---- end to end through the host-buffer C-ABI call ----------------------------------------
-    for i in range(min(args.warmup, 3)):
-        ex.extract_host_into(host[i % 2].data_ptr(), B, T, host_out.data_ptr())
+    host_outs = [host_out, torch.empty(B, D, dtype=torch.float32).pin_memory()]
+
+    def e2e_loop(n):
+        # submit(i) queues H2D (copy stream) + stack + D2H; wait(i-1) hands batch i-1's embeddings to the host
+        ex.submit_host(host[0].data_ptr(), B, T, host_outs[0].data_ptr(), 0)
+        for i in range(1, n):
+            ex.submit_host(host[i % 2].data_ptr(), B, T, host_outs[i % 2].data_ptr(), i % 2)
+            ex.wait((i - 1) % 2)
+        ex.wait((n - 1) % 2)
+
+    e2e_loop(max(2, min(args.warmup, 3)))
     barrier()
-    e0.record()
-    for i in range(args.steps):
-        ex.extract_host_into(host[i % 2].data_ptr(), B, T, host_out.data_ptr())
-    e1.record()
+    t_e2e0 = time.perf_counter()
+    e2e_loop(args.steps)
+    torch.cuda.synchronize()
+    e2e_host_ms = (time.perf_counter() - t_e2e0) * 1e3   # every step ends in the host buffer: host clock
     barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_ms = max_over_ranks(e2e_host_ms)
+    assert torch.isfinite(host_outs[(args.steps - 1) % 2]).all()
     clocks = sampler.stop(wall0, time.time()) if sampler else None
 
     # ---- per-kernel CUDA-event times (roofline) -------------------------------------------------
@@ -260,12 +273,14 @@ def run_native(args, rank, world, local_rank):
                    "weights": "seeded synthetic checkpoint of the reference architecture"},
         "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": B * T * F * 4, "d2h_bytes_per_step": B * D * 4,
-                "api": "xvb_extractor_extract_host (pinned host feats in, host embeddings out)"},
+                "api": "xvb_extractor_submit_host/xvb_extractor_wait (pinned host feats in, host embeddings out; "
+                       "H2D of batch i+1 overlaps the kernels of batch i; timed on the host clock)"},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "tdnn_gemm_bf16x3_kernel (6 launches/step)",
                      "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / pk["bf16_sustained"], "traffic": None,
+                     "frac": achieved / pk["bf16_sustained"], "traffic": NCU_GEMM_TRAFFIC_BYTES_PER_LAUNCH,
+                     "traffic_unit": "bytes/launch (dram read+write, mean of the 6 launches, profiles/r01b_gemm_ncu_summary.txt)",
                      "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)",
                      "algorithmic_flop_per_launch_avg": GEMM_FLOP_PER_STEP / 6,
                      "executed_tflops": 3 * achieved, "executed_frac": 3 * achieved / pk["bf16_sustained"],
@@ -273,7 +288,9 @@ def run_native(args, rank, world, local_rank):
                      "gemm_ms_per_step": gemm_ms},
         "roofline_stats_pool": {"bound": "hbm", "kernel": "stats_pool_kernel", "achieved": pool_gbs,
                                 "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": pool_gbs / pk["hbm_gbs"],
-                                "traffic": None, "ms": pool_ms, "peak_source": pk["src"]},
+                                "traffic": NCU_POOL_TRAFFIC_BYTES_PER_LAUNCH,
+                                "traffic_unit": "bytes/launch (profiles/r01c_pool_ncu_summary.txt); algorithmic 310.3 MB",
+                                "ms": pool_ms, "peak_source": pk["src"]},
         "kernel_ms": {n: float(v) for n, v in zip(names, per)},
         "cpu_baseline": {"value": cpu_batched, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                          "sample": "64 utts x 200 frames batched forward for ~10 s (most favourable to the reference); "

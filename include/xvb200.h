@@ -177,6 +177,12 @@ int xvb_column_mean(const float* x, int64_t rows, int D, float* mean, void* stre
 int xvb_cosine_trials(const float* enroll, const float* test, int D, const int32_t* trial_e, const int32_t* trial_t,
                       int64_t num_trials, float* scores, void* stream);
 
+/* Per-speaker mean of embeddings: `mean` of score/process.sh:156-167 (ivector-mean ark:spk2utt).
+ * CSR lists: speaker s owns rows members[offsets[s] .. offsets[s+1]) of x (N,D); out (S,D).
+ * num_utts[s] = offsets[s+1]-offsets[s] is known to the caller. */
+int xvb_speaker_mean(const float* x, int D, const int32_t* offsets, const int32_t* members, int num_spk, float* out,
+                     void* stream);
+
 /* Per-trial bilinear scores with optional per-row / per-column terms:
  * scores[i] = <enroll[te[i]], test[tt[i]]> + row_term[te[i]] + col_term[tt[i]]  (terms may be NULL).
  * With enroll := E.(Lambda+Lambda^T) and the xvb_plda_terms() vectors this is PLDAScoring
@@ -223,6 +229,14 @@ int xvb_extractor_extract(xvb_extractor_t* h, const float* feats, int B, int T, 
 /* Same through host buffers (H2D of feats, D2H of emb inside; synchronises the stream). */
 int xvb_extractor_extract_host(xvb_extractor_t* h, const float* feats_host, int B, int T, float* emb_host,
                                void* stream);
+/* Pipelined host-buffer path: submit returns as soon as the work is queued (H2D on a private copy
+ * stream into one of two device slots, the stack and the D2H on `stream`), so the host->device
+ * copy of batch i+1 overlaps the kernels of batch i.  feats_host / emb_host must stay valid (and
+ * should be pinned) until xvb_extractor_wait(h, slot) returns.  Typical loop:
+ *   submit(batch0, slot0); for i>=1 { submit(batch_i, i&1); wait((i-1)&1); } wait(last). */
+int xvb_extractor_submit_host(xvb_extractor_t* h, const float* feats_host, int B, int T, float* emb_host, int slot,
+                              void* stream);
+int xvb_extractor_wait(xvb_extractor_t* h, int slot);
 /* Per-kernel timing with CUDA events recorded on the launching stream around every kernel of
  * the next extract calls.  xvb_extractor_kernel_times() waits for the last call and returns the
  * number of kernels n (<= max_n) and their durations in ms, in launch order: split, frame layers,

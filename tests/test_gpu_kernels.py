@@ -213,3 +213,45 @@ def test_no_cpu_path():
     m.cuda()
     with pytest.raises(TypeError):
         m.extract_embedding(np.zeros((10, 23), dtype=np.float64))
+
+
+# ---------------------------------------------------------------- BASELINE-size properties
+def test_full_size_batch_invariance_and_padding_properties():
+    """At the BASELINE shape (256 x 200 x 80) the oracle is too slow to replay, so check
+    size-independent properties: (i) an utterance's embedding does not depend on its batch
+    neighbours or position (bit-exact: tiles only regroup rows, the K order is fixed);
+    (ii) all-zero utterances give the bias-only embedding; (iii) sub-batches agree with the oracle."""
+    m, sd = _model(80, 102, "far")
+    feats = onn.synthetic_feats(256, 200, 80, 2024)
+    feats[7] = 0
+    feats[200] = 0
+    full = m.extract_embedding_batch(feats).cpu().numpy()
+    assert np.all(np.isfinite(full)) and full.shape == (256, 512)
+    assert np.array_equal(full[7], full[200])
+    perm = np.random.RandomState(0).permutation(256)
+    assert np.array_equal(m.extract_embedding_batch(feats[perm]).cpu().numpy(), full[perm])
+    assert np.array_equal(m.extract_embedding_batch(feats[:16]).cpu().numpy(), full[:16])
+    assert np.array_equal(m.extract_embedding_batch(feats[100:101]).cpu().numpy(), full[100:101])
+    with torch.no_grad():
+        ref = onn.xvector_forward(sd, torch.from_numpy(feats[[0, 7, 255]]).transpose(1, 2), "far").squeeze(2).numpy()
+    for got, want in zip(full[[0, 7, 255]], ref):
+        assert rel(got, want) < EMB_TOL
+
+
+def test_pipelined_host_path_matches():
+    m, _ = _model(80, 102, "far")
+    ex = m.extractor()
+    feats = [torch.from_numpy(onn.synthetic_feats(32, 200, 80, 50 + i)).pin_memory() for i in range(4)]
+    outs = [torch.empty(32, 512).pin_memory() for _ in range(4)]
+    ex.submit_host(feats[0].data_ptr(), 32, 200, outs[0].data_ptr(), 0)
+    for i in range(1, 4):
+        ex.submit_host(feats[i].data_ptr(), 32, 200, outs[i].data_ptr(), i % 2)
+        ex.wait((i - 1) % 2)
+    ex.wait(1)
+    for f, o in zip(feats, outs):
+        assert np.array_equal(o.numpy(), m.extract_embedding_batch(f.numpy()).cpu().numpy())
+    from asv_subtools_b200 import _lib
+    ex.submit_host(feats[0].data_ptr(), 32, 200, outs[0].data_ptr(), 0)
+    with pytest.raises(_lib.XvbError):                      # slot still in flight
+        ex.submit_host(feats[1].data_ptr(), 32, 200, outs[1].data_ptr(), 0)
+    ex.wait(0)

@@ -43,6 +43,20 @@ def test_center_length_norm_and_column_mean(ops):
     assert rel(y2.cpu().numpy(), osc.length_norm(emb)) < 1e-6
 
 
+def test_speaker_mean(ops):
+    emb, lab = osc.synthetic_speakers(9, 6, 192, 8)
+    perm = np.random.RandomState(1).permutation(emb.shape[0])
+    emb, lab = emb[perm], lab[perm]
+    spk2rows = [np.flatnonzero(lab == s).tolist() for s in range(9)]
+    spk2rows[3] = spk2rows[3][:2]                       # ragged speakers
+    means, counts = ops.speaker_mean(cuda(emb), spk2rows)
+    for s, rows in enumerate(spk2rows):
+        assert counts[s] == len(rows)
+        assert np.allclose(means[s].cpu().numpy(), emb[rows].astype(np.float64).mean(0), atol=1e-6)
+    ref, cnt = osc.speaker_mean(emb, lab, 9)
+    assert np.allclose(means[0].cpu().numpy(), ref[0], atol=1e-6) and cnt[0] == 6
+
+
 def test_cosine_trials_and_matrix(ops):
     e, _ = osc.synthetic_speakers(40, 3, 512, 4)
     t, _ = osc.synthetic_speakers(30, 4, 512, 5)
