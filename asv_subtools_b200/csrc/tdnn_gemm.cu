@@ -50,6 +50,8 @@ struct TdnnGemmParams {
   const float* row_bias;  // per-frame additive term (PLDA row term), may be NULL
   const float* utt_bias;  // per-utterance x column additive term (B, ld_utt), may be NULL
   long long ld_utt;
+  int log2_tb;            // Tb is a power of two
+  int store_mode;         // 0: epilogue slab -> TMA store; 1: slab -> coalesced st.global (no TMA queueing behind loads)
   int num_src;            // 1, or 2: a second A source accumulated with the same weights (W.(x + x2))
   __nv_bfloat16* y_hi;
   __nv_bfloat16* y_lo;
@@ -277,11 +279,12 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
           f[4 * g + 0] = x0; f[4 * g + 1] = x1; f[4 * g + 2] = x2; f[4 * g + 3] = x3;
         }
         const int n = n0 + ch * 32;
+        const bool direct = p.store_mode == 1;
         if (planes) {
-          // the previous TMA store must have finished reading the slab
-          if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          // the previous store must have finished reading the slab
+          if (!direct && leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           asm volatile("bar.sync 1, 256;" ::: "memory");
-          // two slabs of 64-byte rows (SWIZZLE_64B): 16-byte chunk c of row r sits at c ^ ((r>>1)&3)
+          // two slabs of 64-byte rows (SWIZZLE_64B pattern): 16-byte chunk c of row r sits at c ^ ((r>>1)&3)
           uint8_t* sh = slab_base + row * 64;
           uint8_t* sl = slab_base + 8192 + row * 64;
           const int sw = (row >> 1) & 3;
@@ -300,18 +303,29 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
             *reinterpret_cast<uint4*>(sh + ((c ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
             *reinterpret_cast<uint4*>(sl + ((c ^ sw) << 4)) = make_uint4(l[0], l[1], l[2], l[3]);
           }
-          fence_proxy_async();
+          if (!direct) fence_proxy_async();
           asm volatile("bar.sync 2, 256;" ::: "memory");
-          if (leader) {
+          if (direct) {
+            // transpose through the slab: a warp now owns 8 rows x 64 contiguous bytes per instruction
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int item = etid + 256 * k;
+              const int plane = item >> 9, rr = (item & 511) >> 2, cc = item & 3;
+              const int gb = b0 + (rr >> p.log2_tb), gt = t0 + (rr & (p.Tb - 1)), col = n + cc * 8;
+              const uint4 v = *reinterpret_cast<const uint4*>(slab_base + plane * 8192 + rr * 64 + ((cc ^ ((rr >> 1) & 3)) << 4));
+              if (gb < p.B && gt < p.T && col < p.Cout)
+                *reinterpret_cast<uint4*>((plane ? p.y_lo : p.y_hi) + ((long long)gb * p.T + gt) * p.ldy + col) = v;
+            }
+          } else if (leader) {
             tma_store_3d(&map_y_hi, slab_base, n, t0, b0);
             tma_store_3d(&map_y_lo, slab_base + 8192, n, t0, b0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
         if (f32o) {
-          if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (!direct && leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           asm volatile("bar.sync 1, 256;" ::: "memory");
-          // one slab of 128-byte rows (SWIZZLE_128B): chunk c of row r sits at c ^ (r & 7)
+          // one slab of 128-byte rows (SWIZZLE_128B pattern): chunk c of row r sits at c ^ (r & 7)
           uint8_t* sf = slab_base + row * 128;
           const int sw = row & 7;
 #pragma unroll
@@ -319,9 +333,19 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
             const int c = half * 4 + g;
             *reinterpret_cast<float4*>(sf + ((c ^ sw) << 4)) = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
           }
-          fence_proxy_async();
+          if (!direct) fence_proxy_async();
           asm volatile("bar.sync 2, 256;" ::: "memory");
-          if (leader) {
+          if (direct) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int item = etid + 256 * k;
+              const int rr = item >> 3, cc = item & 7;
+              const int gb = b0 + (rr >> p.log2_tb), gt = t0 + (rr & (p.Tb - 1)), col = n + cc * 4;
+              const float4 v = *reinterpret_cast<const float4*>(slab_base + rr * 128 + ((cc ^ (rr & 7)) << 4));
+              if (gb < p.B && gt < p.T && col < p.Cout)
+                *reinterpret_cast<float4*>(p.y_f32 + ((long long)gb * p.T + gt) * p.ldyf + col) = v;
+            }
+          } else if (leader) {
             tma_store_3d(&map_y_f32, slab_base, n, t0, b0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
@@ -428,6 +452,17 @@ static int gemm_cta_mode() {
   if (mode == 0) {
     const char* e = getenv("XVB_GEMM_CTA");
     mode = (e && e[0] == '1') ? 1 : 2;
+  }
+  return mode;
+}
+
+// XVB_GEMM_STORE=tma routes the epilogue through TMA stores; default: coalesced st.global from the slab
+// (TMA stores queue behind the producer's 64 KB stage loads on the same TMA unit, ~1.5 us per chunk).
+static int gemm_store_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("XVB_GEMM_STORE");
+    mode = (e && e[0] == 't') ? 0 : 1;
   }
   return mode;
 }
@@ -554,6 +589,13 @@ int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream) {
   p.bias = a.bias; p.scale = a.bn_scale; p.shift = a.bn_shift; p.row_bias = a.row_bias;
   p.utt_bias = a.utt_bias; p.ld_utt = a.ld_utt_bias;
   p.num_src = a.x2_hi ? 2 : 1;
+  p.log2_tb = 0;
+  while ((1 << p.log2_tb) < p.Tb) ++p.log2_tb;
+  p.store_mode = gemm_store_mode();
+  if (p.store_mode == 1) {  // vector stores need whole 16-byte groups inside the row
+    if (a.y_hi) XVB_CHECK_ARG(Cout % 8 == 0, "xvb_tdnn_affine: plane output needs Cout%%8==0 (Cout=%d)", Cout);
+    if (a.y_f32) XVB_CHECK_ARG(Cout % 4 == 0, "xvb_tdnn_affine: fp32 output needs Cout%%4==0 (Cout=%d)", Cout);
+  }
   p.y_hi = reinterpret_cast<__nv_bfloat16*>(a.y_hi);
   p.y_lo = reinterpret_cast<__nv_bfloat16*>(a.y_lo);
   p.ldy = a.ldy; p.y_f32 = a.y_f32; p.ldyf = a.ldyf;
@@ -576,7 +618,8 @@ int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream) {
   const int mode = gemm_cta_mode();
   const void* w_hi = a.w_hi;
   const void* w_lo = a.w_lo;
-  if (mode == 2 && Cout >= 256 && m_tiles * ((Cout + 255) / 256) >= sms)
+  static const int force_bn = getenv("XVB_GEMM_BN") ? atoi(getenv("XVB_GEMM_BN")) : 0;  // tuning knob
+  if (mode == 2 && force_bn != 128 && Cout >= 256 && m_tiles * ((Cout + 255) / 256) >= sms)
     return launch_gemm<256, 2>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
   if (mode == 2 && Cout >= 128 && m_tiles * ((Cout + 127) / 128) >= sms)
     return launch_gemm<128, 2>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
