@@ -51,6 +51,7 @@ struct TdnnGemmParams {
   const float* utt_bias;  // per-utterance x column additive term (B, ld_utt), may be NULL
   long long ld_utt;
   int log2_tb;            // Tb is a power of two
+  int debug;              // timing experiments only (XVB_GEMM_DEBUG): bit0 skip epilogue work, bit1 skip MMA issue
   int store_mode;         // 0: epilogue slab -> TMA store; 1: slab -> coalesced st.global (no TMA queueing behind loads)
   int num_src;            // 1, or 2: a second A source accumulated with the same weights (W.(x + x2))
   __nv_bfloat16* y_hi;
@@ -63,27 +64,37 @@ struct TdnnGemmParams {
 // kCta = 1: one CTA per 128 x BLOCK_N tile.  kCta = 2: a CTA pair (cluster of 2, tcgen05
 // cta_group::2) per 256 x BLOCK_N tile -- each CTA stages its own 128 A rows and HALF of the
 // weight tile, so operand traffic per MMA flop drops by a third and a third stage fits.
-template <int BLOCK_N, int kCta>
+// kNSub = 2 ("wide"): one tile spans TWO adjacent BLOCK_N column blocks that share the A tile, so the
+// frame matrix is fetched once per 512 output channels instead of once per 256 (the operand stream
+// out of L2, not the tensor pipe, bounds this kernel: measured 9.2 TB/s with the MMAs skipped).  The
+// price: the 512 TMEM columns hold a single accumulator, so the epilogue no longer overlaps the
+// next tile's MMAs (its TMA loads still run ahead).
+template <int BLOCK_N, int kCta, int kNSub>
 struct GemmCfg {
-  static constexpr int kBRows = BLOCK_N / kCta;   // weight rows staged by one CTA
-  static constexpr int kBBytes = kBRows * kBlockK * 2;
-  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kBRows = BLOCK_N / kCta;   // weight rows staged by one CTA per column block
+  static constexpr int kBBytes = kBRows * kBlockK * 2;          // one plane of one column block
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kNSub * kBBytes;
   static constexpr int kStages = (192 * 1024) / kStageBytes > 6 ? 6 : (192 * 1024) / kStageBytes;
-  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // two accumulator stages
+  static constexpr int kAccStages = kNSub == 1 ? 2 : 1;
+  static constexpr int kTileN = BLOCK_N * kNSub;
+  static constexpr int kTmemCols = kAccStages * kTileN < 32 ? 32 : kAccStages * kTileN;
+  static_assert(kTmemCols <= 512, "TMEM has 512 columns");
   static constexpr int kSmemBytes =
       kStages * kStageBytes + kSlabBytes + 2 * kParamBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
   static_assert(kStages >= 2, "need at least a double-buffered operand pipeline");
 };
 
-template <int BLOCK_N, int kCta>
+template <int BLOCK_N, int kCta, int kNSub>
 __global__ void __launch_bounds__(kNumThreads, 1)
 tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                         const __grid_constant__ CUtensorMap map_a2_hi, const __grid_constant__ CUtensorMap map_a2_lo,
                         const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                         const __grid_constant__ CUtensorMap map_y_hi, const __grid_constant__ CUtensorMap map_y_lo,
                         const __grid_constant__ CUtensorMap map_y_f32, const __grid_constant__ TdnnGemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N, kCta>;
+  using Cfg = GemmCfg<BLOCK_N, kCta, kNSub>;
+  constexpr int kAccStages = Cfg::kAccStages;
+  constexpr int kTileN = Cfg::kTileN;
   constexpr int kStages = Cfg::kStages;
   constexpr int kBBytes = Cfg::kBBytes;
   constexpr int kStageBytes = Cfg::kStageBytes;
@@ -114,7 +125,7 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
       mbar_init(&full_bar[i], kCta);   // leader's barrier: one producer arrival per CTA + all TMA bytes
       mbar_init(&empty_bar[i], 1);     // per CTA, released by (multicast) tcgen05.commit
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&tmem_full_bar[i], 1);                          // per CTA, (multicast) commit
       mbar_init(&tmem_empty_bar[i], kCta * kNumEpiWarps * 32);  // leader's: every epilogue thread of the pair
     }
@@ -137,7 +148,7 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
       for (int tile = tile_first; tile < p.num_tiles; tile += tile_step) {
         const int m_blk = (tile / p.num_n_blk) * kCta + (int)cta_rank, n_blk = tile % p.num_n_blk;
         const int b0 = (m_blk / p.num_t_blk) * p.Bb, t0 = (m_blk % p.num_t_blk) * p.Tb;  // may be fully out of
-        const int n0 = n_blk * BLOCK_N + (int)cta_rank * Cfg::kBRows;                     // range: TMA zero-fills
+        const int n0 = n_blk * kTileN + (int)cta_rank * Cfg::kBRows;                      // range: TMA zero-fills
         for (int src = 0; src < p.num_src; ++src) {
         const CUtensorMap* ma_hi = src == 0 ? &map_a_hi : &map_a2_hi;
         const CUtensorMap* ma_lo = src == 0 ? &map_a_lo : &map_a2_lo;
@@ -151,16 +162,22 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
               mbar_expect_tx(&full_bar[stage], kStageBytes);
               tma_load_3d(s, ma_hi, &full_bar[stage], cb * kBlockK, tt, b0);
               tma_load_3d(s + kABytes, ma_lo, &full_bar[stage], cb * kBlockK, tt, b0);
-              tma_load_2d(s + 2 * kABytes, &map_w_hi, &full_bar[stage], kw, n0);
-              tma_load_2d(s + 2 * kABytes + kBBytes, &map_w_lo, &full_bar[stage], kw, n0);
+#pragma unroll
+              for (int ns = 0; ns < kNSub; ++ns) {
+                tma_load_2d(s + 2 * kABytes + ns * kBBytes, &map_w_hi, &full_bar[stage], kw, n0 + ns * BLOCK_N);
+                tma_load_2d(s + 2 * kABytes + (kNSub + ns) * kBBytes, &map_w_lo, &full_bar[stage], kw, n0 + ns * BLOCK_N);
+              }
             } else {
               // both CTAs' bytes complete on the LEADER's barrier (peer-bit-masked address)
               if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes);
               else mbar_arrive_cluster(&full_bar[stage], 0);
               tma_load_3d_2sm(s, ma_hi, &full_bar[stage], cb * kBlockK, tt, b0);
               tma_load_3d_2sm(s + kABytes, ma_lo, &full_bar[stage], cb * kBlockK, tt, b0);
-              tma_load_2d_2sm(s + 2 * kABytes, &map_w_hi, &full_bar[stage], kw, n0);
-              tma_load_2d_2sm(s + 2 * kABytes + kBBytes, &map_w_lo, &full_bar[stage], kw, n0);
+#pragma unroll
+              for (int ns = 0; ns < kNSub; ++ns) {
+                tma_load_2d_2sm(s + 2 * kABytes + ns * kBBytes, &map_w_hi, &full_bar[stage], kw, n0 + ns * BLOCK_N);
+                tma_load_2d_2sm(s + 2 * kABytes + (kNSub + ns) * kBBytes, &map_w_lo, &full_bar[stage], kw, n0 + ns * BLOCK_N);
+              }
             }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
@@ -178,10 +195,10 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
       uint32_t phase = 0;
       uint32_t it = 0;
       for (int tile = tile_first; tile < p.num_tiles; tile += tile_step, ++it) {
-        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        const uint32_t acc = kAccStages == 2 ? (it & 1) : 0, acc_phase = kAccStages == 2 ? ((it >> 1) & 1) : (it & 1);
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        const uint32_t tmem_d = tmem_base + acc * kTileN;
         uint32_t accumulate = 0;
         for (int kb = 0; kb < num_kblk; ++kb) {
           const int cb = kb % p.num_cblk;
@@ -192,14 +209,18 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
           const uint64_t da_hi = make_kmajor_desc<128>(sa);
           const uint64_t da_lo = make_kmajor_desc<128>(sa + kABytes);
-          const uint64_t db_hi = make_kmajor_desc<128>(sa + 2 * kABytes);
-          const uint64_t db_lo = make_kmajor_desc<128>(sa + 2 * kABytes + kBBytes);
-          for (int s = 0; s < nsteps; ++s) {
+          for (int s = 0; s < ((p.debug & 2) ? 0 : nsteps); ++s) {
             const uint64_t koff = (uint64_t)(s * 32 >> 4);  // 16 bf16 = 32 bytes along K inside the swizzle row
-            umma_bf16<kCta>(tmem_d, da_lo + koff, db_hi + koff, idesc, accumulate);
+#pragma unroll
+            for (int ns = 0; ns < kNSub; ++ns) {
+              const uint64_t db_hi = make_kmajor_desc<128>(sa + 2 * kABytes + ns * kBBytes);
+              const uint64_t db_lo = make_kmajor_desc<128>(sa + 2 * kABytes + (kNSub + ns) * kBBytes);
+              const uint32_t d = tmem_d + ns * BLOCK_N;
+              umma_bf16<kCta>(d, da_lo + koff, db_hi + koff, idesc, accumulate);
+              umma_bf16<kCta>(d, da_hi + koff, db_lo + koff, idesc, 1);
+              umma_bf16<kCta>(d, da_hi + koff, db_hi + koff, idesc, 1);
+            }
             accumulate = 1;
-            umma_bf16<kCta>(tmem_d, da_hi + koff, db_lo + koff, idesc, 1);
-            umma_bf16<kCta>(tmem_d, da_hi + koff, db_hi + koff, idesc, 1);
           }
           umma_commit<kCta>(&empty_bar[stage]);  // frees the smem slot (in both CTAs) once these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -229,36 +250,38 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     const bool f32o = p.y_f32 != nullptr;
     uint32_t it = 0;
     for (int tile = tile_first; tile < p.num_tiles; tile += tile_step, ++it) {
-      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      const uint32_t acc = kAccStages == 2 ? (it & 1) : 0, acc_phase = kAccStages == 2 ? ((it >> 1) & 1) : (it & 1);
       const int m_blk = (tile / p.num_n_blk) * kCta + (int)cta_rank, n_blk = tile % p.num_n_blk;
       const int b0 = (m_blk / p.num_t_blk) * p.Bb, t0 = (m_blk % p.num_t_blk) * p.Tb;
       const int b = b0 + row / p.Tb, t = t0 + row % p.Tb;
       const bool valid = (b < p.B) && (t < p.T);
-      const int n0 = n_blk * BLOCK_N;
+      const int n0 = n_blk * kTileN;
       const float rbias = (p.row_bias && valid) ? __ldg(p.row_bias + (long long)b * p.T + t) : 0.f;
       const float* ub = (p.utt_bias && valid) ? p.utt_bias + (long long)b * p.ld_utt + n0 + half * 16 : nullptr;
       // stage this tile's per-column parameters (double-buffered by accumulator stage; the
       // barrier also orders reuse: nobody can be two tiles ahead of the slowest epilogue thread)
-      float* prm = param_base + acc * (3 * 256);
-      if (etid < BLOCK_N) {
-        const int c = n0 + etid;
+      // layout: kAccStages buffers of [bias | scale | shift], each kTileN floats (6 KB in total either way)
+      float* prm = param_base + acc * (3 * kTileN);
+      if constexpr (kAccStages == 1) asm volatile("bar.sync 3, 256;" ::: "memory");  // single buffer: everyone left the previous tile
+      for (int e = etid; e < kTileN; e += kNumEpiWarps * 32) {
+        const int c = n0 + e;
         const bool in = c < p.Cout;
-        prm[etid] = (in && p.bias) ? __ldg(p.bias + c) : 0.f;
-        prm[256 + etid] = (in && bn) ? __ldg(p.scale + c) : 1.f;
-        prm[512 + etid] = (in && bn) ? __ldg(p.shift + c) : 0.f;
+        prm[e] = (in && p.bias) ? __ldg(p.bias + c) : 0.f;
+        prm[kTileN + e] = (in && bn) ? __ldg(p.scale + c) : 1.f;
+        prm[2 * kTileN + e] = (in && bn) ? __ldg(p.shift + c) : 0.f;
       }
       asm volatile("bar.sync 3, 256;" ::: "memory");
       int nch = (p.Cout - n0 + 31) >> 5;
-      nch = nch > BLOCK_N / 32 ? BLOCK_N / 32 : nch;
+      nch = nch > kTileN / 32 ? kTileN / 32 : nch;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + half * 16;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kTileN + half * 16;
 
       auto process = [&](uint32_t (&v)[16], int ch) {
         const int pc = ch * 32 + half * 16;
         const float4* pb = reinterpret_cast<const float4*>(prm + pc);
-        const float4* ps = reinterpret_cast<const float4*>(prm + 256 + pc);
-        const float4* pt = reinterpret_cast<const float4*>(prm + 512 + pc);
+        const float4* ps = reinterpret_cast<const float4*>(prm + kTileN + pc);
+        const float4* pt = reinterpret_cast<const float4*>(prm + 2 * kTileN + pc);
         float f[16];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -354,7 +377,8 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
 
       uint32_t va[16], vb[16];
       int ch = 0;
-      tmem_ld_32x16(trow, va);
+      if (p.debug & 1) ch = nch;
+      else tmem_ld_32x16(trow, va);
       while (ch < nch) {
         tmem_ld_wait();
         if (ch + 1 < nch) tmem_ld_32x16(trow + (ch + 1) * 32, vb);
@@ -456,13 +480,13 @@ static int gemm_cta_mode() {
   return mode;
 }
 
-// XVB_GEMM_STORE=tma routes the epilogue through TMA stores; default: coalesced st.global from the slab
-// (TMA stores queue behind the producer's 64 KB stage loads on the same TMA unit, ~1.5 us per chunk).
+// Epilogue store path: TMA stores from the swizzled slab (default), or XVB_GEMM_STORE=direct for
+// coalesced st.global after a transpose through the same slab (measured 5-10 % slower, kept as a knob).
 static int gemm_store_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("XVB_GEMM_STORE");
-    mode = (e && e[0] == 't') ? 0 : 1;
+    mode = (e && e[0] == 'd') ? 1 : 0;
   }
   return mode;
 }
@@ -497,23 +521,23 @@ static int make_out_map(CUtensorMap* m, const void* base, int esize, int C, int 
   return XVB_OK;
 }
 
-template <int BLOCK_N, int kCta>
+template <int BLOCK_N, int kCta, int kNSub = 1>
 static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& ma2_hi,
                        const CUtensorMap& ma2_lo, const void* w_hi, const void* w_lo, TdnnGemmParams& p,
                        cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N, kCta>;
+  using Cfg = GemmCfg<BLOCK_N, kCta, kNSub>;
   CUtensorMap mw_hi, mw_lo;
   const long long K = (long long)p.ntaps * p.cin_p16;
   int rc = make_weight_map(&mw_hi, w_hi, K, p.Cout, Cfg::kBRows);
   if (rc) return rc;
   rc = make_weight_map(&mw_lo, w_lo, K, p.Cout, Cfg::kBRows);
   if (rc) return rc;
-  p.num_n_blk = (p.Cout + BLOCK_N - 1) / BLOCK_N;
+  p.num_n_blk = (p.Cout + Cfg::kTileN - 1) / Cfg::kTileN;
   const int num_m_units = (p.num_t_blk * p.num_b_blk + kCta - 1) / kCta;  // 128-row blocks, or pairs of them
   p.num_tiles = num_m_units * p.num_n_blk;
   static bool attr_set = false;
   if (!attr_set) {
-    XVB_CUDA(cudaFuncSetAttribute(tdnn_gemm_bf16x3_kernel<BLOCK_N, kCta>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    XVB_CUDA(cudaFuncSetAttribute(tdnn_gemm_bf16x3_kernel<BLOCK_N, kCta, kNSub>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -543,7 +567,7 @@ static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  XVB_CUDA(cudaLaunchKernelEx(&cfg, tdnn_gemm_bf16x3_kernel<BLOCK_N, kCta>, ma_hi, ma_lo, ma2_hi, ma2_lo, mw_hi, mw_lo,
+  XVB_CUDA(cudaLaunchKernelEx(&cfg, tdnn_gemm_bf16x3_kernel<BLOCK_N, kCta, kNSub>, ma_hi, ma_lo, ma2_hi, ma2_lo, mw_hi, mw_lo,
                               my_hi, my_lo, my_f32, p));
   XVB_LAUNCH_CHECK();
   return XVB_OK;
@@ -592,6 +616,8 @@ int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream) {
   p.log2_tb = 0;
   while ((1 << p.log2_tb) < p.Tb) ++p.log2_tb;
   p.store_mode = gemm_store_mode();
+  static const int dbg = getenv("XVB_GEMM_DEBUG") ? atoi(getenv("XVB_GEMM_DEBUG")) : 0;
+  p.debug = dbg;
   if (p.store_mode == 1) {  // vector stores need whole 16-byte groups inside the row
     if (a.y_hi) XVB_CHECK_ARG(Cout % 8 == 0, "xvb_tdnn_affine: plane output needs Cout%%8==0 (Cout=%d)", Cout);
     if (a.y_f32) XVB_CHECK_ARG(Cout % 4 == 0, "xvb_tdnn_affine: fp32 output needs Cout%%4==0 (Cout=%d)", Cout);
@@ -618,7 +644,10 @@ int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream) {
   const int mode = gemm_cta_mode();
   const void* w_hi = a.w_hi;
   const void* w_lo = a.w_lo;
-  static const int force_bn = getenv("XVB_GEMM_BN") ? atoi(getenv("XVB_GEMM_BN")) : 0;  // tuning knob
+  static const int force_bn = getenv("XVB_GEMM_BN") ? atoi(getenv("XVB_GEMM_BN")) : 0;  // tuning knobs
+  static const int wide = getenv("XVB_GEMM_WIDE") ? atoi(getenv("XVB_GEMM_WIDE")) : 1;
+  if (mode == 2 && wide && force_bn != 128 && Cout >= 512 && (m_tiles / 2) * ((Cout + 511) / 512) >= sms / 2)
+    return launch_gemm<256, 2, 2>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
   if (mode == 2 && force_bn != 128 && Cout >= 256 && m_tiles * ((Cout + 255) / 256) >= sms)
     return launch_gemm<256, 2>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
   if (mode == 2 && Cout >= 128 && m_tiles * ((Cout + 127) / 128) >= sms)
