@@ -261,14 +261,14 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
       // stage this tile's per-column parameters (double-buffered by accumulator stage; the
       // barrier also orders reuse: nobody can be two tiles ahead of the slowest epilogue thread)
       // layout: kAccStages buffers of [bias | scale | shift], each kTileN floats (6 KB in total either way)
-      float* prm = param_base + acc * (3 * kTileN);
+      const uint32_t prm = smem_u32(param_base) + acc * (3 * kTileN * 4);
       if constexpr (kAccStages == 1) asm volatile("bar.sync 3, 256;" ::: "memory");  // single buffer: everyone left the previous tile
       for (int e = etid; e < kTileN; e += kNumEpiWarps * 32) {
         const int c = n0 + e;
         const bool in = c < p.Cout;
-        prm[e] = (in && p.bias) ? __ldg(p.bias + c) : 0.f;
-        prm[kTileN + e] = (in && bn) ? __ldg(p.scale + c) : 1.f;
-        prm[2 * kTileN + e] = (in && bn) ? __ldg(p.shift + c) : 0.f;
+        st_shared_f32(prm + e * 4, (in && p.bias) ? __ldg(p.bias + c) : 0.f);
+        st_shared_f32(prm + (kTileN + e) * 4, (in && bn) ? __ldg(p.scale + c) : 1.f);
+        st_shared_f32(prm + (2 * kTileN + e) * 4, (in && bn) ? __ldg(p.shift + c) : 0.f);
       }
       asm volatile("bar.sync 3, 256;" ::: "memory");
       int nch = (p.Cout - n0 + 31) >> 5;
@@ -276,28 +276,37 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kTileN + half * 16;
+      const uint32_t slab = smem_u32(slab_base);
+      const float relu_floor = relu ? 0.f : -INFINITY;   // branch-free ReLU switch
+      const bool extras = rbias != 0.f || ub != nullptr || act_tanh || act_sigmoid;
 
       auto process = [&](uint32_t (&v)[16], int ch) {
         const int pc = ch * 32 + half * 16;
-        const float4* pb = reinterpret_cast<const float4*>(prm + pc);
-        const float4* ps = reinterpret_cast<const float4*>(prm + kTileN + pc);
-        const float4* pt = reinterpret_cast<const float4*>(prm + 2 * kTileN + pc);
         float f[16];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const float4 bb = pb[g], ss = ps[g], tt = pt[g];
-          float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ub && n0 + pc + 4 * g < p.Cout) u = __ldg(reinterpret_cast<const float4*>(ub + ch * 32) + g);
-          float x0 = __uint_as_float(v[4 * g + 0]) + rbias + bb.x + u.x;
-          float x1 = __uint_as_float(v[4 * g + 1]) + rbias + bb.y + u.y;
-          float x2 = __uint_as_float(v[4 * g + 2]) + rbias + bb.z + u.z;
-          float x3 = __uint_as_float(v[4 * g + 3]) + rbias + bb.w + u.w;
-          if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
-          x0 = fmaf(x0, ss.x, tt.x); x1 = fmaf(x1, ss.y, tt.y); x2 = fmaf(x2, ss.z, tt.z); x3 = fmaf(x3, ss.w, tt.w);
-          if (act_tanh) { x0 = tanhf(x0); x1 = tanhf(x1); x2 = tanhf(x2); x3 = tanhf(x3); }
-          if (act_sigmoid) {
-            x0 = 1.f / (1.f + expf(-x0)); x1 = 1.f / (1.f + expf(-x1));
-            x2 = 1.f / (1.f + expf(-x2)); x3 = 1.f / (1.f + expf(-x3));
+          const float4 bb = ld_shared_f4(prm + (pc + 4 * g) * 4);
+          const float4 ss = ld_shared_f4(prm + (kTileN + pc + 4 * g) * 4);
+          const float4 tt = ld_shared_f4(prm + (2 * kTileN + pc + 4 * g) * 4);
+          float x0 = __uint_as_float(v[4 * g + 0]) + bb.x;
+          float x1 = __uint_as_float(v[4 * g + 1]) + bb.y;
+          float x2 = __uint_as_float(v[4 * g + 2]) + bb.z;
+          float x3 = __uint_as_float(v[4 * g + 3]) + bb.w;
+          if (extras) {  // warp-uniform: PLDA row term / per-utterance bias (ECAPA attention)
+            float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ub && n0 + pc + 4 * g < p.Cout) u = __ldg(reinterpret_cast<const float4*>(ub + ch * 32) + g);
+            x0 += rbias + u.x; x1 += rbias + u.y; x2 += rbias + u.z; x3 += rbias + u.w;
+          }
+          x0 = fmaf(fmaxf(x0, relu_floor), ss.x, tt.x);
+          x1 = fmaf(fmaxf(x1, relu_floor), ss.y, tt.y);
+          x2 = fmaf(fmaxf(x2, relu_floor), ss.z, tt.z);
+          x3 = fmaf(fmaxf(x3, relu_floor), ss.w, tt.w);
+          if (extras) {
+            if (act_tanh) { x0 = tanhf(x0); x1 = tanhf(x1); x2 = tanhf(x2); x3 = tanhf(x3); }
+            if (act_sigmoid) {
+              x0 = 1.f / (1.f + expf(-x0)); x1 = 1.f / (1.f + expf(-x1));
+              x2 = 1.f / (1.f + expf(-x2)); x3 = 1.f / (1.f + expf(-x3));
+            }
           }
           f[4 * g + 0] = x0; f[4 * g + 1] = x1; f[4 * g + 2] = x2; f[4 * g + 3] = x3;
         }
@@ -308,8 +317,7 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
           if (!direct && leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           asm volatile("bar.sync 1, 256;" ::: "memory");
           // two slabs of 64-byte rows (SWIZZLE_64B pattern): 16-byte chunk c of row r sits at c ^ ((r>>1)&3)
-          uint8_t* sh = slab_base + row * 64;
-          uint8_t* sl = slab_base + 8192 + row * 64;
+          const uint32_t sh = slab + row * 64, sl = slab + 8192 + row * 64;
           const int sw = (row >> 1) & 3;
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
@@ -323,8 +331,8 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
               l[k] = pack_bf16x2(l0, l1);
             }
             const int c = half * 2 + g;
-            *reinterpret_cast<uint4*>(sh + ((c ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<uint4*>(sl + ((c ^ sw) << 4)) = make_uint4(l[0], l[1], l[2], l[3]);
+            st_shared_v4(sh + ((c ^ sw) << 4), h[0], h[1], h[2], h[3]);
+            st_shared_v4(sl + ((c ^ sw) << 4), l[0], l[1], l[2], l[3]);
           }
           if (!direct) fence_proxy_async();
           asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -335,9 +343,9 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
               const int item = etid + 256 * k;
               const int plane = item >> 9, rr = (item & 511) >> 2, cc = item & 3;
               const int gb = b0 + (rr >> p.log2_tb), gt = t0 + (rr & (p.Tb - 1)), col = n + cc * 8;
-              const uint4 v = *reinterpret_cast<const uint4*>(slab_base + plane * 8192 + rr * 64 + ((cc ^ ((rr >> 1) & 3)) << 4));
+              const uint4 w = ld_shared_u4(slab + plane * 8192 + rr * 64 + ((cc ^ ((rr >> 1) & 3)) << 4));
               if (gb < p.B && gt < p.T && col < p.Cout)
-                *reinterpret_cast<uint4*>((plane ? p.y_lo : p.y_hi) + ((long long)gb * p.T + gt) * p.ldy + col) = v;
+                *reinterpret_cast<uint4*>((plane ? p.y_lo : p.y_hi) + ((long long)gb * p.T + gt) * p.ldy + col) = w;
             }
           } else if (leader) {
             tma_store_3d(&map_y_hi, slab_base, n, t0, b0);
@@ -349,12 +357,13 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
           if (!direct && leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           asm volatile("bar.sync 1, 256;" ::: "memory");
           // one slab of 128-byte rows (SWIZZLE_128B pattern): chunk c of row r sits at c ^ (r & 7)
-          uint8_t* sf = slab_base + row * 128;
+          const uint32_t sf = slab + row * 128;
           const int sw = row & 7;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int c = half * 4 + g;
-            *reinterpret_cast<float4*>(sf + ((c ^ sw) << 4)) = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+            st_shared_v4(sf + ((c ^ sw) << 4), __float_as_uint(f[4 * g]), __float_as_uint(f[4 * g + 1]),
+                         __float_as_uint(f[4 * g + 2]), __float_as_uint(f[4 * g + 3]));
           }
           if (!direct) fence_proxy_async();
           asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -364,9 +373,9 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
               const int item = etid + 256 * k;
               const int rr = item >> 3, cc = item & 7;
               const int gb = b0 + (rr >> p.log2_tb), gt = t0 + (rr & (p.Tb - 1)), col = n + cc * 4;
-              const float4 v = *reinterpret_cast<const float4*>(slab_base + rr * 128 + ((cc ^ (rr & 7)) << 4));
+              const float4 w = ld_shared_f4(slab + rr * 128 + ((cc ^ (rr & 7)) << 4));
               if (gb < p.B && gt < p.T && col < p.Cout)
-                *reinterpret_cast<float4*>(p.y_f32 + ((long long)gb * p.T + gt) * p.ldyf + col) = v;
+                *reinterpret_cast<float4*>(p.y_f32 + ((long long)gb * p.T + gt) * p.ldyf + col) = w;
             }
           } else if (leader) {
             tma_store_3d(&map_y_f32, slab_base, n, t0, b0);
