@@ -347,7 +347,7 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
               if (gb < p.B && gt < p.T && col < p.Cout)
                 *reinterpret_cast<uint4*>((plane ? p.y_lo : p.y_hi) + ((long long)gb * p.T + gt) * p.ldy + col) = w;
             }
-          } else if (leader) {
+          } else if (leader && !(p.debug & 4)) {
             tma_store_3d(&map_y_hi, slab_base, n, t0, b0);
             tma_store_3d(&map_y_lo, slab_base + 8192, n, t0, b0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -377,7 +377,7 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
               if (gb < p.B && gt < p.T && col < p.Cout)
                 *reinterpret_cast<float4*>(p.y_f32 + ((long long)gb * p.T + gt) * p.ldyf + col) = w;
             }
-          } else if (leader) {
+          } else if (leader && !(p.debug & 4)) {
             tma_store_3d(&map_y_f32, slab_base, n, t0, b0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
@@ -390,11 +390,11 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
       else tmem_ld_32x16(trow, va);
       while (ch < nch) {
         tmem_ld_wait();
-        if (ch + 1 < nch) tmem_ld_32x16(trow + (ch + 1) * 32, vb);
+        if (ch + 1 < nch && !(p.debug & 8)) tmem_ld_32x16(trow + (ch + 1) * 32, vb);
         process(va, ch);
         if (++ch >= nch) break;
         tmem_ld_wait();
-        if (ch + 1 < nch) tmem_ld_32x16(trow + (ch + 1) * 32, va);
+        if (ch + 1 < nch && !(p.debug & 8)) tmem_ld_32x16(trow + (ch + 1) * 32, va);
         process(vb, ch);
         ++ch;
       }
@@ -654,7 +654,9 @@ int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream) {
   const void* w_hi = a.w_hi;
   const void* w_lo = a.w_lo;
   static const int force_bn = getenv("XVB_GEMM_BN") ? atoi(getenv("XVB_GEMM_BN")) : 0;  // tuning knobs
-  static const int wide = getenv("XVB_GEMM_WIDE") ? atoi(getenv("XVB_GEMM_WIDE")) : 1;
+  // wide tiles cut the operand stream by 25-37 % but serialise the epilogue with the MMAs (one
+  // accumulator in TMEM); measured slower end to end (profiles/r01_gemm_experiments.md), so opt-in.
+  static const int wide = getenv("XVB_GEMM_WIDE") ? atoi(getenv("XVB_GEMM_WIDE")) : 0;
   if (mode == 2 && wide && force_bn != 128 && Cout >= 512 && (m_tiles / 2) * ((Cout + 511) / 512) >= sms / 2)
     return launch_gemm<256, 2, 2>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
   if (mode == 2 && force_bn != 128 && Cout >= 256 && m_tiles * ((Cout + 255) / 256) >= sms)
