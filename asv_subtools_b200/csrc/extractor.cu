@@ -57,6 +57,9 @@ struct xvb_extractor {
   int max_c = 0, max_seg_c = 0;
   int last_launches = 0;
   // optional per-kernel CUDA-event timing on the launching stream (bench.py roofline)
+  bool fused_pooling = true;
+  float* pool_partial = nullptr;
+  size_t pool_partial_cap = 0;
   bool profiling = false;
   std::vector<cudaEvent_t> events;
   int events_used = 0;
@@ -227,20 +230,42 @@ extern "C" int xvb_extractor_extract(xvb_extractor_t* h, const float* feats, int
   const uint16_t* x_hi = h->in_hi;
   const uint16_t* x_lo = h->in_lo;
   int64_t ldx = h->ldf;
+  int pool_tb = 0;
+  const int pool_blocks = xvb_pool_partial_blocks(B, T, &pool_tb);
   for (size_t i = 0; i < h->frame.size(); ++i) {
     const Layer& L = h->frame[i];
     const bool last = i + 1 == h->frame.size();
     uint16_t* y_hi = last ? nullptr : h->act_hi[i & 1];
     uint16_t* y_lo = last ? nullptr : h->act_lo[i & 1];
-    rc = xvb_tdnn_affine(x_hi, x_lo, ldx, L.w_hi, L.w_lo, L.bias, L.scale, L.shift, L.flags, L.ctx, L.ntaps, y_hi, y_lo,
-                         L.Cout, last ? h->last_f32 : nullptr, L.Cout, B, T, L.Cin, L.Cout, stream);
+    xvb_tdnn_args_t a{};
+    a.x_hi = x_hi; a.x_lo = x_lo; a.ldx = ldx; a.w_hi = L.w_hi; a.w_lo = L.w_lo;
+    a.bias = L.bias; a.bn_scale = L.scale; a.bn_shift = L.shift; a.flags = L.flags;
+    a.context_host = L.ctx; a.ntaps = L.ntaps;
+    a.y_hi = y_hi; a.y_lo = y_lo; a.ldy = L.Cout;
+    a.B = B; a.T = T; a.Cin = L.Cin; a.Cout = L.Cout;
+    if (last && h->fused_pooling) {
+      const size_t need = (size_t)pool_blocks * B * 2 * L.Cout;
+      if (need > h->pool_partial_cap) {
+        cudaFree(h->pool_partial);
+        if ((rc = dev_alloc(&h->pool_partial, need))) return rc;
+        h->pool_partial_cap = need;
+      }
+      a.pool_partial = h->pool_partial;
+    } else if (last) {
+      a.y_f32 = h->last_f32; a.ldyf = L.Cout;
+    }
+    rc = xvb_tdnn_affine_ex(&a, stream);
     if (rc) return rc;
     if ((rc = h->mark(cs))) return rc;
     x_hi = y_hi; x_lo = y_lo; ldx = L.Cout;
   }
   // 3. statistics pooling (xvector.py:90, pooling.py:58-67)
   const int cl = h->frame.back().Cout;
-  rc = xvb_stats_pool(h->last_f32, cl, B, T, cl, h->pooling_eps, h->stats, h->stats_hi, h->stats_lo, 2 * cl, stream);
+  if (h->fused_pooling)
+    rc = xvb_pool_finalize(h->pool_partial, pool_blocks, pool_tb, B, T, cl, h->pooling_eps, 0, h->stats, h->stats_hi,
+                           h->stats_lo, 2 * cl, stream);
+  else
+    rc = xvb_stats_pool(h->last_f32, cl, B, T, cl, h->pooling_eps, h->stats, h->stats_hi, h->stats_lo, 2 * cl, stream);
   if (rc) return rc;
   if ((rc = h->mark(cs))) return rc;
   // 4. segment-level layers (xvector.py:92-96)
@@ -331,6 +356,12 @@ extern "C" int xvb_extractor_wait(xvb_extractor_t* h, int slot) {
   return XVB_OK;
 }
 
+extern "C" int xvb_extractor_set_fused_pooling(xvb_extractor_t* h, int enable) {
+  XVB_CHECK_ARG(h, "xvb_extractor_set_fused_pooling: null extractor");
+  h->fused_pooling = enable != 0;
+  return XVB_OK;
+}
+
 extern "C" int xvb_extractor_set_profiling(xvb_extractor_t* h, int enable) {
   XVB_CHECK_ARG(h, "xvb_extractor_set_profiling: null extractor");
   h->profiling = enable != 0;
@@ -365,7 +396,7 @@ extern "C" void xvb_extractor_destroy(xvb_extractor_t* h) {
     if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
   }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-  cudaFree(h->h_feats); cudaFree(h->h_emb);
+  cudaFree(h->h_feats); cudaFree(h->h_emb); cudaFree(h->pool_partial);
   for (auto* v : {&h->frame, &h->segment})
     for (Layer& L : *v) { cudaFree(L.w_hi); cudaFree(L.w_lo); cudaFree(L.bias); cudaFree(L.scale); cudaFree(L.shift); }
   delete h;

@@ -138,9 +138,72 @@ stats_pool_tma_kernel(const __grid_constant__ CUtensorMap map_x, int T, int C, f
   }
 }
 
+// Merge the per-time-block [mean | M2] partials written by the fused GEMM epilogue (Chan's update,
+// block k has n_k = min(Tb, T - k*Tb) frames), then apply the reference's std definition.
+__global__ void pool_finalize_kernel(const float* __restrict__ partial, int nblk, int Tb, int B, int T, int C, float eps,
+                                     int mode, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi,
+                                     __nv_bfloat16* __restrict__ out_lo, long long ldo) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int b = blockIdx.y;
+  if (c >= C) return;
+  float n = 0.f;
+  float mean[4] = {0.f, 0.f, 0.f, 0.f}, m2[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k = 0; k < nblk; ++k) {
+    const float* p = partial + ((long long)k * B + b) * (2LL * C) + c;
+    const float4 mk = *reinterpret_cast<const float4*>(p);
+    const float4 qk = *reinterpret_cast<const float4*>(p + C);
+    const float nk = (float)min(Tb, T - k * Tb), tot = n + nk, wb = nk / tot, cross = n * wb;
+    const float mv[4] = {mk.x, mk.y, mk.z, mk.w}, qv[4] = {qk.x, qk.y, qk.z, qk.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float d = mv[j] - mean[j];
+      mean[j] = fmaf(d, wb, mean[j]);
+      m2[j] += qv[j] + d * d * cross;
+    }
+    n = tot;
+  }
+  float sd[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    sd[j] = mode == 0 ? sqrtf(fmaxf(m2[j] / (float)T, eps)) : sqrtf(m2[j] / (float)(T - 1) + eps);
+  float* ob = out + (long long)b * 2 * C;
+  *reinterpret_cast<float4*>(ob + c) = make_float4(mean[0], mean[1], mean[2], mean[3]);
+  *reinterpret_cast<float4*>(ob + C + c) = make_float4(sd[0], sd[1], sd[2], sd[3]);
+  if (out_hi) {
+    __nv_bfloat16 h[8], l[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { split_bf16(mean[k], h[k], l[k]); split_bf16(sd[k], h[4 + k], l[4 + k]); }
+    __nv_bfloat16* oh = out_hi + (long long)b * ldo;
+    __nv_bfloat16* ol = out_lo + (long long)b * ldo;
+    *reinterpret_cast<uint2*>(oh + c) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+    *reinterpret_cast<uint2*>(ol + c) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+    *reinterpret_cast<uint2*>(oh + C + c) = make_uint2(pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+    *reinterpret_cast<uint2*>(ol + C + c) = make_uint2(pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+  }
+}
+
 }  // namespace xvb
 
 using namespace xvb;
+
+extern "C" int xvb_pool_finalize(const float* partial, int num_blocks, int frames_per_block, int B, int T, int C, float eps,
+                                 int mode, float* out, uint16_t* out_hi, uint16_t* out_lo, int64_t ldo, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  XVB_CHECK_ARG(partial && out && num_blocks > 0 && frames_per_block > 0 && B > 0 && T > 0 && C > 0 && C % 4 == 0 && B <= 65535,
+                "xvb_pool_finalize: bad arguments");
+  XVB_CHECK_ARG((long long)num_blocks * frames_per_block >= T && (long long)(num_blocks - 1) * frames_per_block < T,
+                "xvb_pool_finalize: %d blocks of %d frames do not tile T=%d", num_blocks, frames_per_block, T);
+  XVB_CHECK_ARG((out_hi != nullptr) == (out_lo != nullptr), "xvb_pool_finalize: out_hi/out_lo must both be set or both NULL");
+  if (out_hi) XVB_CHECK_ARG(ldo >= 2 * C && ldo % 4 == 0, "xvb_pool_finalize: ldo too small / unaligned");
+  XVB_CHECK_ARG(mode == 0 || mode == 1, "xvb_pool_finalize: mode must be 0 or 1");
+  dim3 grid((C / 4 + 127) / 128, B);
+  pool_finalize_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(partial, num_blocks, frames_per_block, B, T, C, eps, mode, out,
+                                                              reinterpret_cast<__nv_bfloat16*>(out_hi),
+                                                              reinterpret_cast<__nv_bfloat16*>(out_lo), ldo);
+  XVB_LAUNCH_CHECK();
+  return XVB_OK;
+}
 
 extern "C" int xvb_stats_pool(const float* x, int64_t ldx, int B, int T, int C, float eps, float* out, uint16_t* out_hi,
                               uint16_t* out_lo, int64_t ldo, void* stream) {

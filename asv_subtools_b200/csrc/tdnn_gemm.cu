@@ -53,6 +53,7 @@ struct TdnnGemmParams {
   int log2_tb;            // Tb is a power of two
   int debug;              // timing experiments only (XVB_GEMM_DEBUG): bit0 skip epilogue work, bit1 skip MMA issue
   int store_mode;         // 0: epilogue slab -> TMA store; 1: slab -> coalesced st.global (no TMA queueing behind loads)
+  float* pool_partial;    // fused statistics pooling: per (time block, utterance, channel) [mean | M2] partials
   int num_src;            // 1, or 2: a second A source accumulated with the same weights (W.(x + x2))
   __nv_bfloat16* y_hi;
   __nv_bfloat16* y_lo;
@@ -311,6 +312,43 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
           f[4 * g + 0] = x0; f[4 * g + 1] = x1; f[4 * g + 2] = x2; f[4 * g + 3] = x3;
         }
         const int n = n0 + ch * 32;
+        if (p.pool_partial) {
+          // Fused statistics pooling (StatisticsPooling over this tile's Tb frames of each utterance):
+          // the Tb rows of an utterance are Tb consecutive lanes, so a butterfly over lane offsets
+          // < Tb leaves every lane with the utterance's sum.  Per (time block, utterance, channel) we
+          // keep the block mean and the centred sum of squares; pool_finalize merges the blocks with
+          // Chan's update -- two-pass quality, deterministic, and the (B,T,C) tensor never exists.
+          const int nrows = min(p.Tb, p.T - t0);
+          const float inv = 1.f / (float)nrows;
+          float sm[16], sq[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sm[j] = valid ? f[j] : 0.f;
+          for (int off = 1; off < p.Tb; off <<= 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sm[j] += __shfl_xor_sync(0xffffffffu, sm[j], off);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            sm[j] *= inv;
+            const float d = valid ? f[j] - sm[j] : 0.f;
+            sq[j] = d * d;
+          }
+          for (int off = 1; off < p.Tb; off <<= 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sq[j] += __shfl_xor_sync(0xffffffffu, sq[j], off);
+          }
+          if ((row & (p.Tb - 1)) == 0 && b < p.B) {
+            const int col = n + half * 16;
+            float* dst = p.pool_partial + ((long long)(m_blk % p.num_t_blk) * p.B + b) * (2LL * p.Cout) + col;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if (col + 4 * g < p.Cout) {
+                *reinterpret_cast<float4*>(dst + 4 * g) = make_float4(sm[4 * g], sm[4 * g + 1], sm[4 * g + 2], sm[4 * g + 3]);
+                *reinterpret_cast<float4*>(dst + p.Cout + 4 * g) = make_float4(sq[4 * g], sq[4 * g + 1], sq[4 * g + 2], sq[4 * g + 3]);
+              }
+          }
+          return;
+        }
         const bool direct = p.store_mode == 1;
         if (planes) {
           // the previous store must have finished reading the slab
@@ -501,10 +539,10 @@ static int gemm_store_mode() {
 }
 
 // Pick the (Tb, Bb) factorisation of the 128-row M tile with the fewest padded rows.
-static void choose_m_tile(int B, int T, int* Tb_out, int* Bb_out) {
+static void choose_m_tile(int B, int T, int* Tb_out, int* Bb_out, int max_tb = 128) {
   long long best = -1;
-  int bt = 128;
-  for (int Tb = 128; Tb >= 1; Tb >>= 1) {
+  int bt = max_tb;
+  for (int Tb = max_tb; Tb >= 1; Tb >>= 1) {
     const int Bb = 128 / Tb;
     const long long rows = (long long)((T + Tb - 1) / Tb) * Tb * ((B + Bb - 1) / Bb) * Bb;
     if (best < 0 || rows < best) { best = rows; bt = Tb; }
@@ -597,7 +635,9 @@ int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream) {
   XVB_CHECK_ARG((a.x2_hi != nullptr) == (a.x2_lo != nullptr), "xvb_tdnn_affine: x2_hi/x2_lo must both be set or both NULL");
   if (a.x2_hi) XVB_CHECK_ARG(a.ldx2 % 8 == 0 && a.ldx2 >= Cin, "xvb_tdnn_affine: ldx2=%lld must be a multiple of 8 and >= Cin", (long long)a.ldx2);
   XVB_CHECK_ARG((a.y_hi != nullptr) == (a.y_lo != nullptr), "xvb_tdnn_affine: y_hi/y_lo must both be set or both NULL");
-  XVB_CHECK_ARG(a.y_hi || a.y_f32, "xvb_tdnn_affine: no output requested");
+  XVB_CHECK_ARG(a.y_hi || a.y_f32 || a.pool_partial, "xvb_tdnn_affine: no output requested");
+  if (a.pool_partial) XVB_CHECK_ARG(!a.y_hi && !a.y_f32 && Cout % 4 == 0 && (uintptr_t)a.pool_partial % 16 == 0,
+                                    "xvb_tdnn_affine: pool_partial excludes other outputs and needs Cout%%4==0");
   if (a.y_hi) XVB_CHECK_ARG(a.ldy % 8 == 0 && a.ldy >= Cout, "xvb_tdnn_affine: plane output needs ldy%%8==0 and ldy>=Cout");
   if (a.y_f32) XVB_CHECK_ARG(a.ldyf % 4 == 0 && a.ldyf >= Cout, "xvb_tdnn_affine: fp32 output needs ldyf%%4==0 and ldyf>=Cout");
   XVB_CHECK_ARG(!(a.flags & XVB_BN) || (a.bn_scale && a.bn_shift), "xvb_tdnn_affine: XVB_BN without scale/shift");
@@ -611,7 +651,7 @@ int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream) {
 
   TdnnGemmParams p{};
   p.B = B; p.T = T; p.Cin = Cin; p.Cout = Cout;
-  choose_m_tile(B, T, &p.Tb, &p.Bb);
+  choose_m_tile(B, T, &p.Tb, &p.Bb, a.pool_partial ? 32 : 128);  // pooled rows of an utterance stay inside one warp
   p.num_t_blk = (T + p.Tb - 1) / p.Tb;
   p.num_b_blk = (B + p.Bb - 1) / p.Bb;
   p.ntaps = ntaps;
@@ -621,6 +661,7 @@ int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream) {
   p.flags = a.flags;
   p.bias = a.bias; p.scale = a.bn_scale; p.shift = a.bn_shift; p.row_bias = a.row_bias;
   p.utt_bias = a.utt_bias; p.ld_utt = a.ld_utt_bias;
+  p.pool_partial = a.pool_partial;
   p.num_src = a.x2_hi ? 2 : 1;
   p.log2_tb = 0;
   while ((1 << p.log2_tb) < p.Tb) ++p.log2_tb;
@@ -667,6 +708,13 @@ int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream) {
   if (Cout >= 128 && m_tiles * ((Cout + 127) / 128) >= sms) return launch_gemm<128, 1>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
   if (Cout >= 64 && m_tiles * ((Cout + 63) / 64) >= sms / 2) return launch_gemm<64, 1>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
   return launch_gemm<32, 1>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
+}
+
+extern "C" int xvb_pool_partial_blocks(int B, int T, int* frames_per_block) {
+  int Tb, Bb;
+  choose_m_tile(B, T, &Tb, &Bb, 32);
+  if (frames_per_block) *frames_per_block = Tb;
+  return (T + Tb - 1) / Tb;
 }
 
 extern "C" int xvb_tdnn_affine_ex(const xvb_tdnn_args_t* args, void* stream) {

@@ -103,8 +103,21 @@ def tdnn_affine(x, w, cout, context, bias=None, bn_scale=None, bn_shift=None, re
     return y, yf
 
 
+def fused_pool_layer(x, w, cout, context, bias=None, bn_scale=None, bn_shift=None, relu=True, eps=1e-10, mode=0):
+    """TDNN layer whose epilogue pools over time (no (B,T,C) output) + the Chan merge: -> (B, 2*cout) fp32."""
+    b, t = x.hi.shape[0], x.hi.shape[1]
+    tb = C.c_int()
+    nblk = lib.xvb_pool_partial_blocks(b, t, C.byref(tb))
+    partial = torch.empty(nblk, b, 2 * cout, dtype=torch.float32, device=x.hi.device)
+    tdnn_affine_ex(x, w, cout, context, bias=bias, bn_scale=bn_scale, bn_shift=bn_shift, relu=relu, pool_partial=partial)
+    out = torch.empty(b, 2 * cout, dtype=torch.float32, device=x.hi.device)
+    check(lib.xvb_pool_finalize(_ptr(partial), nblk, tb.value, b, t, cout, eps, mode, _ptr(out), None, None, 0, _stream()),
+          "xvb_pool_finalize")
+    return out
+
+
 def tdnn_affine_ex(x, w, cout, context, x2=None, bias=None, bn_scale=None, bn_shift=None, utt_bias=None, row_bias=None,
-                   relu=False, tanh=False, sigmoid=False, y=None, y_f32=None):
+                   relu=False, tanh=False, sigmoid=False, y=None, y_f32=None, pool_partial=None):
     """Full form of the tcgen05 layer (xvb_tdnn_affine_ex).  x / x2: SplitPlanes (B,T,*) (views
     allowed); y: SplitPlanes to write (view allowed) and/or y_f32: fp32 (B,T,>=cout) tensor."""
     b, t = x.hi.shape[0], x.hi.shape[1]
@@ -130,6 +143,8 @@ def tdnn_affine_ex(x, w, cout, context, x2=None, bias=None, bn_scale=None, bn_sh
         if y_f32.dtype != torch.float32 or not y_f32.is_cuda:
             raise TypeError("y_f32 must be a CUDA float32 tensor")
         a.y_f32, a.ldyf = y_f32.data_ptr(), y_f32.stride(-2)
+    if pool_partial is not None:
+        a.pool_partial = pool_partial.data_ptr()
     a.B, a.T, a.Cin, a.Cout = b, t, x.channels, cout
     check(lib.xvb_tdnn_affine_ex(C.byref(a), _stream()), "xvb_tdnn_affine_ex")
 
@@ -366,6 +381,10 @@ class Extractor:
     def extract_host_into(self, feats_ptr, b, t, emb_ptr):
         check(lib.xvb_extractor_extract_host(self._h, C.c_void_p(feats_ptr), b, t, C.c_void_p(emb_ptr), _stream()),
               "xvb_extractor_extract_host")
+
+    def set_fused_pooling(self, enable):
+        """Default on: tdnn5's epilogue pools over time itself; off: fp32 tensor + standalone pooling kernel."""
+        check(lib.xvb_extractor_set_fused_pooling(self._h, 1 if enable else 0), "xvb_extractor_set_fused_pooling")
 
     def set_profiling(self, enable):
         check(lib.xvb_extractor_set_profiling(self._h, 1 if enable else 0), "xvb_extractor_set_profiling")

@@ -112,8 +112,19 @@ typedef struct xvb_tdnn_args {
   uint16_t* y_hi; uint16_t* y_lo; int64_t ldy;
   float* y_f32; int64_t ldyf;
   int B, T, Cin, Cout;
+  /* Fused statistics pooling (no other output): the epilogue reduces each tile's frames per
+   * utterance and writes [mean | centred sum of squares] partials, (num_blocks, B, 2*Cout) fp32 with
+   * num_blocks = xvb_pool_partial_blocks(B, T, &frames_per_block); merge with xvb_pool_finalize. */
+  float* pool_partial;
 } xvb_tdnn_args_t;
 int xvb_tdnn_affine_ex(const xvb_tdnn_args_t* args, void* stream);
+/* Time blocking the fused-pooling epilogue will use for a (B, T) batch. */
+int xvb_pool_partial_blocks(int B, int T, int* frames_per_block);
+/* Merge the fused-pooling partials into StatisticsPooling's output (mode as in xvb_stats_pool_ex):
+ * Chan's parallel update over the time blocks, i.e. the two-pass result of pooling.py:58-67
+ * without ever materialising the (B, T, C) tensor. */
+int xvb_pool_finalize(const float* partial, int num_blocks, int frames_per_block, int B, int T, int C, float eps,
+                      int mode, float* out, uint16_t* out_hi, uint16_t* out_lo, int64_t ldo, void* stream);
 
 /* Same layer on CUDA cores in plain fp32 straight from the *unpacked* reference weight
  * (Cout, Cin, tot_context).  Slow; exists so the tensor-core path and the weight packer can
@@ -243,6 +254,9 @@ int xvb_extractor_wait(xvb_extractor_t* h, int slot);
  * stats pooling, segment layers. */
 int xvb_extractor_set_profiling(xvb_extractor_t* h, int enable);
 int xvb_extractor_kernel_times(xvb_extractor_t* h, float* ms_host, int max_n);
+/* Fused pooling (default on): the last frame layer's epilogue reduces over time itself and the
+ * (B,T,C_last) fp32 tensor is never written.  Off: last layer -> fp32 -> xvb_stats_pool. */
+int xvb_extractor_set_fused_pooling(xvb_extractor_t* h, int enable);
 /* Number of kernels the last extract call launched (bench.py's gpu_launches). */
 int xvb_extractor_last_launches(const xvb_extractor_t* h);
 /* Device pointer/pitch of a frame layer's fp32 output from the last call (debug/tests; only

@@ -190,11 +190,31 @@ def test_xvector_intermediates(golden):
     g = golden("xvector")
     m, _ = _model(80, 102, "far")
     feats = onn.synthetic_feats(2, 50, 80, 102 + 2000)
-    m.extract_embedding_batch(feats)
+    fused_emb = m.extract_embedding_batch(feats).cpu().numpy()
+    fused_stats = m.extractor().debug_f32(-1, (2, 3000)).cpu().numpy()       # pooled in tdnn5's epilogue
+    assert rel(fused_stats, g["xv80_inter_stats"][:, :, 0]) < EMB_TOL
+    m.extractor().set_fused_pooling(False)                                   # fp32 tensor + standalone pooling kernel
+    emb = m.extract_embedding_batch(feats).cpu().numpy()
     stats = m.extractor().debug_f32(-1, (2, 3000)).cpu().numpy()
     assert rel(stats, g["xv80_inter_stats"][:, :, 0]) < EMB_TOL
     last = m.extractor().debug_f32(0, (2, 50, 1500)).cpu().numpy()
     assert rel(last.transpose(0, 2, 1)[:, :8], g["xv80_inter_tdnn5"]) < EMB_TOL
+    assert rel(fused_stats, stats) < 2e-6 and rel(fused_emb, emb) < 2e-6
+
+
+@pytest.mark.parametrize("B,T", [(3, 200), (2, 1), (5, 37), (1, 300), (40, 8)])
+def test_fused_pooling_layer_vs_oracle(ops, B, T):
+    """tdnn5-shaped layer with the pooling fused into the epilogue (ragged T, Tb in {1,4,8,32})."""
+    x, w, b, scale, shift = _layer_inputs(B, T, 512, 1500, [0], 17)
+    xp = ops.split_f32(torch.from_numpy(x).cuda())
+    wp = ops.pack_tdnn_weight(torch.from_numpy(w).cuda(), [0])
+    out = ops.fused_pool_layer(xp, wp, 1500, [0], torch.from_numpy(b).cuda(), torch.from_numpy(scale).cuda(),
+                               torch.from_numpy(shift).cuda(), relu=True).cpu().numpy()
+    y = _oracle_layer(x, w, b, scale, shift, [0], True)
+    with torch.no_grad():
+        ref = onn.statistics_pooling(torch.from_numpy(y).transpose(1, 2)).squeeze(2).numpy()
+    assert rel(out[:, :1500], ref[:, :1500]) < GEMM_TOL
+    assert rel(out[:, 1500:], ref[:, 1500:]) < 1e-4 if T > 1 else np.allclose(out[:, 1500:], 1e-5, rtol=1e-3)
 
 
 def test_host_buffer_path_matches_device_path():

@@ -1,10 +1,8 @@
 #!/bin/bash
 TAG=${1:-ab}
 mkdir -p gpurun_out
-run() { name=$1; shift; env "$@" XVB_GEMM_WIDE=0 timeout 300 python tools/layer_times.py > gpurun_out/${TAG}_$name.txt 2>&1; echo "$name: $(tail -1 gpurun_out/${TAG}_$name.txt)"; }
-run base XVB_GEMM_DEBUG=0
-run no_store_issue XVB_GEMM_DEBUG=4
-run no_ldtm XVB_GEMM_DEBUG=8
-run no_store_no_ldtm XVB_GEMM_DEBUG=12
-run no_store_no_ldtm_no_mma XVB_GEMM_DEBUG=14
-run direct_nomma XVB_GEMM_DEBUG=2 XVB_GEMM_STORE=direct
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -12 gpurun_out/${TAG}_pytest.log
+timeout 300 python bench.py --steps 20 --warmup 3 > gpurun_out/${TAG}_bench.json 2>gpurun_out/${TAG}_bench.err; python -c "
+import json
+d=json.loads(open('gpurun_out/${TAG}_bench.json').read().strip().splitlines()[-1])
+print('value %.3e e2e %.3e exec_frac %.3f pool_frac %.3f' % (d['value'], d['e2e']['value'], d['roofline']['executed_frac'], d['roofline_stats_pool']['frac'])); print({k: round(v*1e3) for k,v in d['kernel_ms'].items()})" || tail -20 gpurun_out/${TAG}_bench.err
