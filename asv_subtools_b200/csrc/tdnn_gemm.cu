@@ -86,7 +86,12 @@ struct GemmCfg {
   static_assert(kStages >= 2, "need at least a double-buffered operand pipeline");
 };
 
-template <int BLOCK_N, int kCta, int kNSub>
+// kPool (CTA pairs only): fused statistics pooling.  The MMA operands swap roles -- the weight tile
+// is the M side (128 output channels per CTA = TMEM lanes), the frame tile the N side (256 frames =
+// TMEM columns) -- so an epilogue thread owns ONE channel and sees the tile's frames as consecutive
+// accumulator columns: pooling over time becomes a running (Welford) update in registers, with no
+// shuffles, no shared memory and no (B,T,C) output at all.
+template <int BLOCK_N, int kCta, int kNSub, bool kPool>
 __global__ void __launch_bounds__(kNumThreads, 1)
 tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                         const __grid_constant__ CUtensorMap map_a2_hi, const __grid_constant__ CUtensorMap map_a2_lo,
@@ -217,9 +222,15 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
               const uint64_t db_hi = make_kmajor_desc<128>(sa + 2 * kABytes + ns * kBBytes);
               const uint64_t db_lo = make_kmajor_desc<128>(sa + 2 * kABytes + (kNSub + ns) * kBBytes);
               const uint32_t d = tmem_d + ns * BLOCK_N;
-              umma_bf16<kCta>(d, da_lo + koff, db_hi + koff, idesc, accumulate);
-              umma_bf16<kCta>(d, da_hi + koff, db_lo + koff, idesc, 1);
-              umma_bf16<kCta>(d, da_hi + koff, db_hi + koff, idesc, 1);
+              if constexpr (kPool) {  // D^T: channels on the lanes, frames on the columns
+                umma_bf16<kCta>(d, db_hi + koff, da_lo + koff, idesc, accumulate);
+                umma_bf16<kCta>(d, db_lo + koff, da_hi + koff, idesc, 1);
+                umma_bf16<kCta>(d, db_hi + koff, da_hi + koff, idesc, 1);
+              } else {
+                umma_bf16<kCta>(d, da_lo + koff, db_hi + koff, idesc, accumulate);
+                umma_bf16<kCta>(d, da_hi + koff, db_lo + koff, idesc, 1);
+                umma_bf16<kCta>(d, da_hi + koff, db_hi + koff, idesc, 1);
+              }
             }
             accumulate = 1;
           }
@@ -257,6 +268,59 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
       const int b = b0 + row / p.Tb, t = t0 + row % p.Tb;
       const bool valid = (b < p.B) && (t < p.T);
       const int n0 = n_blk * kTileN;
+      if constexpr (kPool) {
+        // ---- fused statistics pooling: thread = channel, accumulator columns = the pair's 256 frames
+        const int hb = ew >> 2;                                   // frames of CTA `hb` of the pair (columns hb*128..)
+        const int cch = n0 + (int)cta_rank * 128 + q * 32 + lane;  // this thread's output channel
+        const bool cvalid = cch < p.Cout;
+        const float bias_c = (cvalid && p.bias) ? __ldg(p.bias + cch) : 0.f;
+        const float scale_c = (cvalid && bn) ? __ldg(p.scale + cch) : 1.f;
+        const float shift_c = (cvalid && bn) ? __ldg(p.shift + cch) : 0.f;
+        const float floor_c = relu ? 0.f : -INFINITY;
+        const int mh = (tile / p.num_n_blk) * 2 + hb;
+        const int bh0 = (mh / p.num_t_blk) * p.Bb, th0 = (mh % p.num_t_blk) * p.Tb, tblk = mh % p.num_t_blk;
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tcgen05_fence_after();
+        const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kTileN + hb * 128;
+        float wn = 0.f, wmean = 0.f, wm2 = 0.f;                    // Welford state of the current (utterance, time block)
+        auto consume = [&](uint32_t (&v)[16], int c16) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = c16 * 16 + j, tt = col & (p.Tb - 1);
+            if (th0 + tt < p.T) {                                  // frames past the utterance end were zero-filled: skip
+              const float x = fmaf(fmaxf(__uint_as_float(v[j]) + bias_c, floor_c), scale_c, shift_c);
+              wn += 1.f;
+              const float d = x - wmean;
+              wmean += d / wn;
+              wm2 = fmaf(d, x - wmean, wm2);
+            }
+            if (tt == p.Tb - 1) {                                  // block of this utterance complete: emit [mean | M2]
+              const int bb = bh0 + (col >> p.log2_tb);
+              if (cvalid && bb < p.B && wn > 0.f) {
+                float* dst = p.pool_partial + ((long long)tblk * p.B + bb) * (2LL * p.Cout) + cch;
+                dst[0] = wmean;
+                dst[p.Cout] = wm2;
+              }
+              wn = 0.f; wmean = 0.f; wm2 = 0.f;
+            }
+          }
+        };
+        uint32_t va[16], vb[16];
+        tmem_ld_32x16(tcol, va);
+#pragma unroll 1
+        for (int c16 = 0; c16 < 8; c16 += 2) {
+          tmem_ld_wait();
+          tmem_ld_32x16(tcol + (c16 + 1) * 16, vb);
+          consume(va, c16);
+          tmem_ld_wait();
+          if (c16 + 2 < 8) tmem_ld_32x16(tcol + (c16 + 2) * 16, va);
+          consume(vb, c16 + 1);
+        }
+        tcgen05_fence_before();
+        if constexpr (kCta == 1) mbar_arrive(&tmem_empty_bar[acc]);
+        else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+        continue;
+      }
       const float rbias = (p.row_bias && valid) ? __ldg(p.row_bias + (long long)b * p.T + t) : 0.f;
       const float* ub = (p.utt_bias && valid) ? p.utt_bias + (long long)b * p.ld_utt + n0 + half * 16 : nullptr;
       // stage this tile's per-column parameters (double-buffered by accumulator stage; the
@@ -312,43 +376,6 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
           f[4 * g + 0] = x0; f[4 * g + 1] = x1; f[4 * g + 2] = x2; f[4 * g + 3] = x3;
         }
         const int n = n0 + ch * 32;
-        if (p.pool_partial) {
-          // Fused statistics pooling (StatisticsPooling over this tile's Tb frames of each utterance):
-          // the Tb rows of an utterance are Tb consecutive lanes, so a butterfly over lane offsets
-          // < Tb leaves every lane with the utterance's sum.  Per (time block, utterance, channel) we
-          // keep the block mean and the centred sum of squares; pool_finalize merges the blocks with
-          // Chan's update -- two-pass quality, deterministic, and the (B,T,C) tensor never exists.
-          const int nrows = min(p.Tb, p.T - t0);
-          const float inv = 1.f / (float)nrows;
-          float sm[16], sq[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) sm[j] = valid ? f[j] : 0.f;
-          for (int off = 1; off < p.Tb; off <<= 1) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) sm[j] += __shfl_xor_sync(0xffffffffu, sm[j], off);
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            sm[j] *= inv;
-            const float d = valid ? f[j] - sm[j] : 0.f;
-            sq[j] = d * d;
-          }
-          for (int off = 1; off < p.Tb; off <<= 1) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) sq[j] += __shfl_xor_sync(0xffffffffu, sq[j], off);
-          }
-          if ((row & (p.Tb - 1)) == 0 && b < p.B) {
-            const int col = n + half * 16;
-            float* dst = p.pool_partial + ((long long)(m_blk % p.num_t_blk) * p.B + b) * (2LL * p.Cout) + col;
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              if (col + 4 * g < p.Cout) {
-                *reinterpret_cast<float4*>(dst + 4 * g) = make_float4(sm[4 * g], sm[4 * g + 1], sm[4 * g + 2], sm[4 * g + 3]);
-                *reinterpret_cast<float4*>(dst + p.Cout + 4 * g) = make_float4(sq[4 * g], sq[4 * g + 1], sq[4 * g + 2], sq[4 * g + 3]);
-              }
-          }
-          return;
-        }
         const bool direct = p.store_mode == 1;
         if (planes) {
           // the previous store must have finished reading the slab
@@ -568,7 +595,7 @@ static int make_out_map(CUtensorMap* m, const void* base, int esize, int C, int 
   return XVB_OK;
 }
 
-template <int BLOCK_N, int kCta, int kNSub = 1>
+template <int BLOCK_N, int kCta, int kNSub = 1, bool kPool = false>
 static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& ma2_hi,
                        const CUtensorMap& ma2_lo, const void* w_hi, const void* w_lo, TdnnGemmParams& p,
                        cudaStream_t stream) {
@@ -584,7 +611,7 @@ static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const
   p.num_tiles = num_m_units * p.num_n_blk;
   static bool attr_set = false;
   if (!attr_set) {
-    XVB_CUDA(cudaFuncSetAttribute(tdnn_gemm_bf16x3_kernel<BLOCK_N, kCta, kNSub>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    XVB_CUDA(cudaFuncSetAttribute(tdnn_gemm_bf16x3_kernel<BLOCK_N, kCta, kNSub, kPool>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -614,7 +641,7 @@ static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  XVB_CUDA(cudaLaunchKernelEx(&cfg, tdnn_gemm_bf16x3_kernel<BLOCK_N, kCta, kNSub>, ma_hi, ma_lo, ma2_hi, ma2_lo, mw_hi, mw_lo,
+  XVB_CUDA(cudaLaunchKernelEx(&cfg, tdnn_gemm_bf16x3_kernel<BLOCK_N, kCta, kNSub, kPool>, ma_hi, ma_lo, ma2_hi, ma2_lo, mw_hi, mw_lo,
                               my_hi, my_lo, my_f32, p));
   XVB_LAUNCH_CHECK();
   return XVB_OK;
@@ -651,7 +678,7 @@ int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream) {
 
   TdnnGemmParams p{};
   p.B = B; p.T = T; p.Cin = Cin; p.Cout = Cout;
-  choose_m_tile(B, T, &p.Tb, &p.Bb, a.pool_partial ? 32 : 128);  // pooled rows of an utterance stay inside one warp
+  choose_m_tile(B, T, &p.Tb, &p.Bb);
   p.num_t_blk = (T + p.Tb - 1) / p.Tb;
   p.num_b_blk = (B + p.Bb - 1) / p.Bb;
   p.ntaps = ntaps;
@@ -694,6 +721,8 @@ int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream) {
   const int mode = gemm_cta_mode();
   const void* w_hi = a.w_hi;
   const void* w_lo = a.w_lo;
+  if (a.pool_partial)  // fused pooling always runs on the swapped CTA-pair kernel (any shape: TMA zero-fills)
+    return launch_gemm<256, 2, 1, true>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
   static const int force_bn = getenv("XVB_GEMM_BN") ? atoi(getenv("XVB_GEMM_BN")) : 0;  // tuning knobs
   // wide tiles cut the operand stream by 25-37 % but serialise the epilogue with the MMAs (one
   // accumulator in TMEM); measured slower end to end (profiles/r01_gemm_experiments.md), so opt-in.
@@ -712,7 +741,7 @@ int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream) {
 
 extern "C" int xvb_pool_partial_blocks(int B, int T, int* frames_per_block) {
   int Tb, Bb;
-  choose_m_tile(B, T, &Tb, &Bb, 32);
+  choose_m_tile(B, T, &Tb, &Bb);
   if (frames_per_block) *frames_per_block = Tb;
   return (T + Tb - 1) / Tb;
 }

@@ -251,7 +251,9 @@ def test_full_size_batch_invariance_and_padding_properties():
     perm = np.random.RandomState(0).permutation(256)
     assert np.array_equal(m.extract_embedding_batch(feats[perm]).cpu().numpy(), full[perm])
     assert np.array_equal(m.extract_embedding_batch(feats[:16]).cpu().numpy(), full[:16])
-    assert np.array_equal(m.extract_embedding_batch(feats[100:101]).cpu().numpy(), full[100:101])
+    # a different batch size changes the time blocking of the fused pooling (Chan merge order): ~1 ulp
+    assert rel(m.extract_embedding_batch(feats[100:101]).cpu().numpy(), full[100:101]) < 2e-6
+    assert rel(m.extract_embedding_batch(feats[:3]).cpu().numpy(), full[:3]) < 2e-6
     with torch.no_grad():
         ref = onn.xvector_forward(sd, torch.from_numpy(feats[[0, 7, 255]]).transpose(1, 2), "far").squeeze(2).numpy()
     for got, want in zip(full[[0, 7, 255]], ref):
