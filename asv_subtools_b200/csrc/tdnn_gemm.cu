@@ -24,6 +24,7 @@
 #include <stdlib.h>
 
 #include <mutex>
+#include <type_traits>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -282,27 +283,65 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
         mbar_wait(&tmem_full_bar[acc], acc_phase);
         tcgen05_fence_after();
         const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kTileN + hb * 128;
-        float wn = 0.f, wmean = 0.f, wm2 = 0.f;                    // Welford state of the current (utterance, time block)
-        auto consume = [&](uint32_t (&v)[16], int c16) {
+        float rn = 0.f, rmean = 0.f, rm2 = 0.f;   // running Chan state, only used when a time block spans > 16 columns
+        auto emit = [&](int col, float mean, float m2) {
+          const int bb = bh0 + (col >> p.log2_tb);
+          if (cvalid && bb < p.B) {
+            float* dst = p.pool_partial + ((long long)tblk * p.B + bb) * (2LL * p.Cout) + cch;
+            dst[0] = mean;
+            dst[p.Cout] = m2;
+          }
+        };
+        // one group of G consecutive frame columns (G = min(Tb,16), compile-time): two passes in registers
+        auto group = [&](const float* x, int col0, auto gtag) {
+          constexpr int G = decltype(gtag)::value;
+          const int tt0 = col0 & (p.Tb - 1);
+          int nv = p.T - (th0 + tt0);                              // valid frames of this group (warp-uniform)
+          nv = nv < 0 ? 0 : (nv > G ? G : nv);
+          float sum = 0.f;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int col = c16 * 16 + j, tt = col & (p.Tb - 1);
-            if (th0 + tt < p.T) {                                  // frames past the utterance end were zero-filled: skip
-              const float x = fmaf(fmaxf(__uint_as_float(v[j]) + bias_c, floor_c), scale_c, shift_c);
-              wn += 1.f;
-              const float d = x - wmean;
-              wmean += d / wn;
-              wm2 = fmaf(d, x - wmean, wm2);
+          for (int i = 0; i < G; ++i) sum += i < nv ? x[i] : 0.f;
+          const float mean = nv > 0 ? sum / (float)nv : 0.f;
+          float m2 = 0.f;
+#pragma unroll
+          for (int i = 0; i < G; ++i) { const float d = i < nv ? x[i] - mean : 0.f; m2 = fmaf(d, d, m2); }
+          if (p.Tb <= 16) {
+            if (nv > 0) emit(col0, mean, m2);
+          } else {                                                 // Chan merge of 16-frame groups into the block
+            if (nv > 0) {
+              const float tot = rn + (float)nv, wb = (float)nv / tot, d = mean - rmean;
+              rmean = fmaf(d, wb, rmean);
+              rm2 += m2 + d * d * rn * wb;
+              rn = tot;
             }
-            if (tt == p.Tb - 1) {                                  // block of this utterance complete: emit [mean | M2]
-              const int bb = bh0 + (col >> p.log2_tb);
-              if (cvalid && bb < p.B && wn > 0.f) {
-                float* dst = p.pool_partial + ((long long)tblk * p.B + bb) * (2LL * p.Cout) + cch;
-                dst[0] = wmean;
-                dst[p.Cout] = wm2;
-              }
-              wn = 0.f; wmean = 0.f; wm2 = 0.f;
-            }
+            if (tt0 + G == p.Tb) { if (rn > 0.f) emit(col0, rmean, rm2); rn = 0.f; rmean = 0.f; rm2 = 0.f; }
+          }
+        };
+        auto consume = [&](uint32_t (&v)[16], int c16) {
+          float x[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) x[j] = fmaf(fmaxf(__uint_as_float(v[j]) + bias_c, floor_c), scale_c, shift_c);
+          const int col = c16 * 16;
+          switch (p.log2_tb) {
+            case 0:
+#pragma unroll
+              for (int g = 0; g < 16; ++g) group(x + g, col + g, std::integral_constant<int, 1>{});
+              break;
+            case 1:
+#pragma unroll
+              for (int g = 0; g < 8; ++g) group(x + 2 * g, col + 2 * g, std::integral_constant<int, 2>{});
+              break;
+            case 2:
+#pragma unroll
+              for (int g = 0; g < 4; ++g) group(x + 4 * g, col + 4 * g, std::integral_constant<int, 4>{});
+              break;
+            case 3:
+              group(x, col, std::integral_constant<int, 8>{});
+              group(x + 8, col + 8, std::integral_constant<int, 8>{});
+              break;
+            default:
+              group(x, col, std::integral_constant<int, 16>{});
+              break;
           }
         };
         uint32_t va[16], vb[16];
