@@ -152,6 +152,17 @@ class _Layer:
     def run(self, x, **kw):
         ops.tdnn_affine_ex(x, self.w, self.cout, self.context, bias=self.bias, bn_scale=self.scale, bn_shift=self.shift,
                            relu=self.relu, **kw)
+        _mark("gemm K={}x{} N={}".format(len(self.context), x.channels, self.cout))
+
+
+_PROFILE = None  # list of (label, cuda event) when profiling (tools/bench_ecapa.py --profile)
+
+
+def _mark(label):
+    if _PROFILE is not None:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        _PROFILE.append((label, ev))
 
 
 class EcapaExtractor:
@@ -205,7 +216,9 @@ class EcapaExtractor:
         B, T, _ = feats.shape
         dev, C = feats.device, self.channels
         P = ops.SplitPlanes
+        _mark("start")
         xin = ops.split_f32(feats, ld=self.ldf)
+        _mark("split")
         X = P.empty((B, T, C), dev)
         self.layer1.run(xin, y=X)
         H, R, Z = P.empty((B, T, C), dev), P.empty((B, T, C), dev), P.empty((B, T, C), dev)
@@ -219,21 +232,25 @@ class EcapaExtractor:
             blk["bn1"].run(cur, y=H)
             R.hi[:, :, :w].copy_(H.hi[:, :, :w])       # chunk 0 passes through (ecapa_tdnn_xvector.py:63-64)
             R.lo[:, :, :w].copy_(H.lo[:, :, :w])
+            _mark("chunk0 copy")
             for i, layer in enumerate(blk["res"]):
                 layer.run(H.slice(w * (i + 1), w * (i + 2)), x2=R.slice(w * i, w * (i + 1)) if i >= 1 else None,
                           y=R.slice(w * (i + 1), w * (i + 2)))
             blk["bn2"].run(R, y=Z)
             _, zm = ops.plane_mean(Z)
+            _mark("plane_mean")
             blk["se1"].run(zm, y=s1)
             blk["se2"].run(s1, sigmoid=True, y_f32=gate)
             last = li + 1 == len(self.blocks)
             ops.se_apply(Z, cur, gate.view(B, C), CAT.slice(C * li, C * (li + 1)), None if last else N)
+            _mark("se_apply")
             cur = N
         D = self.mfa_dim
         M = P.empty((B, T, D), dev)
         MF = torch.empty(B, T, D, dtype=torch.float32, device=dev)
         self.mfa.run(CAT, y=M, y_f32=MF)
         _, gp = ops.stats_pool_ex(MF, 1e-5, 1, planes=True)          # global mean | sqrt(var_unbiased + 1e-5)
+        _mark("stats_pool(global)")
         ub = torch.empty(B, 1, self.att_gs.cout, dtype=torch.float32, device=dev)
         self.att_gs.run(gp, y_f32=ub)
         A1 = P.empty((B, T, self.att_x.cout), dev)
@@ -241,6 +258,7 @@ class EcapaExtractor:
         LOG = torch.empty(B, T, D, dtype=torch.float32, device=dev)
         self.att2.run(A1, y_f32=LOG)
         _, pp = ops.attn_stats_pool(LOG, MF, 1e-5, planes=True)
+        _mark("attn_stats_pool")
         emb = torch.empty(B, 1, self.embed_dim, dtype=torch.float32, device=dev)
         self.fc2.run(pp, y_f32=emb)
         return emb.view(B, self.embed_dim)

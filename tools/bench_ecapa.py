@@ -37,6 +37,25 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     flop = 25701908 * B * T
+    if "--profile" in sys.argv:
+        import collections
+        from asv_subtools_b200.model import ecapa_tdnn_xvector as mod
+        agg = collections.OrderedDict()
+        for rep in range(5):
+            mod._PROFILE = []
+            ex.extract(xs[rep % 4])
+            torch.cuda.synchronize()
+            evs = mod._PROFILE
+            for (l0, e0_), (l1, e1_) in zip(evs[:-1], evs[1:]):
+                agg.setdefault(l1, []).append(e0_.elapsed_time(e1_))
+        mod._PROFILE = None
+        tot = 0.0
+        for k, v in agg.items():
+            per_call = sorted(v)[len(v) // 2]
+            n = len(v) // 5
+            tot += per_call * n
+            print("%-28s x%-3d %8.1f us each %9.1f us total" % (k, n, per_call * 1e3, per_call * n * 1e3))
+        print("sum %.1f us" % (tot * 1e3))
     print(json.dumps({"workload": "ECAPA-TDNN c1024, 80-d fbank, 300-frame chunks, batch 128",
                       "ms_per_step": ms, "frames_per_s": B * T / (ms * 1e-3),
                       "algorithmic_tflops": flop / (ms * 1e-3) / 1e12, "finite": bool(torch.isfinite(out).all())}))
