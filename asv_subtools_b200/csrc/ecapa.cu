@@ -81,6 +81,17 @@ plane_mean_kernel(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __r
   }
 }
 
+// ---------------------------------------------------------------- strided row copy (channel-slice pass-through)
+__global__ void copy_rows_kernel(const uint4* __restrict__ src, long long ld_src16, uint4* __restrict__ dst,
+                                 long long ld_dst16, long long rows, int vec_per_row) {
+  const long long total = rows * vec_per_row;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vec_per_row;
+    const int c = (int)(i % vec_per_row);
+    dst[r * ld_dst16 + c] = src[r * ld_src16 + c];
+  }
+}
+
 // ---------------------------------------------------------------- SE gate + residual (+ running sum)
 __global__ void se_apply_kernel(const __nv_bfloat16* __restrict__ zh, const __nv_bfloat16* __restrict__ zl, long long ldz,
                                 const __nv_bfloat16* __restrict__ ih, const __nv_bfloat16* __restrict__ il, long long ldi,
@@ -221,6 +232,24 @@ extern "C" int xvb_plane_mean(const uint16_t* x_hi, const uint16_t* x_lo, int64_
   plane_mean_kernel<<<grid, kPmWarps * 32, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(x_hi), reinterpret_cast<const __nv_bfloat16*>(x_lo), ldx, T, C, out,
       reinterpret_cast<__nv_bfloat16*>(out_hi), reinterpret_cast<__nv_bfloat16*>(out_lo), ldo);
+  XVB_LAUNCH_CHECK();
+  return XVB_OK;
+}
+
+extern "C" int xvb_copy_rows(const void* src, int64_t src_pitch_bytes, void* dst, int64_t dst_pitch_bytes, int64_t rows,
+                             int64_t row_bytes, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  XVB_CHECK_ARG(src && dst && rows > 0 && row_bytes > 0, "xvb_copy_rows: bad arguments");
+  XVB_CHECK_ARG(row_bytes % 16 == 0 && src_pitch_bytes % 16 == 0 && dst_pitch_bytes % 16 == 0 &&
+                    ((uintptr_t)src | (uintptr_t)dst) % 16 == 0, "xvb_copy_rows: 16-byte granularity required");
+  const long long total = rows * (row_bytes / 16);
+  long long g = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (g > cap) g = cap;
+  copy_rows_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(src), src_pitch_bytes / 16,
+                                                                   reinterpret_cast<uint4*>(dst), dst_pitch_bytes / 16, rows,
+                                                                   (int)(row_bytes / 16));
   XVB_LAUNCH_CHECK();
   return XVB_OK;
 }

@@ -230,8 +230,7 @@ class EcapaExtractor:
         for li, blk in enumerate(self.blocks):
             w = blk["width"]
             blk["bn1"].run(cur, y=H)
-            R.hi[:, :, :w].copy_(H.hi[:, :, :w])       # chunk 0 passes through (ecapa_tdnn_xvector.py:63-64)
-            R.lo[:, :, :w].copy_(H.lo[:, :, :w])
+            ops.copy_planes(H.slice(0, w), R.slice(0, w))   # chunk 0 passes through (ecapa_tdnn_xvector.py:63-64)
             _mark("chunk0 copy")
             for i, layer in enumerate(blk["res"]):
                 layer.run(H.slice(w * (i + 1), w * (i + 2)), x2=R.slice(w * i, w * (i + 1)) if i >= 1 else None,

@@ -160,6 +160,14 @@ def plane_mean(x, planes=True):
     return out, op
 
 
+def copy_planes(src, dst):
+    """dst[...] = src[...] for two SplitPlanes views of equal shape (B,T,c), c % 8 == 0."""
+    rows = src.hi.shape[0] * src.hi.shape[1]
+    for s, d in ((src.hi, dst.hi), (src.lo, dst.lo)):
+        check(lib.xvb_copy_rows(s.data_ptr(), s.stride(-2) * 2, d.data_ptr(), d.stride(-2) * 2, rows, src.channels * 2,
+                                _stream()), "xvb_copy_rows")
+
+
 def se_apply(z, xin, gate, out, nxt=None):
     """out = z * gate[b] + xin ; nxt = xin + out   (all SplitPlanes (B,T,C), views allowed)."""
     b, t, c = z.hi.shape[0], z.hi.shape[1], z.channels

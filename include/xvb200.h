@@ -158,6 +158,11 @@ int xvb_stats_pool_ex(const float* x, int64_t ldx, int B, int T, int C, float ep
 int xvb_plane_mean(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, int B, int T, int C, float* out,
                    uint16_t* out_hi, uint16_t* out_lo, int64_t ldo, void* stream);
 
+/* Strided row copy (16-byte granularity): the pass-through of Res2Net's first chunk
+ * (ecapa_tdnn_xvector.py:63-64) between two channel-slice views. */
+int xvb_copy_rows(const void* src, int64_t src_pitch_bytes, void* dst, int64_t dst_pitch_bytes, int64_t rows,
+                  int64_t row_bytes, void* stream);
+
 /* out = z * gate[b,:] + in  and optionally next = in + out, all split planes (B,T,C): the SE
  * scaling + residual of SE_Res2Block.forward (:109-111, :149) fused with the running sums
  * x+x1, x+x1+x2 of ECAPA_TDNN.extract_embedding (:405-408).  gate: (B,C) fp32. */
