@@ -65,8 +65,10 @@ class PldaModel:
     def __init__(self, mean, within, between, smoothing=5e-5, device="cuda"):
         mean = np.asarray(mean, dtype=np.float64).reshape(-1, 1)
         d = mean.shape[0]
-        within = np.asarray(within, dtype=np.float64).reshape(d, d) + smoothing * np.eye(d)   # :65
+        self.mean64, self.within64 = mean.copy(), np.asarray(within, dtype=np.float64).reshape(d, d).copy()
+        within = self.within64 + smoothing * np.eye(d)                                        # :65
         between = np.asarray(between, dtype=np.float64).reshape(d, d)
+        self.between64 = between.copy()
         tot_inv = np.linalg.inv(between + within)                                             # :33-35
         w2b_inv = np.linalg.inv(within + 2 * between)
         w_inv = np.linalg.inv(within)
@@ -83,6 +85,14 @@ class PldaModel:
     def read(cls, spec, **kw):
         parts = dict(kaldi_io.read_vec_flt_ark(spec))
         return cls(parts["mean"], parts["within_var"], parts["between_var"], **kw)
+
+    def write(self, spec):
+        """plda_base.plda_write layout (plda_base.py:337-342): three float vectors keyed mean /
+        within_var / between_var (the un-smoothed within-class covariance is stored)."""
+        with kaldi_io.open_or_fd(spec, "wb") as f:
+            kaldi_io.write_vec_flt(f, self.mean64.reshape(-1), key="mean")
+            kaldi_io.write_vec_flt(f, self.within64.reshape(-1), key="within_var")
+            kaldi_io.write_vec_flt(f, self.between64.reshape(-1), key="between_var")
 
     def terms(self, x):
         """x^T Gamma x + x^T c per row."""
