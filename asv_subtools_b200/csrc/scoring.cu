@@ -93,6 +93,63 @@ __global__ void plda_rowterm_kernel(const float* __restrict__ x, const float* __
   if (lane == 0) term[row] = s;
 }
 
+// ---------------------------------------------------------------- score normalisation (S-norm / AS-norm)
+// One CTA per row of a cohort score matrix: bitonic sort (descending) in shared memory, then mean and
+// unbiased standard deviation of the top n entries -- the groupby().head(top_n) / .mean() / .std()
+// (ddof = 1) of score/ScoreNormalization.py:151-166 (AS-norm) and :93-98 (S-norm, n = all).
+__global__ void topn_mean_std_kernel(const float* __restrict__ S, long long ld, int ncoh, int P, int top_n,
+                                     float* __restrict__ mean, float* __restrict__ stdv) {
+  extern __shared__ float sv[];
+  const float* row = S + (long long)blockIdx.x * ld;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) sv[i] = i < ncoh ? row[i] : -INFINITY;
+  __syncthreads();
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const float a = sv[i], b = sv[ixj];
+          const bool desc = (i & k) == 0;           // descending overall
+          if (desc ? (a < b) : (a > b)) { sv[i] = b; sv[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const int n = top_n > 0 && top_n < ncoh ? top_n : ncoh;
+  __shared__ double red[2][32];
+  double s1 = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s1 += (double)sv[i];
+  for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = s1;
+  __syncthreads();
+  double tot = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[0][w];
+  const double mu = tot / (double)n;
+  double s2 = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { const double d = (double)sv[i] - mu; s2 += d * d; }
+  for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  if ((threadIdx.x & 31) == 0) red[1][threadIdx.x >> 5] = s2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double q = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) q += red[1][w];
+    mean[blockIdx.x] = (float)mu;
+    stdv[blockIdx.x] = (float)sqrt(q / (double)(n - 1));   // ddof = 1 like pandas; n == 1 -> NaN as there
+  }
+}
+
+__global__ void snorm_trials_kernel(const float* __restrict__ s, const int32_t* __restrict__ te,
+                                    const int32_t* __restrict__ tt, const float* __restrict__ me,
+                                    const float* __restrict__ se, const float* __restrict__ mt,
+                                    const float* __restrict__ st, long long n, float* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = s[i];
+    const int e = te[i], t = tt[i];
+    out[i] = 0.5f * ((v - me[e]) / se[e] + (v - mt[t]) / st[t]);   // ScoreNormalization.py:101-104 / :172-173
+  }
+}
+
 struct TempBuf {  // stream-ordered scratch
   void* p = nullptr;
   cudaStream_t s;
@@ -168,6 +225,41 @@ extern "C" int xvb_speaker_mean(const float* x, int D, const int32_t* offsets, c
   if (rc) return rc;
   XVB_CHECK_ARG(x && offsets && members && out && D > 0 && num_spk > 0, "xvb_speaker_mean: bad arguments");
   speaker_mean_kernel<<<num_spk, D < 256 ? ((D + 31) / 32) * 32 : 256, 0, (cudaStream_t)stream>>>(x, D, offsets, members, out);
+  XVB_LAUNCH_CHECK();
+  return XVB_OK;
+}
+
+extern "C" int xvb_topn_mean_std(const float* S, int64_t lds, int64_t rows, int ncoh, int top_n, float* mean, float* stdv,
+                                 void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  XVB_CHECK_ARG(S && mean && stdv && rows > 0 && ncoh > 0 && lds >= ncoh, "xvb_topn_mean_std: bad arguments");
+  XVB_CHECK_ARG(ncoh <= 32768, "xvb_topn_mean_std: cohort of %d exceeds the 32768 entries one CTA sorts on chip", ncoh);
+  int P = 1;
+  while (P < ncoh) P <<= 1;
+  const size_t smem = (size_t)P * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    XVB_CUDA(cudaFuncSetAttribute(topn_mean_std_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
+    attr_set = true;
+  }
+  topn_mean_std_kernel<<<(unsigned)rows, 512, smem, (cudaStream_t)stream>>>(S, lds, ncoh, P, top_n, mean, stdv);
+  XVB_LAUNCH_CHECK();
+  return XVB_OK;
+}
+
+extern "C" int xvb_snorm_trials(const float* scores, const int32_t* trial_e, const int32_t* trial_t, int64_t num_trials,
+                                const float* mean_e, const float* std_e, const float* mean_t, const float* std_t,
+                                float* out, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  XVB_CHECK_ARG(scores && trial_e && trial_t && mean_e && std_e && mean_t && std_t && out, "xvb_snorm_trials: null pointer");
+  if (num_trials == 0) return XVB_OK;
+  long long g = (num_trials + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (g > cap) g = cap;
+  snorm_trials_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(scores, trial_e, trial_t, mean_e, std_e, mean_t, std_t,
+                                                                    num_trials, out);
   XVB_LAUNCH_CHECK();
   return XVB_OK;
 }

@@ -270,6 +270,25 @@ def speaker_mean(x, spk2rows):
     return out, counts
 
 
+def topn_mean_std(S, top_n=0):
+    """Per row of a cohort score matrix: mean / unbiased std of the top_n largest entries (0 = all)."""
+    S = _req(S, torch.float32, "S")
+    m = torch.empty(S.shape[0], dtype=torch.float32, device=S.device)
+    sd = torch.empty_like(m)
+    check(lib.xvb_topn_mean_std(_ptr(S), S.shape[1], S.shape[0], S.shape[1], int(top_n), _ptr(m), _ptr(sd), _stream()),
+          "xvb_topn_mean_std")
+    return m, sd
+
+
+def snorm_trials(scores, trial_e, trial_t, mean_e, std_e, mean_t, std_t):
+    scores = _req(scores, torch.float32, "scores")
+    out = torch.empty_like(scores)
+    check(lib.xvb_snorm_trials(_ptr(scores), _ptr(_req(trial_e, torch.int32, "trial_e")),
+                               _ptr(_req(trial_t, torch.int32, "trial_t")), scores.shape[0], _ptr(mean_e), _ptr(std_e),
+                               _ptr(mean_t), _ptr(std_t), _ptr(out), _stream()), "xvb_snorm_trials")
+    return out
+
+
 def bilinear_trials(enroll, test, trial_e, trial_t, row_term=None, col_term=None):
     enroll = _req(enroll, torch.float32, "enroll")
     test = _req(test, torch.float32, "test")

@@ -1,0 +1,102 @@
+"""S-norm / AS-norm on the GPU -- CLI twin of score/ScoreNormalization.py (:17-57):
+
+    python -m asv_subtools_b200.score.normalization [--method asnorm|snorm] [--top-n 300]
+        [--second-cohort true|false] <enroll-test-score> <enroll-cohort-score> <test-cohort-score> <out-score>
+
+The reference groups pandas frames and loops over trials in Python (its own recipe notes the step
+"could be further optimized with using matrix", recipe/voxcelebSRC/gather_results_from_epochs.sh:30-33);
+here the two cohort score tables become dense matrices, one CTA per row sorts its cohort scores on chip
+and takes mean / std(ddof=1) of the top n (csrc/scoring.cu topn_mean_std_kernel), and one elementwise
+kernel normalises the listed trials.  `asnorm_embeddings` skips the score files altogether (cohort
+scores = two cosine GEMMs)."""
+import argparse
+import sys
+import traceback
+
+import numpy as np
+import torch
+
+from .. import ops
+
+
+def normalize(scores, trial_e, trial_t, enroll_cohort, test_cohort, top_n=0):
+    """scores (n,) fp32; trial_e/trial_t int32 indices into the rows of the two cohort matrices
+    (Ne, Nc) / (Nt, Nc), all CUDA.  top_n <= 0: S-norm (all cohort scores)."""
+    me, se = ops.topn_mean_std(enroll_cohort, top_n)
+    mt, st = ops.topn_mean_std(test_cohort, top_n)
+    return ops.snorm_trials(scores, trial_e, trial_t, me, se, mt, st)
+
+
+def asnorm_embeddings(enroll, test, cohort, trial_e, trial_t, top_n=300):
+    """AS-norm straight from length-normalised embeddings: cohort scores are two cosine GEMMs."""
+    pad = (-cohort.shape[0]) % 4
+    if pad:  # the score-matrix kernel wants a multiple of 4 columns; duplicate-free padding with -inf scores is
+        raise ValueError("cohort size must be a multiple of 4 (got {})".format(cohort.shape[0]))
+    s = ops.cosine_trials(enroll, test, trial_e, trial_t)
+    return normalize(s, trial_e, trial_t, ops.cosine_matrix(enroll, cohort), ops.cosine_matrix(test, cohort), top_n)
+
+
+def _load(path):
+    a, b, s = [], [], []
+    with open(path) as f:
+        for line in f:
+            p = line.split()
+            if p:
+                a.append(p[0])
+                b.append(p[1])
+                s.append(float(p[2]))
+    return a, b, np.asarray(s, dtype=np.float64)
+
+
+def _dense(keys, cohort, vals):
+    """(key, cohort, score) triples -> dense (num_keys, num_cohort) matrix + key index."""
+    kidx, cidx = {}, {}
+    for k in keys:
+        kidx.setdefault(k, len(kidx))
+    for c in cohort:
+        cidx.setdefault(c, len(cidx))
+    m = np.full((len(kidx), len(cidx)), -np.inf, dtype=np.float32)
+    m[[kidx[k] for k in keys], [cidx[c] for c in cohort]] = vals
+    if np.isinf(m).any():
+        raise ValueError("cohort score table is not complete (every key needs a score against every cohort utterance)")
+    return m, kidx
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description="Score Normalization (B200).")
+    ap.add_argument("--method", default="asnorm", choices=["snorm", "asnorm"])
+    ap.add_argument("--top-n", type=int, default=300)
+    ap.add_argument("--second-cohort", default="true", choices=["true", "false"])
+    ap.add_argument("--cross-select", default="false", choices=["true", "false"])
+    ap.add_argument("input_score")
+    ap.add_argument("enroll_cohort_score")
+    ap.add_argument("test_cohort_score")
+    ap.add_argument("output_score")
+    print(" ".join(sys.argv))
+    args = ap.parse_args(argv)
+    try:
+        if args.cross_select == "true":
+            raise NotImplementedError("--cross-select true is not on the B200 path yet")
+        te, tt, s = _load(args.input_score)
+        a, b, v = _load(args.enroll_cohort_score)
+        ek, ec = (a, b) if args.second_cohort == "true" else (b, a)
+        em, eidx = _dense(ek, ec, v)
+        a, b, v = _load(args.test_cohort_score)
+        tk, tc = (a, b) if args.second_cohort == "true" else (b, a)
+        tm, tidx = _dense(tk, tc, v)
+        dev = "cuda"
+        ie = torch.tensor([eidx[k] for k in te], dtype=torch.int32, device=dev)
+        it = torch.tensor([tidx[k] for k in tt], dtype=torch.int32, device=dev)
+        out = normalize(torch.from_numpy(s.astype(np.float32)).to(dev), ie, it, torch.from_numpy(em).to(dev),
+                        torch.from_numpy(tm).to(dev), args.top_n if args.method == "asnorm" else 0).cpu().numpy()
+        with open(args.output_score, "w") as f:
+            for x, y, z in zip(te, tt, out):
+                f.write("{} {} {}\n".format(x, y, repr(float(z))))
+    except BaseException as err:
+        if not isinstance(err, KeyboardInterrupt):
+            traceback.print_exc()
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()

@@ -199,6 +199,16 @@ int xvb_cosine_trials(const float* enroll, const float* test, int D, const int32
 int xvb_speaker_mean(const float* x, int D, const int32_t* offsets, const int32_t* members, int num_spk, float* out,
                      void* stream);
 
+/* Score normalisation (score/ScoreNormalization.py).  xvb_topn_mean_std: per row of a cohort score
+ * matrix S (rows, ncoh), mean and unbiased std of the top_n largest entries (top_n <= 0: all) --
+ * groupby().head(top_n) + .mean()/.std() of :151-166 (AS-norm) / :93-98 (S-norm).  xvb_snorm_trials:
+ * out = 0.5*((s-mean_e[e])/std_e[e] + (s-mean_t[t])/std_t[t]) per listed trial (:101-104, :172-173). */
+int xvb_topn_mean_std(const float* S, int64_t lds, int64_t rows, int ncoh, int top_n, float* mean, float* stdv,
+                      void* stream);
+int xvb_snorm_trials(const float* scores, const int32_t* trial_e, const int32_t* trial_t, int64_t num_trials,
+                     const float* mean_e, const float* std_e, const float* mean_t, const float* std_t, float* out,
+                     void* stream);
+
 /* Per-trial bilinear scores with optional per-row / per-column terms:
  * scores[i] = <enroll[te[i]], test[tt[i]]> + row_term[te[i]] + col_term[tt[i]]  (terms may be NULL).
  * With enroll := E.(Lambda+Lambda^T) and the xvb_plda_terms() vectors this is PLDAScoring

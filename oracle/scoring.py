@@ -189,3 +189,20 @@ def synthetic_speakers(num_spk, utts_per_spk, dim, seed, noise=0.5):
     lab = np.repeat(np.arange(num_spk), utts_per_spk)
     emb = spk[lab] + noise * rng.standard_normal((lab.shape[0], dim)).astype(np.float32)
     return emb.astype(np.float32), lab
+
+
+# ---------------------------------------------------------------- S-norm / AS-norm
+def snorm_stats(cohort_scores, top_n=0):
+    """Per-row mean and std (ddof=1, pandas' default) of the top_n largest cohort scores; top_n <= 0
+    means all of them.  score/ScoreNormalization.py:93-98 (S-norm), :151-166 (AS-norm, cross_select
+    false): sort descending, groupby(key).head(top_n), .mean()/.std()."""
+    s = np.sort(np.asarray(cohort_scores, dtype=np.float64), axis=1)[:, ::-1]
+    if top_n and top_n > 0:
+        s = s[:, :top_n]
+    return s.mean(axis=1), s.std(axis=1, ddof=1)
+
+
+def snorm_apply(scores, trial_e, trial_t, mean_e, std_e, mean_t, std_t):
+    """normed = 0.5*((s-mu_e)/sd_e + (s-mu_t)/sd_t), ScoreNormalization.py:101-104 / :172-173."""
+    s = np.asarray(scores, dtype=np.float64)
+    return 0.5 * ((s - mean_e[trial_e]) / std_e[trial_e] + (s - mean_t[trial_t]) / std_t[trial_t])

@@ -207,6 +207,41 @@ def main():
     np.savez_compressed(os.path.join(HERE, "scoring.npz"), **out)
     print("scoring.npz eer", eer_b, eer_d, dcf_d)
 
+    # ------------------------------------------------------------------ S-norm / AS-norm (score/ScoreNormalization.py)
+    import argparse
+    import tempfile
+    sn = load_file_module("score_normalization", os.path.join(REF, "score/ScoreNormalization.py"))
+    rng = np.random.RandomState(501)
+    ne, nt, nc = 6, 9, 40
+    ec = rng.standard_normal((ne, nc)).astype(np.float32)
+    tc = rng.standard_normal((nt, nc)).astype(np.float32)
+    trials = [(i, j, float(np.float32(rng.standard_normal()))) for i in range(ne) for j in range(nt) if (i + j) % 2 == 0]
+    out = {"sn_enroll_cohort": ec, "sn_test_cohort": tc,
+           "sn_trial_e": np.array([t[0] for t in trials], dtype=np.int32),
+           "sn_trial_t": np.array([t[1] for t in trials], dtype=np.int32),
+           "sn_scores": np.array([t[2] for t in trials], dtype=np.float32)}
+    with tempfile.TemporaryDirectory() as d:
+        with open(os.path.join(d, "in"), "w") as f:
+            for i, j, v in trials:
+                f.write("e{} t{} {}\n".format(i, j, repr(v)))
+        with open(os.path.join(d, "ec"), "w") as f:
+            for i in range(ne):
+                for c in range(nc):
+                    f.write("e{} c{} {}\n".format(i, c, repr(float(ec[i, c]))))
+        with open(os.path.join(d, "tc"), "w") as f:
+            for j in range(nt):
+                for c in range(nc):
+                    f.write("t{} c{} {}\n".format(j, c, repr(float(tc[j, c]))))
+        for method, topn in (("snorm", 0), ("asnorm", 7)):
+            ns = argparse.Namespace(method=method, top_n=topn, second_cohort="true", cross_select="false",
+                                    input_score=os.path.join(d, "in"), enroll_cohort_score=os.path.join(d, "ec"),
+                                    test_cohort_score=os.path.join(d, "tc"), output_score=os.path.join(d, "out_" + method))
+            getattr(sn, method)(ns)
+            vals = [float(l.split()[2]) for l in open(ns.output_score)]
+            out["sn_" + method] = np.array(vals, dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "score_norm.npz"), **out)
+    print("score_norm.npz", out["sn_snorm"][:3], out["sn_asnorm"][:3])
+
     # ------------------------------------------------------------------ Kaldi ark bytes
     out = {}
     rng = np.random.RandomState(401)

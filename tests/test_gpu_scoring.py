@@ -133,6 +133,52 @@ def test_eer_identical_to_three_decimals_cosine_and_plda(ops):
         assert round(fn_ref(ref_p, y)[0] * 100, 3) == round(fn_new(p, y)[0] * 100, 3)
 
 
+def test_score_normalization_matches_reference_golden(ops, golden, tmp_path):
+    """S-norm / AS-norm kernels against score/ScoreNormalization.py run on the same tables; then the
+    embedding-level AS-norm against the oracle on a larger cohort; then the CLI twin."""
+    from asv_subtools_b200.score import normalization as norm
+    g = golden("score_norm")
+    ec, tc = cuda(g["sn_enroll_cohort"]), cuda(g["sn_test_cohort"])
+    te, tt = cuda(g["sn_trial_e"], np.int32), cuda(g["sn_trial_t"], np.int32)
+    for method, topn in (("snorm", 0), ("asnorm", 7)):
+        out = norm.normalize(cuda(g["sn_scores"]), te, tt, ec, tc, topn).cpu().numpy()
+        assert np.max(np.abs(out - g["sn_" + method]) / (1 + np.abs(g["sn_" + method]))) < 2e-5, method
+    # embeddings -> cohort GEMMs -> top-300 of a 2000-utterance cohort
+    emb, lab = osc.synthetic_speakers(60, 5, 192, 77, noise=1.2)
+    coh, _ = osc.synthetic_speakers(400, 5, 192, 78, noise=1.2)
+    x = osc.length_norm(emb)
+    c = osc.length_norm(coh)
+    rng = np.random.RandomState(3)
+    ie = rng.randint(0, 300, 5000).astype(np.int32)
+    it = rng.randint(0, 300, 5000).astype(np.int32)
+    got = norm.asnorm_embeddings(cuda(x), cuda(x), cuda(c), cuda(ie, np.int32), cuda(it, np.int32), top_n=300).cpu().numpy()
+    sc = osc.cosine_matrix(x, c)
+    me, se = osc.snorm_stats(sc, 300)
+    ref = osc.snorm_apply(osc.cosine_trials(x, x, ie, it), ie, it, me, se, me, se)
+    assert np.max(np.abs(got - ref) / (1 + np.abs(ref))) < 1e-3
+    y = (lab[ie] == lab[it]).astype(np.int64)
+    from asv_subtools_b200.score import metrics
+    assert round(metrics.eer_bosaris(got, y)[0] * 100, 2) == round(osc.eer_bosaris_like(ref, y)[0] * 100, 2)
+    # CLI twin on score files
+    keys_e = ["e{}".format(i) for i in range(6)]
+    keys_t = ["t{}".format(j) for j in range(9)]
+    with open(tmp_path / "in", "w") as f:
+        for i, j, v in zip(g["sn_trial_e"], g["sn_trial_t"], g["sn_scores"]):
+            f.write("{} {} {}\n".format(keys_e[i], keys_t[j], repr(float(v))))
+    for name, keys, tab in (("ec", keys_e, g["sn_enroll_cohort"]), ("tc", keys_t, g["sn_test_cohort"])):
+        with open(tmp_path / name, "w") as f:
+            for i, k in enumerate(keys):
+                for cidx in range(tab.shape[1]):
+                    f.write("{} c{} {}\n".format(k, cidx, repr(float(tab[i, cidx]))))
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-m", "asv_subtools_b200.score.normalization", "--method", "asnorm", "--top-n", "7",
+                        str(tmp_path / "in"), str(tmp_path / "ec"), str(tmp_path / "tc"), str(tmp_path / "out")],
+                       capture_output=True, text=True, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stdout + r.stderr
+    vals = np.array([float(l.split()[2]) for l in open(tmp_path / "out")])
+    assert np.max(np.abs(vals - g["sn_asnorm"]) / (1 + np.abs(g["sn_asnorm"]))) < 2e-5
+
+
 def test_extract_and_score_clis_end_to_end(tmp_path):
     """feats.ark + checkpoint + nnet.config -> extract CLI -> xvector.ark -> cosine CLI -> EER CLI,
     compared with the oracle running the reference arithmetic on the same files."""

@@ -128,3 +128,12 @@ def test_length_norm_and_means():
     assert np.all(cnt == 5) and np.allclose(m[2], emb[lab == 2].mean(0), atol=1e-6)
     gm = osc.global_mean(emb)
     assert np.allclose(osc.subtract_global_mean(emb, gm).mean(0), 0, atol=1e-6)
+
+
+def test_score_normalization(golden):
+    g = golden("score_norm")
+    for method, topn in (("snorm", 0), ("asnorm", 7)):
+        me, se = osc.snorm_stats(g["sn_enroll_cohort"], topn)
+        mt, st = osc.snorm_stats(g["sn_test_cohort"], topn)
+        out = osc.snorm_apply(g["sn_scores"], g["sn_trial_e"], g["sn_trial_t"], me, se, mt, st)
+        assert np.max(np.abs(out - g["sn_" + method])) < 1e-9, method
