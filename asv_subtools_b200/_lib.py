@@ -65,6 +65,9 @@ SIGNATURES = {
     "xvb_copy_rows": (_i, [_p, _i64, _p, _i64, _i64, _i64, _p]),
     "xvb_se_apply": (_i, [_p, _p, _i64, _p, _p, _i64, _p, _p, _p, _i64, _p, _p, _i64, _i, _i, _i, _p]),
     "xvb_attn_stats_pool": (_i, [_p, _i64, _p, _i64, _i, _i, _i, _f, _p, _p, _p, _i64, _p]),
+    "xvb_vad_energy": (_i, [_p, _p, _i, _i, _f, _f, _i, _f, _p, _p, _p]),
+    "xvb_cmn": (_i, [_p, _p, _i, _i, _i, _p, _p]),
+    "xvb_select_frames": (_i, [_p, _p, _p, _p, _i, _i, _p, _p]),
     "xvb_center_length_norm": (_i, [_p, _p, _p, _i64, _i, _p]),
     "xvb_column_mean": (_i, [_p, _i64, _i, _p, _p]),
     "xvb_cosine_trials": (_i, [_p, _p, _i, _p, _p, _i64, _p, _p]),

@@ -177,6 +177,29 @@ int xvb_attn_stats_pool(const float* logits, int64_t ldl, const float* x, int64_
                         float* out, uint16_t* out_hi, uint16_t* out_lo, int64_t ldo, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Feature-side front-end on a ragged batch: utterance u owns rows
+ * offsets[u] .. offsets[u+1] of the (sum_T, F) fp32 matrix x.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Energy VAD: TorchAsvExtractor::ComputeVadEnergy, runtime/extractor/torch_asv_extractor.cc:14-62
+ * (column 0 = log-energy; threshold += mean_scale * mean(log-energy); a frame is voiced when at least
+ * proportion_threshold of its +-frames_context neighbours exceed the threshold).  voiced: (sum_T)
+ * bytes 0/1; voiced_counts: (U) number of voiced frames per utterance. */
+int xvb_vad_energy(const float* x, const int32_t* offsets, int num_utts, int F, float energy_threshold,
+                   float energy_mean_scale, int frames_context, float proportion_threshold, uint8_t* voiced,
+                   int32_t* voiced_counts, void* stream);
+
+/* Cepstral mean normalisation, no variance norm.  window <= 0: per-utterance mean
+ * (torch_asv_extractor.cc:99-101).  window > 0: Kaldi apply-cmvn-sliding --center=true
+ * --cmn-window=window as used by pytorch/pipeline/extract_xvectors_for_pytorch.sh:105-111. */
+int xvb_cmn(const float* x, const int32_t* offsets, int num_utts, int F, int window, float* y, void* stream);
+
+/* Keep the voiced frames of every utterance, order preserved (torch_asv_extractor.cc:103-107,
+ * Kaldi select-voiced-frames).  out_offsets (U+1) = exclusive prefix sum of the voiced counts. */
+int xvb_select_frames(const float* x, const int32_t* offsets, const uint8_t* voiced, const int32_t* out_offsets,
+                      int num_utts, int F, float* y, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Back-end scoring
  * ------------------------------------------------------------------------------------------- */
 
