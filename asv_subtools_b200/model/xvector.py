@@ -14,9 +14,8 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
-from asv_subtools_b200 import ops  # noqa: E402
 from asv_subtools_b200.nnet import (ReluBatchNormTdnnLayer, StatisticsPooling,  # noqa: E402
-                                    TopVirtualNnet)
+                                    TopVirtualNnet, build_tdnn_extractor)
 
 
 class Xvector(TopVirtualNnet):
@@ -42,29 +41,8 @@ class Xvector(TopVirtualNnet):
         self.transform_keys = ["tdnn1", "tdnn2", "tdnn3", "tdnn4", "tdnn5", "stats", "tdnn6", "tdnn7"]
 
     def build_extractor(self):
-        if self.extracted_embedding not in ("far", "near"):
-            raise TypeError("Expected far or near position, but got {}".format(self.extracted_embedding))
-        self.device_for_extraction()
-        ex = ops.Extractor(self.inputs_dim)
-
-        def arrays(layer):
-            w = layer.affine.weight.detach().float().cpu().numpy()
-            b = layer.affine.bias.detach().float().cpu().numpy() if layer.affine.bias is not None else None
-            scale, shift = layer.folded_bn()
-            return w, b, scale, shift
-
-        for layer in (self.tdnn1, self.tdnn2, self.tdnn3, self.tdnn4, self.tdnn5):
-            w, b, scale, shift = arrays(layer)
-            ex.add_frame_layer(w, b, layer.affine.context, scale, shift, relu=layer.relu)
-        w, b, scale, shift = arrays(self.tdnn6)
-        if self.extracted_embedding == "far":       # xvector.py:92-93: tdnn6.affine only
-            ex.add_segment_layer(w, b)
-        else:                                       # xvector.py:94-96: tdnn6 (full) -> tdnn7.affine
-            ex.add_segment_layer(w, b, scale, shift, relu=self.tdnn6.relu)
-            w7, b7, _, _ = arrays(self.tdnn7)
-            ex.add_segment_layer(w7, b7)
-        ex.finalize(pooling_eps=self.stats.eps)
-        return ex
+        return build_tdnn_extractor(self, self.inputs_dim, (self.tdnn1, self.tdnn2, self.tdnn3, self.tdnn4, self.tdnn5),
+                                    self.stats, self.tdnn6, self.tdnn7, self.extracted_embedding)
 
 
 if __name__ == "__main__":

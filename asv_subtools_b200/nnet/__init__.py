@@ -3,4 +3,4 @@ containers with the reference's names/shapes (so reference checkpoints load unch
 `TopVirtualNnet` plugin base.  All arithmetic is delegated to the native library."""
 from .components import TdnnAffine, ReluBatchNormTdnnLayer  # noqa: F401
 from .pooling import StatisticsPooling  # noqa: F401
-from .framework import TopVirtualNnet, for_extract_embedding  # noqa: F401
+from .framework import TopVirtualNnet, build_tdnn_extractor, for_extract_embedding  # noqa: F401

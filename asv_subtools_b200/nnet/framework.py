@@ -125,3 +125,34 @@ class TopVirtualNnet(torch.nn.Module):
                 raise ValueError("T > maxChunk: use extract_embedding() per utterance")
             x = x.to(self.device_for_extraction(), non_blocking=True).contiguous()
             return self.extractor().extract(x)
+
+
+def build_tdnn_extractor(model, inputs_dim, frame_layers, stats, tdnn6, tdnn7, extracted_embedding):
+    """Hand a TDNN x-vector family model (frame-level ReluBatchNormTdnnLayers -> StatisticsPooling ->
+    tdnn6 [-> tdnn7]) to the native extractor: weights exactly as stored in the state_dict, eval
+    BatchNorm folded to (scale, shift).  "far" = tdnn6.affine, "near" = tdnn6 (full) -> tdnn7.affine
+    (pytorch/model/xvector.py:92-96, extended_xvector.py:112-116)."""
+    from .. import ops
+    if extracted_embedding not in ("far", "near"):
+        raise TypeError("Expected far or near position, but got {}".format(extracted_embedding))
+    model.device_for_extraction()
+    ex = ops.Extractor(inputs_dim)
+
+    def arrays(layer):
+        w = layer.affine.weight.detach().float().cpu().numpy()
+        b = layer.affine.bias.detach().float().cpu().numpy() if layer.affine.bias is not None else None
+        scale, shift = layer.folded_bn()
+        return w, b, scale, shift
+
+    for layer in frame_layers:
+        w, b, scale, shift = arrays(layer)
+        ex.add_frame_layer(w, b, layer.affine.context, scale, shift, relu=layer.relu)
+    w, b, scale, shift = arrays(tdnn6)
+    if extracted_embedding == "far":
+        ex.add_segment_layer(w, b)
+    else:
+        ex.add_segment_layer(w, b, scale, shift, relu=tdnn6.relu)
+        w7, b7, _, _ = arrays(tdnn7)
+        ex.add_segment_layer(w7, b7)
+    ex.finalize(pooling_eps=stats.eps)
+    return ex

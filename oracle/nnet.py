@@ -108,6 +108,36 @@ def xvector_forward(sd, x, extracted_embedding="far", return_intermediates=False
     return (x, inter) if return_intermediates else x
 
 
+EXTENDED_LAYERS = (  # pytorch/model/extended_xvector.py:25-38 (extend=True), in forward order (:101-110)
+    ("tdnn1", [-2, -1, 0, 1, 2]), ("ex_tdnn1", [0]), ("tdnn2", [-2, 0, 2]), ("ex_tdnn2", [0]),
+    ("tdnn3", [-3, 0, 3]), ("ex_tdnn3", [0]), ("ex_tdnn4", [-4, 0, 4]), ("ex_tdnn5", [0]),
+    ("tdnn4", [0]), ("tdnn5", [0]),
+)
+
+
+def extended_xvector_forward(sd, x, extracted_embedding="far"):
+    """ExtendedXvector.extract_embedding body, pytorch/model/extended_xvector.py:99-116."""
+    for name, ctx in EXTENDED_LAYERS:
+        x = relu_bn_tdnn_layer(x, sd, name, ctx)
+    x = statistics_pooling(x)
+    if extracted_embedding == "far":
+        return tdnn_affine(x, sd["tdnn6.affine.weight"], sd["tdnn6.affine.bias"], [0])
+    x = relu_bn_tdnn_layer(x, sd, "tdnn6", [0])
+    return tdnn_affine(x, sd["tdnn7.affine.weight"], sd["tdnn7.affine.bias"], [0])
+
+
+def extended_xvector_spec(inputs_dim):
+    """Keys/shapes of ExtendedXvector(inputs_dim, N, training=False).state_dict() in registration order."""
+    reg = [("tdnn1", inputs_dim, 512, [-2, -1, 0, 1, 2]), ("ex_tdnn1", 512, 512, [0]), ("tdnn2", 512, 512, [-2, 0, 2]),
+           ("ex_tdnn2", 512, 512, [0]), ("tdnn3", 512, 512, [-3, 0, 3]), ("ex_tdnn3", 512, 512, [0]),
+           ("ex_tdnn4", 512, 512, [-4, 0, 4]), ("ex_tdnn5", 512, 512, [0]), ("tdnn4", 512, 512, [0]),
+           ("tdnn5", 512, 1500, [0]), ("tdnn6", 3000, 512, [0]), ("tdnn7", 512, 512, [0])]
+    spec = []
+    for name, cin, cout, ctx in reg:
+        spec += _affine_entries(name, cin, cout, ctx) + _bn_entries(name + ".batchnorm", cout)
+    return spec
+
+
 # --------------------------------------------------------------------------------------
 # ECAPA-TDNN c1024 (pytorch/model/ecapa_tdnn_xvector.py)
 # --------------------------------------------------------------------------------------

@@ -115,6 +115,15 @@ def main():
     m.load_state_dict(sd, strict=True)
     f = onn.synthetic_feats(1, 10050, 23, 4242)[0]
     out["xv23_far_T10050"] = m.extract_embedding(f).numpy()
+    # extended x-vector (pytorch/model/extended_xvector.py)
+    sd = onn.make_state_dict(onn.extended_xvector_spec(80), 103)
+    for pos in ("far", "near"):
+        m = utils.create_model_from_py(os.path.join(REF, "pytorch/model/extended_xvector.py"),
+                                       'ExtendedXvector(80,10,training=False,extracted_embedding="{}")'.format(pos))
+        m.eval()
+        m.load_state_dict(sd, strict=True)
+        feats = onn.synthetic_feats(3, 150, 80, 1103)
+        out["ext80_{}_emb".format(pos)] = np.stack([m.extract_embedding(feats[i]).numpy() for i in range(3)])
     np.savez_compressed(os.path.join(HERE, "xvector.npz"), **out)
     print("xvector.npz", {k: v.shape for k, v in out.items() if hasattr(v, "shape")})
 

@@ -217,6 +217,21 @@ def test_fused_pooling_layer_vs_oracle(ops, B, T):
     assert rel(out[:, 1500:], ref[:, 1500:]) < 1e-4 if T > 1 else np.allclose(out[:, 1500:], 1e-5, rtol=1e-3)
 
 
+@pytest.mark.parametrize("pos", ["far", "near"])
+def test_extended_xvector_matches_reference_golden(golden, pos):
+    from asv_subtools_b200.model.extended_xvector import ExtendedXvector
+    g = golden("xvector")
+    sd = onn.make_state_dict(onn.extended_xvector_spec(80), 103)
+    m = ExtendedXvector(80, 10, training=False, extracted_embedding=pos)
+    m.load_state_dict(sd, strict=True)
+    m.cuda().eval()
+    feats = onn.synthetic_feats(3, 150, 80, 1103)
+    got = m.extract_embedding_batch(feats).cpu().numpy()
+    for i in range(3):
+        assert rel(got[i], g["ext80_{}_emb".format(pos)][i]) < EMB_TOL
+        assert rel(m.extract_embedding(feats[i]).numpy(), g["ext80_{}_emb".format(pos)][i]) < EMB_TOL
+
+
 def test_host_buffer_path_matches_device_path():
     m, _ = _model(80, 102, "far")
     feats = onn.synthetic_feats(8, 200, 80, 77)

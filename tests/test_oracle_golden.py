@@ -137,3 +137,13 @@ def test_score_normalization(golden):
         mt, st = osc.snorm_stats(g["sn_test_cohort"], topn)
         out = osc.snorm_apply(g["sn_scores"], g["sn_trial_e"], g["sn_trial_t"], me, se, mt, st)
         assert np.max(np.abs(out - g["sn_" + method])) < 1e-9, method
+
+
+def test_extended_xvector(golden):
+    g = golden("xvector")
+    sd = onn.make_state_dict(onn.extended_xvector_spec(80), 103)
+    feats = onn.synthetic_feats(3, 150, 80, 1103)
+    for pos in ("far", "near"):
+        emb = np.stack([onn.extract_embedding(lambda x: onn.extended_xvector_forward(sd, x, pos), feats[i]).numpy()
+                        for i in range(3)])
+        assert rel(emb, g["ext80_{}_emb".format(pos)]) < RTOL
