@@ -29,6 +29,14 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+// Timing experiments (profiles/r01_gemm_experiments.md) switch parts of the kernel off and produce
+// WRONG results; they exist only when the library is built with -DXVB_TIMING_EXPERIMENTS.
+#ifdef XVB_TIMING_EXPERIMENTS
+#define XVB_DBG(p, bit) ((p).debug & (bit))
+#else
+#define XVB_DBG(p, bit) 0
+#endif
+
 namespace xvb {
 
 constexpr int kBlockM = 128;
@@ -52,7 +60,7 @@ struct TdnnGemmParams {
   const float* utt_bias;  // per-utterance x column additive term (B, ld_utt), may be NULL
   long long ld_utt;
   int log2_tb;            // Tb is a power of two
-  int debug;              // timing experiments only (XVB_GEMM_DEBUG): bit0 skip epilogue work, bit1 skip MMA issue
+  int debug;              // -DXVB_TIMING_EXPERIMENTS only: bit0 skip epilogue, bit1 skip MMA, bit2 skip store issue, bit3 skip LDTM
   int store_mode;         // 0: epilogue slab -> TMA store; 1: slab -> coalesced st.global (no TMA queueing behind loads)
   float* pool_partial;    // fused statistics pooling: per (time block, utterance, channel) [mean | M2] partials
   int num_src;            // 1, or 2: a second A source accumulated with the same weights (W.(x + x2))
@@ -216,7 +224,7 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
           const uint64_t da_hi = make_kmajor_desc<128>(sa);
           const uint64_t da_lo = make_kmajor_desc<128>(sa + kABytes);
-          for (int s = 0; s < ((p.debug & 2) ? 0 : nsteps); ++s) {
+          for (int s = 0; s < (XVB_DBG(p, 2) ? 0 : nsteps); ++s) {
             const uint64_t koff = (uint64_t)(s * 32 >> 4);  // 16 bf16 = 32 bytes along K inside the swizzle row
 #pragma unroll
             for (int ns = 0; ns < kNSub; ++ns) {
@@ -451,7 +459,7 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
               if (gb < p.B && gt < p.T && col < p.Cout)
                 *reinterpret_cast<uint4*>((plane ? p.y_lo : p.y_hi) + ((long long)gb * p.T + gt) * p.ldy + col) = w;
             }
-          } else if (leader && !(p.debug & 4)) {
+          } else if (leader && !XVB_DBG(p, 4)) {
             tma_store_3d(&map_y_hi, slab_base, n, t0, b0);
             tma_store_3d(&map_y_lo, slab_base + 8192, n, t0, b0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -481,7 +489,7 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
               if (gb < p.B && gt < p.T && col < p.Cout)
                 *reinterpret_cast<float4*>(p.y_f32 + ((long long)gb * p.T + gt) * p.ldyf + col) = w;
             }
-          } else if (leader && !(p.debug & 4)) {
+          } else if (leader && !XVB_DBG(p, 4)) {
             tma_store_3d(&map_y_f32, slab_base, n, t0, b0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
@@ -490,15 +498,15 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
 
       uint32_t va[16], vb[16];
       int ch = 0;
-      if (p.debug & 1) ch = nch;
+      if (XVB_DBG(p, 1)) ch = nch;
       else tmem_ld_32x16(trow, va);
       while (ch < nch) {
         tmem_ld_wait();
-        if (ch + 1 < nch && !(p.debug & 8)) tmem_ld_32x16(trow + (ch + 1) * 32, vb);
+        if (ch + 1 < nch && !XVB_DBG(p, 8)) tmem_ld_32x16(trow + (ch + 1) * 32, vb);
         process(va, ch);
         if (++ch >= nch) break;
         tmem_ld_wait();
-        if (ch + 1 < nch && !(p.debug & 8)) tmem_ld_32x16(trow + (ch + 1) * 32, va);
+        if (ch + 1 < nch && !XVB_DBG(p, 8)) tmem_ld_32x16(trow + (ch + 1) * 32, va);
         process(vb, ch);
         ++ch;
       }
@@ -732,8 +740,12 @@ int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream) {
   p.log2_tb = 0;
   while ((1 << p.log2_tb) < p.Tb) ++p.log2_tb;
   p.store_mode = gemm_store_mode();
+#ifdef XVB_TIMING_EXPERIMENTS
   static const int dbg = getenv("XVB_GEMM_DEBUG") ? atoi(getenv("XVB_GEMM_DEBUG")) : 0;
   p.debug = dbg;
+#else
+  p.debug = 0;
+#endif
   if (p.store_mode == 1) {  // vector stores need whole 16-byte groups inside the row
     if (a.y_hi) XVB_CHECK_ARG(Cout % 8 == 0, "xvb_tdnn_affine: plane output needs Cout%%8==0 (Cout=%d)", Cout);
     if (a.y_f32) XVB_CHECK_ARG(Cout % 4 == 0, "xvb_tdnn_affine: fp32 output needs Cout%%4==0 (Cout=%d)", Cout);
