@@ -180,10 +180,19 @@ class EcapaExtractor:
 
         self.layer1 = tdnn(m.layer1)
         self.blocks = []
+        self.chain = os.environ.get("XVB_ECAPA_RES2NET", "chain") != "gemm"   # one persistent kernel per Res2Net block
         for blk in (m.layer2, m.layer3, m.layer4):
+            res = [tdnn(b) for b in blk.res2net_block.blocks]
             self.blocks.append({
                 "bn1": tdnn(blk.conv_relu_bn1),
-                "res": [tdnn(b) for b in blk.res2net_block.blocks],
+                "res": res,
+                "res_w_hi": torch.cat([r.w.hi for r in res], dim=0).contiguous(),
+                "res_w_lo": torch.cat([r.w.lo for r in res], dim=0).contiguous(),
+                "res_bias": torch.cat([r.bias for r in res]).contiguous(),
+                "res_scale": torch.cat([r.scale for r in res]).contiguous(),
+                "res_shift": torch.cat([r.shift for r in res]).contiguous(),
+                "dilation": blk.res2net_block.context[-1],
+                "nscale": blk.res2net_block.scale,
                 "width": blk.res2net_block.width,
                 "bn2": tdnn(blk.conv_relu_bn2),
                 "se1": _Layer(blk.se.se[1].weight, blk.se.se[1].bias, [0], relu=True, device=device),
@@ -230,11 +239,16 @@ class EcapaExtractor:
         for li, blk in enumerate(self.blocks):
             w = blk["width"]
             blk["bn1"].run(cur, y=H)
-            ops.copy_planes(H.slice(0, w), R.slice(0, w))   # chunk 0 passes through (ecapa_tdnn_xvector.py:63-64)
-            _mark("chunk0 copy")
-            for i, layer in enumerate(blk["res"]):
-                layer.run(H.slice(w * (i + 1), w * (i + 2)), x2=R.slice(w * i, w * (i + 1)) if i >= 1 else None,
-                          y=R.slice(w * (i + 1), w * (i + 2)))
+            if self.chain and w == 128:
+                ops.res2net_block(H, blk["res_w_hi"], blk["res_w_lo"], blk["res_bias"], blk["res_scale"], blk["res_shift"],
+                                  blk["dilation"], blk["nscale"], R)
+                _mark("res2net chain kernel")
+            else:
+                ops.copy_planes(H.slice(0, w), R.slice(0, w))   # chunk 0 passes through (ecapa_tdnn_xvector.py:63-64)
+                _mark("chunk0 copy")
+                for i, layer in enumerate(blk["res"]):
+                    layer.run(H.slice(w * (i + 1), w * (i + 2)), x2=R.slice(w * i, w * (i + 1)) if i >= 1 else None,
+                              y=R.slice(w * (i + 1), w * (i + 2)))
             blk["bn2"].run(R, y=Z)
             _, zm = ops.plane_mean(Z)
             _mark("plane_mean")

@@ -160,6 +160,14 @@ def plane_mean(x, planes=True):
     return out, op
 
 
+def res2net_block(x, w_hi, w_lo, bias, scale, shift, dilation, nscale, y):
+    """One-kernel Res2Net block: x, y SplitPlanes (B,T,nscale*128); stacked packed weights/params."""
+    b, t = x.hi.shape[0], x.hi.shape[1]
+    check(lib.xvb_res2net_block(x.hi.data_ptr(), x.lo.data_ptr(), x.ld, _ptr(w_hi), _ptr(w_lo), _ptr(bias), _ptr(scale),
+                                _ptr(shift), int(dilation), int(nscale), y.hi.data_ptr(), y.lo.data_ptr(), y.ld, b, t,
+                                _stream()), "xvb_res2net_block")
+
+
 def copy_planes(src, dst):
     """dst[...] = src[...] for two SplitPlanes views of equal shape (B,T,c), c % 8 == 0."""
     rows = src.hi.shape[0] * src.hi.shape[1]

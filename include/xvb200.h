@@ -158,6 +158,16 @@ int xvb_stats_pool_ex(const float* x, int64_t ldx, int B, int T, int C, float ep
 int xvb_plane_mean(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, int B, int T, int C, float* out,
                    uint16_t* out_hi, uint16_t* out_lo, int64_t ldo, void* stream);
 
+/* Res2NetBlock.forward (pytorch/model/ecapa_tdnn_xvector.py:61-75) as ONE persistent kernel: chunk 0
+ * of x passes through; step i = TDNN 128->128, context [-d,0,d], ReLU, BN on (x chunk i+1 [+ y chunk i]),
+ * written to y chunk i+1.  A CTA owns whole utterances and walks them through all scale-1 steps, so the
+ * serial chain needs no grid-wide synchronisation and no per-step launches.  x, y: split planes
+ * (B,T,scale*128) with pitches ldx/ldy (distinct tensors).  w_hi/w_lo: the scale-1 packed weights
+ * (xvb_pack_tdnn_weight, each (128, 3*128)) stacked along rows; bias/bn_scale/bn_shift: (scale-1, 128). */
+int xvb_res2net_block(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, const uint16_t* w_hi, const uint16_t* w_lo,
+                      const float* bias, const float* bn_scale, const float* bn_shift, int dilation, int scale,
+                      uint16_t* y_hi, uint16_t* y_lo, int64_t ldy, int B, int T, void* stream);
+
 /* Strided row copy (16-byte granularity): the pass-through of Res2Net's first chunk
  * (ecapa_tdnn_xvector.py:63-64) between two channel-slice views. */
 int xvb_copy_rows(const void* src, int64_t src_pitch_bytes, void* dst, int64_t dst_pitch_bytes, int64_t rows,

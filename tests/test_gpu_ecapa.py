@@ -61,6 +61,40 @@ def test_second_source_and_channel_slices(ops):
     assert np.all(got[:, :, :256] == 0) and np.all(got[:, :, 384:] == 0)   # nothing outside the slice was touched
 
 
+@pytest.mark.parametrize("B,T,d", [(5, 150, 3), (2, 300, 4), (3, 40, 2), (150, 20, 2)])
+def test_res2net_chain_kernel_vs_oracle(ops, B, T, d):
+    """The one-kernel Res2Net block (CTA-owned utterances, 7 dependent steps) against the oracle's
+    chunk/add/cat restatement, and against the seven-launch GEMM path."""
+    from asv_subtools_b200.nnet.components import fold_batchnorm
+    rng = np.random.RandomState(40 + d)
+    x = rng.standard_normal((B, T, 1024)).astype(np.float32)
+    spec = []
+    for i in range(7):
+        pfx = "blk.blocks.{}".format(i)
+        spec += onn._affine_entries(pfx, 128, 128, [-d, 0, d]) + onn._bn_entries(pfx + ".batchnorm", 128)
+    sd = onn.make_state_dict(spec, 900 + d)
+    with torch.no_grad():
+        ref = onn.res2net_block(torch.from_numpy(x).transpose(1, 2), sd, "blk", d).transpose(1, 2).numpy()
+    xp = ops.split_f32(cu(x))
+    packs, biases, scales, shifts = [], [], [], []
+    for i in range(7):
+        pfx = "blk.blocks.{}".format(i)
+        packs.append(ops.pack_tdnn_weight(sd[pfx + ".affine.weight"].cuda().contiguous(), [-d, 0, d]))
+        biases.append(sd[pfx + ".affine.bias"])
+        bn = torch.nn.BatchNorm1d(128)
+        bn.load_state_dict({k.split(".")[-1]: v for k, v in sd.items() if k.startswith(pfx + ".batchnorm.")})
+        sc, sh = fold_batchnorm(bn)
+        scales.append(torch.from_numpy(sc))
+        shifts.append(torch.from_numpy(sh))
+    y = ops.SplitPlanes.empty((B, T, 1024), "cuda")
+    ops.res2net_block(xp, torch.cat([p.hi for p in packs]).contiguous(), torch.cat([p.lo for p in packs]).contiguous(),
+                      torch.cat(biases).cuda(), torch.cat(scales).cuda(), torch.cat(shifts).cuda(), d, 8, y)
+    got = y.float().cpu().numpy()
+    assert np.all(np.isfinite(got))
+    assert rel(got, ref) < 1e-4            # seven chained layers, each at the 3e-5 GEMM tolerance
+    assert np.array_equal(got[:, :, :128], xp.float().cpu().numpy()[:, :, :128])   # chunk 0 passes through
+
+
 def test_utt_bias_tanh_sigmoid_and_dual_output(ops):
     rng = np.random.RandomState(2)
     B, T, Cin, Cout = 5, 37, 192, 128
