@@ -152,6 +152,9 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
+  // prefetch) may overlap the tail of the previous kernel in the stream; its results are needed from here on.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const int num_kblk = p.num_src * p.ntaps * p.num_cblk;
 
@@ -681,13 +684,16 @@ static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCta;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  static const int pdl = getenv("XVB_PDL") ? atoi(getenv("XVB_PDL")) : 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 2 : 1;
   XVB_CUDA(cudaLaunchKernelEx(&cfg, tdnn_gemm_bf16x3_kernel<BLOCK_N, kCta, kNSub, kPool>, ma_hi, ma_lo, ma2_hi, ma2_lo, mw_hi, mw_lo,
                               my_hi, my_lo, my_f32, p));
   XVB_LAUNCH_CHECK();
