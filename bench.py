@@ -166,6 +166,34 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def c1_latency(dev):
+    """BASELINE configs[0] on the GPU path: one (200, 23) MFCC utterance through the plugin call
+    `model.extract_embedding(ndarray) -> CPU tensor` (H2D, 8 kernels, D2H + sync per call), and the same
+    utterance through the oracle port on the host cores."""
+    from asv_subtools_b200.model.xvector import Xvector
+    from oracle import nnet as onn
+    sd = onn.make_state_dict(onn.xvector_spec(23), 101)
+    m = Xvector(23, 10, training=False, extracted_embedding="far")
+    m.load_state_dict(sd, strict=True)
+    m.to(dev).eval()
+    feats = onn.synthetic_feats(1, 200, 23, 5)[0]
+    for _ in range(10):
+        m.extract_embedding(feats)
+    ts = []
+    for _ in range(100):
+        t0 = time.perf_counter()
+        m.extract_embedding(feats)
+        ts.append(time.perf_counter() - t0)
+    gpu_ms = statistics.median(ts) * 1e3
+    cs = []
+    for _ in range(8):
+        t0 = time.perf_counter()
+        onn.extract_embedding(lambda z: onn.xvector_forward(sd, z, "far"), feats)
+        cs.append(time.perf_counter() - t0)
+    return {"workload": "Xvector(23) one 200-frame utterance, extract_embedding(ndarray)->CPU tensor",
+            "gpu_ms_per_utt": gpu_ms, "cpu_port_ms_per_utt": statistics.median(cs) * 1e3}
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def run_native(args, rank, world, local_rank):
     import torch.distributed as dist
@@ -277,7 +305,9 @@ def run_native(args, rank, world, local_rank):
     value = frames / (ms * 1e-3)
     achieved = GEMM_FLOP_PER_STEP / (gemm_ms * 1e-3) / 1e12
     pool_gbs = POOL_BYTES_PER_STEP / (pool_ms * 1e-3) / 1e9
-    cpu_batched, cpu_per_utt = cpu_port_frames_per_s(sd, 16.0, 64, os.cpu_count() or 1)
+    # CPU arm beside the GPU number: on rank 0 at N=1 only (it costs ~16 s of host time)
+    cpu_batched, cpu_per_utt = cpu_port_frames_per_s(sd, 16.0, 64, os.cpu_count() or 1) if world == 1 else (None, None)
+    c1 = c1_latency(dev) if world == 1 else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -310,11 +340,14 @@ def run_native(args, rank, world, local_rank):
                                 "traffic_unit": "bytes/launch (profiles/r01p_pool_ncu_summary.txt); algorithmic 310.3 MB",
                                 "ms": pool_ms, "peak_source": pk["src"]},
         "kernel_ms": {n: float(v) for n, v in zip(names, per)},
-        "cpu_baseline": {"value": cpu_batched, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                         "sample": "64 utts x 200 frames batched forward for ~10 s (most favourable to the reference); "
-                                   "the reference's literal batch-1 extract_embedding loop: %.0f frames/s" % cpu_per_utt,
-                         "per_utterance_value": cpu_per_utt},
     }
+    if world == 1:
+        line["cpu_baseline"] = {"value": cpu_batched, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                "sample": "64 utts x 200 frames batched forward for ~10 s (most favourable to the "
+                                          "reference); the reference's literal batch-1 extract_embedding loop: "
+                                          "%.0f frames/s" % cpu_per_utt,
+                                "per_utterance_value": cpu_per_utt}
+        line["c1_single_utterance"] = c1
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
