@@ -55,8 +55,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
+// Fused consumer of a score matrix (scoring.cu: xvb_trial_histogram): instead of storing
+// S = A.B^T + row + col, every score is binned into a (2, nbins) histogram by trial class.
+struct TrialHist {
+  unsigned long long* hist;
+  const int* row_label;
+  const int* col_label;
+  float lo, inv_w;
+  int nbins;
+  int symmetric;
+  int unit_first, unit_stride;   // 256-row units walked by this launch: unit_first + k * unit_stride
+};
+
 // tdnn_gemm.cu: the tcgen05 layer behind xvb_tdnn_affine / xvb_tdnn_affine_ex.
-int tdnn_affine_impl(const xvb_tdnn_args_t& args, void* stream);
+int tdnn_affine_impl(const xvb_tdnn_args_t& args, void* stream, const TrialHist* hist = nullptr);
 
 // tdnn_gemm.cu: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda).
 int make_tensor_map(CUtensorMap* m, const void* base, int esize, int rank, const unsigned long long* dims,

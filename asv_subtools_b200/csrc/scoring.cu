@@ -164,28 +164,33 @@ struct TempBuf {  // stream-ordered scratch
 // out (Ne, Nt) = A (Ne, D) . Bm (Nt, D)^T  [+ row_bias[i] + col_bias[j]] through the tcgen05 layer.
 static int matmul_nt(const float* A, int64_t Ne, const float* Bm, int64_t Nt, int D, const float* row_bias,
                      const float* col_bias, float* out, int64_t ldo, uint16_t* out_hi, uint16_t* out_lo,
-                     int64_t ldplane, cudaStream_t s) {
+                     int64_t ldplane, cudaStream_t s, const TrialHist* th = nullptr) {
   const int64_t ldp = round_up(D, 16);
+  const bool same = A == Bm && Ne == Nt;   // all pairs of one set: split once
   TempBuf ta(s), tb(s);
   int rc = ta.alloc((size_t)Ne * ldp * 2 * 2);
   if (rc) return rc;
-  rc = tb.alloc((size_t)Nt * ldp * 2 * 2);
-  if (rc) return rc;
   uint16_t* a_hi = (uint16_t*)ta.p;
   uint16_t* a_lo = a_hi + Ne * ldp;
-  uint16_t* b_hi = (uint16_t*)tb.p;
-  uint16_t* b_lo = b_hi + Nt * ldp;
   rc = xvb_split_f32(A, Ne, D, D, a_hi, a_lo, ldp, s);
   if (rc) return rc;
-  rc = xvb_split_f32(Bm, Nt, D, D, b_hi, b_lo, ldp, s);
-  if (rc) return rc;
+  uint16_t* b_hi = a_hi;
+  uint16_t* b_lo = a_lo;
+  if (!same) {
+    rc = tb.alloc((size_t)Nt * ldp * 2 * 2);
+    if (rc) return rc;
+    b_hi = (uint16_t*)tb.p;
+    b_lo = b_hi + Nt * ldp;
+    rc = xvb_split_f32(Bm, Nt, D, D, b_hi, b_lo, ldp, s);
+    if (rc) return rc;
+  }
   const int ctx0 = 0;
   xvb_tdnn_args_t g{};
   g.x_hi = a_hi; g.x_lo = a_lo; g.ldx = ldp; g.w_hi = b_hi; g.w_lo = b_lo;
   g.bias = col_bias; g.row_bias = row_bias; g.context_host = &ctx0; g.ntaps = 1;
   g.y_hi = out_hi; g.y_lo = out_lo; g.ldy = ldplane; g.y_f32 = out; g.ldyf = ldo;
   g.B = (int)Ne; g.T = 1; g.Cin = D; g.Cout = (int)Nt;
-  return tdnn_affine_impl(g, s);
+  return tdnn_affine_impl(g, s, th);
 }
 
 }  // namespace xvb
@@ -334,4 +339,26 @@ extern "C" int xvb_plda_matrix(const float* enroll, int64_t Ne, const float* tes
   rc = matmul_nt(enroll, Ne, L2, D, D, nullptr, nullptr, (float*)el.p, D, nullptr, nullptr, 0, s);
   if (rc) return rc;
   return matmul_nt((const float*)el.p, Ne, test, Nt, D, row, col, S, lds, nullptr, nullptr, 0, s);
+}
+
+// Scores -> histogram, fused: S = enroll . test^T + row_term + col_term is consumed tile by tile in
+// the GEMM epilogue (shared-memory counters, one u64 flush per CTA), so 10^12 trials cost no HBM
+// traffic beyond the embeddings themselves.  SURVEY Appendix A, C4/C5 "fused consumer".
+extern "C" int xvb_trial_histogram(const float* enroll, int64_t Ne, const int32_t* enroll_spk, const float* test,
+                                   int64_t Nt, const int32_t* test_spk, int D, const float* row_term,
+                                   const float* col_term, int symmetric, int unit_first, int unit_stride, float lo,
+                                   float hi, int nbins, unsigned long long* hist, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  XVB_CHECK_ARG(enroll && test && enroll_spk && test_spk && hist && Ne > 0 && Nt > 0 && D > 0, "xvb_trial_histogram: bad arguments");
+  XVB_CHECK_ARG(Ne < (1ll << 31) && Nt < (1ll << 31), "xvb_trial_histogram: too many rows for one call");
+  XVB_CHECK_ARG(nbins >= 4 && nbins <= 2048, "xvb_trial_histogram: nbins=%d outside [4, 2048] (2 x nbins u32 counters live in 16 KB of shared memory)", nbins);
+  XVB_CHECK_ARG(hi > lo, "xvb_trial_histogram: empty score window [%g, %g)", (double)lo, (double)hi);
+  XVB_CHECK_ARG(unit_first >= 0 && unit_stride >= 1, "xvb_trial_histogram: bad row-unit shard %d/%d", unit_first, unit_stride);
+  XVB_CHECK_ARG(!symmetric || Ne == Nt, "xvb_trial_histogram: symmetric mode needs one set on both sides (Ne == Nt)");
+  TrialHist th{};
+  th.hist = hist; th.row_label = enroll_spk; th.col_label = test_spk;
+  th.lo = lo; th.inv_w = (float)(nbins - 2) / (hi - lo); th.nbins = nbins; th.symmetric = symmetric ? 1 : 0;
+  th.unit_first = unit_first; th.unit_stride = unit_stride;
+  return matmul_nt(enroll, Ne, test, Nt, D, row_term, col_term, nullptr, 0, nullptr, nullptr, 0, (cudaStream_t)stream, &th);
 }

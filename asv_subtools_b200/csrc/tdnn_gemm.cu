@@ -64,6 +64,15 @@ struct TdnnGemmParams {
   int store_mode;         // 0: epilogue slab -> TMA store; 1: slab -> coalesced st.global (no TMA queueing behind loads)
   float* pool_partial;    // fused statistics pooling: per (time block, utterance, channel) [mean | M2] partials
   int num_src;            // 1, or 2: a second A source accumulated with the same weights (W.(x + x2))
+  // M-unit sharding (a unit = kCta x 128 rows): this launch walks units unit_first + k * unit_stride
+  int unit_first, unit_stride;
+  // fused trial histogram (scoring.cu: xvb_trial_histogram): the scores never leave the SM
+  unsigned long long* hist;   // (2, hist_bins) u64 counters [nontarget | target], accumulated; NULL = off
+  const int* row_label;       // speaker id per row / per column
+  const int* col_label;
+  float hist_lo, hist_inv_w;  // bin = 1 + floor((s - lo) * inv_w); bin 0: s < lo; bin nbins-1: at or above hi
+  int hist_bins;
+  int hist_sym;               // count only column index > row index (all pairs of one set, each once)
   __nv_bfloat16* y_hi;
   __nv_bfloat16* y_lo;
   long long ldy;
@@ -100,7 +109,8 @@ struct GemmCfg {
 // TMEM columns) -- so an epilogue thread owns ONE channel and sees the tile's frames as consecutive
 // accumulator columns: pooling over time becomes a running (Welford) update in registers, with no
 // shuffles, no shared memory and no (B,T,C) output at all.
-template <int BLOCK_N, int kCta, int kNSub, bool kPool>
+// kHist: the epilogue bins the scores into a trial histogram instead of storing them (scoring.cu).
+template <int BLOCK_N, int kCta, int kNSub, bool kPool, bool kHist>
 __global__ void __launch_bounds__(kNumThreads, 1)
 tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                         const __grid_constant__ CUtensorMap map_a2_hi, const __grid_constant__ CUtensorMap map_a2_lo,
@@ -164,7 +174,9 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile_first; tile < p.num_tiles; tile += tile_step) {
-        const int m_blk = (tile / p.num_n_blk) * kCta + (int)cta_rank, n_blk = tile % p.num_n_blk;
+        const int m_unit = p.unit_first + (tile / p.num_n_blk) * p.unit_stride, n_blk = tile % p.num_n_blk;
+        if (kHist && p.hist_sym && n_blk < m_unit) continue;   // tile entirely on or below the diagonal (unit rows == kTileN)
+        const int m_blk = m_unit * kCta + (int)cta_rank;
         const int b0 = (m_blk / p.num_t_blk) * p.Bb, t0 = (m_blk % p.num_t_blk) * p.Tb;  // may be fully out of
         const int n0 = n_blk * kTileN + (int)cta_rank * Cfg::kBRows;                      // range: TMA zero-fills
         for (int src = 0; src < p.num_src; ++src) {
@@ -212,8 +224,10 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
-      for (int tile = tile_first; tile < p.num_tiles; tile += tile_step, ++it) {
+      for (int tile = tile_first; tile < p.num_tiles; tile += tile_step) {
+        if (kHist && p.hist_sym && tile % p.num_n_blk < p.unit_first + (tile / p.num_n_blk) * p.unit_stride) continue;
         const uint32_t acc = kAccStages == 2 ? (it & 1) : 0, acc_phase = kAccStages == 2 ? ((it >> 1) & 1) : (it & 1);
+        ++it;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kTileN;
@@ -273,9 +287,40 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     const bool planes = p.y_hi != nullptr;
     const bool f32o = p.y_f32 != nullptr;
     uint32_t it = 0;
-    for (int tile = tile_first; tile < p.num_tiles; tile += tile_step, ++it) {
+    // fused trial histogram: the 16 KB store slab holds 2 x hist_bins u32 counters instead
+    constexpr bool hist = kHist;
+    uint32_t h_below[2] = {0u, 0u}, h_above[2] = {0u, 0u};   // out-of-window scores: counted in registers
+    const uint32_t hslab = smem_u32(slab_base);
+    auto hist_flush = [&]() {
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        if (h_below[c]) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hslab + (c * p.hist_bins) * 4), "r"(h_below[c]) : "memory");
+        if (h_above[c]) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hslab + (c * p.hist_bins + p.hist_bins - 1) * 4), "r"(h_above[c]) : "memory");
+        h_below[c] = 0u; h_above[c] = 0u;
+      }
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+      for (int e = etid; e < 2 * p.hist_bins; e += kNumEpiWarps * 32) {
+        uint32_t c;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c) : "r"(hslab + e * 4) : "memory");
+        if (c) {
+          atomicAdd(p.hist + e, (unsigned long long)c);
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(hslab + e * 4), "r"(0u) : "memory");
+        }
+      }
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+    };
+    if (hist) {
+      for (int e = etid; e < 2 * p.hist_bins; e += kNumEpiWarps * 32)
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(hslab + e * 4), "r"(0u) : "memory");
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+    }
+    for (int tile = tile_first; tile < p.num_tiles; tile += tile_step) {
+      const int m_unit = p.unit_first + (tile / p.num_n_blk) * p.unit_stride, n_blk = tile % p.num_n_blk;
+      if (kHist && p.hist_sym && n_blk < m_unit) continue;
       const uint32_t acc = kAccStages == 2 ? (it & 1) : 0, acc_phase = kAccStages == 2 ? ((it >> 1) & 1) : (it & 1);
-      const int m_blk = (tile / p.num_n_blk) * kCta + (int)cta_rank, n_blk = tile % p.num_n_blk;
+      ++it;
+      const int m_blk = m_unit * kCta + (int)cta_rank;
       const int b0 = (m_blk / p.num_t_blk) * p.Bb, t0 = (m_blk % p.num_t_blk) * p.Tb;
       const int b = b0 + row / p.Tb, t = t0 + row % p.Tb;
       const bool valid = (b < p.B) && (t < p.T);
@@ -289,7 +334,7 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
         const float scale_c = (cvalid && bn) ? __ldg(p.scale + cch) : 1.f;
         const float shift_c = (cvalid && bn) ? __ldg(p.shift + cch) : 0.f;
         const float floor_c = relu ? 0.f : -INFINITY;
-        const int mh = (tile / p.num_n_blk) * 2 + hb;
+        const int mh = m_unit * 2 + hb;
         const int bh0 = (mh / p.num_t_blk) * p.Bb, th0 = (mh % p.num_t_blk) * p.Tb, tblk = mh % p.num_t_blk;
         mbar_wait(&tmem_full_bar[acc], acc_phase);
         tcgen05_fence_after();
@@ -382,7 +427,8 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
         const int c = n0 + e;
         const bool in = c < p.Cout;
         st_shared_f32(prm + e * 4, (in && p.bias) ? __ldg(p.bias + c) : 0.f);
-        st_shared_f32(prm + (kTileN + e) * 4, (in && bn) ? __ldg(p.scale + c) : 1.f);
+        if (hist) st_shared_f32(prm + (kTileN + e) * 4, __int_as_float(in ? __ldg(p.col_label + c) : -2));
+        else st_shared_f32(prm + (kTileN + e) * 4, (in && bn) ? __ldg(p.scale + c) : 1.f);
         st_shared_f32(prm + (2 * kTileN + e) * 4, (in && bn) ? __ldg(p.shift + c) : 0.f);
       }
       asm volatile("bar.sync 3, 256;" ::: "memory");
@@ -499,6 +545,33 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
         }
       };
 
+      // trial histogram: score -> bin -> shared-memory counter of its class (same / different speaker)
+      const int lab_r = (hist && valid) ? __ldg(p.row_label + b) : -1;
+      auto process_hist = [&](uint32_t (&v)[16], int ch) {
+        const int pc = ch * 32 + half * 16;
+        const float top = (float)(p.hist_bins - 2);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float4 bb = ld_shared_f4(prm + (pc + 4 * g) * 4);
+          const float4 ll = ld_shared_f4(prm + (kTileN + pc + 4 * g) * 4);
+          const float cb[4] = {bb.x, bb.y, bb.z, bb.w};
+          const int cl[4] = {__float_as_int(ll.x), __float_as_int(ll.y), __float_as_int(ll.z), __float_as_int(ll.w)};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int col = n0 + pc + 4 * g + k;
+            const bool ok = valid && cl[k] != -2 && (!p.hist_sym || col > b);
+            const float sc = __uint_as_float(v[4 * g + k]) + cb[k] + rbias;
+            const float x = (sc - p.hist_lo) * p.hist_inv_w;
+            const uint32_t cls = cl[k] == lab_r ? 1u : 0u;
+            if (ok) {
+              if (x < 0.f) { h_below[0] += 1u - cls; h_below[1] += cls; }
+              else if (!(x < top)) { h_above[0] += 1u - cls; h_above[1] += cls; }
+              else asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hslab + ((int)cls * p.hist_bins + 1 + (int)x) * 4), "r"(1u) : "memory");
+            }
+          }
+        }
+      };
+
       uint32_t va[16], vb[16];
       int ch = 0;
       if (XVB_DBG(p, 1)) ch = nch;
@@ -506,17 +579,19 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
       while (ch < nch) {
         tmem_ld_wait();
         if (ch + 1 < nch && !XVB_DBG(p, 8)) tmem_ld_32x16(trow + (ch + 1) * 32, vb);
-        process(va, ch);
+        if constexpr (hist) process_hist(va, ch); else process(va, ch);
         if (++ch >= nch) break;
         tmem_ld_wait();
         if (ch + 1 < nch && !XVB_DBG(p, 8)) tmem_ld_32x16(trow + (ch + 1) * 32, va);
-        process(vb, ch);
+        if constexpr (hist) process_hist(vb, ch); else process(vb, ch);
         ++ch;
       }
       tcgen05_fence_before();
       if constexpr (kCta == 1) mbar_arrive(&tmem_empty_bar[acc]);
       else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);  // the leader's barrier counts both CTAs' epilogues
+      if (hist && (it & 0x3fffu) == 0) hist_flush();      // u32 counters: <= 2^14 tiles x 2^15 scores between flushes
     }
+    if (hist) hist_flush();
     if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
   }
 
@@ -645,7 +720,7 @@ static int make_out_map(CUtensorMap* m, const void* base, int esize, int C, int 
   return XVB_OK;
 }
 
-template <int BLOCK_N, int kCta, int kNSub = 1, bool kPool = false>
+template <int BLOCK_N, int kCta, int kNSub = 1, bool kPool = false, bool kHist = false>
 static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& ma2_hi,
                        const CUtensorMap& ma2_lo, const void* w_hi, const void* w_lo, TdnnGemmParams& p,
                        cudaStream_t stream) {
@@ -657,11 +732,14 @@ static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const
   rc = make_weight_map(&mw_lo, w_lo, K, p.Cout, Cfg::kBRows);
   if (rc) return rc;
   p.num_n_blk = (p.Cout + Cfg::kTileN - 1) / Cfg::kTileN;
-  const int num_m_units = (p.num_t_blk * p.num_b_blk + kCta - 1) / kCta;  // 128-row blocks, or pairs of them
+  const int all_m_units = (p.num_t_blk * p.num_b_blk + kCta - 1) / kCta;  // 128-row blocks, or pairs of them
+  if (p.unit_first >= all_m_units) return XVB_OK;                         // this shard owns no rows
+  const int num_m_units = (all_m_units - p.unit_first + p.unit_stride - 1) / p.unit_stride;
+  XVB_CHECK_ARG((long long)num_m_units * p.num_n_blk < (1ll << 31), "xvb_tdnn_affine: %d x %d tiles exceed one launch", num_m_units, p.num_n_blk);
   p.num_tiles = num_m_units * p.num_n_blk;
   static bool attr_set = false;
   if (!attr_set) {
-    XVB_CUDA(cudaFuncSetAttribute(tdnn_gemm_bf16x3_kernel<BLOCK_N, kCta, kNSub, kPool>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    XVB_CUDA(cudaFuncSetAttribute(tdnn_gemm_bf16x3_kernel<BLOCK_N, kCta, kNSub, kPool, kHist>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -694,7 +772,7 @@ static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const
   static const int pdl = getenv("XVB_PDL") ? atoi(getenv("XVB_PDL")) : 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 2 : 1;
-  XVB_CUDA(cudaLaunchKernelEx(&cfg, tdnn_gemm_bf16x3_kernel<BLOCK_N, kCta, kNSub, kPool>, ma_hi, ma_lo, ma2_hi, ma2_lo, mw_hi, mw_lo,
+  XVB_CUDA(cudaLaunchKernelEx(&cfg, tdnn_gemm_bf16x3_kernel<BLOCK_N, kCta, kNSub, kPool, kHist>, ma_hi, ma_lo, ma2_hi, ma2_lo, mw_hi, mw_lo,
                               my_hi, my_lo, my_f32, p));
   XVB_LAUNCH_CHECK();
   return XVB_OK;
@@ -704,7 +782,7 @@ static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const
 
 using namespace xvb;
 
-int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream) {
+int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream, const TrialHist* th) {
   int rc = require_sm100();
   if (rc) return rc;
   const int B = a.B, T = a.T, Cin = a.Cin, Cout = a.Cout, ntaps = a.ntaps;
@@ -715,7 +793,7 @@ int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream) {
   XVB_CHECK_ARG((a.x2_hi != nullptr) == (a.x2_lo != nullptr), "xvb_tdnn_affine: x2_hi/x2_lo must both be set or both NULL");
   if (a.x2_hi) XVB_CHECK_ARG(a.ldx2 % 8 == 0 && a.ldx2 >= Cin, "xvb_tdnn_affine: ldx2=%lld must be a multiple of 8 and >= Cin", (long long)a.ldx2);
   XVB_CHECK_ARG((a.y_hi != nullptr) == (a.y_lo != nullptr), "xvb_tdnn_affine: y_hi/y_lo must both be set or both NULL");
-  XVB_CHECK_ARG(a.y_hi || a.y_f32 || a.pool_partial, "xvb_tdnn_affine: no output requested");
+  XVB_CHECK_ARG(a.y_hi || a.y_f32 || a.pool_partial || th, "xvb_tdnn_affine: no output requested");
   if (a.pool_partial) XVB_CHECK_ARG(!a.y_hi && !a.y_f32 && Cout % 4 == 0 && (uintptr_t)a.pool_partial % 16 == 0,
                                     "xvb_tdnn_affine: pool_partial excludes other outputs and needs Cout%%4==0");
   if (a.y_hi) XVB_CHECK_ARG(a.ldy % 8 == 0 && a.ldy >= Cout, "xvb_tdnn_affine: plane output needs ldy%%8==0 and ldy>=Cout");
@@ -743,6 +821,12 @@ int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream) {
   p.utt_bias = a.utt_bias; p.ld_utt = a.ld_utt_bias;
   p.pool_partial = a.pool_partial;
   p.num_src = a.x2_hi ? 2 : 1;
+  p.unit_first = 0; p.unit_stride = 1;
+  if (th) {
+    p.hist = th->hist; p.row_label = th->row_label; p.col_label = th->col_label;
+    p.hist_lo = th->lo; p.hist_inv_w = th->inv_w; p.hist_bins = th->nbins; p.hist_sym = th->symmetric;
+    p.unit_first = th->unit_first; p.unit_stride = th->unit_stride;
+  }
   p.log2_tb = 0;
   while ((1 << p.log2_tb) < p.Tb) ++p.log2_tb;
   p.store_mode = gemm_store_mode();
@@ -780,6 +864,8 @@ int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream) {
   const void* w_lo = a.w_lo;
   if (a.pool_partial)  // fused pooling always runs on the swapped CTA-pair kernel (any shape: TMA zero-fills)
     return launch_gemm<256, 2, 1, true>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
+  if (th)              // the diagonal test of the symmetric mode assumes 256-row units x 256-column tiles
+    return launch_gemm<256, 2, 1, false, true>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
   static const int force_bn = getenv("XVB_GEMM_BN") ? atoi(getenv("XVB_GEMM_BN")) : 0;  // tuning knobs
   // wide tiles cut the operand stream by 25-37 % but serialise the epilogue with the MMAs (one
   // accumulator in TMEM); measured slower end to end (profiles/r01_gemm_experiments.md), so opt-in.

@@ -345,6 +345,27 @@ def plda_matrix(enroll, test, l2, row, col):
     return s
 
 
+def trial_histogram(enroll, enroll_spk, test, test_spk, lo, hi, nbins=2048, row_term=None, col_term=None,
+                    symmetric=False, unit_first=0, unit_stride=1, out=None):
+    """(2, nbins) int64 histogram [nontarget | target] of enroll.test^T (+ terms) -- scores are never
+    stored.  `out` is accumulated into when given."""
+    enroll = _req(enroll, torch.float32, "enroll")
+    test = enroll if test is enroll else _req(test, torch.float32, "test")
+    enroll_spk = _req(enroll_spk, torch.int32, "enroll_spk")
+    test_spk = enroll_spk if test_spk is enroll_spk else _req(test_spk, torch.int32, "test_spk")
+    if enroll_spk.shape[0] != enroll.shape[0] or test_spk.shape[0] != test.shape[0] or enroll.shape[1] != test.shape[1]:
+        raise ValueError("trial_histogram: shape mismatch")
+    if out is None:
+        out = torch.zeros(2, nbins, dtype=torch.int64, device=enroll.device)
+    elif out.dtype != torch.int64 or tuple(out.shape) != (2, nbins) or not out.is_contiguous() or out.device != enroll.device:
+        raise ValueError("trial_histogram: out must be a contiguous (2, nbins) int64 tensor on the embeddings' device")
+    check(lib.xvb_trial_histogram(_ptr(enroll), enroll.shape[0], _ptr(enroll_spk), _ptr(test), test.shape[0],
+                                  _ptr(test_spk), enroll.shape[1], _ptr(row_term), _ptr(col_term), int(bool(symmetric)),
+                                  int(unit_first), int(unit_stride), float(lo), float(hi), int(nbins), _ptr(out),
+                                  _stream()), "xvb_trial_histogram")
+    return out
+
+
 # ------------------------------------------------------------------ whole-model extractor
 class Extractor:
     """Owner of a native xvb_extractor_t (packed weights + workspace on the current device)."""

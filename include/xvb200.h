@@ -265,6 +265,23 @@ int xvb_plda_terms(const float* x, int64_t rows, int D, const float* gamma, cons
 int xvb_plda_matrix(const float* enroll, int64_t Ne, const float* test, int64_t Nt, int D, const float* L2,
                     const float* row, const float* col, float* S, int64_t lds, void* stream);
 
+/* Fused consumer for score matrices too large to store (BASELINE configs 4/5: 10^12 cosine trials,
+ * 10^10 PLDA trials; SURVEY Appendix A "fused consumer"): every score
+ *   s(i,j) = <enroll[i], test[j]> + row_term[i] + col_term[j]        (terms may be NULL)
+ * is binned in the GEMM epilogue by trial class -- target when enroll_spk[i] == test_spk[j], the
+ * trials file's third column (score/score.sh:82-97, computeEER.sh:21-22) -- and only the counters
+ * leave the SM.  hist is (2, nbins) uint64 [nontarget | target] and is ACCUMULATED into (zero it
+ * first; several calls / shards / GPUs add up).  Bins: w = (hi-lo)/(nbins-2);
+ *   bin 0: s < lo;  bin k (1..nbins-2): lo+(k-1)w <= s < lo+kw;  bin nbins-1: s >= hi,
+ * evaluated in fp32 as 1 + floor((s - lo) * ((nbins-2)/(hi-lo))).  4 <= nbins <= 2048.
+ * symmetric != 0 (needs Ne == Nt, one set on both sides): only pairs j > i are counted, tiles
+ * below the diagonal are skipped.  Row sharding for multi-GPU: this call walks the 256-row units
+ * unit_first, unit_first + unit_stride, ... of enroll (rank r of W passes r, W). */
+int xvb_trial_histogram(const float* enroll, int64_t Ne, const int32_t* enroll_spk, const float* test, int64_t Nt,
+                        const int32_t* test_spk, int D, const float* row_term, const float* col_term, int symmetric,
+                        int unit_first, int unit_stride, float lo, float hi, int nbins, unsigned long long* hist,
+                        void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Whole-model extractor (x-vector TDNN family): owns packed weights + workspace on the current
  * device; replaces Xvector.extract_embedding (pytorch/model/xvector.py:77-98) for a whole batch

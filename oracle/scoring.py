@@ -206,3 +206,19 @@ def snorm_apply(scores, trial_e, trial_t, mean_e, std_e, mean_t, std_t):
     """normed = 0.5*((s-mu_e)/sd_e + (s-mu_t)/sd_t), ScoreNormalization.py:101-104 / :172-173."""
     s = np.asarray(scores, dtype=np.float64)
     return 0.5 * ((s - mean_e[trial_e]) / std_e[trial_e] + (s - mean_t[trial_t]) / std_t[trial_t])
+
+
+# ---------------------------------------------------------------- trial histogram (fused consumer)
+def trial_histogram(scores, is_target, lo, hi, nbins):
+    """Bin rule of include/xvb200.h xvb_trial_histogram, in the same fp32 arithmetic:
+    bin = 1 + floor((s - lo) * ((nbins-2)/(hi-lo))); below lo -> 0; at/above hi -> nbins-1.
+    Returns (2, nbins) int64 [nontarget | target]."""
+    s = np.asarray(scores, dtype=np.float32).reshape(-1)
+    t = np.asarray(is_target).reshape(-1).astype(bool)
+    inv_w = np.float32(np.float32(nbins - 2) / (np.float32(hi) - np.float32(lo)))
+    x = (s - np.float32(lo)) * inv_w
+    b = np.where(x < 0, 0, np.where(x < np.float32(nbins - 2), 1 + np.floor(np.maximum(x, 0)).astype(np.int64), nbins - 1))
+    out = np.zeros((2, nbins), dtype=np.int64)
+    np.add.at(out[0], b[~t], 1)
+    np.add.at(out[1], b[t], 1)
+    return out

@@ -1,10 +1,8 @@
 #!/bin/bash
-TAG=${1:-ab}
+# Scratch GPU visit: trial-histogram tests + scoring bench + bench sanity.
+TAG=${1:-r01s}
 mkdir -p gpurun_out
-run() { name=$1; shift; env "$@" timeout 300 python tools/layer_times.py > gpurun_out/${TAG}_$name.txt 2>&1; echo "$name: $(tail -1 gpurun_out/${TAG}_$name.txt)"; }
-run pdl1 XVB_PDL=1
-run pdl0 XVB_PDL=0
-for P in 1 0; do XVB_PDL=$P timeout 300 python bench.py --steps 20 --warmup 3 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('pdl=$P value %.4e e2e %.3e ms %.4f' % (d['value'], d['e2e']['value'], d['ms_per_step']))"; done
-timeout 900 python -m pytest tests -m gpu -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/${TAG}_pytest.log
+timeout 600 python -m pytest tests/test_trial_histogram.py -m gpu -x -q > gpurun_out/${TAG}_pytest_hist.log 2>&1; echo "pytest hist rc=$?"; tail -25 gpurun_out/${TAG}_pytest_hist.log
+timeout 600 python tools/bench_scoring.py > gpurun_out/${TAG}_scoring_bench.json 2> gpurun_out/${TAG}_scoring_bench.err; echo "scoring bench rc=$?"; cat gpurun_out/${TAG}_scoring_bench.json; tail -5 gpurun_out/${TAG}_scoring_bench.err
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest all rc=$?"; tail -5 gpurun_out/${TAG}_pytest_gpu.log
+timeout 300 python bench.py --steps 20 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; cat gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err

@@ -32,11 +32,19 @@ def main():
     full = ops.center_length_norm(full, ops.column_mean(full))
     rows = full[idx].contiguous()
     block = ops.cosine_matrix(rows, full)                   # (n/world, n) row block of the all-pairs matrix
+    # all-pairs EER without a score matrix: every rank bins its 256-row units, one all-reduce of counters
+    from asv_subtools_b200.score import trial_histogram as th
+    spk = torch.arange(n, device="cuda", dtype=torch.int32) % 50
+    res = th.zoom_eer(full, spk, passes=3, rank=rank, world=world)
     ok = True
+    if rank == 0:
+        one = th.zoom_eer(full, spk, passes=3, group=False)
+        ok = ok and one["eer"] == res["eer"] and int(res["hist"].sum()) == n * (n - 1) // 2
+        print("multi_gpu_demo: all-pairs EER sharded {:.6f} == single {:.6f}: {}".format(res["eer"], one["eer"], ok))
     if rank == 0:
         ref = m.extract_embedding_batch(feats)
         ref = ops.center_length_norm(ref, ops.column_mean(ref))
-        ok = bool(torch.equal(ref, full)) and bool(torch.allclose(ops.cosine_matrix(ref, ref)[idx], block, atol=1e-6))
+        ok = ok and bool(torch.equal(ref, full)) and bool(torch.allclose(ops.cosine_matrix(ref, ref)[idx], block, atol=1e-6))
         print("multi_gpu_demo: world={} n={} gathered==single-GPU: {} block {}".format(world, n, ok, tuple(block.shape)))
     dist.barrier()
     dist.destroy_process_group()
