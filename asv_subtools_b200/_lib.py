@@ -95,6 +95,14 @@ SIGNATURES = {
     "xvb_extractor_last_launches": (_i, [_p]),
     "xvb_extractor_debug_f32": (_p, [_p, _i]),
     "xvb_extractor_destroy": (None, [_p]),
+    "xvb_extractor_load": (_i, [C.POINTER(_p), C.c_char_p]),
+    "xvb_extractor_feat_dim": (_i, [C.c_char_p]),
+    "xvb_ark_reader_open": (_i, [C.POINTER(_p), C.c_char_p]),
+    "xvb_ark_reader_next": (_i, [_p, C.POINTER(C.c_char_p), _ip, _ip, C.POINTER(C.POINTER(C.c_float))]),
+    "xvb_ark_reader_close": (None, [_p]),
+    "xvb_ark_writer_open": (_i, [C.POINTER(_p), C.c_char_p]),
+    "xvb_ark_writer_put_vector": (_i, [_p, C.c_char_p, _p, _i]),
+    "xvb_ark_writer_close": (_i, [_p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

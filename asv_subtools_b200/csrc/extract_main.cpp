@@ -1,0 +1,201 @@
+// xvb-extract: Python-free x-vector extraction over the C ABI.
+//
+//   xvb-extract [--batch N] [--max-chunk N] [--cmn none|utt|sliding] [--cmn-window W] [--gpu-id ID]
+//               <model.xvbm> <feats-rspecifier> <vectors-wspecifier>
+//
+// Positionals follow the reference's extractor CLI (pytorch/pipeline/onestep/extract_embeddings.py
+// :17-45: <model-path> <feats-rspecifier> <vectors-wspecifier>); the role is that of the reference's
+// C++ runtime (runtime/bin/extractor_main.cc + runtime/extractor/torch_asv_extractor.cc:71-122: load
+// a model, optional per-utterance CMN, extract, emit the vector), with features instead of wav on
+// the input side.  What it adds: utterances of equal length are batched (the reference runs batch 1).
+//   * chunk rule of framework.py:34-47: T > max-chunk -> num_split = ceil(T/max), split = T/num_split,
+//     the last chunk takes the remainder, embedding = sum(len_i * emb_i) / T in fp32;
+//   * one "FV" vector per input key (order follows batch completion, which the wspecifier allows);
+//   * errors: message with "ERROR" on stderr, exit status 1 (the reference's shell greps for it,
+//     extract_xvectors_for_pytorch.sh:144-145).  No GPU / not a B200 -> error, there is no CPU path.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/xvb200.h"
+
+namespace {
+
+struct Item {          // one chunk of one utterance
+  int utt;
+  int frames;
+  std::vector<float> feats;   // (frames, F)
+};
+
+struct Utt {
+  std::string key;
+  int frames = 0;
+  int pending = 0;            // chunks not yet extracted
+  std::vector<float> acc;     // sum(len_i * emb_i)
+};
+
+[[noreturn]] void die(const char* what) {
+  const char* e = xvb_last_error();
+  fprintf(stderr, "ERROR: xvb-extract: %s%s%s\n", what, (e && e[0]) ? ": " : "", (e && e[0]) ? e : "");
+  exit(1);
+}
+
+#define CK(call, what) do { if ((call) != XVB_OK) die(what); } while (0)
+#define CU(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { fprintf(stderr, "ERROR: xvb-extract: %s: %s\n", #call, cudaGetErrorString(_e)); exit(1); } } while (0)
+
+struct Runner {
+  xvb_extractor_t* ex = nullptr;
+  xvb_ark_writer_t* out = nullptr;
+  int F = 0, D = 0, batch = 256, cmn = 0, cmn_window = 300;
+  float *d_feats = nullptr, *d_tmp = nullptr, *d_emb = nullptr, *h_feats = nullptr, *h_emb = nullptr;
+  int32_t* d_off = nullptr;
+  size_t cap_frames = 0;
+  std::vector<Utt> utts;
+  long done_utts = 0, done_frames = 0;
+
+  void reserve(size_t frames) {
+    if (frames <= cap_frames) return;
+    if (d_feats) { cudaFree(d_feats); cudaFree(d_tmp); cudaFreeHost(h_feats); }
+    cap_frames = frames + frames / 4;
+    CU(cudaMalloc(&d_feats, cap_frames * F * sizeof(float)));
+    CU(cudaMalloc(&d_tmp, cap_frames * F * sizeof(float)));
+    CU(cudaMallocHost(&h_feats, cap_frames * F * sizeof(float)));
+  }
+
+  // per-utterance / sliding CMN of whole utterances laid back to back on the device (frontend.cu)
+  void cmn_device(float* x, float* y, const std::vector<int32_t>& off) {
+    CU(cudaMemcpy(d_off, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CK(xvb_cmn(x, d_off, (int)off.size() - 1, F, cmn == 2 ? cmn_window : 0, y, nullptr), "xvb_cmn");
+  }
+
+  void run(std::vector<Item>& items) {
+    if (items.empty()) return;
+    const int B = (int)items.size(), T = items[0].frames;
+    reserve((size_t)B * T);
+    for (int i = 0; i < B; ++i) memcpy(h_feats + (size_t)i * T * F, items[i].feats.data(), (size_t)T * F * sizeof(float));
+    CU(cudaMemcpy(d_feats, h_feats, (size_t)B * T * F * sizeof(float), cudaMemcpyHostToDevice));
+    CK(xvb_extractor_extract(ex, d_feats, B, T, d_emb, nullptr), "xvb_extractor_extract");
+    CU(cudaMemcpy(h_emb, d_emb, (size_t)B * D * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < B; ++i) {
+      Utt& u = utts[items[i].utt];
+      const float len = (float)items[i].frames;
+      const float* e = h_emb + (size_t)i * D;
+      if (u.acc.empty()) u.acc.assign(D, 0.f);
+      for (int d = 0; d < D; ++d) u.acc[d] += len * e[d];
+      if (--u.pending == 0) {
+        const float total = (float)u.frames;
+        for (int d = 0; d < D; ++d) u.acc[d] /= total;
+        CK(xvb_ark_writer_put_vector(out, u.key.c_str(), u.acc.data(), D), "writing a vector");
+        std::vector<float>().swap(u.acc);
+        ++done_utts;
+        done_frames += u.frames;
+      }
+    }
+    items.clear();
+  }
+};
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  Runner r;
+  int max_chunk = 10000, gpu = 0;
+  std::vector<const char*> pos;
+  for (int i = 1; i < argc; ++i) {
+    const std::string a = argv[i];
+    auto val = [&](const char* name) -> const char* {
+      if (i + 1 >= argc) { fprintf(stderr, "ERROR: xvb-extract: %s needs a value\n", name); exit(1); }
+      return argv[++i];
+    };
+    if (a == "--batch") r.batch = atoi(val("--batch"));
+    else if (a == "--max-chunk") max_chunk = atoi(val("--max-chunk"));
+    else if (a == "--cmn-window") r.cmn_window = atoi(val("--cmn-window"));
+    else if (a == "--gpu-id") gpu = atoi(val("--gpu-id"));
+    else if (a == "--cmn") {
+      const std::string m = val("--cmn");
+      r.cmn = m == "none" ? 0 : m == "utt" ? 1 : m == "sliding" ? 2 : -1;
+      if (r.cmn < 0) { fprintf(stderr, "ERROR: xvb-extract: --cmn must be none, utt or sliding\n"); return 1; }
+    } else if (a == "--help" || a == "-h") {
+      printf("usage: xvb-extract [--batch N] [--max-chunk N] [--cmn none|utt|sliding] [--cmn-window W] [--gpu-id ID]\n"
+             "                   <model.xvbm> <feats-rspecifier> <vectors-wspecifier>\n");
+      return 0;
+    } else if (a.size() > 2 && a[0] == '-' && a[1] == '-') {
+      fprintf(stderr, "ERROR: xvb-extract: unknown option %s\n", a.c_str());
+      return 1;
+    } else pos.push_back(argv[i]);
+  }
+  if (pos.size() != 3 || r.batch < 1 || max_chunk < 1 || r.cmn_window < 1) {
+    fprintf(stderr, "ERROR: xvb-extract: expected <model.xvbm> <feats-rspecifier> <vectors-wspecifier> (see --help)\n");
+    return 1;
+  }
+  if (cudaSetDevice(gpu) != cudaSuccess) { fprintf(stderr, "ERROR: xvb-extract: no CUDA device %d visible (there is no CPU path)\n", gpu); return 1; }
+  CK(xvb_device_check(), "device check");
+  CK(xvb_extractor_load(&r.ex, pos[0]), "loading the model");
+  r.F = xvb_extractor_feat_dim(pos[0]);
+  r.D = xvb_extractor_embed_dim(r.ex);
+  xvb_ark_reader_t* in = nullptr;
+  CK(xvb_ark_reader_open(&in, pos[1]), "opening the feature rspecifier");
+  CK(xvb_ark_writer_open(&r.out, pos[2]), "opening the vector wspecifier");
+  CU(cudaMalloc(&r.d_emb, (size_t)r.batch * r.D * sizeof(float)));
+  CU(cudaMallocHost(&r.h_emb, (size_t)r.batch * r.D * sizeof(float)));
+  CU(cudaMalloc(&r.d_off, ((size_t)r.batch + 2) * sizeof(int32_t)));
+
+  std::map<int, std::vector<Item>> buckets;   // frames -> pending chunks of that length
+  size_t pending = 0;
+  const size_t max_pending = (size_t)r.batch * 64;
+  const char* key;
+  int rows, cols, rc;
+  const float* data;
+  std::vector<float> normed;
+  while ((rc = xvb_ark_reader_next(in, &key, &rows, &cols, &data)) == 1) {
+    printf("Process utterance for key %s\n", key);   // extract_embeddings.py:81
+    if (cols != r.F) { fprintf(stderr, "ERROR: xvb-extract: %s has %d-dim features, the model expects %d\n", key, cols, r.F); return 1; }
+    if (rows < 1) { fprintf(stderr, "ERROR: xvb-extract: %s has no frames\n", key); return 1; }
+    if (r.cmn) {   // whole utterance, before the chunk rule (the reference normalises upstream of the model)
+      r.reserve((size_t)rows);
+      CU(cudaMemcpy(r.d_feats, data, (size_t)rows * cols * sizeof(float), cudaMemcpyHostToDevice));
+      r.cmn_device(r.d_feats, r.d_tmp, {0, rows});
+      normed.resize((size_t)rows * cols);
+      CU(cudaMemcpy(normed.data(), r.d_tmp, normed.size() * sizeof(float), cudaMemcpyDeviceToHost));
+      data = normed.data();
+    }
+    Utt u;
+    u.key = key;
+    u.frames = rows;
+    const int num_split = (rows + max_chunk - 1) / max_chunk, split = rows / num_split;
+    u.pending = num_split;
+    const int ui = (int)r.utts.size();
+    r.utts.push_back(u);
+    for (int c = 0, off = 0; c < num_split; ++c) {
+      const int len = c + 1 < num_split ? split : rows - off;
+      Item it;
+      it.utt = ui;
+      it.frames = len;
+      it.feats.assign(data + (size_t)off * cols, data + (size_t)(off + len) * cols);
+      off += len;
+      std::vector<Item>& b = buckets[len];
+      b.push_back(std::move(it));
+      ++pending;
+      if ((int)b.size() == r.batch) { pending -= b.size(); r.run(b); }
+    }
+    if (pending > max_pending) {   // bound host memory: flush the fullest bucket
+      auto best = buckets.begin();
+      for (auto it = buckets.begin(); it != buckets.end(); ++it)
+        if (it->second.size() > best->second.size()) best = it;
+      pending -= best->second.size();
+      r.run(best->second);
+    }
+  }
+  if (rc < 0) die("reading features");
+  for (auto& kv : buckets) r.run(kv.second);
+  xvb_ark_reader_close(in);
+  CK(xvb_ark_writer_close(r.out), "closing the vector wspecifier");
+  xvb_extractor_destroy(r.ex);
+  fprintf(stderr, "xvb-extract: %ld utterances, %ld frames\n", r.done_utts, r.done_frames);
+  return 0;
+}

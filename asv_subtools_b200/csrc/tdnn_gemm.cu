@@ -73,6 +73,7 @@ struct TdnnGemmParams {
   float hist_lo, hist_inv_w;  // bin = 1 + floor((s - lo) * inv_w); bin 0: s < lo; bin nbins-1: at or above hi
   int hist_bins;
   int hist_sym;               // count only column index > row index (all pairs of one set, each once)
+  int hist_group, num_units;  // tile raster of the score-matrix mode (decode_tile)
   __nv_bfloat16* y_hi;
   __nv_bfloat16* y_lo;
   long long ldy;
@@ -109,6 +110,27 @@ struct GemmCfg {
 // TMEM columns) -- so an epilogue thread owns ONE channel and sees the tile's frames as consecutive
 // accumulator columns: pooling over time becomes a running (Welford) update in registers, with no
 // shuffles, no shared memory and no (B,T,C) output at all.
+// Tile index -> (M unit, N block).  Layers: N fastest, so the CTAs running together share the frame
+// (A) tile and walk the small, L2-resident weight matrix.  Score matrices (kHist): both operands are
+// huge, so tiles are rastered in bands of `hist_group` M units x all N blocks, M fastest -- the ~74
+// pairs in flight cover hist_group rows x ~9 columns and each test (B) tile leaves HBM once per band
+// instead of once per M unit.  Returns false for tiles that do not exist / lie below the diagonal.
+template <bool kHist>
+__device__ __forceinline__ bool decode_tile(const TdnnGemmParams& p, int tile, int& m_unit, int& n_blk) {
+  if constexpr (!kHist) {
+    m_unit = p.unit_first + (tile / p.num_n_blk) * p.unit_stride;
+    n_blk = tile % p.num_n_blk;
+    return true;
+  } else {
+    const int per_band = p.num_n_blk * p.hist_group;
+    const int band = tile / per_band, r = tile - band * per_band;
+    n_blk = r / p.hist_group;
+    const int mi = band * p.hist_group + (r - n_blk * p.hist_group);
+    m_unit = p.unit_first + mi * p.unit_stride;
+    return mi < p.num_units && !(p.hist_sym && n_blk < m_unit);
+  }
+}
+
 // kHist: the epilogue bins the scores into a trial histogram instead of storing them (scoring.cu).
 template <int BLOCK_N, int kCta, int kNSub, bool kPool, bool kHist>
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -174,8 +196,8 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile_first; tile < p.num_tiles; tile += tile_step) {
-        const int m_unit = p.unit_first + (tile / p.num_n_blk) * p.unit_stride, n_blk = tile % p.num_n_blk;
-        if (kHist && p.hist_sym && n_blk < m_unit) continue;   // tile entirely on or below the diagonal (unit rows == kTileN)
+        int m_unit, n_blk;
+        if (!decode_tile<kHist>(p, tile, m_unit, n_blk)) continue;   // e.g. entirely on or below the diagonal
         const int m_blk = m_unit * kCta + (int)cta_rank;
         const int b0 = (m_blk / p.num_t_blk) * p.Bb, t0 = (m_blk % p.num_t_blk) * p.Tb;  // may be fully out of
         const int n0 = n_blk * kTileN + (int)cta_rank * Cfg::kBRows;                      // range: TMA zero-fills
@@ -225,7 +247,7 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
       uint32_t phase = 0;
       uint32_t it = 0;
       for (int tile = tile_first; tile < p.num_tiles; tile += tile_step) {
-        if (kHist && p.hist_sym && tile % p.num_n_blk < p.unit_first + (tile / p.num_n_blk) * p.unit_stride) continue;
+        if constexpr (kHist) { int mu, nb; if (!decode_tile<true>(p, tile, mu, nb)) continue; }
         const uint32_t acc = kAccStages == 2 ? (it & 1) : 0, acc_phase = kAccStages == 2 ? ((it >> 1) & 1) : (it & 1);
         ++it;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
@@ -316,8 +338,8 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
       asm volatile("bar.sync 3, 256;" ::: "memory");
     }
     for (int tile = tile_first; tile < p.num_tiles; tile += tile_step) {
-      const int m_unit = p.unit_first + (tile / p.num_n_blk) * p.unit_stride, n_blk = tile % p.num_n_blk;
-      if (kHist && p.hist_sym && n_blk < m_unit) continue;
+      int m_unit, n_blk;
+      if (!decode_tile<kHist>(p, tile, m_unit, n_blk)) continue;
       const uint32_t acc = kAccStages == 2 ? (it & 1) : 0, acc_phase = kAccStages == 2 ? ((it >> 1) & 1) : (it & 1);
       ++it;
       const int m_blk = m_unit * kCta + (int)cta_rank;
@@ -735,8 +757,12 @@ static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const
   const int all_m_units = (p.num_t_blk * p.num_b_blk + kCta - 1) / kCta;  // 128-row blocks, or pairs of them
   if (p.unit_first >= all_m_units) return XVB_OK;                         // this shard owns no rows
   const int num_m_units = (all_m_units - p.unit_first + p.unit_stride - 1) / p.unit_stride;
-  XVB_CHECK_ARG((long long)num_m_units * p.num_n_blk < (1ll << 31), "xvb_tdnn_affine: %d x %d tiles exceed one launch", num_m_units, p.num_n_blk);
-  p.num_tiles = num_m_units * p.num_n_blk;
+  p.num_units = num_m_units;
+  p.hist_group = 8;
+  const long long tiles = kHist ? (long long)((num_m_units + p.hist_group - 1) / p.hist_group) * p.hist_group * p.num_n_blk
+                                : (long long)num_m_units * p.num_n_blk;
+  XVB_CHECK_ARG(tiles < (1ll << 31), "xvb_tdnn_affine: %d x %d tiles exceed one launch", num_m_units, p.num_n_blk);
+  p.num_tiles = (int)tiles;
   static bool attr_set = false;
   if (!attr_set) {
     XVB_CUDA(cudaFuncSetAttribute(tdnn_gemm_bf16x3_kernel<BLOCK_N, kCta, kNSub, kPool, kHist>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -297,3 +297,57 @@ def write_vec_ark_scp(ark_path, scp_path, items):
             ark.write((key + " ").encode("latin1"))
             scp.write("{} {}:{}\n".format(key, os.path.abspath(ark_path), ark.tell()))
             write_vec_flt(ark, np.asarray(vec), key="")
+
+
+# ------------------------------------------------------------------ native reader / writer
+def read_mat_ark_native(rspecifier):
+    """Same stream of (key, float32 matrix) as read_mat_ark / read_mat_scp, decoded by the C library
+    (csrc/ark_io.cpp: whole-matrix freads instead of the reference's byte-at-a-time key loop,
+    kaldi_io.py:148-163).  DM matrices arrive converted to float32."""
+    import ctypes as C
+    from ._lib import lib, last_error
+    h = C.c_void_p()
+    if lib.xvb_ark_reader_open(C.byref(h), rspecifier.encode()) != 0:
+        raise KaldiFormatError(last_error())
+    try:
+        key, rows, cols, data = C.c_char_p(), C.c_int(), C.c_int(), C.POINTER(C.c_float)()
+        while True:
+            rc = lib.xvb_ark_reader_next(h, C.byref(key), C.byref(rows), C.byref(cols), C.byref(data))
+            if rc == 0:
+                return
+            if rc < 0:
+                raise KaldiFormatError(last_error())
+            n = rows.value * cols.value
+            m = np.ctypeslib.as_array(data, shape=(n,)).copy().reshape(rows.value, cols.value) if n else \
+                np.zeros((rows.value, cols.value), dtype=np.float32)
+            yield key.value.decode("latin1"), m
+    finally:
+        lib.xvb_ark_reader_close(h)
+
+
+class NativeVectorWriter:
+    """write_vec_flt through the C library: 'ark:f', 'ark,t:f', 'ark,scp:f.ark,f.scp', 'ark:| cmd'."""
+
+    def __init__(self, wspecifier):
+        import ctypes as C
+        from ._lib import lib, last_error
+        self._lib, self._err, self._h = lib, last_error, C.c_void_p()
+        if lib.xvb_ark_writer_open(C.byref(self._h), wspecifier.encode()) != 0:
+            raise KaldiFormatError(last_error())
+
+    def write(self, key, vec):
+        v = np.ascontiguousarray(vec, dtype=np.float32).reshape(-1)
+        if self._lib.xvb_ark_writer_put_vector(self._h, key.encode("latin1"), v.ctypes.data, v.shape[0]) != 0:
+            raise KaldiFormatError(self._err())
+
+    def close(self):
+        if self._h:
+            h, self._h = self._h, None
+            if self._lib.xvb_ark_writer_close(h) != 0:
+                raise KaldiFormatError(self._err())
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

@@ -80,18 +80,32 @@ def _reduce(hist, group):
 
 
 def zoom_eer(enroll, enroll_spk, test=None, test_spk=None, lo=-1.0, hi=1.0, nbins=2048, passes=2, row_term=None,
-             col_term=None, rank=0, world=1, group=None, _histogram=None):
+             col_term=None, rank=0, world=1, group=None, pilot=0, pilot_margin=8, _histogram=None):
     """EER of all enroll x test trials (test=None: all unordered pairs of `enroll`, each counted once).
 
     Every pass is one fused GEMM+histogram sweep over this rank's 256-row units (rank, rank+world, ...)
     followed by an all-reduce of the counters; pass k+1 narrows [lo, hi) to the crossing bracket of
     pass k (one bin of margin either side).  Returns dict(eer, threshold, hist, lo, hi, passes) where
-    hist/lo/hi describe the last pass."""
+    hist/lo/hi describe the last pass.
+
+    pilot = P > 0 runs a cheap locating pass first on every P-th row unit only (the shared-memory
+    counters are the bottleneck of a wide window, where every score lands in a bin; in a narrow window
+    almost all scores are counted in registers): its crossing bracket, widened by `pilot_margin` bins
+    either side, becomes the window of the first full pass.  A full pass whose crossing falls outside
+    its window raises (ValueError from eer_from_histogram) -- rerun without the pilot."""
     histogram = _histogram or ops.trial_histogram
     symmetric = test is None
     if symmetric:
         test, test_spk = enroll, enroll_spk
     result = None
+    if pilot and pilot > 1:
+        h = histogram(enroll, enroll_spk, test, test_spk, lo, hi, nbins, row_term=row_term, col_term=col_term,
+                      symmetric=symmetric, unit_first=rank * pilot, unit_stride=world * pilot)
+        h = _reduce(h, group)
+        hist = h.cpu().numpy() if isinstance(h, torch.Tensor) else np.asarray(h)
+        _, _, (b0, b1) = eer_from_histogram(hist, lo, hi)
+        w = (hi - lo) / (nbins - 2)
+        lo, hi = max(b0, lo) - pilot_margin * w, min(b1, hi) + pilot_margin * w
     for k in range(passes):
         h = histogram(enroll, enroll_spk, test, test_spk, lo, hi, nbins, row_term=row_term, col_term=col_term,
                       symmetric=symmetric, unit_first=rank, unit_stride=world)
@@ -100,8 +114,14 @@ def zoom_eer(enroll, enroll_spk, test=None, test_spk=None, lo=-1.0, hi=1.0, nbin
         eer, thr, (b0, b1) = eer_from_histogram(hist, lo, hi)
         result = dict(eer=eer, threshold=thr, hist=hist, lo=lo, hi=hi, passes=k + 1)
         w = (hi - lo) / (nbins - 2)
+        min_w = 6e-8 * max(abs(lo), abs(hi), 1e-3)        # about one fp32 ulp of the scores: no finer bins
+        if w <= 1.01 * min_w:
+            break
         nlo, nhi = max(b0, lo) - w, min(b1, hi) + w
-        if not (nhi - nlo < hi - lo) or (nhi - nlo) / (nbins - 2) < 1e-7 * max(abs(nlo), abs(nhi), 1e-3):
-            break   # cannot narrow further: the next window would be below fp32 score resolution
+        if (nhi - nlo) / (nbins - 2) < min_w:
+            c, half = 0.5 * (nlo + nhi), 0.5 * min_w * (nbins - 2)
+            nlo, nhi = c - half, c + half
+        if not (nhi - nlo < hi - lo):
+            break
         lo, hi = nlo, nhi
     return result

@@ -329,6 +329,34 @@ int xvb_extractor_last_launches(const xvb_extractor_t* h);
 const float* xvb_extractor_debug_f32(const xvb_extractor_t* h, int which);
 void xvb_extractor_destroy(xvb_extractor_t* h);
 
+/* Load a finalized extractor from an .xvbm model file (written by asv_subtools_b200.ops.Extractor.save:
+ * the layers exactly as the reference's state_dict stores them, eval BatchNorm folded) -- what
+ * torch::jit::load does for the reference's runtime (runtime/extractor/torch_asv_model.cc:8-17). */
+int xvb_extractor_load(xvb_extractor_t** out, const char* path);
+/* Feature dimension recorded in an .xvbm file (> 0), or a negative XVB_E* code.  Host only. */
+int xvb_extractor_feat_dim(const char* path);
+
+/* ---------------------------------------------------------------------------------------------
+ * Kaldi ark/scp I/O on the host (no GPU needed): the byte formats of the reference's
+ * pytorch/libs/support/kaldi_io.py -- read_key :148-163, _read_mat_binary :495-525 (FM/DM),
+ * _read_compressed_mat :527-569 (CM), ascii matrices :478-493, write_vec_flt :367-399 (FV),
+ * open_or_fd :43-73 (files, "-", "cmd |", "| cmd", "file:offset").
+ * rspecifier: "ark:<src>" | "scp:<list>" | "<src>";  wspecifier: "ark:<dst>" | "ark,t:<dst>" |
+ * "ark,scp:<ark file>,<scp file>".
+ * ------------------------------------------------------------------------------------------- */
+typedef struct xvb_ark_reader xvb_ark_reader_t;
+typedef struct xvb_ark_writer xvb_ark_writer_t;
+int xvb_ark_reader_open(xvb_ark_reader_t** out, const char* rspecifier);
+/* Next matrix as fp32 row-major (DM is converted, CM decoded with the reference's fp32 steps).
+ * Returns 1 and fills the outputs (owned by the reader, valid until the next call), 0 at the end
+ * of the stream, a negative XVB_E* code on malformed input. */
+int xvb_ark_reader_next(xvb_ark_reader_t* r, const char** key, int* rows, int* cols, const float** data);
+void xvb_ark_reader_close(xvb_ark_reader_t* r);
+int xvb_ark_writer_open(xvb_ark_writer_t** out, const char* wspecifier);
+int xvb_ark_writer_put_vector(xvb_ark_writer_t* w, const char* key, const float* v, int dim);
+/* Flushes and closes; fails if the stream or the pipe command failed. */
+int xvb_ark_writer_close(xvb_ark_writer_t* w);
+
 #ifdef __cplusplus
 }
 #endif

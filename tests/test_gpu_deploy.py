@@ -1,0 +1,92 @@
+"""Python-free deployment path: .xvbm model files, xvb_extractor_load, and the
+`bin/xvb-extract` binary (native ark reader -> batched extraction -> FV ark/scp writer)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from asv_subtools_b200 import kaldi_io, ops
+from oracle import frontend as ofe
+from oracle import nnet as onn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "asv_subtools_b200", "bin", "xvb-extract")
+
+
+def rel(a, b):
+    return float(np.max(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64))) / max(np.max(np.abs(b)), 1e-30))
+
+
+def test_binary_is_built_and_fails_loudly_without_arguments():
+    assert os.path.exists(BIN), "make in asv_subtools_b200/csrc builds bin/xvb-extract"
+    out = subprocess.run([BIN, "--help"], capture_output=True, text=True)
+    assert out.returncode == 0 and "feats-rspecifier" in out.stdout
+    out = subprocess.run([BIN, "only-one"], capture_output=True, text=True)
+    assert out.returncode == 1 and "ERROR" in out.stderr
+
+
+def _model(dim, seed, pos):
+    from asv_subtools_b200.model.xvector import Xvector
+    sd = onn.make_state_dict(onn.xvector_spec(dim), seed)
+    m = Xvector(dim, 10, training=False, extracted_embedding=pos)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda().eval(), sd
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pos", ["far", "near"])
+def test_model_file_roundtrip_is_bit_exact(tmp_path, pos):
+    m, _ = _model(23, 101, pos)
+    path = str(tmp_path / "xv.xvbm")
+    m.extractor().save(path)
+    ex = ops.Extractor.load(path)
+    assert ex.feat_dim == 23 and ex.embed_dim == 512
+    x = torch.from_numpy(onn.synthetic_feats(6, 120, 23, 5)).cuda()
+    assert torch.equal(ex.extract(x), m.extractor().extract(x))
+    with open(path, "r+b") as f:
+        f.truncate(os.path.getsize(path) - 100)
+    with pytest.raises(RuntimeError):
+        ops.Extractor.load(path)
+    with pytest.raises(RuntimeError):
+        ops.Extractor.load(str(tmp_path / "missing.xvbm"))
+
+
+@pytest.mark.gpu
+def test_xvb_extract_binary_matches_oracle_and_plugin(tmp_path):
+    m, sd = _model(80, 102, "far")
+    model = str(tmp_path / "xv80.xvbm")
+    m.extractor().save(model)
+    lengths = [200, 200, 57, 200, 450, 57, 1, 333]           # 450 and 333 exceed --max-chunk 200: 3 and 2 chunks
+    feats = {"utt{:02d}".format(i): onn.synthetic_feats(1, t, 80, 900 + i)[0] for i, t in enumerate(lengths)}
+    ark = str(tmp_path / "feats.ark")
+    with open(ark, "wb") as f:
+        for k, v in feats.items():
+            kaldi_io.write_mat(f, v, key=k)
+    out_ark, out_scp = str(tmp_path / "xv.ark"), str(tmp_path / "xv.scp")
+    run = subprocess.run([BIN, "--batch", "3", "--max-chunk", "200", model, "ark:" + ark,
+                          "ark,scp:{},{}".format(out_ark, out_scp)], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert run.stdout.count("Process utterance for key") == len(lengths)
+    got = dict(kaldi_io.read_vec_flt_ark(out_ark))
+    assert sorted(got) == sorted(feats) and sorted(dict(kaldi_io.read_vectors("scp:" + out_scp))) == sorted(feats)
+    fwd = lambda x: onn.xvector_forward(sd, x, "far")
+    for k, v in feats.items():
+        want = onn.extract_embedding(fwd, v, max_chunk=200).numpy()
+        assert got[k].shape == (512,) and rel(got[k], want) < 1e-4, k      # north-star tolerance vs the oracle
+        if v.shape[0] <= 200:                                               # same kernels as the plugin call
+            assert rel(got[k], m.extract_embedding(v).numpy()) < 1e-5, k
+    # per-utterance CMN inside the binary == oracle CMN upstream of the model (torch_asv_extractor.cc:99-101)
+    run = subprocess.run([BIN, "--cmn", "utt", model, ark, "ark:" + out_ark], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stderr
+    got = dict(kaldi_io.read_vec_flt_ark(out_ark))
+    for k in ("utt00", "utt02", "utt07"):
+        want = onn.extract_embedding(fwd, ofe.cmn_utterance(feats[k])).numpy()
+        assert rel(got[k], want) < 1e-4, k
+    # wrong feature dimension: message with ERROR, exit 1 (extract_xvectors_for_pytorch.sh:144-145 greps for it)
+    bad = str(tmp_path / "bad.ark")
+    with open(bad, "wb") as f:
+        kaldi_io.write_mat(f, np.zeros((10, 23), np.float32), key="b")
+    run = subprocess.run([BIN, model, bad, "ark:" + out_ark], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 1 and "ERROR" in run.stderr

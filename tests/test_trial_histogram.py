@@ -77,6 +77,8 @@ def test_zoom_converges_to_exact_eer():
     assert r1["hist"].sum() == iu[0].size
     assert abs(r1["eer"] - e_exact) < 5e-3
     assert abs(r4["eer"] - e_exact) < 1e-9 and abs(r4["threshold"] - thr_exact) < 1e-6, (r4["eer"], e_exact)
+    rp = th.zoom_eer(emb, spk, passes=3, pilot=2, group=False, _histogram=oracle_histogram)   # locating pass on half the rows
+    assert abs(rp["eer"] - e_exact) < 1e-9 and rp["hist"].sum() == iu[0].size
     assert r4["hi"] - r4["lo"] < 1e-2 and r4["hist"].sum() == iu[0].size   # out-of-window counts stay exact
     # enroll x test form
     r = th.zoom_eer(emb[:200], spk[:200], emb[200:], spk[200:], passes=4, group=False, _histogram=oracle_histogram)
@@ -117,10 +119,11 @@ def _cuda(*arrs):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n,dim", [(1000, 64), (2304, 512), (300, 192)])
+@pytest.mark.parametrize("n,dim", [(1000, 64), (2304, 512), (300, 192), (4700, 128)])
 def test_gpu_symmetric_histogram_matches_own_matrix_and_oracle(n, dim):
     from asv_subtools_b200 import ops
-    emb, spk = _speakers(n // 10, 10, dim, 21)
+    emb, spk = _speakers(n // 9, 9, dim, 21)
+    n = emb.shape[0]
     e, s = _cuda(emb, spk)
     for lo, hi, nbins in ((-1.0, 1.0, 2048), (0.05, 0.25, 512), (-0.01, 0.01, 4)):
         h = ops.trial_histogram(e, s, e, s, lo, hi, nbins, symmetric=True).cpu().numpy()
