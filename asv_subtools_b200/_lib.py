@@ -95,6 +95,12 @@ SIGNATURES = {
     "xvb_extractor_last_launches": (_i, [_p]),
     "xvb_extractor_debug_f32": (_p, [_p, _i]),
     "xvb_extractor_destroy": (None, [_p]),
+    "xvb_fbank_default_opts": (None, [_p]),
+    "xvb_fbank_create": (_i, [C.POINTER(_p), _p]),
+    "xvb_fbank_dim": (_i, [_p]),
+    "xvb_fbank_num_frames": (_i64, [_p, _i64]),
+    "xvb_fbank_compute": (_i, [_p, _p, _p, _p, _i, _i64, _p, _p]),
+    "xvb_fbank_destroy": (None, [_p]),
     "xvb_extractor_load": (_i, [C.POINTER(_p), C.c_char_p]),
     "xvb_extractor_feat_dim": (_i, [C.c_char_p]),
     "xvb_ark_reader_open": (_i, [C.POINTER(_p), C.c_char_p]),
@@ -109,6 +115,14 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)  # AttributeError here == the .so does not export what the header declares
     _fn.restype = _res
     _fn.argtypes = _args
+
+
+class FbankOpts(C.Structure):
+    """xvb_fbank_opts_t"""
+    _fields_ = [(n, C.c_float) for n in ("sample_frequency", "frame_length_ms", "frame_shift_ms", "preemphasis_coefficient",
+                                         "low_freq", "high_freq", "energy_floor", "cepstral_lifter", "blackman_coeff")] + \
+               [(n, C.c_int) for n in ("num_mel_bins", "num_ceps", "use_energy", "raw_energy", "remove_dc_offset",
+                                       "use_log_fbank", "use_power", "htk_compat", "window_type")]
 
 
 def last_error():

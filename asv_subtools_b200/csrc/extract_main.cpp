@@ -145,6 +145,8 @@ int main(int argc, char** argv) {
   CU(cudaMallocHost(&r.h_emb, (size_t)r.batch * r.D * sizeof(float)));
   CU(cudaMalloc(&r.d_off, ((size_t)r.batch + 2) * sizeof(int32_t)));
 
+  const std::string wspec = pos[2];
+  const bool to_stdout = wspec == "-" || (wspec.size() >= 2 && wspec.compare(wspec.size() - 2, 2, ":-") == 0);   // keep the ark stream clean
   std::map<int, std::vector<Item>> buckets;   // frames -> pending chunks of that length
   size_t pending = 0;
   const size_t max_pending = (size_t)r.batch * 64;
@@ -153,7 +155,7 @@ int main(int argc, char** argv) {
   const float* data;
   std::vector<float> normed;
   while ((rc = xvb_ark_reader_next(in, &key, &rows, &cols, &data)) == 1) {
-    printf("Process utterance for key %s\n", key);   // extract_embeddings.py:81
+    fprintf(to_stdout ? stderr : stdout, "Process utterance for key %s\n", key);   // extract_embeddings.py:81
     if (cols != r.F) { fprintf(stderr, "ERROR: xvb-extract: %s has %d-dim features, the model expects %d\n", key, cols, r.F); return 1; }
     if (rows < 1) { fprintf(stderr, "ERROR: xvb-extract: %s has no frames\n", key); return 1; }
     if (r.cmn) {   // whole utterance, before the chunk rule (the reference normalises upstream of the model)

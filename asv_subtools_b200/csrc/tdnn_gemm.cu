@@ -567,9 +567,14 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
         }
       };
 
-      // trial histogram: score -> bin -> shared-memory counter of its class (same / different speaker)
+      // trial histogram: score -> bin -> shared-memory counter of its class (same / different speaker).
+      // Branch-free counting of the out-of-window scores (the vast majority in a zoomed pass); the
+      // per-score validity test is only compiled in for ragged / diagonal tiles.
       const int lab_r = (hist && valid) ? __ldg(p.row_label + b) : -1;
-      auto process_hist = [&](uint32_t (&v)[16], int ch) {
+      const bool plain_tile = n0 + kTileN <= p.Cout && !(p.hist_sym && n_blk == m_unit);
+      const uint32_t row_ok = valid ? 1u : 0u;
+      auto process_hist = [&](uint32_t (&v)[16], int ch, auto plain_tag) {
+        constexpr bool kPlain = decltype(plain_tag)::value;
         const int pc = ch * 32 + half * 16;
         const float top = (float)(p.hist_bins - 2);
 #pragma unroll
@@ -580,18 +585,26 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
           const int cl[4] = {__float_as_int(ll.x), __float_as_int(ll.y), __float_as_int(ll.z), __float_as_int(ll.w)};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const int col = n0 + pc + 4 * g + k;
-            const bool ok = valid && cl[k] != -2 && (!p.hist_sym || col > b);
+            uint32_t ok = row_ok;
+            if constexpr (!kPlain) {
+              const int col = n0 + pc + 4 * g + k;
+              ok = (valid && cl[k] != -2 && (!p.hist_sym || col > b)) ? 1u : 0u;
+            }
             const float sc = __uint_as_float(v[4 * g + k]) + cb[k] + rbias;
             const float x = (sc - p.hist_lo) * p.hist_inv_w;
             const uint32_t cls = cl[k] == lab_r ? 1u : 0u;
-            if (ok) {
-              if (x < 0.f) { h_below[0] += 1u - cls; h_below[1] += cls; }
-              else if (!(x < top)) { h_above[0] += 1u - cls; h_above[1] += cls; }
-              else asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hslab + ((int)cls * p.hist_bins + 1 + (int)x) * 4), "r"(1u) : "memory");
-            }
+            const uint32_t bl = x < 0.f ? ok : 0u;
+            const uint32_t ab = !(x < top) ? ok : 0u;          // also catches NaN
+            h_below[0] += bl & (cls ^ 1u); h_below[1] += bl & cls;
+            h_above[0] += ab & (cls ^ 1u); h_above[1] += ab & cls;
+            if (ok & ~(bl | ab))
+              asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hslab + ((int)cls * p.hist_bins + 1 + (int)x) * 4), "r"(1u) : "memory");
           }
         }
+      };
+      auto process_hist_any = [&](uint32_t (&v)[16], int ch) {
+        if (plain_tile) process_hist(v, ch, std::true_type{});
+        else process_hist(v, ch, std::false_type{});
       };
 
       uint32_t va[16], vb[16];
@@ -601,11 +614,11 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
       while (ch < nch) {
         tmem_ld_wait();
         if (ch + 1 < nch && !XVB_DBG(p, 8)) tmem_ld_32x16(trow + (ch + 1) * 32, vb);
-        if constexpr (hist) process_hist(va, ch); else process(va, ch);
+        if constexpr (hist) process_hist_any(va, ch); else process(va, ch);
         if (++ch >= nch) break;
         tmem_ld_wait();
         if (ch + 1 < nch && !XVB_DBG(p, 8)) tmem_ld_32x16(trow + (ch + 1) * 32, va);
-        if constexpr (hist) process_hist(vb, ch); else process(vb, ch);
+        if constexpr (hist) process_hist_any(vb, ch); else process(vb, ch);
         ++ch;
       }
       tcgen05_fence_before();

@@ -56,3 +56,91 @@ def select_frames(x, offsets, voiced, counts):
         check(lib.xvb_select_frames(x.data_ptr(), offsets.data_ptr(), voiced.data_ptr(), new_off.data_ptr(),
                                     offsets.shape[0] - 1, x.shape[1], y.data_ptr(), _s()), "xvb_select_frames")
     return y, new_off
+
+
+# ------------------------------------------------------------------ waveform -> fbank / MFCC
+_WINDOWS = {"povey": 0, "hamming": 1, "hanning": 2, "rectangular": 3, "blackman": 4}
+_UNSUPPORTED = {"dither": 0.0, "snip_edges": True, "round_to_power_of_two": True, "vtln_warp": 1.0, "subtract_mean": False,
+                "min_duration": 0.0, "channel": -1}
+
+
+class KaldiFeature:
+    """Mirror of the reference's `KaldiFeature` (pytorch/libs/egs/kaldi_features.py:69-135): same constructor
+    (`feature_type` in {'fbank','mfcc'}, `kaldi_featset` with torchaudio.compliance.kaldi keyword names,
+    `mean_var_conf`), same call (`waveforms [batch, time]` (+ relative `lengths`) or a list of 1-D
+    waveforms) -> list of (frames, dim) feature tensors -- computed by xvb_fbank_compute on the GPU for the
+    whole ragged batch in one launch, mean normalisation by xvb_cmn.  Options torchaudio applies randomly
+    or that the extraction recipes never set (dither != 0, snip_edges=False, VTLN) raise."""
+
+    def __init__(self, feature_type="mfcc", kaldi_featset={}, mean_var_conf={}):
+        from ._lib import FbankOpts
+        assert feature_type in ("mfcc", "fbank")
+        self.feat_type = feature_type
+        self.kaldi_featset = dict(kaldi_featset)
+        o = FbankOpts()
+        lib.xvb_fbank_default_opts(C.byref(o))
+        if feature_type == "mfcc":
+            o.num_ceps = 13
+        for k, v in self.kaldi_featset.items():
+            if k in _UNSUPPORTED:
+                if v != _UNSUPPORTED[k]:
+                    raise NotImplementedError("KaldiFeature: {}={!r} is not supported on the GPU path".format(k, v))
+            elif k == "window_type":
+                o.window_type = _WINDOWS[v]
+            elif k in ("frame_length", "frame_shift"):
+                setattr(o, k + "_ms", float(v))
+            elif k in ("vtln_high", "vtln_low"):
+                pass
+            elif hasattr(o, k):
+                setattr(o, k, type(getattr(o, k))(v))
+            else:
+                raise TypeError("KaldiFeature: unknown option {}".format(k))
+        if feature_type == "fbank":
+            o.num_ceps = 0
+        self.mean_norm = bool(mean_var_conf.get("mean_norm", True)) if mean_var_conf else False
+        if mean_var_conf and mean_var_conf.get("std_norm", False):
+            raise NotImplementedError("KaldiFeature: std_norm is not supported on the GPU path (the recipes use mean_norm only)")
+        self._opts = o
+        self._h = C.c_void_p()
+        check(lib.xvb_fbank_create(C.byref(self._h), C.byref(o)), "xvb_fbank_create")
+        self.dim = lib.xvb_fbank_dim(self._h)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib.xvb_fbank_destroy(h)
+
+    def num_frames(self, num_samples):
+        return int(lib.xvb_fbank_num_frames(self._h, int(num_samples)))
+
+    def compute(self, waves, device="cuda"):
+        """list of 1-D float32 waveforms -> ((sum_frames, dim) CUDA tensor, (U+1) int32 CUDA frame offsets)."""
+        waves = [w.detach().cpu().numpy() if isinstance(w, torch.Tensor) else np.asarray(w) for w in waves]
+        lens = np.array([w.shape[0] for w in waves], dtype=np.int64)
+        soff = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        frames = np.array([self.num_frames(n) for n in lens], dtype=np.int64)
+        foff = np.concatenate([[0], np.cumsum(frames)]).astype(np.int32)
+        x = torch.from_numpy(np.ascontiguousarray(np.concatenate(waves), dtype=np.float32)).to(device)
+        so, fo = torch.from_numpy(soff).to(device), torch.from_numpy(foff).to(device)
+        total = int(foff[-1])
+        feats = torch.empty(total, self.dim, dtype=torch.float32, device=device)
+        check(lib.xvb_fbank_compute(self._h, x.data_ptr(), so.data_ptr(), fo.data_ptr(), len(waves), total, feats.data_ptr(),
+                                    _s()), "xvb_fbank_compute")
+        if self.mean_norm and total:
+            feats = cmn(feats, fo, 0)
+        return feats, fo
+
+    def __call__(self, waveforms, lengths=None):
+        if isinstance(waveforms, torch.Tensor) and waveforms.dim() >= 2:
+            if torch.any(torch.isnan(waveforms)):
+                raise ValueError("feats:{}".format(waveforms))
+            ws = []
+            for i, w in enumerate(waveforms):
+                w = w if w.dim() == 1 else w.transpose(0, 1)[0]     # [time, channel] -> channel 0
+                if lengths is not None:
+                    w = w[: int((lengths[i] * waveforms.shape[1]).long())]
+                ws.append(w)
+        else:
+            ws = list(waveforms)
+        feats, fo = self.compute(ws)
+        return unpack(feats, fo)

@@ -329,6 +329,37 @@ int xvb_extractor_last_launches(const xvb_extractor_t* h);
 const float* xvb_extractor_debug_f32(const xvb_extractor_t* h, int which);
 void xvb_extractor_destroy(xvb_extractor_t* h);
 
+/* ---------------------------------------------------------------------------------------------
+ * Kaldi-compatible fbank / MFCC from raw waveforms (the feature step of the reference's online
+ * path: KaldiFeature, pytorch/libs/egs/kaldi_features.py:69-135 -> torchaudio.compliance.kaldi
+ * fbank/mfcc; C++ runtime: runtime/kaldifeat/csrc/feature-fbank.cc).  snip_edges framing, no
+ * dither (the launchers force dither = 0 for extraction), no VTLN, window rounded up to 2^k.
+ * Field names and defaults are torchaudio's / Kaldi's.  num_ceps > 0 selects MFCC.
+ * ------------------------------------------------------------------------------------------- */
+#define XVB_WINDOW_POVEY 0
+#define XVB_WINDOW_HAMMING 1
+#define XVB_WINDOW_HANNING 2
+#define XVB_WINDOW_RECTANGULAR 3
+#define XVB_WINDOW_BLACKMAN 4
+typedef struct {
+  float sample_frequency, frame_length_ms, frame_shift_ms, preemphasis_coefficient, low_freq, high_freq,
+      energy_floor, cepstral_lifter, blackman_coeff;
+  int num_mel_bins, num_ceps, use_energy, raw_energy, remove_dc_offset, use_log_fbank, use_power, htk_compat,
+      window_type;
+} xvb_fbank_opts_t;
+typedef struct xvb_fbank xvb_fbank_t;
+void xvb_fbank_default_opts(xvb_fbank_opts_t* opts);
+/* Builds window / twiddle / mel / DCT tables (double precision, stored fp32) on the current device. */
+int xvb_fbank_create(xvb_fbank_t** out, const xvb_fbank_opts_t* opts);
+int xvb_fbank_dim(const xvb_fbank_t* h);                            /* columns of the feature matrix */
+int64_t xvb_fbank_num_frames(const xvb_fbank_t* h, int64_t num_samples); /* 1 + (n - window) / shift, or 0 */
+/* wave: all utterances back to back (device, fp32, Kaldi i.e. int16-range scale if the model was
+ * trained that way); sample_offsets (U+1) int64 and frame_offsets (U+1) int32 on the device, with
+ * frame_offsets[u+1]-frame_offsets[u] = xvb_fbank_num_frames(len_u); feats (total_frames, dim). */
+int xvb_fbank_compute(xvb_fbank_t* h, const float* wave, const int64_t* sample_offsets, const int32_t* frame_offsets,
+                      int num_utts, int64_t total_frames, float* feats, void* stream);
+void xvb_fbank_destroy(xvb_fbank_t* h);
+
 /* Load a finalized extractor from an .xvbm model file (written by asv_subtools_b200.ops.Extractor.save:
  * the layers exactly as the reference's state_dict stores them, eval BatchNorm folded) -- what
  * torch::jit::load does for the reference's runtime (runtime/extractor/torch_asv_model.cc:8-17). */

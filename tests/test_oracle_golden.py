@@ -147,3 +147,38 @@ def test_extended_xvector(golden):
         emb = np.stack([onn.extract_embedding(lambda x: onn.extended_xvector_forward(sd, x, pos), feats[i]).numpy()
                         for i in range(3)])
         assert rel(emb, g["ext80_{}_emb".format(pos)]) < RTOL
+
+
+def test_kaldi_fbank_mfcc_oracle_matches_reference_kaldifeature(golden):
+    """oracle.frontend.kaldi_fbank / kaldi_mfcc / sequence_normalize vs the reference's KaldiFeature
+    (tests/golden/make_golden_fbank.py).  The reference computes in fp32 (torch FFT), the oracle in
+    float64: agreement is bounded by fp32 rounding of log-mel energies."""
+    import importlib.util
+    import os
+    from oracle import frontend as ofe
+    spec = importlib.util.spec_from_file_location("mgf", os.path.join(os.path.dirname(__file__), "golden", "make_golden_fbank.py"))
+    mgf = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mgf)
+    g = golden("fbank")
+    seen = 0
+    for cname, (ftype, featset, mv) in mgf.CONFIGS.items():
+        for wname, (n, seed) in mgf.WAVES.items():
+            key = "{}_{}".format(cname, wname)
+            if key not in g.files:
+                continue
+            wave = ofe.synthetic_wave(n, seed, sample_frequency=featset.get("sample_frequency", 16000.0))
+            got = (ofe.kaldi_mfcc if ftype == "mfcc" else ofe.kaldi_fbank)(wave, **featset)
+            if mv:
+                if got.shape[0] == 1 and mv.get("std_norm"):
+                    continue
+                got = ofe.sequence_normalize(got, **mv)
+            ref = g[key].astype(np.float64)
+            assert got.shape == ref.shape, key
+            if mv.get("std_norm") and got.shape[0] < 3:
+                continue     # std over two frames amplifies fp32 noise
+            tol = 2e-4 if featset.get("use_log_fbank", True) else 2e-5 * max(1.0, np.abs(ref).max())
+            if ftype == "mfcc":   # the lifter scales cepstra (and their fp32 noise) by up to 1 + lifter/2
+                tol *= 1.0 + 0.5 * featset.get("cepstral_lifter", 22.0)
+            assert np.max(np.abs(got - ref)) < tol, (key, np.max(np.abs(got - ref)))
+            seen += 1
+    assert seen >= 16
