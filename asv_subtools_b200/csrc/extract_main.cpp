@@ -1,7 +1,14 @@
 // xvb-extract: Python-free x-vector extraction over the C ABI.
 //
 //   xvb-extract [--batch N] [--max-chunk N] [--cmn none|utt|sliding] [--cmn-window W] [--gpu-id ID]
-//               <model.xvbm> <feats-rspecifier> <vectors-wspecifier>
+//               [--wav fbank|mfcc [--num-mel-bins N] [--num-ceps N] [--low-freq F] [--high-freq F]
+//                [--frame-length MS] [--frame-shift MS] [--energy-floor E] [--use-energy]]
+//               <model.xvbm> <feats-rspecifier | wav.scp> <vectors-wspecifier>
+//
+// With --wav the second positional is a Kaldi wav.scp (`<key> <file.wav>`, PCM16 RIFF; samples are used
+// in int16 range like runtime/frontend/wav.h:95-99 and processor.py:429) and features are computed on
+// the GPU by xvb_fbank_compute with the given kaldi_featset (runtime/test/feat_conf.yaml names); add
+// `--cmn utt` for that file's `mean_norm: true`.
 //
 // Positionals follow the reference's extractor CLI (pytorch/pipeline/onestep/extract_embeddings.py
 // :17-45: <model-path> <feats-rspecifier> <vectors-wspecifier>); the role is that of the reference's
@@ -100,11 +107,52 @@ struct Runner {
   }
 };
 
+// PCM16 RIFF reader: channel 0 as float in int16 range (runtime/frontend/wav.h:44-118)
+bool read_wav(const std::string& path, std::vector<float>* out, int* sample_rate) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) { fprintf(stderr, "ERROR: xvb-extract: cannot open wav '%s'\n", path.c_str()); return false; }
+  unsigned char hd[12];
+  bool ok = fread(hd, 1, 12, f) == 12 && memcmp(hd, "RIFF", 4) == 0 && memcmp(hd + 8, "WAVE", 4) == 0;
+  int channels = 0, bits = 0, fmt = 0;
+  *sample_rate = 0;
+  while (ok) {
+    unsigned char ch[8];
+    if (fread(ch, 1, 8, f) != 8) { ok = false; break; }
+    const uint32_t sz = ch[4] | (ch[5] << 8) | (ch[6] << 16) | ((uint32_t)ch[7] << 24);
+    if (memcmp(ch, "fmt ", 4) == 0) {
+      unsigned char b[16];
+      if (sz < 16 || fread(b, 1, 16, f) != 16) { ok = false; break; }
+      fmt = b[0] | (b[1] << 8); channels = b[2] | (b[3] << 8);
+      *sample_rate = b[4] | (b[5] << 8) | (b[6] << 16) | ((uint32_t)b[7] << 24);
+      bits = b[14] | (b[15] << 8);
+      fseek(f, (long)(sz - 16 + (sz & 1)), SEEK_CUR);
+    } else if (memcmp(ch, "data", 4) == 0) {
+      if (fmt != 1 || bits != 16 || channels < 1) { ok = false; break; }
+      std::vector<int16_t> raw(sz / 2);
+      const size_t got = fread(raw.data(), 2, raw.size(), f);   // a streamed header may overstate the size
+      const size_t n = got / channels;
+      out->resize(n);
+      for (size_t i = 0; i < n; ++i) (*out)[i] = (float)raw[i * channels];
+      fclose(f);
+      return true;
+    } else {
+      fseek(f, (long)(sz + (sz & 1)), SEEK_CUR);
+    }
+  }
+  fclose(f);
+  fprintf(stderr, "ERROR: xvb-extract: '%s' is not a PCM16 RIFF wav\n", path.c_str());
+  return false;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
   Runner r;
   int max_chunk = 10000, gpu = 0;
+  std::string wav_type;
+  xvb_fbank_opts_t fo;
+  xvb_fbank_default_opts(&fo);
+  bool ceps_set = false;
   std::vector<const char*> pos;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
@@ -116,19 +164,33 @@ int main(int argc, char** argv) {
     else if (a == "--max-chunk") max_chunk = atoi(val("--max-chunk"));
     else if (a == "--cmn-window") r.cmn_window = atoi(val("--cmn-window"));
     else if (a == "--gpu-id") gpu = atoi(val("--gpu-id"));
+    else if (a == "--wav") wav_type = val("--wav");
+    else if (a == "--num-mel-bins") fo.num_mel_bins = atoi(val("--num-mel-bins"));
+    else if (a == "--num-ceps") { fo.num_ceps = atoi(val("--num-ceps")); ceps_set = true; }
+    else if (a == "--low-freq") fo.low_freq = (float)atof(val("--low-freq"));
+    else if (a == "--high-freq") fo.high_freq = (float)atof(val("--high-freq"));
+    else if (a == "--frame-length") fo.frame_length_ms = (float)atof(val("--frame-length"));
+    else if (a == "--frame-shift") fo.frame_shift_ms = (float)atof(val("--frame-shift"));
+    else if (a == "--energy-floor") fo.energy_floor = (float)atof(val("--energy-floor"));
+    else if (a == "--use-energy") fo.use_energy = 1;
     else if (a == "--cmn") {
       const std::string m = val("--cmn");
       r.cmn = m == "none" ? 0 : m == "utt" ? 1 : m == "sliding" ? 2 : -1;
       if (r.cmn < 0) { fprintf(stderr, "ERROR: xvb-extract: --cmn must be none, utt or sliding\n"); return 1; }
     } else if (a == "--help" || a == "-h") {
       printf("usage: xvb-extract [--batch N] [--max-chunk N] [--cmn none|utt|sliding] [--cmn-window W] [--gpu-id ID]\n"
-             "                   <model.xvbm> <feats-rspecifier> <vectors-wspecifier>\n");
+             "                   [--wav fbank|mfcc [--num-mel-bins N] [--num-ceps N] [--low-freq F] [--high-freq F]\n"
+             "                    [--frame-length MS] [--frame-shift MS] [--energy-floor E] [--use-energy]]\n"
+             "                   <model.xvbm> <feats-rspecifier | wav.scp> <vectors-wspecifier>\n");
       return 0;
     } else if (a.size() > 2 && a[0] == '-' && a[1] == '-') {
       fprintf(stderr, "ERROR: xvb-extract: unknown option %s\n", a.c_str());
       return 1;
     } else pos.push_back(argv[i]);
   }
+  if (!wav_type.empty() && wav_type != "fbank" && wav_type != "mfcc") { fprintf(stderr, "ERROR: xvb-extract: --wav must be fbank or mfcc\n"); return 1; }
+  if (wav_type == "mfcc" && !ceps_set) fo.num_ceps = 13;
+  if (wav_type == "fbank") fo.num_ceps = 0;
   if (pos.size() != 3 || r.batch < 1 || max_chunk < 1 || r.cmn_window < 1) {
     fprintf(stderr, "ERROR: xvb-extract: expected <model.xvbm> <feats-rspecifier> <vectors-wspecifier> (see --help)\n");
     return 1;
@@ -139,7 +201,55 @@ int main(int argc, char** argv) {
   r.F = xvb_extractor_feat_dim(pos[0]);
   r.D = xvb_extractor_embed_dim(r.ex);
   xvb_ark_reader_t* in = nullptr;
-  CK(xvb_ark_reader_open(&in, pos[1]), "opening the feature rspecifier");
+  FILE* wav_scp = nullptr;
+  xvb_fbank_t* fb = nullptr;
+  int wav_rate = 0;
+  std::vector<float> wave, wav_feats;
+  std::string wav_key;
+  float* d_wave = nullptr;
+  int64_t* d_soff = nullptr;
+  size_t wave_cap = 0;
+  if (wav_type.empty()) CK(xvb_ark_reader_open(&in, pos[1]), "opening the feature rspecifier");
+  else {
+    wav_scp = fopen(pos[1], "r");
+    if (!wav_scp) { fprintf(stderr, "ERROR: xvb-extract: cannot open wav.scp '%s'\n", pos[1]); return 1; }
+    CU(cudaMalloc(&d_soff, 2 * sizeof(int64_t)));
+  }
+  // next utterance as a host (rows, cols) fp32 matrix: from the ark stream, or wav -> GPU fbank/MFCC
+  auto next_utt = [&](const char** key, int* rows, int* cols, const float** data) -> int {
+    if (wav_type.empty()) return xvb_ark_reader_next(in, key, rows, cols, data);
+    char line[8192];
+    for (;;) {
+      if (!fgets(line, sizeof line, wav_scp)) return 0;
+      char k[4096], path[4096];
+      if (sscanf(line, "%4095s %4095[^\n]", k, path) != 2) continue;
+      size_t pl = strlen(path);
+      while (pl && (path[pl - 1] == ' ' || path[pl - 1] == '\r')) path[--pl] = 0;
+      wav_key = k;
+      int rate = 0;
+      if (!read_wav(path, &wave, &rate)) exit(1);
+      if (!fb) {
+        wav_rate = rate;
+        fo.sample_frequency = (float)rate;
+        CK(xvb_fbank_create(&fb, &fo), "xvb_fbank_create");
+        if (xvb_fbank_dim(fb) != r.F) { fprintf(stderr, "ERROR: xvb-extract: the feature options give %d dims, the model expects %d\n", xvb_fbank_dim(fb), r.F); exit(1); }
+      } else if (rate != wav_rate) { fprintf(stderr, "ERROR: xvb-extract: %s is sampled at %d Hz, the first file at %d Hz\n", k, rate, wav_rate); exit(1); }
+      const int64_t n = (int64_t)wave.size(), frames = xvb_fbank_num_frames(fb, n);
+      if (frames < 1) { fprintf(stderr, "ERROR: xvb-extract: %s is shorter than one analysis window\n", k); exit(1); }
+      if ((size_t)n > wave_cap) { if (d_wave) cudaFree(d_wave); wave_cap = (size_t)n + (size_t)n / 4; CU(cudaMalloc(&d_wave, wave_cap * sizeof(float))); }
+      r.reserve((size_t)frames);
+      const int64_t soff[2] = {0, n};
+      const int32_t foff[2] = {0, (int32_t)frames};
+      CU(cudaMemcpy(d_wave, wave.data(), (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(d_soff, soff, sizeof soff, cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(r.d_off, foff, sizeof foff, cudaMemcpyHostToDevice));
+      CK(xvb_fbank_compute(fb, d_wave, d_soff, r.d_off, 1, frames, r.d_feats, nullptr), "xvb_fbank_compute");
+      wav_feats.resize((size_t)frames * r.F);
+      CU(cudaMemcpy(wav_feats.data(), r.d_feats, wav_feats.size() * sizeof(float), cudaMemcpyDeviceToHost));
+      *key = wav_key.c_str(); *rows = (int)frames; *cols = r.F; *data = wav_feats.data();
+      return 1;
+    }
+  };
   CK(xvb_ark_writer_open(&r.out, pos[2]), "opening the vector wspecifier");
   CU(cudaMalloc(&r.d_emb, (size_t)r.batch * r.D * sizeof(float)));
   CU(cudaMallocHost(&r.h_emb, (size_t)r.batch * r.D * sizeof(float)));
@@ -154,7 +264,7 @@ int main(int argc, char** argv) {
   int rows, cols, rc;
   const float* data;
   std::vector<float> normed;
-  while ((rc = xvb_ark_reader_next(in, &key, &rows, &cols, &data)) == 1) {
+  while ((rc = next_utt(&key, &rows, &cols, &data)) == 1) {
     fprintf(to_stdout ? stderr : stdout, "Process utterance for key %s\n", key);   // extract_embeddings.py:81
     if (cols != r.F) { fprintf(stderr, "ERROR: xvb-extract: %s has %d-dim features, the model expects %d\n", key, cols, r.F); return 1; }
     if (rows < 1) { fprintf(stderr, "ERROR: xvb-extract: %s has no frames\n", key); return 1; }
@@ -195,7 +305,9 @@ int main(int argc, char** argv) {
   }
   if (rc < 0) die("reading features");
   for (auto& kv : buckets) r.run(kv.second);
-  xvb_ark_reader_close(in);
+  if (in) xvb_ark_reader_close(in);
+  if (wav_scp) fclose(wav_scp);
+  if (fb) xvb_fbank_destroy(fb);
   CK(xvb_ark_writer_close(r.out), "closing the vector wspecifier");
   xvb_extractor_destroy(r.ex);
   fprintf(stderr, "xvb-extract: %ld utterances, %ld frames\n", r.done_utts, r.done_frames);

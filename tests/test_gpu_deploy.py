@@ -90,3 +90,42 @@ def test_xvb_extract_binary_matches_oracle_and_plugin(tmp_path):
         kaldi_io.write_mat(f, np.zeros((10, 23), np.float32), key="b")
     run = subprocess.run([BIN, model, bad, "ark:" + out_ark], capture_output=True, text=True, timeout=120)
     assert run.returncode == 1 and "ERROR" in run.stderr
+
+
+@pytest.mark.gpu
+def test_xvb_extract_wav_scp_mode_matches_oracle_chain(tmp_path):
+    """wav.scp -> GPU fbank (runtime/test/feat_conf.yaml options) -> mean norm -> x-vector, no Python at run
+    time; against the all-CPU oracle chain (kaldi_fbank -> sequence_normalize -> xvector_forward)."""
+    import wave as wavmod
+    m, sd = _model(80, 102, "far")
+    model = str(tmp_path / "xv80.xvbm")
+    m.extractor().save(model)
+    scp = tmp_path / "wav.scp"
+    waves = {}
+    with open(scp, "w") as f:
+        for i, n in enumerate([16000, 24000, 16000, 5000]):
+            pcm = np.clip(np.round(ofe.synthetic_wave(n, 700 + i)), -32768, 32767).astype(np.int16)
+            path = tmp_path / "u{}.wav".format(i)
+            with wavmod.open(str(path), "wb") as w:
+                w.setnchannels(1)
+                w.setsampwidth(2)
+                w.setframerate(16000)
+                w.writeframes(pcm.tobytes())
+            waves["u{}".format(i)] = pcm.astype(np.float32)
+            f.write("u{} {}\n".format(i, path))
+    out_ark = str(tmp_path / "xv.ark")
+    run = subprocess.run([BIN, "--wav", "fbank", "--num-mel-bins", "80", "--low-freq", "40", "--high-freq", "-200",
+                          "--energy-floor", "0", "--cmn", "utt", model, str(scp), "ark:" + out_ark],
+                         capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stdout + run.stderr
+    got = dict(kaldi_io.read_vec_flt_ark(out_ark))
+    featset = dict(dither=0.0, energy_floor=0.0, frame_length=25, frame_shift=10, high_freq=-200, low_freq=40, num_mel_bins=80)
+    fwd = lambda x: onn.xvector_forward(sd, x, "far")
+    for k, wv in waves.items():
+        feats = ofe.sequence_normalize(ofe.kaldi_fbank(wv, **featset)).astype(np.float32)
+        want = onn.extract_embedding(fwd, feats).numpy()
+        assert rel(got[k], want) < 1e-4, k
+    # a model/feature mismatch is an ERROR, not a silent resize
+    run = subprocess.run([BIN, "--wav", "fbank", "--num-mel-bins", "40", model, str(scp), "ark:" + out_ark],
+                         capture_output=True, text=True, timeout=120)
+    assert run.returncode == 1 and "ERROR" in run.stderr
