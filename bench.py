@@ -284,6 +284,17 @@ def run_native(args, rank, world, local_rank):
     e2e_host_ms = (time.perf_counter() - t_e2e0) * 1e3   # every step ends in the host buffer: host clock
     barrier()
     e2e_ms = max_over_ranks(e2e_host_ms)
+    # what bounds e2e: the host->device link.  Same pinned buffer, copy alone, CUDA events.
+    dst = torch.empty_like(batches[0])
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dst.copy_(host[0], non_blocking=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for i in range(8):
+        dst.copy_(host[i % 2], non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = 8 * host[0].numel() * 4 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
     assert torch.isfinite(host_outs[(args.steps - 1) % 2]).all()
     clocks = sampler.stop(wall0, time.time()) if sampler else None
 
@@ -339,7 +350,10 @@ def run_native(args, rank, world, local_rank):
         "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": B * T * F * 4, "d2h_bytes_per_step": B * D * 4,
                 "api": "xvb_extractor_submit_host/xvb_extractor_wait (pinned host feats in, host embeddings out; "
-                       "H2D of batch i+1 overlaps the kernels of batch i; timed on the host clock)"},
+                       "H2D of batch i+1 overlaps the kernels of batch i; timed on the host clock)",
+                "h2d_link_gbs_measured": h2d_gbs,
+                "h2d_link_bound": world * h2d_gbs * 1e9 / (F * 4), "h2d_link_bound_note":
+                "frames/s the host->device link alone allows at 320 B/frame (fp32 80-d features) per GPU"},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "tdnn_gemm_bf16x3_kernel (6 launches/step; tdnn5 pools over time in its epilogue)",
