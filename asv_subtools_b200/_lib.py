@@ -20,7 +20,7 @@ class TdnnArgs(C.Structure):
                 ("y_hi", C.c_void_p), ("y_lo", C.c_void_p), ("ldy", C.c_int64),
                 ("y_f32", C.c_void_p), ("ldyf", C.c_int64),
                 ("B", C.c_int), ("T", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int),
-                ("pool_partial", C.c_void_p)]
+                ("pool_partial", C.c_void_p), ("x_batch_stride", C.c_int64)]
 MAX_TAPS = 16
 
 
@@ -58,6 +58,7 @@ SIGNATURES = {
     "xvb_stats_pool": (_i, [_p, _i64, _i, _i, _i, _f, _p, _p, _p, _i64, _p]),
     "xvb_stats_pool_ex": (_i, [_p, _i64, _i, _i, _i, _f, _i, _p, _p, _p, _i64, _p]),
     "xvb_tdnn_affine_ex": (_i, [_p, _p]),
+    "xvb_split_frames": (_i, [_p, _i, _i, _i, _p, _p, _i64, _i, _i, _p]),
     "xvb_pool_partial_blocks": (_i, [_i, _i, _ip]),
     "xvb_pool_finalize": (_i, [_p, _i, _i, _i, _i, _i, _f, _i, _p, _p, _p, _i64, _p]),
     "xvb_extractor_set_fused_pooling": (_i, [_p, _i]),

@@ -7,6 +7,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <mutex>
+
 #include "../../include/xvb200.h"
 
 namespace xvb {
@@ -73,6 +75,30 @@ int tdnn_affine_impl(const xvb_tdnn_args_t& args, void* stream, const TrialHist*
 // tdnn_gemm.cu: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda).
 int make_tensor_map(CUtensorMap* m, const void* base, int esize, int rank, const unsigned long long* dims,
                     const unsigned long long* strides_bytes, const unsigned* box, int swizzle_bytes);
+
+// stream-ordered scratch from the device's default memory pool
+struct TempBuf {
+  void* p = nullptr;
+  cudaStream_t s;
+  explicit TempBuf(cudaStream_t st) : s(st) {}
+  int alloc(size_t bytes) {
+    // keep freed scratch in the device's pool: with the default release threshold (0) every
+    // synchronisation hands it back to the driver and the next call pays for mapping it again
+    static std::once_flag once[64];
+    int dev = 0;
+    XVB_CUDA(cudaGetDevice(&dev));
+    std::call_once(once[dev & 63], [dev] {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+    });
+    XVB_CUDA(cudaMallocAsync(&p, bytes, s));
+    return XVB_OK;
+  }
+  ~TempBuf() { if (p) cudaFreeAsync(p, s); }
+};
 
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 

@@ -81,6 +81,43 @@ __global__ void split_f32_kernel(const float* __restrict__ x, long long rows, in
   }
 }
 
+// (B, T, C) fp32 frames -> planes (B, pad_front + T + pad_back, ldp) with zero frames around each
+// utterance.  One thread per 8 output columns; float4 loads when the source rows allow it.
+__global__ void split_frames_kernel(const float* __restrict__ x, int B, int T, int C, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo, long long ldp, int pad_front, int Tp, int vec) {
+  const long long groups_per_row = ldp / 8;
+  const long long total = (long long)B * Tp * groups_per_row;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / groups_per_row;
+    const int c0 = (int)(i - r * groups_per_row) * 8;
+    const int b = (int)(r / Tp), t = (int)(r - (long long)b * Tp) - pad_front;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = 0.f;
+    if (t >= 0 && t < T) {
+      const float* src = x + ((long long)b * T + t) * C + c0;
+      if (vec && c0 + 8 <= C) {
+        const float4 a = *reinterpret_cast<const float4*>(src), c = *reinterpret_cast<const float4*>(src + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (c0 + k < C) v[k] = src[k];
+      }
+    }
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      __nv_bfloat16 ah, al, bh, bl;
+      split_bf16(v[2 * k], ah, al);
+      split_bf16(v[2 * k + 1], bh, bl);
+      h[k] = pack_bf16x2(ah, bh);
+      l[k] = pack_bf16x2(al, bl);
+    }
+    *reinterpret_cast<uint4*>(hi + r * ldp + c0) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo + r * ldp + c0) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Reference weight (Cout, Cin, tot) -> packed K-major planes (Cout, ntaps*cin_p16), masked taps dropped.
 // ------------------------------------------------------------------------------------------------
@@ -158,6 +195,22 @@ extern "C" int xvb_split_f32(const float* x, int64_t rows, int C, int64_t ldx, u
   const long long total = rows * (ldp / 8);
   split_f32_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       x, rows, C, ldx, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), ldp);
+  XVB_LAUNCH_CHECK();
+  return XVB_OK;
+}
+
+extern "C" int xvb_split_frames(const float* x, int B, int T, int C, uint16_t* hi, uint16_t* lo, int64_t ldp, int pad_front,
+                                int pad_back, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  XVB_CHECK_ARG(x && hi && lo && B > 0 && T > 0 && C > 0 && ldp >= C && ldp % 8 == 0 && pad_front >= 0 && pad_back >= 0,
+                "xvb_split_frames: bad arguments");
+  XVB_CHECK_ARG(((uintptr_t)hi | (uintptr_t)lo) % 16 == 0, "xvb_split_frames: planes must be 16-byte aligned");
+  const int Tp = pad_front + T + pad_back;
+  const long long total = (long long)B * Tp * (ldp / 8);
+  const int vec = (C % 4 == 0 && (uintptr_t)x % 16 == 0) ? 1 : 0;
+  split_frames_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      x, B, T, C, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), ldp, pad_front, Tp, vec);
   XVB_LAUNCH_CHECK();
   return XVB_OK;
 }

@@ -4,6 +4,7 @@
 // equal-length utterances and for the "load weights, run extraction without Python" role of the
 // reference's C++ runtime (runtime/bin/extractor_main.cc, runtime/speaker/torch_asv_model.cc).
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -58,6 +59,10 @@ struct xvb_extractor {
   int last_launches = 0;
   // optional per-kernel CUDA-event timing on the launching stream (bench.py roofline)
   bool fused_pooling = true;
+  // first layer as an im2col view (consecutive context taps over a time-padded frame matrix): 7 channel
+  // blocks instead of 10 for [-2..2] x 80.  Turned off if the driver rejects the overlapping tensor map.
+  bool im2col_first = false;
+  int pad_front = 0, pad_back = 0;
   float* pool_partial = nullptr;
   size_t pool_partial_cap = 0;
   bool profiling = false;
@@ -175,6 +180,15 @@ extern "C" int xvb_extractor_finalize(xvb_extractor_t* h, float pooling_eps) {
   }
   XVB_CHECK_ARG(h->segment.back().Cout % 4 == 0, "last segment layer: Cout must be a multiple of 4");
   h->pooling_eps = pooling_eps;
+  {
+    const Layer& L0 = h->frame[0];
+    bool consecutive = L0.ntaps > 1 && L0.ctx[0] <= 0 && L0.ctx[L0.ntaps - 1] >= 0;
+    for (int i = 1; i < L0.ntaps; ++i) consecutive = consecutive && L0.ctx[i] == L0.ctx[i - 1] + 1;
+    const int knob = getenv("XVB_IM2COL") ? atoi(getenv("XVB_IM2COL")) : 1;   // read per extractor: tests flip it
+    h->im2col_first = knob && consecutive && h->feat_dim % 16 == 0;   // plane pitch == packed tap pitch
+    h->pad_front = h->im2col_first ? -L0.ctx[0] : 0;
+    h->pad_back = h->im2col_first ? L0.ctx[L0.ntaps - 1] : 0;
+  }
   h->finalized = true;
   return XVB_OK;
 }
@@ -190,8 +204,9 @@ static int reserve(xvb_extractor* h, int B, int T) {
   const int nb = B > h->cap_B ? B : h->cap_B;
   h->free_ws();
   int rc;
-  if ((rc = dev_alloc(&h->in_hi, (size_t)nf * h->ldf))) return rc;
-  if ((rc = dev_alloc(&h->in_lo, (size_t)nf * h->ldf))) return rc;
+  const size_t in_rows = (size_t)nf + (size_t)nb * (h->pad_front + h->pad_back);
+  if ((rc = dev_alloc(&h->in_hi, in_rows * h->ldf))) return rc;
+  if ((rc = dev_alloc(&h->in_lo, in_rows * h->ldf))) return rc;
   if (h->max_c > 0)
     for (int i = 0; i < 2; ++i) {
       if ((rc = dev_alloc(&h->act_hi[i], (size_t)nf * h->max_c))) return rc;
@@ -222,8 +237,12 @@ extern "C" int xvb_extractor_extract(xvb_extractor_t* h, const float* feats, int
   h->events_used = 0;
   h->events_stream = cs;
   if ((rc = h->mark(cs))) return rc;
-  // 1. stage the frame matrix as split planes (framework.py:28-33 staging)
-  rc = xvb_split_f32(feats, (int64_t)B * T, h->feat_dim, h->feat_dim, h->in_hi, h->in_lo, h->ldf, stream);
+  // 1. stage the frame matrix as split planes (framework.py:28-33 staging); for the im2col first layer with
+  //    the zero frames of F.pad (components.py:117) written out around every utterance
+  if (h->im2col_first)
+    rc = xvb_split_frames(feats, B, T, h->feat_dim, h->in_hi, h->in_lo, h->ldf, h->pad_front, h->pad_back, stream);
+  else
+    rc = xvb_split_f32(feats, (int64_t)B * T, h->feat_dim, h->feat_dim, h->in_hi, h->in_lo, h->ldf, stream);
   if (rc) return rc;
   if ((rc = h->mark(cs))) return rc;
   // 2. frame-level TDNN stack (xvector.py:85-89)
@@ -243,6 +262,11 @@ extern "C" int xvb_extractor_extract(xvb_extractor_t* h, const float* feats, int
     a.context_host = L.ctx; a.ntaps = L.ntaps;
     a.y_hi = y_hi; a.y_lo = y_lo; a.ldy = L.Cout;
     a.B = B; a.T = T; a.Cin = L.Cin; a.Cout = L.Cout;
+    const int ctx0 = 0;
+    if (i == 0 && h->im2col_first) {   // window of ntaps consecutive frames = one long row of the padded planes
+      a.context_host = &ctx0; a.ntaps = 1; a.Cin = L.ntaps * L.Cin;
+      a.x_batch_stride = (int64_t)(T + h->pad_front + h->pad_back) * ldx;
+    }
     if (last && h->fused_pooling) {
       const size_t need = (size_t)pool_blocks * B * 2 * L.Cout;
       if (need > h->pool_partial_cap) {
@@ -255,6 +279,11 @@ extern "C" int xvb_extractor_extract(xvb_extractor_t* h, const float* feats, int
       a.y_f32 = h->last_f32; a.ldyf = L.Cout;
     }
     rc = xvb_tdnn_affine_ex(&a, stream);
+    if (rc && i == 0 && h->im2col_first) {   // overlapping tensor map refused: fall back for good
+      h->im2col_first = false;
+      h->pad_front = h->pad_back = 0;
+      return xvb_extractor_extract(h, feats, B, T, emb, stream);
+    }
     if (rc) return rc;
     if ((rc = h->mark(cs))) return rc;
     x_hi = y_hi; x_lo = y_lo; ldx = L.Cout;

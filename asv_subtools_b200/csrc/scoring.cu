@@ -6,6 +6,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace xvb {
@@ -150,16 +152,6 @@ __global__ void snorm_trials_kernel(const float* __restrict__ s, const int32_t* 
   }
 }
 
-struct TempBuf {  // stream-ordered scratch
-  void* p = nullptr;
-  cudaStream_t s;
-  explicit TempBuf(cudaStream_t st) : s(st) {}
-  int alloc(size_t bytes) {
-    XVB_CUDA(cudaMallocAsync(&p, bytes, s));
-    return XVB_OK;
-  }
-  ~TempBuf() { if (p) cudaFreeAsync(p, s); }
-};
 
 // out (Ne, Nt) = A (Ne, D) . Bm (Nt, D)^T  [+ row_bias[i] + col_bias[j]] through the tcgen05 layer.
 static int matmul_nt(const float* A, int64_t Ne, const float* Bm, int64_t Nt, int D, const float* row_bias,

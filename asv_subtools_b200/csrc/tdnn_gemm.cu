@@ -74,6 +74,11 @@ struct TdnnGemmParams {
   int hist_bins;
   int hist_sym;               // count only column index > row index (all pairs of one set, each once)
   int hist_group, num_units;  // tile raster of the score-matrix mode (decode_tile)
+  // split-K for the segment-level layers (M = B rows, K in the thousands: too few tiles to fill the
+  // machine otherwise): slice s of a tile covers channel blocks [s*kb_per_slice, (s+1)*kb_per_slice)
+  // and stores its fp32 partial at "time" s of a (B, k_slices, Cout) buffer; segment_reduce_kernel sums
+  // the slices in order (deterministic) and applies the epilogue.  ntaps == 1, one source only.
+  int k_slices, kb_per_slice;
   __nv_bfloat16* y_hi;
   __nv_bfloat16* y_lo;
   long long ldy;
@@ -116,8 +121,10 @@ struct GemmCfg {
 // pairs in flight cover hist_group rows x ~9 columns and each test (B) tile leaves HBM once per band
 // instead of once per M unit.  Returns false for tiles that do not exist / lie below the diagonal.
 template <bool kHist>
-__device__ __forceinline__ bool decode_tile(const TdnnGemmParams& p, int tile, int& m_unit, int& n_blk) {
+__device__ __forceinline__ bool decode_tile(const TdnnGemmParams& p, int tile, int& m_unit, int& n_blk, int& slice) {
+  slice = 0;
   if constexpr (!kHist) {
+    if (p.k_slices > 1) { slice = tile % p.k_slices; tile /= p.k_slices; }
     m_unit = p.unit_first + (tile / p.num_n_blk) * p.unit_stride;
     n_blk = tile % p.num_n_blk;
     return true;
@@ -196,8 +203,10 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile_first; tile < p.num_tiles; tile += tile_step) {
-        int m_unit, n_blk;
-        if (!decode_tile<kHist>(p, tile, m_unit, n_blk)) continue;   // e.g. entirely on or below the diagonal
+        int m_unit, n_blk, slice;
+        if (!decode_tile<kHist>(p, tile, m_unit, n_blk, slice)) continue;   // e.g. entirely on or below the diagonal
+        const int cb_begin = slice * p.kb_per_slice;                        // (0, num_cblk) unless split-K
+        const int cb_end = p.k_slices > 1 ? min(p.num_cblk, cb_begin + p.kb_per_slice) : p.num_cblk;
         const int m_blk = m_unit * kCta + (int)cta_rank;
         const int b0 = (m_blk / p.num_t_blk) * p.Bb, t0 = (m_blk % p.num_t_blk) * p.Tb;  // may be fully out of
         const int n0 = n_blk * kTileN + (int)cta_rank * Cfg::kBRows;                      // range: TMA zero-fills
@@ -206,7 +215,7 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
         const CUtensorMap* ma_lo = src == 0 ? &map_a_lo : &map_a2_lo;
         for (int tap = 0; tap < p.ntaps; ++tap) {
           const int tt = t0 + p.ctx[tap];
-          for (int cb = 0; cb < p.num_cblk; ++cb) {
+          for (int cb = cb_begin; cb < cb_end; ++cb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* s = smem + stage * kStageBytes;
             const int kw = tap * p.cin_p16 + cb * kBlockK;
@@ -247,14 +256,19 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
       uint32_t phase = 0;
       uint32_t it = 0;
       for (int tile = tile_first; tile < p.num_tiles; tile += tile_step) {
-        if constexpr (kHist) { int mu, nb; if (!decode_tile<true>(p, tile, mu, nb)) continue; }
+        int kb_begin = 0, kb_end = num_kblk;
+        if constexpr (kHist) { int mu, nb, sl; if (!decode_tile<true>(p, tile, mu, nb, sl)) continue; }
+        else if (p.k_slices > 1) {
+          kb_begin = (tile % p.k_slices) * p.kb_per_slice;
+          kb_end = min(num_kblk, kb_begin + p.kb_per_slice);
+        }
         const uint32_t acc = kAccStages == 2 ? (it & 1) : 0, acc_phase = kAccStages == 2 ? ((it >> 1) & 1) : (it & 1);
         ++it;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kTileN;
         uint32_t accumulate = 0;
-        for (int kb = 0; kb < num_kblk; ++kb) {
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           const int cb = kb % p.num_cblk;
           int nsteps = (p.Cin - cb * kBlockK + 15) >> 4;
           nsteps = nsteps > 4 ? 4 : nsteps;
@@ -338,8 +352,8 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
       asm volatile("bar.sync 3, 256;" ::: "memory");
     }
     for (int tile = tile_first; tile < p.num_tiles; tile += tile_step) {
-      int m_unit, n_blk;
-      if (!decode_tile<kHist>(p, tile, m_unit, n_blk)) continue;
+      int m_unit, n_blk, slice;
+      if (!decode_tile<kHist>(p, tile, m_unit, n_blk, slice)) continue;
       const uint32_t acc = kAccStages == 2 ? (it & 1) : 0, acc_phase = kAccStages == 2 ? ((it >> 1) & 1) : (it & 1);
       ++it;
       const int m_blk = m_unit * kCta + (int)cta_rank;
@@ -561,7 +575,7 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                 *reinterpret_cast<float4*>(p.y_f32 + ((long long)gb * p.T + gt) * p.ldyf + col) = w;
             }
           } else if (leader && !XVB_DBG(p, 4)) {
-            tma_store_3d(&map_y_f32, slab_base, n, t0, b0);
+            tma_store_3d(&map_y_f32, slab_base, n, t0 + slice, b0);   // split-K: partial of slice s at "time" s
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
@@ -636,6 +650,33 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
   if (warp == 1) tmem_dealloc<kCta>(tmem_base, Cfg::kTmemCols);
 }
 
+// Split-K tail: y[b,c] = epi(sum_s part[b,s,c]) with the slices added in index order (deterministic),
+// same epilogue order as the GEMM's: +bias -> ReLU -> BN -> tanh/sigmoid -> fp32 and/or split planes.
+__global__ void segment_reduce_kernel(const float* __restrict__ part, int S, int B, int Cout, const float* __restrict__ bias,
+                                      const float* __restrict__ scale, const float* __restrict__ shift, int flags,
+                                      float* __restrict__ y_f32, long long ldyf, __nv_bfloat16* __restrict__ y_hi,
+                                      __nv_bfloat16* __restrict__ y_lo, long long ldy) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * Cout) return;
+  const int b = (int)(idx / Cout), c = (int)(idx - (long long)b * Cout);
+  const float* src = part + (long long)b * S * Cout + c;
+  float x = src[0];
+  for (int s = 1; s < S; ++s) x += src[(long long)s * Cout];
+  x += bias ? bias[c] : 0.f;
+  if (flags & XVB_RELU) x = fmaxf(x, 0.f);
+  if (flags & XVB_BN) x = fmaf(x, scale[c], shift[c]);
+  if (flags & XVB_TANH) x = tanhf(x);
+  if (flags & XVB_SIGMOID) x = 1.f / (1.f + expf(-x));
+  if (y_f32) y_f32[(long long)b * ldyf + c] = x;
+  if (y_hi) {
+    __nv_bfloat16 h, l;
+    split_bf16(x, h, l);
+    y_hi[(long long)b * ldy + c] = h;
+    y_lo[(long long)b * ldy + c] = l;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Host side: tensor maps + launch
 // ------------------------------------------------------------------------------------------------
@@ -675,11 +716,12 @@ int make_tensor_map(CUtensorMap* m, const void* base, int esize, int rank, const
 }
 
 // (C, T, B) bf16 frame matrix with row pitch ld; box = 64 channels x Tb frames x Bb utterances.
-static int make_frame_map(CUtensorMap* m, const void* base, int C, int T, int B, long long ld, int Tb, int Bb) {
+static int make_frame_map(CUtensorMap* m, const void* base, int C, int T, int B, long long ld, int Tb, int Bb,
+                          long long batch_stride = 0) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return XVB_ECUDA; }
   cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
-  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)T};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, batch_stride ? (cuuint64_t)batch_stride * 2 : (cuuint64_t)ld * 2 * (cuuint64_t)T};
   cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)Tb, (cuuint32_t)Bb};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
@@ -773,7 +815,7 @@ static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const
   p.num_units = num_m_units;
   p.hist_group = 8;
   const long long tiles = kHist ? (long long)((num_m_units + p.hist_group - 1) / p.hist_group) * p.hist_group * p.num_n_blk
-                                : (long long)num_m_units * p.num_n_blk;
+                                : (long long)num_m_units * p.num_n_blk * (p.k_slices > 1 ? p.k_slices : 1);
   XVB_CHECK_ARG(tiles < (1ll << 31), "xvb_tdnn_affine: %d x %d tiles exceed one launch", num_m_units, p.num_n_blk);
   p.num_tiles = (int)tiles;
   static bool attr_set = false;
@@ -790,7 +832,7 @@ static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const
     my_hi = mw_hi; my_lo = mw_lo;  // unused
   }
   if (p.y_f32) {
-    if ((rc = make_out_map(&my_f32, p.y_f32, 4, p.Cout, p.T, p.B, p.ldyf, p.Tb, p.Bb))) return rc;
+    if ((rc = make_out_map(&my_f32, p.y_f32, 4, p.Cout, p.k_slices > 1 ? p.k_slices : p.T, p.B, p.ldyf, p.Tb, p.Bb))) return rc;
   } else {
     my_f32 = mw_hi;  // unused
   }
@@ -828,7 +870,13 @@ int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream, const TrialHis
   XVB_CHECK_ARG(a.x_hi && a.x_lo && a.w_hi && a.w_lo, "xvb_tdnn_affine: null operand pointer");
   XVB_CHECK_ARG(B > 0 && T > 0 && Cin > 0 && Cout > 0, "xvb_tdnn_affine: bad shape B=%d T=%d Cin=%d Cout=%d", B, T, Cin, Cout);
   XVB_CHECK_ARG(ntaps >= 1 && ntaps <= XVB_MAX_TAPS && a.context_host, "xvb_tdnn_affine: ntaps=%d out of range", ntaps);
-  XVB_CHECK_ARG(a.ldx % 8 == 0 && a.ldx >= Cin, "xvb_tdnn_affine: ldx=%lld must be a multiple of 8 and >= Cin", (long long)a.ldx);
+  if (a.x_batch_stride)   // im2col view: overlapping rows
+    XVB_CHECK_ARG(a.ldx % 8 == 0 && a.x_batch_stride % 8 == 0 && !a.x2_hi && ntaps == 1 &&
+                  a.x_batch_stride >= (long long)(T - 1) * a.ldx + Cin,
+                  "xvb_tdnn_affine: x_batch_stride=%lld needs ntaps==1, no second source, 8-element alignment and room for T windows",
+                  (long long)a.x_batch_stride);
+  else
+    XVB_CHECK_ARG(a.ldx % 8 == 0 && a.ldx >= Cin, "xvb_tdnn_affine: ldx=%lld must be a multiple of 8 and >= Cin", (long long)a.ldx);
   XVB_CHECK_ARG((a.x2_hi != nullptr) == (a.x2_lo != nullptr), "xvb_tdnn_affine: x2_hi/x2_lo must both be set or both NULL");
   if (a.x2_hi) XVB_CHECK_ARG(a.ldx2 % 8 == 0 && a.ldx2 >= Cin, "xvb_tdnn_affine: ldx2=%lld must be a multiple of 8 and >= Cin", (long long)a.ldx2);
   XVB_CHECK_ARG((a.y_hi != nullptr) == (a.y_lo != nullptr), "xvb_tdnn_affine: y_hi/y_lo must both be set or both NULL");
@@ -883,9 +931,28 @@ int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream, const TrialHis
   p.y_lo = reinterpret_cast<__nv_bfloat16*>(a.y_lo);
   p.ldy = a.ldy; p.y_f32 = a.y_f32; p.ldyf = a.ldyf;
 
+  // Split-K for segment-level layers (T == 1: M = B rows, tdnn6 has K = 3000): the slice count depends
+  // on K only, so a sub-batch reproduces the full batch's rows bit for bit.
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  TempBuf partial(s);
+  const int splitk = getenv("XVB_SPLITK") ? atoi(getenv("XVB_SPLITK")) : 1;   // read per call: tests flip it
+  p.k_slices = 1; p.kb_per_slice = p.num_cblk;
+  if (splitk && T == 1 && ntaps == 1 && !a.x2_hi && !a.pool_partial && !th && !a.row_bias && !a.utt_bias && B <= 1024 &&
+      p.num_cblk >= 24 && Cout % 4 == 0) {
+    int S = p.num_cblk / 6;
+    S = S > 8 ? 8 : S;
+    p.kb_per_slice = (p.num_cblk + S - 1) / S;
+    p.k_slices = (p.num_cblk + p.kb_per_slice - 1) / p.kb_per_slice;   // every slice owns >= 1 channel block
+    if ((rc = partial.alloc((size_t)B * p.k_slices * Cout * sizeof(float)))) return rc;
+    p.y_hi = nullptr; p.y_lo = nullptr;
+    p.y_f32 = static_cast<float*>(partial.p); p.ldyf = Cout;
+    p.bias = nullptr; p.scale = nullptr; p.shift = nullptr; p.flags = 0;
+    p.store_mode = 0;
+  }
+
   CUtensorMap ma_hi, ma_lo, ma2_hi, ma2_lo;
-  if ((rc = make_frame_map(&ma_hi, a.x_hi, Cin, T, B, a.ldx, p.Tb, p.Bb))) return rc;
-  if ((rc = make_frame_map(&ma_lo, a.x_lo, Cin, T, B, a.ldx, p.Tb, p.Bb))) return rc;
+  if ((rc = make_frame_map(&ma_hi, a.x_hi, Cin, T, B, a.ldx, p.Tb, p.Bb, a.x_batch_stride))) return rc;
+  if ((rc = make_frame_map(&ma_lo, a.x_lo, Cin, T, B, a.ldx, p.Tb, p.Bb, a.x_batch_stride))) return rc;
   if (a.x2_hi) {
     if ((rc = make_frame_map(&ma2_hi, a.x2_hi, Cin, T, B, a.ldx2, p.Tb, p.Bb))) return rc;
     if ((rc = make_frame_map(&ma2_lo, a.x2_lo, Cin, T, B, a.ldx2, p.Tb, p.Bb))) return rc;
@@ -893,32 +960,50 @@ int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream, const TrialHis
     ma2_hi = ma_hi; ma2_lo = ma_lo;  // unused
   }
 
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   // Wide N tiles (CTA pairs) when there are enough M tiles to fill the machine, narrow ones for
   // the segment-level layers (M = B rows) so that more SMs get a tile.
-  const long long m_tiles = (long long)p.num_t_blk * p.num_b_blk;
+  const long long m_tiles = (long long)p.num_t_blk * p.num_b_blk * p.k_slices;   // independent work items along M (and K slices)
   const int sms = sm_count();
   const int mode = gemm_cta_mode();
   const void* w_hi = a.w_hi;
   const void* w_lo = a.w_lo;
-  if (a.pool_partial)  // fused pooling always runs on the swapped CTA-pair kernel (any shape: TMA zero-fills)
-    return launch_gemm<256, 2, 1, true>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
-  if (th)              // the diagonal test of the symmetric mode assumes 256-row units x 256-column tiles
-    return launch_gemm<256, 2, 1, false, true>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
-  static const int force_bn = getenv("XVB_GEMM_BN") ? atoi(getenv("XVB_GEMM_BN")) : 0;  // tuning knobs
-  // wide tiles cut the operand stream by 25-37 % but serialise the epilogue with the MMAs (one
-  // accumulator in TMEM); measured slower end to end (profiles/r01_gemm_experiments.md), so opt-in.
-  static const int wide = getenv("XVB_GEMM_WIDE") ? atoi(getenv("XVB_GEMM_WIDE")) : 0;
-  if (mode == 2 && wide && force_bn != 128 && Cout >= 512 && (m_tiles / 2) * ((Cout + 511) / 512) >= sms / 2)
-    return launch_gemm<256, 2, 2>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
-  if (mode == 2 && force_bn != 128 && Cout >= 256 && m_tiles * ((Cout + 255) / 256) >= sms)
-    return launch_gemm<256, 2>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
-  if (mode == 2 && Cout >= 128 && m_tiles * ((Cout + 127) / 128) >= sms)
-    return launch_gemm<128, 2>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
-  if (Cout >= 256 && m_tiles * ((Cout + 255) / 256) >= sms) return launch_gemm<256, 1>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
-  if (Cout >= 128 && m_tiles * ((Cout + 127) / 128) >= sms) return launch_gemm<128, 1>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
-  if (Cout >= 64 && m_tiles * ((Cout + 63) / 64) >= sms / 2) return launch_gemm<64, 1>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
-  return launch_gemm<32, 1>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
+  auto dispatch = [&]() -> int {
+    if (a.pool_partial)  // fused pooling always runs on the swapped CTA-pair kernel (any shape: TMA zero-fills)
+      return launch_gemm<256, 2, 1, true>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
+    if (th)              // the diagonal test of the symmetric mode assumes 256-row units x 256-column tiles
+      return launch_gemm<256, 2, 1, false, true>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
+    static const int force_bn = getenv("XVB_GEMM_BN") ? atoi(getenv("XVB_GEMM_BN")) : 0;  // tuning knobs
+    // wide tiles cut the operand stream by 25-37 % but serialise the epilogue with the MMAs (one
+    // accumulator in TMEM); measured slower end to end (profiles/r01_gemm_experiments.md), so opt-in.
+    static const int wide = getenv("XVB_GEMM_WIDE") ? atoi(getenv("XVB_GEMM_WIDE")) : 0;
+    if (mode == 2 && wide && force_bn != 128 && Cout >= 512 && (m_tiles / 2) * ((Cout + 511) / 512) >= sms / 2)
+      return launch_gemm<256, 2, 2>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
+    if (mode == 2 && force_bn != 128 && Cout >= 256 && m_tiles * ((Cout + 255) / 256) >= sms)
+      return launch_gemm<256, 2>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
+    if (mode == 2 && Cout >= 128 && m_tiles * ((Cout + 127) / 128) >= sms)
+      return launch_gemm<128, 2>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
+    if (Cout >= 256 && m_tiles * ((Cout + 255) / 256) >= sms) return launch_gemm<256, 1>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
+    if (Cout >= 128 && m_tiles * ((Cout + 127) / 128) >= sms) return launch_gemm<128, 1>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
+    if (Cout >= 64 && m_tiles * ((Cout + 63) / 64) >= sms / 2) return launch_gemm<64, 1>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
+    return launch_gemm<32, 1>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
+  };
+  rc = dispatch();
+  if (rc || p.k_slices == 1) return rc;
+  const long long n = (long long)B * Cout;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)((n + 255) / 256));
+  cfg.blockDim = dim3(256);
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  XVB_CUDA(cudaLaunchKernelEx(&cfg, segment_reduce_kernel, (const float*)partial.p, p.k_slices, B, Cout, a.bias, a.bn_scale,
+                              a.bn_shift, a.flags, a.y_f32, (long long)a.ldyf, reinterpret_cast<__nv_bfloat16*>(a.y_hi),
+                              reinterpret_cast<__nv_bfloat16*>(a.y_lo), (long long)a.ldy));
+  XVB_LAUNCH_CHECK();
+  return XVB_OK;
 }
 
 extern "C" int xvb_pool_partial_blocks(int B, int T, int* frames_per_block) {

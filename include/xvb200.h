@@ -71,6 +71,11 @@ int xvb_split_f32(const float* x, int64_t rows, int C, int64_t ldx, uint16_t* hi
  * :78-83); only the taps listed in context[] are kept (the weight*mask of :133-138).
  * Output planes are K-major (Cout, ntaps*cin_p16) with cin_p16 = round_up(Cin,16) and
  * K index = tap*cin_p16 + c.  Size in elements: xvb_packed_weight_elems(). */
+/* (B, T, C) fp32 frames -> split planes with `pad_front` / `pad_back` zero frames around every
+ * utterance: planes are (B, pad_front + T + pad_back, ldp).  The zero frames are F.pad of
+ * TdnnAffine.forward (components.py:117) made explicit, for the im2col view of xvb_tdnn_args_t. */
+int xvb_split_frames(const float* x, int B, int T, int C, uint16_t* hi, uint16_t* lo, int64_t ldp, int pad_front,
+                     int pad_back, void* stream);
 int64_t xvb_packed_weight_elems(int Cout, int Cin, int ntaps);
 int xvb_pack_tdnn_weight(const float* w, int Cout, int Cin, int tot_context, int left_context, const int* context_host,
                          int ntaps, uint16_t* w_hi, uint16_t* w_lo, void* stream);
@@ -116,6 +121,12 @@ typedef struct xvb_tdnn_args {
    * utterance and writes [mean | centred sum of squares] partials, (num_blocks, B, 2*Cout) fp32 with
    * num_blocks = xvb_pool_partial_blocks(B, T, &frames_per_block); merge with xvb_pool_finalize. */
   float* pool_partial;
+  /* 0: utterance b starts at row b*T of the x planes.  Otherwise the element distance between
+   * utterances, and ldx may then be smaller than Cin: row t is the Cin-long window starting at
+   * x[b*x_batch_stride + t*ldx] -- an im2col VIEW of consecutive context taps over a time-padded
+   * frame matrix (ntaps = 1, Cin = taps*channels), so a [-2..2] layer over 80 channels streams 7
+   * channel blocks of 64 instead of 5 x (64 + 16).  Requires x2_* == NULL. */
+  int64_t x_batch_stride;
 } xvb_tdnn_args_t;
 int xvb_tdnn_affine_ex(const xvb_tdnn_args_t* args, void* stream);
 /* Time blocking the fused-pooling epilogue will use for a (B, T) batch. */

@@ -292,3 +292,47 @@ def test_pipelined_host_path_matches():
     with pytest.raises(_lib.XvbError):                      # slot still in flight
         ex.submit_host(feats[1].data_ptr(), 32, 200, outs[1].data_ptr(), 0)
     ex.wait(0)
+
+
+def test_im2col_first_layer_and_split_k_are_equivalent_paths(ops, monkeypatch):
+    """Two shape-driven fast paths of the extractor against their plain forms:
+    (i) the first layer as an im2col view over time-padded planes (7 channel blocks instead of 10 for
+        [-2..2] x 80) keeps the K order, so the embeddings are bit-identical;
+    (ii) split-K of the segment layer (K = 3000) sums slice partials in a fixed order: equal to ~1 ulp."""
+    feats = onn.synthetic_feats(24, 117, 80, 77)
+
+    def run(im2col, splitk, pos="far"):
+        monkeypatch.setenv("XVB_IM2COL", im2col)
+        monkeypatch.setenv("XVB_SPLITK", splitk)
+        m, _ = _model(80, 102, pos)
+        out = m.extract_embedding_batch(feats).cpu().numpy()
+        m.invalidate()
+        return out
+
+    base = run("0", "0")
+    assert np.array_equal(run("1", "0"), base)
+    for pos in ("far", "near"):
+        a, b = run("1", "1", pos), run("0", "0", pos)
+        assert rel(a, b) < 2e-6, pos
+    # ragged tails: T not a multiple of anything, B = 1
+    monkeypatch.setenv("XVB_IM2COL", "1")
+    monkeypatch.setenv("XVB_SPLITK", "1")
+    m, sd = _model(80, 102, "far")
+    for T in (1, 3, 7, 61):
+        f = onn.synthetic_feats(1, T, 80, 500 + T)
+        with torch.no_grad():
+            want = onn.xvector_forward(sd, torch.from_numpy(f).transpose(1, 2), "far").squeeze(2).numpy()
+        assert rel(m.extract_embedding_batch(f).cpu().numpy(), want) < EMB_TOL, T
+
+
+def test_split_frames_pads_with_zero_frames(ops):
+    import ctypes as C
+    from asv_subtools_b200._lib import check, lib
+    x = torch.randn(3, 5, 20, device="cuda")
+    hi = torch.full((3, 9, 24), 7, dtype=torch.bfloat16, device="cuda")
+    lo = torch.full((3, 9, 24), 7, dtype=torch.bfloat16, device="cuda")
+    check(lib.xvb_split_frames(C.c_void_p(x.data_ptr()), 3, 5, 20, C.c_void_p(hi.data_ptr()), C.c_void_p(lo.data_ptr()), 24, 3, 1, None))
+    back = hi.float() + lo.float()
+    assert torch.equal(back[:, :3], torch.zeros(3, 3, 24, device="cuda")) and torch.equal(back[:, 8:], torch.zeros(3, 1, 24, device="cuda"))
+    assert torch.equal(back[:, 3:8, 20:], torch.zeros(3, 5, 4, device="cuda"))
+    assert (back[:, 3:8, :20] - x).abs().max() < 1e-5 * x.abs().max()
