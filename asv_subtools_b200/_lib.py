@@ -81,6 +81,9 @@ SIGNATURES = {
     "xvb_cosine_matrix": (_i, [_p, _i64, _p, _i64, _i, _p, _i64, _p]),
     "xvb_plda_terms": (_i, [_p, _i64, _i, _p, _p, _p, _p]),
     "xvb_plda_matrix": (_i, [_p, _i64, _p, _i64, _i, _p, _p, _p, _p, _i64, _p]),
+    "xvb_matmul_nt": (_i, [_p, _i64, _p, _i64, _i, _p, _p, _p, _i64, _p]),
+    "xvb_center_rows_transposed": (_i, [_p, _p, _p, _p, _i64, _i, _p, _i64, _p]),
+    "xvb_plda_em_rows": (_i, [_p, _p, _p, _p, _i, _i, _p, _p, _i64, _p]),
     "xvb_trial_histogram": (_i, [_p, _i64, _p, _p, _i64, _p, _i, _p, _p, _i, _i, _i, _f, _f, _i, _p, _p]),
     "xvb_extractor_create": (_i, [C.POINTER(_p), _i]),
     "xvb_extractor_add_frame_layer": (_i, [_p, _i, _ip, _i, _p, _p, _p, _p, _i]),

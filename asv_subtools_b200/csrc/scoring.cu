@@ -153,6 +153,62 @@ __global__ void snorm_trials_kernel(const float* __restrict__ s, const int32_t* 
 }
 
 
+// PLDA training helpers (score/pyplda/plda_base.py:50-66, :262-287).  Both write TRANSPOSED (D, N) matrices
+// so that the following Gram product X^T X is an A.B^T GEMM over K-contiguous rows.
+// out[d][i] = sw[spk[i]] * (x[i][d] - mean[spk[i]][d])
+__global__ void center_rows_T_kernel(const float* __restrict__ x, const int32_t* __restrict__ spk,
+                                     const float* __restrict__ means, const float* __restrict__ sw, long long N, int D,
+                                     float* __restrict__ out, long long ldo) {
+  __shared__ float tile[32][33];
+  const long long i0 = (long long)blockIdx.x * 32;
+  const int d0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const long long i = i0 + r;
+    const int d = d0 + threadIdx.x;
+    float v = 0.f;
+    if (i < N && d < D) {
+      const int k = spk[i];
+      v = (x[i * D + d] - means[(long long)k * D + d]) * (sw ? sw[k] : 1.f);
+    }
+    tile[r][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int d = d0 + r;
+    const long long i = i0 + threadIdx.x;
+    if (d < D && i < N) out[(long long)d * ldo + i] = tile[threadIdx.x][r];
+  }
+}
+
+// One EM step's per-class vectors in the basis where within_var = I and between_var = diag(psi):
+//   what = n psi / (1 + n psi) * u ; what_T[d][k] = sqrt(w_k) what ; resid_T[d][k] = sqrt(w_k n_k) (u - what)
+__global__ void plda_em_rows_T_kernel(const float* __restrict__ u, const float* __restrict__ n, const float* __restrict__ w,
+                                      const float* __restrict__ psi, int S, int D, float* __restrict__ what_T,
+                                      float* __restrict__ resid_T, long long ldo) {
+  __shared__ float ta[32][33], tb[32][33];
+  const int k0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int k = k0 + r, d = d0 + threadIdx.x;
+    float a = 0.f, b = 0.f;
+    if (k < S && d < D) {
+      const float nk = n[k], wk = w ? w[k] : 1.f, p = psi[d], uu = u[(long long)k * D + d];
+      const float wh = nk * p / (1.f + nk * p) * uu;
+      a = sqrtf(wk) * wh;
+      b = sqrtf(wk * nk) * (uu - wh);
+    }
+    ta[r][threadIdx.x] = a;
+    tb[r][threadIdx.x] = b;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int d = d0 + r, k = k0 + threadIdx.x;
+    if (d < D && k < S) {
+      what_T[(long long)d * ldo + k] = ta[threadIdx.x][r];
+      resid_T[(long long)d * ldo + k] = tb[threadIdx.x][r];
+    }
+  }
+}
+
 // out (Ne, Nt) = A (Ne, D) . Bm (Nt, D)^T  [+ row_bias[i] + col_bias[j]] through the tcgen05 layer.
 static int matmul_nt(const float* A, int64_t Ne, const float* Bm, int64_t Nt, int D, const float* row_bias,
                      const float* col_bias, float* out, int64_t ldo, uint16_t* out_hi, uint16_t* out_lo,
@@ -353,4 +409,37 @@ extern "C" int xvb_trial_histogram(const float* enroll, int64_t Ne, const int32_
   th.lo = lo; th.inv_w = (float)(nbins - 2) / (hi - lo); th.nbins = nbins; th.symmetric = symmetric ? 1 : 0;
   th.unit_first = unit_first; th.unit_stride = unit_stride;
   return matmul_nt(enroll, Ne, test, Nt, D, row_term, col_term, nullptr, 0, nullptr, nullptr, 0, (cudaStream_t)stream, &th);
+}
+
+// Generic A.B^T (+ row/column terms) on the tcgen05 layer: out (M, N) = a (M, K) . b (N, K)^T + row[i] + col[j].
+extern "C" int xvb_matmul_nt(const float* a, int64_t M, const float* b, int64_t N, int K, const float* row_bias,
+                             const float* col_bias, float* out, int64_t ldo, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  XVB_CHECK_ARG(a && b && out && M > 0 && N > 0 && K > 0, "xvb_matmul_nt: bad arguments");
+  XVB_CHECK_ARG(N % 4 == 0 && ldo % 4 == 0 && ldo >= N, "xvb_matmul_nt: N and ldo must be multiples of 4");
+  XVB_CHECK_ARG(M < (1ll << 31) && N < (1ll << 31), "xvb_matmul_nt: too many rows for one call");
+  return matmul_nt(a, M, b, N, K, row_bias, col_bias, out, ldo, nullptr, nullptr, 0, (cudaStream_t)stream);
+}
+
+extern "C" int xvb_center_rows_transposed(const float* x, const int32_t* spk, const float* means, const float* sqrt_weight,
+                                          int64_t N, int D, float* out, int64_t ldo, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  XVB_CHECK_ARG(x && spk && means && out && N > 0 && D > 0 && ldo >= N, "xvb_center_rows_transposed: bad arguments");
+  dim3 grid((unsigned)((N + 31) / 32), (unsigned)((D + 31) / 32)), block(32, 8);
+  center_rows_T_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, spk, means, sqrt_weight, N, D, out, ldo);
+  XVB_LAUNCH_CHECK();
+  return XVB_OK;
+}
+
+extern "C" int xvb_plda_em_rows(const float* u, const float* n, const float* weight, const float* psi, int S, int D,
+                                float* what_T, float* resid_T, int64_t ldo, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  XVB_CHECK_ARG(u && n && psi && what_T && resid_T && S > 0 && D > 0 && ldo >= S, "xvb_plda_em_rows: bad arguments");
+  dim3 grid((unsigned)((S + 31) / 32), (unsigned)((D + 31) / 32)), block(32, 8);
+  plda_em_rows_T_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(u, n, weight, psi, S, D, what_T, resid_T, ldo);
+  XVB_LAUNCH_CHECK();
+  return XVB_OK;
 }

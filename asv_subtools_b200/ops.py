@@ -345,6 +345,38 @@ def plda_matrix(enroll, test, l2, row, col):
     return s
 
 
+def matmul_nt(a, b, row_bias=None, col_bias=None):
+    """a (M,K) . b (N,K)^T + row_bias[i] + col_bias[j] -> (M,N) fp32 on the tcgen05 layer (N % 4 == 0)."""
+    a = _req(a, torch.float32, "a")
+    b = a if b is a else _req(b, torch.float32, "b")
+    out = torch.empty(a.shape[0], b.shape[0], dtype=torch.float32, device=a.device)
+    check(lib.xvb_matmul_nt(_ptr(a), a.shape[0], _ptr(b), b.shape[0], a.shape[1], _ptr(row_bias), _ptr(col_bias), _ptr(out),
+                            b.shape[0], _stream()), "xvb_matmul_nt")
+    return out
+
+
+def center_rows_transposed(x, spk, means, sqrt_weight=None):
+    """-> (D, N): column i = sqrt_weight[spk[i]] * (x[i] - means[spk[i]])."""
+    x = _req(x, torch.float32, "x")
+    spk = _req(spk, torch.int32, "spk")
+    means = _req(means, torch.float32, "means")
+    out = torch.empty(x.shape[1], x.shape[0], dtype=torch.float32, device=x.device)
+    check(lib.xvb_center_rows_transposed(_ptr(x), _ptr(spk), _ptr(means), _ptr(sqrt_weight), x.shape[0], x.shape[1], _ptr(out),
+                                         x.shape[0], _stream()), "xvb_center_rows_transposed")
+    return out
+
+
+def plda_em_rows(u, n, weight, psi):
+    """-> (what_T, resid_T), both (D, S); see include/xvb200.h."""
+    u = _req(u, torch.float32, "u")
+    s, d = u.shape
+    what = torch.empty(d, s, dtype=torch.float32, device=u.device)
+    resid = torch.empty(d, s, dtype=torch.float32, device=u.device)
+    check(lib.xvb_plda_em_rows(_ptr(u), _ptr(_req(n, torch.float32, "n")), _ptr(weight), _ptr(_req(psi, torch.float32, "psi")),
+                               s, d, _ptr(what), _ptr(resid), s, _stream()), "xvb_plda_em_rows")
+    return what, resid
+
+
 def trial_histogram(enroll, enroll_spk, test, test_spk, lo, hi, nbins=2048, row_term=None, col_term=None,
                     symmetric=False, unit_first=0, unit_stride=1, out=None):
     """(2, nbins) int64 histogram [nontarget | target] of enroll.test^T (+ terms) -- scores are never

@@ -276,6 +276,26 @@ int xvb_plda_terms(const float* x, int64_t rows, int D, const float* gamma, cons
 int xvb_plda_matrix(const float* enroll, int64_t Ne, const float* test, int64_t Nt, int D, const float* L2,
                     const float* row, const float* col, float* S, int64_t lds, void* stream);
 
+/* out (M, N) = a (M, K) . b (N, K)^T + row_bias[i] + col_bias[j] (biases may be NULL), fp32 row-major in
+ * and out, N % 4 == 0: the general form behind xvb_project / xvb_cosine_matrix / xvb_plda_matrix. */
+int xvb_matmul_nt(const float* a, int64_t M, const float* b, int64_t N, int K, const float* row_bias,
+                  const float* col_bias, float* out, int64_t ldo, void* stream);
+
+/* PLDA training on the GPU (score/pyplda/plda_base.py: PldaStats.add_samples :50-66, PldaEstimation
+ * .get_stats_from_class_mean :262-287).  The D x D algebra (Cholesky, eigh, inverses) stays on the host in
+ * float64; the O(N D^2) parts are Gram products X^T X, computed as xvb_matmul_nt(X^T, X^T) on transposed
+ * operands these two kernels emit:
+ *   xvb_center_rows_transposed: out[d][i] = sqrt_weight[spk[i]] * (x[i][d] - means[spk[i]][d])   (D, ldo >= N)
+ *     -> offset_scatter = out . out^T  (the weighted within-class scatter, without the cancellation of
+ *        sum x x^T - n m m^T);
+ *   xvb_plda_em_rows: per class k, in the basis where within_var = I and between_var = diag(psi),
+ *     what = n psi/(1 + n psi) * u;  what_T[d][k] = sqrt(w_k) what;  resid_T[d][k] = sqrt(w_k n_k) (u - what)
+ *     -> the rank-one sums of one EM iteration are what_T . what_T^T and resid_T . resid_T^T. */
+int xvb_center_rows_transposed(const float* x, const int32_t* spk, const float* means, const float* sqrt_weight,
+                               int64_t N, int D, float* out, int64_t ldo, void* stream);
+int xvb_plda_em_rows(const float* u, const float* n, const float* weight, const float* psi, int S, int D, float* what_T,
+                     float* resid_T, int64_t ldo, void* stream);
+
 /* Fused consumer for score matrices too large to store (BASELINE configs 4/5: 10^12 cosine trials,
  * 10^10 PLDA trials; SURVEY Appendix A "fused consumer"): every score
  *   s(i,j) = <enroll[i], test[j]> + row_term[i] + col_term[j]        (terms may be NULL)

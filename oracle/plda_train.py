@@ -1,0 +1,97 @@
+"""Oracle (NumPy float64) restatement of the reference's PLDA training.  TEST INFRASTRUCTURE ONLY.
+
+  plda_stats      : PldaStats.add_samples, score/pyplda/plda_base.py:50-66 (per class: n, mean, weighted
+                    scatter about the class mean; classes sorted by n as PldaEstimation requires, :68-81,:233-236)
+  plda_estimate   : PldaEstimation.estimate / estimate_one_iter, :248-300 -- the literal per-class loop with one
+                    D x D inverse per class
+  plda_estimate_grouped : the same EM step written the way the GPU path computes it -- in the basis that
+                    makes within_var the identity and between_var diagonal (get_output's transform, :302-335)
+                    every per-class matrix is diagonal and depends on n only; used to check the algebra.
+Pinned by tests/golden/plda_train.npz, produced by the imported reference (tests/golden/make_golden_plda.py)."""
+import numpy as np
+
+
+def plda_stats(emb, spk, weights=None):
+    """emb (N, D), spk (N,) int labels -> dict(n (S,), mean (S, D), weight (S,), offset_scatter (D, D), sum (D,),
+    class_weight, example_weight), classes in ascending order of n (stable), as the reference sorts them."""
+    emb = np.asarray(emb, dtype=np.float64)
+    ids = np.unique(spk)
+    groups = [emb[spk == s] for s in ids]
+    w = np.ones(len(ids)) if weights is None else np.asarray(weights, dtype=np.float64)
+    order = np.argsort([g.shape[0] for g in groups], kind="stable")
+    groups = [groups[i] for i in order]
+    w = w[order]
+    D = emb.shape[1]
+    scatter, total = np.zeros((D, D)), np.zeros(D)
+    n, means = [], []
+    for g, wk in zip(groups, w):
+        m = g.mean(axis=0)
+        scatter += wk * (g.T @ g) - g.shape[0] * wk * np.outer(m, m)
+        total += wk * m
+        n.append(g.shape[0])
+        means.append(m)
+    n = np.asarray(n, dtype=np.float64)
+    return dict(n=n, mean=np.asarray(means), weight=w, offset_scatter=scatter, sum=total, class_weight=float(w.sum()),
+                example_weight=float((w * n).sum()))
+
+
+def plda_estimate(stats, num_em_iters=10):
+    """-> (mean (D,), within_var, between_var), the three vectors plda_write stores (:337-342)."""
+    D = stats["mean"].shape[1]
+    within, between = np.eye(D), np.eye(D)
+    gmean = stats["sum"] / stats["class_weight"]
+    for _ in range(num_em_iters):
+        w_stats = stats["offset_scatter"].copy()
+        w_count = stats["example_weight"] - stats["class_weight"]
+        b_stats, b_count = np.zeros((D, D)), 0.0
+        w_inv, b_inv = np.linalg.inv(within), np.linalg.inv(between)
+        for n, mk, wk in zip(stats["n"], stats["mean"], stats["weight"]):
+            mix = np.linalg.inv(b_inv + n * w_inv)
+            m = mk - gmean
+            w = mix @ (n * (w_inv @ m))
+            r = m - w
+            b_stats += wk * mix + wk * np.outer(w, w)
+            b_count += wk
+            w_stats += wk * n * mix + wk * n * np.outer(r, r)
+            w_count += wk
+        within, between = w_stats / w_count, b_stats / b_count
+    return gmean, within, between
+
+
+def diagonalising_transform(within, between):
+    """T with T W T^T = I and T B T^T = diag(psi)  (compute_normalizing_transform + eigh, :302-335)."""
+    t1 = np.linalg.inv(np.linalg.cholesky(within))
+    psi, u = np.linalg.eigh(t1 @ between @ t1.T)
+    return u.T @ t1, psi
+
+
+def plda_estimate_grouped(stats, num_em_iters=10):
+    D = stats["mean"].shape[1]
+    within, between = np.eye(D), np.eye(D)
+    gmean = stats["sum"] / stats["class_weight"]
+    mc = stats["mean"] - gmean
+    n, wk = stats["n"], stats["weight"]
+    for _ in range(num_em_iters):
+        t, psi = diagonalising_transform(within, between)
+        tinv = np.linalg.inv(t)
+        u = mc @ t.T                                         # class means in the diagonal basis
+        mixd = psi[None, :] / (1.0 + n[:, None] * psi[None, :])   # diag of (B^-1 + n W^-1)^-1 there
+        what = n[:, None] * mixd * u
+        r = u - what
+        b_t = np.diag((wk[:, None] * mixd).sum(0)) + (what * wk[:, None]).T @ what
+        w_t = np.diag((wk[:, None] * n[:, None] * mixd).sum(0)) + (r * (wk * n)[:, None]).T @ r
+        between = tinv @ b_t @ tinv.T / wk.sum()
+        within = (tinv @ w_t @ tinv.T + stats["offset_scatter"]) / (stats["example_weight"] - stats["class_weight"] + wk.sum())
+    return gmean, within, between
+
+
+def synthetic_plda_data(num_spk, dim, seed, min_utts=3, max_utts=9):
+    rng = np.random.RandomState(seed)
+    a = rng.standard_normal((dim, dim)) / np.sqrt(dim)
+    b = rng.standard_normal((dim, dim)) / np.sqrt(dim)
+    counts = rng.randint(min_utts, max_utts + 1, num_spk)
+    spk = np.repeat(np.arange(num_spk), counts)
+    centres = rng.standard_normal((num_spk, dim)) @ b.T * 1.5 + 0.3
+    emb = centres[spk] + rng.standard_normal((spk.shape[0], dim)) @ a.T
+    perm = rng.permutation(spk.shape[0])
+    return emb[perm].astype(np.float32), spk[perm].astype(np.int32)

@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""Golden PLDA-training fixture from the REFERENCE's own score/pyplda/plda_base.py (PldaStats,
+PldaEstimation) -- build container only:   python tests/golden/make_golden_plda.py
+
+plda_base.py imports a misspelt `scipye` and the pip package `kaldi_io`: both are stubbed
+(the latter aliased to the reference's own libs/support/kaldi_io.py).  Inputs are the seeded
+oracle.plda_train.synthetic_plda_data sets, so only the outputs are stored: tests/golden/plda_train.npz."""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import plda_train as opt  # noqa: E402
+
+CASES = {"d16": (40, 16, 5), "d24w": (25, 24, 6)}
+
+
+def main():
+    sys.modules["scipye"] = types.ModuleType("scipye")
+    sys.path.insert(0, "/root/reference/pytorch")
+    import libs.support.kaldi_io as kio
+    sys.modules["kaldi_io"] = kio
+    spec = importlib.util.spec_from_file_location("plda_base", "/root/reference/score/pyplda/plda_base.py")
+    pb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pb)
+    out = {}
+    for name, (ns, dim, seed) in CASES.items():
+        emb, spk = opt.synthetic_plda_data(ns, dim, seed)
+        weights = None if not name.endswith("w") else np.random.RandomState(seed).uniform(0.5, 2.0, ns)
+        stats = pb.PldaStats(dim)
+        for i, s in enumerate(np.unique(spk)):
+            stats.add_samples(1.0 if weights is None else float(weights[i]), emb[spk == s].astype(np.float64))
+        stats.sort()
+        est = pb.PldaEstimation(stats)
+        est.estimate(num_em_iters=10)
+        out[name + "_mean"] = np.asarray(est.mean).reshape(-1)
+        out[name + "_within"] = est.within_var
+        out[name + "_between"] = est.between_var
+        out[name + "_scatter"] = stats.offset_scatter
+        plda = est.get_output()
+        out[name + "_psi"] = np.asarray(plda.psi)
+    np.savez_compressed(os.path.join(HERE, "plda_train.npz"), **out)
+    print("plda_train.npz ok", {k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,68 @@
+"""GPU PLDA training (score/plda_train.py: Gram products on the tcgen05 kernel, D x D algebra in float64
+on the host) against the reference's own PldaEstimation outputs (tests/golden/plda_train.npz) and the
+float64 oracle."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import plda_train as opt
+from oracle import scoring as osc
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def rel(a, b):
+    return float(np.max(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64))) / max(np.max(np.abs(b)), 1e-30))
+
+
+def test_gpu_plda_training_matches_reference_golden(golden):
+    from asv_subtools_b200.score.plda_train import PldaEstimation, PldaStats
+    spec = importlib.util.spec_from_file_location("mgp", os.path.join(HERE, "golden", "make_golden_plda.py"))
+    mgp = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mgp)
+    g = golden("plda_train")
+    for name, (ns, dim, seed) in mgp.CASES.items():
+        emb, spk = opt.synthetic_plda_data(ns, dim, seed)
+        weights = None if not name.endswith("w") else np.random.RandomState(seed).uniform(0.5, 2.0, ns)
+        # (i) the reference's call pattern: one add_samples per class
+        stats = PldaStats(dim)
+        for i, s in enumerate(np.unique(spk)):
+            stats.add_samples(1.0 if weights is None else float(weights[i]), emb[spk == s])
+        stats.sort()
+        est = PldaEstimation(stats).estimate(num_em_iters=10)
+        assert rel(est.stats.offset_scatter, g[name + "_scatter"]) < 2e-6
+        assert rel(est.mean, g[name + "_mean"]) < 1e-6
+        assert rel(est.within_var, g[name + "_within"]) < 1e-5, name
+        assert rel(est.between_var, g[name + "_between"]) < 1e-5, name
+        # (ii) whole matrix at once
+        est2 = PldaEstimation(PldaStats.from_matrix(emb, spk, weights)).estimate(10)
+        assert rel(est2.within_var, g[name + "_within"]) < 1e-5 and rel(est2.between_var, g[name + "_between"]) < 1e-5
+
+
+def test_gpu_plda_training_larger_set_then_scoring_eer(tmp_path):
+    from asv_subtools_b200 import kaldi_io
+    from asv_subtools_b200.score import metrics
+    from asv_subtools_b200.score.backend import PldaModel
+    from asv_subtools_b200.score.plda_train import PldaEstimation, PldaStats
+    emb, spk = opt.synthetic_plda_data(600, 64, 17, min_utts=2, max_utts=12)
+    est = PldaEstimation(PldaStats.from_matrix(torch.from_numpy(emb).cuda(), spk)).estimate(10)
+    mean, within, between = opt.plda_estimate(opt.plda_stats(emb, spk), 10)
+    assert rel(est.within_var, within) < 1e-5 and rel(est.between_var, between) < 1e-5 and rel(est.mean, mean) < 1e-6
+    path = str(tmp_path / "plda")
+    est.plda_write(path)
+    parts = dict(kaldi_io.read_vec_flt_ark(path))
+    assert list(parts) == ["mean", "within_var", "between_var"] and parts["within_var"].shape == (64 * 64,)
+    # score held-out trials with the GPU-trained and with the oracle-trained model: same EER to 3 decimals
+    test_emb, test_spk = opt.synthetic_plda_data(60, 64, 18, min_utts=6, max_utts=6)
+    e, t = torch.from_numpy(test_emb[:180]).cuda(), torch.from_numpy(test_emb[180:]).cuda()
+    lab = (test_spk[:180, None] == test_spk[None, 180:]).ravel()
+    s_gpu = est.model().score_matrix(e, t).cpu().numpy().ravel()
+    s_ora = PldaModel(mean, within, between).score_matrix(e, t).cpu().numpy().ravel()
+    assert round(metrics.eer_det(s_gpu, lab)[0] * 100, 3) == round(metrics.eer_det(s_ora, lab)[0] * 100, 3)
+    G, L, c, k = osc.plda_calculate_var(between, osc.plda_smooth_within(within), mean.reshape(-1, 1))
+    want = osc.plda_score_matrix(test_emb[:180], test_emb[180:], G, L, c, k).ravel()
+    assert np.max(np.abs(s_gpu - want)) / np.max(np.abs(want)) < 1e-4

@@ -182,3 +182,27 @@ def test_kaldi_fbank_mfcc_oracle_matches_reference_kaldifeature(golden):
             assert np.max(np.abs(got - ref)) < tol, (key, np.max(np.abs(got - ref)))
             seen += 1
     assert seen >= 16
+
+
+def test_plda_training_oracle_matches_reference(golden):
+    """oracle.plda_train vs the reference's PldaStats / PldaEstimation (10 EM iterations), and the
+    diagonal-basis form of the EM step (what the GPU path computes) vs the literal per-class loop."""
+    import importlib.util
+    import os
+    from oracle import plda_train as opt
+    spec = importlib.util.spec_from_file_location("mgp", os.path.join(os.path.dirname(__file__), "golden", "make_golden_plda.py"))
+    mgp = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mgp)
+    g = golden("plda_train")
+    for name, (ns, dim, seed) in mgp.CASES.items():
+        emb, spk = opt.synthetic_plda_data(ns, dim, seed)
+        weights = None if not name.endswith("w") else np.random.RandomState(seed).uniform(0.5, 2.0, ns)
+        st = opt.plda_stats(emb, spk, weights)
+        assert rel(st["offset_scatter"], g[name + "_scatter"]) < 1e-12
+        mean, within, between = opt.plda_estimate(st, 10)
+        assert rel(mean, g[name + "_mean"]) < 1e-12 and rel(within, g[name + "_within"]) < 1e-10
+        assert rel(between, g[name + "_between"]) < 1e-10
+        _, w2, b2 = opt.plda_estimate_grouped(st, 10)
+        assert rel(w2, within) < 1e-9 and rel(b2, between) < 1e-9
+        _, psi = opt.diagonalising_transform(within, between)
+        assert rel(np.sort(psi), np.sort(g[name + "_psi"])) < 1e-9
