@@ -98,7 +98,8 @@ int read_key(FILE* f, std::string* key) {
 }
 
 // One matrix (binary FM/DM/CM or ascii) at the current position -> fp32 row-major.
-bool read_matrix(FILE* f, std::vector<float>* out, int* rows, int* cols, std::vector<uint8_t>* scratch) {
+bool read_matrix(FILE* f, std::vector<float>* out, int* rows, int* cols, std::vector<uint8_t>* scratch, bool* was_double = nullptr) {
+  if (was_double) *was_double = false;
   char flag[2];
   if (!read_exact(f, flag, 2)) return false;
   if (flag[0] == '\0' && flag[1] == 'B') {
@@ -137,6 +138,7 @@ bool read_matrix(FILE* f, std::vector<float>* out, int* rows, int* cols, std::ve
     }
     if (tok[0] == 'C' && tok[1] == 'M') { set_error("ark: compressed format 'CM%c' is not supported (CM2/CM3)", tok[2]); return false; }
     const bool dbl = tok[0] == 'D';
+    if (was_double) *was_double = dbl;
     if (!((tok[0] == 'F' || dbl) && tok[1] == 'M' && tok[2] == ' ')) { set_error("ark: unknown matrix header '%c%c%c'", tok[0], tok[1], tok[2]); return false; }
     int32_t r, c;
     if (!read_dim(f, &r) || !read_dim(f, &c)) return false;
@@ -226,10 +228,11 @@ extern "C" int xvb_ark_reader_open(xvb_ark_reader_t** out, const char* rspecifie
 
 extern "C" int xvb_ark_reader_next(xvb_ark_reader_t* r, const char** key, int* rows, int* cols, const float** data) {
   if (!r || !key || !rows || !cols || !data) { set_error("xvb_ark_reader_next: null argument"); return XVB_EINVAL; }
+  bool dbl = false;
   if (!r->scp) {
     const int k = read_key(r->in.f, &r->key);
     if (k == 0) return 0;
-    if (k < 0 || !read_matrix(r->in.f, &r->data, rows, cols, &r->scratch)) return XVB_EINVAL;
+    if (k < 0 || !read_matrix(r->in.f, &r->data, rows, cols, &r->scratch, &dbl)) return XVB_EINVAL;
   } else {
     char* line = nullptr;
     size_t cap = 0;
@@ -245,13 +248,13 @@ extern "C" int xvb_ark_reader_next(xvb_ark_reader_t* r, const char** key, int* r
     r->key = l.substr(0, sp);
     Stream st;
     if (!open_stream(l.substr(sp + 1), true, &st)) return XVB_EINVAL;
-    const bool ok = read_matrix(st.f, &r->data, rows, cols, &r->scratch);
+    const bool ok = read_matrix(st.f, &r->data, rows, cols, &r->scratch, &dbl);
     st.close();
     if (!ok) return XVB_EINVAL;
   }
   *key = r->key.c_str();
   *data = r->data.data();
-  return 1;
+  return dbl ? 2 : 1;   // 2: stored as a double ('DM ') matrix, converted
 }
 
 extern "C" void xvb_ark_reader_close(xvb_ark_reader_t* r) {

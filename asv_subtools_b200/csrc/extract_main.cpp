@@ -264,7 +264,8 @@ int main(int argc, char** argv) {
   int rows, cols, rc;
   const float* data;
   std::vector<float> normed;
-  while ((rc = next_utt(&key, &rows, &cols, &data)) == 1) {
+  while ((rc = next_utt(&key, &rows, &cols, &data)) >= 1) {
+    if (rc == 2) { fprintf(stderr, "ERROR: xvb-extract: %s is a double-precision matrix; the extractor takes float32 (FM/CM) features\n", key); return 1; }
     fprintf(to_stdout ? stderr : stdout, "Process utterance for key %s\n", key);   // extract_embeddings.py:81
     if (cols != r.F) { fprintf(stderr, "ERROR: xvb-extract: %s has %d-dim features, the model expects %d\n", key, cols, r.F); return 1; }
     if (rows < 1) { fprintf(stderr, "ERROR: xvb-extract: %s has no frames\n", key); return 1; }

@@ -303,7 +303,8 @@ def write_vec_ark_scp(ark_path, scp_path, items):
 def read_mat_ark_native(rspecifier):
     """Same stream of (key, float32 matrix) as read_mat_ark / read_mat_scp, decoded by the C library
     (csrc/ark_io.cpp: whole-matrix freads instead of the reference's byte-at-a-time key loop,
-    kaldi_io.py:148-163).  DM matrices arrive converted to float32."""
+    kaldi_io.py:148-163).  'DM ' matrices come back as float64 like from read_mat (values rounded through
+    float32 by the C reader)."""
     import ctypes as C
     from ._lib import lib, last_error
     h = C.c_void_p()
@@ -320,7 +321,7 @@ def read_mat_ark_native(rspecifier):
             n = rows.value * cols.value
             m = np.ctypeslib.as_array(data, shape=(n,)).copy().reshape(rows.value, cols.value) if n else \
                 np.zeros((rows.value, cols.value), dtype=np.float32)
-            yield key.value.decode("latin1"), m
+            yield key.value.decode("latin1"), (m.astype(np.float64) if rc == 2 else m)
     finally:
         lib.xvb_ark_reader_close(h)
 

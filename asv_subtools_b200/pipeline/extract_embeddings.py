@@ -133,9 +133,10 @@ def main(argv=None):
         torch.cuda.set_device(int(args.gpu_id.split(",")[0]) if args.gpu_id != "" else 0)
         model.cuda().eval()
         i, n = (int(v) for v in args.shard.split("/"))
-        with kaldi_io.open_or_fd(args.feats_rspecifier, "rb") as r, kaldi_io.open_or_fd(args.vectors_wspecifier, "wb") as w:
-            extract_stream(model, kaldi_io.read_mat_ark(r), lambda k, v: kaldi_io.write_vec_flt(w, v, key=k),
-                           batch_size=args.batch_size, shard=(i, n))
+        # native ark reader (csrc/ark_io.cpp): the reference's byte-at-a-time key loop is the wall at GPU rates
+        with kaldi_io.open_or_fd(args.vectors_wspecifier, "wb") as w:
+            extract_stream(model, kaldi_io.read_mat_ark_native(args.feats_rspecifier),
+                           lambda k, v: kaldi_io.write_vec_flt(w, v, key=k), batch_size=args.batch_size, shard=(i, n))
     except BaseException as err:
         if not isinstance(err, KeyboardInterrupt):
             traceback.print_exc()

@@ -410,8 +410,9 @@ typedef struct xvb_ark_reader xvb_ark_reader_t;
 typedef struct xvb_ark_writer xvb_ark_writer_t;
 int xvb_ark_reader_open(xvb_ark_reader_t** out, const char* rspecifier);
 /* Next matrix as fp32 row-major (DM is converted, CM decoded with the reference's fp32 steps).
- * Returns 1 and fills the outputs (owned by the reader, valid until the next call), 0 at the end
- * of the stream, a negative XVB_E* code on malformed input. */
+ * Returns 1 (2 if the matrix was stored in double precision, which the reference's extractor rejects,
+ * SURVEY Appendix B.1) and fills the outputs (owned by the reader, valid until the next call), 0 at the
+ * end of the stream, a negative XVB_E* code on malformed input. */
 int xvb_ark_reader_next(xvb_ark_reader_t* r, const char** key, int* rows, int* cols, const float** data);
 void xvb_ark_reader_close(xvb_ark_reader_t* r);
 int xvb_ark_writer_open(xvb_ark_writer_t** out, const char* wspecifier);

@@ -129,3 +129,42 @@ def test_xvb_extract_wav_scp_mode_matches_oracle_chain(tmp_path):
     run = subprocess.run([BIN, "--wav", "fbank", "--num-mel-bins", "40", model, str(scp), "ark:" + out_ark],
                          capture_output=True, text=True, timeout=120)
     assert run.returncode == 1 and "ERROR" in run.stderr
+
+
+@pytest.mark.gpu
+def test_online_cli_wav_scp_matches_oracle_chain(tmp_path):
+    """python -m asv_subtools_b200.pipeline.extract_embeddings_online: nnet.config + feat_conf.yaml + wav.scp."""
+    import sys
+    import wave as wavmod
+    import yaml
+    _, sd = _model(80, 102, "far")
+    torch.save(sd, str(tmp_path / "final.params"))
+    blueprint = os.path.join(ROOT, "asv_subtools_b200", "model", "xvector.py")
+    (tmp_path / "nnet.config").write_text('model_blueprint;{}\nmodel_creation;Xvector(80,10,training=False,extracted_embedding="far")\n'.format(blueprint))
+    conf = dict(feature_type="fbank", kaldi_featset=dict(dither=0.0, energy_floor=0.0, frame_length=25, frame_shift=10, high_freq=-200,
+                                                         low_freq=40, num_mel_bins=80, use_energy=False),
+                mean_var_conf=dict(mean_norm=True, std_norm=False))
+    (tmp_path / "feat_conf.yaml").write_text(yaml.safe_dump(conf))
+    waves = {}
+    with open(tmp_path / "wav.scp", "w") as f:
+        for i, n in enumerate([16000, 16000, 9000]):
+            pcm = np.clip(np.round(ofe.synthetic_wave(n, 800 + i)), -32768, 32767).astype(np.int16)
+            path = tmp_path / "o{}.wav".format(i)
+            with wavmod.open(str(path), "wb") as w:
+                w.setnchannels(1)
+                w.setsampwidth(2)
+                w.setframerate(16000)
+                w.writeframes(pcm.tobytes())
+            waves["o{}".format(i)] = pcm.astype(np.float32)
+            f.write("o{} {}\n".format(i, path))
+    out = str(tmp_path / "xv.ark")
+    run = subprocess.run([sys.executable, "-m", "asv_subtools_b200.pipeline.extract_embeddings_online", "--nnet-config",
+                          str(tmp_path / "nnet.config"), "--feat-config", str(tmp_path / "feat_conf.yaml"),
+                          str(tmp_path / "final.params"), str(tmp_path / "wav.scp"), "ark:" + out],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert run.returncode == 0 and "RTF:" in run.stdout, run.stdout + run.stderr
+    got = dict(kaldi_io.read_vec_flt_ark(out))
+    fwd = lambda x: onn.xvector_forward(sd, x, "far")
+    for k, wv in waves.items():
+        feats = ofe.sequence_normalize(ofe.kaldi_fbank(wv, **conf["kaldi_featset"])).astype(np.float32)
+        assert rel(got[k], onn.extract_embedding(fwd, feats).numpy()) < 1e-4, k

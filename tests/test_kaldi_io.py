@@ -103,8 +103,8 @@ def test_native_reader_matches_python_reader_bit_for_bit(golden, tmp_path):
         nat = list(kaldi_io.read_mat_ark_native(spec))
         assert [k for k, _ in nat] == [k for k, _ in py] == ["utt-a", "utt_b", "cmutt", "cm2", "txt", "empty"]
         for (k, a), (_, b) in zip(nat, py):
-            assert a.dtype == np.float32 and a.shape == b.shape, k
-            assert np.array_equal(a, b.astype(np.float32)), k          # incl. the CM decode: same fp32 steps
+            assert a.dtype == b.dtype and a.shape == b.shape, k      # 'DM ' stays float64 like read_mat
+            assert np.array_equal(a.astype(np.float32), b.astype(np.float32)), k   # incl. the CM decode: same fp32 steps
     assert np.array_equal(dict(py)["cmutt"], g["ark_cm_decoded"]) or np.allclose(dict(py)["cmutt"], g["ark_cm_decoded"], rtol=1e-6)
     # scp with byte offsets and a pipe entry
     offs, pos = {}, 0
