@@ -194,6 +194,10 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
   // prefetch) may overlap the tail of the previous kernel in the stream; its results are needed from here on.
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  // the previous kernel may have written our operands with ordinary (generic-proxy) stores -- the staging
+  // / pooling kernels do -- while we read them through TMA (async proxy): order the two proxies explicitly,
+  // a kernel boundary would have done it for us
+  asm volatile("fence.proxy.async;" ::: "memory");
 
   const int num_kblk = p.num_src * p.ntaps * p.num_cblk;
 
@@ -769,6 +773,11 @@ static int gemm_store_mode() {
 
 // Pick the (Tb, Bb) factorisation of the 128-row M tile with the fewest padded rows.
 static void choose_m_tile(int B, int T, int* Tb_out, int* Bb_out, int max_tb = 128) {
+  if (T == 1) {   // segment-level layers: one row per utterance.  (Also what split-K's "slice as time" store
+    *Tb_out = 1;  // relies on: a box taller than one frame would spill zeros into the next slices' rows.)
+    *Bb_out = 128;
+    return;
+  }
   long long best = -1;
   int bt = max_tb;
   for (int Tb = max_tb; Tb >= 1; Tb >>= 1) {
