@@ -85,13 +85,13 @@ def plda_estimate_grouped(stats, num_em_iters=10):
     return gmean, within, between
 
 
-def synthetic_plda_data(num_spk, dim, seed, min_utts=3, max_utts=9):
+def synthetic_plda_data(num_spk, dim, seed, min_utts=3, max_utts=9, spread=1.5):
     rng = np.random.RandomState(seed)
     a = rng.standard_normal((dim, dim)) / np.sqrt(dim)
     b = rng.standard_normal((dim, dim)) / np.sqrt(dim)
     counts = rng.randint(min_utts, max_utts + 1, num_spk)
     spk = np.repeat(np.arange(num_spk), counts)
-    centres = rng.standard_normal((num_spk, dim)) @ b.T * 1.5 + 0.3
+    centres = rng.standard_normal((num_spk, dim)) @ b.T * spread + 0.3
     emb = centres[spk] + rng.standard_normal((spk.shape[0], dim)) @ a.T
     perm = rng.permutation(spk.shape[0])
     return emb[perm].astype(np.float32), spk[perm].astype(np.int32)
