@@ -4,6 +4,7 @@
 TAG=${1:-r01}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_gpu.txt
+timeout 600 python tools/bench_scoring.py > gpurun_out/${TAG}_scoring_bench.json 2> gpurun_out/${TAG}_scoring_bench.err; echo "scoring bench rc=$?"; tail -c 1500 gpurun_out/${TAG}_scoring_bench.json
 for MODE in ${MODES:-2}; do
   XVB_GEMM_CTA=$MODE timeout 900 python -m pytest tests -m gpu -q > gpurun_out/${TAG}_pytest_gpu_cta$MODE.log 2>&1; echo "pytest(cta=$MODE) rc=$?"
   tail -12 gpurun_out/${TAG}_pytest_gpu_cta$MODE.log
@@ -25,5 +26,6 @@ if [ -z "$2" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 64 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 4 --warmup 3 > gpurun_out/${TAG}_ncu_bench.log 2>&1; echo "ncu launches rc=$?"
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:tdnn_gemm -s 12 -c 6 -o gpurun_out/${TAG}_gemm python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:stats_pool -s 2 -c 1 -o gpurun_out/${TAG}_pool python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_ncu_pool.log 2>&1; echo "ncu pool rc=$?"
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:tdnn_gemm -c 2 -o gpurun_out/${TAG}_hist python tools/hist_once.py > gpurun_out/${TAG}_ncu_hist.log 2>&1; echo "ncu hist rc=$?"
 fi
 ls -la gpurun_out | tail -24
