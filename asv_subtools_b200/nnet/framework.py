@@ -130,10 +130,11 @@ class TopVirtualNnet(torch.nn.Module):
 def build_tdnn_extractor(model, inputs_dim, frame_layers, stats, tdnn6, tdnn7, extracted_embedding):
     """Hand a TDNN x-vector family model (frame-level ReluBatchNormTdnnLayers -> StatisticsPooling ->
     tdnn6 [-> tdnn7]) to the native extractor: weights exactly as stored in the state_dict, eval
-    BatchNorm folded to (scale, shift).  "far" = tdnn6.affine, "near" = tdnn6 (full) -> tdnn7.affine
-    (pytorch/model/xvector.py:92-96, extended_xvector.py:112-116)."""
+    BatchNorm folded to (scale, shift).  "far" = tdnn6.affine, "near" / "near_affine" = tdnn6 (full) ->
+    tdnn7.affine (pytorch/model/xvector.py:92-96, extended_xvector.py:112-116), "near_full" = tdnn6 -> tdnn7 with
+    its ReLU and BatchNorm (what snowdar_xvector.py calls "near", :291-294)."""
     from .. import ops
-    if extracted_embedding not in ("far", "near"):
+    if extracted_embedding not in ("far", "near", "near_affine", "near_full"):
         raise TypeError("Expected far or near position, but got {}".format(extracted_embedding))
     model.device_for_extraction()
     ex = ops.Extractor(inputs_dim)
@@ -152,7 +153,10 @@ def build_tdnn_extractor(model, inputs_dim, frame_layers, stats, tdnn6, tdnn7, e
         ex.add_segment_layer(w, b)
     else:
         ex.add_segment_layer(w, b, scale, shift, relu=tdnn6.relu)
-        w7, b7, _, _ = arrays(tdnn7)
-        ex.add_segment_layer(w7, b7)
+        w7, b7, s7, t7 = arrays(tdnn7)
+        if extracted_embedding == "near_full":     # the whole last layer (snowdar_xvector.py:291-294)
+            ex.add_segment_layer(w7, b7, s7, t7, relu=tdnn7.relu)
+        else:
+            ex.add_segment_layer(w7, b7)
     ex.finalize(pooling_eps=stats.eps)
     return ex

@@ -40,8 +40,8 @@ GEMM_FLOP_PER_STEP = FLOP_PER_FRAME * B * T
 POOL_BYTES_PER_STEP = 1212000 * B  # 4*(C*T + 2C) B/utt, C=1500, T=200
 NUM_INPUT_BATCHES = 8             # rotate 8 x 16.4 MB inputs; activations per step ~1.1 GB >> 126 MB L2
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
-NCU_GEMM_TRAFFIC_BYTES_PER_LAUNCH = int((68.7 + 174.9 + 174.2 + 162.7 + 155.4 + 9.3) * 1e6 / 6)  # profiles/r01p_gemm_ncu_summary.txt
-NCU_POOL_TRAFFIC_BYTES_PER_LAUNCH = int((307.2 + 8.3) * 1e6)
+NCU_GEMM_TRAFFIC_BYTES_PER_LAUNCH = int((69.3 + 173.6 + 177.3 + 163.6 + 155.4 + 9.3) * 1e6 / 6)  # profiles/r01x_gemm_ncu_summary.txt
+NCU_POOL_TRAFFIC_BYTES_PER_LAUNCH = int((307.2 + 5.8) * 1e6)   # profiles/r01x_pool_ncu_summary.txt
 METRIC = "frames/sec x-vector extraction (80-d fbank)"
 UNIT = "frames/s"
 
@@ -356,10 +356,10 @@ def run_native(args, rank, world, local_rank):
                 "frames/s the host->device link alone allows at 320 B/frame (fp32 80-d features) per GPU"},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "tdnn_gemm_bf16x3_kernel (6 launches/step; tdnn5 pools over time in its epilogue)",
+        "roofline": {"bound": "tensor", "kernel": "tdnn_gemm_bf16x3_kernel (6 launches/step; tdnn5 pools over time in its epilogue, tdnn6 is split-K + a reduce)",
                      "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / pk["bf16_sustained"], "traffic": NCU_GEMM_TRAFFIC_BYTES_PER_LAUNCH,
-                     "traffic_unit": "bytes/launch (dram read+write, mean of the 6 launches, profiles/r01p_gemm_ncu_summary.txt)",
+                     "traffic_unit": "bytes/launch (dram read+write, mean of the 6 launches, profiles/r01x_gemm_ncu_summary.txt)",
                      "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)",
                      "algorithmic_flop_per_launch_avg": GEMM_FLOP_PER_STEP / 6,
                      "executed_tflops": 3 * achieved, "executed_frac": 3 * achieved / pk["bf16_sustained"],
@@ -370,7 +370,7 @@ def run_native(args, rank, world, local_rank):
                                 "achieved": pool_gbs,
                                 "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": pool_gbs / pk["hbm_gbs"],
                                 "traffic": NCU_POOL_TRAFFIC_BYTES_PER_LAUNCH,
-                                "traffic_unit": "bytes/launch (profiles/r01p_pool_ncu_summary.txt); algorithmic 310.3 MB",
+                                "traffic_unit": "bytes/launch (profiles/r01x_pool_ncu_summary.txt); algorithmic 310.3 MB",
                                 "ms": pool_ms, "peak_source": pk["src"]},
         "kernel_ms": {n: float(v) for n, v in zip(names, per)},
     }

@@ -139,6 +139,47 @@ def extended_xvector_spec(inputs_dim):
 
 
 # --------------------------------------------------------------------------------------
+# Snowdar x-vector (pytorch/model/snowdar_xvector.py), the TDNN options: extend, tdnn_layer_params
+# (default BatchNorm affine=False), positions far / near_affine / near
+# --------------------------------------------------------------------------------------
+def snowdar_layers(extend):
+    """Module order of Xvector.extract_embedding, snowdar_xvector.py:262-283 (SE / skip connection off)."""
+    if not extend:
+        return XVECTOR_LAYERS
+    return [("tdnn1", [-2, -1, 0, 1, 2]), ("ex_tdnn1", [0]), ("tdnn2", [-2, 0, 2]), ("ex_tdnn2", [0]), ("tdnn3", [-3, 0, 3]),
+            ("ex_tdnn3", [0]), ("ex_tdnn4", [-4, 0, 4]), ("ex_tdnn5", [0]), ("tdnn4", [0]), ("tdnn5", [0])]
+
+
+def snowdar_xvector_forward(sd, x, extracted_embedding="far", extend=False):
+    """snowdar_xvector.py:262-294: far = tdnn6.affine; near_affine = tdnn6 -> tdnn7.affine; near = tdnn6 -> tdnn7
+    (the whole layer, ReLU and BatchNorm included)."""
+    for name, ctx in snowdar_layers(extend):
+        x = relu_bn_tdnn_layer(x, sd, name, ctx)
+    x = statistics_pooling(x)
+    if extracted_embedding == "far":
+        return tdnn_affine(x, sd["tdnn6.affine.weight"], sd["tdnn6.affine.bias"], [0])
+    x = relu_bn_tdnn_layer(x, sd, "tdnn6", [0])
+    if extracted_embedding == "near_affine":
+        return tdnn_affine(x, sd["tdnn7.affine.weight"], sd["tdnn7.affine.bias"], [0])
+    return relu_bn_tdnn_layer(x, sd, "tdnn7", [0])
+
+
+def snowdar_xvector_spec(inputs_dim, extend=False, bn_affine=False):
+    """Keys/shapes of snowdar Xvector(inputs_dim, N, extend=..., training=False).state_dict() in registration
+    order (:104-152): tdnn1, [ex_tdnn1], tdnn2, [ex_tdnn2], tdnn3, [ex_tdnn3, ex_tdnn4, ex_tdnn5], tdnn4, tdnn5,
+    tdnn6, tdnn7; default tdnn_layer_params have BatchNorm affine=False (:45-48)."""
+    reg = [("tdnn1", inputs_dim, 512, [-2, -1, 0, 1, 2])] + ([("ex_tdnn1", 512, 512, [0])] if extend else []) + \
+          [("tdnn2", 512, 512, [-2, 0, 2])] + ([("ex_tdnn2", 512, 512, [0])] if extend else []) + \
+          [("tdnn3", 512, 512, [-3, 0, 3])] + \
+          ([("ex_tdnn3", 512, 512, [0]), ("ex_tdnn4", 512, 512, [-4, 0, 4]), ("ex_tdnn5", 512, 512, [0])] if extend else []) + \
+          [("tdnn4", 512, 512, [0]), ("tdnn5", 512, 1500, [0]), ("tdnn6", 3000, 512, [0]), ("tdnn7", 512, 512, [0])]
+    spec = []
+    for name, cin, cout, ctx in reg:
+        spec += _affine_entries(name, cin, cout, ctx) + _bn_entries(name + ".batchnorm", cout, affine=bn_affine)
+    return spec
+
+
+# --------------------------------------------------------------------------------------
 # ECAPA-TDNN c1024 (pytorch/model/ecapa_tdnn_xvector.py)
 # --------------------------------------------------------------------------------------
 def res2net_block(x, sd, prefix, dilation, scale=8):

@@ -10,6 +10,18 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def _cap_cpu_threads():
+    # ATen's small convolutions get slower, not faster, with more threads than the container can schedule
+    try:
+        import torch
+        torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+    except Exception:
+        pass
+
+
+_cap_cpu_threads()
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 

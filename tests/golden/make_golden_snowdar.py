@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""Golden embeddings of the REFERENCE's snowdar x-vector blueprint (pytorch/model/snowdar_xvector.py) --
+build container only:   python tests/golden/make_golden_snowdar.py
+Seeded checkpoints come from oracle.nnet.make_state_dict(snowdar_xvector_spec), inputs from synthetic_feats;
+only the reference's outputs are stored (tests/golden/snowdar.npz)."""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import nnet as onn  # noqa: E402
+
+CASES = {"std": dict(extend=False, seed=301), "ext": dict(extend=True, seed=302)}
+
+
+def main():
+    for name, attrs in (("tkinter", {"N": "n"}), ("tkinter.messagebox", {"NO": "no"}), ("turtle", {"xcor": None})):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        m.__path__ = []
+        sys.modules[name] = m
+    sys.path.insert(0, "/root/reference/pytorch")
+    import libs.support.utils as utils
+    out = {}
+    for cname, c in CASES.items():
+        sd = onn.make_state_dict(onn.snowdar_xvector_spec(40, extend=c["extend"]), c["seed"])
+        feats = onn.synthetic_feats(3, 120, 40, c["seed"] + 1000)
+        for pos in ("far", "near_affine", "near"):
+            model = utils.create_model_from_py("/root/reference/pytorch/model/snowdar_xvector.py",
+                                               'Xvector(40,10,extend={},training=False,extracted_embedding="{}")'.format(c["extend"], pos))
+            missing = model.load_state_dict(sd, strict=True)
+            model.eval()
+            emb = np.stack([model.extract_embedding(feats[i]).numpy() for i in range(3)])
+            out["{}_{}".format(cname, pos)] = emb
+    np.savez_compressed(os.path.join(HERE, "snowdar.npz"), **out)
+    print("snowdar.npz ok", {k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

@@ -338,3 +338,22 @@ def test_split_frames_pads_with_zero_frames(ops):
     assert torch.equal(back[:, :3], torch.zeros(3, 3, 24, device="cuda")) and torch.equal(back[:, 8:], torch.zeros(3, 1, 24, device="cuda"))
     assert torch.equal(back[:, 3:8, 20:], torch.zeros(3, 5, 4, device="cuda"))
     assert (back[:, 3:8, :20] - x).abs().max() < 1e-5 * x.abs().max()
+
+
+@pytest.mark.parametrize("cname,extend,seed", [("std", False, 301), ("ext", True, 302)])
+def test_snowdar_xvector_matches_reference_golden(golden, cname, extend, seed):
+    """model/snowdar_xvector.py (default BatchNorm affine=False; positions far / near_affine / near) against the
+    reference blueprint's own outputs (tests/golden/make_golden_snowdar.py)."""
+    from asv_subtools_b200.model.snowdar_xvector import Xvector
+    g = golden("snowdar")
+    sd = onn.make_state_dict(onn.snowdar_xvector_spec(40, extend=extend), seed)
+    feats = onn.synthetic_feats(3, 120, 40, seed + 1000)
+    for pos in ("far", "near_affine", "near"):
+        m = Xvector(40, 10, extend=extend, training=False, extracted_embedding=pos)
+        m.load_state_dict(sd, strict=True)
+        m.cuda().eval()
+        emb = np.stack([m.extract_embedding(feats[i]).numpy() for i in range(3)])
+        assert rel(emb, g["{}_{}".format(cname, pos)]) < EMB_TOL, pos
+        assert rel(m.extract_embedding_batch(feats).cpu().numpy(), g["{}_{}".format(cname, pos)]) < EMB_TOL, pos
+    with pytest.raises(NotImplementedError):
+        Xvector(40, 10, SE=True)

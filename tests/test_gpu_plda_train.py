@@ -60,7 +60,8 @@ def test_gpu_plda_training_larger_set_then_scoring_eer(tmp_path):
     assert list(parts) == ["mean", "within_var", "between_var"] and parts["within_var"].shape == (64 * 64,)
     # held-out speakers scored with the GPU-trained and with the oracle-trained model
     te_emb, te_spk = all_emb[~tr], all_spk[~tr]
-    half = te_emb.shape[0] // 2
+    half = te_emb.shape[0] // 8 * 4                       # xvb_plda_matrix wants a multiple of 4 columns
+    te_emb, te_spk = te_emb[:2 * half], te_spk[:2 * half]
     e, t = torch.from_numpy(te_emb[:half]).cuda(), torch.from_numpy(te_emb[half:]).cuda()
     lab = (te_spk[:half, None] == te_spk[None, half:]).ravel()
     s_gpu = est.model().score_matrix(e, t).cpu().numpy().ravel()

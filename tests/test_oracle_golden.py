@@ -206,3 +206,14 @@ def test_plda_training_oracle_matches_reference(golden):
         assert rel(w2, within) < 1e-9 and rel(b2, between) < 1e-9
         _, psi = opt.diagonalising_transform(within, between)
         assert rel(np.sort(psi), np.sort(g[name + "_psi"])) < 1e-9
+
+
+def test_snowdar_xvector_oracle_matches_reference(golden):
+    g = golden("snowdar")
+    for cname, extend, seed in (("std", False, 301), ("ext", True, 302)):
+        sd = onn.make_state_dict(onn.snowdar_xvector_spec(40, extend=extend), seed)
+        feats = onn.synthetic_feats(3, 120, 40, seed + 1000)
+        for pos in ("far", "near_affine", "near"):
+            emb = np.stack([onn.extract_embedding(lambda x: onn.snowdar_xvector_forward(sd, x, pos, extend), feats[i]).numpy()
+                            for i in range(3)])
+            assert rel(emb, g["{}_{}".format(cname, pos)]) < RTOL, (cname, pos)
