@@ -115,3 +115,96 @@ class PldaEstimation:
     def model(self):
         from .backend import PldaModel
         return PldaModel(self.mean, self.within_var, self.between_var)
+
+
+class PLDA:
+    """The diagonalised model `PldaEstimation.get_output()` returns (plda_base.py:302-335, :84-224): `transform`
+    with transform.W.transform^T = I and transform.B.transform^T = diag(psi) (psi descending like Kaldi's),
+    `offset = -transform.mean`; written in Kaldi's text format by `plda_trans_write` (:211-224)."""
+
+    def __init__(self, mean, within_var, between_var):
+        self.mean = np.asarray(mean, dtype=np.float64).reshape(-1, 1)
+        self.dim = self.mean.shape[0]
+        t1 = np.linalg.inv(np.linalg.cholesky(np.asarray(within_var, dtype=np.float64)))
+        s, u = np.linalg.eigh(t1 @ np.asarray(between_var, dtype=np.float64) @ t1.T)
+        order = np.argsort(s)[::-1]
+        s, u = s[order], u[:, order]
+        if s.min() <= 0:
+            raise ValueError("between-class covariance is not positive definite")
+        self.transform = u.T @ t1
+        self.psi = s
+        self.offset = -1.0 * (self.transform @ self.mean)
+
+    def plda_trans_write(self, plda):
+        with open(plda, "w") as f:
+            f.write("<Plda>  [ " + " ".join(map(str, self.mean.reshape(-1))) + " ]\n")
+            f.write(" [")
+            for row in self.transform:
+                f.write("\n  " + " ".join(map(str, row)))
+            f.write(" ]")
+            f.write("\n [ " + " ".join(map(str, self.psi.reshape(-1))) + " ]\n")
+            f.write("</Plda> ")
+
+
+def _get_output(self):
+    return PLDA(self.mean, self.within_var, self.between_var)
+
+
+PldaEstimation.get_output = _get_output
+
+
+class Coral:
+    """CORAL adaptation of a two-covariance PLDA to unlabelled in-domain vectors -- mirror of
+    score/pyplda/ivector-adapt-plda-coral.py (CORAL.add_stats :30-38, update_plda :40-84): the adaptation
+    data's total covariance (its Gram product, on the GPU) is matched by the linear map A = C_i . C_o with
+    C_o = (W + B)^(-1/2), C_i = Var^(1/2); W and B become A W A^T and A B A^T; the mean moves to the data's."""
+
+    def __init__(self, mean_diff_scale=1.0, within_covar_scale=0.8, between_covar_scale=0.8):
+        self.mean_diff_scale = mean_diff_scale
+        self.within_covar_scale, self.between_covar_scale = within_covar_scale, between_covar_scale
+        self._rows = []
+
+    def plda_read(self, plda):
+        parts = dict(kaldi_io.read_vec_flt_ark(plda))
+        self.mean = np.asarray(parts["mean"], dtype=np.float64).reshape(-1, 1)
+        self.dim = self.mean.shape[0]
+        self.within_var = np.asarray(parts["within_var"], dtype=np.float64).reshape(self.dim, self.dim)
+        self.between_var = np.asarray(parts["between_var"], dtype=np.float64).reshape(self.dim, self.dim)
+
+    def add_stats(self, weight, ivector):
+        if weight != 1:
+            raise NotImplementedError("Coral.add_stats: the reference CLI only ever passes weight 1")
+        self._rows.append(np.asarray(ivector, dtype=np.float32).reshape(-1))
+
+    def add_matrix(self, emb):
+        self._emb = emb
+
+    def update_plda(self, device="cuda"):
+        x = getattr(self, "_emb", None)
+        if x is None:
+            x = torch.from_numpy(np.stack(self._rows))
+        x = (x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)))
+        x = x.to(device=device, dtype=torch.float32).contiguous()
+        n = x.shape[0]
+        mean_d = ops.column_mean(x)
+        zero = torch.zeros(n, dtype=torch.int32, device=device)
+        ct = ops.center_rows_transposed(x, zero, mean_d.view(1, -1).contiguous())
+        variance = ops.matmul_nt(ct, ct).double().cpu().numpy() / n          # E[x x^T] - E[x] E[x]^T without the cancellation
+        variance = 0.5 * (variance + variance.T)
+        mean = mean_d.double().cpu().numpy().reshape(-1, 1)
+        diff = mean - self.mean
+        variance += self.mean_diff_scale * (diff @ diff.T)
+        self.mean = mean
+        eo, qo = np.linalg.eigh(self.within_var + self.between_var)
+        ei, qi = np.linalg.eigh(variance)
+        c_o = qo @ np.diag(1.0 / np.sqrt(eo)) @ qo.T
+        c_i = qi @ np.diag(np.sqrt(ei)) @ qi.T
+        self.A = c_i @ c_o
+        self.within_var = self.A @ self.within_var @ self.A.T
+        self.between_var = self.A @ self.between_var @ self.A.T
+
+    def plda_write(self, plda):
+        with kaldi_io.open_or_fd(plda, "wb") as f:
+            kaldi_io.write_vec_flt(f, self.mean.reshape(-1), key="mean")
+            kaldi_io.write_vec_flt(f, self.within_var.reshape(-1), key="within_var")
+            kaldi_io.write_vec_flt(f, self.between_var.reshape(-1), key="between_var")

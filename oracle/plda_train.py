@@ -95,3 +95,24 @@ def synthetic_plda_data(num_spk, dim, seed, min_utts=3, max_utts=9, spread=1.5):
     emb = centres[spk] + rng.standard_normal((spk.shape[0], dim)) @ a.T
     perm = rng.permutation(spk.shape[0])
     return emb[perm].astype(np.float32), spk[perm].astype(np.int32)
+
+
+def synthetic_adaptation_data(n, dim, seed):
+    """Unlabelled in-domain vectors: another covariance, another mean."""
+    rng = np.random.RandomState(seed)
+    a = rng.standard_normal((dim, dim)) / np.sqrt(dim) * 1.7
+    return (rng.standard_normal((n, dim)) @ a.T + 0.8).astype(np.float32)
+
+
+def coral_adapt(mean, within, between, adapt, mean_diff_scale=1.0):
+    """CORAL.update_plda, score/pyplda/ivector-adapt-plda-coral.py:40-84 (eigh is ascending already, so its
+    sort_svd is a no-op): A = Var^(1/2) (W + B)^(-1/2); W, B -> A W A^T, A B A^T; mean -> data mean."""
+    x = np.asarray(adapt, dtype=np.float64)
+    m = x.mean(axis=0).reshape(-1, 1)
+    var = x.T @ x / x.shape[0] - m @ m.T
+    d = m - np.asarray(mean, dtype=np.float64).reshape(-1, 1)
+    var = var + mean_diff_scale * (d @ d.T)
+    eo, qo = np.linalg.eigh(within + between)
+    ei, qi = np.linalg.eigh(var)
+    a = (qi @ np.diag(np.sqrt(ei)) @ qi.T) @ (qo @ np.diag(1.0 / np.sqrt(eo)) @ qo.T)
+    return m.reshape(-1), a @ within @ a.T, a @ between @ a.T

@@ -44,6 +44,20 @@ def main():
         out[name + "_scatter"] = stats.offset_scatter
         plda = est.get_output()
         out[name + "_psi"] = np.asarray(plda.psi)
+    # CORAL adaptation (ivector-adapt-plda-coral.py) of the d16 model to a shifted, rescaled domain
+    spec = importlib.util.spec_from_file_location("coral", "/root/reference/score/pyplda/ivector-adapt-plda-coral.py")
+    cm = importlib.util.module_from_spec(spec)
+    sys.modules["plda_base"] = pb
+    spec.loader.exec_module(cm)
+    coral = cm.CORAL()
+    coral.mean = out["d16_mean"].reshape(-1, 1).copy()
+    coral.dim = 16
+    coral.within_var, coral.between_var = out["d16_within"].copy(), out["d16_between"].copy()
+    adapt = opt.synthetic_adaptation_data(500, 16, 77)
+    for v in adapt:
+        coral.add_stats(1, v.astype(np.float64))
+    coral.update_plda()
+    out["coral_mean"], out["coral_within"], out["coral_between"] = coral.mean.reshape(-1), coral.within_var, coral.between_var
     np.savez_compressed(os.path.join(HERE, "plda_train.npz"), **out)
     print("plda_train.npz ok", {k: v.shape for k, v in out.items()})
 

@@ -73,3 +73,30 @@ def test_gpu_plda_training_larger_set_then_scoring_eer(tmp_path):
     G, L, c, k = osc.plda_calculate_var(between, osc.plda_smooth_within(within), mean.reshape(-1, 1))
     want = osc.plda_score_matrix(te_emb[:half], te_emb[half:], G, L, c, k).ravel()
     assert np.max(np.abs(s_gpu - want)) / np.max(np.abs(want)) < 1e-4
+
+
+def test_gpu_coral_adaptation_and_diagonalised_output(golden, tmp_path):
+    from asv_subtools_b200 import kaldi_io
+    from asv_subtools_b200.score.plda_train import PLDA, Coral
+    g = golden("plda_train")
+    path = str(tmp_path / "plda.ori")
+    with open(path, "wb") as f:
+        kaldi_io.write_vec_flt(f, g["d16_mean"], key="mean")
+        kaldi_io.write_vec_flt(f, g["d16_within"].reshape(-1), key="within_var")
+        kaldi_io.write_vec_flt(f, g["d16_between"].reshape(-1), key="between_var")
+    c = Coral()
+    c.plda_read(path)
+    for v in opt.synthetic_adaptation_data(500, 16, 77):
+        c.add_stats(1, v)
+    c.update_plda()
+    assert rel(c.mean.reshape(-1), g["coral_mean"]) < 1e-6
+    assert rel(c.within_var, g["coral_within"]) < 2e-5 and rel(c.between_var, g["coral_between"]) < 2e-5
+    c.plda_write(str(tmp_path / "plda.adapt"))
+    assert list(dict(kaldi_io.read_vec_flt_ark(str(tmp_path / "plda.adapt")))) == ["mean", "within_var", "between_var"]
+    # get_output: T W T^T = I, T B T^T = diag(psi) with the reference's psi
+    p = PLDA(g["d16_mean"], g["d16_within"], g["d16_between"])
+    assert rel(np.sort(p.psi), np.sort(g["d16_psi"])) < 1e-9
+    assert rel(p.transform @ g["d16_within"] @ p.transform.T, np.eye(16)) < 1e-9
+    p.plda_trans_write(str(tmp_path / "plda.txt"))
+    txt = open(str(tmp_path / "plda.txt")).read()
+    assert txt.startswith("<Plda>  [ ") and txt.rstrip().endswith("</Plda>")

@@ -217,3 +217,10 @@ def test_snowdar_xvector_oracle_matches_reference(golden):
             emb = np.stack([onn.extract_embedding(lambda x: onn.snowdar_xvector_forward(sd, x, pos, extend), feats[i]).numpy()
                             for i in range(3)])
             assert rel(emb, g["{}_{}".format(cname, pos)]) < RTOL, (cname, pos)
+
+
+def test_coral_adaptation_oracle_matches_reference(golden):
+    from oracle import plda_train as opt
+    g = golden("plda_train")
+    m, w, b = opt.coral_adapt(g["d16_mean"], g["d16_within"], g["d16_between"], opt.synthetic_adaptation_data(500, 16, 77))
+    assert rel(m, g["coral_mean"]) < 1e-10 and rel(w, g["coral_within"]) < 1e-9 and rel(b, g["coral_between"]) < 1e-9
