@@ -81,6 +81,8 @@ SIGNATURES = {
     "xvb_cosine_matrix": (_i, [_p, _i64, _p, _i64, _i, _p, _i64, _p]),
     "xvb_plda_terms": (_i, [_p, _i64, _i, _p, _p, _p, _p]),
     "xvb_plda_matrix": (_i, [_p, _i64, _p, _i64, _i, _p, _p, _p, _p, _i64, _p]),
+    "xvb_topn_indices": (_i, [_p, _i64, _i64, _i, _i, _p, _p]),
+    "xvb_snorm_cross_trials": (_i, [_p, _p, _p, _i64, _p, _i64, _p, _i64, _p, _p, _i, _p, _p]),
     "xvb_matmul_nt": (_i, [_p, _i64, _p, _i64, _i, _p, _p, _p, _i64, _p]),
     "xvb_center_rows_transposed": (_i, [_p, _p, _p, _p, _i64, _i, _p, _i64, _p]),
     "xvb_plda_em_rows": (_i, [_p, _p, _p, _p, _i, _i, _p, _p, _i64, _p]),

@@ -141,6 +141,63 @@ __global__ void topn_mean_std_kernel(const float* __restrict__ S, long long ld, 
   }
 }
 
+// Cohort indices of the top_n largest scores of every row, in descending score order (ties: lower index
+// first): bitonic sort of (score, index) pairs in shared memory.  For AS-norm with cross selection.
+__global__ void topn_index_kernel(const float* __restrict__ S, long long ld, int ncoh, int P, int top_n,
+                                  int32_t* __restrict__ idx_out) {
+  extern __shared__ float sv[];
+  int* si = reinterpret_cast<int*>(sv + P);
+  const float* row = S + (long long)blockIdx.x * ld;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) { sv[i] = i < ncoh ? row[i] : -INFINITY; si[i] = i; }
+  __syncthreads();
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const float a = sv[i], b = sv[ixj];
+          const int ia = si[i], ib = si[ixj];
+          const bool a_first = a > b || (a == b && ia < ib);   // the order we want: a before b
+          const bool desc = (i & k) == 0;
+          if (desc ? !a_first : a_first) { sv[i] = b; sv[ixj] = a; si[i] = ib; si[ixj] = ia; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < top_n; i += blockDim.x) idx_out[(long long)blockIdx.x * top_n + i] = si[i];
+}
+
+// One warp per trial: enroll statistics over the TEST side's top-n cohort, test statistics over the ENROLL
+// side's (ScoreNormalization.py:146-160), mean and std(ddof = 1) in double like the table path.
+__global__ void snorm_cross_trials_kernel(const float* __restrict__ s, const int32_t* __restrict__ te,
+                                          const int32_t* __restrict__ tt, const float* __restrict__ ec, long long lde,
+                                          const float* __restrict__ tc, long long ldt, const int32_t* __restrict__ top_e,
+                                          const int32_t* __restrict__ top_t, int top_n, long long n,
+                                          float* __restrict__ out) {
+  const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const int e = te[w], t = tt[w];
+  auto stats = [&](const float* row, const int32_t* idx, double& mu, double& sd) {
+    double s1 = 0.0;
+    for (int i = lane; i < top_n; i += 32) s1 += (double)row[idx[i]];
+    for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    mu = s1 / (double)top_n;
+    double s2 = 0.0;
+    for (int i = lane; i < top_n; i += 32) { const double d = (double)row[idx[i]] - mu; s2 += d * d; }
+    for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    sd = sqrt(s2 / (double)(top_n - 1));
+  };
+  double me, se, mt, st;
+  stats(ec + (long long)e * lde, top_t + (long long)t * top_n, me, se);
+  stats(tc + (long long)t * ldt, top_e + (long long)e * top_n, mt, st);
+  if (lane == 0) {
+    const double v = (double)s[w];
+    out[w] = (float)(0.5 * ((v - me) / se + (v - mt) / st));
+  }
+}
+
 __global__ void snorm_trials_kernel(const float* __restrict__ s, const int32_t* __restrict__ te,
                                     const int32_t* __restrict__ tt, const float* __restrict__ me,
                                     const float* __restrict__ se, const float* __restrict__ mt,
@@ -440,6 +497,39 @@ extern "C" int xvb_plda_em_rows(const float* u, const float* n, const float* wei
   XVB_CHECK_ARG(u && n && psi && what_T && resid_T && S > 0 && D > 0 && ldo >= S, "xvb_plda_em_rows: bad arguments");
   dim3 grid((unsigned)((S + 31) / 32), (unsigned)((D + 31) / 32)), block(32, 8);
   plda_em_rows_T_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(u, n, weight, psi, S, D, what_T, resid_T, ldo);
+  XVB_LAUNCH_CHECK();
+  return XVB_OK;
+}
+
+extern "C" int xvb_topn_indices(const float* S, int64_t lds, int64_t rows, int ncoh, int top_n, int32_t* idx, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  XVB_CHECK_ARG(S && idx && rows > 0 && ncoh > 0 && lds >= ncoh && top_n >= 1 && top_n <= ncoh, "xvb_topn_indices: bad arguments");
+  XVB_CHECK_ARG(ncoh <= 16384, "xvb_topn_indices: cohort of %d exceeds the 16384 (score, index) pairs one CTA sorts on chip", ncoh);
+  int P = 1;
+  while (P < ncoh) P <<= 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    XVB_CUDA(cudaFuncSetAttribute(topn_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+    attr_set = true;
+  }
+  topn_index_kernel<<<(unsigned)rows, 512, (size_t)P * 8, (cudaStream_t)stream>>>(S, lds, ncoh, P, top_n, idx);
+  XVB_LAUNCH_CHECK();
+  return XVB_OK;
+}
+
+extern "C" int xvb_snorm_cross_trials(const float* scores, const int32_t* trial_e, const int32_t* trial_t, int64_t num_trials,
+                                      const float* enroll_cohort, int64_t lde, const float* test_cohort, int64_t ldt,
+                                      const int32_t* top_enroll, const int32_t* top_test, int top_n, float* out,
+                                      void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  XVB_CHECK_ARG(scores && trial_e && trial_t && enroll_cohort && test_cohort && top_enroll && top_test && out && top_n >= 2,
+                "xvb_snorm_cross_trials: bad arguments (top_n >= 2)");
+  if (num_trials == 0) return XVB_OK;
+  const long long threads = num_trials * 32;
+  snorm_cross_trials_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      scores, trial_e, trial_t, enroll_cohort, lde, test_cohort, ldt, top_enroll, top_test, top_n, num_trials, out);
   XVB_LAUNCH_CHECK();
   return XVB_OK;
 }

@@ -345,6 +345,25 @@ def plda_matrix(enroll, test, l2, row, col):
     return s
 
 
+def topn_indices(S, top_n):
+    """(rows, top_n) int32: cohort indices of every row's top_n scores, best first."""
+    S = _req(S, torch.float32, "S")
+    idx = torch.empty(S.shape[0], top_n, dtype=torch.int32, device=S.device)
+    check(lib.xvb_topn_indices(_ptr(S), S.shape[1], S.shape[0], S.shape[1], int(top_n), _ptr(idx), _stream()), "xvb_topn_indices")
+    return idx
+
+
+def snorm_cross_trials(scores, trial_e, trial_t, enroll_cohort, test_cohort, top_enroll, top_test):
+    scores = _req(scores, torch.float32, "scores")
+    out = torch.empty_like(scores)
+    check(lib.xvb_snorm_cross_trials(_ptr(scores), _ptr(_req(trial_e, torch.int32, "trial_e")), _ptr(_req(trial_t, torch.int32, "trial_t")),
+                                     scores.shape[0], _ptr(_req(enroll_cohort, torch.float32, "enroll_cohort")), enroll_cohort.shape[1],
+                                     _ptr(_req(test_cohort, torch.float32, "test_cohort")), test_cohort.shape[1],
+                                     _ptr(_req(top_enroll, torch.int32, "top_enroll")), _ptr(_req(top_test, torch.int32, "top_test")),
+                                     top_enroll.shape[1], _ptr(out), _stream()), "xvb_snorm_cross_trials")
+    return out
+
+
 def matmul_nt(a, b, row_bias=None, col_bias=None):
     """a (M,K) . b (N,K)^T + row_bias[i] + col_bias[j] -> (M,N) fp32 on the tcgen05 layer (N % 4 == 0)."""
     a = _req(a, torch.float32, "a")

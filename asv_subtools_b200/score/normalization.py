@@ -19,9 +19,15 @@ import torch
 from .. import ops
 
 
-def normalize(scores, trial_e, trial_t, enroll_cohort, test_cohort, top_n=0):
+def normalize(scores, trial_e, trial_t, enroll_cohort, test_cohort, top_n=0, cross_select=False):
     """scores (n,) fp32; trial_e/trial_t int32 indices into the rows of the two cohort matrices
-    (Ne, Nc) / (Nt, Nc), all CUDA.  top_n <= 0: S-norm (all cohort scores)."""
+    (Ne, Nc) / (Nt, Nc), all CUDA.  top_n <= 0: S-norm (all cohort scores).  cross_select: AS-norm where each
+    side's statistics use the OTHER side's top-n cohort (ScoreNormalization.py:146-160)."""
+    if cross_select:
+        if top_n < 2:
+            raise ValueError("cross selection needs top_n >= 2")
+        return ops.snorm_cross_trials(scores, trial_e, trial_t, enroll_cohort, test_cohort,
+                                      ops.topn_indices(enroll_cohort, top_n), ops.topn_indices(test_cohort, top_n))
     me, se = ops.topn_mean_std(enroll_cohort, top_n)
     mt, st = ops.topn_mean_std(test_cohort, top_n)
     return ops.snorm_trials(scores, trial_e, trial_t, me, se, mt, st)
@@ -75,8 +81,8 @@ def main(argv=None):
     print(" ".join(sys.argv))
     args = ap.parse_args(argv)
     try:
-        if args.cross_select == "true":
-            raise NotImplementedError("--cross-select true is not on the B200 path yet")
+        if args.cross_select == "true" and args.method != "asnorm":
+            raise ValueError("--cross-select applies to asnorm")
         te, tt, s = _load(args.input_score)
         a, b, v = _load(args.enroll_cohort_score)
         ek, ec = (a, b) if args.second_cohort == "true" else (b, a)
@@ -88,7 +94,8 @@ def main(argv=None):
         ie = torch.tensor([eidx[k] for k in te], dtype=torch.int32, device=dev)
         it = torch.tensor([tidx[k] for k in tt], dtype=torch.int32, device=dev)
         out = normalize(torch.from_numpy(s.astype(np.float32)).to(dev), ie, it, torch.from_numpy(em).to(dev),
-                        torch.from_numpy(tm).to(dev), args.top_n if args.method == "asnorm" else 0).cpu().numpy()
+                        torch.from_numpy(tm).to(dev), args.top_n if args.method == "asnorm" else 0,
+                        cross_select=args.cross_select == "true").cpu().numpy()
         with open(args.output_score, "w") as f:
             for x, y, z in zip(te, tt, out):
                 f.write("{} {} {}\n".format(x, y, repr(float(z))))

@@ -276,6 +276,17 @@ int xvb_plda_terms(const float* x, int64_t rows, int D, const float* gamma, cons
 int xvb_plda_matrix(const float* enroll, int64_t Ne, const float* test, int64_t Nt, int D, const float* L2,
                     const float* row, const float* col, float* S, int64_t lds, void* stream);
 
+/* AS-norm with cross selection (score/ScoreNormalization.py:146-160, --cross-select true): the statistics of
+ * the enroll side of trial (e, t) are taken over the cohort utterances that are the top_n of the TEST side and
+ * vice versa.  xvb_topn_indices: idx (rows, top_n) int32 = cohort indices of every row's top_n scores, best
+ * first (ncoh <= 16384); xvb_snorm_cross_trials: out[i] = 0.5 ((s - mu_e)/sd_e + (s - mu_t)/sd_t) with
+ * mu_e, sd_e over enroll_cohort[e, top_test[t, :]] and mu_t, sd_t over test_cohort[t, top_enroll[e, :]],
+ * std with ddof = 1 like pandas. */
+int xvb_topn_indices(const float* S, int64_t lds, int64_t rows, int ncoh, int top_n, int32_t* idx, void* stream);
+int xvb_snorm_cross_trials(const float* scores, const int32_t* trial_e, const int32_t* trial_t, int64_t num_trials,
+                           const float* enroll_cohort, int64_t lde, const float* test_cohort, int64_t ldt,
+                           const int32_t* top_enroll, const int32_t* top_test, int top_n, float* out, void* stream);
+
 /* out (M, N) = a (M, K) . b (N, K)^T + row_bias[i] + col_bias[j] (biases may be NULL), fp32 row-major in
  * and out, N % 4 == 0: the general form behind xvb_project / xvb_cosine_matrix / xvb_plda_matrix. */
 int xvb_matmul_nt(const float* a, int64_t M, const float* b, int64_t N, int K, const float* row_bias,

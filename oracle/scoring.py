@@ -222,3 +222,19 @@ def trial_histogram(scores, is_target, lo, hi, nbins):
     np.add.at(out[0], b[~t], 1)
     np.add.at(out[1], b[t], 1)
     return out
+
+
+def snorm_cross_apply(scores, trial_e, trial_t, enroll_cohort, test_cohort, top_n):
+    """AS-norm with cross selection, score/ScoreNormalization.py:146-160,:171-173: for trial (e, t) the enroll
+    statistics are taken over the cohort utterances that are the top_n of the TEST side, and vice versa;
+    std is pandas' (ddof = 1)."""
+    ec = np.asarray(enroll_cohort, dtype=np.float64)
+    tc = np.asarray(test_cohort, dtype=np.float64)
+    top_e = np.argsort(-ec, axis=1, kind="stable")[:, :top_n]
+    top_t = np.argsort(-tc, axis=1, kind="stable")[:, :top_n]
+    out = np.empty(len(scores), dtype=np.float64)
+    for k, (e, t, s) in enumerate(zip(trial_e, trial_t, np.asarray(scores, dtype=np.float64))):
+        ge = ec[e, top_t[t]]
+        gt = tc[t, top_e[e]]
+        out[k] = 0.5 * ((s - ge.mean()) / ge.std(ddof=1) + (s - gt.mean()) / gt.std(ddof=1))
+    return out

@@ -179,6 +179,42 @@ def test_score_normalization_matches_reference_golden(ops, golden, tmp_path):
     assert np.max(np.abs(vals - g["sn_asnorm"]) / (1 + np.abs(g["sn_asnorm"]))) < 2e-5
 
 
+def test_asnorm_cross_select_matches_reference_golden(ops, golden, tmp_path):
+    """--cross-select true: top-n (score, index) sort + per-trial gather statistics against the reference's pandas
+    merge (tests/golden/make_golden_snorm_cross.py), a larger random case against the oracle, and the CLI."""
+    from asv_subtools_b200.score import normalization as norm
+    g, gc = golden("score_norm"), golden("score_norm_cross")
+    ec, tc = cuda(g["sn_enroll_cohort"]), cuda(g["sn_test_cohort"])
+    te, tt = cuda(g["sn_trial_e"], np.int32), cuda(g["sn_trial_t"], np.int32)
+    for topn in (7, 19):
+        out = norm.normalize(cuda(g["sn_scores"]), te, tt, ec, tc, topn, cross_select=True).cpu().numpy()
+        ref = gc["cross_top%d" % topn]
+        assert np.max(np.abs(out - ref) / (1 + np.abs(ref))) < 2e-5, topn
+    idx = ops.topn_indices(ec, 7).cpu().numpy()
+    assert np.array_equal(idx, np.argsort(-g["sn_enroll_cohort"], axis=1, kind="stable")[:, :7])
+    rng = np.random.RandomState(9)
+    E, T = rng.standard_normal((50, 1000)).astype(np.float32), rng.standard_normal((70, 1000)).astype(np.float32)
+    ie, it = rng.randint(0, 50, 3000).astype(np.int32), rng.randint(0, 70, 3000).astype(np.int32)
+    sc = rng.standard_normal(3000).astype(np.float32)
+    got = norm.normalize(cuda(sc), cuda(ie, np.int32), cuda(it, np.int32), cuda(E), cuda(T), 300, cross_select=True).cpu().numpy()
+    ref = osc.snorm_cross_apply(sc, ie, it, E, T, 300)
+    assert np.max(np.abs(got - ref) / (1 + np.abs(ref))) < 2e-5
+    with open(tmp_path / "in", "w") as f:
+        for i, j, v in zip(g["sn_trial_e"], g["sn_trial_t"], g["sn_scores"]):
+            f.write("e{} t{} {}\n".format(i, j, repr(float(v))))
+    for name, p, tab in (("ec", "e", g["sn_enroll_cohort"]), ("tc", "t", g["sn_test_cohort"])):
+        with open(tmp_path / name, "w") as f:
+            for i in range(tab.shape[0]):
+                for cidx in range(tab.shape[1]):
+                    f.write("{}{} c{} {}\n".format(p, i, cidx, repr(float(tab[i, cidx]))))
+    r = subprocess.run([sys.executable, "-m", "asv_subtools_b200.score.normalization", "--method", "asnorm", "--top-n", "19",
+                        "--cross-select", "true", str(tmp_path / "in"), str(tmp_path / "ec"), str(tmp_path / "tc"),
+                        str(tmp_path / "out")], capture_output=True, text=True, env=dict(os.environ, PYTHONPATH=ROOT), cwd=ROOT)
+    assert r.returncode == 0, r.stdout + r.stderr
+    vals = np.array([float(l.split()[2]) for l in open(tmp_path / "out")])
+    assert np.max(np.abs(vals - gc["cross_top19"]) / (1 + np.abs(gc["cross_top19"]))) < 2e-5
+
+
 def test_extract_and_score_clis_end_to_end(tmp_path):
     """feats.ark + checkpoint + nnet.config -> extract CLI -> xvector.ark -> cosine CLI -> EER CLI,
     compared with the oracle running the reference arithmetic on the same files."""

@@ -224,3 +224,10 @@ def test_coral_adaptation_oracle_matches_reference(golden):
     g = golden("plda_train")
     m, w, b = opt.coral_adapt(g["d16_mean"], g["d16_within"], g["d16_between"], opt.synthetic_adaptation_data(500, 16, 77))
     assert rel(m, g["coral_mean"]) < 1e-10 and rel(w, g["coral_within"]) < 1e-9 and rel(b, g["coral_between"]) < 1e-9
+
+
+def test_score_normalization_cross_select(golden):
+    g, gc = golden("score_norm"), golden("score_norm_cross")
+    for topn in (7, 19):
+        out = osc.snorm_cross_apply(g["sn_scores"], g["sn_trial_e"], g["sn_trial_t"], g["sn_enroll_cohort"], g["sn_test_cohort"], topn)
+        assert np.max(np.abs(out - gc["cross_top%d" % topn])) < 1e-9
