@@ -85,10 +85,18 @@ def plda_estimate_grouped(stats, num_em_iters=10):
     return gmean, within, between
 
 
-def synthetic_plda_data(num_spk, dim, seed, min_utts=3, max_utts=9, spread=1.5):
+def synthetic_plda_data(num_spk, dim, seed, min_utts=3, max_utts=9, spread=1.5, conditioned=False):
+    """conditioned=True: within / between factors with singular values in [0.6, 1.4] (a square Gaussian matrix has
+    a condition number in the thousands, which turns fp32-level differences of the covariances into visible
+    score differences through the inverses of the scoring formula)."""
     rng = np.random.RandomState(seed)
     a = rng.standard_normal((dim, dim)) / np.sqrt(dim)
     b = rng.standard_normal((dim, dim)) / np.sqrt(dim)
+    if conditioned:
+        qa, _ = np.linalg.qr(a)
+        qb, _ = np.linalg.qr(b)
+        a = qa * rng.uniform(0.6, 1.4, dim)[None, :]
+        b = qb * rng.uniform(0.6, 1.4, dim)[None, :]
     counts = rng.randint(min_utts, max_utts + 1, num_spk)
     spk = np.repeat(np.arange(num_spk), counts)
     centres = rng.standard_normal((num_spk, dim)) @ b.T * spread + 0.3
