@@ -11,9 +11,14 @@
 //     F.pad(..., value=0) (components.py:117) and can never cross an utterance boundary;
 //   * fp32-grade accuracy at bf16 tensor rate: operands are bf16 "split planes" (hi, lo) and each
 //     K step issues hi*hi + lo*hi + hi*lo into the same fp32 TMEM accumulator;
-//   * warp-specialised persistent CTAs: warp0 = TMA producer, warp1 = tcgen05.mma issuer,
-//     warps2-5 = epilogue (tcgen05.ld -> +bias -> ReLU -> BN -> split -> global), double-buffered
-//     accumulators in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   * warp-specialised persistent CTAs (usually CTA pairs, cta_group::2): warp0 = TMA producer, warp1 =
+//     tcgen05.mma issuer, warps2-9 = epilogue (tcgen05.ld -> +bias -> ReLU -> BN -> split -> swizzled smem
+//     slab -> TMA store), double-buffered accumulators in TMEM so the epilogue of tile i overlaps the MMAs
+//     of tile i+1.
+// Variants of the same kernel (template flags): kPool -- swapped operands, the epilogue pools over time
+// instead of storing (fused statistics pooling); kHist -- the epilogue bins scores into a trial histogram
+// (scoring.cu); runtime: a second A source (W.(a+b)), split-K slices for the segment layers, an im2col
+// view of the first layer (x_batch_stride).
 //
 // An M tile is 128 rows = Bb utterances x Tb consecutive frames (Tb*Bb = 128, chosen on the host
 // to minimise padding: T=200 -> Tb=8, Bb=16 has none).
