@@ -107,6 +107,16 @@ SIGNATURES = {
     "xvb_fbank_num_frames": (_i64, [_p, _i64]),
     "xvb_fbank_compute": (_i, [_p, _p, _p, _p, _i, _i64, _p, _p]),
     "xvb_fbank_destroy": (None, [_p]),
+    "xvb_ecapa_create": (_i, [C.POINTER(_p), _i, _i, _i, _i, _i]),
+    "xvb_ecapa_set_layer": (_i, [_p, C.c_char_p, _i, _i, _ip, _i, _p, _p, _p, _p, _i]),
+    "xvb_ecapa_finalize": (_i, [_p]),
+    "xvb_ecapa_embed_dim": (_i, [_p]),
+    "xvb_ecapa_feat_dim": (_i, [_p]),
+    "xvb_ecapa_extract": (_i, [_p, _p, _i, _i, _p, _p]),
+    "xvb_ecapa_last_launches": (_i, [_p]),
+    "xvb_ecapa_save": (_i, [_p, C.c_char_p]),
+    "xvb_ecapa_load": (_i, [C.POINTER(_p), C.c_char_p]),
+    "xvb_ecapa_destroy": (None, [_p]),
     "xvb_extractor_load": (_i, [C.POINTER(_p), C.c_char_p]),
     "xvb_extractor_feat_dim": (_i, [C.c_char_p]),
     "xvb_ark_reader_open": (_i, [C.POINTER(_p), C.c_char_p]),

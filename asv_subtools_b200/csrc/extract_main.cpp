@@ -56,7 +56,8 @@ struct Utt {
 #define CU(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { fprintf(stderr, "ERROR: xvb-extract: %s: %s\n", #call, cudaGetErrorString(_e)); exit(1); } } while (0)
 
 struct Runner {
-  xvb_extractor_t* ex = nullptr;
+  xvb_extractor_t* ex = nullptr;   // TDNN x-vector family (XVBM0001) ...
+  xvb_ecapa_t* ec = nullptr;       // ... or ECAPA-TDNN (XVBE0001)
   xvb_ark_writer_t* out = nullptr;
   int F = 0, D = 0, batch = 256, cmn = 0, cmn_window = 300;
   float *d_feats = nullptr, *d_tmp = nullptr, *d_emb = nullptr, *h_feats = nullptr, *h_emb = nullptr;
@@ -86,7 +87,8 @@ struct Runner {
     reserve((size_t)B * T);
     for (int i = 0; i < B; ++i) memcpy(h_feats + (size_t)i * T * F, items[i].feats.data(), (size_t)T * F * sizeof(float));
     CU(cudaMemcpy(d_feats, h_feats, (size_t)B * T * F * sizeof(float), cudaMemcpyHostToDevice));
-    CK(xvb_extractor_extract(ex, d_feats, B, T, d_emb, nullptr), "xvb_extractor_extract");
+    if (ex) CK(xvb_extractor_extract(ex, d_feats, B, T, d_emb, nullptr), "xvb_extractor_extract");
+    else CK(xvb_ecapa_extract(ec, d_feats, B, T, d_emb, nullptr), "xvb_ecapa_extract");
     CU(cudaMemcpy(h_emb, d_emb, (size_t)B * D * sizeof(float), cudaMemcpyDeviceToHost));
     for (int i = 0; i < B; ++i) {
       Utt& u = utts[items[i].utt];
@@ -197,9 +199,21 @@ int main(int argc, char** argv) {
   }
   if (cudaSetDevice(gpu) != cudaSuccess) { fprintf(stderr, "ERROR: xvb-extract: no CUDA device %d visible (there is no CPU path)\n", gpu); return 1; }
   CK(xvb_device_check(), "device check");
-  CK(xvb_extractor_load(&r.ex, pos[0]), "loading the model");
-  r.F = xvb_extractor_feat_dim(pos[0]);
-  r.D = xvb_extractor_embed_dim(r.ex);
+  {
+    char magic[8] = {0};
+    FILE* mf = fopen(pos[0], "rb");
+    if (!mf || fread(magic, 1, 8, mf) != 8) { fprintf(stderr, "ERROR: xvb-extract: cannot read model file '%s'\n", pos[0]); return 1; }
+    fclose(mf);
+    if (memcmp(magic, "XVBE0001", 8) == 0) {
+      CK(xvb_ecapa_load(&r.ec, pos[0]), "loading the ECAPA model");
+      r.F = xvb_ecapa_feat_dim(r.ec);
+      r.D = xvb_ecapa_embed_dim(r.ec);
+    } else {
+      CK(xvb_extractor_load(&r.ex, pos[0]), "loading the model");
+      r.F = xvb_extractor_feat_dim(pos[0]);
+      r.D = xvb_extractor_embed_dim(r.ex);
+    }
+  }
   xvb_ark_reader_t* in = nullptr;
   FILE* wav_scp = nullptr;
   xvb_fbank_t* fb = nullptr;
@@ -310,7 +324,8 @@ int main(int argc, char** argv) {
   if (wav_scp) fclose(wav_scp);
   if (fb) xvb_fbank_destroy(fb);
   CK(xvb_ark_writer_close(r.out), "closing the vector wspecifier");
-  xvb_extractor_destroy(r.ex);
+  if (r.ex) xvb_extractor_destroy(r.ex);
+  if (r.ec) xvb_ecapa_destroy(r.ec);
   fprintf(stderr, "xvb-extract: %ld utterances, %ld frames\n", r.done_utts, r.done_frames);
   return 0;
 }

@@ -132,7 +132,10 @@ class ECAPA_TDNN(TopVirtualNnet):
             if self.extracted_embedding == "far":
                 raise AssertionError("extracted_embedding='far' needs fc1 (ecapa_tdnn_xvector.py:415-416)")
             raise TypeError("Expected far or near position, but got {}".format(self.extracted_embedding))
-        return EcapaExtractor(self, self.device_for_extraction())
+        dev = self.device_for_extraction()
+        if os.environ.get("XVB_ECAPA_NATIVE", "1") == "0" or self.layer1.affine.output_dim != 1024:
+            return EcapaExtractor(self, dev)       # op-by-op twin; also the path for other channel counts
+        return NativeEcapaExtractor(self, dev)
 
 
 class _Layer:
@@ -165,8 +168,107 @@ def _mark(label):
         _PROFILE.append((label, ev))
 
 
+def _named_layers(m):
+    """(name, weight (Cout,Cin,tot) ndarray, bias, context, scale, shift, relu) for xvb_ecapa_set_layer: the state_dict
+    tensors as stored, eval BatchNorm folded; the attention conv split into its x / [mean|std] columns (:179) and
+    bn_stats folded into fc2 (W' = W diag(s), b' = W t + b)."""
+    f = lambda t: t.detach().float().cpu().numpy()  # noqa: E731
+
+    def tdnn(name, layer):
+        scale, shift = fold_batchnorm(layer.batchnorm)
+        return (name, f(layer.affine.weight), f(layer.affine.bias) if layer.affine.bias is not None else None,
+                list(layer.affine.context), scale, shift, layer.relu)
+
+    out = [tdnn("layer1", m.layer1)]
+    for li, blk in zip((2, 3, 4), (m.layer2, m.layer3, m.layer4)):
+        p = "layer{}.".format(li)
+        out.append(tdnn(p + "bn1", blk.conv_relu_bn1))
+        out += [tdnn(p + "res{}".format(i), b) for i, b in enumerate(blk.res2net_block.blocks)]
+        out.append(tdnn(p + "bn2", blk.conv_relu_bn2))
+        out.append((p + "se1", f(blk.se.se[1].weight), f(blk.se.se[1].bias), [0], None, None, True))
+        out.append((p + "se2", f(blk.se.se[3].weight), f(blk.se.se[3].bias), [0], None, None, False))
+    out.append(tdnn("mfa", m.mfa))
+    att, c = m.stats.attention, m.stats.in_dim
+    w0 = f(att[0].weight)
+    s, t = fold_batchnorm(att[2])
+    out.append(("att_x", np.ascontiguousarray(w0[:, :c]), None, [0], s, t, True))
+    out.append(("att_gs", np.ascontiguousarray(w0[:, c:]), f(att[0].bias), [0], None, None, False))
+    out.append(("att2", f(att[4].weight), f(att[4].bias), [0], None, None, False))
+    s, t = fold_batchnorm(m.bn_stats)
+    w = m.fc2.affine.weight.detach().double().cpu().numpy()[:, :, 0]
+    b = m.fc2.affine.bias.detach().double().cpu().numpy()
+    w2 = (w * s.astype(np.float64)[None, :]).astype(np.float32)[:, :, None]
+    b2 = (w @ t.astype(np.float64) + b).astype(np.float32)
+    full = m.extracted_embedding == "near"
+    fs, ft = fold_batchnorm(m.fc2.batchnorm) if full else (None, None)
+    out.append(("fc2", w2, b2, [0], fs, ft, full and m.fc2.relu))
+    return out
+
+
+class NativeEcapaExtractor:
+    """xvb_ecapa_t: packed weights, workspace and the whole launch sequence in the C library."""
+
+    def __init__(self, m=None, device=None, path=None):
+        import ctypes as C
+        from asv_subtools_b200._lib import check, int_array, lib
+        self._C, self._lib, self._check = C, lib, check
+        self._h = C.c_void_p()
+        if path is not None:
+            check(lib.xvb_ecapa_load(C.byref(self._h), str(path).encode()), "xvb_ecapa_load")
+        else:
+            check(lib.xvb_ecapa_create(C.byref(self._h), m.inputs_dim, m.layer1.affine.output_dim, m.stats.in_dim,
+                                       m.stats.attention[0].out_channels, m.embd_dim), "xvb_ecapa_create")
+            for name, w, b, ctx, scale, shift, relu in _named_layers(m):
+                w = np.ascontiguousarray(w, dtype=np.float32)
+                w3 = w.reshape(w.shape[0], w.shape[1], -1)
+                arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float32) for a in (b, scale, shift)]
+                ptr = [None if a is None else a.ctypes.data_as(C.c_void_p) for a in arrs]
+                flags = (1 if relu else 0) | (2 if scale is not None else 0)
+                check(lib.xvb_ecapa_set_layer(self._h, name.encode(), w3.shape[0], w3.shape[1], int_array(ctx), len(ctx),
+                                              w3.ctypes.data_as(C.c_void_p), ptr[0], ptr[1], ptr[2], flags), "xvb_ecapa_set_layer")
+            check(lib.xvb_ecapa_finalize(self._h), "xvb_ecapa_finalize")
+        self.feat_dim = lib.xvb_ecapa_feat_dim(self._h)
+        self.embed_dim = lib.xvb_ecapa_embed_dim(self._h)
+
+    @classmethod
+    def load(cls, path):
+        return cls(path=path)
+
+    def save(self, path):
+        self._check(self._lib.xvb_ecapa_save(self._h, str(path).encode()), "xvb_ecapa_save")
+
+    @property
+    def last_launches(self):
+        return self._lib.xvb_ecapa_last_launches(self._h)
+
+    def extract(self, feats):
+        if not (isinstance(feats, torch.Tensor) and feats.is_cuda and feats.dtype == torch.float32 and feats.is_contiguous()):
+            raise TypeError("feats must be a contiguous CUDA float32 tensor")
+        if feats.shape[2] != self.feat_dim:
+            raise ValueError("expected feature dim {}, got {}".format(self.feat_dim, feats.shape[2]))
+        B, T, _ = feats.shape
+        emb = torch.empty(B, self.embed_dim, dtype=torch.float32, device=feats.device)
+        C = self._C
+        self._check(self._lib.xvb_ecapa_extract(self._h, C.c_void_p(feats.data_ptr()), B, T, C.c_void_p(emb.data_ptr()),
+                                                C.c_void_p(torch.cuda.current_stream().cuda_stream)), "xvb_ecapa_extract")
+        return emb
+
+    def close(self):
+        h, self._h = self._h, None
+        if h:
+            self._lib.xvb_ecapa_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class EcapaExtractor:
-    """Packed weights on one device + the launch sequence of ECAPA_TDNN.extract_embedding (:403-426)."""
+    """Packed weights on one device + the launch sequence of ECAPA_TDNN.extract_embedding (:403-426), driven from
+    Python op by op: the A/B and profiling twin of NativeEcapaExtractor (XVB_ECAPA_NATIVE=0, tools/bench_ecapa.py
+    --profile)."""
 
     def __init__(self, m, device):
         self.device = device

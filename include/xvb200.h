@@ -402,6 +402,33 @@ int xvb_fbank_compute(xvb_fbank_t* h, const float* wave, const int64_t* sample_o
                       int num_utts, int64_t total_frames, float* feats, void* stream);
 void xvb_fbank_destroy(xvb_fbank_t* h);
 
+/* ---------------------------------------------------------------------------------------------
+ * Whole-model extractor for ECAPA-TDNN (pytorch/model/ecapa_tdnn_xvector.py, ECAPA_TDNN.extract_embedding
+ * :403-426; canonical c1024 parameters runEcapaXvector_online.py:221-263).  Layers are set by name with the
+ * weights as the state_dict stores them (host fp32 (Cout, Cin, tot_context); eval BatchNorm folded to
+ * scale/shift; flags XVB_RELU | XVB_BN):
+ *   "layer1"; for L in 2..4: "layerL.bn1", "layerL.res0".."layerL.res6" (128 -> 128, [-d,0,d]),
+ *   "layerL.bn2", "layerL.se1" (ReLU), "layerL.se2"; "mfa"; "att_x" = the first attention conv's columns
+ *   over x with its ReLU + BatchNorm, "att_gs" = its columns over [mean | std] plus its bias (:179),
+ *   "att2"; "fc2" with bn_stats folded into the weight (and fc2's own BatchNorm for position "near").
+ * channels must be 1024 (Res2Net scale 8 x width 128, the chain kernel's shape).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct xvb_ecapa xvb_ecapa_t;
+int xvb_ecapa_create(xvb_ecapa_t** out, int feat_dim, int channels, int mfa_dim, int att_hidden, int embed_dim);
+int xvb_ecapa_set_layer(xvb_ecapa_t* h, const char* name, int Cout, int Cin, const int* context_host, int ntaps,
+                        const float* w_host, const float* bias_host, const float* bn_scale_host,
+                        const float* bn_shift_host, int flags);
+int xvb_ecapa_finalize(xvb_ecapa_t* h);
+int xvb_ecapa_embed_dim(const xvb_ecapa_t* h);
+int xvb_ecapa_feat_dim(const xvb_ecapa_t* h);
+/* feats (B, T, feat_dim) fp32 on the device -> emb (B, embed_dim) fp32 on the device; asynchronous. */
+int xvb_ecapa_extract(xvb_ecapa_t* h, const float* feats, int B, int T, float* emb, void* stream);
+int xvb_ecapa_last_launches(const xvb_ecapa_t* h);
+/* "XVBE0001" model files: the named layers as handed to xvb_ecapa_set_layer. */
+int xvb_ecapa_save(const xvb_ecapa_t* h, const char* path);
+int xvb_ecapa_load(xvb_ecapa_t** out, const char* path);
+void xvb_ecapa_destroy(xvb_ecapa_t* h);
+
 /* Load a finalized extractor from an .xvbm model file (written by asv_subtools_b200.ops.Extractor.save:
  * the layers exactly as the reference's state_dict stores them, eval BatchNorm folded) -- what
  * torch::jit::load does for the reference's runtime (runtime/extractor/torch_asv_model.cc:8-17). */

@@ -168,3 +168,31 @@ def test_online_cli_wav_scp_matches_oracle_chain(tmp_path):
     for k, wv in waves.items():
         feats = ofe.sequence_normalize(ofe.kaldi_fbank(wv, **conf["kaldi_featset"])).astype(np.float32)
         assert rel(got[k], onn.extract_embedding(fwd, feats).numpy()) < 1e-4, k
+
+
+@pytest.mark.gpu
+def test_xvb_extract_binary_runs_an_ecapa_model_file(tmp_path):
+    """XVBE0001 model file -> bin/xvb-extract: ECAPA-TDNN without Python, against the oracle forward."""
+    from asv_subtools_b200.model.ecapa_tdnn_xvector import ECAPA_TDNN
+    canon = dict(training=False, extracted_embedding="near",
+                 ecapa_params={"channels": 1024, "embd_dim": 192, "mfa_conv": 1536,
+                               "bn_params": {"momentum": 0.5, "affine": True, "track_running_stats": True}},
+                 fc2_params={"nonlinearity": "", "bn": True, "bn_params": {"momentum": 0.5, "affine": False, "track_running_stats": True}})
+    sd = onn.make_state_dict(onn.ecapa_spec(80), 201)
+    m = ECAPA_TDNN(80, 10, **canon)
+    m.load_state_dict(sd, strict=True)
+    m.cuda().eval()
+    model = str(tmp_path / "ecapa.xvbm")
+    m.extractor().save(model)
+    feats = {"e{}".format(i): onn.synthetic_feats(1, t, 80, 300 + i)[0] for i, t in enumerate([120, 120, 75])}
+    ark = str(tmp_path / "feats.ark")
+    with open(ark, "wb") as f:
+        for k, v in feats.items():
+            kaldi_io.write_mat(f, v, key=k)
+    out = str(tmp_path / "xv.ark")
+    run = subprocess.run([BIN, "--batch", "4", model, ark, "ark:" + out], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stdout + run.stderr
+    got = dict(kaldi_io.read_vec_flt_ark(out))
+    for k, v in feats.items():
+        want = onn.extract_embedding(lambda x: onn.ecapa_forward(sd, x, "near"), v).numpy()
+        assert got[k].shape == (192,) and rel(got[k], want) < 1e-4, k

@@ -196,3 +196,35 @@ def test_ecapa_vs_oracle_batch():
         ref = onn.ecapa_forward(sd, torch.from_numpy(feats).transpose(1, 2), "near").squeeze(2).numpy()
     for i in range(5):
         assert rel(got[i], ref[i]) < EMB_TOL
+
+
+def test_native_ecapa_extractor_equals_python_orchestration_and_model_file(tmp_path, monkeypatch):
+    """xvb_ecapa_t (the launch sequence in C++) against the op-by-op Python twin: same kernels, same order ->
+    bit-identical embeddings; and the XVBE0001 model file round trip."""
+    from asv_subtools_b200.model import ecapa_tdnn_xvector as mod
+    sd = onn.make_state_dict(onn.ecapa_spec(80), 201)
+    feats = torch.from_numpy(onn.synthetic_feats(5, 90, 80, 4242)).cuda()
+    outs = {}
+    for native in ("1", "0"):
+        monkeypatch.setenv("XVB_ECAPA_NATIVE", native)
+        for pos in ("near", "near_affine"):
+            m = mod.ECAPA_TDNN(80, 10, **dict(CANON, extracted_embedding=pos))
+            m.load_state_dict(sd, strict=True)
+            m.cuda().eval()
+            ex = m.extractor()
+            assert type(ex).__name__ == ("NativeEcapaExtractor" if native == "1" else "EcapaExtractor")
+            outs[native, pos] = ex.extract(feats)
+            if native == "1" and pos == "near":
+                path = str(tmp_path / "ecapa.xvbm")
+                ex.save(path)
+                ex2 = mod.NativeEcapaExtractor.load(path)
+                assert ex2.feat_dim == 80 and ex2.embed_dim == 192
+                assert torch.equal(ex2.extract(feats), outs[native, pos])
+                assert ex.last_launches > 30
+            m.invalidate()
+    for pos in ("near", "near_affine"):
+        assert torch.equal(outs["1", pos], outs["0", pos]), pos
+    with open(str(tmp_path / "ecapa.xvbm"), "r+b") as f:
+        f.truncate(1000)
+    with pytest.raises(RuntimeError):
+        mod.NativeEcapaExtractor.load(str(tmp_path / "ecapa.xvbm"))

@@ -24,6 +24,8 @@ def main():
     m = ECAPA_TDNN(F, 10, **CANON)
     m.load_state_dict(onn.make_state_dict(onn.ecapa_spec(F), 201), strict=True)
     m.cuda().eval()
+    if "--profile" in sys.argv:
+        os.environ["XVB_ECAPA_NATIVE"] = "0"   # per-op CUDA events live in the op-by-op Python twin
     ex = m.extractor()
     xs = [torch.randn(B, T, F, device="cuda") for _ in range(4)]
     for i in range(3):
@@ -58,7 +60,8 @@ def main():
         print("sum %.1f us" % (tot * 1e3))
     print(json.dumps({"workload": "ECAPA-TDNN c1024, 80-d fbank, 300-frame chunks, batch 128",
                       "ms_per_step": ms, "frames_per_s": B * T / (ms * 1e-3),
-                      "algorithmic_tflops": flop / (ms * 1e-3) / 1e12, "finite": bool(torch.isfinite(out).all())}))
+                      "algorithmic_tflops": flop / (ms * 1e-3) / 1e12, "finite": bool(torch.isfinite(out).all()),
+                      "extractor": type(ex).__name__, "launches": getattr(ex, "last_launches", None)}))
 
 
 if __name__ == "__main__":
