@@ -17,6 +17,7 @@
 // are prepared by the caller -- see EcapaExtractor.save() / the Python blueprint.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -75,6 +76,9 @@ struct xvb_ecapa {
   Planes in, X, Hh, R, Z, N, CAT, M, A1, gp, s1, zm, pp;
   float *MF = nullptr, *LOG = nullptr, *gate = nullptr, *ub = nullptr, *zmean = nullptr, *gstat = nullptr, *pstat = nullptr;
   int last_launches = 0;
+  // layer1 as an im2col view over time-padded planes (see extractor.cu): consecutive taps, feat_dim % 16 == 0
+  bool im2col_first = false;
+  int pad_front = 0, pad_back = 0;
 
   void free_ws() {
     for (void* p : ws) cudaFree(p);
@@ -202,6 +206,15 @@ extern "C" int xvb_ecapa_finalize(xvb_ecapa_t* h) {
   if ((rc = need("mfa", 3 * C, h->D, 1)) || (rc = need("att_x", h->D, h->H, 1)) || (rc = need("att_gs", 2 * h->D, h->H, 1)) ||
       (rc = need("att2", h->H, h->D, 1)) || (rc = need("fc2", 2 * h->D, h->E, 1)))
     return rc;
+  {
+    const ELayer* L0 = find(h, "layer1");
+    bool consecutive = L0->ntaps > 1 && L0->ctx[0] <= 0 && L0->ctx[L0->ntaps - 1] >= 0;
+    for (int i = 1; i < L0->ntaps; ++i) consecutive = consecutive && L0->ctx[i] == L0->ctx[i - 1] + 1;
+    const int knob = getenv("XVB_IM2COL") ? atoi(getenv("XVB_IM2COL")) : 1;
+    h->im2col_first = knob && consecutive && h->feat_dim % 16 == 0;
+    h->pad_front = h->im2col_first ? -L0->ctx[0] : 0;
+    h->pad_back = h->im2col_first ? L0->ctx[L0->ntaps - 1] : 0;
+  }
   h->finalized = true;
   return XVB_OK;
 }
@@ -218,7 +231,7 @@ static int reserve(xvb_ecapa* h, int B, int T) {
   h->free_ws();
   const int C = h->C, D = h->D;
   int rc;
-  if ((rc = h->planes(&h->in, nf, h->ldf)) || (rc = h->planes(&h->X, nf, C)) || (rc = h->planes(&h->Hh, nf, C)) ||
+  if ((rc = h->planes(&h->in, nf + nb * (size_t)(h->pad_front + h->pad_back), h->ldf)) || (rc = h->planes(&h->X, nf, C)) || (rc = h->planes(&h->Hh, nf, C)) ||
       (rc = h->planes(&h->R, nf, C)) || (rc = h->planes(&h->Z, nf, C)) || (rc = h->planes(&h->N, nf, C)) ||
       (rc = h->planes(&h->CAT, nf, 3 * C)) || (rc = h->planes(&h->M, nf, D)) || (rc = h->planes(&h->A1, nf, h->H)) ||
       (rc = h->planes(&h->gp, nb, 2 * D)) || (rc = h->planes(&h->s1, nb, h->se_dim)) || (rc = h->planes(&h->zm, nb, C)) ||
@@ -241,6 +254,8 @@ struct Run {   // one layer launch: fill only what differs from the defaults
   int64_t ld_utt = 0;
   int extra_flags = 0;
   int B, T;
+  int im2col_taps = 0;          // > 0: one-tap view, Cin = taps * L->Cin, rows overlap (x_batch_stride)
+  int64_t x_batch_stride = 0;
 };
 int launch(const Run& r, void* stream) {
   xvb_tdnn_args_t a{};
@@ -250,9 +265,11 @@ int launch(const Run& r, void* stream) {
   a.flags = r.L->flags | r.extra_flags;
   a.utt_bias = r.utt_bias; a.ld_utt_bias = r.ld_utt;
   a.context_host = r.L->ctx; a.ntaps = r.L->ntaps;
+  const int ctx0 = 0;
+  if (r.im2col_taps > 0) { a.context_host = &ctx0; a.ntaps = 1; a.x_batch_stride = r.x_batch_stride; }
   a.y_hi = r.y.hi; a.y_lo = r.y.lo; a.ldy = r.y.ld;
   a.y_f32 = r.y_f32; a.ldyf = r.ldyf;
-  a.B = r.B; a.T = r.T; a.Cin = r.L->Cin; a.Cout = r.L->Cout;
+  a.B = r.B; a.T = r.T; a.Cin = r.im2col_taps > 0 ? r.im2col_taps * r.L->Cin : r.L->Cin; a.Cout = r.L->Cout;
   return xvb_tdnn_affine_ex(&a, stream);
 }
 }  // namespace
@@ -265,11 +282,22 @@ extern "C" int xvb_ecapa_extract(xvb_ecapa_t* h, const float* feats, int B, int 
   const long before = g_launches;
   const int C = h->C, D = h->D;
   auto L = [&](const std::string& n) { return find(h, n); };
-  if ((rc = xvb_split_f32(feats, (int64_t)B * T, h->feat_dim, h->feat_dim, h->in.hi, h->in.lo, h->ldf, stream))) return rc;
+  if (h->im2col_first)
+    rc = xvb_split_frames(feats, B, T, h->feat_dim, h->in.hi, h->in.lo, h->ldf, h->pad_front, h->pad_back, stream);
+  else
+    rc = xvb_split_f32(feats, (int64_t)B * T, h->feat_dim, h->feat_dim, h->in.hi, h->in.lo, h->ldf, stream);
+  if (rc) return rc;
   Run r{};
   r.B = B; r.T = T;
   r.L = L("layer1"); r.x = h->in; r.y = h->X;
-  if ((rc = launch(r, stream))) return rc;
+  if (h->im2col_first) { r.im2col_taps = r.L->ntaps; r.x_batch_stride = (int64_t)(T + h->pad_front + h->pad_back) * h->ldf; }
+  rc = launch(r, stream);
+  if (rc && h->im2col_first) {   // overlapping tensor map refused by the driver: plain path from now on
+    h->im2col_first = false;
+    h->pad_front = h->pad_back = 0;
+    return xvb_ecapa_extract(h, feats, B, T, emb, stream);
+  }
+  if (rc) return rc;
   Planes cur = h->X;
   for (int b = 0; b < 3; ++b) {
     const std::string p = "layer" + std::to_string(b + 2) + ".";
