@@ -40,7 +40,8 @@ def _ensure_native_built():
     """The .so is git-ignored; build it in-tree if this checkout does not have it yet (nvcc
     cross-compiles without a GPU).  On the GPU box the prebuilt .so travels with the snapshot."""
     so = os.path.join(ROOT, "asv_subtools_b200", "libxvb200.so")
-    if not os.path.exists(so):
+    exe = os.path.join(ROOT, "asv_subtools_b200", "bin", "xvb-extract")
+    if not (os.path.exists(so) and os.path.exists(exe)):
         import shutil
         if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
             import __graft_entry__
