@@ -1,6 +1,6 @@
 """Host-side mirror of the reference's `libs.nnet` surface for the extraction path: parameter
 containers with the reference's names/shapes (so reference checkpoints load unchanged) and the
 `TopVirtualNnet` plugin base.  All arithmetic is delegated to the native library."""
-from .components import TdnnAffine, ReluBatchNormTdnnLayer  # noqa: F401
+from .components import FTdnnBlock, ReluBatchNormTdnnLayer, TdnnAffine  # noqa: F401
 from .pooling import StatisticsPooling  # noqa: F401
 from .framework import TopVirtualNnet, build_tdnn_extractor, for_extract_embedding  # noqa: F401

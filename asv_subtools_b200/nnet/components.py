@@ -62,6 +62,23 @@ class ReluBatchNormTdnnLayer(torch.nn.Module):
         return fold_batchnorm(self.batchnorm)
 
 
+class FTdnnBlock(torch.nn.Module):
+    """Factorised TDNN block (components.py:168-212): factor (in -> bottleneck, context [-c,0], no bias) ->
+    affine (bottleneck -> out, context [0,c]) -> ReLU -> BatchNorm -> + bypass_scale * input.  Parameter
+    containers only; the semi-orthogonal constraint step is training-side."""
+
+    def __init__(self, input_dim, output_dim, bottleneck_dim, context_size=0, bypass_scale=0.66, pad=True):
+        super().__init__()
+        if bypass_scale != 0 and input_dim != output_dim:
+            raise ValueError("bypass needs input_dim == output_dim")
+        self.input_dim, self.output_dim, self.bottleneck_dim = input_dim, output_dim, bottleneck_dim
+        self.context_size, self.bypass_scale = context_size, bypass_scale
+        c1, c2 = ([-context_size, 0], [0, context_size]) if context_size > 0 else ([0], [0])
+        self.factor = TdnnAffine(input_dim, bottleneck_dim, c1, pad=pad, bias=False)
+        self.affine = TdnnAffine(bottleneck_dim, output_dim, c2, pad=pad, bias=True)
+        self.bn = torch.nn.BatchNorm1d(output_dim, momentum=0.1, affine=True, track_running_stats=True)
+
+
 def fold_batchnorm(bn):
     if bn is None:
         return None, None

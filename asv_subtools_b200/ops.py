@@ -103,17 +103,20 @@ def tdnn_affine(x, w, cout, context, bias=None, bn_scale=None, bn_shift=None, re
     return y, yf
 
 
-def fused_pool_layer(x, w, cout, context, bias=None, bn_scale=None, bn_shift=None, relu=True, eps=1e-10, mode=0):
-    """TDNN layer whose epilogue pools over time (no (B,T,C) output) + the Chan merge: -> (B, 2*cout) fp32."""
+def fused_pool_layer(x, w, cout, context, bias=None, bn_scale=None, bn_shift=None, relu=True, eps=1e-10, mode=0, planes=False):
+    """TDNN layer whose epilogue pools over time (no (B,T,C) output) + the Chan merge: -> (B, 2*cout) fp32
+    [, the same as SplitPlanes (B,1,2*cout) for a following segment-level GEMM]."""
     b, t = x.hi.shape[0], x.hi.shape[1]
     tb = C.c_int()
     nblk = lib.xvb_pool_partial_blocks(b, t, C.byref(tb))
     partial = torch.empty(nblk, b, 2 * cout, dtype=torch.float32, device=x.hi.device)
     tdnn_affine_ex(x, w, cout, context, bias=bias, bn_scale=bn_scale, bn_shift=bn_shift, relu=relu, pool_partial=partial)
     out = torch.empty(b, 2 * cout, dtype=torch.float32, device=x.hi.device)
-    check(lib.xvb_pool_finalize(_ptr(partial), nblk, tb.value, b, t, cout, eps, mode, _ptr(out), None, None, 0, _stream()),
-          "xvb_pool_finalize")
-    return out
+    op = SplitPlanes.empty((b, 1, 2 * cout), x.hi.device) if planes else None
+    check(lib.xvb_pool_finalize(_ptr(partial), nblk, tb.value, b, t, cout, eps, mode, _ptr(out),
+                                op.hi.data_ptr() if op else None, op.lo.data_ptr() if op else None, 2 * cout if op else 0,
+                                _stream()), "xvb_pool_finalize")
+    return (out, op) if planes else out
 
 
 def tdnn_affine_ex(x, w, cout, context, x2=None, bias=None, bn_scale=None, bn_shift=None, utt_bias=None, row_bias=None,

@@ -180,6 +180,57 @@ def snowdar_xvector_spec(inputs_dim, extend=False, bn_affine=False):
 
 
 # --------------------------------------------------------------------------------------
+# Factored (F-TDNN) x-vector (pytorch/model/factored_xvector.py; FTdnnBlock components.py:168-212)
+# --------------------------------------------------------------------------------------
+FTDNN_BLOCKS = {2: (512, 1024, 2, 0.0), 3: (1024, 1024, 0, 0.66), 4: (1024, 1024, 3, 0.66), 5: (1024, 1024, 0, 0.66),
+                6: (1024, 1024, 3, 0.66), 7: (2048, 1024, 3, 0.0), 8: (1024, 1024, 3, 0.66), 9: (3072, 1024, 0, 0.0)}
+
+
+def ftdnn_block(x, sd, prefix, context_size, bypass_scale):
+    """FTdnnBlock.forward: factor (no bias, [-c,0]) -> affine ([0,c]) -> ReLU -> BN -> + bypass_scale * input."""
+    c1, c2 = ([-context_size, 0], [0, context_size]) if context_size > 0 else ([0], [0])
+    out = tdnn_affine(x, sd[prefix + ".factor.weight"], None, c1)
+    out = tdnn_affine(out, sd[prefix + ".affine.weight"], sd[prefix + ".affine.bias"], c2)
+    out = batchnorm_eval(F.relu(out), sd, prefix + ".bn")
+    return out + bypass_scale * x if bypass_scale != 0 else out
+
+
+def factored_xvector_forward(sd, x, extracted_embedding="far"):
+    """Xvector.extract_embedding, factored_xvector.py:99-122."""
+    blk = lambda i, v: ftdnn_block(v, sd, "layer{:02d}".format(i), FTDNN_BLOCKS[i][2], FTDNN_BLOCKS[i][3])  # noqa: E731
+    x1 = relu_bn_tdnn_layer(x, sd, "layer01", [-2, -1, 0, 1, 2])
+    x2 = blk(2, x1)
+    x3 = blk(3, x2)
+    x4 = blk(4, x3)
+    x5 = blk(5, x3)
+    x6 = blk(6, x5)
+    x7 = blk(7, torch.cat((x2, x4), 1))
+    x8 = blk(8, x7)
+    x9 = blk(9, torch.cat((x4, x6, x8), 1))
+    v = statistics_pooling(relu_bn_tdnn_layer(x9, sd, "layer10", [0]))
+    if extracted_embedding == "far":
+        return tdnn_affine(v, sd["embedding1.affine.weight"], sd["embedding1.affine.bias"], [0])
+    v = relu_bn_tdnn_layer(v, sd, "embedding1", [0])
+    return tdnn_affine(v, sd["embedding2.affine.weight"], sd["embedding2.affine.bias"], [0])
+
+
+def factored_xvector_spec(inputs_dim, embd_dim=512):
+    """Keys/shapes of factored Xvector(inputs_dim, N, training=False).state_dict() in registration order."""
+    spec = _affine_entries("layer01", inputs_dim, 512, [-2, -1, 0, 1, 2]) + _bn_entries("layer01.batchnorm", 512)
+    for i in range(2, 10):
+        cin, cout, c, _ = FTDNN_BLOCKS[i]
+        p = "layer{:02d}".format(i)
+        c1, c2 = ([-c, 0], [0, c]) if c > 0 else ([0], [0])
+        spec += [e for e in _affine_entries(p + ".factor", cin, 256, c1, key_style="plain") if not e[0].endswith(".bias")]
+        spec += _affine_entries(p + ".affine", 256, cout, c2, key_style="plain")
+        spec += _bn_entries(p + ".bn", cout)
+    spec += _affine_entries("layer10", 1024, 2048, [0]) + _bn_entries("layer10.batchnorm", 2048)
+    spec += _affine_entries("embedding1", 4096, embd_dim, [0]) + _bn_entries("embedding1.batchnorm", embd_dim)
+    spec += _affine_entries("embedding2", embd_dim, embd_dim, [0]) + _bn_entries("embedding2.batchnorm", embd_dim)
+    return spec
+
+
+# --------------------------------------------------------------------------------------
 # ECAPA-TDNN c1024 (pytorch/model/ecapa_tdnn_xvector.py)
 # --------------------------------------------------------------------------------------
 def res2net_block(x, sd, prefix, dilation, scale=8):

@@ -357,3 +357,24 @@ def test_snowdar_xvector_matches_reference_golden(golden, cname, extend, seed):
         assert rel(m.extract_embedding_batch(feats).cpu().numpy(), g["{}_{}".format(cname, pos)]) < EMB_TOL, pos
     with pytest.raises(NotImplementedError):
         Xvector(40, 10, SE=True)
+
+
+@pytest.mark.parametrize("pos", ["far", "near"])
+def test_factored_xvector_matches_reference_golden(golden, pos):
+    """model/factored_xvector.py (F-TDNN blocks, skip concatenations, bypass) against the reference blueprint's own
+    outputs (tests/golden/make_golden_ftdnn.py); ragged lengths against the oracle."""
+    from asv_subtools_b200.model.factored_xvector import Xvector
+    g = golden("ftdnn")
+    sd = onn.make_state_dict(onn.factored_xvector_spec(40), 401)
+    feats = onn.synthetic_feats(2, 90, 40, 1401)
+    m = Xvector(40, 10, training=False, extracted_embedding=pos)
+    m.load_state_dict(sd, strict=True)
+    m.cuda().eval()
+    emb = np.stack([m.extract_embedding(feats[i]).numpy() for i in range(2)])
+    assert rel(emb, g[pos]) < EMB_TOL
+    assert rel(m.extract_embedding_batch(feats).cpu().numpy(), g[pos]) < EMB_TOL
+    for T in (1, 5, 33):
+        f = onn.synthetic_feats(3, T, 40, 1500 + T)
+        with torch.no_grad():
+            want = onn.factored_xvector_forward(sd, torch.from_numpy(f).transpose(1, 2), pos).squeeze(2).numpy()
+        assert rel(m.extract_embedding_batch(f).cpu().numpy(), want) < EMB_TOL, T

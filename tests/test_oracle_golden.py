@@ -231,3 +231,12 @@ def test_score_normalization_cross_select(golden):
     for topn in (7, 19):
         out = osc.snorm_cross_apply(g["sn_scores"], g["sn_trial_e"], g["sn_trial_t"], g["sn_enroll_cohort"], g["sn_test_cohort"], topn)
         assert np.max(np.abs(out - gc["cross_top%d" % topn])) < 1e-9
+
+
+def test_factored_xvector_oracle_matches_reference(golden):
+    g = golden("ftdnn")
+    sd = onn.make_state_dict(onn.factored_xvector_spec(40), 401)
+    feats = onn.synthetic_feats(2, 90, 40, 1401)
+    for pos in ("far", "near"):
+        emb = np.stack([onn.extract_embedding(lambda x: onn.factored_xvector_forward(sd, x, pos), feats[i]).numpy() for i in range(2)])
+        assert rel(emb, g[pos]) < RTOL, pos

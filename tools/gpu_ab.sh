@@ -1,7 +1,10 @@
 #!/bin/bash
-# Scratch GPU visit: native ECAPA extractor (tests + bench native vs Python twin) and the newest tests.
-TAG=${1:-r02a}
+# Scratch GPU visit: compute-sanitizer on the SIMT kernels added late (fbank, front-end, score normalisation, PLDA helpers).
+TAG=${1:-r02b}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_ecapa.py tests/test_gpu_deploy.py tests/test_gpu_scoring.py tests/test_gpu_plda_train.py -m gpu -q > gpurun_out/${TAG}_pytest_new.log 2>&1; echo "pytest rc=$?"; tail -25 gpurun_out/${TAG}_pytest_new.log
-timeout 300 python tools/bench_ecapa.py 10 > gpurun_out/${TAG}_ecapa_native.json 2> gpurun_out/${TAG}_ecapa_native.err; echo "ecapa native rc=$?"; cat gpurun_out/${TAG}_ecapa_native.json; tail -3 gpurun_out/${TAG}_ecapa_native.err
-XVB_ECAPA_NATIVE=0 timeout 300 python tools/bench_ecapa.py 10 > gpurun_out/${TAG}_ecapa_python.json 2> gpurun_out/${TAG}_ecapa_python.err; echo "ecapa python rc=$?"; cat gpurun_out/${TAG}_ecapa_python.json
+export PYTHONUNBUFFERED=1
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_fbank.py tests/test_gpu_frontend.py -m gpu -q -x > gpurun_out/${TAG}_memcheck_frontend.log 2>&1; echo "memcheck fbank/frontend rc=$?"; grep -c "Invalid\|out of bounds" gpurun_out/${TAG}_memcheck_frontend.log; tail -4 gpurun_out/${TAG}_memcheck_frontend.log
+timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_fbank.py -m gpu -q -x -k "match_reference or batched" > gpurun_out/${TAG}_racecheck_fbank.log 2>&1; echo "racecheck fbank rc=$?"; grep -i "race\|hazard" gpurun_out/${TAG}_racecheck_fbank.log | head -5; tail -3 gpurun_out/${TAG}_racecheck_fbank.log
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_scoring.py -m gpu -q -x -k "cross_select or normalization" > gpurun_out/${TAG}_memcheck_snorm.log 2>&1; echo "memcheck snorm rc=$?"; tail -3 gpurun_out/${TAG}_memcheck_snorm.log
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_plda_train.py -m gpu -q -x -k "golden or coral" > gpurun_out/${TAG}_memcheck_plda.log 2>&1; echo "memcheck plda rc=$?"; tail -3 gpurun_out/${TAG}_memcheck_plda.log
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_trial_histogram.py -m gpu -q -x -k "row_units or plda_terms" > gpurun_out/${TAG}_memcheck_hist.log 2>&1; echo "memcheck hist rc=$?"; tail -3 gpurun_out/${TAG}_memcheck_hist.log
