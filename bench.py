@@ -41,6 +41,9 @@ POOL_BYTES_PER_STEP = 1212000 * B  # 4*(C*T + 2C) B/utt, C=1500,
 NUM_INPUT_BATCHES = 8             # rotate 8 x 16.4 MB inputs; activations per step ~1.1 GB >> 126 MB L2
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
 NCU_GEMM_TRAFFIC_BYTES_PER_LAUNCH = int((69.3 + 173.6 + 177.3 + 163.6 + 155.4 + 9.3) * 1e6 / 6)  # profiles/r01x_gemm_ncu_summary.txt
+# sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active and gpu__time_duration of the same capture
+NCU_TENSOR_PIPE = {"tdnn1": (46.4, 73.1), "tdnn2": (84.0, 157.9), "tdnn3": (83.0, 157.3), "tdnn4": (58.4, 75.4),
+                   "tdnn5+pool": (80.3, 155.6), "tdnn6": (16.6, 12.1)}
 NCU_POOL_TRAFFIC_BYTES_PER_LAUNCH = int((307.2 + 5.8) * 1e6)   # profiles/r01x_pool_ncu_summary.txt
 METRIC = "frames/sec x-vector extraction (80-d fbank)"
 UNIT = "frames/s"
@@ -364,6 +367,10 @@ def run_native(args, rank, world, local_rank):
                      "algorithmic_flop_per_launch_avg": GEMM_FLOP_PER_STEP / 6,
                      "executed_tflops": 3 * achieved, "executed_frac": 3 * achieved / pk["bf16_sustained"],
                      "note": "3 bf16 MMAs per algorithmic MAC (hi*hi + lo*hi + hi*lo) to hold 1e-4 parity",
+                     "ncu_tensor_pipe_pct": dict({k: v[0] for k, v in NCU_TENSOR_PIPE.items()},
+                                                 time_weighted=sum(a * b for a, b in NCU_TENSOR_PIPE.values()) /
+                                                 sum(b for _, b in NCU_TENSOR_PIPE.values()),
+                                                 source="profiles/r01x_gemm_ncu_summary.txt (ncu --set full, one step)"),
                      "gemm_ms_per_step": gemm_ms},
         "roofline_stats_pool": {"bound": "hbm", "kernel": "stats_pool_tma_kernel (standalone, (256,200,1500) fp32, "
                                                           "12 back-to-back launches over 3 rotating inputs)",

@@ -1,10 +1,7 @@
 #!/bin/bash
-# Scratch GPU visit: compute-sanitizer on the SIMT kernels added late (fbank, front-end, score normalisation, PLDA helpers).
-TAG=${1:-r02b}
+# Scratch GPU visit: F-TDNN blueprint tests; memcheck over the tcgen05 layer / pooling / Res2Net / extractor tests.
+TAG=${1:-r02c}
 mkdir -p gpurun_out
-export PYTHONUNBUFFERED=1
-timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_fbank.py tests/test_gpu_frontend.py -m gpu -q -x > gpurun_out/${TAG}_memcheck_frontend.log 2>&1; echo "memcheck fbank/frontend rc=$?"; grep -c "Invalid\|out of bounds" gpurun_out/${TAG}_memcheck_frontend.log; tail -4 gpurun_out/${TAG}_memcheck_frontend.log
-timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_fbank.py -m gpu -q -x -k "match_reference or batched" > gpurun_out/${TAG}_racecheck_fbank.log 2>&1; echo "racecheck fbank rc=$?"; grep -i "race\|hazard" gpurun_out/${TAG}_racecheck_fbank.log | head -5; tail -3 gpurun_out/${TAG}_racecheck_fbank.log
-timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_scoring.py -m gpu -q -x -k "cross_select or normalization" > gpurun_out/${TAG}_memcheck_snorm.log 2>&1; echo "memcheck snorm rc=$?"; tail -3 gpurun_out/${TAG}_memcheck_snorm.log
-timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_plda_train.py -m gpu -q -x -k "golden or coral" > gpurun_out/${TAG}_memcheck_plda.log 2>&1; echo "memcheck plda rc=$?"; tail -3 gpurun_out/${TAG}_memcheck_plda.log
-timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_trial_histogram.py -m gpu -q -x -k "row_units or plda_terms" > gpurun_out/${TAG}_memcheck_hist.log 2>&1; echo "memcheck hist rc=$?"; tail -3 gpurun_out/${TAG}_memcheck_hist.log
+timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -k "factored or snowdar" > gpurun_out/${TAG}_pytest_ftdnn.log 2>&1; echo "pytest ftdnn rc=$?"; tail -12 gpurun_out/${TAG}_pytest_ftdnn.log
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "tdnn_gemm_vs_oracle or fused_pooling or zero_padding or stats_pool or im2col or edge_lengths" > gpurun_out/${TAG}_memcheck_gemm.log 2>&1; echo "memcheck gemm rc=$?"; grep -h "passed\|failed\|ERROR SUMMARY" gpurun_out/${TAG}_memcheck_gemm.log | tail -3
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_ecapa.py -m gpu -q -x -k "res2net or se_apply or attn or native" > gpurun_out/${TAG}_memcheck_ecapa.log 2>&1; echo "memcheck ecapa rc=$?"; grep -h "passed\|failed\|ERROR SUMMARY" gpurun_out/${TAG}_memcheck_ecapa.log | tail -3
