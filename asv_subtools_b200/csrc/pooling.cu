@@ -22,12 +22,15 @@ constexpr int kPoolWarps = 8;
 constexpr int kPoolBoxRows = 40;                 // frames per TMA box (20 KB)
 constexpr int kPoolSlabRows = 200;               // 5 boxes resident: 100 KB -> two CTAs per SM
 constexpr int kPoolNumBars = (kPoolSlabRows + kPoolBoxRows - 1) / kPoolBoxRows;
-constexpr int kPoolSmemBytes = kPoolNumBars * kPoolBoxRows * 128 * 4 + kPoolWarps * 128 * 4 + 128;
+constexpr int kPoolSmemBytes = kPoolNumBars * kPoolBoxRows * 128 * 4 + kPoolWarps * 128 * 4 + 128 + 128 /* alignment slack */;
 
 __global__ void __launch_bounds__(kPoolWarps * 32, 2)
 stats_pool_tma_kernel(const __grid_constant__ CUtensorMap map_x, int T, int C, float eps, int mode, float* __restrict__ out,
                       __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, long long ldo) {
-  extern __shared__ __align__(128) uint8_t pool_smem[];
+  // TMA destinations need 128-byte alignment; CUDA only promises 16 for dynamic shared memory (and a tool that adds
+  // its own static shared memory, e.g. compute-sanitizer, does shift the base), so align by hand
+  extern __shared__ uint8_t pool_smem_raw[];
+  uint8_t* pool_smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pool_smem_raw) + 127) & ~uintptr_t(127));
   float* slab = reinterpret_cast<float*>(pool_smem);                                  // [rows][128]
   float* scratch = slab + kPoolNumBars * kPoolBoxRows * 128;                          // [warps][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + kPoolWarps * 128);           // [kPoolNumBars]
