@@ -66,7 +66,7 @@ struct TdnnGemmParams {
   long long ld_utt;
   int log2_tb;            // Tb is a power of two
   int debug;              // -DXVB_TIMING_EXPERIMENTS only: bit0 skip epilogue, bit1 skip MMA, bit2 skip store issue, bit3 skip LDTM
-  int store_mode;         // 0: epilogue slab -> TMA store; 1: slab -> coalesced st.global (no TMA queueing behind loads)
+  int store_mode;         // 0: epilogue slab -> TMA store; 1: slab -> coalesced st.global; 2: registers -> st.global (sector-sized)
   float* pool_partial;    // fused statistics pooling: per (time block, utterance, channel) [mean | M2] partials
   int num_src;            // 1, or 2: a second A source accumulated with the same weights (W.(x + x2))
   // M-unit sharding (a unit = kCta x 128 rows): this launch walks units unit_first + k * unit_stride
@@ -517,6 +517,44 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
           f[4 * g + 0] = x0; f[4 * g + 1] = x1; f[4 * g + 2] = x2; f[4 * g + 3] = x3;
         }
         const int n = n0 + ch * 32;
+        if (p.store_mode == 2) {
+          // straight from registers: a thread owns 16 consecutive columns of its row = one 32-byte sector per
+          // bf16 plane (64 bytes of fp32).  Not coalesced across lanes, but every store fills whole sectors and
+          // the epilogue needs neither the slab, nor its two barriers per chunk, nor the wait for the TMA engine
+          // to have read the previous chunk -- which is what bounds the layers with few K blocks.
+          if (valid) {
+            const long long grow = (long long)b * p.T + t;
+            const int c16 = n + half * 16;
+            if (planes) {
+              __nv_bfloat16* dh = p.y_hi + grow * p.ldy + c16;
+              __nv_bfloat16* dl = p.y_lo + grow * p.ldy + c16;
+#pragma unroll
+              for (int g = 0; g < 2; ++g) {
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  __nv_bfloat16 h0, l0, h1, l1;
+                  split_bf16(f[g * 8 + 2 * k], h0, l0);
+                  split_bf16(f[g * 8 + 2 * k + 1], h1, l1);
+                  h[k] = pack_bf16x2(h0, h1);
+                  l[k] = pack_bf16x2(l0, l1);
+                }
+                if (c16 + 8 * g < p.Cout) {   // Cout % 8 == 0 on this path
+                  *reinterpret_cast<uint4*>(dh + 8 * g) = make_uint4(h[0], h[1], h[2], h[3]);
+                  *reinterpret_cast<uint4*>(dl + 8 * g) = make_uint4(l[0], l[1], l[2], l[3]);
+                }
+              }
+            }
+            if (f32o) {
+              float* df = p.y_f32 + grow * p.ldyf + c16;
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                if (c16 + 4 * g < p.Cout)     // Cout % 4 == 0 on this path
+                  *reinterpret_cast<float4*>(df + 4 * g) = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+            }
+          }
+          return;
+        }
         const bool direct = p.store_mode == 1;
         if (planes) {
           // the previous store must have finished reading the slab
@@ -767,11 +805,11 @@ static int gemm_cta_mode() {
 
 // Epilogue store path: TMA stores from the swizzled slab (default), or XVB_GEMM_STORE=direct for
 // coalesced st.global after a transpose through the same slab (measured 5-10 % slower, kept as a knob).
-static int gemm_store_mode() {
-  static int mode = -1;
-  if (mode < 0) {
+static int gemm_store_mode() {   // -1: automatic (per layer shape)
+  static int mode = -2;
+  if (mode == -2) {
     const char* e = getenv("XVB_GEMM_STORE");
-    mode = (e && e[0] == 'd') ? 1 : 0;
+    mode = !e ? -1 : e[0] == 'd' ? 1 : e[0] == 'r' ? 2 : e[0] == 't' ? 0 : -1;
   }
   return mode;
 }
@@ -931,13 +969,20 @@ int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream, const TrialHis
   p.log2_tb = 0;
   while ((1 << p.log2_tb) < p.Tb) ++p.log2_tb;
   p.store_mode = gemm_store_mode();
+  if (p.store_mode < 0) {
+    // few K blocks per tile: the epilogue, not the MMAs, sets the pace, and its cost is the slab hand-over to
+    // the TMA store engine -> store from registers.  Many K blocks: the TMA store is hidden anyway and frees
+    // the LSU.  (XVB_GEMM_STORE=tma|reg|direct forces one.)
+    const long long kblk = (long long)(a.x2_hi ? 2 : 1) * ntaps * ((Cin + kBlockK - 1) / kBlockK);
+    p.store_mode = (kblk <= 12 && Cout % 8 == 0 && (!a.y_hi || a.ldy % 8 == 0)) ? 2 : 0;
+  }
 #ifdef XVB_TIMING_EXPERIMENTS
   static const int dbg = getenv("XVB_GEMM_DEBUG") ? atoi(getenv("XVB_GEMM_DEBUG")) : 0;
   p.debug = dbg;
 #else
   p.debug = 0;
 #endif
-  if (p.store_mode == 1) {  // vector stores need whole 16-byte groups inside the row
+  if (p.store_mode >= 1) {  // vector stores need whole 16-byte groups inside the row
     if (a.y_hi) XVB_CHECK_ARG(Cout % 8 == 0, "xvb_tdnn_affine: plane output needs Cout%%8==0 (Cout=%d)", Cout);
     if (a.y_f32) XVB_CHECK_ARG(Cout % 4 == 0, "xvb_tdnn_affine: fp32 output needs Cout%%4==0 (Cout=%d)", Cout);
   }
