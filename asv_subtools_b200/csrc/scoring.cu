@@ -266,6 +266,52 @@ __global__ void plda_em_rows_T_kernel(const float* __restrict__ u, const float* 
   }
 }
 
+// Kaldi-style PLDA scoring in the diagonalised space (score/pyplda/plda_base.py: transform_ivector :93-107,
+// get_normalization_factor :151-158, log_likelihood_ratio :109-136).  One warp per row.
+// u <- u * sqrt(D / sum_d u_d^2 / (psi_d + 1/n))   (simple: sqrt(D) / ||u||)
+__global__ void plda_normalize_rows_kernel(float* __restrict__ u, const float* __restrict__ psi, const float* __restrict__ n,
+                                           long long rows, int D, int simple) {
+  const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float* x = u + r * D;
+  const float inv_n = 1.f / (n ? n[r] : 1.f);
+  float s = 0.f;
+  for (int d = lane; d < D; d += 32) s += x[d] * x[d] * (simple ? 1.f : 1.f / (psi[d] + inv_n));
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float f = sqrtf((float)D / s);
+  for (int d = lane; d < D; d += 32) x[d] *= f;
+}
+
+// LLR(i,j) = [t_j^2 | t_j] . [-1/(2 v_i) | m_i / v_i] + row_i + col_j with m = n psi/(n psi + 1) u, v = 1 + psi/(n psi + 1):
+// side 0 (enroll): a = [-1/(2v) | m/v], term = -1/2 (sum log v + sum m^2/v)
+// side 1 (test)  : a = [t^2 | t],      term = +1/2 (sum log(psi+1) + sum t^2/(psi+1))
+__global__ void plda_llr_operands_kernel(const float* __restrict__ u, const float* __restrict__ psi, const float* __restrict__ n,
+                                         long long rows, int D, int side, float* __restrict__ a, float* __restrict__ term) {
+  const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* x = u + r * D;
+  float* o = a + r * 2 * D;
+  const float nn = (side == 0 && n) ? n[r] : 1.f;
+  float acc = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float p = psi[d], xv = x[d];
+    if (side == 0) {
+      const float m = nn * p / (nn * p + 1.f) * xv, v = 1.f + p / (nn * p + 1.f);
+      o[d] = -0.5f / v;
+      o[D + d] = m / v;
+      acc += logf(v) + m * m / v;
+    } else {
+      o[d] = xv * xv;
+      o[D + d] = xv;
+      acc += logf(p + 1.f) + xv * xv / (p + 1.f);
+    }
+  }
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (lane == 0) term[r] = side == 0 ? -0.5f * acc : 0.5f * acc;
+}
+
 // out (Ne, Nt) = A (Ne, D) . Bm (Nt, D)^T  [+ row_bias[i] + col_bias[j]] through the tcgen05 layer.
 static int matmul_nt(const float* A, int64_t Ne, const float* Bm, int64_t Nt, int D, const float* row_bias,
                      const float* col_bias, float* out, int64_t ldo, uint16_t* out_hi, uint16_t* out_lo,
@@ -530,6 +576,30 @@ extern "C" int xvb_snorm_cross_trials(const float* scores, const int32_t* trial_
   const long long threads = num_trials * 32;
   snorm_cross_trials_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       scores, trial_e, trial_t, enroll_cohort, lde, test_cohort, ldt, top_enroll, top_test, top_n, num_trials, out);
+  XVB_LAUNCH_CHECK();
+  return XVB_OK;
+}
+
+extern "C" int xvb_plda_normalize_rows(float* u, const float* psi, const float* num_examples, int64_t rows, int D,
+                                       int simple_length_norm, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  XVB_CHECK_ARG(u && psi && rows > 0 && D > 0, "xvb_plda_normalize_rows: bad arguments");
+  const long long threads = rows * 32;
+  plda_normalize_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(u, psi, num_examples, rows, D,
+                                                                                              simple_length_norm);
+  XVB_LAUNCH_CHECK();
+  return XVB_OK;
+}
+
+extern "C" int xvb_plda_llr_operands(const float* u, const float* psi, const float* num_examples, int64_t rows, int D, int side,
+                                     float* operand, float* term, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  XVB_CHECK_ARG(u && psi && operand && term && rows > 0 && D > 0 && (side == 0 || side == 1), "xvb_plda_llr_operands: bad arguments");
+  const long long threads = rows * 32;
+  plda_llr_operands_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(u, psi, num_examples, rows, D, side,
+                                                                                            operand, term);
   XVB_LAUNCH_CHECK();
   return XVB_OK;
 }

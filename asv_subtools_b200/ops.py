@@ -399,6 +399,24 @@ def plda_em_rows(u, n, weight, psi):
     return what, resid
 
 
+def plda_normalize_rows(u, psi, num_examples=None, simple=False):
+    """In place: u[r] *= sqrt(D / sum_d u_d^2 / (psi_d + 1/n_r))  (simple: sqrt(D) / ||u[r]||)."""
+    u = _req(u, torch.float32, "u")
+    check(lib.xvb_plda_normalize_rows(_ptr(u), _ptr(_req(psi, torch.float32, "psi")), _ptr(num_examples), u.shape[0], u.shape[1],
+                                      int(bool(simple)), _stream()), "xvb_plda_normalize_rows")
+    return u
+
+
+def plda_llr_operands(u, psi, num_examples, side):
+    """-> ((rows, 2D) operand, (rows,) term) of the Kaldi-style PLDA LLR; side 0 = enroll, 1 = test."""
+    u = _req(u, torch.float32, "u")
+    a = torch.empty(u.shape[0], 2 * u.shape[1], dtype=torch.float32, device=u.device)
+    term = torch.empty(u.shape[0], dtype=torch.float32, device=u.device)
+    check(lib.xvb_plda_llr_operands(_ptr(u), _ptr(_req(psi, torch.float32, "psi")), _ptr(num_examples), u.shape[0], u.shape[1],
+                                    int(side), _ptr(a), _ptr(term), _stream()), "xvb_plda_llr_operands")
+    return a, term
+
+
 def trial_histogram(enroll, enroll_spk, test, test_spk, lo, hi, nbins=2048, row_term=None, col_term=None,
                     symmetric=False, unit_first=0, unit_stride=1, out=None):
     """(2, nbins) int64 histogram [nontarget | target] of enroll.test^T (+ terms) -- scores are never

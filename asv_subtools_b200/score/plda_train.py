@@ -135,6 +135,55 @@ class PLDA:
         self.psi = s
         self.offset = -1.0 * (self.transform @ self.mean)
 
+    # ---- Kaldi-style scoring (ivector-plda-scoring as restated by plda_base.py :93-136, :151-158) on the GPU
+    def _dev(self, device):
+        if getattr(self, "_d", None) is None or self._d[0] != str(device):
+            f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device)  # noqa: E731
+            self._d = (str(device), f32(self.transform), f32(self.offset.reshape(-1)), f32(self.psi))
+        return self._d[1:]
+
+    def smooth_within_class_covariance(self, smoothing_factor):
+        """Kaldi's SmoothWithinClassCovariance (ivector-copy-plda --smoothing): within (the identity here) grows by
+        smoothing_factor * psi; psi and the rows of `transform` are rescaled so that it is the identity again.  (The
+        reference's restatement, plda_base.py:138-149, multiplies `np.diag(.) * transform` elementwise, which zeroes
+        the transform's off-diagonal entries; it has no caller.  This is the Kaldi operation.)"""
+        w = 1.0 + smoothing_factor * self.psi
+        self.psi = self.psi / w
+        self.transform = self.transform * (w ** -0.5)[:, None]
+        self.offset = -1.0 * (self.transform @ self.mean)
+        self._d = None
+
+    def transform_ivectors(self, x, num_examples=None, normalize_length=True, simple_length_norm=False):
+        """x (N, D) fp32 CUDA -> transformed (N, D); num_examples (N,) (enroll averages of n utterances) or None = 1."""
+        t, off, psi = self._dev(x.device)
+        u = ops.matmul_nt(x, t, col_bias=off)
+        if normalize_length:
+            n = None if num_examples is None else torch.as_tensor(num_examples, dtype=torch.float32, device=x.device).contiguous()
+            ops.plda_normalize_rows(u, psi, n, simple_length_norm)
+        return u
+
+    def _operands(self, enroll_u, num_examples, test_u):
+        _, _, psi = self._dev(enroll_u.device)
+        n = None if num_examples is None else torch.as_tensor(num_examples, dtype=torch.float32, device=enroll_u.device).contiguous()
+        return ops.plda_llr_operands(enroll_u, psi, n, 0) + ops.plda_llr_operands(test_u, psi, None, 1)
+
+    def log_likelihood_ratio_matrix(self, enroll_u, num_examples, test_u):
+        """(Ne, Nt) log-likelihood ratios of transformed vectors: one GEMM with K = 2D plus row / column terms."""
+        a, row, b, col = self._operands(enroll_u, num_examples, test_u)
+        return ops.matmul_nt(a, b, row_bias=row, col_bias=col)
+
+    def log_likelihood_ratio_trials(self, enroll_u, num_examples, test_u, trial_e, trial_t):
+        a, row, b, col = self._operands(enroll_u, num_examples, test_u)
+        return ops.bilinear_trials(a, b, trial_e, trial_t, row, col)
+
+    @classmethod
+    def read_ori(cls, path):
+        """From the three-vector file PldaEstimation.plda_write produces (`<plda>.ori`)."""
+        parts = dict(kaldi_io.read_vec_flt_ark(path))
+        d = np.asarray(parts["mean"]).shape[0]
+        return cls(parts["mean"], np.asarray(parts["within_var"], dtype=np.float64).reshape(d, d),
+                   np.asarray(parts["between_var"], dtype=np.float64).reshape(d, d))
+
     def plda_trans_write(self, plda):
         with open(plda, "w") as f:
             f.write("<Plda>  [ " + " ".join(map(str, self.mean.reshape(-1))) + " ]\n")

@@ -307,6 +307,20 @@ int xvb_center_rows_transposed(const float* x, const int32_t* spk, const float* 
 int xvb_plda_em_rows(const float* u, const float* n, const float* weight, const float* psi, int S, int D, float* what_T,
                      float* resid_T, int64_t ldo, void* stream);
 
+/* Kaldi-style PLDA scoring in the diagonalised space, the arithmetic of ivector-plda-scoring as restated by the
+ * reference's score/pyplda/plda_base.py (PLDA.transform_ivector :93-107, get_normalization_factor :151-158,
+ * log_likelihood_ratio :109-136; called from score/score.sh:99-121 through the Kaldi binary):
+ *   u = transform . x + offset                       -> xvb_matmul_nt with col_bias = offset
+ *   u *= sqrt(D / sum_d u_d^2 / (psi_d + 1/n))       -> xvb_plda_normalize_rows (simple: sqrt(D)/||u||)
+ *   LLR(i,j) = [t_j^2 | t_j] . [-1/(2 v_i) | m_i/v_i] + term_i + term_j,  m = n psi/(n psi+1) u, v = 1 + psi/(n psi+1)
+ *     -> xvb_plda_llr_operands(side 0 = enroll with num_examples n, side 1 = test) writes the (rows, 2D) operand
+ *        and the per-row term; the score matrix is xvb_matmul_nt(enroll_operand, test_operand, row, col), listed
+ *        trials xvb_bilinear_trials. */
+int xvb_plda_normalize_rows(float* u, const float* psi, const float* num_examples, int64_t rows, int D,
+                            int simple_length_norm, void* stream);
+int xvb_plda_llr_operands(const float* u, const float* psi, const float* num_examples, int64_t rows, int D, int side,
+                          float* operand, float* term, void* stream);
+
 /* Fused consumer for score matrices too large to store (BASELINE configs 4/5: 10^12 cosine trials,
  * 10^10 PLDA trials; SURVEY Appendix A "fused consumer"): every score
  *   s(i,j) = <enroll[i], test[j]> + row_term[i] + col_term[j]        (terms may be NULL)

@@ -124,3 +124,27 @@ def coral_adapt(mean, within, between, adapt, mean_diff_scale=1.0):
     ei, qi = np.linalg.eigh(var)
     a = (qi @ np.diag(np.sqrt(ei)) @ qi.T) @ (qo @ np.diag(1.0 / np.sqrt(eo)) @ qo.T)
     return m.reshape(-1), a @ within @ a.T, a @ between @ a.T
+
+
+# ---------------------------------------------------------------- Kaldi-style PLDA scoring (plda_base.py PLDA)
+def plda_transform(x, transform, offset, psi, num_examples=1, normalize_length=True, simple_length_norm=False,
+                   reference_dim_quirk=False):
+    """PLDA.transform_ivector, plda_base.py:93-107 (+ get_normalization_factor :151-158).  The reference only accepts a
+    column vector and then sets self.dim = ivector.shape[-1] = 1 (:95), so it scales by sqrt(1/...) where Kaldi's
+    ivector-plda-scoring (the binary score.sh actually calls) uses sqrt(D/...); reference_dim_quirk=True reproduces
+    the reference as written, False is the Kaldi semantics the GPU path implements."""
+    u = transform @ np.asarray(x, dtype=np.float64) + np.asarray(offset, dtype=np.float64).reshape(-1)
+    d = 1 if reference_dim_quirk else u.shape[0]
+    if normalize_length:
+        f = np.sqrt(d) / np.linalg.norm(u) if simple_length_norm else np.sqrt(d / np.dot(1.0 / (psi + 1.0 / num_examples), u ** 2))
+        u = f * u
+    return u
+
+
+def plda_llr(train_u, num_utts, test_u, psi):
+    """PLDA.log_likelihood_ratio, plda_base.py:109-136."""
+    mean = num_utts * psi / (num_utts * psi + 1.0) * train_u
+    var = 1.0 + psi / (num_utts * psi + 1.0)
+    given = -0.5 * (np.sum(np.log(var)) + np.sum((test_u - mean) ** 2 / var))
+    without = -0.5 * (np.sum(np.log(psi + 1.0)) + np.sum(test_u ** 2 / (psi + 1.0)))
+    return given - without

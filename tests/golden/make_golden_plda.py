@@ -44,6 +44,21 @@ def main():
         out[name + "_scatter"] = stats.offset_scatter
         plda = est.get_output()
         out[name + "_psi"] = np.asarray(plda.psi)
+        if name == "d16":
+            est_d16 = est
+    # Kaldi-style scoring with the diagonalised d16 model: transform_ivector + log_likelihood_ratio (1-D vectors)
+    plda = est_d16.get_output()
+    rng = np.random.RandomState(31)
+    ev, tv = rng.standard_normal((5, 16)) * 1.3 + 0.2, rng.standard_normal((7, 16)) * 1.3 + 0.2
+    nu = np.array([1, 3, 2, 5, 1])
+    # column vectors: the only shape transform_ivector accepts -- and for which it sets self.dim = 1 (:95), so its
+    # length normalisation is sqrt(1/...) instead of Kaldi's sqrt(D/...); stored as the reference computes it
+    eu = np.stack([np.asarray(plda.transform_ivector(ev[i].reshape(-1, 1), int(nu[i]))).reshape(-1) for i in range(5)])
+    tu = np.stack([np.asarray(plda.transform_ivector(tv[j].reshape(-1, 1), 1)).reshape(-1) for j in range(7)])
+    llr = np.array([[float(np.asarray(plda.log_likelihood_ratio(eu[i].reshape(-1, 1), int(nu[i]), tu[j].reshape(-1, 1))).reshape(-1)[0])
+                     for j in range(7)] for i in range(5)])
+    out.update(kaldi_enroll=ev, kaldi_test=tv, kaldi_num_utts=nu, kaldi_enroll_u=eu, kaldi_test_u=tu, kaldi_llr=llr,
+               kaldi_transform=plda.transform, kaldi_psi=np.asarray(plda.psi), kaldi_offset=np.asarray(plda.offset).reshape(-1))
     # CORAL adaptation (ivector-adapt-plda-coral.py) of the d16 model to a shifted, rescaled domain
     spec = importlib.util.spec_from_file_location("coral", "/root/reference/score/pyplda/ivector-adapt-plda-coral.py")
     cm = importlib.util.module_from_spec(spec)

@@ -100,3 +100,34 @@ def test_gpu_coral_adaptation_and_diagonalised_output(golden, tmp_path):
     p.plda_trans_write(str(tmp_path / "plda.txt"))
     txt = open(str(tmp_path / "plda.txt")).read()
     assert txt.startswith("<Plda>  [ ") and txt.rstrip().endswith("</Plda>")
+
+
+def test_gpu_kaldi_style_plda_scoring(golden):
+    """PLDA.transform_ivectors / log_likelihood_ratio_matrix|trials (Kaldi semantics) against the float64 oracle, and
+    against the reference's own numbers where they coincide (its vectors are ours / sqrt(D), see the oracle)."""
+    from asv_subtools_b200.score.plda_train import PLDA
+    g = golden("plda_train")
+    p = PLDA(g["d16_mean"], g["d16_within"], g["d16_between"])
+    assert rel(np.sort(p.psi), np.sort(g["kaldi_psi"])) < 1e-9
+    T, off, psi = p.transform, p.offset.reshape(-1), p.psi
+    ev, tv, nu = g["kaldi_enroll"].astype(np.float32), g["kaldi_test"].astype(np.float32), g["kaldi_num_utts"]
+    eu = p.transform_ivectors(torch.from_numpy(ev).cuda(), nu)
+    tu = p.transform_ivectors(torch.from_numpy(tv).cuda())
+    want_e = np.stack([opt.plda_transform(ev[i], T, off, psi, int(nu[i])) for i in range(5)])
+    want_t = np.stack([opt.plda_transform(tv[j], T, off, psi, 1) for j in range(7)])
+    assert rel(eu.cpu().numpy(), want_e) < 2e-5 and rel(tu.cpu().numpy(), want_t) < 2e-5
+    # the rows agree with the reference's up to the sign of each eigenvector, the order of psi (PldaEstimation.get_output
+    # keeps eigh's ascending order, this class sorts descending like plda_base.PLDA.get_output) and the sqrt(D) of its dim quirk
+    assert rel(np.abs(eu.cpu().numpy())[:, ::-1] / 4.0, np.abs(g["kaldi_enroll_u"])) < 2e-5
+    pad = torch.zeros(1, 16, device="cuda")                                   # matmul_nt wants a multiple of 4 columns
+    tu8 = torch.cat([tu, pad]).contiguous()
+    S = p.log_likelihood_ratio_matrix(eu, nu, tu8).cpu().numpy()[:, :7]
+    want = np.array([[opt.plda_llr(want_e[i], int(nu[i]), want_t[j], psi) for j in range(7)] for i in range(5)])
+    assert np.max(np.abs(S - want)) < 2e-4 * max(1.0, np.max(np.abs(want)))
+    te = torch.tensor([0, 4, 2, 2], dtype=torch.int32, device="cuda")
+    tt = torch.tensor([6, 0, 3, 1], dtype=torch.int32, device="cuda")
+    s = p.log_likelihood_ratio_trials(eu, nu, tu, te, tt).cpu().numpy()
+    assert np.max(np.abs(s - want[[0, 4, 2, 2], [6, 0, 3, 1]])) < 2e-4 * max(1.0, np.max(np.abs(want)))
+    # smoothing keeps T W T^T = I structure: psi shrinks, rows of the transform rescale
+    p.smooth_within_class_covariance(0.1)
+    assert np.all(p.psi < psi + 1e-12) and rel(p.transform @ g["d16_within"] @ p.transform.T, np.diag(1.0 / (1.0 + 0.1 * psi))) < 1e-9

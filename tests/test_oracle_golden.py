@@ -240,3 +240,19 @@ def test_factored_xvector_oracle_matches_reference(golden):
     for pos in ("far", "near"):
         emb = np.stack([onn.extract_embedding(lambda x: onn.factored_xvector_forward(sd, x, pos), feats[i]).numpy() for i in range(2)])
         assert rel(emb, g[pos]) < RTOL, pos
+
+
+def test_kaldi_style_plda_scoring_oracle_matches_reference(golden):
+    """oracle.plda_train.plda_transform / plda_llr vs the reference's PLDA.transform_ivector / log_likelihood_ratio."""
+    from oracle import plda_train as opt
+    g = golden("plda_train")
+    T, off, psi = g["kaldi_transform"], g["kaldi_offset"], g["kaldi_psi"]
+    for i in range(5):
+        u = opt.plda_transform(g["kaldi_enroll"][i], T, off, psi, int(g["kaldi_num_utts"][i]), reference_dim_quirk=True)
+        assert rel(u, g["kaldi_enroll_u"][i]) < 1e-12
+        for j in range(7):
+            t = opt.plda_transform(g["kaldi_test"][j], T, off, psi, 1, reference_dim_quirk=True)
+            assert abs(opt.plda_llr(u, int(g["kaldi_num_utts"][i]), t, psi) - g["kaldi_llr"][i, j]) < 1e-10
+    # Kaldi semantics = the reference's vectors times sqrt(D)
+    u = opt.plda_transform(g["kaldi_enroll"][1], T, off, psi, 3)
+    assert rel(u, g["kaldi_enroll_u"][1] * 4.0) < 1e-12
