@@ -177,6 +177,23 @@ class PLDA:
         return ops.bilinear_trials(a, b, trial_e, trial_t, row, col)
 
     @classmethod
+    def read_trans(cls, path):
+        """From the Kaldi-text file plda_trans_write produces: <Plda> [ mean ] [ transform rows ] [ psi ] </Plda>."""
+        txt = open(path).read()
+        if not txt.lstrip().startswith("<Plda>"):
+            raise ValueError("{} is not a Kaldi-text PLDA file".format(path))
+        body = txt.replace("<Plda>", " ").replace("</Plda>", " ")
+        groups = [g.split() for g in body.replace("]", "[").split("[") if g.split()]
+        mean = np.array(groups[0], dtype=np.float64)
+        d = mean.shape[0]
+        self = cls.__new__(cls)
+        self.mean, self.dim = mean.reshape(-1, 1), d
+        self.transform = np.array(groups[1], dtype=np.float64).reshape(d, d)
+        self.psi = np.array(groups[2], dtype=np.float64)
+        self.offset = -1.0 * (self.transform @ self.mean)
+        return self
+
+    @classmethod
     def read_ori(cls, path):
         """From the three-vector file PldaEstimation.plda_write produces (`<plda>.ori`)."""
         parts = dict(kaldi_io.read_vec_flt_ark(path))

@@ -131,3 +131,39 @@ def test_gpu_kaldi_style_plda_scoring(golden):
     # smoothing keeps T W T^T = I structure: psi shrinks, rows of the transform rescale
     p.smooth_within_class_covariance(0.1)
     assert np.all(p.psi < psi + 1e-12) and rel(p.transform @ g["d16_within"] @ p.transform.T, np.diag(1.0 / (1.0 + 0.1 * psi))) < 1e-9
+
+
+def test_kaldi_form_plda_cli(golden, tmp_path):
+    """score.sh `plda` positionals: <trials> <num_utts> <plda> <enroll> <test> <out>, Kaldi-text model file."""
+    import subprocess
+    import sys
+    from asv_subtools_b200 import kaldi_io
+    from asv_subtools_b200.score.plda_train import PLDA
+    g = golden("plda_train")
+    root = os.path.dirname(HERE)
+    p = PLDA(g["d16_mean"], g["d16_within"], g["d16_between"])
+    p.plda_trans_write(str(tmp_path / "plda"))
+    q = PLDA.read_trans(str(tmp_path / "plda"))
+    assert rel(q.transform, p.transform) < 1e-12 and rel(q.psi, p.psi) < 1e-12
+    ev, tv, nu = g["kaldi_enroll"].astype(np.float32), g["kaldi_test"].astype(np.float32), g["kaldi_num_utts"]
+    with open(tmp_path / "enroll.ark", "wb") as f:
+        for i in range(5):
+            kaldi_io.write_vec_flt(f, ev[i], key="spk{}".format(i))
+    with open(tmp_path / "test.ark", "wb") as f:
+        for j in range(7):
+            kaldi_io.write_vec_flt(f, tv[j], key="utt{}".format(j))
+    (tmp_path / "num_utts.ark").write_text("".join("spk{} {}\n".format(i, int(nu[i])) for i in range(5)))
+    (tmp_path / "trials").write_text("".join("spk{} utt{} {}\n".format(i, j, "target" if (i + j) % 3 == 0 else "nontarget")
+                                             for i in range(5) for j in range(7)))
+    r = subprocess.run([sys.executable, "-m", "asv_subtools_b200.score.plda", "--kaldi", str(tmp_path / "trials"),
+                        str(tmp_path / "num_utts.ark"), str(tmp_path / "plda"), str(tmp_path / "enroll.ark"),
+                        str(tmp_path / "test.ark"), str(tmp_path / "out.score")], capture_output=True, text=True, cwd=root,
+                       env=dict(os.environ, PYTHONPATH=root))
+    assert r.returncode == 0, r.stdout + r.stderr
+    T, off, psi = p.transform, p.offset.reshape(-1), p.psi
+    lines = [l.split() for l in open(tmp_path / "out.score")]
+    assert len(lines) == 35
+    for e_key, t_key, sc in lines:
+        i, j = int(e_key[3:]), int(t_key[3:])
+        want = opt.plda_llr(opt.plda_transform(ev[i], T, off, psi, int(nu[i])), int(nu[i]), opt.plda_transform(tv[j], T, off, psi, 1), psi)
+        assert abs(float(sc) - want) < 2e-4 * max(1.0, abs(want))
