@@ -518,10 +518,10 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
         }
         const int n = n0 + ch * 32;
         if (p.store_mode == 2) {
-          // straight from registers: a thread owns 16 consecutive columns of its row = one 32-byte sector per
-          // bf16 plane (64 bytes of fp32).  Not coalesced across lanes, but every store fills whole sectors and
-          // the epilogue needs neither the slab, nor its two barriers per chunk, nor the wait for the TMA engine
-          // to have read the previous chunk -- which is what bounds the layers with few K blocks.
+          // XVB_GEMM_STORE=reg (experiment): straight from registers, a thread owns 16 consecutive columns of its
+          // row = one 32-byte sector per bf16 plane.  No slab, no barriers, no wait for the TMA engine -- but the
+          // 32 scattered sectors per warp store cost more LSU time than all of that: measured 12-16 % slower on the
+          // K <= 512 layers it was meant for (profiles/r01_gemm_experiments.md).  Kept as a knob.
           if (valid) {
             const long long grow = (long long)b * p.T + t;
             const int c16 = n + half * 16;
@@ -969,19 +969,7 @@ int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream, const TrialHis
   p.log2_tb = 0;
   while ((1 << p.log2_tb) < p.Tb) ++p.log2_tb;
   p.store_mode = gemm_store_mode();
-  if (p.store_mode < 0) {
-    // few K blocks per tile: the epilogue, not the MMAs, sets the pace, and its cost is the slab hand-over to
-    // the TMA store engine -> store from registers.  Many K blocks: the TMA store is hidden anyway and frees
-    // the LSU.  (XVB_GEMM_STORE=tma|reg|direct forces one.)
-    const long long kblk = (long long)(a.x2_hi ? 2 : 1) * ntaps * ((Cin + kBlockK - 1) / kBlockK);
-    p.store_mode = (kblk <= 12 && Cout % 8 == 0 && (!a.y_hi || a.ldy % 8 == 0)) ? 2 : 0;
-  }
-#ifdef XVB_TIMING_EXPERIMENTS
-  static const int dbg = getenv("XVB_GEMM_DEBUG") ? atoi(getenv("XVB_GEMM_DEBUG")) : 0;
-  p.debug = dbg;
-#else
-  p.debug = 0;
-#endif
+  if (p.store_mode < 0) p.store_mode = 0;   // TMA stores; `reg` / `direct` measured slower (profiles/r01_gemm_experiments.md)
   if (p.store_mode >= 1) {  // vector stores need whole 16-byte groups inside the row
     if (a.y_hi) XVB_CHECK_ARG(Cout % 8 == 0, "xvb_tdnn_affine: plane output needs Cout%%8==0 (Cout=%d)", Cout);
     if (a.y_f32) XVB_CHECK_ARG(Cout % 4 == 0, "xvb_tdnn_affine: fp32 output needs Cout%%4==0 (Cout=%d)", Cout);
