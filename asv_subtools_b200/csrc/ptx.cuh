@@ -249,15 +249,6 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
       : "r"(taddr)
       : "memory");
 }
-// 8 consecutive columns of this thread's lane into v[off .. off+8)
-template <int kOff>
-__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(v[kOff + 0]), "=r"(v[kOff + 1]), "=r"(v[kOff + 2]), "=r"(v[kOff + 3]), "=r"(v[kOff + 4]),
-                 "=r"(v[kOff + 5]), "=r"(v[kOff + 6]), "=r"(v[kOff + 7])
-               : "r"(taddr)
-               : "memory");
-}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- descriptors

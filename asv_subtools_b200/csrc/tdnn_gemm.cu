@@ -66,7 +66,7 @@ struct TdnnGemmParams {
   long long ld_utt;
   int log2_tb;            // Tb is a power of two
   int debug;              // -DXVB_TIMING_EXPERIMENTS only: bit0 skip epilogue, bit1 skip MMA, bit2 skip store issue, bit3 skip LDTM
-  int store_mode;         // 0: two alternating 8 KB slabs -> TMA stores; 2: registers -> st.global (experiment knob)
+  int store_mode;         // 0: epilogue slab -> TMA store; 1: slab -> coalesced st.global; 2: registers -> st.global (sector-sized)
   float* pool_partial;    // fused statistics pooling: per (time block, utterance, channel) [mean | M2] partials
   int num_src;            // 1, or 2: a second A source accumulated with the same weights (W.(x + x2))
   // M-unit sharding (a unit = kCta x 128 rows): this launch walks units unit_first + k * unit_stride
@@ -462,6 +462,7 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
         continue;
       }
       const float rbias = (p.row_bias && valid) ? __ldg(p.row_bias + (long long)b * p.T + t) : 0.f;
+      const float* ub = (p.utt_bias && valid) ? p.utt_bias + (long long)b * p.ld_utt + n0 + half * 16 : nullptr;
       // stage this tile's per-column parameters (double-buffered by accumulator stage; the
       // barrier also orders reuse: nobody can be two tiles ahead of the slowest epilogue thread)
       // layout: kAccStages buffers of [bias | scale | shift], each kTileN floats (6 KB in total either way)
@@ -483,113 +484,146 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kTileN + half * 16;
       const uint32_t slab = smem_u32(slab_base);
       const float relu_floor = relu ? 0.f : -INFINITY;   // branch-free ReLU switch
-      const bool extras = rbias != 0.f || (p.utt_bias && valid) || act_tanh || act_sigmoid;
+      const bool extras = rbias != 0.f || ub != nullptr || act_tanh || act_sigmoid;
 
-      // Store path.  A 32-column chunk is handed to the TMA store engine as two 16-column sub-chunks through two
-      // 8 KB slabs that alternate: while the engine still reads sub-slab s of the previous chunk, the warps fill
-      // the other one, so the per-chunk critical path no longer contains the engine's read latency
-      // (cp.async.bulk.wait_group.read 1 = "all but the newest store have left shared memory").  A thread owns
-      // one row and columns [half*8, +8) of each sub-chunk: v[0..7] and v[8..15].
-      const float* ub0 = (p.utt_bias && valid) ? p.utt_bias + (long long)b * p.ld_utt + n0 : nullptr;
       auto process = [&](uint32_t (&v)[16], int ch) {
-        const int n = n0 + ch * 32;
+        const int pc = ch * 32 + half * 16;
+        float f[16];
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          const int nsub = n + s * 16;
-          if (nsub >= p.Cout) break;                       // whole sub-chunk beyond the last channel (tile-uniform)
-          const int pc = ch * 32 + s * 16 + half * 8;      // tile column of this thread's first value
-          float f[8];
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            const float4 bb = ld_shared_f4(prm + (pc + 4 * g) * 4);
-            const float4 ss = ld_shared_f4(prm + (kTileN + pc + 4 * g) * 4);
-            const float4 tt = ld_shared_f4(prm + (2 * kTileN + pc + 4 * g) * 4);
-            float x0 = __uint_as_float(v[8 * s + 4 * g + 0]) + bb.x;
-            float x1 = __uint_as_float(v[8 * s + 4 * g + 1]) + bb.y;
-            float x2 = __uint_as_float(v[8 * s + 4 * g + 2]) + bb.z;
-            float x3 = __uint_as_float(v[8 * s + 4 * g + 3]) + bb.w;
-            if (extras) {  // warp-uniform: PLDA row term / per-utterance bias (ECAPA attention)
-              float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (ub0 && n0 + pc + 4 * g < p.Cout) u = __ldg(reinterpret_cast<const float4*>(ub0 + pc + 4 * g));
-              x0 += rbias + u.x; x1 += rbias + u.y; x2 += rbias + u.z; x3 += rbias + u.w;
+        for (int g = 0; g < 4; ++g) {
+          const float4 bb = ld_shared_f4(prm + (pc + 4 * g) * 4);
+          const float4 ss = ld_shared_f4(prm + (kTileN + pc + 4 * g) * 4);
+          const float4 tt = ld_shared_f4(prm + (2 * kTileN + pc + 4 * g) * 4);
+          float x0 = __uint_as_float(v[4 * g + 0]) + bb.x;
+          float x1 = __uint_as_float(v[4 * g + 1]) + bb.y;
+          float x2 = __uint_as_float(v[4 * g + 2]) + bb.z;
+          float x3 = __uint_as_float(v[4 * g + 3]) + bb.w;
+          if (extras) {  // warp-uniform: PLDA row term / per-utterance bias (ECAPA attention)
+            float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ub && n0 + pc + 4 * g < p.Cout) u = __ldg(reinterpret_cast<const float4*>(ub + ch * 32) + g);
+            x0 += rbias + u.x; x1 += rbias + u.y; x2 += rbias + u.z; x3 += rbias + u.w;
+          }
+          x0 = fmaf(fmaxf(x0, relu_floor), ss.x, tt.x);
+          x1 = fmaf(fmaxf(x1, relu_floor), ss.y, tt.y);
+          x2 = fmaf(fmaxf(x2, relu_floor), ss.z, tt.z);
+          x3 = fmaf(fmaxf(x3, relu_floor), ss.w, tt.w);
+          if (extras) {
+            if (act_tanh) { x0 = tanhf(x0); x1 = tanhf(x1); x2 = tanhf(x2); x3 = tanhf(x3); }
+            if (act_sigmoid) {
+              x0 = 1.f / (1.f + expf(-x0)); x1 = 1.f / (1.f + expf(-x1));
+              x2 = 1.f / (1.f + expf(-x2)); x3 = 1.f / (1.f + expf(-x3));
             }
-            x0 = fmaf(fmaxf(x0, relu_floor), ss.x, tt.x);
-            x1 = fmaf(fmaxf(x1, relu_floor), ss.y, tt.y);
-            x2 = fmaf(fmaxf(x2, relu_floor), ss.z, tt.z);
-            x3 = fmaf(fmaxf(x3, relu_floor), ss.w, tt.w);
-            if (extras) {
-              if (act_tanh) { x0 = tanhf(x0); x1 = tanhf(x1); x2 = tanhf(x2); x3 = tanhf(x3); }
-              if (act_sigmoid) {
-                x0 = 1.f / (1.f + expf(-x0)); x1 = 1.f / (1.f + expf(-x1));
-                x2 = 1.f / (1.f + expf(-x2)); x3 = 1.f / (1.f + expf(-x3));
+          }
+          f[4 * g + 0] = x0; f[4 * g + 1] = x1; f[4 * g + 2] = x2; f[4 * g + 3] = x3;
+        }
+        const int n = n0 + ch * 32;
+        if (p.store_mode == 2) {
+          // XVB_GEMM_STORE=reg (experiment): straight from registers, a thread owns 16 consecutive columns of its
+          // row = one 32-byte sector per bf16 plane.  No slab, no barriers, no wait for the TMA engine -- but the
+          // 32 scattered sectors per warp store cost more LSU time than all of that: measured 12-16 % slower on the
+          // K <= 512 layers it was meant for (profiles/r01_gemm_experiments.md).  Kept as a knob.
+          if (valid) {
+            const long long grow = (long long)b * p.T + t;
+            const int c16 = n + half * 16;
+            if (planes) {
+              __nv_bfloat16* dh = p.y_hi + grow * p.ldy + c16;
+              __nv_bfloat16* dl = p.y_lo + grow * p.ldy + c16;
+#pragma unroll
+              for (int g = 0; g < 2; ++g) {
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  __nv_bfloat16 h0, l0, h1, l1;
+                  split_bf16(f[g * 8 + 2 * k], h0, l0);
+                  split_bf16(f[g * 8 + 2 * k + 1], h1, l1);
+                  h[k] = pack_bf16x2(h0, h1);
+                  l[k] = pack_bf16x2(l0, l1);
+                }
+                if (c16 + 8 * g < p.Cout) {   // Cout % 8 == 0 on this path
+                  *reinterpret_cast<uint4*>(dh + 8 * g) = make_uint4(h[0], h[1], h[2], h[3]);
+                  *reinterpret_cast<uint4*>(dl + 8 * g) = make_uint4(l[0], l[1], l[2], l[3]);
+                }
               }
             }
-            f[4 * g + 0] = x0; f[4 * g + 1] = x1; f[4 * g + 2] = x2; f[4 * g + 3] = x3;
+            if (f32o) {
+              float* df = p.y_f32 + grow * p.ldyf + c16;
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                if (c16 + 4 * g < p.Cout)     // Cout % 4 == 0 on this path
+                  *reinterpret_cast<float4*>(df + 4 * g) = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+            }
           }
-          uint32_t h[4], l[4];
-          if (planes) {
+          return;
+        }
+        const bool direct = p.store_mode == 1;
+        if (planes) {
+          // the previous store must have finished reading the slab
+          if (!direct && leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          // two slabs of 64-byte rows (SWIZZLE_64B pattern): 16-byte chunk c of row r sits at c ^ ((r>>1)&3)
+          const uint32_t sh = slab + row * 64, sl = slab + 8192 + row * 64;
+          const int sw = (row >> 1) & 3;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            uint32_t h[4], l[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(f[2 * k], h0, l0);
-              split_bf16(f[2 * k + 1], h1, l1);
+              split_bf16(f[g * 8 + 2 * k], h0, l0);
+              split_bf16(f[g * 8 + 2 * k + 1], h1, l1);
               h[k] = pack_bf16x2(h0, h1);
               l[k] = pack_bf16x2(l0, l1);
             }
+            const int c = half * 2 + g;
+            st_shared_v4(sh + ((c ^ sw) << 4), h[0], h[1], h[2], h[3]);
+            st_shared_v4(sl + ((c ^ sw) << 4), l[0], l[1], l[2], l[3]);
           }
-          if (p.store_mode == 2) {
-            // XVB_GEMM_STORE=reg (experiment): straight from registers.  No slab, no barriers, no wait for the TMA
-            // engine -- but the scattered 16-byte stores cost more LSU time than all of that: measured 12-16 %
-            // slower on the K <= 512 layers it was meant for (profiles/r01_gemm_experiments.md).  Kept as a knob.
-            const int c8 = nsub + half * 8;
-            if (valid && c8 < p.Cout) {
-              const long long grow = (long long)b * p.T + t;
-              if (planes) {
-                *reinterpret_cast<uint4*>(p.y_hi + grow * p.ldy + c8) = make_uint4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<uint4*>(p.y_lo + grow * p.ldy + c8) = make_uint4(l[0], l[1], l[2], l[3]);
-              }
-              if (f32o) {
-                float* df = p.y_f32 + grow * p.ldyf + c8;
-                *reinterpret_cast<float4*>(df) = make_float4(f[0], f[1], f[2], f[3]);
-                if (c8 + 4 < p.Cout) *reinterpret_cast<float4*>(df + 4) = make_float4(f[4], f[5], f[6], f[7]);
-              }
+          if (!direct) fence_proxy_async();
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          if (direct) {
+            // transpose through the slab: a warp now owns 8 rows x 64 contiguous bytes per instruction
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int item = etid + 256 * k;
+              const int plane = item >> 9, rr = (item & 511) >> 2, cc = item & 3;
+              const int gb = b0 + (rr >> p.log2_tb), gt = t0 + (rr & (p.Tb - 1)), col = n + cc * 8;
+              const uint4 w = ld_shared_u4(slab + plane * 8192 + rr * 64 + ((cc ^ ((rr >> 1) & 3)) << 4));
+              if (gb < p.B && gt < p.T && col < p.Cout)
+                *reinterpret_cast<uint4*>((plane ? p.y_lo : p.y_hi) + ((long long)gb * p.T + gt) * p.ldy + col) = w;
             }
-            continue;
+          } else if (leader && !XVB_DBG(p, 4)) {
+            tma_store_3d(&map_y_hi, slab_base, n, t0, b0);
+            tma_store_3d(&map_y_lo, slab_base + 8192, n, t0, b0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-          const uint32_t sl = slab + s * 8192;
-          uint8_t* sl_ptr = slab_base + s * 8192;
-          if (planes) {
-            if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // this sub-slab's previous store has been read
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            // hi (4 KB) | lo (4 KB), rows of 32 bytes in the SWIZZLE_32B pattern: 16-byte chunk c of row r sits at c ^ ((r>>2)&1)
-            const uint32_t off = row * 32 + ((half ^ ((row >> 2) & 1)) << 4);
-            st_shared_v4(sl + off, h[0], h[1], h[2], h[3]);
-            st_shared_v4(sl + 4096 + off, l[0], l[1], l[2], l[3]);
-            fence_proxy_async();
-            asm volatile("bar.sync 2, 256;" ::: "memory");
-            if (leader && !XVB_DBG(p, 4)) {
-              tma_store_3d(&map_y_hi, sl_ptr, nsub, t0, b0);
-              tma_store_3d(&map_y_lo, sl_ptr + 4096, nsub, t0, b0);
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
+        }
+        if (f32o) {
+          if (!direct && leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          // one slab of 128-byte rows (SWIZZLE_128B pattern): chunk c of row r sits at c ^ (r & 7)
+          const uint32_t sf = slab + row * 128;
+          const int sw = row & 7;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int c = half * 4 + g;
+            st_shared_v4(sf + ((c ^ sw) << 4), __float_as_uint(f[4 * g]), __float_as_uint(f[4 * g + 1]),
+                         __float_as_uint(f[4 * g + 2]), __float_as_uint(f[4 * g + 3]));
           }
-          if (f32o) {
-            if (leader) {
-              if (planes) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the planes store just issued reads this sub-slab
-              else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          if (!direct) fence_proxy_async();
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          if (direct) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int item = etid + 256 * k;
+              const int rr = item >> 3, cc = item & 7;
+              const int gb = b0 + (rr >> p.log2_tb), gt = t0 + (rr & (p.Tb - 1)), col = n + cc * 4;
+              const float4 w = ld_shared_f4(slab + rr * 128 + ((cc ^ (rr & 7)) << 4));
+              if (gb < p.B && gt < p.T && col < p.Cout)
+                *reinterpret_cast<float4*>(p.y_f32 + ((long long)gb * p.T + gt) * p.ldyf + col) = w;
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            // rows of 64 bytes in the SWIZZLE_64B pattern: chunk c of row r sits at c ^ ((r>>1)&3)
-            const uint32_t base = sl + row * 64;
-            const int sw = (row >> 1) & 3;
-            st_shared_v4(base + (((half * 2) ^ sw) << 4), __float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
-            st_shared_v4(base + (((half * 2 + 1) ^ sw) << 4), __float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7]));
-            fence_proxy_async();
-            asm volatile("bar.sync 2, 256;" ::: "memory");
-            if (leader && !XVB_DBG(p, 4)) {
-              tma_store_3d(&map_y_f32, sl_ptr, nsub, t0 + slice, b0);   // split-K: partial of slice s at "time" s
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
+          } else if (leader && !XVB_DBG(p, 4)) {
+            tma_store_3d(&map_y_f32, slab_base, n, t0 + slice, b0);   // split-K: partial of slice s at "time" s
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
       };
@@ -635,25 +669,16 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
       };
 
       uint32_t va[16], vb[16];
-      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kTileN;
-      auto load_chunk = [&](int c, uint32_t (&v)[16]) {
-        if constexpr (hist) {
-          tmem_ld_32x16(trow + c * 32, v);                 // 16 consecutive columns per thread
-        } else {                                           // columns [half*8, +8) of both 16-column sub-chunks
-          tmem_ld_32x8<0>(tbase + c * 32 + half * 8, v);
-          tmem_ld_32x8<8>(tbase + c * 32 + 16 + half * 8, v);
-        }
-      };
       int ch = 0;
       if (XVB_DBG(p, 1)) ch = nch;
-      else load_chunk(0, va);
+      else tmem_ld_32x16(trow, va);
       while (ch < nch) {
         tmem_ld_wait();
-        if (ch + 1 < nch && !XVB_DBG(p, 8)) load_chunk(ch + 1, vb);
+        if (ch + 1 < nch && !XVB_DBG(p, 8)) tmem_ld_32x16(trow + (ch + 1) * 32, vb);
         if constexpr (hist) process_hist_any(va, ch); else process(va, ch);
         if (++ch >= nch) break;
         tmem_ld_wait();
-        if (ch + 1 < nch && !XVB_DBG(p, 8)) load_chunk(ch + 1, va);
+        if (ch + 1 < nch && !XVB_DBG(p, 8)) tmem_ld_32x16(trow + (ch + 1) * 32, va);
         if constexpr (hist) process_hist_any(vb, ch); else process(vb, ch);
         ++ch;
       }
@@ -784,7 +809,7 @@ static int gemm_store_mode() {   // -1: automatic (per layer shape)
   static int mode = -2;
   if (mode == -2) {
     const char* e = getenv("XVB_GEMM_STORE");
-    mode = !e ? -1 : e[0] == 'r' ? 2 : e[0] == 't' ? 0 : -1;
+    mode = !e ? -1 : e[0] == 'd' ? 1 : e[0] == 'r' ? 2 : e[0] == 't' ? 0 : -1;
   }
   return mode;
 }
@@ -807,18 +832,18 @@ static void choose_m_tile(int B, int T, int* Tb_out, int* Bb_out, int max_tb = 1
   *Bb_out = 128 / bt;
 }
 
-// Output tensor map: (Cout, T, B) with row pitch ld elements of `esize` bytes; box = 16 columns x
-// Tb x Bb (one sub-chunk of the epilogue); 32-byte rows (bf16) use SWIZZLE_32B, 64-byte rows (fp32) SWIZZLE_64B.
+// Output tensor map: (Cout, T, B) with row pitch ld elements of `esize` bytes; box = 32 columns x
+// Tb x Bb; 64-byte rows (bf16) use SWIZZLE_64B, 128-byte rows (fp32) SWIZZLE_128B.
 static int make_out_map(CUtensorMap* m, const void* base, int esize, int C, int T, int B, long long ld, int Tb, int Bb) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return XVB_ECUDA; }
   cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
   cuuint64_t strides[2] = {(cuuint64_t)ld * esize, (cuuint64_t)ld * esize * (cuuint64_t)T};
-  cuuint32_t box[3] = {16u, (cuuint32_t)Tb, (cuuint32_t)Bb};
+  cuuint32_t box[3] = {32u, (cuuint32_t)Tb, (cuuint32_t)Bb};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   esize == 2 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   esize == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(output map C=%d T=%d B=%d ld=%lld) failed: %d", C, T, B, ld, (int)r); return XVB_ECUDA; }
   return XVB_OK;
