@@ -66,6 +66,7 @@ struct TdnnGemmParams {
   long long ld_utt;
   int log2_tb;            // Tb is a power of two
   int debug;              // -DXVB_TIMING_EXPERIMENTS only: bit0 skip epilogue, bit1 skip MMA, bit2 skip store issue, bit3 skip LDTM
+  int plane_box64;        // plane-only outputs: 64-column chunks, hi then lo through the slab, 128-byte store rows
   int store_mode;         // 0: epilogue slab -> TMA store; 1: slab -> coalesced st.global; 2: registers -> st.global (sector-sized)
   float* pool_partial;    // fused statistics pooling: per (time block, utterance, channel) [mean | M2] partials
   int num_src;            // 1, or 2: a second A source accumulated with the same weights (W.(x + x2))
@@ -668,6 +669,80 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
         else process_hist(v, ch, std::false_type{});
       };
 
+      if (!hist && p.plane_box64) {
+        // Plane-only outputs (every frame layer but the last): 64-column chunks, the hi plane and then the lo plane
+        // of the chunk through the 16 KB slab (128 rows x 128 bytes, SWIZZLE_128B).  Same number of barriers and slab
+        // hand-overs per column as the 32-column path, but every store row is a whole 128-byte line instead of two
+        // 64-byte halves written at different times: half as many write requests next to the operand stream
+        // (profiles/r01_gemm_experiments.md: shorter rows cost 12-16 % on the K <= 512 layers).
+        const int nch64 = (min(p.Cout - n0, kTileN) + 63) >> 6;
+        const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kTileN + half * 32;
+        uint32_t v0[16], v1[16];
+        tmem_ld_32x16(tq, v0);
+        tmem_ld_32x16(tq + 16, v1);
+#pragma unroll 1
+        for (int c64 = 0; c64 < nch64; ++c64) {
+          tmem_ld_wait();
+          const int pc = c64 * 64 + half * 32;
+          uint32_t hh[16], ll[16];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 bb = ld_shared_f4(prm + (pc + 4 * g) * 4);
+            const float4 ss = ld_shared_f4(prm + (kTileN + pc + 4 * g) * 4);
+            const float4 tt = ld_shared_f4(prm + (2 * kTileN + pc + 4 * g) * 4);
+            const uint32_t* src = g < 4 ? v0 + 4 * g : v1 + 4 * (g - 4);
+            float x0 = __uint_as_float(src[0]) + bb.x, x1 = __uint_as_float(src[1]) + bb.y;
+            float x2 = __uint_as_float(src[2]) + bb.z, x3 = __uint_as_float(src[3]) + bb.w;
+            if (extras) {
+              float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.utt_bias && valid && n0 + pc + 4 * g < p.Cout)
+                u = __ldg(reinterpret_cast<const float4*>(p.utt_bias + (long long)b * p.ld_utt + n0 + pc + 4 * g));
+              x0 += rbias + u.x; x1 += rbias + u.y; x2 += rbias + u.z; x3 += rbias + u.w;
+            }
+            x0 = fmaf(fmaxf(x0, relu_floor), ss.x, tt.x);
+            x1 = fmaf(fmaxf(x1, relu_floor), ss.y, tt.y);
+            x2 = fmaf(fmaxf(x2, relu_floor), ss.z, tt.z);
+            x3 = fmaf(fmaxf(x3, relu_floor), ss.w, tt.w);
+            if (extras) {
+              if (act_tanh) { x0 = tanhf(x0); x1 = tanhf(x1); x2 = tanhf(x2); x3 = tanhf(x3); }
+              if (act_sigmoid) {
+                x0 = 1.f / (1.f + expf(-x0)); x1 = 1.f / (1.f + expf(-x1));
+                x2 = 1.f / (1.f + expf(-x2)); x3 = 1.f / (1.f + expf(-x3));
+              }
+            }
+            __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
+            split_bf16(x0, h0, l0); split_bf16(x1, h1, l1); split_bf16(x2, h2, l2); split_bf16(x3, h3, l3);
+            hh[2 * g] = pack_bf16x2(h0, h1); hh[2 * g + 1] = pack_bf16x2(h2, h3);
+            ll[2 * g] = pack_bf16x2(l0, l1); ll[2 * g + 1] = pack_bf16x2(l2, l3);
+          }
+          if (c64 + 1 < nch64) {                             // the accumulator values are consumed: fetch the next chunk
+            tmem_ld_32x16(tq + (c64 + 1) * 64, v0);
+            tmem_ld_32x16(tq + (c64 + 1) * 64 + 16, v1);
+          }
+          const int ncol = n0 + c64 * 64;
+          const uint32_t rowaddr = slab + row * 128;
+          const int sw = row & 7;
+#pragma unroll
+          for (int plane = 0; plane < 2; ++plane) {
+            if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const uint32_t* w = plane == 0 ? hh : ll;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)                      // this thread's 32 columns = 4 chunks of 16 bytes
+              st_shared_v4(rowaddr + (((half * 4 + k) ^ sw) << 4), w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+            fence_proxy_async();
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (leader && !XVB_DBG(p, 4)) {
+              tma_store_3d(plane == 0 ? &map_y_hi : &map_y_lo, slab_base, ncol, t0, b0);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
+        }
+        tcgen05_fence_before();
+        if constexpr (kCta == 1) mbar_arrive(&tmem_empty_bar[acc]);
+        else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+        continue;
+      }
       uint32_t va[16], vb[16];
       int ch = 0;
       if (XVB_DBG(p, 1)) ch = nch;
@@ -834,16 +909,17 @@ static void choose_m_tile(int B, int T, int* Tb_out, int* Bb_out, int max_tb = 1
 
 // Output tensor map: (Cout, T, B) with row pitch ld elements of `esize` bytes; box = 32 columns x
 // Tb x Bb; 64-byte rows (bf16) use SWIZZLE_64B, 128-byte rows (fp32) SWIZZLE_128B.
-static int make_out_map(CUtensorMap* m, const void* base, int esize, int C, int T, int B, long long ld, int Tb, int Bb) {
+static int make_out_map(CUtensorMap* m, const void* base, int esize, int C, int T, int B, long long ld, int Tb, int Bb,
+                        int box_cols = 32) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return XVB_ECUDA; }
   cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
   cuuint64_t strides[2] = {(cuuint64_t)ld * esize, (cuuint64_t)ld * esize * (cuuint64_t)T};
-  cuuint32_t box[3] = {32u, (cuuint32_t)Tb, (cuuint32_t)Bb};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)Tb, (cuuint32_t)Bb};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   esize == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   box_cols * esize == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(output map C=%d T=%d B=%d ld=%lld) failed: %d", C, T, B, ld, (int)r); return XVB_ECUDA; }
   return XVB_OK;
@@ -877,9 +953,12 @@ static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const
     attr_set = true;
   }
   CUtensorMap my_hi, my_lo, my_f32;
+  static const int box64_knob = getenv("XVB_GEMM_BOX64") ? atoi(getenv("XVB_GEMM_BOX64")) : 1;
+  p.plane_box64 = (box64_knob && !kPool && !kHist && p.y_hi && !p.y_f32 && p.store_mode == 0 && Cfg::kTileN >= 64) ? 1 : 0;
   if (p.y_hi) {
-    if ((rc = make_out_map(&my_hi, p.y_hi, 2, p.Cout, p.T, p.B, p.ldy, p.Tb, p.Bb))) return rc;
-    if ((rc = make_out_map(&my_lo, p.y_lo, 2, p.Cout, p.T, p.B, p.ldy, p.Tb, p.Bb))) return rc;
+    const int bc = p.plane_box64 ? 64 : 32;
+    if ((rc = make_out_map(&my_hi, p.y_hi, 2, p.Cout, p.T, p.B, p.ldy, p.Tb, p.Bb, bc))) return rc;
+    if ((rc = make_out_map(&my_lo, p.y_lo, 2, p.Cout, p.T, p.B, p.ldy, p.Tb, p.Bb, bc))) return rc;
   } else {
     my_hi = mw_hi; my_lo = mw_lo;  // unused
   }

@@ -1,23 +1,17 @@
 #!/bin/bash
-# Scratch GPU visit: register-direct epilogue stores for few-K-block layers: tests + A/B.
-TAG=${1:-r02e}
+# Scratch GPU visit: 64-column plane-at-a-time epilogue (128-byte store rows): tests + A/B.
+TAG=${1:-r02g}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest all rc=$?"; tail -6 gpurun_out/${TAG}_pytest_gpu.log
-for MODE in auto tma reg; do
-  XVB_GEMM_STORE=$MODE timeout 300 python bench.py --steps 20 --warmup 3 > gpurun_out/${TAG}_bench_$MODE.json 2> gpurun_out/${TAG}_bench_$MODE.err; echo "bench($MODE) rc=$?"
+for K in 1 0; do
+  XVB_GEMM_BOX64=$K timeout 300 python bench.py --steps 20 --warmup 3 > gpurun_out/${TAG}_bench_box$K.json 2> gpurun_out/${TAG}_bench_box$K.err; echo "bench(box64=$K) rc=$?"
   python - <<PY
 import json
 try:
-    d=json.loads(open("gpurun_out/${TAG}_bench_$MODE.json").read().strip().splitlines()[-1])
-    print("$MODE value %.4e ms/step %.4f" % (d["value"], d["ms_per_step"]), {k: round(v*1e3,1) for k,v in d["kernel_ms"].items()})
+    d=json.loads(open("gpurun_out/${TAG}_bench_box$K.json").read().strip().splitlines()[-1])
+    print("box64=$K value %.4e e2e %.4e ms/step %.4f exec_frac %.3f" % (d["value"], d["e2e"]["value"], d["ms_per_step"], d["roofline"]["executed_frac"]), {k: round(v*1e3,1) for k,v in d["kernel_ms"].items()})
 except Exception as e:
-    print("bench parse failed", e); print(open("gpurun_out/${TAG}_bench_$MODE.err").read()[-1500:])
+    print("bench parse failed", e); print(open("gpurun_out/${TAG}_bench_box$K.err").read()[-1500:])
 PY
-  XVB_GEMM_STORE=$MODE timeout 300 python tools/bench_ecapa.py 10 2>/dev/null | tail -1 | cut -c1-200
+  XVB_GEMM_BOX64=$K timeout 300 python tools/bench_ecapa.py 10 2>/dev/null | tail -1 | cut -c1-200
 done
-XVB_GEMM_STORE=tma timeout 300 python tools/bench_scoring.py 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('tma', {k:(round(v.get('ms',v.get('narrow_window_pass_ms',0)),2)) for k,v in d.items()})"
-timeout 300 python tools/bench_scoring.py 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('auto', {k:(round(v.get('ms',v.get('narrow_window_pass_ms',0)),2)) for k,v in d.items()})"
