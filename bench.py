@@ -40,10 +40,10 @@ GEMM_FLOP_PER_STEP = FLOP_PER_FRAME * B * T
 POOL_BYTES_PER_STEP = 1212000 * B  # 4*(C*T + 2C) B/utt, C=1500, T=200
 NUM_INPUT_BATCHES = 8             # rotate 8 x 16.4 MB inputs; activations per step ~1.1 GB >> 126 MB L2
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
-NCU_GEMM_TRAFFIC_BYTES_PER_LAUNCH = int((69.3 + 173.6 + 177.3 + 163.6 + 155.4 + 9.3) * 1e6 / 6)  # profiles/r01x_gemm_ncu_summary.txt
+NCU_GEMM_TRAFFIC_BYTES_PER_LAUNCH = int((62.9 + 169.6 + 171.9 + 158.7 + 155.9 + 9.3) * 1e6 / 6)  # profiles/r02h_gemm_ncu_summary.txt
 # sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active and gpu__time_duration of the same capture
-NCU_TENSOR_PIPE = {"tdnn1": (46.4, 73.1), "tdnn2": (84.0, 157.9), "tdnn3": (83.0, 157.3), "tdnn4": (58.4, 75.4),
-                   "tdnn5+pool": (80.3, 155.6), "tdnn6": (16.6, 12.1)}
+NCU_TENSOR_PIPE = {"tdnn1": (46.5, 79.7), "tdnn2": (86.6, 177.2), "tdnn3": (86.4, 177.9), "tdnn4": (59.5, 81.4),
+                   "tdnn5+pool": (83.1, 174.4), "tdnn6": (12.6, 14.9)}
 NCU_POOL_TRAFFIC_BYTES_PER_LAUNCH = int((307.2 + 5.8) * 1e6)   # profiles/r01x_pool_ncu_summary.txt
 METRIC = "frames/sec x-vector extraction (80-d fbank)"
 UNIT = "frames/s"
@@ -362,7 +362,7 @@ def run_native(args, rank, world, local_rank):
         "roofline": {"bound": "tensor", "kernel": "tdnn_gemm_bf16x3_kernel (6 launches/step; tdnn5 pools over time in its epilogue, tdnn6 is split-K + a reduce)",
                      "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / pk["bf16_sustained"], "traffic": NCU_GEMM_TRAFFIC_BYTES_PER_LAUNCH,
-                     "traffic_unit": "bytes/launch (dram read+write, mean of the 6 launches, profiles/r01x_gemm_ncu_summary.txt)",
+                     "traffic_unit": "bytes/launch (dram read+write, mean of the 6 launches, profiles/r02h_gemm_ncu_summary.txt)",
                      "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)",
                      "algorithmic_flop_per_launch_avg": GEMM_FLOP_PER_STEP / 6,
                      "executed_tflops": 3 * achieved, "executed_frac": 3 * achieved / pk["bf16_sustained"],
@@ -370,7 +370,7 @@ def run_native(args, rank, world, local_rank):
                      "ncu_tensor_pipe_pct": dict({k: v[0] for k, v in NCU_TENSOR_PIPE.items()},
                                                  time_weighted=sum(a * b for a, b in NCU_TENSOR_PIPE.values()) /
                                                  sum(b for _, b in NCU_TENSOR_PIPE.values()),
-                                                 source="profiles/r01x_gemm_ncu_summary.txt (ncu --set full, one step)"),
+                                                 source="profiles/r02h_gemm_ncu_summary.txt (ncu --set full, one step)"),
                      "gemm_ms_per_step": gemm_ms},
         "roofline_stats_pool": {"bound": "hbm", "kernel": "stats_pool_tma_kernel (standalone, (256,200,1500) fp32, "
                                                           "12 back-to-back launches over 3 rotating inputs)",
