@@ -46,6 +46,8 @@ NCU_TENSOR_PIPE = {"tdnn1": (46.5, 79.7), "tdnn2": (86.6, 177.2), "tdnn3": (86.4
                    "tdnn5+pool": (83.1, 174.4), "tdnn6": (12.6, 14.9)}
 NCU_POOL_TRAFFIC_BYTES_PER_LAUNCH = int((307.2 + 5.8) * 1e6)   # profiles/r01x_pool_ncu_summary.txt
 METRIC = "frames/sec x-vector extraction (80-d fbank)"
+WORKLOAD = ("x-vector TDNN (pytorch/model/xvector.py), 80-d fbank, 200-frame chunks, batch 256 per GPU, "
+            "extracted_embedding=far (BASELINE configs[1])")
 UNIT = "frames/s"
 
 
@@ -176,8 +178,11 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "x-vector TDNN, 80-d fbank, 200-frame chunks (BASELINE configs[1])",
-                   "sample": "{} utterances x {} frames per step, batched forward".format(sample_utts, T)},
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "frames_per_utt": T, "feat_dim": F,
+                   "parallelism": "host cores of rank 0 ({} threads)".format(threads),
+                   "sample": "each step is a bounded sample of the workload: {} of its {} utterances x {} frames, "
+                             "batched forward (the form most favourable to the reference)".format(sample_utts, B, T),
+                   "weights": "seeded synthetic checkpoint of the reference architecture"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "{} steps x {} utts x {} frames, oracle port (torch CPU ops incl. masked taps) of "
                                    "the reference forward, batched".format(args.steps, sample_utts, T)},
@@ -345,8 +350,7 @@ def run_native(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (bf16x3 split operands on tcgen05, fp32 accumulate in TMEM)", "data": "synthetic",
-        "config": {"workload": "x-vector TDNN (pytorch/model/xvector.py), 80-d fbank, 200-frame chunks, "
-                               "batch 256 per GPU, extracted_embedding=far (BASELINE configs[1])",
+        "config": {"workload": WORKLOAD,
                    "batch_per_gpu": B, "frames_per_utt": T, "feat_dim": F, "parallelism": "utterance-sharded x%d" % world,
                    "l2_policy": "inputs rotate over %d batches; ~1.1 GB of activations per step >> 126 MB L2" % NUM_INPUT_BATCHES,
                    "weights": "seeded synthetic checkpoint of the reference architecture"},
