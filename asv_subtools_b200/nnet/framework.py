@@ -109,9 +109,31 @@ class TopVirtualNnet(torch.nn.Module):
 
     # ---- extraction surface ----------------------------------------------------------------
     @for_extract_embedding(maxChunk=10000, isMatrix=True)
-    def extract_embedding(self, inputs):
+    def _extract_embedding_chunked(self, inputs):
         """inputs (1, frames, feat_dim) CUDA float32 -> (1, D)."""
         return self.extractor().extract(inputs)
+
+    def extract_embedding(self, feats):
+        """feats (T, F) float32 ndarray / CPU tensor -> 1-D CPU float32 tensor: the reference's plugin call
+        (framework.py:12-55, :146-153).  An utterance that fits one chunk -- every utterance up to maxChunk = 10000
+        frames -- goes through the C host-buffer call (H2D, the stack, D2H and one synchronisation inside the
+        library, no torch kernels), which roughly halves the per-call latency; the reference's arithmetic for that
+        case, `(T * emb) / T` in fp32, is applied on the host.  Longer utterances take the chunk rule."""
+        x = feats.numpy() if isinstance(feats, torch.Tensor) and not feats.is_cuda else feats
+        if isinstance(x, np.ndarray) and x.ndim == 2 and 0 < x.shape[0] <= 10000:
+            if x.dtype != np.float32:
+                raise TypeError("extract_embedding expects float32 features, got {}".format(x.dtype))
+            ex = self.extractor() if next(self.parameters()).is_cuda else None
+            if ex is not None and hasattr(ex, "extract_host"):
+                train_status = self.training
+                self.eval()
+                n = np.float32(x.shape[0])
+                with torch.cuda.device(next(self.parameters()).device):
+                    emb = (n * ex.extract_host(x[None])[0]) / n
+                if train_status:
+                    self.train()
+                return torch.from_numpy(np.ascontiguousarray(emb, dtype=np.float32))
+        return self._extract_embedding_chunked(feats)
 
     def extract_embedding_batch(self, feats):
         """Equal-length utterances in one call: feats (B, T, F) float32 (CUDA tensor, CPU tensor or
