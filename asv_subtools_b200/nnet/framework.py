@@ -78,6 +78,7 @@ class TopVirtualNnet(torch.nn.Module):
         if self._extractor is not None:
             self._extractor.close()
         self._extractor = None
+        self._extractor_device = None
 
     def extractor(self):
         if self._extractor is None:
@@ -101,6 +102,14 @@ class TopVirtualNnet(torch.nn.Module):
                                "(extract_embeddings.py --use-gpu true)")
         return dev
 
+    def _extraction_device(self):
+        """The CUDA device the packed weights live on (cached with the extractor), or None on the CPU."""
+        if self._extractor is not None and getattr(self, "_extractor_device", None) is not None:
+            return self._extractor_device
+        dev = next(self.parameters()).device
+        self._extractor_device = dev if dev.type == "cuda" else None
+        return self._extractor_device
+
     def load_transform_state_dict(self, state_dict):
         keep = {self.rename_transform_keys.get(k, k): v for k, v in state_dict.items()
                 if k.split(".")[0] in self.transform_keys or k in self.transform_keys}
@@ -123,16 +132,21 @@ class TopVirtualNnet(torch.nn.Module):
         if isinstance(x, np.ndarray) and x.ndim == 2 and 0 < x.shape[0] <= 10000:
             if x.dtype != np.float32:
                 raise TypeError("extract_embedding expects float32 features, got {}".format(x.dtype))
-            ex = self.extractor() if next(self.parameters()).is_cuda else None
+            dev = self._extraction_device()
+            ex = self.extractor() if dev is not None else None
             if ex is not None and hasattr(ex, "extract_host"):
                 train_status = self.training
-                self.eval()
+                if train_status:
+                    self.eval()
                 n = np.float32(x.shape[0])
-                with torch.cuda.device(next(self.parameters()).device):
+                if torch.cuda.current_device() == dev.index:
                     emb = (n * ex.extract_host(x[None])[0]) / n
+                else:
+                    with torch.cuda.device(dev):
+                        emb = (n * ex.extract_host(x[None])[0]) / n
                 if train_status:
                     self.train()
-                return torch.from_numpy(np.ascontiguousarray(emb, dtype=np.float32))
+                return torch.from_numpy(emb)
         return self._extract_embedding_chunked(feats)
 
     def extract_embedding_batch(self, feats):
