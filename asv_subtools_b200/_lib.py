@@ -115,6 +115,7 @@ SIGNATURES = {
     "xvb_ecapa_embed_dim": (_i, [_p]),
     "xvb_ecapa_feat_dim": (_i, [_p]),
     "xvb_ecapa_extract": (_i, [_p, _p, _i, _i, _p, _p]),
+    "xvb_ecapa_extract_host": (_i, [_p, _p, _i, _i, _p, _p]),
     "xvb_ecapa_last_launches": (_i, [_p]),
     "xvb_ecapa_save": (_i, [_p, C.c_char_p]),
     "xvb_ecapa_load": (_i, [C.POINTER(_p), C.c_char_p]),

@@ -76,6 +76,8 @@ struct xvb_ecapa {
   Planes in, X, Hh, R, Z, N, CAT, M, A1, gp, s1, zm, pp;
   float *MF = nullptr, *LOG = nullptr, *gate = nullptr, *ub = nullptr, *zmean = nullptr, *gstat = nullptr, *pstat = nullptr;
   int last_launches = 0;
+  float* h_feats = nullptr; float* h_emb = nullptr;   // device staging of xvb_ecapa_extract_host
+  size_t h_feats_cap = 0, h_emb_cap = 0;
   // layer1 as an im2col view over time-padded planes (see extractor.cu): consecutive taps, feat_dim % 16 == 0
   bool im2col_first = false;
   int pad_front = 0, pad_back = 0;
@@ -336,6 +338,30 @@ extern "C" int xvb_ecapa_extract(xvb_ecapa_t* h, const float* feats, int B, int 
   return XVB_OK;
 }
 
+extern "C" int xvb_ecapa_extract_host(xvb_ecapa_t* h, const float* feats_host, int B, int T, float* emb_host, void* stream) {
+  XVB_CHECK_ARG(h && h->finalized && feats_host && emb_host && B > 0 && T > 0, "xvb_ecapa_extract_host: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t nf = (size_t)B * T * h->feat_dim, ne = (size_t)B * h->E;
+  if (nf > h->h_feats_cap) {
+    cudaFree(h->h_feats);
+    int rc = ealloc(&h->h_feats, nf);
+    if (rc) return rc;
+    h->h_feats_cap = nf;
+  }
+  if (ne > h->h_emb_cap) {
+    cudaFree(h->h_emb);
+    int rc = ealloc(&h->h_emb, ne);
+    if (rc) return rc;
+    h->h_emb_cap = ne;
+  }
+  XVB_CUDA(cudaMemcpyAsync(h->h_feats, feats_host, nf * sizeof(float), cudaMemcpyHostToDevice, s));
+  int rc = xvb_ecapa_extract(h, h->h_feats, B, T, h->h_emb, stream);
+  if (rc) return rc;
+  XVB_CUDA(cudaMemcpyAsync(emb_host, h->h_emb, ne * sizeof(float), cudaMemcpyDeviceToHost, s));
+  XVB_CUDA(cudaStreamSynchronize(s));
+  return XVB_OK;
+}
+
 // ---- .xvbm files for ECAPA ("XVBE0001"): dims, then named layer records -------------------------------------
 extern "C" int xvb_ecapa_save(const xvb_ecapa_t* h, const char* path) {
   XVB_CHECK_ARG(h && h->finalized && path, "xvb_ecapa_save: model not finalized");
@@ -401,6 +427,7 @@ extern "C" int xvb_ecapa_load(xvb_ecapa_t** out, const char* path) {
 extern "C" void xvb_ecapa_destroy(xvb_ecapa_t* h) {
   if (!h) return;
   h->free_ws();
+  cudaFree(h->h_feats); cudaFree(h->h_emb);
   for (auto& kv : h->layers) {
     ELayer& L = kv.second;
     cudaFree(L.w_hi); cudaFree(L.w_lo); cudaFree(L.bias); cudaFree(L.scale); cudaFree(L.shift);

@@ -253,6 +253,19 @@ class NativeEcapaExtractor:
                                                 C.c_void_p(torch.cuda.current_stream().cuda_stream)), "xvb_ecapa_extract")
         return emb
 
+    def extract_host(self, feats_np):
+        """feats (B,T,F) float32 host array -> (B,D) float32 host array (H2D + D2H + one sync inside the call)."""
+        feats_np = np.ascontiguousarray(feats_np, dtype=np.float32)
+        b, t, f = feats_np.shape
+        if f != self.feat_dim:
+            raise ValueError("expected feature dim {}, got {}".format(self.feat_dim, f))
+        emb = np.empty((b, self.embed_dim), dtype=np.float32)
+        C = self._C
+        self._check(self._lib.xvb_ecapa_extract_host(self._h, feats_np.ctypes.data_as(C.c_void_p), b, t,
+                                                     emb.ctypes.data_as(C.c_void_p),
+                                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)), "xvb_ecapa_extract_host")
+        return emb
+
     def close(self):
         h, self._h = self._h, None
         if h:

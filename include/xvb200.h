@@ -437,6 +437,8 @@ int xvb_ecapa_embed_dim(const xvb_ecapa_t* h);
 int xvb_ecapa_feat_dim(const xvb_ecapa_t* h);
 /* feats (B, T, feat_dim) fp32 on the device -> emb (B, embed_dim) fp32 on the device; asynchronous. */
 int xvb_ecapa_extract(xvb_ecapa_t* h, const float* feats, int B, int T, float* emb, void* stream);
+/* Same through host buffers (H2D of feats, D2H of emb inside; synchronises the stream). */
+int xvb_ecapa_extract_host(xvb_ecapa_t* h, const float* feats_host, int B, int T, float* emb_host, void* stream);
 int xvb_ecapa_last_launches(const xvb_ecapa_t* h);
 /* "XVBE0001" model files: the named layers as handed to xvb_ecapa_set_layer. */
 int xvb_ecapa_save(const xvb_ecapa_t* h, const char* path);
