@@ -144,3 +144,53 @@ dist.destroy_process_group()
                          capture_output=True, text=True, timeout=110)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+def _run_cli(module, *args):
+    return subprocess.run([sys.executable, "-m", module, *args], capture_output=True, text=True, cwd=ROOT,
+                          env=dict(os.environ, PYTHONPATH=ROOT), timeout=120)
+
+
+def test_cli_twins_fail_like_the_reference_clis(tmp_path):
+    """Reference contract: on any error the CLIs print a traceback and exit 1 -- the shell wrappers grep
+    the logs for it.  Checked here on the paths that fail before any GPU work."""
+    r = _run_cli("asv_subtools_b200.score.plda", "only", "three", "args")
+    assert r.returncode == 1 and "Traceback" in r.stderr and "expected <trials>" in r.stderr
+    r = _run_cli("asv_subtools_b200.score.plda", "--kaldi", "a", "b", "c", "d", "e")
+    assert r.returncode == 1 and "num_utts" in r.stderr
+    r = _run_cli("asv_subtools_b200.score.compute_plda", str(tmp_path / "missing_spk2utt"), "ark:x", str(tmp_path / "plda"))
+    assert r.returncode == 1 and "Traceback" in r.stderr
+    r = _run_cli("asv_subtools_b200.score.normalization", "--method", "snorm", "--cross-select", "true",
+                 str(tmp_path / "a"), str(tmp_path / "b"), str(tmp_path / "c"), str(tmp_path / "d"))
+    assert r.returncode == 1 and "cross-select applies to asnorm" in r.stderr
+    r = _run_cli("asv_subtools_b200.pipeline.extract_embeddings", "--use-gpu", "false", "--model-blueprint",
+                 os.path.join(ROOT, "asv_subtools_b200", "model", "xvector.py"), "--model-creation",
+                 "Xvector(23,10,training=False)", str(tmp_path / "final.params"), "ark:x", "ark:y")
+    assert r.returncode == 1 and "no CPU path" in r.stderr
+    r = _run_cli("asv_subtools_b200.pipeline.extract_embeddings_online", "--feat-config", str(tmp_path / "missing.yaml"),
+                 "--model-blueprint", os.path.join(ROOT, "asv_subtools_b200", "model", "xvector.py"), "--model-creation",
+                 "Xvector(80,10,training=False)", str(tmp_path / "final.params"), str(tmp_path / "wav.scp"), "ark:y")
+    assert r.returncode == 1 and "Traceback" in r.stderr
+
+
+def test_blueprints_keep_the_reference_constructor_surface():
+    """Creation strings as the launchers write them (runXvector.py:265-266 style) evaluate on every blueprint, expose
+    `extracted_embedding`, and carry the reference's state_dict keys."""
+    from oracle import nnet as onn
+    cases = [("xvector.py", 'Xvector(23,10,training=False,extracted_embedding="far")', onn.xvector_spec(23)),
+             ("extended_xvector.py", 'ExtendedXvector(40,10,training=False,extracted_embedding="near")', onn.extended_xvector_spec(40)),
+             ("snowdar_xvector.py", 'Xvector(40,10,extend=True,training=False,extracted_embedding="near")', onn.snowdar_xvector_spec(40, extend=True)),
+             ("factored_xvector.py", 'Xvector(40,10,training=False,extracted_embedding="far")', onn.factored_xvector_spec(40)),
+             ("ecapa_tdnn_xvector.py", 'ECAPA_TDNN(80,10,training=False,extracted_embedding="near",ecapa_params={"channels":1024,'
+              '"embd_dim":192,"mfa_conv":1536},fc2_params={"nonlinearity":"","bn":True,"bn_params":{"momentum":0.5,"affine":False,'
+              '"track_running_stats":True}})', onn.ecapa_spec(80))]
+    for fname, creation, spec in cases:
+        m = cli.create_model_from_py(os.path.join(ROOT, "asv_subtools_b200", "model", fname), creation)
+        assert hasattr(m, "extracted_embedding") and callable(m.extract_embedding)
+        keys = set(m.state_dict().keys())
+        want = {e[0] for e in spec}
+        assert want <= keys, (fname, sorted(want - keys)[:5])
+        extra = {k for k in keys - want if not k.endswith("num_batches_tracked")}
+        assert not extra, (fname, sorted(extra)[:5])
+        with pytest.raises(RuntimeError):                      # on the CPU: fails loudly, no fallback
+            m.extract_embedding(np.zeros((20, m.inputs_dim), dtype=np.float32))
