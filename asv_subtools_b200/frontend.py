@@ -107,8 +107,11 @@ class KaldiFeature:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
-            lib.xvb_fbank_destroy(h)
+        try:
+            if h and lib is not None:
+                lib.xvb_fbank_destroy(h)
+        except Exception:      # interpreter shutdown: module globals may already be gone
+            pass
 
     def num_frames(self, num_samples):
         return int(lib.xvb_fbank_num_frames(self._h, int(num_samples)))
