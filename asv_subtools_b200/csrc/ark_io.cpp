@@ -136,7 +136,31 @@ bool read_matrix(FILE* f, std::vector<float>* out, int* rows, int* cols, std::ve
       *rows = h.rows; *cols = h.cols;
       return true;
     }
-    if (tok[0] == 'C' && tok[1] == 'M') { set_error("ark: compressed format 'CM%c' is not supported (CM2/CM3)", tok[2]); return false; }
+    if (tok[0] == 'C' && tok[1] == 'M' && (tok[2] == '2' || tok[2] == '3')) {
+      // Kaldi's two header-only compressed formats (restated from Kaldi's CompressedMatrix::Write/Read; Kaldi is not
+      // vendored by the reference, so this is unpinned), which the reference's kaldi_io does not read: 'CM2' = uint16, 'CM3' = uint8, row-major, value = min + range * q / (65535 | 255).
+      // A space follows the 3-character token.
+      struct { float gmin, grange; int32_t rows, cols; } h;
+      if (fgetc(f) != ' ' || !read_exact(f, &h, 16)) { set_error("ark: truncated CM%c header", tok[2]); return false; }
+      if (h.rows < 0 || h.cols < 0) { set_error("ark: negative compressed matrix size"); return false; }
+      const size_t n = (size_t)h.rows * h.cols;
+      out->resize(n);
+      if (tok[2] == '2') {
+        scratch->resize(n * 2);
+        if (!read_exact(f, scratch->data(), n * 2)) return false;
+        const uint16_t* q = reinterpret_cast<const uint16_t*>(scratch->data());
+        const float inc = h.grange * (1.0f / 65535.0f);
+        for (size_t i = 0; i < n; ++i) (*out)[i] = h.gmin + (float)q[i] * inc;
+      } else {
+        scratch->resize(n);
+        if (!read_exact(f, scratch->data(), n)) return false;
+        const float inc = h.grange * (1.0f / 255.0f);
+        for (size_t i = 0; i < n; ++i) (*out)[i] = h.gmin + (float)(*scratch)[i] * inc;
+      }
+      *rows = h.rows; *cols = h.cols;
+      return true;
+    }
+    if (tok[0] == 'C' && tok[1] == 'M') { set_error("ark: unknown compressed format 'CM%c'", tok[2]); return false; }
     const bool dbl = tok[0] == 'D';
     if (was_double) *was_double = dbl;
     if (!((tok[0] == 'F' || dbl) && tok[1] == 'M' && tok[2] == ' ')) { set_error("ark: unknown matrix header '%c%c%c'", tok[0], tok[1], tok[2]); return false; }

@@ -124,7 +124,8 @@ def test_native_reader_matches_python_reader_bit_for_bit(golden, tmp_path):
 
 def test_native_reader_rejects_malformed_streams(tmp_path):
     bad = tmp_path / "bad.ark"
-    for blob in (b"k \0BXM \4\1\0\0\0\4\1\0\0\0\0\0\0\0", b"k \0BFM \4\5\0\0\0\4\5\0\0\0\1\2", b"k \0BCM2" + b"\0" * 16, b"k zz"):
+    for blob in (b"k \0BXM \4\1\0\0\0\4\1\0\0\0\0\0\0\0", b"k \0BFM \4\5\0\0\0\4\5\0\0\0\1\2", b"k \0BCM2" + b"\0" * 10,
+                 b"k \0BCM7 " + b"\0" * 16, b"k zz"):
         bad.write_bytes(blob)
         with pytest.raises(kaldi_io.KaldiFormatError):
             list(kaldi_io.read_mat_ark_native(str(bad)))
@@ -162,3 +163,22 @@ def test_native_writer_is_byte_identical_and_scp_offsets_resolve(golden, tmp_pat
     with kaldi_io.NativeVectorWriter("ark:" + str(tmp_path / "e.ark")) as w:
         with pytest.raises(kaldi_io.KaldiFormatError):
             w.write("two words", items[0][1])
+
+
+def test_native_reader_decodes_kaldi_cm2_cm3(tmp_path):
+    """The header-only compressed formats Kaldi also writes (the reference's reader rejects them; the native one,
+    which replaces the `copy-feats ark:- |` pipe in front of the extractor, reads them)."""
+    import struct
+    rng = np.random.RandomState(4)
+    gmin, grange = np.float32(-7.5), np.float32(21.25)
+    q16 = rng.randint(0, 65536, size=(9, 5)).astype("<u2")
+    q8 = rng.randint(0, 256, size=(4, 6)).astype(np.uint8)
+    blob = b"a \0BCM2 " + struct.pack("<ffii", gmin, grange, 9, 5) + q16.tobytes() + \
+           b"b \0BCM3 " + struct.pack("<ffii", gmin, grange, 4, 6) + q8.tobytes()
+    p = tmp_path / "c.ark"
+    p.write_bytes(blob)
+    got = dict(kaldi_io.read_mat_ark_native(str(p)))
+    assert np.allclose(got["a"], gmin + grange * q16.astype(np.float32) / np.float32(65535), rtol=1e-6, atol=1e-6)
+    assert np.allclose(got["b"], gmin + grange * q8.astype(np.float32) / np.float32(255), rtol=1e-6, atol=1e-6)
+    with pytest.raises(kaldi_io.KaldiFormatError):               # the Python mirror keeps the reference's behaviour
+        list(kaldi_io.read_mat_ark(str(p)))
