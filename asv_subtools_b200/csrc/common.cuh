@@ -7,6 +7,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "../../include/xvb200.h"
@@ -43,6 +44,27 @@ extern thread_local long g_launches;
       ::xvb::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
       return XVB_ECUDA;                                                                 \
     }                                                                                   \
+  } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to ONE device (context): opt in once per
+// (kernel, device).  `done` is the call site's own bitset of device ordinals, so the first launch of a
+// kernel on a second GPU of the same process opts in there too; thread-safe (a lost race sets it twice).
+static inline int ensure_dyn_smem_impl(const void* kernel, int bytes, std::atomic<unsigned long long>& done) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { set_error("cudaGetDevice failed: %s", cudaGetErrorString(e)); return XVB_ECUDA; }
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (dev < 64 && (done.load(std::memory_order_acquire) & bit)) return XVB_OK;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(%d B dynamic smem) failed: %s", bytes, cudaGetErrorString(e)); return XVB_ECUDA; }
+  if (dev < 64) done.fetch_or(bit, std::memory_order_release);
+  return XVB_OK;
+}
+#define XVB_ENSURE_DYN_SMEM(kernel, bytes)                                                         \
+  do {                                                                                             \
+    static std::atomic<unsigned long long> _xvb_done{0};                                           \
+    int _rc = ::xvb::ensure_dyn_smem_impl(reinterpret_cast<const void*>(kernel), (bytes), _xvb_done); \
+    if (_rc) return _rc;                                                                           \
   } while (0)
 
 int require_sm100();  // XVB_OK or XVB_ENODEVICE (cached per device)

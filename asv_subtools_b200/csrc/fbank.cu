@@ -282,11 +282,7 @@ extern "C" int xvb_fbank_compute(xvb_fbank_t* h, const float* wave, const int64_
   if (total_frames == 0) return XVB_OK;
   const int M = h->d.N / 2;
   const size_t smem = (size_t)kFbankWarps * (h->d.N + (M + 4) + 128) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    XVB_CUDA(cudaFuncSetAttribute(fbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  XVB_ENSURE_DYN_SMEM((fbank_kernel), 200 * 1024);
   static_assert(sizeof(long long) == sizeof(int64_t), "offset type");
   const unsigned grid = (unsigned)((total_frames + kFbankWarps - 1) / kFbankWarps);
   fbank_kernel<<<grid, kFbankWarps * 32, smem, (cudaStream_t)stream>>>(

@@ -230,11 +230,7 @@ extern "C" int xvb_stats_pool_ex(const float* x, int64_t ldx, int B, int T, int 
   const unsigned box[3] = {128u, (unsigned)kPoolBoxRows, 1u};
   rc = make_tensor_map(&map, x, 4, 3, dims, strides, box, 0);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    XVB_CUDA(cudaFuncSetAttribute(stats_pool_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoolSmemBytes));
-    attr_set = true;
-  }
+  XVB_ENSURE_DYN_SMEM((stats_pool_tma_kernel), kPoolSmemBytes);
   dim3 grid((C + 127) / 128, B);
   stats_pool_tma_kernel<<<grid, kPoolWarps * 32, kPoolSmemBytes, (cudaStream_t)stream>>>(
       map, T, C, eps, mode, out, reinterpret_cast<__nv_bfloat16*>(out_hi), reinterpret_cast<__nv_bfloat16*>(out_lo), ldo);

@@ -302,11 +302,7 @@ extern "C" int xvb_res2net_block(const uint16_t* x_hi, const uint16_t* x_lo, int
   const unsigned box_w[2] = {64u, (unsigned)kRW};
   if ((rc = make_tensor_map(&mw_hi, w_hi, 2, 2, dw, sw, box_w, 128))) return rc;
   if ((rc = make_tensor_map(&mw_lo, w_lo, 2, 2, dw, sw, box_w, 128))) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    XVB_CUDA(cudaFuncSetAttribute(res2net_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRSmemBytes));
-    attr_set = true;
-  }
+  XVB_ENSURE_DYN_SMEM((res2net_chain_kernel), kRSmemBytes);
   const int grid = B < sm_count() ? B : sm_count();
   res2net_chain_kernel<<<grid, kRThreads, kRSmemBytes, (cudaStream_t)stream>>>(mx_hi, mx_lo, myi_hi, myi_lo, mw_hi, mw_lo,
                                                                               myo_hi, myo_lo, p);

@@ -394,11 +394,7 @@ extern "C" int xvb_topn_mean_std(const float* S, int64_t lds, int64_t rows, int 
   int P = 1;
   while (P < ncoh) P <<= 1;
   const size_t smem = (size_t)P * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    XVB_CUDA(cudaFuncSetAttribute(topn_mean_std_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
-    attr_set = true;
-  }
+  XVB_ENSURE_DYN_SMEM((topn_mean_std_kernel), 32768 * 4);
   topn_mean_std_kernel<<<(unsigned)rows, 512, smem, (cudaStream_t)stream>>>(S, lds, ncoh, P, top_n, mean, stdv);
   XVB_LAUNCH_CHECK();
   return XVB_OK;
@@ -554,11 +550,7 @@ extern "C" int xvb_topn_indices(const float* S, int64_t lds, int64_t rows, int n
   XVB_CHECK_ARG(ncoh <= 16384, "xvb_topn_indices: cohort of %d exceeds the 16384 (score, index) pairs one CTA sorts on chip", ncoh);
   int P = 1;
   while (P < ncoh) P <<= 1;
-  static bool attr_set = false;
-  if (!attr_set) {
-    XVB_CUDA(cudaFuncSetAttribute(topn_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
-    attr_set = true;
-  }
+  XVB_ENSURE_DYN_SMEM((topn_index_kernel), 16384 * 8);
   topn_index_kernel<<<(unsigned)rows, 512, (size_t)P * 8, (cudaStream_t)stream>>>(S, lds, ncoh, P, top_n, idx);
   XVB_LAUNCH_CHECK();
   return XVB_OK;

@@ -946,12 +946,7 @@ static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const
                                 : (long long)num_m_units * p.num_n_blk * (p.k_slices > 1 ? p.k_slices : 1);
   XVB_CHECK_ARG(tiles < (1ll << 31), "xvb_tdnn_affine: %d x %d tiles exceed one launch", num_m_units, p.num_n_blk);
   p.num_tiles = (int)tiles;
-  static bool attr_set = false;
-  if (!attr_set) {
-    XVB_CUDA(cudaFuncSetAttribute(tdnn_gemm_bf16x3_kernel<BLOCK_N, kCta, kNSub, kPool, kHist>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  XVB_ENSURE_DYN_SMEM((tdnn_gemm_bf16x3_kernel<BLOCK_N, kCta, kNSub, kPool, kHist>), Cfg::kSmemBytes);
   CUtensorMap my_hi, my_lo, my_f32;
   static const int box64_knob = getenv("XVB_GEMM_BOX64") ? atoi(getenv("XVB_GEMM_BOX64")) : 1;
   p.plane_box64 = (box64_knob && !kPool && !kHist && p.y_hi && !p.y_f32 && p.store_mode == 0 && Cfg::kTileN >= 64) ? 1 : 0;

@@ -30,20 +30,85 @@ class KaldiFormatError(Exception):
 _PREFIX = re.compile(r"^(ark|scp)(,scp|,b|,t|,n?f|,n?p|,b?o|,n?s|,n?cs)*:")
 
 
+class _PipeStream:
+    """One end of a shell pipe that owns its child.  close() (or leaving a `with` block) waits for the
+    command and raises on a nonzero exit status, so a writer such as `ark:| copy-vector ark:- ark,scp:x.ark,x.scp`
+    has finished x.scp when the extractor returns and a failed pipe command fails the job (the reference's
+    popen, kaldi_io.py:75-110, keeps the interpreter alive on non-daemon cleanup threads; a stream that is
+    never closed is reaped the same way here)."""
+
+    def __init__(self, cmd, mode):
+        self.cmd, self.mode = cmd, mode
+        if mode == "rb":
+            self.proc = subprocess.Popen(cmd, shell=True, stdout=subprocess.PIPE, stderr=sys.stderr)
+            self.raw = self.proc.stdout
+        else:
+            self.proc = subprocess.Popen(cmd, shell=True, stdin=subprocess.PIPE, stderr=sys.stderr)
+            self.raw = self.proc.stdin
+        self._closed = False
+        # non-daemon: the interpreter does not exit before the child has (reference behaviour)
+        self._reaper = threading.Thread(target=self._reap, daemon=False)
+        self._reaper.start()
+
+    def _reap(self):
+        rc = self.proc.wait()
+        if rc != 0 and not self._closed:
+            sys.stderr.write("ERROR: command `{}` exited with {}\n".format(self.cmd, rc))
+
+    def read(self, *a):
+        return self.raw.read(*a)
+
+    def readline(self, *a):
+        return self.raw.readline(*a)
+
+    def write(self, b):
+        return self.raw.write(b)
+
+    def flush(self):
+        return self.raw.flush()
+
+    def fileno(self):
+        return self.raw.fileno()
+
+    def tell(self):
+        return self.raw.tell()
+
+    def seek(self, *a):
+        return self.raw.seek(*a)
+
+    def seekable(self):
+        return False
+
+    def __iter__(self):
+        return iter(self.raw)
+
+    @property
+    def closed(self):
+        return self._closed
+
+    def close(self):
+        if self._closed:
+            return
+        self._closed = True
+        try:
+            self.raw.close()
+        except BrokenPipeError:
+            pass
+        rc = self.proc.wait()
+        self._reaper.join()
+        if rc != 0 and not (self.mode == "rb" and rc in (-13, 141)):   # a reader may stop before the producer has (SIGPIPE)
+            raise subprocess.CalledProcessError(rc, self.cmd)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+
 def _popen(cmd, mode):
-    if mode == "rb":
-        proc = subprocess.Popen(cmd, shell=True, stdout=subprocess.PIPE, stderr=sys.stderr)
-        stream = proc.stdout
-    else:
-        proc = subprocess.Popen(cmd, shell=True, stdin=subprocess.PIPE, stderr=sys.stderr)
-        stream = proc.stdin
-
-    def reap():
-        if proc.wait() != 0:
-            sys.stderr.write("ERROR: command `{}` exited with {}\n".format(cmd, proc.returncode))
-
-    threading.Thread(target=reap, daemon=True).start()
-    return stream
+    return _PipeStream(cmd, mode)
 
 
 def open_or_fd(spec, mode="rb"):

@@ -351,6 +351,7 @@ def plda_matrix(enroll, test, l2, row, col):
 def topn_indices(S, top_n):
     """(rows, top_n) int32: cohort indices of every row's top_n scores, best first."""
     S = _req(S, torch.float32, "S")
+    top_n = min(int(top_n), S.shape[1])   # groupby().head(top_n): a cohort smaller than top_n is used whole
     idx = torch.empty(S.shape[0], top_n, dtype=torch.int32, device=S.device)
     check(lib.xvb_topn_indices(_ptr(S), S.shape[1], S.shape[0], S.shape[1], int(top_n), _ptr(idx), _stream()), "xvb_topn_indices")
     return idx

@@ -53,12 +53,15 @@ def create_model_from_py(model_blueprint, model_creation):
 class Batcher:
     """Buckets (key, feats) by frame count; yields full buckets, and everything at flush()."""
 
-    def __init__(self, batch_size, max_pending_frames=4_000_000):
+    def __init__(self, batch_size, max_pending_frames=4_000_000, length=None):
+        """`length(item)`: the bucketing key (default: rows of the item); `max_pending_frames` bounds what is held
+        back waiting for a bucket to fill (in units of that key), after which everything pending is flushed."""
         self.batch_size, self.max_pending = batch_size, max_pending_frames
         self.buckets, self.pending = {}, 0
+        self.length = length or (lambda a: a.shape[0])
 
     def add(self, key, feats):
-        t = feats.shape[0]
+        t = self.length(feats)
         b = self.buckets.setdefault(t, [])
         b.append((key, feats))
         self.pending += t

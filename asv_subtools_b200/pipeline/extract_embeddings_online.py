@@ -9,7 +9,7 @@
 runtime/test/feat_conf.yaml): `feature_type`, `kaldi_featset`, `mean_var_conf`.  The reference decodes
 each file with torchaudio, scales to int16 range (processor.py:429), computes KaldiFeature on the CPU
 and extracts one utterance at a time; here PCM16 files are read with the standard library, features for a
-whole bucket of equal-length files come from ONE xvb_fbank_compute launch, and the bucket is extracted
+whole bucket of files with the same FRAME count come from ONE (ragged) xvb_fbank_compute launch, and the bucket is extracted
 in one batched call.  One `FV` vector per key; `RTF:` line at the end like the reference (:131)."""
 import argparse
 import os
@@ -69,7 +69,9 @@ def main(argv=None):
         torch.cuda.set_device(int(args.gpu_id.split(",")[0]) if args.gpu_id != "" else 0)
         model.cuda().eval()
         feature, rate = None, None
-        batcher = Batcher(args.batch_size, max_pending_frames=1 << 62)
+        # bucket by FRAME count (real files almost never share a sample count); at most ~2 M frames (a few
+        # hundred MB of samples) wait for their bucket to fill before everything pending is extracted
+        batcher = Batcher(args.batch_size, max_pending_frames=2_000_000, length=lambda wav: feature.num_frames(wav.shape[0]))
         total_dur, t_extract = 0.0, 0.0
 
         def run(bucket, w):
@@ -102,7 +104,8 @@ def main(argv=None):
                     feature = KaldiFeature(conf.get("feature_type", "fbank"), featset, conf.get("mean_var_conf", {}))
                 elif sr != rate:
                     raise ValueError("{} is sampled at {} Hz, the first file at {} Hz".format(key, sr, rate))
-                if feature.num_frames(wav.shape[0]) < 1:
+                nf = feature.num_frames(wav.shape[0])
+                if nf < 1:
                     raise ValueError("{} is shorter than one analysis window".format(key))
                 for bucket in batcher.add(key, wav):
                     run(bucket, w)

@@ -26,6 +26,11 @@ def normalize(scores, trial_e, trial_t, enroll_cohort, test_cohort, top_n=0, cro
     if cross_select:
         if top_n < 2:
             raise ValueError("cross selection needs top_n >= 2")
+        if enroll_cohort.shape[1] != test_cohort.shape[1]:
+            # one side's top-n column indices address the other side's matrix: both must share ONE cohort order
+            raise ValueError("cross selection needs the same cohort (same columns, same order) on both sides: "
+                             "{} vs {}".format(enroll_cohort.shape[1], test_cohort.shape[1]))
+        top_n = min(top_n, enroll_cohort.shape[1])    # groupby().head(top_n) semantics: a small cohort is used whole
         return ops.snorm_cross_trials(scores, trial_e, trial_t, enroll_cohort, test_cohort,
                                       ops.topn_indices(enroll_cohort, top_n), ops.topn_indices(test_cohort, top_n))
     me, se = ops.topn_mean_std(enroll_cohort, top_n)
@@ -54,13 +59,25 @@ def _load(path):
     return a, b, np.asarray(s, dtype=np.float64)
 
 
-def _dense(keys, cohort, vals):
-    """(key, cohort, score) triples -> dense (num_keys, num_cohort) matrix + key index."""
-    kidx, cidx = {}, {}
+def cohort_index(*cohort_lists):
+    """ONE cohort -> column map for every score table of a run (first-appearance order over all lists): the
+    reference joins on the cohort name (ScoreNormalization.py:146-160), so a column index must mean the same
+    utterance in the enroll-cohort and in the test-cohort matrix whatever order the files list them in."""
+    cidx = {}
+    for cohort in cohort_lists:
+        for c in cohort:
+            cidx.setdefault(c, len(cidx))
+    return cidx
+
+
+def _dense(keys, cohort, vals, cidx=None):
+    """(key, cohort, score) triples -> dense (num_keys, num_cohort) matrix + key index.  `cidx`: shared
+    cohort -> column map (cohort_index); a table that lacks a score for any of its columns raises."""
+    kidx = {}
     for k in keys:
         kidx.setdefault(k, len(kidx))
-    for c in cohort:
-        cidx.setdefault(c, len(cidx))
+    if cidx is None:
+        cidx = cohort_index(cohort)
     m = np.full((len(kidx), len(cidx)), -np.inf, dtype=np.float32)
     m[[kidx[k] for k in keys], [cidx[c] for c in cohort]] = vals
     if np.isinf(m).any():
@@ -86,10 +103,17 @@ def main(argv=None):
         te, tt, s = _load(args.input_score)
         a, b, v = _load(args.enroll_cohort_score)
         ek, ec = (a, b) if args.second_cohort == "true" else (b, a)
-        em, eidx = _dense(ek, ec, v)
-        a, b, v = _load(args.test_cohort_score)
+        a, b, v2 = _load(args.test_cohort_score)
         tk, tc = (a, b) if args.second_cohort == "true" else (b, a)
-        tm, tidx = _dense(tk, tc, v)
+        if args.cross_select == "true":
+            if set(ec) != set(tc):
+                raise ValueError("--cross-select needs the same cohort set in both cohort score files "
+                                 "({} vs {} utterances)".format(len(set(ec)), len(set(tc))))
+            cidx_e = cidx_t = cohort_index(ec, tc)
+        else:
+            cidx_e, cidx_t = cohort_index(ec), cohort_index(tc)
+        em, eidx = _dense(ek, ec, v, cidx_e)
+        tm, tidx = _dense(tk, tc, v2, cidx_t)
         dev = "cuda"
         ie = torch.tensor([eidx[k] for k in te], dtype=torch.int32, device=dev)
         it = torch.tensor([tidx[k] for k in tt], dtype=torch.int32, device=dev)

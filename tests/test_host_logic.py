@@ -194,3 +194,45 @@ def test_blueprints_keep_the_reference_constructor_surface():
         assert not extra, (fname, sorted(extra)[:5])
         with pytest.raises(RuntimeError):                      # on the CPU: fails loudly, no fallback
             m.extract_embedding(np.zeros((20, m.inputs_dim), dtype=np.float32))
+
+
+def test_output_pipe_is_waited_for_and_a_failed_command_fails_the_job(tmp_path):
+    """`ark:| copy-vector ark:- ark,scp:...` must have finished when the writer returns, and a pipe command
+    that exits nonzero must raise (the CLIs turn that into exit 1)."""
+    import time
+    from asv_subtools_b200 import kaldi_io
+    out = tmp_path / "v.ark"
+    t0 = time.time()
+    with kaldi_io.open_or_fd("ark:| sleep 0.5; cat > {}".format(out), "wb") as w:
+        kaldi_io.write_vec_flt(w, np.arange(4, dtype=np.float32), key="utt")
+    assert time.time() - t0 >= 0.45 and out.exists() and out.stat().st_size > 0
+    assert [k for k, _ in kaldi_io.read_vec_flt_ark("ark:cat {} |".format(out))] == ["utt"]
+    with pytest.raises(subprocess.CalledProcessError):
+        with kaldi_io.open_or_fd("ark:| cat > /dev/null; exit 3", "wb") as w:
+            kaldi_io.write_vec_flt(w, np.arange(4, dtype=np.float32), key="utt")
+
+
+def test_cohort_columns_are_shared_between_score_tables_whatever_their_order():
+    """AS-norm --cross-select indexes one cohort matrix with the other's top-n columns."""
+    from asv_subtools_b200.score import normalization as sn
+    keys_a, coh_a = ["e1", "e1", "e1", "e2", "e2", "e2"], ["c1", "c2", "c3", "c1", "c2", "c3"]
+    keys_b, coh_b = ["t1", "t1", "t1"], ["c3", "c1", "c2"]
+    cidx = sn.cohort_index(coh_a, coh_b)
+    ma, _ = sn._dense(keys_a, coh_a, np.arange(6, dtype=np.float32), cidx)
+    mb, _ = sn._dense(keys_b, coh_b, np.array([30., 10., 20.], dtype=np.float32), cidx)
+    assert cidx == {"c1": 0, "c2": 1, "c3": 2}
+    assert mb.tolist() == [[10., 20., 30.]] and ma.tolist() == [[0., 1., 2.], [3., 4., 5.]]
+    with pytest.raises(ValueError):   # a table that misses one of the shared columns is incomplete
+        sn._dense(["t1", "t1"], ["c1", "c2"], np.zeros(2, dtype=np.float32), cidx)
+
+
+def test_batcher_buckets_by_a_length_key_and_flushes_incrementally():
+    """the waveform CLI buckets by frame count with a finite amount held back."""
+    b = cli.Batcher(2, max_pending_frames=10, length=lambda w: w.shape[0] // 4)
+    out = []
+    for i, n in enumerate([8, 9, 16, 17, 4, 24, 32]):
+        out += [[k for k, _ in bucket] for bucket in b.add("u%d" % i, np.zeros(n, dtype=np.float32))]
+    out += [[k for k, _ in bucket] for bucket in b.flush()]
+    assert out[0] == ["u0", "u1"] and out[1] == ["u2", "u3"]          # equal FRAME counts share a bucket
+    assert sorted(k for bucket in out for k in bucket) == ["u%d" % i for i in range(7)]
+    assert len(out) >= 4                                               # the pending cap flushed before the end
