@@ -98,6 +98,8 @@ SIGNATURES = {
     "xvb_extractor_extract_host": (_i, [_p, _p, _i, _i, _p, _p]),
     "xvb_extractor_submit_host": (_i, [_p, _p, _i, _i, _p, _i, _p]),
     "xvb_extractor_wait": (_i, [_p, _i]),
+    "xvb_extractor_extract_shard": (_i, [_p, _p, C.c_int64, _i, _i, _p, _p]),
+    "xvb_extractor_extract_shard_host": (_i, [_p, _p, C.c_int64, _i, _i, _p, _p]),
     "xvb_extractor_set_profiling": (_i, [_p, _i]),
     "xvb_extractor_kernel_times": (_i, [_p, C.POINTER(C.c_float), _i]),
     "xvb_extractor_last_launches": (_i, [_p]),
@@ -116,6 +118,8 @@ SIGNATURES = {
     "xvb_ecapa_feat_dim": (_i, [_p]),
     "xvb_ecapa_extract": (_i, [_p, _p, _i, _i, _p, _p]),
     "xvb_ecapa_extract_host": (_i, [_p, _p, _i, _i, _p, _p]),
+    "xvb_ecapa_extract_shard": (_i, [_p, _p, C.c_int64, _i, _i, _p, _p]),
+    "xvb_ecapa_extract_shard_host": (_i, [_p, _p, C.c_int64, _i, _i, _p, _p]),
     "xvb_ecapa_last_launches": (_i, [_p]),
     "xvb_ecapa_save": (_i, [_p, C.c_char_p]),
     "xvb_ecapa_load": (_i, [C.POINTER(_p), C.c_char_p]),

@@ -94,6 +94,15 @@ struct TrialHist {
 // tdnn_gemm.cu: the tcgen05 layer behind xvb_tdnn_affine / xvb_tdnn_affine_ex.
 int tdnn_affine_impl(const xvb_tdnn_args_t& args, void* stream, const TrialHist* hist = nullptr);
 
+// Plan / launch split of the same layer (tdnn_gemm.cu): a GemmPlan freezes tile geometry, tensor maps, kernel
+// instantiation and grid for one (shapes, pointers) combination; launching it costs one kernel launch (two for
+// split-K).  `scratch`: gemm_plan_scratch_bytes() bytes that stay valid for the life of the plan (split-K partials).
+struct GemmPlan;
+size_t gemm_plan_scratch_bytes(const xvb_tdnn_args_t& args, const TrialHist* hist = nullptr);
+int gemm_plan_build(GemmPlan** out, const xvb_tdnn_args_t& args, const TrialHist* hist, void* scratch);
+int gemm_plan_launch(const GemmPlan* plan, void* stream, float* y_f32_override = nullptr);
+void gemm_plan_destroy(GemmPlan* plan);
+
 // tdnn_gemm.cu: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda).
 int make_tensor_map(CUtensorMap* m, const void* base, int esize, int rank, const unsigned long long* dims,
                     const unsigned long long* strides_bytes, const unsigned* box, int swizzle_bytes);

@@ -78,6 +78,11 @@ struct xvb_ecapa {
   int last_launches = 0;
   float* h_feats = nullptr; float* h_emb = nullptr;   // device staging of xvb_ecapa_extract_host
   size_t h_feats_cap = 0, h_emb_cap = 0;
+  // two-slot pipeline of xvb_ecapa_extract_shard_host
+  float* p_feats[2] = {nullptr, nullptr}; float* p_emb[2] = {nullptr, nullptr};
+  size_t p_feats_cap[2] = {0, 0}, p_emb_cap[2] = {0, 0};
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   // layer1 as an im2col view over time-padded planes (see extractor.cu): consecutive taps, feat_dim % 16 == 0
   bool im2col_first = false;
   int pad_front = 0, pad_back = 0;
@@ -362,6 +367,67 @@ extern "C" int xvb_ecapa_extract_host(xvb_ecapa_t* h, const float* feats_host, i
   return XVB_OK;
 }
 
+// A whole shard of N equal-length utterances in `batch`-utterance batches (the reference's caller loop,
+// extract_embeddings.py:73-83), device-resident / through pinned host buffers with the copies overlapped
+// (same protocol as xvb_extractor_extract_shard[_host]).
+extern "C" int xvb_ecapa_extract_shard(xvb_ecapa_t* h, const float* feats, int64_t N, int T, int batch, float* emb, void* stream) {
+  XVB_CHECK_ARG(h && h->finalized && feats && emb && N > 0 && T > 0 && batch > 0, "xvb_ecapa_extract_shard: bad arguments");
+  int launches = 0;
+  for (int64_t i = 0; i < N; i += batch) {
+    const int b = (int)(N - i < batch ? N - i : batch);
+    int rc = xvb_ecapa_extract(h, feats + (size_t)i * T * h->feat_dim, b, T, emb + (size_t)i * h->E, stream);
+    if (rc) return rc;
+    launches += h->last_launches;
+  }
+  h->last_launches = launches;
+  return XVB_OK;
+}
+
+extern "C" int xvb_ecapa_extract_shard_host(xvb_ecapa_t* h, const float* feats_host, int64_t N, int T, int batch, float* emb_host,
+                                            void* stream) {
+  XVB_CHECK_ARG(h && h->finalized && feats_host && emb_host && N > 0 && T > 0 && batch > 0, "xvb_ecapa_extract_shard_host: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!h->copy_stream) {
+    XVB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      XVB_CUDA(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+      XVB_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+    }
+  }
+  const int bmax = (int)(N < batch ? N : batch);
+  const size_t nf = (size_t)bmax * T * h->feat_dim, ne = (size_t)bmax * h->E;
+  int rc;
+  for (int slot = 0; slot < 2; ++slot) {
+    if (nf > h->p_feats_cap[slot]) {
+      cudaFree(h->p_feats[slot]); h->p_feats[slot] = nullptr; h->p_feats_cap[slot] = 0;
+      if ((rc = ealloc(&h->p_feats[slot], nf))) return rc;
+      h->p_feats_cap[slot] = nf;
+    }
+    if (ne > h->p_emb_cap[slot]) {
+      cudaFree(h->p_emb[slot]); h->p_emb[slot] = nullptr; h->p_emb_cap[slot] = 0;
+      if ((rc = ealloc(&h->p_emb[slot], ne))) return rc;
+      h->p_emb_cap[slot] = ne;
+    }
+  }
+  int launches = 0, k = 0;
+  for (int64_t i = 0; i < N; i += batch, ++k) {
+    const int b = (int)(N - i < batch ? N - i : batch);
+    const int slot = k & 1;
+    if (k >= 2) XVB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[slot], 0));
+    XVB_CUDA(cudaMemcpyAsync(h->p_feats[slot], feats_host + (size_t)i * T * h->feat_dim, (size_t)b * T * h->feat_dim * sizeof(float),
+                             cudaMemcpyHostToDevice, h->copy_stream));
+    XVB_CUDA(cudaEventRecord(h->ev_h2d[slot], h->copy_stream));
+    XVB_CUDA(cudaStreamWaitEvent(s, h->ev_h2d[slot], 0));
+    if ((rc = xvb_ecapa_extract(h, h->p_feats[slot], b, T, h->p_emb[slot], stream))) return rc;
+    XVB_CUDA(cudaMemcpyAsync(emb_host + (size_t)i * h->E, h->p_emb[slot], (size_t)b * h->E * sizeof(float), cudaMemcpyDeviceToHost, s));
+    XVB_CUDA(cudaEventRecord(h->ev_done[slot], s));
+    launches += h->last_launches;
+  }
+  XVB_CUDA(cudaStreamSynchronize(s));
+  h->last_launches = launches;
+  return XVB_OK;
+}
+
 // ---- .xvbm files for ECAPA ("XVBE0001"): dims, then named layer records -------------------------------------
 extern "C" int xvb_ecapa_save(const xvb_ecapa_t* h, const char* path) {
   XVB_CHECK_ARG(h && h->finalized && path, "xvb_ecapa_save: model not finalized");
@@ -428,6 +494,12 @@ extern "C" void xvb_ecapa_destroy(xvb_ecapa_t* h) {
   if (!h) return;
   h->free_ws();
   cudaFree(h->h_feats); cudaFree(h->h_emb);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(h->p_feats[i]); cudaFree(h->p_emb[i]);
+    if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
+    if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+  }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (auto& kv : h->layers) {
     ELayer& L = kv.second;
     cudaFree(L.w_hi); cudaFree(L.w_lo); cudaFree(L.bias); cudaFree(L.scale); cudaFree(L.shift);

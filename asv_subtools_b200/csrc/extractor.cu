@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
+#include <map>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -28,6 +30,19 @@ static int dev_alloc(T** p, size_t n) {
   return XVB_OK;
 }
 
+// Everything one (B, T) batch shape needs besides launches: a GemmPlan per layer (tensor maps over the
+// extractor's own workspace, tile geometry, kernel instantiation) and the split-K scratch those plans own.
+struct StepPlan {
+  std::vector<GemmPlan*> frame, segment;
+  std::vector<void*> scratch;
+  int pool_blocks = 0, pool_tb = 0;
+  ~StepPlan() {
+    for (GemmPlan* g : frame) gemm_plan_destroy(g);
+    for (GemmPlan* g : segment) gemm_plan_destroy(g);
+    for (void* q : scratch) cudaFree(q);
+  }
+};
+
 }  // namespace xvb
 
 using namespace xvb;
@@ -45,6 +60,7 @@ struct xvb_extractor {
   uint16_t* act_lo[2] = {nullptr, nullptr};
   float* last_f32 = nullptr;                                   // (B,T,C_last)
   float* stats = nullptr;                                      // (B,2*C_last)
+  float* emb_ws = nullptr;                                     // (B,D): nominal target of the last layer's plan
   uint16_t* stats_hi = nullptr; uint16_t* stats_lo = nullptr;
   uint16_t* seg_hi[2] = {nullptr, nullptr}; uint16_t* seg_lo[2] = {nullptr, nullptr};  // (B,max_seg_c)
   float* h_feats = nullptr; float* h_emb = nullptr;            // device staging for *_host
@@ -65,7 +81,14 @@ struct xvb_extractor {
   int pad_front = 0, pad_back = 0;
   float* pool_partial = nullptr;
   size_t pool_partial_cap = 0;
+  // launch plans per batch shape; they hold pointers into the workspace, so anything that reallocates it clears them
+  std::map<std::pair<int, int>, StepPlan*> plans;
+  void drop_plans() {
+    for (auto& kv : plans) delete kv.second;
+    plans.clear();
+  }
   bool profiling = false;
+  bool in_shard = false;
   std::vector<cudaEvent_t> events;
   int events_used = 0;
   cudaStream_t events_stream = nullptr;
@@ -82,10 +105,11 @@ struct xvb_extractor {
   }
 
   void free_ws() {
+    drop_plans();
     cudaFree(in_hi); cudaFree(in_lo);
     for (int i = 0; i < 2; ++i) { cudaFree(act_hi[i]); cudaFree(act_lo[i]); cudaFree(seg_hi[i]); cudaFree(seg_lo[i]); }
-    cudaFree(last_f32); cudaFree(stats); cudaFree(stats_hi); cudaFree(stats_lo);
-    in_hi = in_lo = nullptr; last_f32 = stats = nullptr; stats_hi = stats_lo = nullptr;
+    cudaFree(last_f32); cudaFree(stats); cudaFree(stats_hi); cudaFree(stats_lo); cudaFree(emb_ws);
+    in_hi = in_lo = nullptr; last_f32 = stats = emb_ws = nullptr; stats_hi = stats_lo = nullptr;
     for (int i = 0; i < 2; ++i) act_hi[i] = act_lo[i] = seg_hi[i] = seg_lo[i] = nullptr;
     cap_frames = 0; cap_B = 0;
   }
@@ -215,6 +239,7 @@ static int reserve(xvb_extractor* h, int B, int T) {
   const int cl = h->frame.back().Cout;
   if ((rc = dev_alloc(&h->last_f32, (size_t)nf * cl))) return rc;
   if ((rc = dev_alloc(&h->stats, (size_t)nb * 2 * cl))) return rc;
+  if ((rc = dev_alloc(&h->emb_ws, (size_t)nb * h->segment.back().Cout))) return rc;
   if ((rc = dev_alloc(&h->stats_hi, (size_t)nb * 2 * cl))) return rc;
   if ((rc = dev_alloc(&h->stats_lo, (size_t)nb * 2 * cl))) return rc;
   if (h->max_seg_c > 0)
@@ -227,30 +252,28 @@ static int reserve(xvb_extractor* h, int B, int T) {
   return XVB_OK;
 }
 
-extern "C" int xvb_extractor_extract(xvb_extractor_t* h, const float* feats, int B, int T, float* emb, void* stream) {
-  XVB_CHECK_ARG(h && h->finalized, "xvb_extractor_extract: extractor not finalized");
-  XVB_CHECK_ARG(feats && emb && B > 0 && T > 0, "xvb_extractor_extract: bad arguments");
-  int rc = reserve(h, B, T);
-  if (rc) return rc;
-  const long before = g_launches;
-  cudaStream_t cs = (cudaStream_t)stream;
-  h->events_used = 0;
-  h->events_stream = cs;
-  if ((rc = h->mark(cs))) return rc;
-  // 1. stage the frame matrix as split planes (framework.py:28-33 staging); for the im2col first layer with
-  //    the zero frames of F.pad (components.py:117) written out around every utterance
-  if (h->im2col_first)
-    rc = xvb_split_frames(feats, B, T, h->feat_dim, h->in_hi, h->in_lo, h->ldf, h->pad_front, h->pad_back, stream);
-  else
-    rc = xvb_split_f32(feats, (int64_t)B * T, h->feat_dim, h->feat_dim, h->in_hi, h->in_lo, h->ldf, stream);
-  if (rc) return rc;
-  if ((rc = h->mark(cs))) return rc;
-  // 2. frame-level TDNN stack (xvector.py:85-89)
+// Build the launch plan of one batch shape (see StepPlan).  On failure nothing is cached.
+static int build_step_plan(xvb_extractor* h, int B, int T, StepPlan** out) {
+  StepPlan* sp = new StepPlan();
+  struct Guard { StepPlan* p; ~Guard() { delete p; } } guard{sp};
+  int rc;
+  sp->pool_blocks = xvb_pool_partial_blocks(B, T, &sp->pool_tb);
   const uint16_t* x_hi = h->in_hi;
   const uint16_t* x_lo = h->in_lo;
   int64_t ldx = h->ldf;
-  int pool_tb = 0;
-  const int pool_blocks = xvb_pool_partial_blocks(B, T, &pool_tb);
+  auto add = [&](std::vector<GemmPlan*>& dst, const xvb_tdnn_args_t& a) -> int {
+    void* scratch = nullptr;
+    const size_t need = gemm_plan_scratch_bytes(a);
+    if (need) {
+      XVB_CUDA(cudaMalloc(&scratch, need));
+      sp->scratch.push_back(scratch);
+    }
+    GemmPlan* g = nullptr;
+    int r = gemm_plan_build(&g, a, nullptr, scratch);
+    if (r) return r;
+    dst.push_back(g);
+    return XVB_OK;
+  };
   for (size_t i = 0; i < h->frame.size(); ++i) {
     const Layer& L = h->frame[i];
     const bool last = i + 1 == h->frame.size();
@@ -268,49 +291,123 @@ extern "C" int xvb_extractor_extract(xvb_extractor_t* h, const float* feats, int
       a.x_batch_stride = (int64_t)(T + h->pad_front + h->pad_back) * ldx;
     }
     if (last && h->fused_pooling) {
-      const size_t need = (size_t)pool_blocks * B * 2 * L.Cout;
-      if (need > h->pool_partial_cap) {
-        cudaFree(h->pool_partial);
-        if ((rc = dev_alloc(&h->pool_partial, need))) return rc;
-        h->pool_partial_cap = need;
-      }
       a.pool_partial = h->pool_partial;
     } else if (last) {
       a.y_f32 = h->last_f32; a.ldyf = L.Cout;
     }
-    rc = xvb_tdnn_affine_ex(&a, stream);
-    if (rc && i == 0 && h->im2col_first) {   // overlapping tensor map refused: fall back for good
-      h->im2col_first = false;
-      h->pad_front = h->pad_back = 0;
-      return xvb_extractor_extract(h, feats, B, T, emb, stream);
-    }
+    rc = add(sp->frame, a);
+    if (rc && i == 0 && h->im2col_first) return -1000;   // overlapping tensor map refused: caller falls back for good
     if (rc) return rc;
-    if ((rc = h->mark(cs))) return rc;
     x_hi = y_hi; x_lo = y_lo; ldx = L.Cout;
   }
-  // 3. statistics pooling (xvector.py:90, pooling.py:58-67)
   const int cl = h->frame.back().Cout;
-  if (h->fused_pooling)
-    rc = xvb_pool_finalize(h->pool_partial, pool_blocks, pool_tb, B, T, cl, h->pooling_eps, 0, h->stats, h->stats_hi,
-                           h->stats_lo, 2 * cl, stream);
-  else
-    rc = xvb_stats_pool(h->last_f32, cl, B, T, cl, h->pooling_eps, h->stats, h->stats_hi, h->stats_lo, 2 * cl, stream);
-  if (rc) return rc;
-  if ((rc = h->mark(cs))) return rc;
-  // 4. segment-level layers (xvector.py:92-96)
   x_hi = h->stats_hi; x_lo = h->stats_lo; ldx = 2 * cl;
   for (size_t i = 0; i < h->segment.size(); ++i) {
     const Layer& L = h->segment[i];
     const bool last = i + 1 == h->segment.size();
     uint16_t* y_hi = last ? nullptr : h->seg_hi[i & 1];
     uint16_t* y_lo = last ? nullptr : h->seg_lo[i & 1];
-    rc = xvb_tdnn_affine(x_hi, x_lo, ldx, L.w_hi, L.w_lo, L.bias, L.scale, L.shift, L.flags, L.ctx, 1, y_hi, y_lo, L.Cout,
-                         last ? emb : nullptr, L.Cout, B, 1, L.Cin, L.Cout, stream);
-    if (rc) return rc;
-    if ((rc = h->mark(cs))) return rc;
+    xvb_tdnn_args_t a{};
+    a.x_hi = x_hi; a.x_lo = x_lo; a.ldx = ldx; a.w_hi = L.w_hi; a.w_lo = L.w_lo;
+    a.bias = L.bias; a.bn_scale = L.scale; a.bn_shift = L.shift; a.flags = L.flags;
+    a.context_host = L.ctx; a.ntaps = 1;
+    a.y_hi = y_hi; a.y_lo = y_lo; a.ldy = L.Cout;
+    if (last) { a.y_f32 = h->emb_ws; a.ldyf = L.Cout; }   // redirected to the caller's matrix at launch
+    a.B = B; a.T = 1; a.Cin = L.Cin; a.Cout = L.Cout;
+    if ((rc = add(sp->segment, a))) return rc;
     x_hi = y_hi; x_lo = y_lo; ldx = L.Cout;
   }
+  guard.p = nullptr;
+  *out = sp;
+  return XVB_OK;
+}
+
+extern "C" int xvb_extractor_extract(xvb_extractor_t* h, const float* feats, int B, int T, float* emb, void* stream) {
+  XVB_CHECK_ARG(h && h->finalized, "xvb_extractor_extract: extractor not finalized");
+  XVB_CHECK_ARG(feats && emb && B > 0 && T > 0, "xvb_extractor_extract: bad arguments");
+  int rc = reserve(h, B, T);
+  if (rc) return rc;
+  const long before = g_launches;
+  cudaStream_t cs = (cudaStream_t)stream;
+  if (!h->in_shard) h->events_used = 0;   // a shard call keeps the events of all its batches
+  h->events_stream = cs;
+  StepPlan* sp = nullptr;
+  auto it = h->plans.find(std::make_pair(B, T));
+  if (it != h->plans.end()) {
+    sp = it->second;
+  } else {
+    if (h->fused_pooling) {   // partials of the fused pooling epilogue: (time blocks, B, 2C) fp32
+      int tb = 0;
+      const size_t need = (size_t)xvb_pool_partial_blocks(B, T, &tb) * B * 2 * h->frame.back().Cout;
+      if (need > h->pool_partial_cap) {
+        h->drop_plans();      // they point into the old buffer
+        cudaFree(h->pool_partial);
+        h->pool_partial = nullptr; h->pool_partial_cap = 0;
+        if ((rc = dev_alloc(&h->pool_partial, need))) return rc;
+        h->pool_partial_cap = need;
+      }
+    }
+    rc = build_step_plan(h, B, T, &sp);
+    if (rc == -1000) {        // the driver refused the overlapping (im2col) tensor map: plain first layer from now on
+      h->im2col_first = false;
+      h->pad_front = h->pad_back = 0;
+      h->drop_plans();
+      return xvb_extractor_extract(h, feats, B, T, emb, stream);
+    }
+    if (rc) return rc;
+    h->plans[std::make_pair(B, T)] = sp;
+  }
+  if ((rc = h->mark(cs))) return rc;
+  // 1. stage the frame matrix as split planes (framework.py:28-33 staging); for the im2col first layer with
+  //    the zero frames of F.pad (components.py:117) written out around every utterance
+  if (h->im2col_first)
+    rc = xvb_split_frames(feats, B, T, h->feat_dim, h->in_hi, h->in_lo, h->ldf, h->pad_front, h->pad_back, stream);
+  else
+    rc = xvb_split_f32(feats, (int64_t)B * T, h->feat_dim, h->feat_dim, h->in_hi, h->in_lo, h->ldf, stream);
+  if (rc) return rc;
+  if ((rc = h->mark(cs))) return rc;
+  // 2. frame-level TDNN stack (xvector.py:85-89)
+  for (GemmPlan* g : sp->frame) {
+    if ((rc = gemm_plan_launch(g, stream))) return rc;
+    if ((rc = h->mark(cs))) return rc;
+  }
+  // 3. statistics pooling (xvector.py:90, pooling.py:58-67)
+  const int cl = h->frame.back().Cout;
+  if (h->fused_pooling)
+    rc = xvb_pool_finalize(h->pool_partial, sp->pool_blocks, sp->pool_tb, B, T, cl, h->pooling_eps, 0, h->stats, h->stats_hi,
+                           h->stats_lo, 2 * cl, stream);
+  else
+    rc = xvb_stats_pool(h->last_f32, cl, B, T, cl, h->pooling_eps, h->stats, h->stats_hi, h->stats_lo, 2 * cl, stream);
+  if (rc) return rc;
+  if ((rc = h->mark(cs))) return rc;
+  // 4. segment-level layers (xvector.py:92-96); the last one writes the caller's embedding matrix
+  for (size_t i = 0; i < sp->segment.size(); ++i) {
+    const bool last = i + 1 == sp->segment.size();
+    if ((rc = gemm_plan_launch(sp->segment[i], stream, last ? emb : nullptr))) return rc;
+    if ((rc = h->mark(cs))) return rc;
+  }
   h->last_launches = (int)(g_launches - before);
+  return XVB_OK;
+}
+
+// The caller loop of the reference (extract_embeddings.py:73-83: one utterance per iteration) for a whole
+// shard of N equal-length utterances resident on the device: ceil(N / batch) batches through the stack, back
+// to back on `stream`, embeddings written in place.  Asynchronous.
+extern "C" int xvb_extractor_extract_shard(xvb_extractor_t* h, const float* feats, int64_t N, int T, int batch, float* emb,
+                                           void* stream) {
+  XVB_CHECK_ARG(h && h->finalized && feats && emb && N > 0 && T > 0 && batch > 0, "xvb_extractor_extract_shard: bad arguments");
+  const int D = h->segment.back().Cout;
+  int launches = 0;
+  h->events_used = 0;
+  h->in_shard = true;
+  for (int64_t i = 0; i < N; i += batch) {
+    const int b = (int)(N - i < batch ? N - i : batch);
+    int rc = xvb_extractor_extract(h, feats + (size_t)i * T * h->feat_dim, b, T, emb + (size_t)i * D, stream);
+    if (rc) { h->in_shard = false; return rc; }
+    launches += h->last_launches;
+  }
+  h->in_shard = false;
+  h->last_launches = launches;
   return XVB_OK;
 }
 
@@ -339,32 +436,44 @@ extern "C" int xvb_extractor_extract_host(xvb_extractor_t* h, const float* feats
   return XVB_OK;
 }
 
-extern "C" int xvb_extractor_submit_host(xvb_extractor_t* h, const float* feats_host, int B, int T, float* emb_host,
-                                         int slot, void* stream) {
-  XVB_CHECK_ARG(h && h->finalized && feats_host && emb_host && B > 0 && T > 0 && (slot == 0 || slot == 1),
-                "xvb_extractor_submit_host: bad arguments (slot must be 0 or 1)");
-  XVB_CHECK_ARG(!h->slot_busy[slot], "xvb_extractor_submit_host: slot %d still in flight (call xvb_extractor_wait)", slot);
-  cudaStream_t s = (cudaStream_t)stream;
-  if (!h->copy_stream) {
-    XVB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-      XVB_CUDA(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
-      XVB_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
-    }
+static int ensure_pipeline(xvb_extractor* h) {
+  if (h->copy_stream) return XVB_OK;
+  XVB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    XVB_CUDA(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+    XVB_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
   }
-  const size_t nf = (size_t)B * T * h->feat_dim, ne = (size_t)B * h->segment.back().Cout;
+  return XVB_OK;
+}
+
+static int reserve_slot(xvb_extractor* h, int slot, size_t nf, size_t ne) {
   if (nf > h->p_feats_cap[slot]) {
     cudaFree(h->p_feats[slot]);
+    h->p_feats[slot] = nullptr; h->p_feats_cap[slot] = 0;
     int rc = dev_alloc(&h->p_feats[slot], nf);
     if (rc) return rc;
     h->p_feats_cap[slot] = nf;
   }
   if (ne > h->p_emb_cap[slot]) {
     cudaFree(h->p_emb[slot]);
+    h->p_emb[slot] = nullptr; h->p_emb_cap[slot] = 0;
     int rc = dev_alloc(&h->p_emb[slot], ne);
     if (rc) return rc;
     h->p_emb_cap[slot] = ne;
   }
+  return XVB_OK;
+}
+
+extern "C" int xvb_extractor_submit_host(xvb_extractor_t* h, const float* feats_host, int B, int T, float* emb_host,
+                                         int slot, void* stream) {
+  XVB_CHECK_ARG(h && h->finalized && feats_host && emb_host && B > 0 && T > 0 && (slot == 0 || slot == 1),
+                "xvb_extractor_submit_host: bad arguments (slot must be 0 or 1)");
+  XVB_CHECK_ARG(!h->slot_busy[slot], "xvb_extractor_submit_host: slot %d still in flight (call xvb_extractor_wait)", slot);
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc0 = ensure_pipeline(h);
+  if (rc0) return rc0;
+  const size_t nf = (size_t)B * T * h->feat_dim, ne = (size_t)B * h->segment.back().Cout;
+  if ((rc0 = reserve_slot(h, slot, nf, ne))) return rc0;
   // the copy engine fills this slot while the compute stream still works on the other one
   XVB_CUDA(cudaMemcpyAsync(h->p_feats[slot], feats_host, nf * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream));
   XVB_CUDA(cudaEventRecord(h->ev_h2d[slot], h->copy_stream));
@@ -385,8 +494,44 @@ extern "C" int xvb_extractor_wait(xvb_extractor_t* h, int slot) {
   return XVB_OK;
 }
 
+// The same loop end to end through HOST buffers (pinned, so that the copies are asynchronous): batch k's features
+// cross the link on the copy stream into one of two device slots while batch k-1 runs; embeddings go back batch by
+// batch on `stream`.  No host synchronisation inside the loop (slot reuse is ordered by events on the device);
+// returns when the whole shard's embeddings are in `emb_host`.
+extern "C" int xvb_extractor_extract_shard_host(xvb_extractor_t* h, const float* feats_host, int64_t N, int T, int batch,
+                                                float* emb_host, void* stream) {
+  XVB_CHECK_ARG(h && h->finalized && feats_host && emb_host && N > 0 && T > 0 && batch > 0,
+                "xvb_extractor_extract_shard_host: bad arguments");
+  XVB_CHECK_ARG(!h->slot_busy[0] && !h->slot_busy[1], "xvb_extractor_extract_shard_host: a submit_host slot is still in flight");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc;
+  if ((rc = ensure_pipeline(h))) return rc;
+  const int D = h->segment.back().Cout;
+  const int bmax = (int)(N < batch ? N : batch);
+  for (int slot = 0; slot < 2; ++slot)
+    if ((rc = reserve_slot(h, slot, (size_t)bmax * T * h->feat_dim, (size_t)bmax * D))) return rc;
+  int launches = 0, k = 0;
+  for (int64_t i = 0; i < N; i += batch, ++k) {
+    const int b = (int)(N - i < batch ? N - i : batch);
+    const int slot = k & 1;
+    if (k >= 2) XVB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[slot], 0));   // batch k-2 has left this slot
+    XVB_CUDA(cudaMemcpyAsync(h->p_feats[slot], feats_host + (size_t)i * T * h->feat_dim, (size_t)b * T * h->feat_dim * sizeof(float),
+                             cudaMemcpyHostToDevice, h->copy_stream));
+    XVB_CUDA(cudaEventRecord(h->ev_h2d[slot], h->copy_stream));
+    XVB_CUDA(cudaStreamWaitEvent(s, h->ev_h2d[slot], 0));
+    if ((rc = xvb_extractor_extract(h, h->p_feats[slot], b, T, h->p_emb[slot], stream))) return rc;
+    XVB_CUDA(cudaMemcpyAsync(emb_host + (size_t)i * D, h->p_emb[slot], (size_t)b * D * sizeof(float), cudaMemcpyDeviceToHost, s));
+    XVB_CUDA(cudaEventRecord(h->ev_done[slot], s));
+    launches += h->last_launches;
+  }
+  XVB_CUDA(cudaStreamSynchronize(s));
+  h->last_launches = launches;
+  return XVB_OK;
+}
+
 extern "C" int xvb_extractor_set_fused_pooling(xvb_extractor_t* h, int enable) {
   XVB_CHECK_ARG(h, "xvb_extractor_set_fused_pooling: null extractor");
+  if (h->fused_pooling != (enable != 0)) h->drop_plans();
   h->fused_pooling = enable != 0;
   return XVB_OK;
 }

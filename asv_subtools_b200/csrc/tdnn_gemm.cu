@@ -925,47 +925,33 @@ static int make_out_map(CUtensorMap* m, const void* base, int esize, int C, int 
   return XVB_OK;
 }
 
-template <int BLOCK_N, int kCta, int kNSub = 1, bool kPool = false, bool kHist = false>
-static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& ma2_hi,
-                       const CUtensorMap& ma2_lo, const void* w_hi, const void* w_lo, TdnnGemmParams& p,
-                       cudaStream_t stream) {
+// ------------------------------------------------------------------------------------------------
+// Plan / launch split.  Everything that depends only on shapes and pointers -- tile geometry, the nine
+// tensor maps (cuTensorMapEncodeTiled is a ~1 us driver call each), the kernel instantiation, the grid --
+// is decided once in a GemmPlan; launching a plan is one cudaLaunchKernelEx (+ the split-K reduce).  The
+// extractor objects keep their plans per (B, T), so a batch costs launches only (C1 latency).
+// ------------------------------------------------------------------------------------------------
+struct GemmPlan {
+  CUtensorMap ma_hi, ma_lo, ma2_hi, ma2_lo, mw_hi, mw_lo, my_hi, my_lo, my_f32;
+  TdnnGemmParams p;
+  int (*launch)(const GemmPlan&, const CUtensorMap&, cudaStream_t) = nullptr;   // nullptr: this shard owns no rows
+  int grid = 0;
+  int pdl = 1;
+  // split-K tail (segment_reduce_kernel); the GEMM itself then writes fp32 partials into `scratch`
+  bool reduce = false;
+  const float* r_bias = nullptr; const float* r_scale = nullptr; const float* r_shift = nullptr;
+  int r_flags = 0;
+  float* r_y_f32 = nullptr; long long r_ldyf = 0;
+  __nv_bfloat16* r_y_hi = nullptr; __nv_bfloat16* r_y_lo = nullptr; long long r_ldy = 0;
+  int out_Tdim = 0;          // time extent of the fp32 output map (k_slices for split-K)
+};
+
+template <int BLOCK_N, int kCta, int kNSub, bool kPool, bool kHist>
+static int launch_inst(const GemmPlan& pl, const CUtensorMap& my_f32, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, kCta, kNSub>;
-  CUtensorMap mw_hi, mw_lo;
-  const long long K = (long long)p.ntaps * p.cin_p16;
-  int rc = make_weight_map(&mw_hi, w_hi, K, p.Cout, Cfg::kBRows);
-  if (rc) return rc;
-  rc = make_weight_map(&mw_lo, w_lo, K, p.Cout, Cfg::kBRows);
-  if (rc) return rc;
-  p.num_n_blk = (p.Cout + Cfg::kTileN - 1) / Cfg::kTileN;
-  const int all_m_units = (p.num_t_blk * p.num_b_blk + kCta - 1) / kCta;  // 128-row blocks, or pairs of them
-  if (p.unit_first >= all_m_units) return XVB_OK;                         // this shard owns no rows
-  const int num_m_units = (all_m_units - p.unit_first + p.unit_stride - 1) / p.unit_stride;
-  p.num_units = num_m_units;
-  p.hist_group = 8;
-  const long long tiles = kHist ? (long long)((num_m_units + p.hist_group - 1) / p.hist_group) * p.hist_group * p.num_n_blk
-                                : (long long)num_m_units * p.num_n_blk * (p.k_slices > 1 ? p.k_slices : 1);
-  XVB_CHECK_ARG(tiles < (1ll << 31), "xvb_tdnn_affine: %d x %d tiles exceed one launch", num_m_units, p.num_n_blk);
-  p.num_tiles = (int)tiles;
   XVB_ENSURE_DYN_SMEM((tdnn_gemm_bf16x3_kernel<BLOCK_N, kCta, kNSub, kPool, kHist>), Cfg::kSmemBytes);
-  CUtensorMap my_hi, my_lo, my_f32;
-  static const int box64_knob = getenv("XVB_GEMM_BOX64") ? atoi(getenv("XVB_GEMM_BOX64")) : 1;
-  p.plane_box64 = (box64_knob && !kPool && !kHist && p.y_hi && !p.y_f32 && p.store_mode == 0 && Cfg::kTileN >= 64) ? 1 : 0;
-  if (p.y_hi) {
-    const int bc = p.plane_box64 ? 64 : 32;
-    if ((rc = make_out_map(&my_hi, p.y_hi, 2, p.Cout, p.T, p.B, p.ldy, p.Tb, p.Bb, bc))) return rc;
-    if ((rc = make_out_map(&my_lo, p.y_lo, 2, p.Cout, p.T, p.B, p.ldy, p.Tb, p.Bb, bc))) return rc;
-  } else {
-    my_hi = mw_hi; my_lo = mw_lo;  // unused
-  }
-  if (p.y_f32) {
-    if ((rc = make_out_map(&my_f32, p.y_f32, 4, p.Cout, p.k_slices > 1 ? p.k_slices : p.T, p.B, p.ldyf, p.Tb, p.Bb))) return rc;
-  } else {
-    my_f32 = mw_hi;  // unused
-  }
-  const int units = sm_count() / kCta;  // CTAs (kCta=1) or CTA pairs (kCta=2) resident at once
-  const int grid = (p.num_tiles < units ? p.num_tiles : units) * kCta;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
+  cfg.gridDim = dim3(pl.grid);
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
@@ -976,22 +962,85 @@ static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
-  static const int pdl = getenv("XVB_PDL") ? atoi(getenv("XVB_PDL")) : 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 2 : 1;
-  XVB_CUDA(cudaLaunchKernelEx(&cfg, tdnn_gemm_bf16x3_kernel<BLOCK_N, kCta, kNSub, kPool, kHist>, ma_hi, ma_lo, ma2_hi, ma2_lo, mw_hi, mw_lo,
-                              my_hi, my_lo, my_f32, p));
+  cfg.numAttrs = pl.pdl ? 2 : 1;
+  XVB_CUDA(cudaLaunchKernelEx(&cfg, tdnn_gemm_bf16x3_kernel<BLOCK_N, kCta, kNSub, kPool, kHist>, pl.ma_hi, pl.ma_lo, pl.ma2_hi,
+                              pl.ma2_lo, pl.mw_hi, pl.mw_lo, pl.my_hi, pl.my_lo, my_f32, pl.p));
   XVB_LAUNCH_CHECK();
   return XVB_OK;
+}
+
+template <int BLOCK_N, int kCta, int kNSub = 1, bool kPool = false, bool kHist = false>
+static int prepare_gemm(GemmPlan& pl, const void* w_hi, const void* w_lo) {
+  using Cfg = GemmCfg<BLOCK_N, kCta, kNSub>;
+  TdnnGemmParams& p = pl.p;
+  const long long K = (long long)p.ntaps * p.cin_p16;
+  int rc = make_weight_map(&pl.mw_hi, w_hi, K, p.Cout, Cfg::kBRows);
+  if (rc) return rc;
+  rc = make_weight_map(&pl.mw_lo, w_lo, K, p.Cout, Cfg::kBRows);
+  if (rc) return rc;
+  p.num_n_blk = (p.Cout + Cfg::kTileN - 1) / Cfg::kTileN;
+  const int all_m_units = (p.num_t_blk * p.num_b_blk + kCta - 1) / kCta;  // 128-row blocks, or pairs of them
+  if (p.unit_first >= all_m_units) { pl.launch = nullptr; return XVB_OK; }  // this shard owns no rows
+  const int num_m_units = (all_m_units - p.unit_first + p.unit_stride - 1) / p.unit_stride;
+  p.num_units = num_m_units;
+  p.hist_group = 8;
+  const long long tiles = kHist ? (long long)((num_m_units + p.hist_group - 1) / p.hist_group) * p.hist_group * p.num_n_blk
+                                : (long long)num_m_units * p.num_n_blk * (p.k_slices > 1 ? p.k_slices : 1);
+  XVB_CHECK_ARG(tiles < (1ll << 31), "xvb_tdnn_affine: %d x %d tiles exceed one launch", num_m_units, p.num_n_blk);
+  p.num_tiles = (int)tiles;
+  static const int box64_knob = getenv("XVB_GEMM_BOX64") ? atoi(getenv("XVB_GEMM_BOX64")) : 1;
+  p.plane_box64 = (box64_knob && !kPool && !kHist && p.y_hi && !p.y_f32 && p.store_mode == 0 && Cfg::kTileN >= 64) ? 1 : 0;
+  if (p.y_hi) {
+    const int bc = p.plane_box64 ? 64 : 32;
+    if ((rc = make_out_map(&pl.my_hi, p.y_hi, 2, p.Cout, p.T, p.B, p.ldy, p.Tb, p.Bb, bc))) return rc;
+    if ((rc = make_out_map(&pl.my_lo, p.y_lo, 2, p.Cout, p.T, p.B, p.ldy, p.Tb, p.Bb, bc))) return rc;
+  } else {
+    pl.my_hi = pl.mw_hi; pl.my_lo = pl.mw_lo;  // unused
+  }
+  pl.out_Tdim = p.k_slices > 1 ? p.k_slices : p.T;
+  if (p.y_f32) {
+    if ((rc = make_out_map(&pl.my_f32, p.y_f32, 4, p.Cout, pl.out_Tdim, p.B, p.ldyf, p.Tb, p.Bb))) return rc;
+  } else {
+    pl.my_f32 = pl.mw_hi;  // unused
+  }
+  const int units = sm_count() / kCta;  // CTAs (kCta=1) or CTA pairs (kCta=2) resident at once
+  pl.grid = (p.num_tiles < units ? p.num_tiles : units) * kCta;
+  static const int pdl = getenv("XVB_PDL") ? atoi(getenv("XVB_PDL")) : 1;
+  pl.pdl = pdl;
+  pl.launch = &launch_inst<BLOCK_N, kCta, kNSub, kPool, kHist>;
+  return XVB_OK;
+}
+
+// Split-K for segment-level layers (T == 1: M = B rows, tdnn6 has K = 3000): the slice count depends
+// on K only, so a sub-batch reproduces the full batch's rows bit for bit.  Returns the number of slices (1 = off).
+static int splitk_slices(const xvb_tdnn_args_t& a, bool has_hist, int* kb_per_slice) {
+  const int num_cblk = (a.Cin + kBlockK - 1) / kBlockK;
+  *kb_per_slice = num_cblk;
+  const int splitk = getenv("XVB_SPLITK") ? atoi(getenv("XVB_SPLITK")) : 1;   // read per plan: tests flip it
+  if (!(splitk && a.T == 1 && a.ntaps == 1 && !a.x2_hi && !a.pool_partial && !has_hist && !a.row_bias && !a.utt_bias &&
+        a.B <= 1024 && num_cblk >= 24 && a.Cout % 4 == 0))
+    return 1;
+  int S = num_cblk / 6;
+  S = S > 8 ? 8 : S;
+  *kb_per_slice = (num_cblk + S - 1) / S;
+  return (num_cblk + *kb_per_slice - 1) / *kb_per_slice;   // every slice owns >= 1 channel block
 }
 
 }  // namespace xvb
 
 using namespace xvb;
 
-int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream, const TrialHist* th) {
+size_t xvb::gemm_plan_scratch_bytes(const xvb_tdnn_args_t& a, const TrialHist* th) {
+  int kb;
+  const int S = splitk_slices(a, th != nullptr, &kb);
+  return S > 1 ? (size_t)a.B * S * a.Cout * sizeof(float) : 0;
+}
+
+int xvb::gemm_plan_build(GemmPlan** out, const xvb_tdnn_args_t& a, const TrialHist* th, void* scratch) {
   int rc = require_sm100();
   if (rc) return rc;
+  *out = nullptr;
   const int B = a.B, T = a.T, Cin = a.Cin, Cout = a.Cout, ntaps = a.ntaps;
   XVB_CHECK_ARG(a.x_hi && a.x_lo && a.w_hi && a.w_lo, "xvb_tdnn_affine: null operand pointer");
   XVB_CHECK_ARG(B > 0 && T > 0 && Cin > 0 && Cout > 0, "xvb_tdnn_affine: bad shape B=%d T=%d Cin=%d Cout=%d", B, T, Cin, Cout);
@@ -1020,7 +1069,11 @@ int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream, const TrialHis
   for (int i = 1; i < ntaps; ++i)
     XVB_CHECK_ARG(a.context_host[i] > a.context_host[i - 1], "xvb_tdnn_affine: context must be strictly increasing (components.py:34-36)");
 
-  TdnnGemmParams p{};
+  GemmPlan* plp = new GemmPlan();
+  struct Guard { GemmPlan* p; ~Guard() { delete p; } } guard{plp};
+  GemmPlan& pl = *plp;
+  TdnnGemmParams& p = pl.p;
+  p = TdnnGemmParams{};
   p.B = B; p.T = T; p.Cin = Cin; p.Cout = Cout;
   choose_m_tile(B, T, &p.Tb, &p.Bb);
   p.num_t_blk = (T + p.Tb - 1) / p.Tb;
@@ -1052,33 +1105,26 @@ int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream, const TrialHis
   p.y_lo = reinterpret_cast<__nv_bfloat16*>(a.y_lo);
   p.ldy = a.ldy; p.y_f32 = a.y_f32; p.ldyf = a.ldyf;
 
-  // Split-K for segment-level layers (T == 1: M = B rows, tdnn6 has K = 3000): the slice count depends
-  // on K only, so a sub-batch reproduces the full batch's rows bit for bit.
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  TempBuf partial(s);
-  const int splitk = getenv("XVB_SPLITK") ? atoi(getenv("XVB_SPLITK")) : 1;   // read per call: tests flip it
-  p.k_slices = 1; p.kb_per_slice = p.num_cblk;
-  if (splitk && T == 1 && ntaps == 1 && !a.x2_hi && !a.pool_partial && !th && !a.row_bias && !a.utt_bias && B <= 1024 &&
-      p.num_cblk >= 24 && Cout % 4 == 0) {
-    int S = p.num_cblk / 6;
-    S = S > 8 ? 8 : S;
-    p.kb_per_slice = (p.num_cblk + S - 1) / S;
-    p.k_slices = (p.num_cblk + p.kb_per_slice - 1) / p.kb_per_slice;   // every slice owns >= 1 channel block
-    if ((rc = partial.alloc((size_t)B * p.k_slices * Cout * sizeof(float)))) return rc;
+  p.k_slices = splitk_slices(a, th != nullptr, &p.kb_per_slice);
+  if (p.k_slices > 1) {
+    XVB_CHECK_ARG(scratch, "xvb_tdnn_affine: split-K plan needs %zu bytes of scratch", gemm_plan_scratch_bytes(a, th));
+    pl.reduce = true;
+    pl.r_bias = a.bias; pl.r_scale = a.bn_scale; pl.r_shift = a.bn_shift; pl.r_flags = a.flags;
+    pl.r_y_f32 = a.y_f32; pl.r_ldyf = a.ldyf;
+    pl.r_y_hi = reinterpret_cast<__nv_bfloat16*>(a.y_hi); pl.r_y_lo = reinterpret_cast<__nv_bfloat16*>(a.y_lo); pl.r_ldy = a.ldy;
     p.y_hi = nullptr; p.y_lo = nullptr;
-    p.y_f32 = static_cast<float*>(partial.p); p.ldyf = Cout;
+    p.y_f32 = static_cast<float*>(scratch); p.ldyf = Cout;
     p.bias = nullptr; p.scale = nullptr; p.shift = nullptr; p.flags = 0;
     p.store_mode = 0;
   }
 
-  CUtensorMap ma_hi, ma_lo, ma2_hi, ma2_lo;
-  if ((rc = make_frame_map(&ma_hi, a.x_hi, Cin, T, B, a.ldx, p.Tb, p.Bb, a.x_batch_stride))) return rc;
-  if ((rc = make_frame_map(&ma_lo, a.x_lo, Cin, T, B, a.ldx, p.Tb, p.Bb, a.x_batch_stride))) return rc;
+  if ((rc = make_frame_map(&pl.ma_hi, a.x_hi, Cin, T, B, a.ldx, p.Tb, p.Bb, a.x_batch_stride))) return rc;
+  if ((rc = make_frame_map(&pl.ma_lo, a.x_lo, Cin, T, B, a.ldx, p.Tb, p.Bb, a.x_batch_stride))) return rc;
   if (a.x2_hi) {
-    if ((rc = make_frame_map(&ma2_hi, a.x2_hi, Cin, T, B, a.ldx2, p.Tb, p.Bb))) return rc;
-    if ((rc = make_frame_map(&ma2_lo, a.x2_lo, Cin, T, B, a.ldx2, p.Tb, p.Bb))) return rc;
+    if ((rc = make_frame_map(&pl.ma2_hi, a.x2_hi, Cin, T, B, a.ldx2, p.Tb, p.Bb))) return rc;
+    if ((rc = make_frame_map(&pl.ma2_lo, a.x2_lo, Cin, T, B, a.ldx2, p.Tb, p.Bb))) return rc;
   } else {
-    ma2_hi = ma_hi; ma2_lo = ma_lo;  // unused
+    pl.ma2_hi = pl.ma_hi; pl.ma2_lo = pl.ma_lo;  // unused
   }
 
   // Wide N tiles (CTA pairs) when there are enough M tiles to fill the machine, narrow ones for
@@ -1090,27 +1136,52 @@ int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream, const TrialHis
   const void* w_lo = a.w_lo;
   auto dispatch = [&]() -> int {
     if (a.pool_partial)  // fused pooling always runs on the swapped CTA-pair kernel (any shape: TMA zero-fills)
-      return launch_gemm<256, 2, 1, true>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
+      return prepare_gemm<256, 2, 1, true>(pl, w_hi, w_lo);
     if (th)              // the diagonal test of the symmetric mode assumes 256-row units x 256-column tiles
-      return launch_gemm<256, 2, 1, false, true>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
+      return prepare_gemm<256, 2, 1, false, true>(pl, w_hi, w_lo);
     static const int force_bn = getenv("XVB_GEMM_BN") ? atoi(getenv("XVB_GEMM_BN")) : 0;  // tuning knobs
     // wide tiles cut the operand stream by 25-37 % but serialise the epilogue with the MMAs (one
     // accumulator in TMEM); measured slower end to end (profiles/r01_gemm_experiments.md), so opt-in.
     static const int wide = getenv("XVB_GEMM_WIDE") ? atoi(getenv("XVB_GEMM_WIDE")) : 0;
     if (mode == 2 && wide && force_bn != 128 && Cout >= 512 && (m_tiles / 2) * ((Cout + 511) / 512) >= sms / 2)
-      return launch_gemm<256, 2, 2>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
+      return prepare_gemm<256, 2, 2>(pl, w_hi, w_lo);
     if (mode == 2 && force_bn != 128 && Cout >= 256 && m_tiles * ((Cout + 255) / 256) >= sms)
-      return launch_gemm<256, 2>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
+      return prepare_gemm<256, 2>(pl, w_hi, w_lo);
     if (mode == 2 && Cout >= 128 && m_tiles * ((Cout + 127) / 128) >= sms)
-      return launch_gemm<128, 2>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
-    if (Cout >= 256 && m_tiles * ((Cout + 255) / 256) >= sms) return launch_gemm<256, 1>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
-    if (Cout >= 128 && m_tiles * ((Cout + 127) / 128) >= sms) return launch_gemm<128, 1>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
-    if (Cout >= 64 && m_tiles * ((Cout + 63) / 64) >= sms / 2) return launch_gemm<64, 1>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
-    return launch_gemm<32, 1>(ma_hi, ma_lo, ma2_hi, ma2_lo, w_hi, w_lo, p, s);
+      return prepare_gemm<128, 2>(pl, w_hi, w_lo);
+    if (Cout >= 256 && m_tiles * ((Cout + 255) / 256) >= sms) return prepare_gemm<256, 1>(pl, w_hi, w_lo);
+    if (Cout >= 128 && m_tiles * ((Cout + 127) / 128) >= sms) return prepare_gemm<128, 1>(pl, w_hi, w_lo);
+    if (Cout >= 64 && m_tiles * ((Cout + 63) / 64) >= sms / 2) return prepare_gemm<64, 1>(pl, w_hi, w_lo);
+    return prepare_gemm<32, 1>(pl, w_hi, w_lo);
   };
-  rc = dispatch();
-  if (rc || p.k_slices == 1) return rc;
-  const long long n = (long long)B * Cout;
+  if ((rc = dispatch())) return rc;
+  guard.p = nullptr;
+  *out = plp;
+  return XVB_OK;
+}
+
+void xvb::gemm_plan_destroy(GemmPlan* pl) { delete pl; }
+
+// Launch a plan.  `y_f32_override` (optional) redirects the fp32 output of this launch to another buffer of the
+// same shape and pitch (the extractors' last layer writes straight into the caller's embedding matrix): for a
+// split-K plan it is just the reduce kernel's pointer, otherwise the one output tensor map is re-encoded.
+int xvb::gemm_plan_launch(const GemmPlan* plp, void* stream, float* y_f32_override) {
+  const GemmPlan& pl = *plp;
+  if (!pl.launch) return XVB_OK;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int rc;
+  if (!pl.reduce && y_f32_override && y_f32_override != pl.p.y_f32) {
+    XVB_CHECK_ARG(pl.p.y_f32 && !pl.p.hist && !pl.p.pool_partial && (uintptr_t)y_f32_override % 16 == 0,
+                  "gemm_plan_launch: this plan has no fp32 output to redirect");
+    GemmPlan tmp = pl;
+    tmp.p.y_f32 = y_f32_override;
+    if ((rc = make_out_map(&tmp.my_f32, y_f32_override, 4, pl.p.Cout, pl.out_Tdim, pl.p.B, pl.p.ldyf, pl.p.Tb, pl.p.Bb))) return rc;
+    return tmp.launch(tmp, tmp.my_f32, s);
+  }
+  if ((rc = pl.launch(pl, pl.my_f32, s))) return rc;
+  if (!pl.reduce) return XVB_OK;
+  float* yf = y_f32_override ? y_f32_override : pl.r_y_f32;
+  const long long n = (long long)pl.p.B * pl.p.Cout;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)((n + 255) / 256));
   cfg.blockDim = dim3(256);
@@ -1120,11 +1191,24 @@ int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream, const TrialHis
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  XVB_CUDA(cudaLaunchKernelEx(&cfg, segment_reduce_kernel, (const float*)partial.p, p.k_slices, B, Cout, a.bias, a.bn_scale,
-                              a.bn_shift, a.flags, a.y_f32, (long long)a.ldyf, reinterpret_cast<__nv_bfloat16*>(a.y_hi),
-                              reinterpret_cast<__nv_bfloat16*>(a.y_lo), (long long)a.ldy));
+  XVB_CUDA(cudaLaunchKernelEx(&cfg, segment_reduce_kernel, (const float*)pl.p.y_f32, pl.p.k_slices, pl.p.B, pl.p.Cout, pl.r_bias,
+                              pl.r_scale, pl.r_shift, pl.r_flags, yf, pl.r_ldyf, pl.r_y_hi, pl.r_y_lo, pl.r_ldy));
   XVB_LAUNCH_CHECK();
   return XVB_OK;
+}
+
+int xvb::tdnn_affine_impl(const xvb_tdnn_args_t& a, void* stream, const TrialHist* th) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  TempBuf partial(s);
+  int rc;
+  XVB_CHECK_ARG(a.B > 0 && a.Cin > 0 && a.Cout > 0, "xvb_tdnn_affine: bad shape B=%d Cin=%d Cout=%d", a.B, a.Cin, a.Cout);
+  const size_t need = gemm_plan_scratch_bytes(a, th);
+  if (need && (rc = partial.alloc(need))) return rc;
+  GemmPlan* pl = nullptr;
+  if ((rc = gemm_plan_build(&pl, a, th, partial.p))) return rc;
+  rc = gemm_plan_launch(pl, stream, nullptr);
+  gemm_plan_destroy(pl);
+  return rc;
 }
 
 extern "C" int xvb_pool_partial_blocks(int B, int T, int* frames_per_block) {

@@ -253,6 +253,28 @@ class NativeEcapaExtractor:
                                                 C.c_void_p(torch.cuda.current_stream().cuda_stream)), "xvb_ecapa_extract")
         return emb
 
+    def extract_shard(self, feats, batch=128, out=None):
+        """feats (N,T,F) fp32 CUDA -> (N,D): the whole shard in `batch`-utterance batches, one C call."""
+        if not (isinstance(feats, torch.Tensor) and feats.is_cuda and feats.dtype == torch.float32 and feats.is_contiguous()):
+            raise TypeError("feats must be a contiguous CUDA float32 tensor")
+        n, t, f = feats.shape
+        if f != self.feat_dim:
+            raise ValueError("expected feature dim {}, got {}".format(self.feat_dim, f))
+        emb = out if out is not None else torch.empty(n, self.embed_dim, dtype=torch.float32, device=feats.device)
+        C = self._C
+        self._check(self._lib.xvb_ecapa_extract_shard(self._h, C.c_void_p(feats.data_ptr()), n, t, int(batch),
+                                                      C.c_void_p(emb.data_ptr()),
+                                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)), "xvb_ecapa_extract_shard")
+        return emb
+
+    def extract_shard_host(self, feats_ptr, n, t, emb_ptr, batch=128):
+        """Pinned host feats (n,t,F) in, host embeddings (n,D) out; copies overlap the stack."""
+        C = self._C
+        self._check(self._lib.xvb_ecapa_extract_shard_host(self._h, C.c_void_p(feats_ptr), int(n), int(t), int(batch),
+                                                           C.c_void_p(emb_ptr),
+                                                           C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                    "xvb_ecapa_extract_shard_host")
+
     def extract_host(self, feats_np):
         """feats (B,T,F) float32 host array -> (B,D) float32 host array (H2D + D2H + one sync inside the call)."""
         feats_np = np.ascontiguousarray(feats_np, dtype=np.float32)

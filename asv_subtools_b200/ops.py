@@ -544,6 +544,27 @@ class Extractor:
     def wait(self, slot):
         check(lib.xvb_extractor_wait(self._h, slot), "xvb_extractor_wait")
 
+    def extract_shard(self, feats, batch=256, out=None):
+        """feats (N,T,F) fp32 CUDA -> (N,D) fp32 CUDA: the whole shard in `batch`-utterance batches, one C call
+        (extract_embeddings.py:73-83's loop), asynchronous on the current stream."""
+        feats = _req(feats, torch.float32, "feats")
+        n, t, f = feats.shape
+        if f != self.feat_dim:
+            raise ValueError("expected feature dim {}, got {}".format(self.feat_dim, f))
+        emb = out if out is not None else torch.empty(n, self.embed_dim, dtype=torch.float32, device=feats.device)
+        if out is not None:
+            _req(out, torch.float32, "out")
+            if tuple(out.shape) != (n, self.embed_dim):
+                raise ValueError("out must be ({}, {})".format(n, self.embed_dim))
+        check(lib.xvb_extractor_extract_shard(self._h, _ptr(feats), n, t, int(batch), _ptr(emb), _stream()),
+              "xvb_extractor_extract_shard")
+        return emb
+
+    def extract_shard_host(self, feats_ptr, n, t, emb_ptr, batch=256):
+        """Host-buffer shard call (pinned feats in, embeddings out, copies overlapped with the stack)."""
+        check(lib.xvb_extractor_extract_shard_host(self._h, C.c_void_p(feats_ptr), int(n), int(t), int(batch),
+                                                   C.c_void_p(emb_ptr), _stream()), "xvb_extractor_extract_shard_host")
+
     def extract_host_into(self, feats_ptr, b, t, emb_ptr):
         check(lib.xvb_extractor_extract_host(self._h, C.c_void_p(feats_ptr), b, t, C.c_void_p(emb_ptr), _stream()),
               "xvb_extractor_extract_host")
@@ -555,10 +576,11 @@ class Extractor:
     def set_profiling(self, enable):
         check(lib.xvb_extractor_set_profiling(self._h, 1 if enable else 0), "xvb_extractor_set_profiling")
 
-    def kernel_times_ms(self):
-        """Durations (ms) of the kernels of the last extract call, launch order (needs set_profiling)."""
-        buf = (C.c_float * 64)()
-        n = lib.xvb_extractor_kernel_times(self._h, buf, 64)
+    def kernel_times_ms(self, max_n=64):
+        """Durations (ms) between consecutive profiling events of the last extract call, launch order (needs
+        set_profiling).  After extract_shard(): every batch contributes its kernels plus the gap to the next batch."""
+        buf = (C.c_float * max_n)()
+        n = lib.xvb_extractor_kernel_times(self._h, buf, max_n)
         if n < 0:
             check(n, "xvb_extractor_kernel_times")
         return [float(buf[i]) for i in range(n)]

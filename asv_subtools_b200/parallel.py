@@ -24,3 +24,14 @@ def all_gather_embeddings(local, n_total, rank, world):
     # row r*n_max + j holds utterance j*world + r
     out = gathered.view(world, n_max, d).transpose(0, 1).reshape(world * n_max, d)
     return out[:n_total].contiguous()
+
+
+def all_gather_blocks(local, out=None):
+    """Contiguous sharding (rank r owns rows [r*n, (r+1)*n), every rank the same n): ONE all_gather_into_tensor
+    straight into the (world*n, D) table, no padding, no reordering pass, no second buffer -- the layout the
+    1 M-utterance job uses (bench.py, BASELINE configs[3]: 2.05 GB at 1 M x 512)."""
+    world = dist.get_world_size()
+    if out is None:
+        out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous())
+    return out

@@ -369,10 +369,22 @@ int xvb_extractor_extract_host(xvb_extractor_t* h, const float* feats_host, int 
 int xvb_extractor_submit_host(xvb_extractor_t* h, const float* feats_host, int B, int T, float* emb_host, int slot,
                               void* stream);
 int xvb_extractor_wait(xvb_extractor_t* h, int slot);
+/* A whole shard of N equal-length utterances -- the caller loop of the reference
+ * (pytorch/pipeline/onestep/extract_embeddings.py:73-83, one utterance per iteration; sharded over `nj` jobs by
+ * extract_xvectors_for_pytorch.sh:125-136) as ONE call: ceil(N / batch) batches through the stack back to back.
+ *   _shard      : feats (N, T, feat_dim) and emb (N, embed_dim) on the device; asynchronous on `stream`;
+ *   _shard_host : the same through host buffers (pinned, so that the copies overlap): batch i+1 crosses the link
+ *                 while batch i runs (the submit/wait protocol above); returns when emb_host is complete.
+ * Launch plans (tensor maps, tile geometry) are cached per batch shape, so a batch costs its launches only. */
+int xvb_extractor_extract_shard(xvb_extractor_t* h, const float* feats, int64_t N, int T, int batch, float* emb,
+                                void* stream);
+int xvb_extractor_extract_shard_host(xvb_extractor_t* h, const float* feats_host, int64_t N, int T, int batch,
+                                     float* emb_host, void* stream);
 /* Per-kernel timing with CUDA events recorded on the launching stream around every kernel of
  * the next extract calls.  xvb_extractor_kernel_times() waits for the last call and returns the
  * number of kernels n (<= max_n) and their durations in ms, in launch order: split, frame layers,
- * stats pooling, segment layers. */
+ * stats pooling, segment layers.  After xvb_extractor_extract_shard the events of ALL its batches are kept: per batch
+ * the same kernel intervals followed by the interval to the next batch's first event. */
 int xvb_extractor_set_profiling(xvb_extractor_t* h, int enable);
 int xvb_extractor_kernel_times(xvb_extractor_t* h, float* ms_host, int max_n);
 /* Fused pooling (default on): the last frame layer's epilogue reduces over time itself and the
@@ -439,6 +451,11 @@ int xvb_ecapa_feat_dim(const xvb_ecapa_t* h);
 int xvb_ecapa_extract(xvb_ecapa_t* h, const float* feats, int B, int T, float* emb, void* stream);
 /* Same through host buffers (H2D of feats, D2H of emb inside; synchronises the stream). */
 int xvb_ecapa_extract_host(xvb_ecapa_t* h, const float* feats_host, int B, int T, float* emb_host, void* stream);
+/* Whole shard of N equal-length utterances in `batch`-utterance batches (extract_embeddings.py:73-83's loop as one
+ * call): device-resident and asynchronous, or through pinned host buffers with the copies overlapped. */
+int xvb_ecapa_extract_shard(xvb_ecapa_t* h, const float* feats, int64_t N, int T, int batch, float* emb, void* stream);
+int xvb_ecapa_extract_shard_host(xvb_ecapa_t* h, const float* feats_host, int64_t N, int T, int batch, float* emb_host,
+                                 void* stream);
 int xvb_ecapa_last_launches(const xvb_ecapa_t* h);
 /* "XVBE0001" model files: the named layers as handed to xvb_ecapa_set_layer. */
 int xvb_ecapa_save(const xvb_ecapa_t* h, const char* path);

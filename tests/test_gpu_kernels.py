@@ -378,3 +378,36 @@ def test_factored_xvector_matches_reference_golden(golden, pos):
         with torch.no_grad():
             want = onn.factored_xvector_forward(sd, torch.from_numpy(f).transpose(1, 2), pos).squeeze(2).numpy()
         assert rel(m.extract_embedding_batch(f).cpu().numpy(), want) < EMB_TOL, T
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pos", ["far", "near"])
+def test_shard_calls_and_cached_launch_plans_equal_per_batch_extraction(pos):
+    """xvb_extractor_extract_shard[_host] (the reference's caller loop, extract_embeddings.py:73-83, as one call) and
+    the per-(B, T) launch-plan cache: a shard in ragged batches, the same shard through pinned host buffers, and batch
+    shapes revisited in a different order all reproduce independent per-batch calls bit for bit ("far": split-K last
+    layer, reduce kernel redirected; "near": the last layer's output map re-encoded per destination)."""
+    m, _ = _model(80, 102, pos)
+    ex = m.extractor()
+    n, t = 150, 61
+    feats = torch.from_numpy(onn.synthetic_feats(n, t, 80, 909)).cuda()
+    want = torch.cat([ex.extract(feats[i:i + 64]).clone() for i in range(0, n, 64)])      # batches of 64, 64, 22
+    got = ex.extract_shard(feats, 64)
+    assert torch.equal(got, want)
+    assert ex.last_launches >= 3 * 8
+    other = torch.from_numpy(onn.synthetic_feats(5, 33, 80, 910)).cuda()                  # another shape in between
+    w_other = ex.extract(other).clone()
+    assert torch.equal(ex.extract_shard(feats, 64), want) and torch.equal(ex.extract(other), w_other)
+    m2, _ = _model(80, 102, pos)                                                            # cold extractor, no cached plans
+    assert torch.equal(m2.extractor().extract(other), w_other)
+    host = torch.empty(n, t, 80, dtype=torch.float32, pin_memory=True)
+    host.copy_(feats)
+    out = torch.empty(n, ex.embed_dim, dtype=torch.float32, pin_memory=True)
+    ex.extract_shard_host(host.data_ptr(), n, t, out.data_ptr(), 64)
+    assert torch.equal(out, want.cpu())
+    ex.set_profiling(True)                                                                 # events of every batch are kept
+    ex.extract_shard(feats, 64)
+    times = ex.kernel_times_ms(max_n=256)
+    ex.set_profiling(False)
+    per_batch = len(times) // 3 + 1
+    assert len(times) == 3 * per_batch - 1 and all(x >= 0 for x in times)

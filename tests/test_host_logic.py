@@ -128,7 +128,7 @@ def test_world_size_2_gloo_sharding_and_gather(tmp_path):
     script.write_text('''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, %r)
-from asv_subtools_b200.parallel import shard_indices, all_gather_embeddings
+from asv_subtools_b200.parallel import shard_indices, all_gather_embeddings, all_gather_blocks
 dist.init_process_group("gloo")
 r, w = dist.get_rank(), dist.get_world_size()
 n, d = 11, 4
@@ -136,6 +136,10 @@ idx = shard_indices(n, r, w)
 local = torch.stack([torch.full((d,), float(i)) for i in idx])
 full = all_gather_embeddings(local, n, r, w)
 assert full.shape == (n, d) and torch.equal(full[:, 0], torch.arange(n, dtype=torch.float32)), full
+# contiguous blocks (the 1 M-utterance job's layout): rank r owns rows [r*5, (r+1)*5)
+blk = (torch.arange(5, dtype=torch.float32) + 5 * r)[:, None].repeat(1, d)
+tab = all_gather_blocks(blk)
+assert tab.shape == (5 * w, d) and torch.equal(tab[:, 0], torch.arange(5 * w, dtype=torch.float32)), tab
 print("rank", r, "ok")
 dist.destroy_process_group()
 ''' % ROOT)
