@@ -405,8 +405,11 @@ def config4_block(tm, full, spk_full, rank, world, verify_single):
     from asv_subtools_b200 import ops
     from asv_subtools_b200.score import trial_histogram as th
     n = full.shape[0]
-    th.zoom_eer(full[:4096].contiguous(), spk_full[:4096].contiguous(), passes=1, group=False)      # warm the kernels
     x, prep_ms = tm.wall(lambda: ops.center_length_norm(full, ops.column_mean(full)))
+    try:                                                      # warm the histogram kernel on a corner of the table
+        th.zoom_eer(x[:4096].contiguous(), spk_full[:4096].contiguous(), passes=1, group=False)
+    except ValueError:
+        pass
     pilot = 32 if n >= 1 << 16 else 0
 
     def eer_job(**kw):
