@@ -99,7 +99,7 @@ __global__ void plda_rowterm_kernel(const float* __restrict__ x, const float* __
 // One CTA per row of a cohort score matrix: bitonic sort (descending) in shared memory, then mean and
 // unbiased standard deviation of the top n entries -- the groupby().head(top_n) / .mean() / .std()
 // (ddof = 1) of score/ScoreNormalization.py:151-166 (AS-norm) and :93-98 (S-norm, n = all).
-__global__ void topn_mean_std_kernel(const float* __restrict__ S, long long ld, int ncoh, int P, int top_n,
+__global__ void topn_mean_std_kernel(const float* __restrict__ S, long long ld, int ncoh, int P, int top_n, int ddof,
                                      float* __restrict__ mean, float* __restrict__ stdv) {
   extern __shared__ float sv[];
   const float* row = S + (long long)blockIdx.x * ld;
@@ -137,7 +137,7 @@ __global__ void topn_mean_std_kernel(const float* __restrict__ S, long long ld, 
     double q = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) q += red[1][w];
     mean[blockIdx.x] = (float)mu;
-    stdv[blockIdx.x] = (float)sqrt(q / (double)(n - 1));   // ddof = 1 like pandas; n == 1 -> NaN as there
+    stdv[blockIdx.x] = (float)sqrt(q / (double)(n - ddof));   // ddof = 1 like pandas (n == 1 -> NaN as there); 0 like np.std
   }
 }
 
@@ -387,15 +387,21 @@ extern "C" int xvb_speaker_mean(const float* x, int D, const int32_t* offsets, c
 
 extern "C" int xvb_topn_mean_std(const float* S, int64_t lds, int64_t rows, int ncoh, int top_n, float* mean, float* stdv,
                                  void* stream) {
+  return xvb_topn_mean_std_ddof(S, lds, rows, ncoh, top_n, 1, mean, stdv, stream);
+}
+
+extern "C" int xvb_topn_mean_std_ddof(const float* S, int64_t lds, int64_t rows, int ncoh, int top_n, int ddof, float* mean,
+                                      float* stdv, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
-  XVB_CHECK_ARG(S && mean && stdv && rows > 0 && ncoh > 0 && lds >= ncoh, "xvb_topn_mean_std: bad arguments");
+  XVB_CHECK_ARG(S && mean && stdv && rows > 0 && ncoh > 0 && lds >= ncoh && (ddof == 0 || ddof == 1),
+                "xvb_topn_mean_std: bad arguments (ddof is 0 or 1)");
   XVB_CHECK_ARG(ncoh <= 32768, "xvb_topn_mean_std: cohort of %d exceeds the 32768 entries one CTA sorts on chip", ncoh);
   int P = 1;
   while (P < ncoh) P <<= 1;
   const size_t smem = (size_t)P * sizeof(float);
   XVB_ENSURE_DYN_SMEM((topn_mean_std_kernel), 32768 * 4);
-  topn_mean_std_kernel<<<(unsigned)rows, 512, smem, (cudaStream_t)stream>>>(S, lds, ncoh, P, top_n, mean, stdv);
+  topn_mean_std_kernel<<<(unsigned)rows, 512, smem, (cudaStream_t)stream>>>(S, lds, ncoh, P, top_n, ddof, mean, stdv);
   XVB_LAUNCH_CHECK();
   return XVB_OK;
 }

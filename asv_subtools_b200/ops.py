@@ -281,13 +281,14 @@ def speaker_mean(x, spk2rows):
     return out, counts
 
 
-def topn_mean_std(S, top_n=0):
-    """Per row of a cohort score matrix: mean / unbiased std of the top_n largest entries (0 = all)."""
+def topn_mean_std(S, top_n=0, ddof=1):
+    """Per row of a cohort score matrix: mean / std of the top_n largest entries (0 = all); ddof = 1 is pandas'
+    .std() (score/ScoreNormalization.py), ddof = 0 np.std (subtools2/egrecho/score/asnorm.py)."""
     S = _req(S, torch.float32, "S")
     m = torch.empty(S.shape[0], dtype=torch.float32, device=S.device)
     sd = torch.empty_like(m)
-    check(lib.xvb_topn_mean_std(_ptr(S), S.shape[1], S.shape[0], S.shape[1], int(top_n), _ptr(m), _ptr(sd), _stream()),
-          "xvb_topn_mean_std")
+    check(lib.xvb_topn_mean_std_ddof(_ptr(S), S.shape[1], S.shape[0], S.shape[1], int(top_n), int(ddof), _ptr(m), _ptr(sd),
+                                     _stream()), "xvb_topn_mean_std")
     return m, sd
 
 

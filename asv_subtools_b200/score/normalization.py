@@ -19,10 +19,11 @@ import torch
 from .. import ops
 
 
-def normalize(scores, trial_e, trial_t, enroll_cohort, test_cohort, top_n=0, cross_select=False):
+def normalize(scores, trial_e, trial_t, enroll_cohort, test_cohort, top_n=0, cross_select=False, ddof=1):
     """scores (n,) fp32; trial_e/trial_t int32 indices into the rows of the two cohort matrices
     (Ne, Nc) / (Nt, Nc), all CUDA.  top_n <= 0: S-norm (all cohort scores).  cross_select: AS-norm where each
-    side's statistics use the OTHER side's top-n cohort (ScoreNormalization.py:146-160)."""
+    side's statistics use the OTHER side's top-n cohort (ScoreNormalization.py:146-160).  ddof: 1 = pandas .std() of
+    ScoreNormalization.py, 0 = np.std of subtools2/egrecho/score/asnorm.py:137-140."""
     if cross_select:
         if top_n < 2:
             raise ValueError("cross selection needs top_n >= 2")
@@ -33,18 +34,19 @@ def normalize(scores, trial_e, trial_t, enroll_cohort, test_cohort, top_n=0, cro
         top_n = min(top_n, enroll_cohort.shape[1])    # groupby().head(top_n) semantics: a small cohort is used whole
         return ops.snorm_cross_trials(scores, trial_e, trial_t, enroll_cohort, test_cohort,
                                       ops.topn_indices(enroll_cohort, top_n), ops.topn_indices(test_cohort, top_n))
-    me, se = ops.topn_mean_std(enroll_cohort, top_n)
-    mt, st = ops.topn_mean_std(test_cohort, top_n)
+    me, se = ops.topn_mean_std(enroll_cohort, top_n, ddof)
+    mt, st = ops.topn_mean_std(test_cohort, top_n, ddof)
     return ops.snorm_trials(scores, trial_e, trial_t, me, se, mt, st)
 
 
-def asnorm_embeddings(enroll, test, cohort, trial_e, trial_t, top_n=300):
-    """AS-norm straight from length-normalised embeddings: cohort scores are two cosine GEMMs."""
+def asnorm_embeddings(enroll, test, cohort, trial_e, trial_t, top_n=300, ddof=1):
+    """AS-norm straight from length-normalised embeddings: cohort scores are two cosine GEMMs.  With ddof = 0 this is
+    `ScoreNorm.norm` of subtools2/egrecho/score/asnorm.py:283-352 (cosine GEMM -> top-n -> np.mean / np.std)."""
     pad = (-cohort.shape[0]) % 4
     if pad:  # the score-matrix kernel wants a multiple of 4 columns; duplicate-free padding with -inf scores is
         raise ValueError("cohort size must be a multiple of 4 (got {})".format(cohort.shape[0]))
     s = ops.cosine_trials(enroll, test, trial_e, trial_t)
-    return normalize(s, trial_e, trial_t, ops.cosine_matrix(enroll, cohort), ops.cosine_matrix(test, cohort), top_n)
+    return normalize(s, trial_e, trial_t, ops.cosine_matrix(enroll, cohort), ops.cosine_matrix(test, cohort), top_n, ddof=ddof)
 
 
 def _load(path):

@@ -274,3 +274,98 @@ class Coral:
             kaldi_io.write_vec_flt(f, self.mean.reshape(-1), key="mean")
             kaldi_io.write_vec_flt(f, self.within_var.reshape(-1), key="within_var")
             kaldi_io.write_vec_flt(f, self.between_var.reshape(-1), key="between_var")
+
+
+def read_ori(plda):
+    """(mean (D,1), within (D,D), between (D,D)) float64 from the three-vector ark the pyplda scripts exchange
+    (`plda_read` of every ivector-adapt-plda-*.py; written by plda_base.py:337-342)."""
+    parts = dict(kaldi_io.read_vec_flt_ark(plda))
+    mean = np.asarray(parts["mean"], dtype=np.float64).reshape(-1, 1)
+    d = mean.shape[0]
+    return (mean, np.asarray(parts["within_var"], dtype=np.float64).reshape(d, d),
+            np.asarray(parts["between_var"], dtype=np.float64).reshape(d, d))
+
+
+def _excess_over(base, target):
+    """B^-T max(0, E - I) B^-1 where B diagonalises the pair: B^T base B = I, B^T target B = diag(E) -- the part of
+    `target` that exceeds `base`, the regulariser shared by CORAL+ / LIP-reg / CIP-reg
+    (ivector-adapt-plda-coralplus.py:76-84).  D x D float64 algebra on the host, like the EM's."""
+    lam, q = np.linalg.eigh(base)
+    scale = q / np.sqrt(lam)[None, :]                              # Q diag(lam^-1/2): base -> I
+    e, p = np.linalg.eigh(scale.T @ target @ scale)
+    b_inv = p.T @ (q * np.sqrt(lam)[None, :]).T                    # (Q diag(lam^-1/2) P)^-1 = P^T diag(lam^1/2) Q^T
+    return b_inv.T @ (np.maximum(0.0, e - 1.0)[:, None] * b_inv)
+
+
+class _Adapter:
+    def plda_write(self, plda):
+        Coral.plda_write(self, plda)
+
+    def get_output(self):
+        return PLDA(self.mean, self.within_var, self.between_var)
+
+
+class CoralPlus(Coral):
+    """CORAL+ (ivector-adapt-plda-coralplus.py, CORALPlus.update_plda :40-96): the pseudo in-domain covariances of
+    CORAL only add their excess over the out-of-domain ones, scaled by within/between_covar_scale."""
+
+    def update_plda(self, device="cuda"):
+        w0, b0 = self.within_var, self.between_var
+        super().update_plda(device)                                # adaptation-set covariance: Gram product on the GPU
+        self.within_var = w0 + self.within_covar_scale * _excess_over(w0, self.within_var)
+        self.between_var = b0 + self.between_covar_scale * _excess_over(b0, self.between_var)
+
+
+class Lip(_Adapter):
+    """Linear interpolation of an out-of-domain and an in-domain model (ivector-adapt-plda-lip.py :25-34)."""
+
+    def __init__(self, interpolation_weight=0.4):
+        self.interpolation_weight = interpolation_weight
+
+    def interpolation(self, plda_out_domain, plda_in_domain):
+        a = self.interpolation_weight
+        _, w_out, b_out = read_ori(plda_out_domain)
+        self.mean, w_in, b_in = read_ori(plda_in_domain)
+        self.within_var, self.between_var = a * w_out + (1 - a) * w_in, a * b_out + (1 - a) * b_in
+
+
+class LipReg(_Adapter):
+    """ivector-adapt-plda-lip-reg.py :26-49: in-domain model + (1 - weight) x the out-of-domain model's excess over it."""
+
+    def __init__(self, interpolation_weight=0.6):
+        self.interpolation_weight = interpolation_weight
+
+    def interpolation(self, plda_out_domain, plda_in_domain):
+        a = 1.0 - self.interpolation_weight
+        _, w_out, b_out = read_ori(plda_out_domain)
+        self.mean, w_in, b_in = read_ori(plda_in_domain)
+        self.within_var, self.between_var = w_in + a * _excess_over(w_in, w_out), b_in + a * _excess_over(b_in, b_out)
+
+
+class Cip(_Adapter):
+    """ivector-adapt-plda-cip.py :113-121: interpolation of a CORAL-adapted out-of-domain model (a `Coral` after
+    update_plda) with the in-domain model."""
+
+    def __init__(self, interpolation_weight=0.5):
+        self.interpolation_weight = interpolation_weight
+
+    def interpolation(self, coral, plda_in_domain):
+        a = self.interpolation_weight
+        self.mean, w_in, b_in = read_ori(plda_in_domain)
+        self.within_var, self.between_var = a * coral.within_var + (1 - a) * w_in, a * coral.between_var + (1 - a) * b_in
+
+
+class CipReg(_Adapter):
+    """ivector-adapt-plda-cip-reg.py :109-128: plda_read(in-domain), then add weight x the CORAL model's excess."""
+
+    def __init__(self, interpolation_weight=0.5):
+        self.interpolation_weight = interpolation_weight
+
+    def plda_read(self, plda):
+        self.mean, self.within_var, self.between_var = read_ori(plda)
+        self.dim = self.mean.shape[0]
+
+    def interpolation(self, coral):
+        a = self.interpolation_weight
+        self.within_var = self.within_var + a * _excess_over(self.within_var, coral.within_var)
+        self.between_var = self.between_var + a * _excess_over(self.between_var, coral.between_var)

@@ -249,6 +249,10 @@ int xvb_speaker_mean(const float* x, int D, const int32_t* offsets, const int32_
  * out = 0.5*((s-mean_e[e])/std_e[e] + (s-mean_t[t])/std_t[t]) per listed trial (:101-104, :172-173). */
 int xvb_topn_mean_std(const float* S, int64_t lds, int64_t rows, int ncoh, int top_n, float* mean, float* stdv,
                       void* stream);
+/* The same with the divisor of the variance stated: ddof = 1 is pandas' .std() (ScoreNormalization.py:163-166),
+ * ddof = 0 is np.std of subtools2/egrecho/score/asnorm.py:137-140 (`compute_cohort_stats`). */
+int xvb_topn_mean_std_ddof(const float* S, int64_t lds, int64_t rows, int ncoh, int top_n, int ddof, float* mean,
+                           float* stdv, void* stream);
 int xvb_snorm_trials(const float* scores, const int32_t* trial_e, const int32_t* trial_t, int64_t num_trials,
                      const float* mean_e, const float* std_e, const float* mean_t, const float* std_t, float* out,
                      void* stream);

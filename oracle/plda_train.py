@@ -126,6 +126,50 @@ def coral_adapt(mean, within, between, adapt, mean_diff_scale=1.0):
     return m.reshape(-1), a @ within @ a.T, a @ between @ a.T
 
 
+def covariance_regulariser(base, target):
+    """The term shared by CORAL+ / LIP-reg / CIP-reg (ivector-adapt-plda-coralplus.py:76-84, -lip-reg.py:35-41,
+    -cip-reg.py:113-121): with B the simultaneous diagonaliser of (base, target) -- B^T base B = I,
+    B^T target B = diag(E) -- return B^-T max(0, diag(E) - I) B^-1, i.e. the part of `target` that exceeds `base`."""
+    base = np.asarray(base, dtype=np.float64)
+    lam, q = np.linalg.eigh(base)
+    t = np.diag(1.0 / np.sqrt(lam)) @ q.T                       # base -> I
+    e, p = np.linalg.eigh(t @ np.asarray(target, dtype=np.float64) @ t.T)
+    b_inv = np.linalg.inv(q @ np.diag(1.0 / np.sqrt(lam)) @ p)
+    return b_inv.T @ np.maximum(0.0, np.diag(e) - np.eye(base.shape[0])) @ b_inv
+
+
+def coralplus_adapt(mean, within, between, adapt, within_scale=0.8, between_scale=0.8, mean_diff_scale=1.0):
+    """CORALPlus.update_plda, ivector-adapt-plda-coralplus.py:40-96: the CORAL pseudo in-domain covariances only ADD
+    their excess over the out-of-domain ones."""
+    m, s_w, s_b = coral_adapt(mean, within, between, adapt, mean_diff_scale)
+    return (m, within + within_scale * covariance_regulariser(within, s_w),
+            between + between_scale * covariance_regulariser(between, s_b))
+
+
+def lip_adapt(out_model, in_model, weight=0.4):
+    """LIP.interpolation, ivector-adapt-plda-lip.py:25-34.  Models are (mean, within, between); mean of the in-domain one."""
+    return (in_model[0], weight * out_model[1] + (1 - weight) * in_model[1], weight * out_model[2] + (1 - weight) * in_model[2])
+
+
+def lipreg_adapt(out_model, in_model, weight=0.6):
+    """LIPReg.interpolation, ivector-adapt-plda-lip-reg.py:26-49."""
+    return (in_model[0], in_model[1] + (1 - weight) * covariance_regulariser(in_model[1], out_model[1]),
+            in_model[2] + (1 - weight) * covariance_regulariser(in_model[2], out_model[2]))
+
+
+def cip_adapt(out_model, in_model, adapt, weight=0.5):
+    """CORAL.update_plda + CIP.interpolation, ivector-adapt-plda-cip.py:38-77, :113-121."""
+    _, s_w, s_b = coral_adapt(out_model[0], out_model[1], out_model[2], adapt)
+    return (in_model[0], weight * s_w + (1 - weight) * in_model[1], weight * s_b + (1 - weight) * in_model[2])
+
+
+def cipreg_adapt(out_model, in_model, adapt, weight=0.5):
+    """CORAL.update_plda + CIPReg.interpolation, ivector-adapt-plda-cip-reg.py:109-128."""
+    _, s_w, s_b = coral_adapt(out_model[0], out_model[1], out_model[2], adapt)
+    return (in_model[0], in_model[1] + weight * covariance_regulariser(in_model[1], s_w),
+            in_model[2] + weight * covariance_regulariser(in_model[2], s_b))
+
+
 # ---------------------------------------------------------------- Kaldi-style PLDA scoring (plda_base.py PLDA)
 def plda_transform(x, transform, offset, psi, num_examples=1, normalize_length=True, simple_length_norm=False,
                    reference_dim_quirk=False):

@@ -6,13 +6,22 @@ Pinned pieces (replayed against the imported reference in tests/golden):
   * two-covariance PLDA (score/pyplda/gaussian-plda-scoring.py:23-50, :65)
   * Bosaris-like EER (computeEER-like-Bosaris.py:50-107)
   * DET-interpolated EER (subtools2/egrecho/score/binary_metrics.py:11-120)
-Unpinned pieces ("parity unpinned": the arithmetic lives in Kaldi binaries which the
-reference neither vendors nor pins -- README.md:195-196 -- and which are absent here;
-restated from Kaldi's published semantics and anchored on the call sites):
-  * ivector-normalize-length --scaleup=false  (score/process.sh:194-203)
+  * global mean / per-speaker mean / mean subtraction + length normalisation + dot product -- pinned through the
+    reference tree's OWN restatement of those Kaldi steps, subtools2/egrecho/score/{utils.py:11-24, score.py:160-175,
+    asnorm.py:30-98} (tests/golden/make_golden_egrecho.py -> egrecho_backend.npz): `compute_mean_stats` ==
+    `global_mean` / `speaker_mean`; torch cosine_similarity of mean-subtracted vectors ==
+    `cosine_trials(length_norm(subtract_global_mean(.)))`
+  * AS-norm in both forms of the tree: pandas / ddof = 1 (score/ScoreNormalization.py) and NumPy / ddof = 0
+    (subtools2/egrecho/score/asnorm.py:101-142, :283-352)
+Still unpinned ("parity unpinned": the arithmetic lives in Kaldi binaries which the reference neither vendors nor
+pins -- README.md:195-196 -- and which are absent here; restated from Kaldi's published semantics and anchored on
+the call sites).  The egrecho pin above covers their arithmetic, not Kaldi's own rounding / file conventions:
+  * ivector-normalize-length --scaleup=false  (score/process.sh:194-203)  [scaleup=true would multiply by sqrt(D)]
   * ivector-mean / ivector-subtract-global-mean (score/process.sh:156-192)
   * ivector-compute-dot-products              (score/score.sh:82-97)
   * compute-eer                               (computeEER.sh:21-22)
+  * ivector-plda-scoring                      (score/score.sh:99-121; arithmetic pinned via plda_base.py instead)
+  * apply-cmvn-sliding                        (extract_xvectors_for_pytorch.sh:106-111; oracle/frontend.py)
 """
 from __future__ import annotations
 
@@ -192,14 +201,15 @@ def synthetic_speakers(num_spk, utts_per_spk, dim, seed, noise=0.5):
 
 
 # ---------------------------------------------------------------- S-norm / AS-norm
-def snorm_stats(cohort_scores, top_n=0):
+def snorm_stats(cohort_scores, top_n=0, ddof=1):
     """Per-row mean and std (ddof=1, pandas' default) of the top_n largest cohort scores; top_n <= 0
     means all of them.  score/ScoreNormalization.py:93-98 (S-norm), :151-166 (AS-norm, cross_select
-    false): sort descending, groupby(key).head(top_n), .mean()/.std()."""
+    false): sort descending, groupby(key).head(top_n), .mean()/.std().  ddof=0 is the other AS-norm of the tree,
+    subtools2/egrecho/score/asnorm.py:128-140 (np.partition top-n, np.mean / np.std)."""
     s = np.sort(np.asarray(cohort_scores, dtype=np.float64), axis=1)[:, ::-1]
     if top_n and top_n > 0:
         s = s[:, :top_n]
-    return s.mean(axis=1), s.std(axis=1, ddof=1)
+    return s.mean(axis=1), s.std(axis=1, ddof=ddof)
 
 
 def snorm_apply(scores, trial_e, trial_t, mean_e, std_e, mean_t, std_t):
@@ -238,3 +248,66 @@ def snorm_cross_apply(scores, trial_e, trial_t, enroll_cohort, test_cohort, top_
         gt = tc[t, top_e[e]]
         out[k] = 0.5 * ((s - ge.mean()) / ge.std(ddof=1) + (s - gt.mean()) / gt.std(ddof=1))
     return out
+
+
+# ---------------------------------------------------------------- back-end transforms (process.sh trainlda / trainwhiten / trainpcawhiten)
+def zca_whitening(x, regularization=1e-6):
+    """score/whiten/train_ZCA_Whitening.py ZCA.fit (:34-52) + write_matrix (:68-76): cov = X^T X / (n-1) with NO mean
+    removal, SVD, whiten = U diag(1/sqrt(clip(S))) U^T, a zero bias column appended.  Pinned by tests/golden/whiten.npz
+    (the script itself, run as process.sh:235-248 runs it)."""
+    x = np.asarray(x, dtype=np.float64)
+    cov = x.T @ x / (x.shape[0] - 1)
+    u, s, _ = np.linalg.svd(cov)
+    w = u @ np.diag(1.0 / np.sqrt(s.clip(regularization))) @ u.T
+    return np.concatenate([w, np.zeros((w.shape[0], 1))], axis=1)
+
+
+def lda_transform(x, spk, dim, total_covariance_factor=0.1, covariance_floor=1e-6):
+    """Kaldi ivector-compute-lda --dim --total-covariance-factor (process.sh:218-228), restated from Kaldi's published
+    source semantics -- PARITY UNPINNED (Kaldi absent): subtract the global mean; per speaker accumulate
+    tot += X^T X, between += n * avg avg^T; total = tot/N, within = total - between/N; T whitens
+    tcf*total + (1-tcf)*within (eigenvalues floored at floor * largest); eigenvectors of T between T^T, largest
+    first, top `dim`; A = U_part^T T; last column = -A mean.  Returns (dim, D+1)."""
+    x = np.asarray(x, dtype=np.float64)
+    mean = x.mean(axis=0)
+    xc = x - mean
+    d = x.shape[1]
+    tot, btw, n = np.zeros((d, d)), np.zeros((d, d)), 0
+    for s in np.unique(spk):
+        rows = xc[np.asarray(spk) == s]
+        tot += rows.T @ rows
+        avg = rows.mean(axis=0)
+        btw += rows.shape[0] * np.outer(avg, avg)
+        n += rows.shape[0]
+    total, between = tot / n, btw / n
+    within = total - between
+    s, u = np.linalg.eigh(total_covariance_factor * total + (1 - total_covariance_factor) * within)
+    s, u = s[::-1], u[:, ::-1]
+    s = np.maximum(s, covariance_floor * s[0])
+    t = np.diag(s ** -0.5) @ u.T
+    e, v = np.linalg.eigh(t @ between @ t.T)
+    order = np.argsort(-e, kind="stable")
+    a = v[:, order[:dim]].T @ t
+    return np.concatenate([a, -(a @ mean)[:, None]], axis=1)
+
+
+def pca_transform(x, dim=-1, normalize_variance=False, normalize_mean=True):
+    """Kaldi est-pca --read-vectors=true with its defaults (process.sh:250-260) -- PARITY UNPINNED: eigenvectors of the
+    centred covariance (divided by N), largest eigenvalue first, as rows; offset column = -P mean."""
+    x = np.asarray(x, dtype=np.float64)
+    mean = x.mean(axis=0)
+    cov = x.T @ x / x.shape[0] - np.outer(mean, mean)
+    s, p = np.linalg.eigh(cov)
+    order = np.argsort(-s, kind="stable")
+    k = x.shape[1] if dim < 0 else dim
+    a = p[:, order[:k]].T
+    if normalize_variance:
+        a = a / np.sqrt(s[order[:k]])[:, None]
+    return np.concatenate([a, -(a @ mean)[:, None]], axis=1) if normalize_mean else a
+
+
+def apply_affine(x, mat):
+    """ivector-transform (process.sh:205-216): A x, plus the last column as offset when mat is (., D+1)."""
+    x = np.asarray(x, dtype=np.float64)
+    d = x.shape[1]
+    return x @ mat[:, :d].T + (mat[:, d] if mat.shape[1] == d + 1 else 0.0)

@@ -102,6 +102,58 @@ def test_gpu_coral_adaptation_and_diagonalised_output(golden, tmp_path):
     assert txt.startswith("<Plda>  [ ") and txt.rstrip().endswith("</Plda>")
 
 
+def test_gpu_plda_adaptation_family_matches_reference_golden(golden, tmp_path):
+    """CORAL+ / LIP / LIP-reg / CIP / CIP-reg (score/pyplda/ivector-adapt-plda-*.py) against the reference's own classes
+    (tests/golden/make_golden_plda_adapt.py), through the classes and through the CLI twin."""
+    from asv_subtools_b200 import kaldi_io
+    from asv_subtools_b200.score import adapt_plda
+    from asv_subtools_b200.score.plda_train import Cip, CipReg, Coral, CoralPlus, Lip, LipReg, read_ori
+    g, ga = golden("plda_train"), golden("plda_adapt")
+
+    def write(path, m, w, b):
+        with open(path, "wb") as f:
+            kaldi_io.write_vec_flt(f, np.asarray(m).reshape(-1), key="mean")
+            kaldi_io.write_vec_flt(f, np.asarray(w).reshape(-1), key="within_var")
+            kaldi_io.write_vec_flt(f, np.asarray(b).reshape(-1), key="between_var")
+    p_out, p_in, p_vec = str(tmp_path / "out.ori"), str(tmp_path / "in.ori"), str(tmp_path / "adapt.ark")
+    write(p_out, g["d16_mean"], g["d16_within"], g["d16_between"])
+    write(p_in, ga["in_mean"], ga["in_within"], ga["in_between"])
+    adapt = opt.synthetic_adaptation_data(500, 16, 77)
+    with open(p_vec, "wb") as f:
+        for i, v in enumerate(adapt):
+            kaldi_io.write_vec_flt(f, v, key="a%04d" % i)
+
+    def coral(cls=Coral):
+        c = cls()
+        c.plda_read(p_out)
+        c.add_matrix(adapt)
+        c.update_plda()
+        return c
+    got = {"coralplus": coral(CoralPlus)}
+    for name, cls in (("lip", Lip), ("lipreg", LipReg)):
+        m = cls()
+        m.interpolation(p_out, p_in)
+        got[name] = m
+    m = Cip()
+    m.interpolation(coral(), p_in)
+    got["cip"] = m
+    m = CipReg()
+    m.plda_read(p_in)
+    m.interpolation(coral())
+    got["cipreg"] = m
+    for name, m in got.items():
+        assert rel(m.mean.reshape(-1), ga[name + "_mean"]) < 1e-6, name
+        tol = 1e-9 if name.startswith("lip") else 5e-5              # LIP*: pure float64; the rest carry the fp32-grade Gram product
+        assert rel(m.within_var, ga[name + "_within"]) < tol and rel(m.between_var, ga[name + "_between"]) < tol, name
+    for method, paths in (("coralplus", [p_out, p_vec]), ("lip-reg", [p_out, p_in]), ("cip-reg", [p_out, p_vec, p_in])):
+        dst = str(tmp_path / ("adapt_" + method))
+        adapt_plda.main(["--method", method] + paths + [dst])
+        _, w, b = read_ori(dst + ".ori")
+        key = method.replace("-", "")
+        assert rel(w, ga[key + "_within"]) < 5e-5 and rel(b, ga[key + "_between"]) < 5e-5, method
+        assert open(dst).read().startswith("<Plda>  [ ")
+
+
 def test_gpu_kaldi_style_plda_scoring(golden):
     """PLDA.transform_ivectors / log_likelihood_ratio_matrix|trials (Kaldi semantics) against the float64 oracle, and
     against the reference's own numbers where they coincide (its vectors are ours / sqrt(D), see the oracle)."""

@@ -179,6 +179,100 @@ def test_score_normalization_matches_reference_golden(ops, golden, tmp_path):
     assert np.max(np.abs(vals - g["sn_asnorm"]) / (1 + np.abs(g["sn_asnorm"]))) < 2e-5
 
 
+def test_kaldi_boundary_steps_match_egrecho_golden(ops, golden):
+    """SURVEY 8a row a12 on the GPU against the reference tree's own restatement (subtools2/egrecho/score, run
+    unmodified by tests/golden/make_golden_egrecho.py): column mean, speaker mean, submean + length-norm, per-trial
+    cosine (5-decimal score file), cohort top-n statistics with ddof = 0, AS-norm end to end."""
+    from asv_subtools_b200.score import normalization as norm
+    g = golden("egrecho_backend")
+    emb, mean = cuda(g["emb"]), g["mean"]
+    assert np.max(np.abs(ops.column_mean(emb).cpu().numpy() - mean)) < 1e-6
+    rows = [np.flatnonzero(g["cohort_spk"] == s) for s in range(g["cohort_mean"].shape[0])]
+    sm, cnt = ops.speaker_mean(cuda(g["cohort_utt"]), rows)
+    assert np.all(cnt == 5) and np.max(np.abs(sm.cpu().numpy() - g["cohort_mean"])) < 1e-6
+    x = ops.center_length_norm(emb, cuda(mean))
+    te, tt = cuda(g["trial_e"], np.int32), cuda(g["trial_t"], np.int32)
+    cos = ops.cosine_trials(x, x, te, tt).cpu().numpy()
+    assert np.max(np.abs(cos - g["cosine_5dp"])) < 6e-6
+    x0 = ops.center_length_norm(emb, None)
+    assert np.max(np.abs(ops.cosine_trials(x0, x0, te, tt).cpu().numpy() - g["cosine_nosub_5dp"])) < 6e-6
+    c = ops.center_length_norm(cuda(g["cohort_mean"]), cuda(mean))
+    top_n = int(g["top_n"])
+    ie, it = torch.from_numpy(g["stats_e_idx"].astype(np.int64)).cuda(), torch.from_numpy(g["stats_t_idx"].astype(np.int64)).cuda()
+    me, se = ops.topn_mean_std(ops.cosine_matrix(x[ie].contiguous(), c), top_n, ddof=0)
+    mt, st = ops.topn_mean_std(ops.cosine_matrix(x[it].contiguous(), c), top_n, ddof=0)
+    for got, want in ((me, g["e_mean"]), (se, g["e_std"]), (mt, g["t_mean"]), (st, g["t_std"])):
+        assert np.max(np.abs(got.cpu().numpy() - want)) < 2e-5      # bf16x3 cohort GEMM: ~1e-5 on a cosine
+    sc = cuda(g["cosine_5dp"].astype(np.float32))
+    out = norm.normalize(sc, te, tt, ops.cosine_matrix(x, c), ops.cosine_matrix(x, c), top_n, ddof=0).cpu().numpy()
+    assert np.max(np.abs(out - g["asnorm_5dp"]) / (1 + np.abs(g["asnorm_5dp"]))) < 2e-4   # scores / std ~ 10x amplification
+    got = norm.asnorm_embeddings(x, x, c, te, tt, top_n=top_n, ddof=0).cpu().numpy()
+    assert np.max(np.abs(got - g["asnorm_5dp"]) / (1 + np.abs(g["asnorm_5dp"]))) < 5e-4
+
+
+def test_process_steps_cli_matches_oracle_and_reference_whitening(ops, golden, tmp_path):
+    """score/process.sh twin (asv_subtools_b200.score.process) through files, step by step: getmean / submean / norm /
+    mean against the oracle, trainwhiten against the reference's own ZCA script (tests/golden/whiten.npz), trainlda /
+    trainpcawhiten against the oracle's restatement of the Kaldi binaries (rows compared up to sign), and the
+    affine `transform` with an output dimension that is not a multiple of 4."""
+    from asv_subtools_b200 import kaldi_io
+    from asv_subtools_b200.score import process as proc
+    emb, lab = osc.synthetic_speakers(40, 6, 16, 5, noise=0.9)
+    emb = (emb + 0.7).astype(np.float32)
+    keys = ["u%03d" % i for i in range(emb.shape[0])]
+    ark = str(tmp_path / "xv.ark")
+    with open(ark, "wb") as f:
+        for k, v in zip(keys, emb):
+            kaldi_io.write_vec_flt(f, v, key=k)
+    with open(tmp_path / "utt2spk", "w") as f:
+        for k, s in zip(keys, lab):
+            f.write("%s s%02d\n" % (k, s))
+    with open(tmp_path / "spk2utt", "w") as f:
+        for s in np.unique(lab):
+            f.write("s%02d %s\n" % (s, " ".join(k for k, l in zip(keys, lab) if l == s)))
+    P = lambda n: str(tmp_path / n)  # noqa: E731
+
+    def vecs(path):
+        d = dict(kaldi_io.read_vec_flt_ark(path))
+        return np.stack([d[k] for k in keys if k in d]) if keys[0] in d else d
+    proc.main(["getmean", ark, P("mean.vec")])
+    mean = kaldi_io.read_vec_flt(P("mean.vec"))
+    assert np.max(np.abs(mean - osc.global_mean(emb))) < 1e-6
+    proc.main(["submean", P("mean.vec"), ark, P("sub.ark")])
+    assert np.max(np.abs(vecs(P("sub.ark")) - osc.subtract_global_mean(emb, osc.global_mean(emb)))) < 1e-6
+    proc.main(["norm", P("sub.ark"), P("norm.ark")])
+    assert np.max(np.abs(vecs(P("norm.ark")) - osc.length_norm(osc.subtract_global_mean(emb, osc.global_mean(emb))))) < 1e-6
+    proc.main(["mean", P("spk2utt"), ark, P("spk.ark"), P("num_utts.ark")])
+    sm, cnt = osc.speaker_mean(emb, lab, 40)
+    got = vecs(P("spk.ark"))
+    assert np.max(np.abs(np.stack([got["s%02d" % s] for s in range(40)]) - sm)) < 1e-6
+    assert [l.split() for l in open(P("num_utts.ark"))] == [["s%02d" % s, str(int(c))] for s, c in enumerate(cnt)]
+
+    def same_rows_up_to_sign(a, b, tol):
+        d = a.shape[1] - 1
+        sign = np.sign(np.sum(a[:, :d] * b[:, :d], axis=1))[:, None]
+        return np.max(np.abs(a * sign - b)) / np.max(np.abs(b)) < tol
+    proc.main(["trainlda", "--dim", "6", ark, P("utt2spk"), P("lda.mat")])
+    lda = kaldi_io.read_mat(P("lda.mat"))
+    assert lda.shape == (6, 17) and same_rows_up_to_sign(lda.astype(np.float64), osc.lda_transform(emb, lab, 6), 2e-4)
+    proc.main(["lda", P("lda.mat"), ark, P("lda.ark")])
+    assert rel(vecs(P("lda.ark")), osc.apply_affine(emb, lda.astype(np.float64))) < 1e-4
+    proc.main(["trainpcawhiten", ark, P("pca.mat")])
+    assert same_rows_up_to_sign(kaldi_io.read_mat(P("pca.mat")).astype(np.float64), osc.pca_transform(emb), 2e-4)
+    g = golden("whiten")
+    zark = str(tmp_path / "z.ark")
+    with open(zark, "wb") as f:
+        for i, v in enumerate(g["emb"]):
+            kaldi_io.write_vec_flt(f, v, key="z%03d" % i)
+    proc.main(["trainwhiten", zark, P("zca.mat")])
+    zca = kaldi_io.read_mat(P("zca.mat"))
+    assert np.max(np.abs(zca - g["zca"])) / np.max(np.abs(g["zca"])) < 1e-4
+    proc.main(["whiten", P("zca.mat"), zark, P("zw.ark")])
+    zd = dict(kaldi_io.read_vec_flt_ark(P("zw.ark")))
+    zw = np.stack([zd["z%03d" % i] for i in range(g["emb"].shape[0])])
+    assert rel(zw, osc.apply_affine(g["emb"], g["zca"])) < 1e-4
+
+
 def test_asnorm_cross_select_matches_reference_golden(ops, golden, tmp_path):
     """--cross-select true: top-n (score, index) sort + per-trial gather statistics against the reference's pandas
     merge (tests/golden/make_golden_snorm_cross.py), a larger random case against the oracle, and the CLI."""

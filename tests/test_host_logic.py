@@ -240,3 +240,52 @@ def test_batcher_buckets_by_a_length_key_and_flushes_incrementally():
     assert out[0] == ["u0", "u1"] and out[1] == ["u2", "u3"]          # equal FRAME counts share a bucket
     assert sorted(k for bucket in out for k in bucket) == ["u%d" % i for i in range(7)]
     assert len(out) >= 4                                               # the pending cap flushed before the end
+
+
+def test_host_side_plda_interpolators_match_reference_golden(golden, tmp_path):
+    """LIP / LIP-reg are pure float64 host algebra (no adaptation vectors, no Gram product): checked here on the CPU
+    against the reference's own classes; the CORAL-based members of the family are GPU tests."""
+    from asv_subtools_b200 import kaldi_io
+    from asv_subtools_b200.score.plda_train import Lip, LipReg, _excess_over
+    from oracle import plda_train as opt
+    g, ga = golden("plda_train"), golden("plda_adapt")
+    paths = []
+    for name, (m, w, b) in (("out", (g["d16_mean"], g["d16_within"], g["d16_between"])),
+                            ("in", (ga["in_mean"], ga["in_within"], ga["in_between"]))):
+        p = str(tmp_path / (name + ".ori"))
+        with open(p, "wb") as f:
+            kaldi_io.write_vec_flt(f, m.reshape(-1), key="mean")
+            kaldi_io.write_vec_flt(f, w.reshape(-1), key="within_var")
+            kaldi_io.write_vec_flt(f, b.reshape(-1), key="between_var")
+        paths.append(p)
+    for key, cls in (("lip", Lip), ("lipreg", LipReg)):
+        m = cls()
+        m.interpolation(*paths)
+        for got, want in ((m.mean.reshape(-1), ga[key + "_mean"]), (m.within_var, ga[key + "_within"]), (m.between_var, ga[key + "_between"])):
+            assert np.max(np.abs(got - want)) / np.max(np.abs(want)) < 1e-9, key
+    x = _excess_over(ga["in_within"], g["d16_within"])
+    assert np.max(np.abs(x - opt.covariance_regulariser(ga["in_within"], g["d16_within"]))) < 1e-10 * np.max(np.abs(x))
+    assert np.min(np.linalg.eigvalsh(x)) > -1e-10            # a positive semi-definite excess
+
+
+def test_backend_transform_host_algebra_matches_oracle_and_reference(golden):
+    """The D x D float64 halves of trainlda / trainwhiten / trainpcawhiten (score/process.py) on statistics computed
+    in NumPy: ZCA against the reference script's matrix, LDA / PCA against the oracle (sign-free comparisons)."""
+    from asv_subtools_b200.score import process as proc
+    from oracle import scoring as osc
+    g = golden("whiten")
+    x = g["emb"].astype(np.float64)
+    assert np.max(np.abs(proc.zca_from_gram(x.T @ x, x.shape[0]) - g["zca"])) < 1e-6
+    emb, lab = osc.synthetic_speakers(40, 6, 16, 5, noise=0.9)
+    emb = emb.astype(np.float64) + 0.7
+    mean = emb.mean(0)
+    xc = emb - mean
+    total = xc.T @ xc / emb.shape[0]
+    means = np.stack([xc[lab == s].mean(0) for s in np.unique(lab)])
+    between = (means.T * np.bincount(lab)) @ means / emb.shape[0]
+    got, want = proc.lda_from_statistics(mean, total, between, 6), osc.lda_transform(emb, lab, 6)
+    sign = np.sign(np.sum(got[:, :16] * want[:, :16], axis=1))[:, None]
+    assert np.max(np.abs(got * sign - want)) < 1e-8
+    got, want = proc.pca_from_statistics(mean, total), osc.pca_transform(emb)
+    sign = np.sign(np.sum(got[:, :16] * want[:, :16], axis=1))[:, None]
+    assert np.max(np.abs(got * sign - want)) < 1e-8

@@ -139,6 +139,57 @@ def test_score_normalization(golden):
         assert np.max(np.abs(out - g["sn_" + method])) < 1e-9, method
 
 
+def test_kaldi_boundary_steps_match_the_reference_trees_own_restatement(golden):
+    """Row a12 (submean / norm / mean / cosine) and the ddof = 0 AS-norm against subtools2/egrecho/score run
+    unmodified (tests/golden/make_golden_egrecho.py).  The reference writes scores with 5 decimals."""
+    g = golden("egrecho_backend")
+    emb, mean = g["emb"], g["mean"]
+    assert np.max(np.abs(osc.global_mean(emb) - mean)) < 1e-7
+    sm, cnt = osc.speaker_mean(g["cohort_utt"], g["cohort_spk"], g["cohort_mean"].shape[0])
+    assert np.all(cnt == 5) and np.max(np.abs(sm - g["cohort_mean"])) < 1e-7
+    x = osc.length_norm(osc.subtract_global_mean(emb, mean))
+    cos = osc.cosine_trials(x, x, g["trial_e"], g["trial_t"])
+    assert np.max(np.abs(cos - g["cosine_5dp"])) < 5.5e-6
+    x0 = osc.length_norm(emb)
+    assert np.max(np.abs(osc.cosine_trials(x0, x0, g["trial_e"], g["trial_t"]) - g["cosine_nosub_5dp"])) < 5.5e-6
+    c = osc.length_norm(osc.subtract_global_mean(g["cohort_mean"], mean))
+    top_n = int(g["top_n"])
+    me, se = osc.snorm_stats(osc.cosine_matrix(x[g["stats_e_idx"]], c), top_n, ddof=0)
+    mt, st = osc.snorm_stats(osc.cosine_matrix(x[g["stats_t_idx"]], c), top_n, ddof=0)
+    for got, want in ((me, g["e_mean"]), (se, g["e_std"]), (mt, g["t_mean"]), (st, g["t_std"])):
+        assert np.max(np.abs(got - want)) < 1e-6
+    # end to end on the reference's 5-decimal cosine file, statistics indexed by utterance
+    me_all, se_all = osc.snorm_stats(osc.cosine_matrix(x, c), top_n, ddof=0)
+    out = osc.snorm_apply(g["cosine_5dp"], g["trial_e"], g["trial_t"], me_all, se_all, me_all, se_all)
+    assert np.max(np.abs(out - g["asnorm_5dp"])) < 1e-5              # 5 decimals written by the reference
+
+
+def test_zca_whitening_oracle_matches_reference_script(golden):
+    g = golden("whiten")
+    assert np.max(np.abs(osc.zca_whitening(g["emb"]) - g["zca"])) < 1e-6      # the script writes %f (6 decimals)
+
+
+def test_lda_and_pca_oracle_properties():
+    """Kaldi semantics (unpinned): the LDA output has unit tcf-mixed covariance and diagonal, descending between-class
+    covariance; PCA rows are orthonormal and decorrelate the data; both centre it."""
+    emb, lab = osc.synthetic_speakers(40, 6, 16, 5, noise=0.9)
+    emb = emb + 0.7
+    lda = osc.lda_transform(emb, lab, 6)
+    y = osc.apply_affine(emb, lda)
+    assert lda.shape == (6, 17) and np.max(np.abs(y.mean(0))) < 1e-9
+    means = np.stack([y[lab == s].mean(0) for s in np.unique(lab)])
+    btw = (means.T * np.bincount(lab)) @ means / y.shape[0]
+    tot = y.T @ y / y.shape[0]
+    mix = 0.1 * tot + 0.9 * (tot - btw)
+    assert np.max(np.abs(mix - np.eye(6))) < 1e-9
+    assert np.max(np.abs(btw - np.diag(np.diag(btw)))) < 1e-9 and np.all(np.diff(np.diag(btw)) <= 1e-12)
+    pca = osc.pca_transform(emb)
+    z = osc.apply_affine(emb, pca)
+    cov = z.T @ z / z.shape[0]
+    assert np.max(np.abs(pca[:, :16] @ pca[:, :16].T - np.eye(16))) < 1e-9
+    assert np.max(np.abs(cov - np.diag(np.diag(cov)))) < 1e-9 and np.all(np.diff(np.diag(cov)) <= 1e-12)
+
+
 def test_extended_xvector(golden):
     g = golden("xvector")
     sd = onn.make_state_dict(onn.extended_xvector_spec(80), 103)
@@ -224,6 +275,22 @@ def test_coral_adaptation_oracle_matches_reference(golden):
     g = golden("plda_train")
     m, w, b = opt.coral_adapt(g["d16_mean"], g["d16_within"], g["d16_between"], opt.synthetic_adaptation_data(500, 16, 77))
     assert rel(m, g["coral_mean"]) < 1e-10 and rel(w, g["coral_within"]) < 1e-9 and rel(b, g["coral_between"]) < 1e-9
+
+
+def test_plda_adaptation_family_oracle_matches_reference(golden):
+    """CORAL+ / LIP / LIP-reg / CIP / CIP-reg restatements against the reference's own classes
+    (tests/golden/make_golden_plda_adapt.py)."""
+    from oracle import plda_train as opt
+    g, ga = golden("plda_train"), golden("plda_adapt")
+    out_m = (g["d16_mean"], g["d16_within"], g["d16_between"])
+    in_m = (ga["in_mean"], ga["in_within"], ga["in_between"])
+    adapt = opt.synthetic_adaptation_data(500, 16, 77)
+    got = {"coralplus": opt.coralplus_adapt(*out_m, adapt), "lip": opt.lip_adapt(out_m, in_m),
+           "lipreg": opt.lipreg_adapt(out_m, in_m), "cip": opt.cip_adapt(out_m, in_m, adapt),
+           "cipreg": opt.cipreg_adapt(out_m, in_m, adapt)}
+    for name, (m, w, b) in got.items():
+        assert rel(m, ga[name + "_mean"]) < 1e-10, name
+        assert rel(w, ga[name + "_within"]) < 1e-8 and rel(b, ga[name + "_between"]) < 1e-8, name
 
 
 def test_score_normalization_cross_select(golden):
