@@ -117,6 +117,9 @@ def main(argv=None):
     ap.add_argument("--gpu-id", type=str, default="")
     ap.add_argument("--batch-size", type=int, default=256)
     ap.add_argument("--shard", type=str, default="0/1", help="i/n: keep utterances with index %% n == i")
+    ap.add_argument("--blueprint-dir", type=str, default="",
+                    help="take the blueprint of the same file name from this directory (asv_subtools_b200/model) instead of "
+                         "the path stored in nnet.config, so a reference model dir is used as it is")
     ap.add_argument("model_path", metavar="model-path")
     ap.add_argument("feats_rspecifier", metavar="feats-rspecifier")
     ap.add_argument("vectors_wspecifier", metavar="vectors-wspecifier")
@@ -129,6 +132,11 @@ def main(argv=None):
             blueprint, creation = args.model_blueprint, args.model_creation
         else:
             raise ValueError("Expected nnet_config or (model_blueprint, model_creation) to exist.")
+        if args.blueprint_dir:
+            swapped = os.path.join(args.blueprint_dir, os.path.basename(blueprint))
+            if not os.path.exists(swapped):
+                raise FileNotFoundError("no B200 blueprint named {} in {}".format(os.path.basename(blueprint), args.blueprint_dir))
+            blueprint = swapped
         if args.use_gpu != "true":
             raise RuntimeError("asv_subtools_b200 has no CPU path: run with --use-gpu true on a B200")
         model = create_model_from_py(blueprint, creation)

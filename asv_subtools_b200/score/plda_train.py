@@ -245,7 +245,9 @@ class Coral:
     def add_matrix(self, emb):
         self._emb = emb
 
-    def update_plda(self, device="cuda"):
+    def _adaptation_covariance(self, device="cuda"):
+        """(variance + mean_diff_scale * diff diff^T, data mean): the adaptation set's total covariance as one centred
+        Gram product on the GPU (E[x x^T] - E[x] E[x]^T without the cancellation)."""
         x = getattr(self, "_emb", None)
         if x is None:
             x = torch.from_numpy(np.stack(self._rows))
@@ -255,12 +257,14 @@ class Coral:
         mean_d = ops.column_mean(x)
         zero = torch.zeros(n, dtype=torch.int32, device=device)
         ct = ops.center_rows_transposed(x, zero, mean_d.view(1, -1).contiguous())
-        variance = ops.matmul_nt(ct, ct).double().cpu().numpy() / n          # E[x x^T] - E[x] E[x]^T without the cancellation
+        variance = ops.matmul_nt(ct, ct).double().cpu().numpy() / n
         variance = 0.5 * (variance + variance.T)
         mean = mean_d.double().cpu().numpy().reshape(-1, 1)
         diff = mean - self.mean
-        variance += self.mean_diff_scale * (diff @ diff.T)
-        self.mean = mean
+        return variance + self.mean_diff_scale * (diff @ diff.T), mean
+
+    def update_plda(self, device="cuda"):
+        variance, self.mean = self._adaptation_covariance(device)
         eo, qo = np.linalg.eigh(self.within_var + self.between_var)
         ei, qi = np.linalg.eigh(variance)
         c_o = qo @ np.diag(1.0 / np.sqrt(eo)) @ qo.T
@@ -369,3 +373,31 @@ class CipReg(_Adapter):
         a = self.interpolation_weight
         self.within_var = self.within_var + a * _excess_over(self.within_var, coral.within_var)
         self.between_var = self.between_var + a * _excess_over(self.between_var, coral.between_var)
+
+
+class PldaUnsupervisedAdaptor(Coral):
+    """Kaldi's ivector-adapt-plda as the reference restates it (score/pyplda/plda_base.py PldaUnsupervisedAdaptor
+    :344-485; the `trainaplda` step of score/process.sh:280-292): in the space where the model's total covariance is the
+    identity, each direction in which the adaptation data's covariance exceeds 1 hands that excess to the within- and
+    between-class covariances in the proportions within_covar_scale / between_covar_scale.  add_stats / add_matrix and the
+    adaptation-set covariance (one Gram product on the GPU) are Coral's; update_plda(plda) rewrites plda.mean / transform /
+    psi / offset in place (psi descending, like PLDA.get_output) and returns the adapted (within, between)."""
+
+    def __init__(self, mean_diff_scale=1.0, within_covar_scale=0.3, between_covar_scale=0.7):
+        super().__init__(mean_diff_scale, within_covar_scale, between_covar_scale)
+
+    def update_plda(self, plda, device="cuda"):
+        self.mean = np.asarray(plda.mean, dtype=np.float64).reshape(-1, 1)
+        variance, mean = self._adaptation_covariance(device)
+        psi = np.asarray(plda.psi, dtype=np.float64)
+        tm = np.asarray(plda.transform, dtype=np.float64) / np.sqrt(1.0 + psi)[:, None]      # total covariance -> I
+        s, p = np.linalg.eigh(tm @ variance @ tm.T)
+        excess = np.maximum(s - 1.0, 0.0)
+        w2 = p.T @ (p / (1.0 + psi)[:, None]) + np.diag(self.within_covar_scale * excess)
+        b2 = p.T @ (p * (psi / (1.0 + psi))[:, None]) + np.diag(self.between_covar_scale * excess)
+        back = np.linalg.inv(p.T @ tm)
+        self.within_var, self.between_var = back @ w2 @ back.T, back @ b2 @ back.T
+        self.mean = mean
+        new = PLDA(mean, self.within_var, self.between_var)
+        plda.mean, plda.transform, plda.psi, plda.offset = new.mean, new.transform, new.psi, new.offset
+        return self.within_var, self.between_var

@@ -170,6 +170,30 @@ def cipreg_adapt(out_model, in_model, adapt, weight=0.5):
             in_model[2] + weight * covariance_regulariser(in_model[2], s_b))
 
 
+def unsupervised_adapt(mean, within, between, adapt, within_scale=0.3, between_scale=0.7, mean_diff_scale=1.0):
+    """PldaUnsupervisedAdaptor.update_plda, plda_base.py:368-485 (the reference's restatement of Kaldi's
+    ivector-adapt-plda): in the space where the model's total covariance is I, every direction in which the adaptation
+    data's covariance exceeds 1 hands its excess to the within / between covariances in the given proportions.
+    Returns (mean, within, between) of the adapted model in the original space."""
+    x = np.asarray(adapt, dtype=np.float64)
+    m = x.mean(axis=0).reshape(-1, 1)
+    var = x.T @ x / x.shape[0] - m @ m.T
+    d = m - np.asarray(mean, dtype=np.float64).reshape(-1, 1)
+    var = var + mean_diff_scale * (d @ d.T)
+    c_inv = np.linalg.inv(np.linalg.cholesky(within))
+    psi, u = np.linalg.eigh(c_inv @ between @ c_inv.T)
+    t = u.T @ c_inv                                             # within -> I, between -> diag(psi)
+    tm = t / np.sqrt(1.0 + psi)[:, None]                        # total -> I
+    s, p = np.linalg.eigh(tm @ var @ tm.T)
+    w2 = p.T @ np.diag(1.0 / (1.0 + psi)) @ p
+    b2 = p.T @ np.diag(psi / (1.0 + psi)) @ p
+    excess = np.maximum(s - 1.0, 0.0)
+    w2 = w2 + np.diag(within_scale * excess)
+    b2 = b2 + np.diag(between_scale * excess)
+    back = np.linalg.inv(p.T @ tm)
+    return m.reshape(-1), back @ w2 @ back.T, back @ b2 @ back.T
+
+
 # ---------------------------------------------------------------- Kaldi-style PLDA scoring (plda_base.py PLDA)
 def plda_transform(x, transform, offset, psi, num_examples=1, normalize_length=True, simple_length_norm=False,
                    reference_dim_quirk=False):

@@ -7,6 +7,8 @@
   ivector-adapt-plda-lip-reg.py    LIPReg.interpolation           (:26-49)
   ivector-adapt-plda-cip.py        CORAL.update_plda + CIP.interpolation      (:38-77, :113-121)
   ivector-adapt-plda-cip-reg.py    CORAL.update_plda + CIPReg.interpolation   (:109-128)
+  plda_base.py                     PldaUnsupervisedAdaptor.update_plda        (:344-485; Kaldi's ivector-adapt-plda,
+                                   the `trainaplda` step of score/process.sh:280-292)
 
 Out-of-domain model = the d16 model of plda_train.npz (reference PldaEstimation, 10 EM iterations); in-domain model =
 the reference's PldaEstimation on a second seeded set; adaptation vectors = oracle.plda_train.synthetic_adaptation_data.
@@ -98,6 +100,22 @@ def main():
         cr.plda_read(p_in)
         cr.interpolation(coral)
         out.update(cipreg_mean=cr.mean.reshape(-1), cipreg_within=cr.within_var, cipreg_between=cr.between_var)
+    # Kaldi's ivector-adapt-plda as restated by the reference itself: plda_base.PldaUnsupervisedAdaptor (:344-485);
+    # stored as the adapted covariances reconstructed from (transform, psi): eigenvector order / sign free
+    for tag, (ws, bs) in (("default", (0.3, 0.7)), ("scoresets", (0.70, 0.30))):
+        p = pb.PLDA()
+        p.mean, p.dim = out_mean.reshape(-1, 1).copy(), 16
+        p.within_var, p.between_var = out_w.copy(), out_b.copy()
+        p.get_output()
+        ad = pb.PldaUnsupervisedAdaptor(mean_diff_scale=1.0, within_covar_scale=ws, between_covar_scale=bs)
+        for v in adapt:
+            ad.add_stats(1, v.astype(np.float64))
+        ad.update_plda(p)
+        tinv = np.linalg.inv(np.real(p.transform))
+        out["unsup_%s_mean" % tag] = np.asarray(p.mean).reshape(-1)
+        out["unsup_%s_within" % tag] = tinv @ tinv.T
+        out["unsup_%s_between" % tag] = tinv @ np.diag(np.real(p.psi)) @ tinv.T
+        out["unsup_%s_psi_sorted" % tag] = np.sort(np.real(p.psi))[::-1]
     np.savez_compressed(os.path.join(HERE, "plda_adapt.npz"), **out)
     print("plda_adapt.npz ok", sorted(out))
 

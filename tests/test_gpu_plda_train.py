@@ -145,6 +145,20 @@ def test_gpu_plda_adaptation_family_matches_reference_golden(golden, tmp_path):
         assert rel(m.mean.reshape(-1), ga[name + "_mean"]) < 1e-6, name
         tol = 1e-9 if name.startswith("lip") else 5e-5              # LIP*: pure float64; the rest carry the fp32-grade Gram product
         assert rel(m.within_var, ga[name + "_within"]) < tol and rel(m.between_var, ga[name + "_between"]) < tol, name
+    from asv_subtools_b200.score.plda_train import PLDA, PldaUnsupervisedAdaptor
+    for tag, (ws, bs) in (("default", (0.3, 0.7)), ("scoresets", (0.70, 0.30))):
+        p = PLDA(g["d16_mean"], g["d16_within"], g["d16_between"])
+        ad = PldaUnsupervisedAdaptor(1.0, ws, bs)
+        for v in adapt:
+            ad.add_stats(1, v)
+        w, b = ad.update_plda(p)
+        assert rel(w, ga["unsup_%s_within" % tag]) < 5e-5 and rel(b, ga["unsup_%s_between" % tag]) < 5e-5, tag
+        assert rel(p.psi, ga["unsup_%s_psi_sorted" % tag]) < 5e-4 and rel(p.mean.reshape(-1), ga["unsup_%s_mean" % tag]) < 1e-6
+        tinv = np.linalg.inv(p.transform)
+        assert rel(tinv @ tinv.T, w) < 1e-9                        # the rewritten transform diagonalises the adapted model
+    dst = str(tmp_path / "adapt_kaldi")
+    adapt_plda.main(["--method", "kaldi", "--within-covar-scale", "0.70", "--between-covar-scale", "0.30", p_out, p_vec, dst])
+    assert rel(read_ori(dst + ".ori")[1], ga["unsup_scoresets_within"]) < 5e-5
     for method, paths in (("coralplus", [p_out, p_vec]), ("lip-reg", [p_out, p_in]), ("cip-reg", [p_out, p_vec, p_in])):
         dst = str(tmp_path / ("adapt_" + method))
         adapt_plda.main(["--method", method] + paths + [dst])

@@ -291,6 +291,10 @@ def test_plda_adaptation_family_oracle_matches_reference(golden):
     for name, (m, w, b) in got.items():
         assert rel(m, ga[name + "_mean"]) < 1e-10, name
         assert rel(w, ga[name + "_within"]) < 1e-8 and rel(b, ga[name + "_between"]) < 1e-8, name
+    for tag, (ws, bs) in (("default", (0.3, 0.7)), ("scoresets", (0.70, 0.30))):
+        m, w, b = opt.unsupervised_adapt(*out_m, adapt, ws, bs)
+        assert rel(m, ga["unsup_%s_mean" % tag]) < 1e-10
+        assert rel(w, ga["unsup_%s_within" % tag]) < 1e-8 and rel(b, ga["unsup_%s_between" % tag]) < 1e-8, tag
 
 
 def test_score_normalization_cross_select(golden):
