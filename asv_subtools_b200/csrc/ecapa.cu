@@ -216,9 +216,122 @@ attn_stats_pool_kernel(const float* __restrict__ logits, long long ldl, const fl
   }
 }
 
+// ---------------------------------------------------------------- attention pooling with a head map
+// The single-/multi-head attention poolings of libs/nnet/pooling.py (:322-587) differ only in WHICH logit weights
+// WHICH channel: output channel o in [0, O) pools input channel c = o % C with the softmax over time of logit
+// g = o / gdiv.  AttentiveStatisticsPooling: gdiv = C (one shared alpha); MultiHeadAttentionPooling share=True:
+// gdiv = C / num_head, share=False: gdiv = 1; Global / MultiResolution multi-head: O = num_head * C, gdiv = C
+// (share) or 1.  One streaming pass, online softmax; per-frame loads of x are 16-byte, logits are scalar
+// (broadcast within the warp when heads are wide).  unweighted_var = 1: std of `stddev_attention=False`
+// (:357-359): mean_T((x - mean)^2) around the attention-weighted mean.
+struct OnlineU {
+  float m, s0, s1, s2, u1, u2;
+};
+
+__global__ void __launch_bounds__(kApWarps * 32)
+attn_head_stats_pool_kernel(const float* __restrict__ logits, long long ldl, const float* __restrict__ x, long long ldx,
+                            int T, int C, int O, int gdiv, float floor_, int unweighted_var, float* __restrict__ out,
+                            __nv_bfloat16* __restrict__ oh, __nv_bfloat16* __restrict__ ol, long long ldo) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int o = blockIdx.x * 128 + lane * 4;
+  const bool active = o < O;   // O % 4 == 0, C % 4 == 0: the four outputs read four consecutive input channels
+  OnlineU st[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) st[k] = {-INFINITY, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (active) {
+    const int c = o % C;
+    int g[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g[k] = (o + k) / gdiv;
+    const float* lb = logits + (long long)b * T * ldl;
+    const float* xb = x + (long long)b * T * ldx + c;
+    for (int t = warp; t < T; t += kApWarps) {
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(xb + (long long)t * ldx));
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+      const float* lr = lb + (long long)t * ldl;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float l = __ldg(lr + g[k]);
+        OnlineU& s = st[k];
+        const float mn = fmaxf(s.m, l);
+        const float sc = expf(s.m - mn), e = expf(l - mn);
+        s.s0 = fmaf(s.s0, sc, e);
+        s.s1 = fmaf(s.s1, sc, e * xs[k]);
+        s.s2 = fmaf(s.s2, sc, e * xs[k] * xs[k]);
+        s.m = mn;
+        s.u1 += xs[k];
+        s.u2 = fmaf(xs[k], xs[k], s.u2);
+      }
+    }
+  }
+  __shared__ OnlineU sh[kApWarps][32][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sh[warp][lane][k] = st[k];
+  __syncthreads();
+  if (warp == 0 && active) {
+    float mu[4], sd[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      OnlineU a = sh[0][lane][k];
+      for (int w = 1; w < kApWarps; ++w) {
+        const OnlineU& q = sh[w][lane][k];
+        if (q.s0 > 0.f) {
+          const float mn = fmaxf(a.m, q.m);
+          const float sa = expf(a.m - mn), sb = expf(q.m - mn);
+          a.s0 = a.s0 * sa + q.s0 * sb;
+          a.s1 = a.s1 * sa + q.s1 * sb;
+          a.s2 = a.s2 * sa + q.s2 * sb;
+          a.m = mn;
+          a.u1 += q.u1;
+          a.u2 += q.u2;
+        }
+      }
+      mu[k] = a.s1 / a.s0;
+      const float var = unweighted_var ? (a.u2 - 2.f * mu[k] * a.u1) / (float)T + mu[k] * mu[k]
+                                       : a.s2 / a.s0 - mu[k] * mu[k];
+      sd[k] = sqrtf(fmaxf(var, floor_));
+    }
+    float* ob = out + (long long)b * 2 * O;
+    *reinterpret_cast<float4*>(ob + o) = make_float4(mu[0], mu[1], mu[2], mu[3]);
+    *reinterpret_cast<float4*>(ob + O + o) = make_float4(sd[0], sd[1], sd[2], sd[3]);
+    if (oh) {
+      __nv_bfloat16 h[8], l[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { split_bf16(mu[k], h[k], l[k]); split_bf16(sd[k], h[4 + k], l[4 + k]); }
+      __nv_bfloat16* ph = oh + (long long)b * ldo;
+      __nv_bfloat16* pl = ol + (long long)b * ldo;
+      *reinterpret_cast<uint2*>(ph + o) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+      *reinterpret_cast<uint2*>(pl + o) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+      *reinterpret_cast<uint2*>(ph + O + o) = make_uint2(pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+      *reinterpret_cast<uint2*>(pl + O + o) = make_uint2(pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+    }
+  }
+}
+
 }  // namespace xvb
 
 using namespace xvb;
+
+extern "C" int xvb_attn_head_stats_pool(const float* logits, int64_t ldl, int G, const float* x, int64_t ldx, int B, int T,
+                                        int C, int O, int gdiv, float floor_, int unweighted_var, float* out,
+                                        uint16_t* out_hi, uint16_t* out_lo, int64_t ldo, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  XVB_CHECK_ARG(logits && x && out, "xvb_attn_head_stats_pool: null pointer");
+  XVB_CHECK_ARG(B > 0 && T > 0 && C > 0 && C % 4 == 0 && O > 0 && O % C == 0 && ldx % 4 == 0 && ldx >= C && B <= 65535,
+                "xvb_attn_head_stats_pool: need C%%4==0, O a multiple of C, ldx%%4==0");
+  XVB_CHECK_ARG(gdiv > 0 && G > 0 && ldl >= G && (O - 1) / gdiv < G,
+                "xvb_attn_head_stats_pool: the head map o / gdiv must stay inside the %d logits", G);
+  XVB_CHECK_ARG((out_hi != nullptr) == (out_lo != nullptr), "xvb_attn_head_stats_pool: out_hi/out_lo must both be set or both NULL");
+  if (out_hi) XVB_CHECK_ARG(ldo % 4 == 0 && ldo >= 2 * (int64_t)O, "xvb_attn_head_stats_pool: ldo too small / unaligned");
+  dim3 grid((O + 127) / 128, B);
+  attn_head_stats_pool_kernel<<<grid, kApWarps * 32, 0, (cudaStream_t)stream>>>(
+      logits, ldl, x, ldx, T, C, O, gdiv, floor_, unweighted_var, out, reinterpret_cast<__nv_bfloat16*>(out_hi),
+      reinterpret_cast<__nv_bfloat16*>(out_lo), ldo);
+  XVB_LAUNCH_CHECK();
+  return XVB_OK;
+}
 
 extern "C" int xvb_plane_mean(const uint16_t* x_hi, const uint16_t* x_lo, int64_t ldx, int B, int T, int C, float* out,
                               uint16_t* out_hi, uint16_t* out_lo, int64_t ldo, void* stream) {

@@ -1,9 +1,10 @@
 # -*- coding:utf-8 -*-
 """Snowdar x-vector blueprint for the B200 path -- drop-in for pytorch/model/snowdar_xvector.py (Xvector.init
 :15-152, extract_embedding :262-294) in its TDNN configurations: standard or `extend=True` stack,
-`tdnn_layer_params` (default BatchNorm affine=False, momentum 0.5), statistics pooling, positions
+`tdnn_layer_params` (default BatchNorm affine=False, momentum 0.5), pooling = statistics | attentive | multi-head |
+multi-resolution (pooling.py:15-76, :322-440, :518-587; the blueprint's switch :119-136), positions
 far / near_affine / near.  Same constructor keywords and state_dict keys.  The options that add other
-operators (SE blocks, skip connection, attentive / multi-head / LDE pooling) raise NotImplementedError;
+operators (SE blocks, skip connection, LDE / xi-vector pooling) raise NotImplementedError;
 training-only keywords (mixup, specaugment, dropouts, margin loss, step params) are accepted and ignored,
 as the launchers rewrite the creation string with training=False for extraction."""
 import os
@@ -11,8 +12,9 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
-from asv_subtools_b200.nnet import (ReluBatchNormTdnnLayer, StatisticsPooling,  # noqa: E402
-                                    TopVirtualNnet, build_tdnn_extractor)
+from asv_subtools_b200.nnet import (AttentionPoolingExtractor, AttentiveStatisticsPooling,  # noqa: E402
+                                    MultiHeadAttentionPooling, MultiResolutionMultiHeadAttentionPooling,
+                                    ReluBatchNormTdnnLayer, StatisticsPooling, TopVirtualNnet, build_tdnn_extractor)
 
 
 class Xvector(TopVirtualNnet):
@@ -25,8 +27,9 @@ class Xvector(TopVirtualNnet):
              step_params={}, transfer_from="softmax_loss", training=True, extracted_embedding="far"):
         if SE or skip_connection:
             raise NotImplementedError("SE blocks / skip connection are not on the B200 path")
-        if pooling != "statistics":
-            raise NotImplementedError("pooling={!r}: only statistics pooling is on the B200 path".format(pooling))
+        if pooling not in ("statistics", "attentive", "multi-head", "multi-resolution"):
+            raise NotImplementedError("pooling={!r}: statistics / attentive / multi-head / multi-resolution are on the B200 "
+                                      "path".format(pooling))
         if not tdnn6:
             raise NotImplementedError("tdnn6=False is not on the B200 path")
         layer = {"nonlinearity": "relu", "nonlinearity_params": {"inplace": True}, "bn-relu": False, "bn": True,
@@ -36,8 +39,11 @@ class Xvector(TopVirtualNnet):
         last.update(tdnn7_params)
         if last.get("nonlinearity") == "default":
             last["nonlinearity"] = layer["nonlinearity"]
-        num_nodes = dict(pooling_params).get("num_nodes", 1500)
-        if not dict(pooling_params).get("stddev", True):
+        pool = {"num_nodes": 1500, "num_head": 1, "share": True, "affine_layers": 1, "hidden_size": 64, "context": [0],
+                "stddev": True, "temperature": False, "fixed": True}                                      # :44-55
+        pool.update(pooling_params)
+        num_nodes = pool.pop("num_nodes")
+        if not pool.pop("stddev"):
             raise NotImplementedError("stddev=False is not on the B200 path")
         self.inputs_dim = inputs_dim
         self.extracted_embedding = extracted_embedding
@@ -52,7 +58,15 @@ class Xvector(TopVirtualNnet):
         self.ex_tdnn5 = L(512, 512, **layer) if extend else None
         self.tdnn4 = L(512, 512, **layer)
         self.tdnn5 = L(512, num_nodes, **layer)
-        self.stats = StatisticsPooling(num_nodes, stddev=True)
+        if pooling == "attentive":                                                                          # :123-126
+            self.stats = AttentiveStatisticsPooling(num_nodes, affine_layers=pool["affine_layers"],
+                                                    hidden_size=pool["hidden_size"], context=pool["context"], stddev=True)
+        elif pooling == "multi-head":                                                                       # :127-128
+            self.stats = MultiHeadAttentionPooling(num_nodes, stddev=True, **pool)
+        elif pooling == "multi-resolution":                                                                 # :129-130
+            self.stats = MultiResolutionMultiHeadAttentionPooling(num_nodes, **pool)
+        else:
+            self.stats = StatisticsPooling(num_nodes, stddev=True)
         self.tdnn6 = L(self.stats.get_output_dim(), 512, **layer)
         self.tdnn7 = L(512, 512, **last)
         self.transform_keys = ["tdnn1", "tdnn2", "tdnn3", "tdnn4", "tdnn5", "stats", "tdnn6", "tdnn7", "ex_tdnn1",
@@ -64,8 +78,10 @@ class Xvector(TopVirtualNnet):
         pos = {"far": "far", "near_affine": "near_affine", "near": "near_full"}.get(self.extracted_embedding)
         if pos is None:
             raise TypeError("Expected far or near position, but got {}".format(self.extracted_embedding))
-        return build_tdnn_extractor(self, self.inputs_dim, [l for l in order if l is not None], self.stats, self.tdnn6,
-                                    self.tdnn7, pos)
+        layers = [l for l in order if l is not None]
+        if not isinstance(self.stats, StatisticsPooling):
+            return AttentionPoolingExtractor(self, self.inputs_dim, layers, self.stats, self.tdnn6, self.tdnn7, pos)
+        return build_tdnn_extractor(self, self.inputs_dim, layers, self.stats, self.tdnn6, self.tdnn7, pos)
 
 
 if __name__ == "__main__":

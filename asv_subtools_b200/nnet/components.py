@@ -7,9 +7,10 @@ import torch
 
 class TdnnAffine(torch.nn.Module):
     """y = splice(w * x, context) + b.  Same constructor contract as the reference
-    (components.py:30-97): `weight` is (output_dim, input_dim, tot_context) *including* the taps
-    that `context` skips; only stride=1, groups=1, pad=True, no weight/feature normalisation is
-    supported on the B200 path (the two target blueprints use nothing else)."""
+    (components.py:30-97): `weight` is (output_dim, input_dim // groups, tot_context) *including* the taps
+    that `context` skips; stride=1, pad=True, no weight/feature normalisation on the B200 path.  `groups` > 1
+    (the multi-head attention poolings, pooling.py:262-298) keeps the reference's parameter shape; `dense_weight()`
+    expands it to the block-diagonal (output_dim, input_dim, tot_context) form the GEMM kernel packs."""
 
     def __init__(self, input_dim, output_dim, context=[0], bias=True, pad=True, stride=1, groups=1,
                  norm_w=False, norm_f=False):
@@ -17,21 +18,36 @@ class TdnnAffine(torch.nn.Module):
         for i in range(len(context) - 1):
             if context[i] >= context[i + 1]:
                 raise ValueError("Context tuple {} is invalid, such as the order.".format(context))
-        if stride != 1 or groups != 1 or not pad or norm_w or norm_f:
-            raise NotImplementedError("B200 TdnnAffine supports stride=1, groups=1, pad=True, norm_w/f=False only")
-        self.input_dim, self.output_dim, self.context = input_dim, output_dim, list(context)
+        if stride != 1 or not pad or norm_w or norm_f:
+            raise NotImplementedError("B200 TdnnAffine supports stride=1, pad=True, norm_w/f=False only")
+        if input_dim % groups != 0 or output_dim % groups != 0:
+            raise ValueError("input_dim {} and output_dim {} must be divisible by groups {}".format(input_dim, output_dim, groups))
+        self.input_dim, self.output_dim, self.context, self.groups = input_dim, output_dim, list(context), groups
         self.bool_bias = bias
         self.left_context = context[0] if context[0] < 0 else 0
         self.right_context = context[-1] if context[-1] > 0 else 0
         self.tot_context = self.right_context - self.left_context + 1
-        self.weight = torch.nn.Parameter(torch.empty(output_dim, input_dim, self.tot_context))
+        self.weight = torch.nn.Parameter(torch.empty(output_dim, input_dim // groups, self.tot_context))
         self.bias = torch.nn.Parameter(torch.empty(output_dim)) if bias else None
         torch.nn.init.normal_(self.weight, 0.0, 0.01)  # components.py:99-104
         if self.bias is not None:
             torch.nn.init.constant_(self.bias, 0.0)
 
     def extra_repr(self):
-        return "{}, {}, context={}, bias={}".format(self.input_dim, self.output_dim, self.context, self.bool_bias)
+        return "{}, {}, context={}, bias={}, groups={}".format(self.input_dim, self.output_dim, self.context, self.bool_bias,
+                                                               self.groups)
+
+    def dense_weight(self):
+        """(output_dim, input_dim, tot_context) fp32: the stored weight, or its block-diagonal expansion for groups > 1
+        (group g maps input channels [g*Cin/G, (g+1)*Cin/G) to output channels [g*Cout/G, (g+1)*Cout/G), conv1d's rule)."""
+        w = self.weight.detach().float()
+        if self.groups == 1:
+            return w
+        g, ci, co = self.groups, self.input_dim // self.groups, self.output_dim // self.groups
+        dense = torch.zeros(self.output_dim, self.input_dim, self.tot_context, dtype=torch.float32, device=w.device)
+        for k in range(g):
+            dense[k * co:(k + 1) * co, k * ci:(k + 1) * ci] = w[k * co:(k + 1) * co]
+        return dense
 
 
 class ReluBatchNormTdnnLayer(torch.nn.Module):

@@ -196,3 +196,112 @@ def build_tdnn_extractor(model, inputs_dim, frame_layers, stats, tdnn6, tdnn7, e
             ex.add_segment_layer(w7, b7)
     ex.finalize(pooling_eps=stats.eps)
     return ex
+
+
+class _PackedAffine:
+    """One TdnnAffine (+ optional ReLU / folded eval-BatchNorm) packed for the tcgen05 layer kernel on `device`:
+    block-diagonal expansion for groups > 1, output rows zero-padded to a multiple of `pad_to`, `row_scale` folded into
+    weight and bias (per-head temperature of the attention logits)."""
+
+    def __init__(self, affine, device, bn=None, relu=False, pad_to=8, row_scale=None):
+        from .. import ops
+        from .components import fold_batchnorm
+        w = affine.dense_weight().to(device)
+        b = affine.bias.detach().float().to(device) if affine.bias is not None else None
+        if row_scale is not None:
+            w = w * row_scale.to(device).view(-1, 1, 1)
+            b = b * row_scale.to(device) if b is not None else None
+        self.cout_real = w.shape[0]
+        pad = (-w.shape[0]) % pad_to
+        if pad:
+            w = torch.cat([w, torch.zeros(pad, w.shape[1], w.shape[2], device=device)], 0)
+            b = torch.cat([b, torch.zeros(pad, device=device)], 0) if b is not None else None
+        self.context, self.cout = list(affine.context), w.shape[0]
+        self.w = ops.pack_tdnn_weight(w.contiguous(), self.context)
+        self.bias = b.contiguous() if b is not None else None
+        scale, shift = fold_batchnorm(bn)
+        if scale is not None and pad:                            # padded output channels come out as exact zeros
+            scale, shift = np.concatenate([scale, np.zeros(pad, np.float32)]), np.concatenate([shift, np.zeros(pad, np.float32)])
+        self.scale = torch.from_numpy(scale).to(device) if scale is not None else None
+        self.shift = torch.from_numpy(shift).to(device) if shift is not None else None
+        self.relu = relu
+
+    def run(self, x, **kw):
+        from .. import ops
+        ops.tdnn_affine_ex(x, self.w, self.cout, self.context, bias=self.bias, bn_scale=self.scale, bn_shift=self.shift,
+                           relu=self.relu, **kw)
+
+    def planes(self, b, t, device):
+        """(buffer to write, view of the real channels for the next layer)."""
+        from .. import ops
+        y = ops.SplitPlanes.empty((b, t, self.cout), device)
+        return y, (y if self.cout == self.cout_real else y.slice(0, self.cout_real))
+
+
+class AttentionPoolingExtractor:
+    """Launch sequence of a TDNN x-vector whose pooling is one of the attention poolings (nnet/pooling.py): frame layers
+    on the tcgen05 layer kernel (the last one also writes fp32, the pooling kernel's x), the attention affines as
+    GEMMs (grouped weights expanded block-diagonally, temperature folded into the last affine, logits fp32), softmax over
+    time + weighted mean / std in one pass (`xvb_attn_head_stats_pool`), then the segment layers on T = 1."""
+
+    def __init__(self, model, inputs_dim, frame_layers, stats, tdnn6, tdnn7, position):
+        dev = model.device_for_extraction()
+        self.feat_dim = inputs_dim
+        self.frames = [_PackedAffine(l.affine, dev, l.batchnorm, l.relu) for l in frame_layers]
+        att = stats.attention
+        self.first = _PackedAffine(att.first_affine, dev, relu=True) if att.relu_affine else None
+        temps = att.head_temperatures()
+        row_scale = None
+        if temps is not None:                                    # logits of head h are divided by t_h (pooling.py:314-316)
+            row_scale = (1.0 / temps).repeat_interleave(att.final_dim)
+        self.last = _PackedAffine(att.last_affine, dev, row_scale=row_scale)
+        self.channels, self.pooled, self.gdiv = stats.input_dim, stats.pooled_channels(), stats.logit_divisor()
+        self.eps, self.unweighted = stats.eps, not stats.stddev_attention
+        if position == "far":
+            self.segment = [_PackedAffine(tdnn6.affine, dev)]
+        else:
+            self.segment = [_PackedAffine(tdnn6.affine, dev, tdnn6.batchnorm, tdnn6.relu)]
+            if position == "near_full":
+                self.segment.append(_PackedAffine(tdnn7.affine, dev, tdnn7.batchnorm, tdnn7.relu))
+            else:
+                self.segment.append(_PackedAffine(tdnn7.affine, dev))
+        self.embed_dim = self.segment[-1].cout_real
+        self.last_launches = 0
+
+    def extract(self, feats):
+        from .. import ops
+        if feats.shape[2] != self.feat_dim:
+            raise ValueError("expected feature dim {}, got {}".format(self.feat_dim, feats.shape[2]))
+        B, T, _ = feats.shape
+        dev, P = feats.device, ops.SplitPlanes
+        x = ops.split_f32(feats, ld=(self.feat_dim + 7) // 8 * 8)
+        for layer in self.frames[:-1]:
+            y, view = layer.planes(B, T, dev)
+            layer.run(x, y=y)
+            x = view
+        top = self.frames[-1]
+        y, xp = top.planes(B, T, dev)
+        xf = torch.empty(B, T, top.cout, dtype=torch.float32, device=dev)
+        top.run(x, y=y, y_f32=xf)
+        h = xp
+        if self.first is not None:
+            y, h = self.first.planes(B, T, dev)
+            self.first.run(xp, y=y)
+        logits = torch.empty(B, T, self.last.cout, dtype=torch.float32, device=dev)
+        self.last.run(h, y_f32=logits)
+        _, stats = ops.attn_head_stats_pool(logits[..., :self.last.cout_real], xf[..., :top.cout_real], self.pooled, self.gdiv,
+                                            floor=self.eps, unweighted_var=self.unweighted, planes=True)
+        x = stats
+        for i, layer in enumerate(self.segment):
+            if i + 1 == len(self.segment):
+                emb = torch.empty(B, 1, layer.cout, dtype=torch.float32, device=dev)
+                layer.run(x, y_f32=emb)
+            else:
+                y, view = layer.planes(B, 1, dev)
+                layer.run(x, y=y)
+                x = view
+        self.last_launches = len(self.frames) + (2 if self.first is not None else 1) + 2 + len(self.segment)
+        return emb.view(B, -1)[:, :self.embed_dim]
+
+    def close(self):
+        pass

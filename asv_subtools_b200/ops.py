@@ -213,6 +213,23 @@ def attn_stats_pool(logits, x, floor=1e-5, planes=False):
     return (out, op) if planes else out
 
 
+def attn_head_stats_pool(logits, x, out_channels, gdiv, floor=1e-10, unweighted_var=False, planes=False):
+    """Attention pooling with a head map (xvb_attn_head_stats_pool): logits (B,T,G) fp32 (any row pitch >= G), x (B,T,C)
+    fp32; output channel o pools x[..., o % C] with softmax_T(logits[..., o // gdiv]).  -> (B, 2*out_channels)."""
+    for name, v in (("logits", logits), ("x", x)):       # channel-slice views of wider buffers are fine: rows stay contiguous
+        if v.dtype != torch.float32 or not v.is_cuda or v.dim() != 3 or v.stride(-1) != 1 or v.stride(0) != v.shape[1] * v.stride(1):
+            raise TypeError("{} must be a (B,T,*) CUDA float32 tensor with contiguous rows".format(name))
+    b, t, c = x.shape
+    g = logits.shape[-1]
+    out = torch.empty(b, 2 * out_channels, dtype=torch.float32, device=x.device)
+    op = SplitPlanes.empty((b, 1, 2 * out_channels), x.device) if planes else None
+    check(lib.xvb_attn_head_stats_pool(_ptr(logits), logits.stride(-2), g, _ptr(x), x.stride(-2), b, t, c, out_channels, int(gdiv),
+                                       floor, 1 if unweighted_var else 0, _ptr(out), op.hi.data_ptr() if op else None,
+                                       op.lo.data_ptr() if op else None, 2 * out_channels, _stream()),
+          "xvb_attn_head_stats_pool")
+    return (out, op) if planes else out
+
+
 def tdnn_affine_simt(x, weight, context, bias=None, bn_scale=None, bn_shift=None, relu=False):
     """fp32 CUDA-core cross-check: x (B,T,Cin) fp32, weight (Cout,Cin,tot) as in the reference."""
     x = _req(x, torch.float32, "x")

@@ -197,6 +197,16 @@ int xvb_se_apply(const uint16_t* z_hi, const uint16_t* z_lo, int64_t ldz, const 
 int xvb_attn_stats_pool(const float* logits, int64_t ldl, const float* x, int64_t ldx, int B, int T, int C, float floor_,
                         float* out, uint16_t* out_hi, uint16_t* out_lo, int64_t ldo, void* stream);
 
+/* The attention poolings of libs/nnet/pooling.py with shared / per-head weights: AttentiveStatisticsPooling
+ * (:322-368), MultiHeadAttentionPooling (:371-440), Global / MultiResolution multi-head (:443-587).  logits
+ * (B,T,G) fp32 are the output of AttentionAlphaComponent's last affine (:300-319; temperature folded into its
+ * weights); output channel o in [0,O) pools input channel o % C of x (B,T,C) with alpha = softmax_T(logits[:,:,o/gdiv]):
+ * mean = sum alpha x, std = sqrt(max(sum alpha x^2 - mean^2, floor)) (unweighted_var = 1: the `stddev_attention=False`
+ * branch, mean_T((x-mean)^2)).  out (B,2O) = [mean | std], optionally also as split planes. */
+int xvb_attn_head_stats_pool(const float* logits, int64_t ldl, int G, const float* x, int64_t ldx, int B, int T, int C,
+                             int O, int gdiv, float floor_, int unweighted_var, float* out, uint16_t* out_hi,
+                             uint16_t* out_lo, int64_t ldo, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Feature-side front-end on a ragged batch: utterance u owns rows
  * offsets[u] .. offsets[u+1] of the (sum_T, F) fp32 matrix x.

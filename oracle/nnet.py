@@ -32,12 +32,12 @@ def context_span(context):
     return left, right, right - left + 1
 
 
-def tdnn_affine(x, weight, bias, context):
+def tdnn_affine(x, weight, bias, context, groups=1):
     """TdnnAffine.forward, pytorch/libs/nnet/components.py:107-149.
 
-    x (B, Cin, T); weight (Cout, Cin, tot_context) *including* the masked taps; zero pad
+    x (B, Cin, T); weight (Cout, Cin / groups, tot_context) *including* the masked taps; zero pad
     (-left, right) (:117); taps not in ``context`` are multiplied by 0 (:133-138); dense
-    conv1d, stride 1 (:147)."""
+    conv1d, stride 1 (:147), `groups` as given to the constructor (:68-76)."""
     left, right, tot = context_span(context)
     assert weight.shape[2] == tot, (weight.shape, context)
     x = F.pad(x, (-left, right), mode="constant", value=0.0)
@@ -45,7 +45,7 @@ def tdnn_affine(x, weight, bias, context):
         mask = torch.tensor([[[1.0 if i in context else 0.0 for i in range(left, right + 1)]]],
                             dtype=weight.dtype)
         weight = weight * mask
-    return F.conv1d(x, weight, bias, stride=1, padding=0, dilation=1, groups=1)
+    return F.conv1d(x, weight, bias, stride=1, padding=0, dilation=1, groups=groups)
 
 
 def batchnorm_eval(x, sd, prefix):
@@ -150,12 +150,90 @@ def snowdar_layers(extend):
             ("ex_tdnn3", [0]), ("ex_tdnn4", [-4, 0, 4]), ("ex_tdnn5", [0]), ("tdnn4", [0]), ("tdnn5", [0])]
 
 
-def snowdar_xvector_forward(sd, x, extracted_embedding="far", extend=False):
+ATTENTION_DEFAULTS = {"num_head": 1, "share": True, "affine_layers": 1, "hidden_size": 64, "context": [0],
+                      "temperature": False, "fixed": True}            # snowdar_xvector.py:44-55
+
+
+def attention_layout(input_dim, num_head=1, split_input=True, share=True, affine_layers=2, hidden_size=64, bias=True):
+    """Shapes / groups of AttentionAlphaComponent's affines, pooling.py:262-298:
+    -> (first (cin, cout, groups) | None, last (cin, cout, groups), final_dim)."""
+    final_dim = 1 if share else (input_dim // num_head if split_input else input_dim)
+    first_groups = last_groups = 1
+    if affine_layers == 1:
+        last_in = input_dim
+        if num_head > 1 and split_input:
+            last_groups = num_head
+        first = None
+    else:
+        last_in = hidden_size * num_head
+        if num_head > 1:
+            last_groups = num_head
+            if split_input:
+                first_groups = num_head
+        first = (input_dim, last_in, first_groups)
+    return first, (last_in, final_dim * num_head, last_groups), final_dim
+
+
+def attention_alpha(x, sd, prefix, input_dim, num_head=1, split_input=True, share=True, affine_layers=2, hidden_size=64,
+                    context=(0,), bias=True, temperature=False, fixed=True):
+    """AttentionAlphaComponent.forward, pooling.py:300-319: alpha (B, final_dim * num_head, T) = softmax over T of
+    last_affine(relu(first_affine(x))), per-head temperature t (fixed: max(1, (i // 2) * 5), :245-249; learnt:
+    1 + t^2, :311-312) dividing the logits."""
+    first, last, _ = attention_layout(input_dim, num_head, split_input, share, affine_layers, hidden_size, bias)
+    context = list(context)
+    if first is not None:
+        x = F.relu(tdnn_affine(x, sd[prefix + ".first_affine.weight"], sd.get(prefix + ".first_affine.bias"), context, first[2]))
+    logits = tdnn_affine(x, sd[prefix + ".last_affine.weight"], sd.get(prefix + ".last_affine.bias"), context, last[2])
+    if num_head > 1 and temperature:
+        b, _, t = logits.shape
+        temp = sd[prefix + ".t"].float() if fixed else 1 + sd[prefix + ".t"] ** 2
+        logits = (logits.reshape(b, num_head, -1, t) / temp).reshape(b, -1, t)
+    return torch.softmax(logits, dim=2)
+
+
+def attention_pooling(x, alpha, num_head, global_heads, stddev_attention=True, eps=1.0e-10):
+    """The shared tail of AttentiveStatisticsPooling (:347-362), MultiHeadAttentionPooling (:407-437) and the Global /
+    MultiResolution variants (:482-512, :553-583): alpha reshaped to (B, head, -1, T) weights x reshaped to
+    (B, head, -1, T) (split heads) or (B, 1, -1, T) (global heads); mean = sum_T alpha x; std =
+    sqrt(clamp(sum_T alpha x^2 - mean^2, eps)) or, without stddev_attention, sqrt(clamp(mean_T (x - mean)^2, eps))."""
+    b, c, t = x.shape
+    a = alpha.reshape(b, num_head, -1, t)
+    xs = x.reshape(b, 1, -1, t) if global_heads else x.reshape(b, num_head, -1, t)
+    mean = torch.sum((a * xs).reshape(b, -1, t), dim=2, keepdim=True)
+    if stddev_attention:
+        var = torch.sum((a * xs ** 2).reshape(b, -1, t), dim=2, keepdim=True) - mean ** 2
+    else:
+        var = torch.mean((x - mean) ** 2, dim=2, keepdim=True)
+    return torch.cat((mean, torch.sqrt(var.clamp(min=eps))), dim=1)
+
+
+def snowdar_pooling(x, sd, pooling, params, num_nodes):
+    """Xvector.init's pooling switch, snowdar_xvector.py:119-136, for statistics / attentive / multi-head /
+    multi-resolution."""
+    if pooling == "statistics":
+        return statistics_pooling(x)
+    p = dict(ATTENTION_DEFAULTS)
+    p.update(params)
+    if pooling == "attentive":       # :124-126 -> AttentiveStatisticsPooling(:327-337): one head, shared weight, bias
+        alpha = attention_alpha(x, sd, "stats.attention", num_nodes, 1, True, True, p["affine_layers"], p["hidden_size"], p["context"])
+        return attention_pooling(x, alpha, 1, False)
+    if pooling == "multi-head":      # :127-128 -> MultiHeadAttentionPooling(:377-396): split input, no bias
+        alpha = attention_alpha(x, sd, "stats.attention", num_nodes, p["num_head"], True, p["share"], p["affine_layers"],
+                                p["hidden_size"], p["context"], False, p["temperature"], p["fixed"])
+        return attention_pooling(x, alpha, p["num_head"], False)
+    if pooling == "multi-resolution":  # :129-130 -> MultiResolutionMultiHeadAttentionPooling(:520-545): global heads, temperature
+        alpha = attention_alpha(x, sd, "stats.attention", num_nodes, p["num_head"], False, p["share"], p["affine_layers"],
+                                p["hidden_size"], p["context"], True, True, p["fixed"])
+        return attention_pooling(x, alpha, p["num_head"], True)
+    raise ValueError(pooling)
+
+
+def snowdar_xvector_forward(sd, x, extracted_embedding="far", extend=False, pooling="statistics", pooling_params=None):
     """snowdar_xvector.py:262-294: far = tdnn6.affine; near_affine = tdnn6 -> tdnn7.affine; near = tdnn6 -> tdnn7
     (the whole layer, ReLU and BatchNorm included)."""
     for name, ctx in snowdar_layers(extend):
         x = relu_bn_tdnn_layer(x, sd, name, ctx)
-    x = statistics_pooling(x)
+    x = snowdar_pooling(x, sd, pooling, pooling_params or {}, x.shape[1])
     if extracted_embedding == "far":
         return tdnn_affine(x, sd["tdnn6.affine.weight"], sd["tdnn6.affine.bias"], [0])
     x = relu_bn_tdnn_layer(x, sd, "tdnn6", [0])
@@ -164,7 +242,36 @@ def snowdar_xvector_forward(sd, x, extracted_embedding="far", extend=False):
     return relu_bn_tdnn_layer(x, sd, "tdnn7", [0])
 
 
-def snowdar_xvector_spec(inputs_dim, extend=False, bn_affine=False):
+def snowdar_pooling_spec(pooling, params, num_nodes=1500):
+    """(state_dict entries of `stats`, output dim) for the attention poolings (registration order: [t], first_affine,
+    last_affine -- pooling.py:245-298)."""
+    if pooling == "statistics":
+        return [], 2 * num_nodes
+    p = dict(ATTENTION_DEFAULTS)
+    p.update(params)
+    if pooling == "attentive":
+        heads, split, share, bias, temp = 1, True, True, True, False
+    elif pooling == "multi-head":
+        heads, split, share, bias, temp = p["num_head"], True, p["share"], False, p["temperature"]
+    else:
+        heads, split, share, bias, temp = p["num_head"], False, p["share"], True, True
+    first, last, _ = attention_layout(num_nodes, heads, split, share, p["affine_layers"], p["hidden_size"], bias)
+    _, _, tot = context_span(p["context"])
+    spec = []
+    if heads > 1 and temp:       # buffer of fixed temperatures max(1, (i // 2) * 5) (:245-249) or the learnt parameter (:253)
+        spec.append(("stats.attention.t", (1, heads, 1, 1), ("temp_fixed" if p["fixed"] else "b", 0)))
+    for name, lay in (("first_affine", first), ("last_affine", last)):
+        if lay is None:
+            continue
+        cin, cout, groups = lay
+        spec.append(("stats.attention.{}.weight".format(name), (cout, cin // groups, tot), ("w", cin // groups * len(p["context"]))))
+        if bias:
+            spec.append(("stats.attention.{}.bias".format(name), (cout,), ("b", 0)))
+    out_dim = 2 * num_nodes * (heads if pooling == "multi-resolution" else 1)
+    return spec, out_dim
+
+
+def snowdar_xvector_spec(inputs_dim, extend=False, bn_affine=False, pooling="statistics", pooling_params=None):
     """Keys/shapes of snowdar Xvector(inputs_dim, N, extend=..., training=False).state_dict() in registration
     order (:104-152): tdnn1, [ex_tdnn1], tdnn2, [ex_tdnn2], tdnn3, [ex_tdnn3, ex_tdnn4, ex_tdnn5], tdnn4, tdnn5,
     tdnn6, tdnn7; default tdnn_layer_params have BatchNorm affine=False (:45-48)."""
@@ -172,9 +279,13 @@ def snowdar_xvector_spec(inputs_dim, extend=False, bn_affine=False):
           [("tdnn2", 512, 512, [-2, 0, 2])] + ([("ex_tdnn2", 512, 512, [0])] if extend else []) + \
           [("tdnn3", 512, 512, [-3, 0, 3])] + \
           ([("ex_tdnn3", 512, 512, [0]), ("ex_tdnn4", 512, 512, [-4, 0, 4]), ("ex_tdnn5", 512, 512, [0])] if extend else []) + \
-          [("tdnn4", 512, 512, [0]), ("tdnn5", 512, 1500, [0]), ("tdnn6", 3000, 512, [0]), ("tdnn7", 512, 512, [0])]
+          [("tdnn4", 512, 512, [0]), ("tdnn5", 512, 1500, [0])]
+    pool_spec, stats_dim = snowdar_pooling_spec(pooling, pooling_params or {})
     spec = []
     for name, cin, cout, ctx in reg:
+        spec += _affine_entries(name, cin, cout, ctx) + _bn_entries(name + ".batchnorm", cout, affine=bn_affine)
+    spec += pool_spec
+    for name, cin, cout, ctx in [("tdnn6", stats_dim, 512, [0]), ("tdnn7", 512, 512, [0])]:
         spec += _affine_entries(name, cin, cout, ctx) + _bn_entries(name + ".batchnorm", cout, affine=bn_affine)
     return spec
 
@@ -416,6 +527,9 @@ def make_state_dict(spec, seed):
             v = rng.uniform(0.5, 1.5, shape).astype(np.float32)
         elif kind == "nbt":
             sd[key] = torch.tensor(1000, dtype=torch.long)
+            continue
+        elif kind == "temp_fixed":
+            sd[key] = torch.tensor([[[[max(1, (i // 2) * 5)]] for i in range(shape[1])]])
             continue
         else:
             raise ValueError(kind)

@@ -16,6 +16,14 @@ sys.path.insert(0, ROOT)
 from oracle import nnet as onn  # noqa: E402
 
 CASES = {"std": dict(extend=False, seed=301), "ext": dict(extend=True, seed=302)}
+# attention poolings of libs/nnet/pooling.py behind the blueprint's `pooling` switch (snowdar_xvector.py:119-136)
+POOLING_CASES = {
+    "attn1": ("attentive", {}, 311),                                                  # snowdar default: one affine
+    "attn2": ("attentive", {"affine_layers": 2, "hidden_size": 64}, 312),
+    "mha_share": ("multi-head", {"num_head": 4}, 313),                                # the paper's form: shared weights
+    "mha_full": ("multi-head", {"num_head": 4, "share": False, "affine_layers": 2}, 314),
+    "mres": ("multi-resolution", {"num_head": 4, "temperature": True, "affine_layers": 2}, 315),
+}
 
 
 def main():
@@ -37,6 +45,16 @@ def main():
             model.eval()
             emb = np.stack([model.extract_embedding(feats[i]).numpy() for i in range(3)])
             out["{}_{}".format(cname, pos)] = emb
+    for cname, (pooling, pp, seed) in POOLING_CASES.items():
+        sd = onn.make_state_dict(onn.snowdar_xvector_spec(40, pooling=pooling, pooling_params=pp), seed)
+        feats = onn.synthetic_feats(3, 120, 40, seed + 1000)
+        for pos in ("far", "near"):
+            model = utils.create_model_from_py(
+                "/root/reference/pytorch/model/snowdar_xvector.py",
+                'Xvector(40,10,training=False,extracted_embedding="{}",pooling="{}",pooling_params={!r})'.format(pos, pooling, pp))
+            model.load_state_dict(sd, strict=True)
+            model.eval()
+            out["{}_{}".format(cname, pos)] = np.stack([model.extract_embedding(feats[i]).numpy() for i in range(3)])
     np.savez_compressed(os.path.join(HERE, "snowdar.npz"), **out)
     print("snowdar.npz ok", {k: v.shape for k, v in out.items()})
 

@@ -359,6 +359,61 @@ def test_snowdar_xvector_matches_reference_golden(golden, cname, extend, seed):
         Xvector(40, 10, SE=True)
 
 
+SNOWDAR_POOLING_CASES = {
+    "attn1": ("attentive", {}, 311),
+    "attn2": ("attentive", {"affine_layers": 2, "hidden_size": 64}, 312),
+    "mha_share": ("multi-head", {"num_head": 4}, 313),
+    "mha_full": ("multi-head", {"num_head": 4, "share": False, "affine_layers": 2}, 314),
+    "mres": ("multi-resolution", {"num_head": 4, "temperature": True, "affine_layers": 2}, 315),
+}
+
+
+@pytest.mark.parametrize("cname", sorted(SNOWDAR_POOLING_CASES))
+def test_snowdar_attention_poolings_match_reference_golden(golden, cname):
+    """pooling = attentive / multi-head / multi-resolution of the snowdar blueprint (libs/nnet/pooling.py:214-587 behind
+    snowdar_xvector.py:119-136) against the reference's own outputs: grouped attention affines, shared and per-channel
+    alphas, head boundaries that are not multiples of four channels (1500 / 4 = 375), per-head temperature."""
+    from asv_subtools_b200.model.snowdar_xvector import Xvector
+    pooling, pp, seed = SNOWDAR_POOLING_CASES[cname]
+    g = golden("snowdar")
+    sd = onn.make_state_dict(onn.snowdar_xvector_spec(40, pooling=pooling, pooling_params=pp), seed)
+    feats = onn.synthetic_feats(3, 120, 40, seed + 1000)
+    for pos in ("far", "near"):
+        m = Xvector(40, 10, training=False, extracted_embedding=pos, pooling=pooling, pooling_params=pp)
+        m.load_state_dict(sd, strict=True)
+        m.cuda().eval()
+        want = g["{}_{}".format(cname, pos)]
+        assert rel(m.extract_embedding_batch(feats).cpu().numpy(), want) < EMB_TOL, (cname, pos)
+        assert rel(m.extract_embedding(feats[1]).numpy(), want[1]) < EMB_TOL, (cname, pos)
+    with pytest.raises(NotImplementedError):
+        Xvector(40, 10, pooling="lde")
+
+
+@pytest.mark.parametrize("heads,gdiv_kind,global_heads,unweighted", [(1, "share", False, False), (4, "share", False, True),
+                                                                     (4, "full", False, False), (3, "share", True, False),
+                                                                     (2, "full", True, True)])
+def test_attn_head_stats_pool_kernel_vs_oracle(heads, gdiv_kind, global_heads, unweighted):
+    """xvb_attn_head_stats_pool against oracle.attention_pooling for every head map, both std branches, strided inputs."""
+    from asv_subtools_b200 import ops
+    rng = np.random.RandomState(11)
+    B, T, C = 3, 77, 24 * heads if not global_heads else 20
+    x = rng.standard_normal((B, T, C)).astype(np.float32) * 1.5 + 0.3
+    pooled = C * heads if global_heads else C
+    G = heads if gdiv_kind == "share" else pooled
+    logits = rng.standard_normal((B, T, G)).astype(np.float32) * 2.0
+    gdiv = 1 if gdiv_kind == "full" else (C if global_heads else C // heads)
+    xw = torch.zeros(B, T, C + 4, device="cuda")
+    xw[..., :C] = torch.from_numpy(x).cuda()
+    lw = torch.zeros(B, T, (G + 7) // 8 * 8, device="cuda")
+    lw[..., :G] = torch.from_numpy(logits).cuda()
+    got, planes = ops.attn_head_stats_pool(lw[..., :G], xw[..., :C], pooled, gdiv, unweighted_var=unweighted, planes=True)
+    alpha = torch.softmax(torch.from_numpy(logits).transpose(1, 2), dim=2)              # (B, G, T)
+    ref = onn.attention_pooling(torch.from_numpy(x).transpose(1, 2), alpha, heads, global_heads,
+                                stddev_attention=not unweighted).squeeze(2).numpy()
+    assert got.shape == ref.shape and rel(got.cpu().numpy(), ref) < 2e-6
+    assert rel(planes.float().view(B, -1).cpu().numpy(), ref) < 1e-5
+
+
 @pytest.mark.parametrize("pos", ["far", "near"])
 def test_factored_xvector_matches_reference_golden(golden, pos):
     """model/factored_xvector.py (F-TDNN blocks, skip concatenations, bypass) against the reference blueprint's own

@@ -270,6 +270,28 @@ def test_snowdar_xvector_oracle_matches_reference(golden):
             assert rel(emb, g["{}_{}".format(cname, pos)]) < RTOL, (cname, pos)
 
 
+SNOWDAR_POOLING_CASES = {
+    "attn1": ("attentive", {}, 311),
+    "attn2": ("attentive", {"affine_layers": 2, "hidden_size": 64}, 312),
+    "mha_share": ("multi-head", {"num_head": 4}, 313),
+    "mha_full": ("multi-head", {"num_head": 4, "share": False, "affine_layers": 2}, 314),
+    "mres": ("multi-resolution", {"num_head": 4, "temperature": True, "affine_layers": 2}, 315),
+}
+
+
+def test_snowdar_attention_poolings_oracle_matches_reference(golden):
+    """AttentiveStatisticsPooling / MultiHeadAttentionPooling / MultiResolutionMultiHeadAttentionPooling behind the
+    snowdar blueprint's `pooling` switch (pooling.py:214-587, snowdar_xvector.py:119-136)."""
+    g = golden("snowdar")
+    for cname, (pooling, pp, seed) in SNOWDAR_POOLING_CASES.items():
+        sd = onn.make_state_dict(onn.snowdar_xvector_spec(40, pooling=pooling, pooling_params=pp), seed)
+        feats = onn.synthetic_feats(3, 120, 40, seed + 1000)
+        for pos in ("far", "near"):
+            fwd = lambda x: onn.snowdar_xvector_forward(sd, x, pos, pooling=pooling, pooling_params=pp)  # noqa: E731
+            emb = np.stack([onn.extract_embedding(fwd, feats[i]).numpy() for i in range(3)])
+            assert rel(emb, g["{}_{}".format(cname, pos)]) < RTOL, (cname, pos)
+
+
 def test_coral_adaptation_oracle_matches_reference(golden):
     from oracle import plda_train as opt
     g = golden("plda_train")
