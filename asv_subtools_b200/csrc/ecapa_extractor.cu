@@ -86,6 +86,13 @@ struct xvb_ecapa {
   // layer1 as an im2col view over time-padded planes (see extractor.cu): consecutive taps, feat_dim % 16 == 0
   bool im2col_first = false;
   int pad_front = 0, pad_back = 0;
+  // two-lane shard pipeline (see extractor.cu): `lane1` shares the weights, owns its workspace; batches alternate
+  // between the lanes on two streams so that one batch's bandwidth kernels (plane mean, SE apply, the two pooling
+  // passes, staging) run next to the other batch's GEMM CTAs
+  xvb_ecapa* lane1 = nullptr;
+  bool is_lane = false;
+  cudaStream_t lane_stream[2] = {nullptr, nullptr};
+  cudaEvent_t ev_lane_start = nullptr, ev_lane_done[2] = {nullptr, nullptr};
 
   void free_ws() {
     for (void* p : ws) cudaFree(p);
@@ -370,9 +377,69 @@ extern "C" int xvb_ecapa_extract_host(xvb_ecapa_t* h, const float* feats_host, i
 // A whole shard of N equal-length utterances in `batch`-utterance batches (the reference's caller loop,
 // extract_embeddings.py:73-83), device-resident / through pinned host buffers with the copies overlapped
 // (same protocol as xvb_extractor_extract_shard[_host]).
+static bool ecapa_lanes_enabled() {
+  static const int knob = getenv("XVB_LANES") ? atoi(getenv("XVB_LANES")) : 1;
+  return knob != 0;
+}
+
+static int ecapa_ensure_lanes(xvb_ecapa* h) {
+  if (h->lane1) return XVB_OK;
+  for (int i = 0; i < 2; ++i) {
+    XVB_CUDA(cudaStreamCreateWithFlags(&h->lane_stream[i], cudaStreamNonBlocking));
+    XVB_CUDA(cudaEventCreateWithFlags(&h->ev_lane_done[i], cudaEventDisableTiming));
+  }
+  XVB_CUDA(cudaEventCreateWithFlags(&h->ev_lane_start, cudaEventDisableTiming));
+  xvb_ecapa* c = new xvb_ecapa();
+  c->feat_dim = h->feat_dim; c->ldf = h->ldf; c->C = h->C; c->D = h->D; c->H = h->H; c->E = h->E; c->scale = h->scale;
+  c->se_dim = h->se_dim; c->finalized = true;
+  for (int b = 0; b < 3; ++b) {
+    c->dilation[b] = h->dilation[b];
+    c->res_w_hi[b] = h->res_w_hi[b]; c->res_w_lo[b] = h->res_w_lo[b]; c->res_bias[b] = h->res_bias[b];
+    c->res_scale[b] = h->res_scale[b]; c->res_shift[b] = h->res_shift[b];
+  }
+  for (const auto& kv : h->layers) {            // device pointers + shapes only: the twin never saves, so no host copies
+    ELayer L;
+    L.Cin = kv.second.Cin; L.Cout = kv.second.Cout; L.ntaps = kv.second.ntaps; L.flags = kv.second.flags; L.tot = kv.second.tot;
+    for (int i = 0; i < XVB_MAX_TAPS; ++i) L.ctx[i] = kv.second.ctx[i];
+    L.w_hi = kv.second.w_hi; L.w_lo = kv.second.w_lo; L.bias = kv.second.bias; L.scale = kv.second.scale; L.shift = kv.second.shift;
+    c->layers[kv.first] = L;
+  }
+  c->im2col_first = h->im2col_first; c->pad_front = h->pad_front; c->pad_back = h->pad_back;
+  c->is_lane = true;
+  h->lane1 = c;
+  return XVB_OK;
+}
+static int ecapa_lanes_fork(xvb_ecapa* h, cudaStream_t s) {
+  XVB_CUDA(cudaEventRecord(h->ev_lane_start, s));
+  for (int i = 0; i < 2; ++i) XVB_CUDA(cudaStreamWaitEvent(h->lane_stream[i], h->ev_lane_start, 0));
+  return XVB_OK;
+}
+static int ecapa_lanes_join(xvb_ecapa* h, cudaStream_t s) {
+  for (int i = 0; i < 2; ++i) {
+    XVB_CUDA(cudaEventRecord(h->ev_lane_done[i], h->lane_stream[i]));
+    XVB_CUDA(cudaStreamWaitEvent(s, h->ev_lane_done[i], 0));
+  }
+  return XVB_OK;
+}
+
 extern "C" int xvb_ecapa_extract_shard(xvb_ecapa_t* h, const float* feats, int64_t N, int T, int batch, float* emb, void* stream) {
   XVB_CHECK_ARG(h && h->finalized && feats && emb && N > 0 && T > 0 && batch > 0, "xvb_ecapa_extract_shard: bad arguments");
   int launches = 0;
+  if (ecapa_lanes_enabled() && N > batch) {
+    int rc = ecapa_ensure_lanes(h);
+    if (rc) return rc;
+    if ((rc = ecapa_lanes_fork(h, (cudaStream_t)stream))) return rc;
+    int k = 0;
+    for (int64_t i = 0; i < N; i += batch, ++k) {
+      const int b = (int)(N - i < batch ? N - i : batch);
+      xvb_ecapa* lane = (k & 1) ? h->lane1 : h;
+      if ((rc = xvb_ecapa_extract(lane, feats + (size_t)i * T * h->feat_dim, b, T, emb + (size_t)i * h->E, h->lane_stream[k & 1]))) return rc;
+      launches += lane->last_launches;
+    }
+    if ((rc = ecapa_lanes_join(h, (cudaStream_t)stream))) return rc;
+    h->last_launches = launches;
+    return XVB_OK;
+  }
   for (int64_t i = 0; i < N; i += batch) {
     const int b = (int)(N - i < batch ? N - i : batch);
     int rc = xvb_ecapa_extract(h, feats + (size_t)i * T * h->feat_dim, b, T, emb + (size_t)i * h->E, stream);
@@ -409,20 +476,28 @@ extern "C" int xvb_ecapa_extract_shard_host(xvb_ecapa_t* h, const float* feats_h
       h->p_emb_cap[slot] = ne;
     }
   }
+  const bool lanes = ecapa_lanes_enabled() && N > batch;
+  if (lanes) {
+    if ((rc = ecapa_ensure_lanes(h))) return rc;
+    if ((rc = ecapa_lanes_fork(h, s))) return rc;
+  }
   int launches = 0, k = 0;
   for (int64_t i = 0; i < N; i += batch, ++k) {
     const int b = (int)(N - i < batch ? N - i : batch);
     const int slot = k & 1;
+    xvb_ecapa* lane = (lanes && slot) ? h->lane1 : h;
+    cudaStream_t ls = lanes ? h->lane_stream[slot] : s;
     if (k >= 2) XVB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[slot], 0));
     XVB_CUDA(cudaMemcpyAsync(h->p_feats[slot], feats_host + (size_t)i * T * h->feat_dim, (size_t)b * T * h->feat_dim * sizeof(float),
                              cudaMemcpyHostToDevice, h->copy_stream));
     XVB_CUDA(cudaEventRecord(h->ev_h2d[slot], h->copy_stream));
-    XVB_CUDA(cudaStreamWaitEvent(s, h->ev_h2d[slot], 0));
-    if ((rc = xvb_ecapa_extract(h, h->p_feats[slot], b, T, h->p_emb[slot], stream))) return rc;
-    XVB_CUDA(cudaMemcpyAsync(emb_host + (size_t)i * h->E, h->p_emb[slot], (size_t)b * h->E * sizeof(float), cudaMemcpyDeviceToHost, s));
-    XVB_CUDA(cudaEventRecord(h->ev_done[slot], s));
-    launches += h->last_launches;
+    XVB_CUDA(cudaStreamWaitEvent(ls, h->ev_h2d[slot], 0));
+    if ((rc = xvb_ecapa_extract(lane, h->p_feats[slot], b, T, h->p_emb[slot], ls))) return rc;
+    XVB_CUDA(cudaMemcpyAsync(emb_host + (size_t)i * h->E, h->p_emb[slot], (size_t)b * h->E * sizeof(float), cudaMemcpyDeviceToHost, ls));
+    XVB_CUDA(cudaEventRecord(h->ev_done[slot], ls));
+    launches += lane->last_launches;
   }
+  if (lanes && (rc = ecapa_lanes_join(h, s))) return rc;
   XVB_CUDA(cudaStreamSynchronize(s));
   h->last_launches = launches;
   return XVB_OK;
@@ -492,6 +567,12 @@ extern "C" int xvb_ecapa_load(xvb_ecapa_t** out, const char* path) {
 
 extern "C" void xvb_ecapa_destroy(xvb_ecapa_t* h) {
   if (!h) return;
+  if (h->lane1) xvb_ecapa_destroy(h->lane1);
+  for (int i = 0; i < 2; ++i) {
+    if (h->lane_stream[i]) cudaStreamDestroy(h->lane_stream[i]);
+    if (h->ev_lane_done[i]) cudaEventDestroy(h->ev_lane_done[i]);
+  }
+  if (h->ev_lane_start) cudaEventDestroy(h->ev_lane_start);
   h->free_ws();
   cudaFree(h->h_feats); cudaFree(h->h_emb);
   for (int i = 0; i < 2; ++i) {
@@ -500,12 +581,14 @@ extern "C" void xvb_ecapa_destroy(xvb_ecapa_t* h) {
     if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
   }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-  for (auto& kv : h->layers) {
-    ELayer& L = kv.second;
-    cudaFree(L.w_hi); cudaFree(L.w_lo); cudaFree(L.bias); cudaFree(L.scale); cudaFree(L.shift);
-  }
-  for (int b = 0; b < 3; ++b) {
-    cudaFree(h->res_w_hi[b]); cudaFree(h->res_w_lo[b]); cudaFree(h->res_bias[b]); cudaFree(h->res_scale[b]); cudaFree(h->res_shift[b]);
+  if (!h->is_lane) {
+    for (auto& kv : h->layers) {
+      ELayer& L = kv.second;
+      cudaFree(L.w_hi); cudaFree(L.w_lo); cudaFree(L.bias); cudaFree(L.scale); cudaFree(L.shift);
+    }
+    for (int b = 0; b < 3; ++b) {
+      cudaFree(h->res_w_hi[b]); cudaFree(h->res_w_lo[b]); cudaFree(h->res_bias[b]); cudaFree(h->res_scale[b]); cudaFree(h->res_shift[b]);
+    }
   }
   delete h;
 }

@@ -87,6 +87,15 @@ struct xvb_extractor {
     for (auto& kv : plans) delete kv.second;
     plans.clear();
   }
+  // Two-lane shard pipeline: batches of a shard alternate between this extractor and `lane1`, a shallow twin that
+  // shares the packed weights but owns its workspace and plans, each on its own stream.  The tcgen05 layer kernels
+  // occupy whole SMs, so the two lanes' GEMMs queue behind one another; what overlaps is everything else -- the
+  // bandwidth-bound staging / pooling-merge / split-K-reduce kernels of one batch run on the SMs' spare thread and
+  // register slots next to the other batch's GEMM CTAs, and a GEMM's ragged tail is filled by the other lane's CTAs.
+  xvb_extractor* lane1 = nullptr;
+  bool is_lane = false;                      // a twin does not own the weights
+  cudaStream_t lane_stream[2] = {nullptr, nullptr};
+  cudaEvent_t ev_lane_start = nullptr, ev_lane_done[2] = {nullptr, nullptr};
   bool profiling = false;
   bool in_shard = false;
   std::vector<cudaEvent_t> events;
@@ -390,14 +399,68 @@ extern "C" int xvb_extractor_extract(xvb_extractor_t* h, const float* feats, int
   return XVB_OK;
 }
 
+static bool lanes_enabled() {
+  static const int knob = getenv("XVB_LANES") ? atoi(getenv("XVB_LANES")) : 1;
+  return knob != 0;
+}
+
+// Second lane + the two lane streams, created on first use.
+static int ensure_lanes(xvb_extractor* h) {
+  if (h->lane1) return XVB_OK;
+  for (int i = 0; i < 2; ++i) {
+    XVB_CUDA(cudaStreamCreateWithFlags(&h->lane_stream[i], cudaStreamNonBlocking));
+    XVB_CUDA(cudaEventCreateWithFlags(&h->ev_lane_done[i], cudaEventDisableTiming));
+  }
+  XVB_CUDA(cudaEventCreateWithFlags(&h->ev_lane_start, cudaEventDisableTiming));
+  xvb_extractor* c = new xvb_extractor();
+  c->feat_dim = h->feat_dim; c->ldf = h->ldf; c->finalized = true; c->pooling_eps = h->pooling_eps;
+  c->frame = h->frame; c->segment = h->segment;          // Layer = device pointers + shape: shared, not owned
+  c->max_c = h->max_c; c->max_seg_c = h->max_seg_c; c->fused_pooling = h->fused_pooling;
+  c->im2col_first = h->im2col_first; c->pad_front = h->pad_front; c->pad_back = h->pad_back;
+  c->is_lane = true;
+  h->lane1 = c;
+  return XVB_OK;
+}
+
+// fork: both lane streams start after everything already queued on `s`; join: `s` continues after both lanes
+static int lanes_fork(xvb_extractor* h, cudaStream_t s) {
+  XVB_CUDA(cudaEventRecord(h->ev_lane_start, s));
+  for (int i = 0; i < 2; ++i) XVB_CUDA(cudaStreamWaitEvent(h->lane_stream[i], h->ev_lane_start, 0));
+  return XVB_OK;
+}
+static int lanes_join(xvb_extractor* h, cudaStream_t s) {
+  for (int i = 0; i < 2; ++i) {
+    XVB_CUDA(cudaEventRecord(h->ev_lane_done[i], h->lane_stream[i]));
+    XVB_CUDA(cudaStreamWaitEvent(s, h->ev_lane_done[i], 0));
+  }
+  return XVB_OK;
+}
+
 // The caller loop of the reference (extract_embeddings.py:73-83: one utterance per iteration) for a whole
-// shard of N equal-length utterances resident on the device: ceil(N / batch) batches through the stack, back
-// to back on `stream`, embeddings written in place.  Asynchronous.
+// shard of N equal-length utterances resident on the device: ceil(N / batch) batches through the stack,
+// embeddings written in place.  Asynchronous on `stream` (the two lanes fork from it and join it again; with
+// per-kernel profiling on, or XVB_LANES=0, the batches run back to back on `stream` itself).
 extern "C" int xvb_extractor_extract_shard(xvb_extractor_t* h, const float* feats, int64_t N, int T, int batch, float* emb,
                                            void* stream) {
   XVB_CHECK_ARG(h && h->finalized && feats && emb && N > 0 && T > 0 && batch > 0, "xvb_extractor_extract_shard: bad arguments");
   const int D = h->segment.back().Cout;
   int launches = 0;
+  if (lanes_enabled() && !h->profiling && N > batch) {
+    int rc = ensure_lanes(h);
+    if (rc) return rc;
+    if ((rc = lanes_fork(h, (cudaStream_t)stream))) return rc;
+    int k = 0;
+    for (int64_t i = 0; i < N; i += batch, ++k) {
+      const int b = (int)(N - i < batch ? N - i : batch);
+      xvb_extractor* lane = (k & 1) ? h->lane1 : h;
+      rc = xvb_extractor_extract(lane, feats + (size_t)i * T * h->feat_dim, b, T, emb + (size_t)i * D, h->lane_stream[k & 1]);
+      if (rc) return rc;
+      launches += lane->last_launches;
+    }
+    if ((rc = lanes_join(h, (cudaStream_t)stream))) return rc;
+    h->last_launches = launches;
+    return XVB_OK;
+  }
   h->events_used = 0;
   h->in_shard = true;
   for (int64_t i = 0; i < N; i += batch) {
@@ -510,20 +573,29 @@ extern "C" int xvb_extractor_extract_shard_host(xvb_extractor_t* h, const float*
   const int bmax = (int)(N < batch ? N : batch);
   for (int slot = 0; slot < 2; ++slot)
     if ((rc = reserve_slot(h, slot, (size_t)bmax * T * h->feat_dim, (size_t)bmax * D))) return rc;
+  // slot k & 1 belongs to lane k & 1: its stack and the copy of its embeddings back run on that lane's stream
+  const bool lanes = lanes_enabled() && !h->profiling && N > batch;
+  if (lanes) {
+    if ((rc = ensure_lanes(h))) return rc;
+    if ((rc = lanes_fork(h, s))) return rc;
+  }
   int launches = 0, k = 0;
   for (int64_t i = 0; i < N; i += batch, ++k) {
     const int b = (int)(N - i < batch ? N - i : batch);
     const int slot = k & 1;
+    xvb_extractor* lane = (lanes && slot) ? h->lane1 : h;
+    cudaStream_t ls = lanes ? h->lane_stream[slot] : s;
     if (k >= 2) XVB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[slot], 0));   // batch k-2 has left this slot
     XVB_CUDA(cudaMemcpyAsync(h->p_feats[slot], feats_host + (size_t)i * T * h->feat_dim, (size_t)b * T * h->feat_dim * sizeof(float),
                              cudaMemcpyHostToDevice, h->copy_stream));
     XVB_CUDA(cudaEventRecord(h->ev_h2d[slot], h->copy_stream));
-    XVB_CUDA(cudaStreamWaitEvent(s, h->ev_h2d[slot], 0));
-    if ((rc = xvb_extractor_extract(h, h->p_feats[slot], b, T, h->p_emb[slot], stream))) return rc;
-    XVB_CUDA(cudaMemcpyAsync(emb_host + (size_t)i * D, h->p_emb[slot], (size_t)b * D * sizeof(float), cudaMemcpyDeviceToHost, s));
-    XVB_CUDA(cudaEventRecord(h->ev_done[slot], s));
-    launches += h->last_launches;
+    XVB_CUDA(cudaStreamWaitEvent(ls, h->ev_h2d[slot], 0));
+    if ((rc = xvb_extractor_extract(lane, h->p_feats[slot], b, T, h->p_emb[slot], ls))) return rc;
+    XVB_CUDA(cudaMemcpyAsync(emb_host + (size_t)i * D, h->p_emb[slot], (size_t)b * D * sizeof(float), cudaMemcpyDeviceToHost, ls));
+    XVB_CUDA(cudaEventRecord(h->ev_done[slot], ls));
+    launches += lane->last_launches;
   }
+  if (lanes && (rc = lanes_join(h, s))) return rc;
   XVB_CUDA(cudaStreamSynchronize(s));
   h->last_launches = launches;
   return XVB_OK;
@@ -533,6 +605,7 @@ extern "C" int xvb_extractor_set_fused_pooling(xvb_extractor_t* h, int enable) {
   XVB_CHECK_ARG(h, "xvb_extractor_set_fused_pooling: null extractor");
   if (h->fused_pooling != (enable != 0)) h->drop_plans();
   h->fused_pooling = enable != 0;
+  if (h->lane1) return xvb_extractor_set_fused_pooling(h->lane1, enable);
   return XVB_OK;
 }
 
@@ -562,6 +635,12 @@ extern "C" const float* xvb_extractor_debug_f32(const xvb_extractor_t* h, int wh
 
 extern "C" void xvb_extractor_destroy(xvb_extractor_t* h) {
   if (!h) return;
+  if (h->lane1) xvb_extractor_destroy(h->lane1);
+  for (int i = 0; i < 2; ++i) {
+    if (h->lane_stream[i]) cudaStreamDestroy(h->lane_stream[i]);
+    if (h->ev_lane_done[i]) cudaEventDestroy(h->ev_lane_done[i]);
+  }
+  if (h->ev_lane_start) cudaEventDestroy(h->ev_lane_start);
   h->free_ws();
   for (cudaEvent_t e : h->events) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i) {
@@ -571,7 +650,8 @@ extern "C" void xvb_extractor_destroy(xvb_extractor_t* h) {
   }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   cudaFree(h->h_feats); cudaFree(h->h_emb); cudaFree(h->pool_partial);
-  for (auto* v : {&h->frame, &h->segment})
-    for (Layer& L : *v) { cudaFree(L.w_hi); cudaFree(L.w_lo); cudaFree(L.bias); cudaFree(L.scale); cudaFree(L.shift); }
+  if (!h->is_lane)
+    for (auto* v : {&h->frame, &h->segment})
+      for (Layer& L : *v) { cudaFree(L.w_hi); cudaFree(L.w_lo); cudaFree(L.bias); cudaFree(L.scale); cudaFree(L.shift); }
   delete h;
 }

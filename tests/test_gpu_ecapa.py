@@ -198,6 +198,31 @@ def test_ecapa_vs_oracle_batch():
         assert rel(got[i], ref[i]) < EMB_TOL
 
 
+def test_ecapa_shard_calls_on_two_lanes_equal_per_batch_extraction():
+    """xvb_ecapa_extract_shard[_host]: batches alternate between the two lanes (twin workspaces, two streams) and must
+    reproduce independent per-batch calls bit for bit, ragged tail batch included; C3's full batch size (128 x 300) is
+    checked against sub-batches of itself (batch invariance at the BASELINE shape)."""
+    m, _ = _model("near")
+    ex = m.extractor()
+    n, t = 11, 47
+    feats = torch.from_numpy(onn.synthetic_feats(n, t, 80, 777)).cuda()
+    want = torch.cat([ex.extract(feats[i:i + 4]).clone() for i in range(0, n, 4)])         # batches of 4, 4, 3
+    assert torch.equal(ex.extract_shard(feats, 4), want)
+    assert torch.equal(ex.extract_shard(feats, 4), want)                                    # lanes reused
+    host = torch.empty(n, t, 80, dtype=torch.float32, pin_memory=True)
+    host.copy_(feats)
+    out = torch.empty(n, ex.embed_dim, dtype=torch.float32, pin_memory=True)
+    ex.extract_shard_host(host.data_ptr(), n, t, out.data_ptr(), 4)
+    assert torch.equal(out, want.cpu())
+    full = torch.from_numpy(onn.synthetic_feats(128, 300, 80, 778)).cuda()
+    whole = ex.extract(full).clone()
+    assert torch.isfinite(whole).all()
+    parts = ex.extract_shard(full, 32)                                                      # 4 sub-batches on 2 lanes
+    assert (whole - parts).abs().max() <= 1e-6 * whole.abs().max()      # split-free layers: same arithmetic per utterance
+    one = ex.extract(full[77:78]).clone()
+    assert (one[0] - whole[77]).abs().max() <= 1e-6 * whole.abs().max()
+
+
 def test_native_ecapa_extractor_equals_python_orchestration_and_model_file(tmp_path, monkeypatch):
     """xvb_ecapa_t (the launch sequence in C++) against the op-by-op Python twin: same kernels, same order ->
     bit-identical embeddings; and the XVBE0001 model file round trip."""
