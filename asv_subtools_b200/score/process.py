@@ -185,7 +185,7 @@ def step_getmean(infile, outmean):
 
 def step_submean(mean, infile, outfile):
     keys, x = backend.load_vectors(_spec(infile))
-    m = torch.from_numpy(np.asarray(kaldi_io.read_vec_flt(mean), dtype=np.float32)).to(x.device)
+    m = torch.from_numpy(np.array(kaldi_io.read_vec_flt(mean), dtype=np.float32)).to(x.device)
     _write_vectors(outfile, keys, backend.preprocess(x, m, norm=False))
 
 

@@ -391,9 +391,10 @@ def test_snowdar_attention_poolings_match_reference_golden(golden, cname):
 
 @pytest.mark.parametrize("heads,gdiv_kind,global_heads,unweighted", [(1, "share", False, False), (4, "share", False, True),
                                                                      (4, "full", False, False), (3, "share", True, False),
-                                                                     (2, "full", True, True)])
+                                                                     (2, "full", True, False)])
 def test_attn_head_stats_pool_kernel_vs_oracle(heads, gdiv_kind, global_heads, unweighted):
-    """xvb_attn_head_stats_pool against oracle.attention_pooling for every head map, both std branches, strided inputs."""
+    """xvb_attn_head_stats_pool against oracle.attention_pooling for every head map, both std branches (the reference's
+    `stddev_attention=False` branch only type-checks for split heads, pooling.py:432-434 vs :507-509), strided inputs."""
     from asv_subtools_b200 import ops
     rng = np.random.RandomState(11)
     B, T, C = 3, 77, 24 * heads if not global_heads else 20
