@@ -44,6 +44,7 @@ struct Res2Params {
   __nv_bfloat16* y_hi;         // block output planes (B,T,ldy)
   __nv_bfloat16* y_lo;
   long long ldx, ldy;
+  int debug;              // timing experiments only (XVB_RES2_DEBUG, wrong results): bit0 one A source, bit1 every store issued twice
 };
 
 __global__ void __launch_bounds__(kRThreads, 1)
@@ -89,7 +90,7 @@ res2net_chain_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_
         for (int st = 0; st < p.num_steps; ++st) {
           for (int m = 0; m < p.num_m; ++m) {
             const int t0 = m * 128;
-            for (int src = 0; src < (st == 0 ? 1 : 2); ++src) {
+            for (int src = 0; src < ((st == 0 || (p.debug & 1)) ? 1 : 2); ++src) {
               if (src == 1 && m == 0) {
                 // outputs of step st-1 (all tiles of this utterance) must have landed before we read them back
                 mbar_wait(step_bar, steps_done & 1);
@@ -131,7 +132,7 @@ res2net_chain_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_
       uint32_t phase = 0, it = 0;
       for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
         for (int st = 0; st < p.num_steps; ++st) {
-          const int nkb = (st == 0 ? 1 : 2) * 6;
+          const int nkb = ((st == 0 || (p.debug & 1)) ? 1 : 2) * 6;
           for (int m = 0; m < p.num_m; ++m, ++it) {
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
             mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
@@ -231,6 +232,18 @@ res2net_chain_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_
               tma_store_3d(&map_yout_lo, slab_base + 8192, n, t0, b);
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
+            if (p.debug & 2) {   // timing experiment: the same hand-over a second time
+              if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              asm volatile("bar.sync 1, 256;" ::: "memory");
+              fence_proxy_async();
+              asm volatile("bar.sync 2, 256;" ::: "memory");
+              if (leader) {
+                const int n = (st + 1) * kRW + ch * 32;
+                tma_store_3d(&map_yout_hi, slab_base, n, t0, b);
+                tma_store_3d(&map_yout_lo, slab_base + 8192, n, t0, b);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
+            }
           };
           uint32_t va[16], vb[16];
           tmem_ld_32x16(trow, va);
@@ -252,7 +265,7 @@ res2net_chain_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_
         if (leader) {
           asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
           fence_proxy_async();
-          mbar_arrive(step_bar);
+          if (!(p.debug & 1) || st == p.num_steps - 1) mbar_arrive(step_bar);
         }
       }
     }
@@ -286,6 +299,7 @@ extern "C" int xvb_res2net_block(const uint16_t* x_hi, const uint16_t* x_lo, int
   p.x_hi = reinterpret_cast<const __nv_bfloat16*>(x_hi); p.x_lo = reinterpret_cast<const __nv_bfloat16*>(x_lo);
   p.y_hi = reinterpret_cast<__nv_bfloat16*>(y_hi); p.y_lo = reinterpret_cast<__nv_bfloat16*>(y_lo);
   p.ldx = ldx; p.ldy = ldy;
+  p.debug = getenv("XVB_RES2_DEBUG") ? atoi(getenv("XVB_RES2_DEBUG")) : 0;
   CUtensorMap mx_hi, mx_lo, myi_hi, myi_lo, mw_hi, mw_lo, myo_hi, myo_lo;
   const unsigned long long dx[3] = {(unsigned long long)C, (unsigned long long)T, (unsigned long long)B};
   const unsigned long long sx[2] = {(unsigned long long)ldx * 2, (unsigned long long)ldx * 2 * T};

@@ -65,7 +65,8 @@ struct TdnnGemmParams {
   const float* utt_bias;  // per-utterance x column additive term (B, ld_utt), may be NULL
   long long ld_utt;
   int log2_tb;            // Tb is a power of two
-  int debug;              // -DXVB_TIMING_EXPERIMENTS only: bit0 skip epilogue, bit1 skip MMA, bit2 skip store issue, bit3 skip LDTM
+  int debug;              // -DXVB_TIMING_EXPERIMENTS only: bit0 skip epilogue, bit1 skip MMA, bit2 skip store issue, bit3 skip LDTM,
+                          // box64 epilogue: bit4 parameters not read from smem, bit5 slab not filled, bit6 no hand-over barriers
   int plane_box64;        // plane-only outputs: 64-column chunks, hi then lo through the slab, 128-byte store rows
   int store_mode;         // 0: epilogue slab -> TMA store; 1: slab -> coalesced st.global; 2: registers -> st.global (sector-sized)
   float* pool_partial;    // fused statistics pooling: per (time block, utterance, channel) [mean | M2] partials
@@ -675,7 +676,7 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
         // hand-overs per column as the 32-column path, but every store row is a whole 128-byte line instead of two
         // 64-byte halves written at different times: half as many write requests next to the operand stream
         // (profiles/r01_gemm_experiments.md: shorter rows cost 12-16 % on the K <= 512 layers).
-        const int nch64 = (min(p.Cout - n0, kTileN) + 63) >> 6;
+        const int nch64 = XVB_DBG(p, 1) ? 0 : (min(p.Cout - n0, kTileN) + 63) >> 6;
         const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kTileN + half * 32;
         uint32_t v0[16], v1[16];
         tmem_ld_32x16(tq, v0);
@@ -687,9 +688,12 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
           uint32_t hh[16], ll[16];
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
-            const float4 bb = ld_shared_f4(prm + (pc + 4 * g) * 4);
-            const float4 ss = ld_shared_f4(prm + (kTileN + pc + 4 * g) * 4);
-            const float4 tt = ld_shared_f4(prm + (2 * kTileN + pc + 4 * g) * 4);
+            float4 bb = make_float4(0.1f, 0.1f, 0.1f, 0.1f), ss = make_float4(1.1f, 1.1f, 1.1f, 1.1f), tt = bb;
+            if (!XVB_DBG(p, 16)) {
+              bb = ld_shared_f4(prm + (pc + 4 * g) * 4);
+              ss = ld_shared_f4(prm + (kTileN + pc + 4 * g) * 4);
+              tt = ld_shared_f4(prm + (2 * kTileN + pc + 4 * g) * 4);
+            }
             const uint32_t* src = g < 4 ? v0 + 4 * g : v1 + 4 * (g - 4);
             float x0 = __uint_as_float(src[0]) + bb.x, x1 = __uint_as_float(src[1]) + bb.y;
             float x2 = __uint_as_float(src[2]) + bb.z, x3 = __uint_as_float(src[3]) + bb.w;
@@ -725,13 +729,17 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
 #pragma unroll
           for (int plane = 0; plane < 2; ++plane) {
             if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (!XVB_DBG(p, 64)) asm volatile("bar.sync 1, 256;" ::: "memory");
             const uint32_t* w = plane == 0 ? hh : ll;
+            if (!XVB_DBG(p, 32)) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)                      // this thread's 32 columns = 4 chunks of 16 bytes
-              st_shared_v4(rowaddr + (((half * 4 + k) ^ sw) << 4), w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+              for (int k = 0; k < 4; ++k)                      // this thread's 32 columns = 4 chunks of 16 bytes
+                st_shared_v4(rowaddr + (((half * 4 + k) ^ sw) << 4), w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+            } else if (w[0] == 0x12345678u) {                  // keep the values live
+              st_shared_v4(rowaddr, w[0], w[5], w[10], w[15]);
+            }
             fence_proxy_async();
-            asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (!XVB_DBG(p, 64)) asm volatile("bar.sync 2, 256;" ::: "memory");
             if (leader && !XVB_DBG(p, 4)) {
               tma_store_3d(plane == 0 ? &map_y_hi : &map_y_lo, slab_base, ncol, t0, b0);
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -989,6 +997,9 @@ static int prepare_gemm(GemmPlan& pl, const void* w_hi, const void* w_lo) {
                                 : (long long)num_m_units * p.num_n_blk * (p.k_slices > 1 ? p.k_slices : 1);
   XVB_CHECK_ARG(tiles < (1ll << 31), "xvb_tdnn_affine: %d x %d tiles exceed one launch", num_m_units, p.num_n_blk);
   p.num_tiles = (int)tiles;
+#ifdef XVB_TIMING_EXPERIMENTS
+  p.debug = getenv("XVB_GEMM_DEBUG") ? atoi(getenv("XVB_GEMM_DEBUG")) : 0;
+#endif
   static const int box64_knob = getenv("XVB_GEMM_BOX64") ? atoi(getenv("XVB_GEMM_BOX64")) : 1;
   p.plane_box64 = (box64_knob && !kPool && !kHist && p.y_hi && !p.y_f32 && p.store_mode == 0 && Cfg::kTileN >= 64) ? 1 : 0;
   if (p.y_hi) {
