@@ -728,6 +728,27 @@ tdnn_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
           const int sw = row & 7;
 #pragma unroll
           for (int plane = 0; plane < 2; ++plane) {
+            if (p.store_mode == 1) {
+              // XVB_GEMM_STORE=direct (experiment): the slab is drained by the epilogue threads themselves -- 16 bytes per
+              // thread, a warp instruction covers four whole 128-byte lines -- instead of by the TMA unit
+              asm volatile("bar.sync 1, 256;" ::: "memory");          // everybody has read the previous contents
+              const uint32_t* wd = plane == 0 ? hh : ll;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                st_shared_v4(rowaddr + (((half * 4 + k) ^ sw) << 4), wd[4 * k], wd[4 * k + 1], wd[4 * k + 2], wd[4 * k + 3]);
+              asm volatile("bar.sync 2, 256;" ::: "memory");
+              __nv_bfloat16* base = plane == 0 ? p.y_hi : p.y_lo;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int item = etid + 256 * k;
+                const int rr = item >> 3, cc = item & 7;
+                const int gb = b0 + (rr >> p.log2_tb), gt = t0 + (rr & (p.Tb - 1)), col = ncol + cc * 8;
+                const uint4 wv = ld_shared_u4(slab + rr * 128 + ((cc ^ (rr & 7)) << 4));
+                if (gb < p.B && gt < p.T && col < p.Cout)
+                  *reinterpret_cast<uint4*>(base + ((long long)gb * p.T + gt) * p.ldy + col) = wv;
+              }
+              continue;
+            }
             if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             if (!XVB_DBG(p, 64)) asm volatile("bar.sync 1, 256;" ::: "memory");
             const uint32_t* w = plane == 0 ? hh : ll;
@@ -1001,7 +1022,7 @@ static int prepare_gemm(GemmPlan& pl, const void* w_hi, const void* w_lo) {
   p.debug = getenv("XVB_GEMM_DEBUG") ? atoi(getenv("XVB_GEMM_DEBUG")) : 0;
 #endif
   static const int box64_knob = getenv("XVB_GEMM_BOX64") ? atoi(getenv("XVB_GEMM_BOX64")) : 1;
-  p.plane_box64 = (box64_knob && !kPool && !kHist && p.y_hi && !p.y_f32 && p.store_mode == 0 && Cfg::kTileN >= 64) ? 1 : 0;
+  p.plane_box64 = (box64_knob && !kPool && !kHist && p.y_hi && !p.y_f32 && p.store_mode <= 1 && Cfg::kTileN >= 64) ? 1 : 0;
   if (p.y_hi) {
     const int bc = p.plane_box64 ? 64 : 32;
     if ((rc = make_out_map(&pl.my_hi, p.y_hi, 2, p.Cout, p.T, p.B, p.ldy, p.Tb, p.Bb, bc))) return rc;

@@ -11,7 +11,7 @@ tests)
 small)
   XVB_BENCH_UTTS=8192 XVB_BENCH_ECAPA_UTTS=2048 timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_bench_small.json 2> gpurun_out/${TAG}_bench_small.err; echo "small bench rc=$?"; tail -c 3000 gpurun_out/${TAG}_bench_small.json; tail -5 gpurun_out/${TAG}_bench_small.err ;;
 bench)
-  timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; tail -5 gpurun_out/${TAG}_bench.err
+  timeout 900 python bench.py --steps ${STEPS:-10} --warmup ${WARMUP:-3} > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; tail -5 gpurun_out/${TAG}_bench.err
   python - <<PY
 import json
 try:
