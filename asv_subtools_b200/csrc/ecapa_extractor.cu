@@ -79,10 +79,11 @@ struct xvb_ecapa {
   float* h_feats = nullptr; float* h_emb = nullptr;   // device staging of xvb_ecapa_extract_host
   size_t h_feats_cap = 0, h_emb_cap = 0;
   // two-slot pipeline of xvb_ecapa_extract_shard_host
-  float* p_feats[2] = {nullptr, nullptr}; float* p_emb[2] = {nullptr, nullptr};
-  size_t p_feats_cap[2] = {0, 0}, p_emb_cap[2] = {0, 0};
+  static constexpr int kSlots = 4;    // two device slots per lane: the copy engine runs ahead of both lanes
+  float* p_feats[kSlots] = {nullptr, nullptr, nullptr, nullptr}; float* p_emb[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+  size_t p_feats_cap[kSlots] = {0, 0, 0, 0}, p_emb_cap[kSlots] = {0, 0, 0, 0};
   cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  cudaEvent_t ev_h2d[kSlots] = {nullptr, nullptr, nullptr, nullptr}, ev_done[kSlots] = {nullptr, nullptr, nullptr, nullptr};
   // layer1 as an im2col view over time-padded planes (see extractor.cu): consecutive taps, feat_dim % 16 == 0
   bool im2col_first = false;
   int pad_front = 0, pad_back = 0;
@@ -456,15 +457,16 @@ extern "C" int xvb_ecapa_extract_shard_host(xvb_ecapa_t* h, const float* feats_h
   cudaStream_t s = (cudaStream_t)stream;
   if (!h->copy_stream) {
     XVB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < xvb_ecapa::kSlots; ++i) {
       XVB_CUDA(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
       XVB_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
     }
   }
+  constexpr int S = xvb_ecapa::kSlots;
   const int bmax = (int)(N < batch ? N : batch);
   const size_t nf = (size_t)bmax * T * h->feat_dim, ne = (size_t)bmax * h->E;
   int rc;
-  for (int slot = 0; slot < 2; ++slot) {
+  for (int slot = 0; slot < S; ++slot) {
     if (nf > h->p_feats_cap[slot]) {
       cudaFree(h->p_feats[slot]); h->p_feats[slot] = nullptr; h->p_feats_cap[slot] = 0;
       if ((rc = ealloc(&h->p_feats[slot], nf))) return rc;
@@ -484,10 +486,10 @@ extern "C" int xvb_ecapa_extract_shard_host(xvb_ecapa_t* h, const float* feats_h
   int launches = 0, k = 0;
   for (int64_t i = 0; i < N; i += batch, ++k) {
     const int b = (int)(N - i < batch ? N - i : batch);
-    const int slot = k & 1;
-    xvb_ecapa* lane = (lanes && slot) ? h->lane1 : h;
-    cudaStream_t ls = lanes ? h->lane_stream[slot] : s;
-    if (k >= 2) XVB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[slot], 0));
+    const int slot = k % S;
+    xvb_ecapa* lane = (lanes && (k & 1)) ? h->lane1 : h;
+    cudaStream_t ls = lanes ? h->lane_stream[k & 1] : s;
+    if (k >= S) XVB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[slot], 0));
     XVB_CUDA(cudaMemcpyAsync(h->p_feats[slot], feats_host + (size_t)i * T * h->feat_dim, (size_t)b * T * h->feat_dim * sizeof(float),
                              cudaMemcpyHostToDevice, h->copy_stream));
     XVB_CUDA(cudaEventRecord(h->ev_h2d[slot], h->copy_stream));
@@ -575,7 +577,7 @@ extern "C" void xvb_ecapa_destroy(xvb_ecapa_t* h) {
   if (h->ev_lane_start) cudaEventDestroy(h->ev_lane_start);
   h->free_ws();
   cudaFree(h->h_feats); cudaFree(h->h_emb);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < xvb_ecapa::kSlots; ++i) {
     cudaFree(h->p_feats[i]); cudaFree(h->p_emb[i]);
     if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
     if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);

@@ -66,10 +66,13 @@ struct xvb_extractor {
   float* h_feats = nullptr; float* h_emb = nullptr;            // device staging for *_host
   size_t h_feats_cap = 0, h_emb_cap = 0;
   // double-buffered pipelined host path (submit/wait): H2D of batch i+1 overlaps the stack of batch i
-  float* p_feats[2] = {nullptr, nullptr}; float* p_emb[2] = {nullptr, nullptr};
-  size_t p_feats_cap[2] = {0, 0}, p_emb_cap[2] = {0, 0};
+  // (slots 0/1 serve submit_host/wait; the shard call uses all kSlots: two per lane, so a lane's next batch is already
+  // on the device when its current one finishes)
+  static constexpr int kSlots = 4;
+  float* p_feats[kSlots] = {nullptr, nullptr, nullptr, nullptr}; float* p_emb[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+  size_t p_feats_cap[kSlots] = {0, 0, 0, 0}, p_emb_cap[kSlots] = {0, 0, 0, 0};
   cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  cudaEvent_t ev_h2d[kSlots] = {nullptr, nullptr, nullptr, nullptr}, ev_done[kSlots] = {nullptr, nullptr, nullptr, nullptr};
   bool slot_busy[2] = {false, false};
   int max_c = 0, max_seg_c = 0;
   int last_launches = 0;
@@ -502,7 +505,7 @@ extern "C" int xvb_extractor_extract_host(xvb_extractor_t* h, const float* feats
 static int ensure_pipeline(xvb_extractor* h) {
   if (h->copy_stream) return XVB_OK;
   XVB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < xvb_extractor::kSlots; ++i) {
     XVB_CUDA(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
     XVB_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
   }
@@ -571,9 +574,11 @@ extern "C" int xvb_extractor_extract_shard_host(xvb_extractor_t* h, const float*
   if ((rc = ensure_pipeline(h))) return rc;
   const int D = h->segment.back().Cout;
   const int bmax = (int)(N < batch ? N : batch);
-  for (int slot = 0; slot < 2; ++slot)
+  constexpr int S = xvb_extractor::kSlots;
+  for (int slot = 0; slot < S; ++slot)
     if ((rc = reserve_slot(h, slot, (size_t)bmax * T * h->feat_dim, (size_t)bmax * D))) return rc;
-  // slot k & 1 belongs to lane k & 1: its stack and the copy of its embeddings back run on that lane's stream
+  // batch k: lane k & 1, device slot k % 4 (two per lane: the copy engine runs up to two batches ahead of a lane); the
+  // stack and the copy of the embeddings back run on that lane's stream
   const bool lanes = lanes_enabled() && !h->profiling && N > batch;
   if (lanes) {
     if ((rc = ensure_lanes(h))) return rc;
@@ -582,10 +587,10 @@ extern "C" int xvb_extractor_extract_shard_host(xvb_extractor_t* h, const float*
   int launches = 0, k = 0;
   for (int64_t i = 0; i < N; i += batch, ++k) {
     const int b = (int)(N - i < batch ? N - i : batch);
-    const int slot = k & 1;
-    xvb_extractor* lane = (lanes && slot) ? h->lane1 : h;
-    cudaStream_t ls = lanes ? h->lane_stream[slot] : s;
-    if (k >= 2) XVB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[slot], 0));   // batch k-2 has left this slot
+    const int slot = k % S;
+    xvb_extractor* lane = (lanes && (k & 1)) ? h->lane1 : h;
+    cudaStream_t ls = lanes ? h->lane_stream[k & 1] : s;
+    if (k >= S) XVB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[slot], 0));   // batch k-4 has left this slot
     XVB_CUDA(cudaMemcpyAsync(h->p_feats[slot], feats_host + (size_t)i * T * h->feat_dim, (size_t)b * T * h->feat_dim * sizeof(float),
                              cudaMemcpyHostToDevice, h->copy_stream));
     XVB_CUDA(cudaEventRecord(h->ev_h2d[slot], h->copy_stream));
@@ -643,7 +648,7 @@ extern "C" void xvb_extractor_destroy(xvb_extractor_t* h) {
   if (h->ev_lane_start) cudaEventDestroy(h->ev_lane_start);
   h->free_ws();
   for (cudaEvent_t e : h->events) cudaEventDestroy(e);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < xvb_extractor::kSlots; ++i) {
     cudaFree(h->p_feats[i]); cudaFree(h->p_emb[i]);
     if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
     if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
