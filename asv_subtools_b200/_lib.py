@@ -74,6 +74,14 @@ SIGNATURES = {
     "xvb_column_mean": (_i, [_p, _i64, _i, _p, _p]),
     "xvb_cosine_trials": (_i, [_p, _p, _i, _p, _p, _i64, _p, _p]),
     "xvb_speaker_mean": (_i, [_p, _i, _p, _p, _i, _p, _p]),
+    "xvb_ipc_alloc": (_i, [_p, C.c_size_t]),
+    "xvb_ipc_free": (_i, [_p]),
+    "xvb_ipc_export": (_i, [_p, _p]),
+    "xvb_ipc_open": (_i, [_p, _p]),
+    "xvb_ipc_close": (_i, [_p]),
+    "xvb_scatter_rows": (_i, [_p, _i64, _i, _p, _i, _i64, _i64, _p]),
+    "xvb_extractor_set_gather": (_i, [_p, _p, _i, _i64, _i64]),
+    "xvb_ecapa_set_gather": (_i, [_p, _p, _i, _i64, _i64]),
     "xvb_attn_head_stats_pool": (_i, [_p, _i64, _i, _p, _i64, _i, _i, _i, _i, _i, _f, _i, _p, _p, _p, _i64, _p]),
     "xvb_topn_mean_std": (_i, [_p, _i64, _i64, _i, _i, _p, _p, _p]),
     "xvb_topn_mean_std_ddof": (_i, [_p, _i64, _i64, _i, _i, _i, _p, _p, _p]),

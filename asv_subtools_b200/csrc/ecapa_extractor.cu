@@ -92,6 +92,10 @@ struct xvb_ecapa {
   // passes, staging) run next to the other batch's GEMM CTAs
   xvb_ecapa* lane1 = nullptr;
   bool is_lane = false;
+  // replicated embedding table (peer.cu): every batch's rows go to all these copies as soon as they exist
+  float* gather_tables[XVB_MAX_PEERS] = {nullptr};
+  int gather_n = 0;
+  int64_t gather_row0 = 0, gather_ld = 0;
   cudaStream_t lane_stream[2] = {nullptr, nullptr};
   cudaEvent_t ev_lane_start = nullptr, ev_lane_done[2] = {nullptr, nullptr};
 
@@ -378,6 +382,15 @@ extern "C" int xvb_ecapa_extract_host(xvb_ecapa_t* h, const float* feats_host, i
 // A whole shard of N equal-length utterances in `batch`-utterance batches (the reference's caller loop,
 // extract_embeddings.py:73-83), device-resident / through pinned host buffers with the copies overlapped
 // (same protocol as xvb_extractor_extract_shard[_host]).
+extern "C" int xvb_ecapa_set_gather(xvb_ecapa_t* h, float* const* tables, int ntables, int64_t row0, int64_t ld) {
+  XVB_CHECK_ARG(h && h->finalized && ntables >= 0 && ntables <= XVB_MAX_PEERS, "xvb_ecapa_set_gather: bad arguments");
+  XVB_CHECK_ARG(ntables == 0 || (tables && row0 >= 0 && ld >= h->E && ld % 4 == 0),
+                "xvb_ecapa_set_gather: need tables, row0 >= 0, ld >= embed_dim and ld %% 4 == 0");
+  for (int k = 0; k < ntables; ++k) h->gather_tables[k] = tables[k];
+  h->gather_n = ntables; h->gather_row0 = row0; h->gather_ld = ld;
+  return XVB_OK;
+}
+
 static bool ecapa_lanes_enabled() {
   static const int knob = getenv("XVB_LANES") ? atoi(getenv("XVB_LANES")) : 1;
   return knob != 0;
@@ -436,6 +449,8 @@ extern "C" int xvb_ecapa_extract_shard(xvb_ecapa_t* h, const float* feats, int64
       xvb_ecapa* lane = (k & 1) ? h->lane1 : h;
       if ((rc = xvb_ecapa_extract(lane, feats + (size_t)i * T * h->feat_dim, b, T, emb + (size_t)i * h->E, h->lane_stream[k & 1]))) return rc;
       launches += lane->last_launches;
+      if (h->gather_n && (rc = xvb_scatter_rows(emb + (size_t)i * h->E, b, h->E, h->gather_tables, h->gather_n, h->gather_row0 + i,
+                                                h->gather_ld, h->lane_stream[k & 1]))) return rc;
     }
     if ((rc = ecapa_lanes_join(h, (cudaStream_t)stream))) return rc;
     h->last_launches = launches;
@@ -444,6 +459,8 @@ extern "C" int xvb_ecapa_extract_shard(xvb_ecapa_t* h, const float* feats, int64
   for (int64_t i = 0; i < N; i += batch) {
     const int b = (int)(N - i < batch ? N - i : batch);
     int rc = xvb_ecapa_extract(h, feats + (size_t)i * T * h->feat_dim, b, T, emb + (size_t)i * h->E, stream);
+    if (!rc && h->gather_n)
+      rc = xvb_scatter_rows(emb + (size_t)i * h->E, b, h->E, h->gather_tables, h->gather_n, h->gather_row0 + i, h->gather_ld, stream);
     if (rc) return rc;
     launches += h->last_launches;
   }
@@ -495,6 +512,8 @@ extern "C" int xvb_ecapa_extract_shard_host(xvb_ecapa_t* h, const float* feats_h
     XVB_CUDA(cudaEventRecord(h->ev_h2d[slot], h->copy_stream));
     XVB_CUDA(cudaStreamWaitEvent(ls, h->ev_h2d[slot], 0));
     if ((rc = xvb_ecapa_extract(lane, h->p_feats[slot], b, T, h->p_emb[slot], ls))) return rc;
+    if (h->gather_n && (rc = xvb_scatter_rows(h->p_emb[slot], b, h->E, h->gather_tables, h->gather_n, h->gather_row0 + i, h->gather_ld, ls)))
+      return rc;
     XVB_CUDA(cudaMemcpyAsync(emb_host + (size_t)i * h->E, h->p_emb[slot], (size_t)b * h->E * sizeof(float), cudaMemcpyDeviceToHost, ls));
     XVB_CUDA(cudaEventRecord(h->ev_done[slot], ls));
     launches += lane->last_launches;

@@ -97,6 +97,10 @@ struct xvb_extractor {
   // register slots next to the other batch's GEMM CTAs, and a GEMM's ragged tail is filled by the other lane's CTAs.
   xvb_extractor* lane1 = nullptr;
   bool is_lane = false;                      // a twin does not own the weights
+  // replicated embedding table (peer.cu): every batch's rows go to all these copies as soon as they exist
+  float* gather_tables[XVB_MAX_PEERS] = {nullptr};
+  int gather_n = 0;
+  int64_t gather_row0 = 0, gather_ld = 0;
   cudaStream_t lane_stream[2] = {nullptr, nullptr};
   cudaEvent_t ev_lane_start = nullptr, ev_lane_done[2] = {nullptr, nullptr};
   bool profiling = false;
@@ -402,6 +406,15 @@ extern "C" int xvb_extractor_extract(xvb_extractor_t* h, const float* feats, int
   return XVB_OK;
 }
 
+extern "C" int xvb_extractor_set_gather(xvb_extractor_t* h, float* const* tables, int ntables, int64_t row0, int64_t ld) {
+  XVB_CHECK_ARG(h && h->finalized && ntables >= 0 && ntables <= XVB_MAX_PEERS, "xvb_extractor_set_gather: bad arguments");
+  XVB_CHECK_ARG(ntables == 0 || (tables && row0 >= 0 && ld >= h->segment.back().Cout && ld % 4 == 0),
+                "xvb_extractor_set_gather: need tables, row0 >= 0, ld >= embed_dim and ld %% 4 == 0");
+  for (int k = 0; k < ntables; ++k) h->gather_tables[k] = tables[k];
+  h->gather_n = ntables; h->gather_row0 = row0; h->gather_ld = ld;
+  return XVB_OK;
+}
+
 static bool lanes_enabled() {
   static const int knob = getenv("XVB_LANES") ? atoi(getenv("XVB_LANES")) : 1;
   return knob != 0;
@@ -459,6 +472,11 @@ extern "C" int xvb_extractor_extract_shard(xvb_extractor_t* h, const float* feat
       rc = xvb_extractor_extract(lane, feats + (size_t)i * T * h->feat_dim, b, T, emb + (size_t)i * D, h->lane_stream[k & 1]);
       if (rc) return rc;
       launches += lane->last_launches;
+      if (h->gather_n) {
+        if ((rc = xvb_scatter_rows(emb + (size_t)i * D, b, D, h->gather_tables, h->gather_n, h->gather_row0 + i, h->gather_ld,
+                                   h->lane_stream[k & 1]))) return rc;
+        ++launches;
+      }
     }
     if ((rc = lanes_join(h, (cudaStream_t)stream))) return rc;
     h->last_launches = launches;
@@ -469,6 +487,8 @@ extern "C" int xvb_extractor_extract_shard(xvb_extractor_t* h, const float* feat
   for (int64_t i = 0; i < N; i += batch) {
     const int b = (int)(N - i < batch ? N - i : batch);
     int rc = xvb_extractor_extract(h, feats + (size_t)i * T * h->feat_dim, b, T, emb + (size_t)i * D, stream);
+    if (!rc && h->gather_n && !h->profiling)
+      rc = xvb_scatter_rows(emb + (size_t)i * D, b, D, h->gather_tables, h->gather_n, h->gather_row0 + i, h->gather_ld, stream);
     if (rc) { h->in_shard = false; return rc; }
     launches += h->last_launches;
   }
@@ -596,6 +616,8 @@ extern "C" int xvb_extractor_extract_shard_host(xvb_extractor_t* h, const float*
     XVB_CUDA(cudaEventRecord(h->ev_h2d[slot], h->copy_stream));
     XVB_CUDA(cudaStreamWaitEvent(ls, h->ev_h2d[slot], 0));
     if ((rc = xvb_extractor_extract(lane, h->p_feats[slot], b, T, h->p_emb[slot], ls))) return rc;
+    if (h->gather_n && (rc = xvb_scatter_rows(h->p_emb[slot], b, D, h->gather_tables, h->gather_n, h->gather_row0 + i, h->gather_ld, ls)))
+      return rc;
     XVB_CUDA(cudaMemcpyAsync(emb_host + (size_t)i * D, h->p_emb[slot], (size_t)b * D * sizeof(float), cudaMemcpyDeviceToHost, ls));
     XVB_CUDA(cudaEventRecord(h->ev_done[slot], ls));
     launches += lane->last_launches;

@@ -267,6 +267,10 @@ class NativeEcapaExtractor:
                                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)), "xvb_ecapa_extract_shard")
         return emb
 
+    def set_gather(self, pointers, ntables, row0, ld):
+        """Replicated-table form of the shard calls (parallel.PeerTable.attach)."""
+        self._check(self._lib.xvb_ecapa_set_gather(self._h, pointers, int(ntables), int(row0), int(ld)), "xvb_ecapa_set_gather")
+
     def extract_shard_host(self, feats_ptr, n, t, emb_ptr, batch=128):
         """Pinned host feats (n,t,F) in, host embeddings (n,D) out; copies overlap the stack."""
         C = self._C

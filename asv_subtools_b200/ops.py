@@ -583,6 +583,11 @@ class Extractor:
         check(lib.xvb_extractor_extract_shard_host(self._h, C.c_void_p(feats_ptr), int(n), int(t), int(batch),
                                                    C.c_void_p(emb_ptr), _stream()), "xvb_extractor_extract_shard_host")
 
+    def set_gather(self, pointers, ntables, row0, ld):
+        """Replicated-table form of the shard calls (parallel.PeerTable.attach): every batch's embeddings also go to
+        `ntables` table copies at row0 + row; ntables = 0 turns it off."""
+        check(lib.xvb_extractor_set_gather(self._h, pointers, int(ntables), int(row0), int(ld)), "xvb_extractor_set_gather")
+
     def extract_host_into(self, feats_ptr, b, t, emb_ptr):
         check(lib.xvb_extractor_extract_host(self._h, C.c_void_p(feats_ptr), b, t, C.c_void_p(emb_ptr), _stream()),
               "xvb_extractor_extract_host")

@@ -582,15 +582,38 @@ def run_native(args, rank, world, local_rank):
     n_spk = max(2, n_total // UTTS_PER_SPK)
     feats, spk = synthetic_shard(n, T, F, rank * n, n_spk, dev, 2048 + rank)
     emb = torch.empty(n, D, device=dev)
-    full = torch.empty(n_total, D, device=dev) if world > 1 else emb
+    # The path's one exchange: every GPU needs the whole (N x n, 512) table.  Default: the table's copies are mapped
+    # into one another over NVLink (CUDA IPC) and every batch's embeddings are stored into all of them while the next
+    # batches run (csrc/peer.cu); a step then ends with a one-word all-reduce as the rendezvous.  XVB_BENCH_GATHER=nccl
+    # (or a refused mapping): one NCCL all-gather after the shard.
+    table, gather_kind = None, "none"
+    if world > 1:
+        gather_kind = "nccl"
+        if os.environ.get("XVB_BENCH_GATHER", "p2p") != "nccl":
+            try:
+                from asv_subtools_b200.parallel import PeerTable
+                table = PeerTable(n, D)
+                gather_kind = "p2p"
+            except RuntimeError as err:
+                if rank == 0:
+                    print("bench.py: peer table unavailable (%s): NCCL all-gather" % err, file=sys.stderr)
+    full = table.tensor if table is not None else (torch.empty(n_total, D, device=dev) if world > 1 else emb)
     spk_full = torch.empty(n_total, dtype=torch.int32, device=dev) if world > 1 else spk
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
     if world > 1:
         dist.all_gather_into_tensor(spk_full, spk)
+    if table is not None:
+        table.attach(ex)
+
+    def exchange():
+        if table is not None:
+            dist.all_reduce(flag)                      # rendezvous: every rank's peer stores are complete
+        elif world > 1:
+            dist.all_gather_into_tensor(full, emb)     # (N x n, 512) fp32 over NVLink
 
     def step():
         ex.extract_shard(feats, B, out=emb)
-        if world > 1:
-            dist.all_gather_into_tensor(full, emb)     # the path's one collective: (N x n, 512) fp32 over NVLink
+        exchange()
 
     # ---- device-resident throughput (sustained) --------------------------------------------------
     for _ in range(args.warmup):
@@ -603,8 +626,7 @@ def run_native(args, rank, world, local_rank):
     for i in range(args.steps):
         ex.extract_shard(feats, B, out=emb)
         ev[2 * i + 1].record()
-        if world > 1:
-            dist.all_gather_into_tensor(full, emb)
+        exchange()
         ev[2 * i + 2].record()
     tm.barrier()
     wall1 = time.time()
@@ -614,19 +636,27 @@ def run_native(args, rank, world, local_rank):
     launches_per_step = ex.last_launches
     assert torch.isfinite(emb).all()
     # the collective alone: inside a step its CUDA-event span also holds the wait for the slowest rank's shard
-    gather_alone_ms = 0.0
+    gather_alone_ms, p2p_equals_nccl = 0.0, None
     if world > 1:
+        check = torch.empty(n_total, D, device=dev)
         tm.barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
         for _ in range(5):
-            dist.all_gather_into_tensor(full, emb)
+            dist.all_gather_into_tensor(check, emb)
         g1.record()
         tm.barrier()
         gather_alone_ms = tm.max_over_ranks(g0.elapsed_time(g1) / 5)
+        if table is not None:                              # the peer-stored table must be the all-gathered one, bit for bit
+            same = torch.tensor([1 if torch.equal(check, full) else 0], device=dev)
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            p2p_equals_nccl = bool(same.item())
+        del check
     clocks_value = sampler.window(wall0, wall1) if sampler else None
 
     # ---- end to end through the host-buffer C-ABI shard call ----------------------------------------
+    if table is not None:
+        table.detach(ex)                                   # the end-to-end leg below measures the plain host-buffer call
     host = pinned_copy(feats)
     host_out = torch.empty(n, D, dtype=torch.float32, pin_memory=True)
     ex.extract_shard_host(host.data_ptr(), min(n, 8 * B), T, host_out.data_ptr(), B)      # warm: slots, copy stream
@@ -667,12 +697,21 @@ def run_native(args, rank, world, local_rank):
         sampler.stop()
 
     # ---- BASELINE configs[3] back end on the gathered table ---------------------------------------------
-    if world > 1:
+    if world > 1 and table is None:
         dist.all_gather_into_tensor(full, emb)
+    if table is not None:                                  # refill through the peer path (the e2e leg ran detached)
+        table.attach(ex)
+        ex.extract_shard(feats, B, out=emb)
+        table.detach(ex)
+        table.barrier()
     c4 = config4_block(tm, full, spk_full, rank, world, verify_single=True)
     del feats
     torch.cuda.empty_cache()
     c3, c5 = ecapa_blocks(tm, dev, rank, world, pk, args.steps)
+    if table is not None:
+        tm.barrier()                                       # nobody unmaps while a peer may still read
+        del full
+        table.close()
 
     if rank != 0:
         if world > 1:
@@ -689,13 +728,16 @@ def run_native(args, rank, world, local_rank):
         "dtype": "f32 (bf16x3 split operands on tcgen05, fp32 accumulate in TMEM)", "data": "synthetic",
         "config": workload_config(world),
         "timed_region_s": ms * 1e-3,
+        "exchange": {"kind": gather_kind, "p2p_equals_nccl": p2p_equals_nccl,
+                     "what": "p2p: every batch's embeddings are stored into all N table copies over NVLink peer mappings (CUDA IPC) "
+                             "while the next batches run, a one-word all-reduce ends the step; nccl: one all-gather after the shard"},
         "phases_ms": {"extract_shard": extract_ms, "all_gather_in_step": gather_ms, "all_gather_alone": gather_alone_ms,
                       "all_gather_bytes_out": gather_bytes,
                       "all_gather_busbw_gbs": (gather_bytes * (world - 1) / world) / (gather_alone_ms * 1e-3) / 1e9 if world > 1 and gather_alone_ms > 0 else None,
                       "note": "medians over the timed steps, max over ranks; all_gather_in_step spans from the end of this rank's shard "
-                              "to the end of the collective, i.e. it includes waiting for the slowest rank; all_gather_alone = the same "
-                              "collective timed by itself after a barrier (5 back to back), which is what the bus bandwidth is quoted on; "
-                              "it delivers the whole (N x %d, 512) fp32 table to every GPU" % n},
+                              "to the end of the step's exchange (p2p: the rendezvous all-reduce; nccl: the all-gather), i.e. it includes "
+                              "waiting for the slowest rank; all_gather_alone = the NCCL all-gather of the (N x %d, 512) fp32 table timed "
+                              "by itself after a barrier (5 back to back), which is what the bus bandwidth is quoted on" % n},
         "shard_pipeline": "two lanes: batches alternate between twin workspaces on two streams (XVB_LANES=%s)" % os.environ.get("XVB_LANES", "1"),
         "e2e": {"value": frames_per_step * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / e2e_steps,
                 "steps": e2e_steps, "h2d_bytes_per_step": n * T * F * 4, "d2h_bytes_per_step": n * D * 4,

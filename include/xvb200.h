@@ -394,6 +394,28 @@ int xvb_extractor_extract_shard(xvb_extractor_t* h, const float* feats, int64_t 
                                 void* stream);
 int xvb_extractor_extract_shard_host(xvb_extractor_t* h, const float* feats_host, int64_t N, int T, int batch,
                                      float* emb_host, void* stream);
+/* ---------------------------------------------------------------------------------------------
+ * The embedding table of BASELINE configs[3] on every GPU of a node without a collective after extraction
+ * (replaces the `cat xvector.*.scp` of extract_xvectors_for_pytorch.sh:147-151 and the NCCL all-gather
+ * of the plain path).  Each rank allocates its copy of the (world x n, D) table with xvb_ipc_alloc, exports it
+ * (64-byte CUDA IPC handle, exchanged by the caller -- torch.distributed, MPI, a file), and maps its peers' copies
+ * with xvb_ipc_open (NVLink peer access).  xvb_extractor_set_gather / xvb_ecapa_set_gather then make the shard calls
+ * store every batch's embeddings into ALL copies at row0 + (row inside the shard) as soon as the batch's last layer
+ * has produced them (xvb_scatter_rows on the batch's stream), overlapped with the following batches; the caller ends
+ * the step with a barrier.  tables[k], k < ntables: base pointers valid in THIS process (own copy included);
+ * ntables = 0 turns it off.  `emb` of the shard call still receives the rank's own rows.
+ * ------------------------------------------------------------------------------------------- */
+#define XVB_MAX_PEERS 16
+#define XVB_IPC_HANDLE_BYTES 64
+int xvb_ipc_alloc(void** ptr, size_t bytes);
+int xvb_ipc_free(void* ptr);
+int xvb_ipc_export(void* ptr, void* handle64);
+int xvb_ipc_open(const void* handle64, void** ptr);
+int xvb_ipc_close(void* ptr);
+int xvb_scatter_rows(const float* src, int64_t rows, int D, float* const* tables, int ntables, int64_t row0, int64_t ld,
+                     void* stream);
+int xvb_extractor_set_gather(xvb_extractor_t* h, float* const* tables, int ntables, int64_t row0, int64_t ld);
+
 /* Per-kernel timing with CUDA events recorded on the launching stream around every kernel of
  * the next extract calls.  xvb_extractor_kernel_times() waits for the last call and returns the
  * number of kernels n (<= max_n) and their durations in ms, in launch order: split, frame layers,
@@ -468,6 +490,8 @@ int xvb_ecapa_extract_host(xvb_ecapa_t* h, const float* feats_host, int B, int T
 /* Whole shard of N equal-length utterances in `batch`-utterance batches (extract_embeddings.py:73-83's loop as one
  * call): device-resident and asynchronous, or through pinned host buffers with the copies overlapped. */
 int xvb_ecapa_extract_shard(xvb_ecapa_t* h, const float* feats, int64_t N, int T, int batch, float* emb, void* stream);
+/* the replicated-table form of the shard calls, see xvb_extractor_set_gather */
+int xvb_ecapa_set_gather(xvb_ecapa_t* h, float* const* tables, int ntables, int64_t row0, int64_t ld);
 int xvb_ecapa_extract_shard_host(xvb_ecapa_t* h, const float* feats_host, int64_t N, int T, int batch, float* emb_host,
                                  void* stream);
 int xvb_ecapa_last_launches(const xvb_ecapa_t* h);

@@ -359,6 +359,59 @@ def test_snowdar_xvector_matches_reference_golden(golden, cname, extend, seed):
         Xvector(40, 10, SE=True)
 
 
+def test_replicated_table_hooks_store_every_batch_into_every_copy():
+    """xvb_extractor_set_gather + xvb_scatter_rows on ONE GPU (csrc/peer.cu; the multi-process NVLink form is
+    tools/peer_table_check.py under torchrun): two table copies allocated with xvb_ipc_alloc, the shard call (device
+    and host-buffer forms, two lanes, ragged tail batch) fills both at the rank's row offset and still returns its own
+    rows; turning the hook off stops the stores."""
+    import ctypes as C
+    from asv_subtools_b200._lib import check, lib
+    m, _ = _model(80, 102, "far")
+    ex = m.extractor()
+    n, t, d, row0, rows = 150, 61, 512, 40, 256
+    feats = torch.from_numpy(onn.synthetic_feats(n, t, 80, 919)).cuda()
+    want = ex.extract_shard(feats, 64).clone()
+    ptrs = (C.c_void_p * 2)()
+    for k in range(2):
+        p = C.c_void_p()
+        check(lib.xvb_ipc_alloc(C.byref(p), rows * d * 4), "xvb_ipc_alloc")
+        ptrs[k] = p.value
+
+    def view(k):
+        holder = type("_B", (), {})()
+        holder.__cuda_array_interface__ = {"shape": (rows, d), "typestr": "<f4", "data": (int(ptrs[k]), False), "version": 3, "strides": None}
+        return torch.as_tensor(holder, device="cuda")
+    tabs = [view(0), view(1)]
+    handle = (C.c_uint8 * 64)()
+    check(lib.xvb_ipc_export(C.c_void_p(ptrs[0]), handle), "xvb_ipc_export")       # exportable (opening needs a second process)
+    try:
+        ex.set_gather(ptrs, 2, row0, d)
+        for tb in tabs:
+            tb.fill_(-7.0)
+        got = ex.extract_shard(feats, 64)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want)
+        for tb in tabs:
+            assert torch.equal(tb[row0:row0 + n], want) and bool((tb[:row0] == -7.0).all()) and bool((tb[row0 + n:] == -7.0).all())
+        host = torch.empty(n, t, 80, dtype=torch.float32, pin_memory=True)
+        host.copy_(feats)
+        out = torch.empty(n, d, dtype=torch.float32, pin_memory=True)
+        tabs[1].fill_(-7.0)
+        ex.extract_shard_host(host.data_ptr(), n, t, out.data_ptr(), 64)
+        assert torch.equal(out, want.cpu()) and torch.equal(tabs[1][row0:row0 + n], want)
+        ex.set_gather(None, 0, 0, 0)
+        tabs[0].fill_(-7.0)
+        ex.extract_shard(feats, 64)
+        torch.cuda.synchronize()
+        assert bool((tabs[0] == -7.0).all())
+    finally:
+        ex.set_gather(None, 0, 0, 0)
+        torch.cuda.synchronize()
+        del tabs
+        for k in range(2):
+            lib.xvb_ipc_free(C.c_void_p(ptrs[k]))
+
+
 SNOWDAR_POOLING_CASES = {
     "attn1": ("attentive", {}, 311),
     "attn2": ("attentive", {"affine_layers": 2, "hidden_size": 64}, 312),
