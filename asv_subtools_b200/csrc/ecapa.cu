@@ -216,6 +216,87 @@ attn_stats_pool_kernel(const float* __restrict__ logits, long long ldl, const fl
   }
 }
 
+// ---------------------------------------------------------------- segment-level affine on CUDA cores
+// y[b, n] = epi(bias[n] + sum_k W[n, k] x[b, k]) for a handful of rows b (one per utterance): the SE gate's two 1x1
+// convolutions on the time-mean (ecapa_tdnn_xvector.py:97-111), the time-constant half of the attention's first conv
+// (:179-181) and fc2 (:412-422).  As tcgen05 launches these M = B-row GEMMs cost 11-29 us each, latency-bound, while
+// holding whole SMs; here they are plain fp32 FMAs -- a warp owns a 4 x 4 (n x b) tile, its lanes stride over K with
+// 16-byte loads, one butterfly at the end -- small enough to run next to the other lane's GEMM CTAs.
+// epilogue order as everywhere: +bias -> ReLU -> BN(scale, shift) -> sigmoid | tanh; fp32 and/or split-plane output.
+constexpr int kSaWarps = 8;
+
+__global__ void __launch_bounds__(kSaWarps * 32)
+small_affine_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ w, int B, int K, int N,
+                    const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift, int flags,
+                    float* __restrict__ y, long long ldy, __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl,
+                    long long ldp) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = (blockIdx.x * 2 + (warp & 1)) * 4;           // block: 2 n-tiles x 4 b-tiles
+  const int b0 = (blockIdx.y * 4 + (warp >> 1)) * 4;
+  if (n0 >= N || b0 >= B) return;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const float* wr[4];
+  const float* xr[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    wr[i] = w + (long long)min(n0 + i, N - 1) * K;             // clamped rows are computed and dropped
+    xr[i] = x + (long long)min(b0 + i, B - 1) * ldx;
+  }
+  for (int k = lane * 4; k < K; k += 128) {                    // K % 4 == 0
+    float4 wv[4], xv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      wv[i] = __ldg(reinterpret_cast<const float4*>(wr[i] + k));
+      xv[i] = __ldg(reinterpret_cast<const float4*>(xr[i] + k));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[i][j] = fmaf(wv[i].x, xv[j].x, acc[i][j]);
+        acc[i][j] = fmaf(wv[i].y, xv[j].y, acc[i][j]);
+        acc[i][j] = fmaf(wv[i].z, xv[j].z, acc[i][j]);
+        acc[i][j] = fmaf(wv[i].w, xv[j].w, acc[i][j]);
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v = acc[i][j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      acc[i][j] = v;
+    }
+  if (lane < 16) {
+    const int i = lane & 3, j = lane >> 2;                     // lane -> (n0 + i, b0 + j)
+    const int n = n0 + i, b = b0 + j;
+    if (n < N && b < B) {
+      float v = 0.f;
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) v = (ii == i && jj == j) ? acc[ii][jj] : v;
+      v += bias ? __ldg(bias + n) : 0.f;
+      if (flags & XVB_RELU) v = fmaxf(v, 0.f);
+      if (flags & XVB_BN) v = fmaf(v, __ldg(scale + n), __ldg(shift + n));
+      if (flags & XVB_TANH) v = tanhf(v);
+      if (flags & XVB_SIGMOID) v = 1.f / (1.f + expf(-v));
+      if (y) y[(long long)b * ldy + n] = v;
+      if (yh) {
+        __nv_bfloat16 h, l;
+        split_bf16(v, h, l);
+        yh[(long long)b * ldp + n] = h;
+        yl[(long long)b * ldp + n] = l;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- attention pooling with a head map
 // The single-/multi-head attention poolings of libs/nnet/pooling.py (:322-587) differ only in WHICH logit weights
 // WHICH channel: output channel o in [0, O) pools input channel c = o % C with the softmax over time of logit
@@ -312,6 +393,26 @@ attn_head_stats_pool_kernel(const float* __restrict__ logits, long long ldl, con
 }  // namespace xvb
 
 using namespace xvb;
+
+extern "C" int xvb_small_affine(const float* x, int64_t ldx, const float* w, int B, int K, int N, const float* bias,
+                                const float* bn_scale, const float* bn_shift, int flags, float* y, int64_t ldy,
+                                uint16_t* y_hi, uint16_t* y_lo, int64_t ldplane, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  XVB_CHECK_ARG(x && w && (y || y_hi) && B > 0 && K > 0 && N > 0, "xvb_small_affine: bad arguments");
+  XVB_CHECK_ARG(K % 4 == 0 && ldx % 4 == 0 && ldx >= K && ((uintptr_t)x | (uintptr_t)w) % 16 == 0,
+                "xvb_small_affine: K and ldx must be multiples of 4, x and w 16-byte aligned");
+  XVB_CHECK_ARG(!(flags & XVB_BN) || (bn_scale && bn_shift), "xvb_small_affine: XVB_BN without scale/shift");
+  XVB_CHECK_ARG((y_hi != nullptr) == (y_lo != nullptr), "xvb_small_affine: y_hi/y_lo must both be set or both NULL");
+  XVB_CHECK_ARG((!y || ldy >= N) && (!y_hi || ldplane >= N), "xvb_small_affine: output pitch smaller than N");
+  dim3 grid((N + 7) / 8, (B + 15) / 16);
+  XVB_CHECK_ARG(grid.y <= 65535, "xvb_small_affine: too many rows (%d) -- this is the segment-level kernel", B);
+  small_affine_kernel<<<grid, kSaWarps * 32, 0, (cudaStream_t)stream>>>(
+      x, ldx, w, B, K, N, bias, bn_scale, bn_shift, flags, y, ldy, reinterpret_cast<__nv_bfloat16*>(y_hi),
+      reinterpret_cast<__nv_bfloat16*>(y_lo), ldplane);
+  XVB_LAUNCH_CHECK();
+  return XVB_OK;
+}
 
 extern "C" int xvb_attn_head_stats_pool(const float* logits, int64_t ldl, int G, const float* x, int64_t ldx, int B, int T,
                                         int C, int O, int gdiv, float floor_, int unweighted_var, float* out,

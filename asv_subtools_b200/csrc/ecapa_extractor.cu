@@ -36,6 +36,7 @@ struct ELayer {
   float* bias = nullptr;
   float* scale = nullptr;
   float* shift = nullptr;
+  float* w_f32 = nullptr;   // (Cout, Cin) fp32 as stored, kept for one-tap layers: the segment-level ones run on CUDA cores
   // host copies for save()
   std::vector<float> hw, hb, hs, ht;
 };
@@ -75,6 +76,7 @@ struct xvb_ecapa {
   std::vector<void*> ws;
   Planes in, X, Hh, R, Z, N, CAT, M, A1, gp, s1, zm, pp;
   float *MF = nullptr, *LOG = nullptr, *gate = nullptr, *ub = nullptr, *zmean = nullptr, *gstat = nullptr, *pstat = nullptr;
+  float* s1f = nullptr;   // (B, se_dim) fp32: hidden vector of the SE gate
   int last_launches = 0;
   float* h_feats = nullptr; float* h_emb = nullptr;   // device staging of xvb_ecapa_extract_host
   size_t h_feats_cap = 0, h_emb_cap = 0;
@@ -160,7 +162,8 @@ extern "C" int xvb_ecapa_set_layer(xvb_ecapa_t* h, const char* name, int Cout, i
   rc = xvb_pack_tdnn_weight(w_dev, Cout, Cin, L.tot, left, L.ctx, ntaps, L.w_hi, L.w_lo, nullptr);
   if (rc) return rc;
   XVB_CUDA(cudaDeviceSynchronize());
-  cudaFree(w_dev);
+  if (L.tot == 1 && Cin % 4 == 0) L.w_f32 = w_dev;   // one tap: (Cout, Cin, 1) is the (N, K) matrix xvb_small_affine takes
+  else cudaFree(w_dev);
   auto up = [&](float** d, const std::vector<float>& v) -> int {
     if (v.empty()) return XVB_OK;
     int r = ealloc(d, v.size());
@@ -256,7 +259,7 @@ static int reserve(xvb_ecapa* h, int B, int T) {
       (rc = h->planes(&h->gp, nb, 2 * D)) || (rc = h->planes(&h->s1, nb, h->se_dim)) || (rc = h->planes(&h->zm, nb, C)) ||
       (rc = h->planes(&h->pp, nb, 2 * D)) || (rc = h->f32(&h->MF, nf * D)) || (rc = h->f32(&h->LOG, nf * D)) ||
       (rc = h->f32(&h->gate, nb * C)) || (rc = h->f32(&h->ub, nb * h->H)) || (rc = h->f32(&h->zmean, nb * C)) ||
-      (rc = h->f32(&h->gstat, nb * 2 * D)) || (rc = h->f32(&h->pstat, nb * 2 * D)))
+      (rc = h->f32(&h->gstat, nb * 2 * D)) || (rc = h->f32(&h->pstat, nb * 2 * D)) || (rc = h->f32(&h->s1f, nb * (size_t)h->se_dim)))
     return rc;
   h->cap_frames = (long long)nf;
   h->cap_B = (int)nb;
@@ -276,6 +279,15 @@ struct Run {   // one layer launch: fill only what differs from the defaults
   int im2col_taps = 0;          // > 0: one-tap view, Cin = taps * L->Cin, rows overlap (x_batch_stride)
   int64_t x_batch_stride = 0;
 };
+// segment-level layer (one row per utterance) on CUDA cores: fp32 in, fp32 out
+int small_layer(const ELayer* L, const float* x, int64_t ldx, int B, float* y, int64_t ldy, int extra_flags, void* stream) {
+  return xvb_small_affine(x, ldx, L->w_f32, B, L->Cin, L->Cout, L->bias, L->scale, L->shift, L->flags | extra_flags, y, ldy,
+                          nullptr, nullptr, 0, stream);
+}
+bool small_ok(const ELayer* L) {
+  static const int knob = getenv("XVB_ECAPA_SMALL") ? atoi(getenv("XVB_ECAPA_SMALL")) : 1;
+  return knob && L->w_f32 != nullptr;
+}
 int launch(const Run& r, void* stream) {
   xvb_tdnn_args_t a{};
   a.x_hi = r.x.hi; a.x_lo = r.x.lo; a.ldx = r.x.ld;
@@ -328,10 +340,17 @@ extern "C" int xvb_ecapa_extract(xvb_ecapa_t* h, const float* feats, int B, int 
     r = Run{}; r.B = B; r.T = T; r.L = L(p + "bn2"); r.x = h->R; r.y = h->Z;
     if ((rc = launch(r, stream))) return rc;
     if ((rc = xvb_plane_mean(h->Z.hi, h->Z.lo, C, B, T, C, h->zmean, h->zm.hi, h->zm.lo, C, stream))) return rc;
-    r = Run{}; r.B = B; r.T = 1; r.L = L(p + "se1"); r.x = h->zm; r.y = h->s1;
-    if ((rc = launch(r, stream))) return rc;
-    r = Run{}; r.B = B; r.T = 1; r.L = L(p + "se2"); r.x = h->s1; r.y_f32 = h->gate; r.ldyf = C; r.extra_flags = XVB_SIGMOID;
-    if ((rc = launch(r, stream))) return rc;
+    if (small_ok(L(p + "se1")) && small_ok(L(p + "se2"))) {
+      rc = small_layer(L(p + "se1"), h->zmean, C, B, h->s1f, h->se_dim, 0, stream);
+      if (rc) return rc;
+      rc = small_layer(L(p + "se2"), h->s1f, h->se_dim, B, h->gate, C, XVB_SIGMOID, stream);
+      if (rc) return rc;
+    } else {
+      r = Run{}; r.B = B; r.T = 1; r.L = L(p + "se1"); r.x = h->zm; r.y = h->s1;
+      if ((rc = launch(r, stream))) return rc;
+      r = Run{}; r.B = B; r.T = 1; r.L = L(p + "se2"); r.x = h->s1; r.y_f32 = h->gate; r.ldyf = C; r.extra_flags = XVB_SIGMOID;
+      if ((rc = launch(r, stream))) return rc;
+    }
     const bool last = b == 2;
     const Planes slot = h->CAT.slice(C * b);
     if ((rc = xvb_se_apply(h->Z.hi, h->Z.lo, C, cur.hi, cur.lo, cur.ld, h->gate, slot.hi, slot.lo, slot.ld,
@@ -342,15 +361,25 @@ extern "C" int xvb_ecapa_extract(xvb_ecapa_t* h, const float* feats, int B, int 
   r = Run{}; r.B = B; r.T = T; r.L = L("mfa"); r.x = h->CAT; r.y = h->M; r.y_f32 = h->MF; r.ldyf = D;
   if ((rc = launch(r, stream))) return rc;
   if ((rc = xvb_stats_pool_ex(h->MF, D, B, T, D, 1e-5f, 1, h->gstat, h->gp.hi, h->gp.lo, 2 * D, stream))) return rc;
-  r = Run{}; r.B = B; r.T = 1; r.L = L("att_gs"); r.x = h->gp; r.y_f32 = h->ub; r.ldyf = h->H;
-  if ((rc = launch(r, stream))) return rc;
+  if (small_ok(L("att_gs"))) {
+    rc = small_layer(L("att_gs"), h->gstat, 2 * D, B, h->ub, h->H, 0, stream);
+      if (rc) return rc;
+  } else {
+    r = Run{}; r.B = B; r.T = 1; r.L = L("att_gs"); r.x = h->gp; r.y_f32 = h->ub; r.ldyf = h->H;
+    if ((rc = launch(r, stream))) return rc;
+  }
   r = Run{}; r.B = B; r.T = T; r.L = L("att_x"); r.x = h->M; r.y = h->A1; r.utt_bias = h->ub; r.ld_utt = h->H; r.extra_flags = XVB_TANH;
   if ((rc = launch(r, stream))) return rc;
   r = Run{}; r.B = B; r.T = T; r.L = L("att2"); r.x = h->A1; r.y_f32 = h->LOG; r.ldyf = D;
   if ((rc = launch(r, stream))) return rc;
   if ((rc = xvb_attn_stats_pool(h->LOG, D, h->MF, D, B, T, D, 1e-5f, h->pstat, h->pp.hi, h->pp.lo, 2 * D, stream))) return rc;
-  r = Run{}; r.B = B; r.T = 1; r.L = L("fc2"); r.x = h->pp; r.y_f32 = emb; r.ldyf = h->E;
-  if ((rc = launch(r, stream))) return rc;
+  if (small_ok(L("fc2"))) {
+    rc = small_layer(L("fc2"), h->pstat, 2 * D, B, emb, h->E, 0, stream);
+      if (rc) return rc;
+  } else {
+    r = Run{}; r.B = B; r.T = 1; r.L = L("fc2"); r.x = h->pp; r.y_f32 = emb; r.ldyf = h->E;
+    if ((rc = launch(r, stream))) return rc;
+  }
   h->last_launches = (int)(g_launches - before);
   return XVB_OK;
 }
@@ -416,6 +445,7 @@ static int ecapa_ensure_lanes(xvb_ecapa* h) {
     L.Cin = kv.second.Cin; L.Cout = kv.second.Cout; L.ntaps = kv.second.ntaps; L.flags = kv.second.flags; L.tot = kv.second.tot;
     for (int i = 0; i < XVB_MAX_TAPS; ++i) L.ctx[i] = kv.second.ctx[i];
     L.w_hi = kv.second.w_hi; L.w_lo = kv.second.w_lo; L.bias = kv.second.bias; L.scale = kv.second.scale; L.shift = kv.second.shift;
+    L.w_f32 = kv.second.w_f32;
     c->layers[kv.first] = L;
   }
   c->im2col_first = h->im2col_first; c->pad_front = h->pad_front; c->pad_back = h->pad_back;
@@ -605,7 +635,7 @@ extern "C" void xvb_ecapa_destroy(xvb_ecapa_t* h) {
   if (!h->is_lane) {
     for (auto& kv : h->layers) {
       ELayer& L = kv.second;
-      cudaFree(L.w_hi); cudaFree(L.w_lo); cudaFree(L.bias); cudaFree(L.scale); cudaFree(L.shift);
+      cudaFree(L.w_hi); cudaFree(L.w_lo); cudaFree(L.bias); cudaFree(L.scale); cudaFree(L.shift); cudaFree(L.w_f32);
     }
     for (int b = 0; b < 3; ++b) {
       cudaFree(h->res_w_hi[b]); cudaFree(h->res_w_lo[b]); cudaFree(h->res_bias[b]); cudaFree(h->res_scale[b]); cudaFree(h->res_shift[b]);

@@ -146,6 +146,8 @@ class _Layer:
         self.context = list(context)
         self.w = ops.pack_tdnn_weight(w, self.context)
         self.cout = w.shape[0]
+        # one-tap layers keep the (N, K) fp32 matrix too: the segment-level ones run on CUDA cores (ops.small_affine)
+        self.w_f32 = w[:, :, 0].contiguous() if w.shape[2] == 1 and w.shape[1] % 4 == 0 else None
         self.bias = bias.detach().float().to(device).contiguous() if bias is not None else None
         self.relu = relu
         scale, shift = scale_shift if scale_shift is not None else fold_batchnorm(bn)
@@ -157,8 +159,15 @@ class _Layer:
                            relu=self.relu, **kw)
         _mark("gemm K={}x{} N={}".format(len(self.context), x.channels, self.cout))
 
+    def run_rows(self, x, sigmoid=False):
+        """Segment-level form: x (B, K) fp32 -> (B, N) fp32 on CUDA cores (same kernel as the native extractor)."""
+        y = ops.small_affine(x, self.w_f32, self.bias, self.scale, self.shift, relu=self.relu, sigmoid=sigmoid)
+        _mark("rows K={} N={}".format(x.shape[1], self.cout))
+        return y
+
 
 _PROFILE = None  # list of (label, cuda event) when profiling (tools/bench_ecapa.py --profile)
+SMALL_ROWS = os.environ.get("XVB_ECAPA_SMALL", "1") != "0"   # segment-level layers on CUDA cores (csrc/ecapa.cu small_affine)
 
 
 def _mark(label):
@@ -391,10 +400,13 @@ class EcapaExtractor:
                     layer.run(H.slice(w * (i + 1), w * (i + 2)), x2=R.slice(w * i, w * (i + 1)) if i >= 1 else None,
                               y=R.slice(w * (i + 1), w * (i + 2)))
             blk["bn2"].run(R, y=Z)
-            _, zm = ops.plane_mean(Z)
+            zmean, zm = ops.plane_mean(Z)
             _mark("plane_mean")
-            blk["se1"].run(zm, y=s1)
-            blk["se2"].run(s1, sigmoid=True, y_f32=gate)
+            if SMALL_ROWS:
+                gate = blk["se2"].run_rows(blk["se1"].run_rows(zmean), sigmoid=True).view(B, 1, C)
+            else:
+                blk["se1"].run(zm, y=s1)
+                blk["se2"].run(s1, sigmoid=True, y_f32=gate)
             last = li + 1 == len(self.blocks)
             ops.se_apply(Z, cur, gate.view(B, C), CAT.slice(C * li, C * (li + 1)), None if last else N)
             _mark("se_apply")
@@ -403,16 +415,21 @@ class EcapaExtractor:
         M = P.empty((B, T, D), dev)
         MF = torch.empty(B, T, D, dtype=torch.float32, device=dev)
         self.mfa.run(CAT, y=M, y_f32=MF)
-        _, gp = ops.stats_pool_ex(MF, 1e-5, 1, planes=True)          # global mean | sqrt(var_unbiased + 1e-5)
+        gstat, gp = ops.stats_pool_ex(MF, 1e-5, 1, planes=True)      # global mean | sqrt(var_unbiased + 1e-5)
         _mark("stats_pool(global)")
-        ub = torch.empty(B, 1, self.att_gs.cout, dtype=torch.float32, device=dev)
-        self.att_gs.run(gp, y_f32=ub)
+        if SMALL_ROWS:
+            ub = self.att_gs.run_rows(gstat)
+        else:
+            ub = torch.empty(B, 1, self.att_gs.cout, dtype=torch.float32, device=dev)
+            self.att_gs.run(gp, y_f32=ub)
         A1 = P.empty((B, T, self.att_x.cout), dev)
         self.att_x.run(M, utt_bias=ub.view(B, -1), tanh=True, y=A1)
         LOG = torch.empty(B, T, D, dtype=torch.float32, device=dev)
         self.att2.run(A1, y_f32=LOG)
-        _, pp = ops.attn_stats_pool(LOG, MF, 1e-5, planes=True)
+        pstat, pp = ops.attn_stats_pool(LOG, MF, 1e-5, planes=True)
         _mark("attn_stats_pool")
+        if SMALL_ROWS:
+            return self.fc2.run_rows(pstat)
         emb = torch.empty(B, 1, self.embed_dim, dtype=torch.float32, device=dev)
         self.fc2.run(pp, y_f32=emb)
         return emb.view(B, self.embed_dim)

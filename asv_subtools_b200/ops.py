@@ -213,6 +213,22 @@ def attn_stats_pool(logits, x, floor=1e-5, planes=False):
     return (out, op) if planes else out
 
 
+def small_affine(x, w, bias=None, bn_scale=None, bn_shift=None, relu=False, sigmoid=False, tanh=False, planes=False):
+    """Segment-level fp32 affine on CUDA cores (xvb_small_affine): x (B, K) fp32, w (N, K) fp32 -> (B, N) fp32
+    [, the same as SplitPlanes (B, 1, N)]."""
+    x = _req(x, torch.float32, "x")
+    w = _req(w, torch.float32, "w")
+    b, k = x.shape
+    n = w.shape[0]
+    y = torch.empty(b, n, dtype=torch.float32, device=x.device)
+    op = SplitPlanes.empty((b, 1, (n + 7) // 8 * 8), x.device) if planes else None
+    flags = (RELU if relu else 0) | (BN if bn_scale is not None else 0) | (TANH if tanh else 0) | (SIGMOID if sigmoid else 0)
+    check(lib.xvb_small_affine(_ptr(x), k, _ptr(w), b, k, n, _ptr(bias), _ptr(bn_scale), _ptr(bn_shift), flags, _ptr(y), n,
+                               op.hi.data_ptr() if op else None, op.lo.data_ptr() if op else None, op.ld if op else 0, _stream()),
+          "xvb_small_affine")
+    return (y, op) if planes else y
+
+
 def attn_head_stats_pool(logits, x, out_channels, gdiv, floor=1e-10, unweighted_var=False, planes=False):
     """Attention pooling with a head map (xvb_attn_head_stats_pool): logits (B,T,G) fp32 (any row pitch >= G), x (B,T,C)
     fp32; output channel o pools x[..., o % C] with softmax_T(logits[..., o // gdiv]).  -> (B, 2*out_channels)."""

@@ -197,6 +197,15 @@ int xvb_se_apply(const uint16_t* z_hi, const uint16_t* z_lo, int64_t ldz, const 
 int xvb_attn_stats_pool(const float* logits, int64_t ldl, const float* x, int64_t ldx, int B, int T, int C, float floor_,
                         float* out, uint16_t* out_hi, uint16_t* out_lo, int64_t ldo, void* stream);
 
+/* Segment-level affine on CUDA cores, fp32 throughout: y[b,n] = epi(bias[n] + sum_k w[n,k] x[b,k]) for the few rows
+ * (one per utterance) of the SE gate's two 1x1 convolutions (ecapa_tdnn_xvector.py:97-111), the time-constant half of
+ * the attention's first conv (:179-181) and fc2 (:412-422).  x (B, >=K) fp32 pitch ldx, w (N, K) fp32 exactly as the
+ * state_dict stores a kernel-size-1 conv weight; flags XVB_RELU | XVB_BN | XVB_SIGMOID | XVB_TANH applied in that
+ * order after the bias; y fp32 (pitch ldy) and/or split planes (pitch ldplane).  K % 4 == 0. */
+int xvb_small_affine(const float* x, int64_t ldx, const float* w, int B, int K, int N, const float* bias,
+                     const float* bn_scale, const float* bn_shift, int flags, float* y, int64_t ldy, uint16_t* y_hi,
+                     uint16_t* y_lo, int64_t ldplane, void* stream);
+
 /* The attention poolings of libs/nnet/pooling.py with shared / per-head weights: AttentiveStatisticsPooling
  * (:322-368), MultiHeadAttentionPooling (:371-440), Global / MultiResolution multi-head (:443-587).  logits
  * (B,T,G) fp32 are the output of AttentionAlphaComponent's last affine (:300-319; temperature folded into its

@@ -154,6 +154,26 @@ def test_global_context_stats_and_attentive_pool(ops):
     assert rel(pl.float().cpu().numpy()[:, 0], ref) < 2e-5
 
 
+@pytest.mark.parametrize("B,K,N", [(128, 1024, 128), (128, 128, 1024), (5, 3072, 192), (1, 3072, 128), (37, 64, 20)])
+def test_small_affine_rows_vs_float64(ops, B, K, N):
+    """xvb_small_affine (segment-level fp32 affine on CUDA cores) against a float64 product, every epilogue flag, ragged
+    tile edges (B, N not multiples of the 4 x 4 warp tile), fp32 and split-plane outputs."""
+    rng = np.random.RandomState(B + K + N)
+    x = rng.standard_normal((B, K)).astype(np.float32)
+    w = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32) * 0.1
+    s, t = rng.uniform(0.5, 1.5, N).astype(np.float32), rng.standard_normal(N).astype(np.float32) * 0.1
+    base = x.astype(np.float64) @ w.astype(np.float64).T + b
+    cases = [(dict(), base), (dict(relu=True), np.maximum(base, 0)),
+             (dict(relu=True, bn_scale=cuda(s), bn_shift=cuda(t)), np.maximum(base, 0) * s + t),
+             (dict(sigmoid=True), 1 / (1 + np.exp(-base))), (dict(tanh=True), np.tanh(base))]
+    for kw, want in cases:
+        got = ops.small_affine(cuda(x), cuda(w), cuda(b), **kw)
+        assert rel(got.cpu().numpy(), want) < 2e-6, kw
+    y, planes = ops.small_affine(cuda(x), cuda(w), cuda(b), planes=True)
+    assert rel(planes.float().view(B, -1)[:, :N].cpu().numpy(), base) < 1e-5 and rel(y.cpu().numpy(), base) < 2e-6
+
+
 def _model(pos, seed=201, default_fc2=False):
     from asv_subtools_b200.model.ecapa_tdnn_xvector import ECAPA_TDNN
     if default_fc2:
