@@ -165,12 +165,12 @@ def test_small_affine_rows_vs_float64(ops, B, K, N):
     s, t = rng.uniform(0.5, 1.5, N).astype(np.float32), rng.standard_normal(N).astype(np.float32) * 0.1
     base = x.astype(np.float64) @ w.astype(np.float64).T + b
     cases = [(dict(), base), (dict(relu=True), np.maximum(base, 0)),
-             (dict(relu=True, bn_scale=cuda(s), bn_shift=cuda(t)), np.maximum(base, 0) * s + t),
+             (dict(relu=True, bn_scale=cu(s), bn_shift=cu(t)), np.maximum(base, 0) * s + t),
              (dict(sigmoid=True), 1 / (1 + np.exp(-base))), (dict(tanh=True), np.tanh(base))]
     for kw, want in cases:
-        got = ops.small_affine(cuda(x), cuda(w), cuda(b), **kw)
+        got = ops.small_affine(cu(x), cu(w), cu(b), **kw)
         assert rel(got.cpu().numpy(), want) < 2e-6, kw
-    y, planes = ops.small_affine(cuda(x), cuda(w), cuda(b), planes=True)
+    y, planes = ops.small_affine(cu(x), cu(w), cu(b), planes=True)
     assert rel(planes.float().view(B, -1)[:, :N].cpu().numpy(), base) < 1e-5 and rel(y.cpu().numpy(), base) < 2e-6
 
 
