@@ -82,6 +82,7 @@ SIGNATURES = {
     "xvb_scatter_rows": (_i, [_p, _i64, _i, _p, _i, _i64, _i64, _p]),
     "xvb_extractor_set_gather": (_i, [_p, _p, _i, _i64, _i64]),
     "xvb_ecapa_set_gather": (_i, [_p, _p, _i, _i64, _i64]),
+    "xvb_lde_pool": (_i, [_p, _i64, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _i64, _p]),
     "xvb_small_affine": (_i, [_p, _i64, _p, _i, _i, _i, _p, _p, _p, _i, _p, _i64, _p, _p, _i64, _p]),
     "xvb_attn_head_stats_pool": (_i, [_p, _i64, _i, _p, _i64, _i, _i, _i, _i, _i, _f, _i, _p, _p, _p, _i64, _p]),
     "xvb_topn_mean_std": (_i, [_p, _i64, _i64, _i, _i, _p, _p, _p]),

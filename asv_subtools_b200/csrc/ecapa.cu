@@ -216,6 +216,126 @@ attn_stats_pool_kernel(const float* __restrict__ logits, long long ldl, const fl
   }
 }
 
+// ---------------------------------------------------------------- LDE pooling (learnable dictionary encoding)
+// LDEPooling.forward, libs/nnet/pooling.py:148-159:  r[t,c,k] = x[t,c] - mu[c,k];  w[t,k] = softmax_k(-(s_k^2 + eps) * sum_c r^2);
+// e[c,k] = mean_t(w[t,k] * r[t,c,k]);  out (B, C*K), index c*K + k.  The squared distances are summed DIRECTLY in fp32
+// (expanding |x - mu|^2 = |x|^2 - 2 x.mu + |mu|^2 on the tensor cores would lose ~1e-3 of the softmax weights to
+// cancellation).  Two kernels: the weights (a block = 32 frames x all K clusters, x and mu staged through shared
+// memory in channel chunks) and the weighted residual mean (a block = one utterance x 32 channels, w rows staged in
+// shared memory in time chunks).  K <= 64, K % 4 == 0 (pad the dictionary with zero-weight columns: beta = +inf is
+// not needed, the caller passes neg_beta = -inf for padded clusters so that their softmax weight is exactly 0).
+constexpr int kLdeFrames = 32, kLdeChunk = 64, kLdeMaxK = 64;
+
+__global__ void __launch_bounds__(256)
+lde_weights_kernel(const float* __restrict__ x, long long ldx, long long rows, int C, const float* __restrict__ mu, int K,
+                   const float* __restrict__ neg_beta, float* __restrict__ w) {
+  __shared__ float xs[kLdeFrames][kLdeChunk + 1];
+  __shared__ float ms[kLdeChunk][kLdeMaxK];
+  const int f = threadIdx.x >> 3, g = threadIdx.x & 7;       // frame within the tile, cluster group: clusters g*kq .. +kq
+  const int kq = (K + 7) >> 3;                               // clusters per thread (<= 8)
+  const long long row0 = (long long)blockIdx.x * kLdeFrames;
+  float d[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) d[i] = 0.f;
+  for (int c0 = 0; c0 < C; c0 += kLdeChunk) {
+    const int cc = min(kLdeChunk, C - c0);
+    for (int e = threadIdx.x; e < kLdeFrames * kLdeChunk; e += 256) {
+      const int ff = e / kLdeChunk, c = e - ff * kLdeChunk;
+      xs[ff][c] = (row0 + ff < rows && c < cc) ? __ldg(x + (row0 + ff) * ldx + c0 + c) : 0.f;
+    }
+    for (int e = threadIdx.x; e < kLdeChunk * K; e += 256) {
+      const int c = e / K, k = e - c * K;
+      ms[c][k] = c < cc ? __ldg(mu + (long long)(c0 + c) * K + k) : 0.f;   // padded channels: x = mu = 0
+    }
+    __syncthreads();
+    for (int c = 0; c < cc; ++c) {
+      const float xv = xs[f][c];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = g * kq + i;
+        if (i < kq && k < K) { const float r = xv - ms[c][k]; d[i] = fmaf(r, r, d[i]); }
+      }
+    }
+    __syncthreads();
+  }
+  // softmax over the K clusters of this frame: the 8 threads of a frame are 8 consecutive lanes
+  float l[8], mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = g * kq + i;
+    l[i] = (i < kq && k < K) ? __ldg(neg_beta + k) * d[i] : -INFINITY;
+    mx = fmaxf(mx, l[i]);
+  }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { l[i] = expf(l[i] - mx); sum += l[i]; }   // exp(-inf) = 0 for absent clusters
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (row0 + f < rows) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = g * kq + i;
+      if (i < kq && k < K) w[(row0 + f) * K + k] = l[i] / sum;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+lde_encode_kernel(const float* __restrict__ x, long long ldx, int T, int C, const float* __restrict__ mu, int K,
+                  const float* __restrict__ w, float* __restrict__ out, __nv_bfloat16* __restrict__ oh,
+                  __nv_bfloat16* __restrict__ ol, long long ldo) {
+  __shared__ float ws[64][kLdeMaxK];                          // 64 frames of weights at a time
+  const int b = blockIdx.y;
+  const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;      // channel within the tile, cluster group
+  const int c = blockIdx.x * 32 + cl;
+  const int kq = (K + 7) >> 3;
+  float acc[8], m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = g * kq + i;
+    acc[i] = 0.f;
+    m[i] = (i < kq && k < K && c < C) ? __ldg(mu + (long long)c * K + k) : 0.f;
+  }
+  const float* xb = x + (long long)b * T * ldx;
+  const float* wb = w + (long long)b * T * K;
+  for (int t0 = 0; t0 < T; t0 += 64) {
+    const int tn = min(64, T - t0);
+    for (int e = threadIdx.x; e < tn * K; e += 256) ws[e / K][e % K] = __ldg(wb + (long long)t0 * K + e);
+    __syncthreads();
+    if (c < C) {
+      for (int t = 0; t < tn; ++t) {
+        const float xv = __ldg(xb + (long long)(t0 + t) * ldx + c);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int k = g * kq + i;
+          if (i < kq && k < K) acc[i] = fmaf(ws[t][k], xv - m[i], acc[i]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (c < C) {
+    const float inv = 1.f / (float)T;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = g * kq + i;
+      if (i < kq && k < K) {
+        const float v = acc[i] * inv;
+        const long long o = (long long)c * K + k;
+        out[(long long)b * C * K + o] = v;
+        if (oh) {
+          __nv_bfloat16 h, l;
+          split_bf16(v, h, l);
+          oh[(long long)b * ldo + o] = h;
+          ol[(long long)b * ldo + o] = l;
+        }
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- segment-level affine on CUDA cores
 // y[b, n] = epi(bias[n] + sum_k W[n, k] x[b, k]) for a handful of rows b (one per utterance): the SE gate's two 1x1
 // convolutions on the time-mean (ecapa_tdnn_xvector.py:97-111), the time-constant half of the attention's first conv
@@ -393,6 +513,26 @@ attn_head_stats_pool_kernel(const float* __restrict__ logits, long long ldl, con
 }  // namespace xvb
 
 using namespace xvb;
+
+extern "C" int xvb_lde_pool(const float* x, int64_t ldx, int B, int T, int C, const float* mu, int K, const float* neg_beta,
+                            float* w_scratch, float* out, uint16_t* out_hi, uint16_t* out_lo, int64_t ldo, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  XVB_CHECK_ARG(x && mu && neg_beta && w_scratch && out && B > 0 && T > 0 && C > 0 && ldx >= C, "xvb_lde_pool: bad arguments");
+  XVB_CHECK_ARG(K >= 1 && K <= kLdeMaxK, "xvb_lde_pool: %d clusters (1..%d)", K, kLdeMaxK);
+  XVB_CHECK_ARG((out_hi != nullptr) == (out_lo != nullptr) && (!out_hi || ldo >= (int64_t)C * K), "xvb_lde_pool: bad plane output");
+  XVB_CHECK_ARG(B <= 65535, "xvb_lde_pool: too many utterances for one launch");
+  const long long rows = (long long)B * T;
+  lde_weights_kernel<<<(unsigned)((rows + kLdeFrames - 1) / kLdeFrames), 256, 0, (cudaStream_t)stream>>>(x, ldx, rows, C, mu, K,
+                                                                                                        neg_beta, w_scratch);
+  XVB_LAUNCH_CHECK();
+  dim3 grid((C + 31) / 32, B);
+  lde_encode_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, T, C, mu, K, w_scratch, out,
+                                                           reinterpret_cast<__nv_bfloat16*>(out_hi),
+                                                           reinterpret_cast<__nv_bfloat16*>(out_lo), ldo);
+  XVB_LAUNCH_CHECK();
+  return XVB_OK;
+}
 
 extern "C" int xvb_small_affine(const float* x, int64_t ldx, const float* w, int B, int K, int N, const float* bias,
                                 const float* bn_scale, const float* bn_shift, int flags, float* y, int64_t ldy,

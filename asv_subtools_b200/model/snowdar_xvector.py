@@ -2,9 +2,9 @@
 """Snowdar x-vector blueprint for the B200 path -- drop-in for pytorch/model/snowdar_xvector.py (Xvector.init
 :15-152, extract_embedding :262-294) in its TDNN configurations: standard or `extend=True` stack,
 `tdnn_layer_params` (default BatchNorm affine=False, momentum 0.5), pooling = statistics | attentive | multi-head |
-multi-resolution (pooling.py:15-76, :322-440, :518-587; the blueprint's switch :119-136), positions
+multi-resolution | lde (pooling.py:15-76, :130-162, :322-440, :518-587; the blueprint's switch :119-136), positions
 far / near_affine / near.  Same constructor keywords and state_dict keys.  The options that add other
-operators (SE blocks, skip connection, LDE / xi-vector pooling) raise NotImplementedError;
+operators (SE blocks, skip connection, xi-vector pooling) raise NotImplementedError;
 training-only keywords (mixup, specaugment, dropouts, margin loss, step params) are accepted and ignored,
 as the launchers rewrite the creation string with training=False for extraction."""
 import os
@@ -12,7 +12,7 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
-from asv_subtools_b200.nnet import (AttentionPoolingExtractor, AttentiveStatisticsPooling,  # noqa: E402
+from asv_subtools_b200.nnet import (AttentionPoolingExtractor, AttentiveStatisticsPooling, LDEPooling,  # noqa: E402
                                     MultiHeadAttentionPooling, MultiResolutionMultiHeadAttentionPooling,
                                     ReluBatchNormTdnnLayer, StatisticsPooling, TopVirtualNnet, build_tdnn_extractor)
 
@@ -27,9 +27,9 @@ class Xvector(TopVirtualNnet):
              step_params={}, transfer_from="softmax_loss", training=True, extracted_embedding="far"):
         if SE or skip_connection:
             raise NotImplementedError("SE blocks / skip connection are not on the B200 path")
-        if pooling not in ("statistics", "attentive", "multi-head", "multi-resolution"):
-            raise NotImplementedError("pooling={!r}: statistics / attentive / multi-head / multi-resolution are on the B200 "
-                                      "path".format(pooling))
+        if pooling not in ("statistics", "lde", "attentive", "multi-head", "multi-resolution"):
+            raise NotImplementedError("pooling={!r}: statistics / lde / attentive / multi-head / multi-resolution are on the "
+                                      "B200 path".format(pooling))
         if not tdnn6:
             raise NotImplementedError("tdnn6=False is not on the B200 path")
         layer = {"nonlinearity": "relu", "nonlinearity_params": {"inplace": True}, "bn-relu": False, "bn": True,
@@ -58,7 +58,9 @@ class Xvector(TopVirtualNnet):
         self.ex_tdnn5 = L(512, 512, **layer) if extend else None
         self.tdnn4 = L(512, 512, **layer)
         self.tdnn5 = L(512, num_nodes, **layer)
-        if pooling == "attentive":                                                                          # :123-126
+        if pooling == "lde":                                                                                # :121-122
+            self.stats = LDEPooling(num_nodes, c_num=pool["num_head"])
+        elif pooling == "attentive":                                                                        # :123-126
             self.stats = AttentiveStatisticsPooling(num_nodes, affine_layers=pool["affine_layers"],
                                                     hidden_size=pool["hidden_size"], context=pool["context"], stddev=True)
         elif pooling == "multi-head":                                                                       # :127-128

@@ -239,15 +239,22 @@ class _PackedAffine:
 
 
 class AttentionPoolingExtractor:
-    """Launch sequence of a TDNN x-vector whose pooling is one of the attention poolings (nnet/pooling.py): frame layers
-    on the tcgen05 layer kernel (the last one also writes fp32, the pooling kernel's x), the attention affines as
-    GEMMs (grouped weights expanded block-diagonally, temperature folded into the last affine, logits fp32), softmax over
-    time + weighted mean / std in one pass (`xvb_attn_head_stats_pool`), then the segment layers on T = 1."""
+    """Launch sequence of a TDNN x-vector whose pooling is one of the attention poolings or LDE (nnet/pooling.py): frame
+    layers on the tcgen05 layer kernel (the last one also writes fp32, the pooling kernel's x), then either the attention
+    affines as GEMMs (grouped weights expanded block-diagonally, temperature folded into the last affine, logits fp32) +
+    softmax over time + weighted mean / std in one pass (`xvb_attn_head_stats_pool`), or the dictionary encoding
+    (`xvb_lde_pool`); then the segment layers on T = 1."""
 
     def __init__(self, model, inputs_dim, frame_layers, stats, tdnn6, tdnn7, position):
         dev = model.device_for_extraction()
         self.feat_dim = inputs_dim
         self.frames = [_PackedAffine(l.affine, dev, l.batchnorm, l.relu) for l in frame_layers]
+        self.lde = None
+        if hasattr(stats, "mu"):                                 # LDEPooling: no attention network
+            self.lde = (stats.mu.detach().float().to(dev).contiguous(), stats.neg_beta().to(dev).contiguous())
+            self.first = self.last = None
+            self._segments(dev, tdnn6, tdnn7, position)
+            return
         att = stats.attention
         self.first = _PackedAffine(att.first_affine, dev, relu=True) if att.relu_affine else None
         temps = att.head_temperatures()
@@ -257,6 +264,9 @@ class AttentionPoolingExtractor:
         self.last = _PackedAffine(att.last_affine, dev, row_scale=row_scale)
         self.channels, self.pooled, self.gdiv = stats.input_dim, stats.pooled_channels(), stats.logit_divisor()
         self.eps, self.unweighted = stats.eps, not stats.stddev_attention
+        self._segments(dev, tdnn6, tdnn7, position)
+
+    def _segments(self, dev, tdnn6, tdnn7, position):
         if position == "far":
             self.segment = [_PackedAffine(tdnn6.affine, dev)]
         else:
@@ -282,16 +292,19 @@ class AttentionPoolingExtractor:
         top = self.frames[-1]
         y, xp = top.planes(B, T, dev)
         xf = torch.empty(B, T, top.cout, dtype=torch.float32, device=dev)
-        top.run(x, y=y, y_f32=xf)
-        h = xp
-        if self.first is not None:
-            y, h = self.first.planes(B, T, dev)
-            self.first.run(xp, y=y)
-        logits = torch.empty(B, T, self.last.cout, dtype=torch.float32, device=dev)
-        self.last.run(h, y_f32=logits)
-        _, stats = ops.attn_head_stats_pool(logits[..., :self.last.cout_real], xf[..., :top.cout_real], self.pooled, self.gdiv,
+        if self.lde is not None:
+            top.run(x, y_f32=xf)
+            _, x = ops.lde_pool(xf[..., :top.cout_real], self.lde[0], self.lde[1], planes=True)
+        else:
+            top.run(x, y=y, y_f32=xf)
+            h = xp
+            if self.first is not None:
+                y, h = self.first.planes(B, T, dev)
+                self.first.run(xp, y=y)
+            logits = torch.empty(B, T, self.last.cout, dtype=torch.float32, device=dev)
+            self.last.run(h, y_f32=logits)
+            _, x = ops.attn_head_stats_pool(logits[..., :self.last.cout_real], xf[..., :top.cout_real], self.pooled, self.gdiv,
                                             floor=self.eps, unweighted_var=self.unweighted, planes=True)
-        x = stats
         for i, layer in enumerate(self.segment):
             if i + 1 == len(self.segment):
                 emb = torch.empty(B, 1, layer.cout, dtype=torch.float32, device=dev)
@@ -300,7 +313,8 @@ class AttentionPoolingExtractor:
                 y, view = layer.planes(B, 1, dev)
                 layer.run(x, y=y)
                 x = view
-        self.last_launches = len(self.frames) + (2 if self.first is not None else 1) + 2 + len(self.segment)
+        self.last_launches = len(self.frames) + (2 if self.lde is not None else (2 if self.first is not None else 1) + 1) + 1 + \
+            len(self.segment)
         return emb.view(B, -1)[:, :self.embed_dim]
 
     def close(self):

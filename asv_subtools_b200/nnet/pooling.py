@@ -1,4 +1,4 @@
-"""Pooling layers mirroring pytorch/libs/nnet/pooling.py: StatisticsPooling (:15-76) and the attention poolings built
+"""Pooling layers mirroring pytorch/libs/nnet/pooling.py: StatisticsPooling (:15-76), LDEPooling (:130-162) and the attention poolings built
 on AttentionAlphaComponent (:214-319) -- AttentiveStatisticsPooling (:322-368), MultiHeadAttentionPooling (:371-440),
 GlobalMultiHeadAttentionPooling (:443-515), MultiResolutionMultiHeadAttentionPooling (:518-587).  Parameter containers
 under the reference's state_dict keys; the arithmetic lives in csrc/pooling.cu / csrc/ecapa.cu
@@ -24,6 +24,27 @@ class StatisticsPooling(torch.nn.Module):
         """inputs: (B, C, T) like the reference -> (B, 2C, 1)."""
         x = inputs.transpose(1, 2).contiguous().float()
         return ops.stats_pool(x, eps=self.eps).unsqueeze(2)
+
+
+class LDEPooling(torch.nn.Module):
+    """Learnable dictionary encoding (pooling.py:130-162): parameters `mu` (input_dim, c_num) and `s` (c_num,) under the
+    reference's names; arithmetic in csrc/ecapa.cu (`xvb_lde_pool`: squared distances summed directly in fp32, softmax over
+    the clusters, weighted residual mean over time).  c_num <= 64."""
+
+    def __init__(self, input_dim, c_num=64, eps=1.0e-10):
+        super().__init__()
+        if c_num > 64:
+            raise NotImplementedError("B200 LDEPooling holds at most 64 clusters (xvb_lde_pool)")
+        self.input_dim, self.output_dim, self.eps = input_dim, input_dim * c_num, eps
+        self.mu = torch.nn.Parameter(torch.randn(input_dim, c_num))
+        self.s = torch.nn.Parameter(torch.ones(c_num))
+
+    def get_output_dim(self):
+        return self.output_dim
+
+    def neg_beta(self):
+        """-(s^2 + eps) per cluster, fp32 like the reference's forward (:155)."""
+        return -(self.s.detach().float() ** 2 + self.eps)
 
 
 class AttentionAlphaComponent(torch.nn.Module):

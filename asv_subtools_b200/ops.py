@@ -213,6 +213,30 @@ def attn_stats_pool(logits, x, floor=1e-5, planes=False):
     return (out, op) if planes else out
 
 
+def lde_pool(x, mu, neg_beta, planes=False):
+    """LDE pooling (xvb_lde_pool): x (B,T,C) fp32 (row stride may exceed C), mu (C,K) fp32, neg_beta (K,) fp32
+    -> (B, C*K) fp32 [, SplitPlanes (B,1,round_up(C*K,8))]."""
+    if x.dtype != torch.float32 or not x.is_cuda or x.dim() != 3 or x.stride(-1) != 1 or x.stride(0) != x.shape[1] * x.stride(1):
+        raise TypeError("x must be a (B,T,C) CUDA float32 tensor with contiguous rows")
+    mu = _req(mu, torch.float32, "mu")
+    neg_beta = _req(neg_beta, torch.float32, "neg_beta")
+    b, t, c = x.shape
+    k = mu.shape[1]
+    out = torch.empty(b, c * k, dtype=torch.float32, device=x.device)
+    w = torch.empty(b * t, k, dtype=torch.float32, device=x.device)
+    op = None
+    if planes:
+        op = SplitPlanes.empty((b, 1, (c * k + 7) // 8 * 8), x.device)
+        if op.ld != c * k:
+            op.hi.zero_()
+            op.lo.zero_()
+            op.channels = c * k
+    check(lib.xvb_lde_pool(_ptr(x), x.stride(-2), b, t, c, _ptr(mu), k, _ptr(neg_beta), _ptr(w), _ptr(out),
+                           op.hi.data_ptr() if op else None, op.lo.data_ptr() if op else None, op.ld if op else 0, _stream()),
+          "xvb_lde_pool")
+    return (out, op) if planes else out
+
+
 def small_affine(x, w, bias=None, bn_scale=None, bn_shift=None, relu=False, sigmoid=False, tanh=False, planes=False):
     """Segment-level fp32 affine on CUDA cores (xvb_small_affine): x (B, K) fp32, w (N, K) fp32 -> (B, N) fp32
     [, the same as SplitPlanes (B, 1, N)]."""

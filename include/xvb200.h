@@ -197,6 +197,13 @@ int xvb_se_apply(const uint16_t* z_hi, const uint16_t* z_lo, int64_t ldz, const 
 int xvb_attn_stats_pool(const float* logits, int64_t ldl, const float* x, int64_t ldx, int B, int T, int C, float floor_,
                         float* out, uint16_t* out_hi, uint16_t* out_lo, int64_t ldo, void* stream);
 
+/* LDEPooling.forward (libs/nnet/pooling.py:130-162): x (B,T,C) fp32, dictionary mu (C,K) fp32 as the state_dict stores
+ * it, neg_beta[k] = -(s_k^2 + eps); w[t,k] = softmax_k(neg_beta[k] * sum_c (x[t,c] - mu[c,k])^2) (distances summed directly
+ * in fp32), out[b, c*K + k] = mean_t w[t,k] (x[t,c] - mu[c,k]); out (B, C*K) fp32, optionally also split planes.
+ * w_scratch: (B*T, K) fp32.  K <= 64. */
+int xvb_lde_pool(const float* x, int64_t ldx, int B, int T, int C, const float* mu, int K, const float* neg_beta,
+                 float* w_scratch, float* out, uint16_t* out_hi, uint16_t* out_lo, int64_t ldo, void* stream);
+
 /* Segment-level affine on CUDA cores, fp32 throughout: y[b,n] = epi(bias[n] + sum_k w[n,k] x[b,k]) for the few rows
  * (one per utterance) of the SE gate's two 1x1 convolutions (ecapa_tdnn_xvector.py:97-111), the time-constant half of
  * the attention's first conv (:179-181) and fc2 (:412-422).  x (B, >=K) fp32 pitch ldx, w (N, K) fp32 exactly as the

@@ -207,11 +207,22 @@ def attention_pooling(x, alpha, num_head, global_heads, stddev_attention=True, e
     return torch.cat((mean, torch.sqrt(var.clamp(min=eps))), dim=1)
 
 
+def lde_pooling(x, mu, s, eps=1.0e-10):
+    """LDEPooling.forward, pooling.py:148-159: r = x^T[..., None] - mu; w = softmax over clusters of
+    -(s^2 + eps) * sum_c r^2; e = mean over T of w * r; (B, C * c_num, 1)."""
+    r = x.transpose(1, 2).unsqueeze(3) - mu
+    w = torch.softmax(-(s ** 2 + eps) * torch.sum(r ** 2, dim=2, keepdim=True), dim=3)
+    e = torch.mean(w * r, dim=1)
+    return e.reshape(-1, mu.shape[0] * mu.shape[1], 1)
+
+
 def snowdar_pooling(x, sd, pooling, params, num_nodes):
     """Xvector.init's pooling switch, snowdar_xvector.py:119-136, for statistics / attentive / multi-head /
     multi-resolution."""
     if pooling == "statistics":
         return statistics_pooling(x)
+    if pooling == "lde":             # :121-122 -> LDEPooling(num_nodes, c_num=num_head)
+        return lde_pooling(x, sd["stats.mu"], sd["stats.s"])
     p = dict(ATTENTION_DEFAULTS)
     p.update(params)
     if pooling == "attentive":       # :124-126 -> AttentiveStatisticsPooling(:327-337): one head, shared weight, bias
@@ -242,13 +253,16 @@ def snowdar_xvector_forward(sd, x, extracted_embedding="far", extend=False, pool
     return relu_bn_tdnn_layer(x, sd, "tdnn7", [0])
 
 
-def snowdar_pooling_spec(pooling, params, num_nodes=1500):
+def snowdar_pooling_spec(pooling, params, num_nodes=1500):   # num_nodes may also come inside params, like the blueprint's
     """(state_dict entries of `stats`, output dim) for the attention poolings (registration order: [t], first_affine,
     last_affine -- pooling.py:245-298)."""
     if pooling == "statistics":
         return [], 2 * num_nodes
     p = dict(ATTENTION_DEFAULTS)
     p.update(params)
+    if pooling == "lde":             # parameters mu (C, c_num) ~ randn, s (c_num,) ~ ones (pooling.py:143-144)
+        return [("stats.mu", (num_nodes, p["num_head"]), ("lde_mu", 0)), ("stats.s", (p["num_head"],), ("lde_s", 0))], \
+            num_nodes * p["num_head"]
     if pooling == "attentive":
         heads, split, share, bias, temp = 1, True, True, True, False
     elif pooling == "multi-head":
@@ -279,8 +293,8 @@ def snowdar_xvector_spec(inputs_dim, extend=False, bn_affine=False, pooling="sta
           [("tdnn2", 512, 512, [-2, 0, 2])] + ([("ex_tdnn2", 512, 512, [0])] if extend else []) + \
           [("tdnn3", 512, 512, [-3, 0, 3])] + \
           ([("ex_tdnn3", 512, 512, [0]), ("ex_tdnn4", 512, 512, [-4, 0, 4]), ("ex_tdnn5", 512, 512, [0])] if extend else []) + \
-          [("tdnn4", 512, 512, [0]), ("tdnn5", 512, 1500, [0])]
-    pool_spec, stats_dim = snowdar_pooling_spec(pooling, pooling_params or {})
+          [("tdnn4", 512, 512, [0]), ("tdnn5", 512, (pooling_params or {}).get("num_nodes", 1500), [0])]
+    pool_spec, stats_dim = snowdar_pooling_spec(pooling, pooling_params or {}, (pooling_params or {}).get("num_nodes", 1500))
     spec = []
     for name, cin, cout, ctx in reg:
         spec += _affine_entries(name, cin, cout, ctx) + _bn_entries(name + ".batchnorm", cout, affine=bn_affine)
@@ -528,6 +542,10 @@ def make_state_dict(spec, seed):
         elif kind == "nbt":
             sd[key] = torch.tensor(1000, dtype=torch.long)
             continue
+        elif kind == "lde_mu":
+            v = (0.6 * rng.standard_normal(shape)).astype(np.float32)
+        elif kind == "lde_s":
+            v = rng.uniform(0.05, 0.15, shape).astype(np.float32)      # beta = s^2 ~ 0.01: soft assignments over C ~ 1e2..1e3 dims
         elif kind == "temp_fixed":
             sd[key] = torch.tensor([[[[max(1, (i // 2) * 5)]] for i in range(shape[1])]])
             continue

@@ -23,6 +23,7 @@ POOLING_CASES = {
     "mha_share": ("multi-head", {"num_head": 4}, 313),                                # the paper's form: shared weights
     "mha_full": ("multi-head", {"num_head": 4, "share": False, "affine_layers": 2}, 314),
     "mres": ("multi-resolution", {"num_head": 4, "temperature": True, "affine_layers": 2}, 315),
+    "lde": ("lde", {"num_head": 12, "num_nodes": 200}, 316),                        # LDEPooling(200, c_num=12): 2400-d encoding
 }
 
 

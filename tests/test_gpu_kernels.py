@@ -418,6 +418,7 @@ SNOWDAR_POOLING_CASES = {
     "mha_share": ("multi-head", {"num_head": 4}, 313),
     "mha_full": ("multi-head", {"num_head": 4, "share": False, "affine_layers": 2}, 314),
     "mres": ("multi-resolution", {"num_head": 4, "temperature": True, "affine_layers": 2}, 315),
+    "lde": ("lde", {"num_head": 12, "num_nodes": 200}, 316),                        # LDEPooling(200, c_num=12): 2400-d encoding
 }
 
 
@@ -439,7 +440,25 @@ def test_snowdar_attention_poolings_match_reference_golden(golden, cname):
         assert rel(m.extract_embedding_batch(feats).cpu().numpy(), want) < EMB_TOL, (cname, pos)
         assert rel(m.extract_embedding(feats[1]).numpy(), want[1]) < EMB_TOL, (cname, pos)
     with pytest.raises(NotImplementedError):
-        Xvector(40, 10, pooling="lde")
+        Xvector(40, 10, pooling="xi-postmean-softplus2")
+
+
+@pytest.mark.parametrize("B,T,C,K", [(3, 77, 200, 12), (2, 130, 64, 64), (1, 5, 24, 1), (2, 33, 20, 7)])
+def test_lde_pool_kernels_vs_oracle(B, T, C, K):
+    """xvb_lde_pool against oracle.lde_pooling (LDEPooling.forward, pooling.py:148-159): cluster counts that do and do not
+    fill the eight thread groups, more than one 64-frame staging chunk, a strided input view."""
+    from asv_subtools_b200 import ops
+    rng = np.random.RandomState(C + K)
+    x = (rng.standard_normal((B, T, C)) * 0.6).astype(np.float32)
+    mu = (rng.standard_normal((C, K)) * 0.6).astype(np.float32)
+    s = rng.uniform(0.05, 0.3, K).astype(np.float32)
+    xw = torch.zeros(B, T, C + 4, device="cuda")
+    xw[..., :C] = torch.from_numpy(x).cuda()
+    neg_beta = torch.from_numpy(-(s ** 2 + np.float32(1e-10))).cuda()
+    got, planes = ops.lde_pool(xw[..., :C], torch.from_numpy(mu).cuda(), neg_beta, planes=True)
+    ref = onn.lde_pooling(torch.from_numpy(x).transpose(1, 2), torch.from_numpy(mu), torch.from_numpy(s)).squeeze(2).numpy()
+    assert got.shape == ref.shape and rel(got.cpu().numpy(), ref) < 5e-6
+    assert rel(planes.float().view(B, -1)[:, :C * K].cpu().numpy(), ref) < 2e-5
 
 
 @pytest.mark.parametrize("heads,gdiv_kind,global_heads,unweighted", [(1, "share", False, False), (4, "share", False, True),
