@@ -265,7 +265,7 @@ def test_native_ecapa_extractor_equals_python_orchestration_and_model_file(tmp_p
                 ex2 = mod.NativeEcapaExtractor.load(path)
                 assert ex2.feat_dim == 80 and ex2.embed_dim == 192
                 assert torch.equal(ex2.extract(feats), outs[native, pos])
-                assert ex.last_launches > 30
+                assert ex.last_launches >= 30
             m.invalidate()
     for pos in ("near", "near_affine"):
         assert torch.equal(outs["1", pos], outs["0", pos]), pos
