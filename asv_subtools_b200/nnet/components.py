@@ -18,8 +18,9 @@ class TdnnAffine(torch.nn.Module):
         for i in range(len(context) - 1):
             if context[i] >= context[i + 1]:
                 raise ValueError("Context tuple {} is invalid, such as the order.".format(context))
-        if stride != 1 or not pad or norm_w or norm_f:
-            raise NotImplementedError("B200 TdnnAffine supports stride=1, pad=True, norm_w/f=False only")
+        if stride != 1 or not pad or norm_f:
+            raise NotImplementedError("B200 TdnnAffine supports stride=1, pad=True, norm_f=False only")
+        self.norm_w = bool(norm_w)
         if input_dim % groups != 0 or output_dim % groups != 0:
             raise ValueError("input_dim {} and output_dim {} must be divisible by groups {}".format(input_dim, output_dim, groups))
         self.input_dim, self.output_dim, self.context, self.groups = input_dim, output_dim, list(context), groups
@@ -41,6 +42,8 @@ class TdnnAffine(torch.nn.Module):
         """(output_dim, input_dim, tot_context) fp32: the stored weight, or its block-diagonal expansion for groups > 1
         (group g maps input channels [g*Cin/G, (g+1)*Cin/G) to output channels [g*Cout/G, (g+1)*Cout/G), conv1d's rule)."""
         w = self.weight.detach().float()
+        if self.norm_w:      # F.normalize(filters, dim=1) at forward time (components.py:139-140): unit L2 per (output, tap)
+            w = torch.nn.functional.normalize(w, dim=1)
         if self.groups == 1:
             return w
         g, ci, co = self.groups, self.input_dim // self.groups, self.output_dim // self.groups
@@ -59,8 +62,9 @@ class ReluBatchNormTdnnLayer(torch.nn.Module):
         super().__init__()
         if affine_type != "tdnn":
             raise NotImplementedError("only affine_type='tdnn' is supported")
-        if options.get("bn-relu", False) or options.get("ln_replace", False):
-            raise NotImplementedError("bn-relu / LayerNorm variants are not on the B200 path")
+        if options.get("ln_replace", False):
+            raise NotImplementedError("the LayerNorm variant is not on the B200 path")
+        self.bn_relu = bool(options.get("bn-relu", False))     # affine -> BN -> ReLU instead of affine -> ReLU -> BN (:386-396)
         nonlin = options.get("nonlinearity", "relu")
         if nonlin not in ("relu", "", None, False):
             raise NotImplementedError("nonlinearity {!r} is not on the B200 path".format(nonlin))
@@ -76,6 +80,20 @@ class ReluBatchNormTdnnLayer(torch.nn.Module):
         """eval-mode BatchNorm as (scale, shift) float32 arrays: y = x*scale + shift with
         scale = gamma / sqrt(running_var + eps), shift = beta - running_mean*scale."""
         return fold_batchnorm(self.batchnorm)
+
+    def export(self):
+        """(weight (Cout, Cin, tot) fp32 tensor, bias | None, scale | None, shift | None, relu) in the kernel's epilogue
+        order +bias -> ReLU -> BN.  The "bn-relu" order (BN straight after the affine, then ReLU) has no epilogue of its own:
+        eval-mode BN after an affine IS an affine, so it is folded into weight and bias (W' = s W, b' = s b + t) in float64."""
+        w = self.affine.dense_weight()
+        b = self.affine.bias.detach().float() if self.affine.bias is not None else None
+        scale, shift = self.folded_bn()
+        if not self.bn_relu or scale is None:
+            return w, b, scale, shift, self.relu
+        s64, t64 = torch.from_numpy(scale.astype(np.float64)), torch.from_numpy(shift.astype(np.float64))
+        w2 = (w.double().cpu() * s64.view(-1, 1, 1)).float().to(w.device)
+        b2 = ((b.double().cpu() if b is not None else 0.0) * s64 + t64).float().to(w.device)
+        return w2, b2, None, None, self.relu
 
 
 class FTdnnBlock(torch.nn.Module):

@@ -176,24 +176,24 @@ def build_tdnn_extractor(model, inputs_dim, frame_layers, stats, tdnn6, tdnn7, e
     ex = ops.Extractor(inputs_dim)
 
     def arrays(layer):
-        w = layer.affine.weight.detach().float().cpu().numpy()
-        b = layer.affine.bias.detach().float().cpu().numpy() if layer.affine.bias is not None else None
-        scale, shift = layer.folded_bn()
-        return w, b, scale, shift
+        w, b, scale, shift, _ = layer.export()         # "bn-relu" layers come back with the BatchNorm folded in
+        return w.cpu().numpy(), (b.cpu().numpy() if b is not None else None), scale, shift
 
     for layer in frame_layers:
         w, b, scale, shift = arrays(layer)
         ex.add_frame_layer(w, b, layer.affine.context, scale, shift, relu=layer.relu)
     w, b, scale, shift = arrays(tdnn6)
-    if extracted_embedding == "far":
-        ex.add_segment_layer(w, b)
+    if extracted_embedding == "far":               # tdnn6.affine alone: the stored weight, whatever the layer's BN order
+        ex.add_segment_layer(tdnn6.affine.dense_weight().cpu().numpy(),
+                             tdnn6.affine.bias.detach().float().cpu().numpy() if tdnn6.affine.bias is not None else None)
     else:
         ex.add_segment_layer(w, b, scale, shift, relu=tdnn6.relu)
         w7, b7, s7, t7 = arrays(tdnn7)
         if extracted_embedding == "near_full":     # the whole last layer (snowdar_xvector.py:291-294)
             ex.add_segment_layer(w7, b7, s7, t7, relu=tdnn7.relu)
-        else:
-            ex.add_segment_layer(w7, b7)
+        else:                                      # tdnn7.affine alone
+            ex.add_segment_layer(tdnn7.affine.dense_weight().cpu().numpy(),
+                                 tdnn7.affine.bias.detach().float().cpu().numpy() if tdnn7.affine.bias is not None else None)
     ex.finalize(pooling_eps=stats.eps)
     return ex
 
@@ -203,11 +203,18 @@ class _PackedAffine:
     block-diagonal expansion for groups > 1, output rows zero-padded to a multiple of `pad_to`, `row_scale` folded into
     weight and bias (per-head temperature of the attention logits)."""
 
-    def __init__(self, affine, device, bn=None, relu=False, pad_to=8, row_scale=None):
+    @classmethod
+    def from_layer(cls, layer, device):
+        """A whole ReluBatchNormTdnnLayer (its `export()` folds the BatchNorm in for the "bn-relu" order)."""
+        w, b, scale, shift, relu = layer.export()
+        return cls(layer.affine, device, relu=relu, arrays=(w, b, scale, shift))
+
+    def __init__(self, affine, device, bn=None, relu=False, pad_to=8, row_scale=None, arrays=None):
         from .. import ops
         from .components import fold_batchnorm
-        w = affine.dense_weight().to(device)
-        b = affine.bias.detach().float().to(device) if affine.bias is not None else None
+        w = (arrays[0] if arrays is not None else affine.dense_weight()).to(device)
+        b = arrays[1] if arrays is not None else (affine.bias.detach().float() if affine.bias is not None else None)
+        b = b.to(device) if b is not None else None
         if row_scale is not None:
             w = w * row_scale.to(device).view(-1, 1, 1)
             b = b * row_scale.to(device) if b is not None else None
@@ -219,7 +226,7 @@ class _PackedAffine:
         self.context, self.cout = list(affine.context), w.shape[0]
         self.w = ops.pack_tdnn_weight(w.contiguous(), self.context)
         self.bias = b.contiguous() if b is not None else None
-        scale, shift = fold_batchnorm(bn)
+        scale, shift = (arrays[2], arrays[3]) if arrays is not None else fold_batchnorm(bn)
         if scale is not None and pad:                            # padded output channels come out as exact zeros
             scale, shift = np.concatenate([scale, np.zeros(pad, np.float32)]), np.concatenate([shift, np.zeros(pad, np.float32)])
         self.scale = torch.from_numpy(scale).to(device) if scale is not None else None
@@ -248,7 +255,7 @@ class AttentionPoolingExtractor:
     def __init__(self, model, inputs_dim, frame_layers, stats, tdnn6, tdnn7, position):
         dev = model.device_for_extraction()
         self.feat_dim = inputs_dim
-        self.frames = [_PackedAffine(l.affine, dev, l.batchnorm, l.relu) for l in frame_layers]
+        self.frames = [_PackedAffine.from_layer(l, dev) for l in frame_layers]
         self.lde = None
         if hasattr(stats, "mu"):                                 # LDEPooling: no attention network
             self.lde = (stats.mu.detach().float().to(dev).contiguous(), stats.neg_beta().to(dev).contiguous())
@@ -270,9 +277,9 @@ class AttentionPoolingExtractor:
         if position == "far":
             self.segment = [_PackedAffine(tdnn6.affine, dev)]
         else:
-            self.segment = [_PackedAffine(tdnn6.affine, dev, tdnn6.batchnorm, tdnn6.relu)]
+            self.segment = [_PackedAffine.from_layer(tdnn6, dev)]
             if position == "near_full":
-                self.segment.append(_PackedAffine(tdnn7.affine, dev, tdnn7.batchnorm, tdnn7.relu))
+                self.segment.append(_PackedAffine.from_layer(tdnn7, dev))
             else:
                 self.segment.append(_PackedAffine(tdnn7.affine, dev))
         self.embed_dim = self.segment[-1].cout_real

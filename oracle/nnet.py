@@ -57,10 +57,20 @@ def batchnorm_eval(x, sd, prefix):
                         training=False, momentum=0.0, eps=BN_EPS)
 
 
-def relu_bn_tdnn_layer(x, sd, prefix, context, relu=True, bn=True):
+def relu_bn_tdnn_layer(x, sd, prefix, context, relu=True, bn=True, bn_relu=False, norm_w=False):
     """ReluBatchNormTdnnLayer.forward = affine -> ReLU -> BatchNorm (order: ReLU first),
-    components.py:410-431, :434-461."""
-    y = tdnn_affine(x, sd[prefix + ".affine.weight"], sd[prefix + ".affine.bias"], context)
+    components.py:410-431, :434-461; bn_relu: the other order, affine -> BatchNorm -> ReLU (:386-396, :398-403);
+    norm_w: F.normalize(filters, dim=1) inside the affine (:139-140)."""
+    w = sd[prefix + ".affine.weight"]
+    if norm_w:
+        left, right, tot = context_span(context)
+        mask = torch.tensor([[[1.0 if i in context else 0.0 for i in range(left, right + 1)]]], dtype=w.dtype)
+        w = F.normalize(w * mask, dim=1)
+    y = tdnn_affine(x, w, sd[prefix + ".affine.bias"], context)
+    if bn_relu:
+        if bn:
+            y = batchnorm_eval(y, sd, prefix + ".batchnorm")
+        return F.relu(y) if relu else y
     if relu:
         y = F.relu(y)
     if bn:
@@ -239,18 +249,19 @@ def snowdar_pooling(x, sd, pooling, params, num_nodes):
     raise ValueError(pooling)
 
 
-def snowdar_xvector_forward(sd, x, extracted_embedding="far", extend=False, pooling="statistics", pooling_params=None):
+def snowdar_xvector_forward(sd, x, extracted_embedding="far", extend=False, pooling="statistics", pooling_params=None,
+                            bn_relu=False):
     """snowdar_xvector.py:262-294: far = tdnn6.affine; near_affine = tdnn6 -> tdnn7.affine; near = tdnn6 -> tdnn7
-    (the whole layer, ReLU and BatchNorm included)."""
+    (the whole layer, ReLU and BatchNorm included).  bn_relu: tdnn_layer_params={"bn-relu": True}."""
     for name, ctx in snowdar_layers(extend):
-        x = relu_bn_tdnn_layer(x, sd, name, ctx)
+        x = relu_bn_tdnn_layer(x, sd, name, ctx, bn_relu=bn_relu)
     x = snowdar_pooling(x, sd, pooling, pooling_params or {}, x.shape[1])
     if extracted_embedding == "far":
         return tdnn_affine(x, sd["tdnn6.affine.weight"], sd["tdnn6.affine.bias"], [0])
-    x = relu_bn_tdnn_layer(x, sd, "tdnn6", [0])
+    x = relu_bn_tdnn_layer(x, sd, "tdnn6", [0], bn_relu=bn_relu)
     if extracted_embedding == "near_affine":
         return tdnn_affine(x, sd["tdnn7.affine.weight"], sd["tdnn7.affine.bias"], [0])
-    return relu_bn_tdnn_layer(x, sd, "tdnn7", [0])
+    return relu_bn_tdnn_layer(x, sd, "tdnn7", [0], bn_relu=bn_relu)
 
 
 def snowdar_pooling_spec(pooling, params, num_nodes=1500):   # num_nodes may also come inside params, like the blueprint's

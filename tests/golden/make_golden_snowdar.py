@@ -56,6 +56,17 @@ def main():
             model.load_state_dict(sd, strict=True)
             model.eval()
             out["{}_{}".format(cname, pos)] = np.stack([model.extract_embedding(feats[i]).numpy() for i in range(3)])
+    # the other BatchNorm order: tdnn_layer_params={"bn-relu": True} (components.py:386-403), BatchNorm with affine parameters
+    tlp = {"bn-relu": True, "bn_params": {"momentum": 0.5, "affine": True, "track_running_stats": True}}
+    sd = onn.make_state_dict(onn.snowdar_xvector_spec(40, bn_affine=True), 317)
+    feats = onn.synthetic_feats(3, 120, 40, 1317)
+    for pos in ("far", "near_affine", "near"):
+        model = utils.create_model_from_py(
+            "/root/reference/pytorch/model/snowdar_xvector.py",
+            'Xvector(40,10,training=False,extracted_embedding="{}",tdnn_layer_params={!r})'.format(pos, tlp))
+        model.load_state_dict(sd, strict=True)
+        model.eval()
+        out["bnrelu_{}".format(pos)] = np.stack([model.extract_embedding(feats[i]).numpy() for i in range(3)])
     np.savez_compressed(os.path.join(HERE, "snowdar.npz"), **out)
     print("snowdar.npz ok", {k: v.shape for k, v in out.items()})
 

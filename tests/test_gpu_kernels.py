@@ -443,6 +443,50 @@ def test_snowdar_attention_poolings_match_reference_golden(golden, cname):
         Xvector(40, 10, pooling="xi-postmean-softplus2")
 
 
+def test_snowdar_bn_relu_order_and_weight_normalisation(golden):
+    """tdnn_layer_params={"bn-relu": True} (affine -> BatchNorm -> ReLU, components.py:386-403; folded into weight and bias
+    at hand-over) against the reference's own outputs, through the native extractor (statistics pooling) and through the
+    op-by-op extractor (attentive pooling, against the oracle); TdnnAffine(norm_w=True) (components.py:139-140) layer
+    against the oracle."""
+    from asv_subtools_b200 import ops
+    from asv_subtools_b200.model.snowdar_xvector import Xvector
+    from asv_subtools_b200.nnet import ReluBatchNormTdnnLayer
+    from asv_subtools_b200.nnet.components import TdnnAffine
+    g = golden("snowdar")
+    tlp = {"bn-relu": True, "bn_params": {"momentum": 0.5, "affine": True, "track_running_stats": True}}
+    sd = onn.make_state_dict(onn.snowdar_xvector_spec(40, bn_affine=True), 317)
+    feats = onn.synthetic_feats(3, 120, 40, 1317)
+    for pos in ("far", "near_affine", "near"):
+        m = Xvector(40, 10, training=False, extracted_embedding=pos, tdnn_layer_params=tlp)
+        m.load_state_dict(sd, strict=True)
+        m.cuda().eval()
+        assert rel(m.extract_embedding_batch(feats).cpu().numpy(), g["bnrelu_{}".format(pos)]) < EMB_TOL, pos
+    pp = {"affine_layers": 2, "hidden_size": 64}
+    sd2 = onn.make_state_dict(onn.snowdar_xvector_spec(40, bn_affine=True, pooling="attentive", pooling_params=pp), 318)
+    m = Xvector(40, 10, training=False, extracted_embedding="near", tdnn_layer_params=tlp, pooling="attentive", pooling_params=pp)
+    m.load_state_dict(sd2, strict=True)
+    m.cuda().eval()
+    with torch.no_grad():
+        ref = onn.snowdar_xvector_forward(sd2, torch.from_numpy(feats).transpose(1, 2), "near", pooling="attentive",
+                                          pooling_params=pp, bn_relu=True).squeeze(2).numpy()
+    assert rel(m.extract_embedding_batch(feats).cpu().numpy(), ref) < EMB_TOL
+    # norm_w
+    aff = TdnnAffine(48, 64, context=[-2, 0, 2], norm_w=True)
+    torch.manual_seed(5)
+    torch.nn.init.normal_(aff.weight, 0.0, 0.3)
+    torch.nn.init.normal_(aff.bias, 0.0, 0.1)
+    x = torch.randn(2, 48, 37)
+    ref = onn.relu_bn_tdnn_layer(x, {"l.affine.weight": aff.weight.detach(), "l.affine.bias": aff.bias.detach()}, "l", [-2, 0, 2],
+                                 relu=False, bn=False, norm_w=True).transpose(1, 2).numpy()
+    w = ops.pack_tdnn_weight(aff.dense_weight().cuda().contiguous(), [-2, 0, 2])
+    xin = ops.split_f32(x.transpose(1, 2).contiguous().cuda())
+    _, y = ops.tdnn_affine(xin, w, 64, [-2, 0, 2], bias=aff.bias.detach().cuda(), out_planes=False, out_f32=True)
+    assert rel(y.cpu().numpy(), ref) < 3e-5
+    with pytest.raises(NotImplementedError):
+        TdnnAffine(48, 64, norm_f=True)
+    assert isinstance(ReluBatchNormTdnnLayer(8, 8, **tlp).export()[2], type(None))
+
+
 @pytest.mark.parametrize("B,T,C,K", [(3, 77, 200, 12), (2, 130, 64, 64), (1, 5, 24, 1), (2, 33, 20, 7)])
 def test_lde_pool_kernels_vs_oracle(B, T, C, K):
     """xvb_lde_pool against oracle.lde_pooling (LDEPooling.forward, pooling.py:148-159): cluster counts that do and do not

@@ -184,6 +184,11 @@ def test_blueprints_keep_the_reference_constructor_surface():
     cases = [("xvector.py", 'Xvector(23,10,training=False,extracted_embedding="far")', onn.xvector_spec(23)),
              ("extended_xvector.py", 'ExtendedXvector(40,10,training=False,extracted_embedding="near")', onn.extended_xvector_spec(40)),
              ("snowdar_xvector.py", 'Xvector(40,10,extend=True,training=False,extracted_embedding="near")', onn.snowdar_xvector_spec(40, extend=True)),
+             ("snowdar_xvector.py", 'Xvector(40,10,training=False,pooling="multi-head",pooling_params={"num_head":4,"share":False,'
+              '"affine_layers":2})', onn.snowdar_xvector_spec(40, pooling="multi-head",
+                                                               pooling_params={"num_head": 4, "share": False, "affine_layers": 2})),
+             ("snowdar_xvector.py", 'Xvector(40,10,training=False,pooling="lde",pooling_params={"num_head":12,"num_nodes":200})',
+              onn.snowdar_xvector_spec(40, pooling="lde", pooling_params={"num_head": 12, "num_nodes": 200})),
              ("factored_xvector.py", 'Xvector(40,10,training=False,extracted_embedding="far")', onn.factored_xvector_spec(40)),
              ("ecapa_tdnn_xvector.py", 'ECAPA_TDNN(80,10,training=False,extracted_embedding="near",ecapa_params={"channels":1024,'
               '"embd_dim":192,"mfa_conv":1536},fc2_params={"nonlinearity":"","bn":True,"bn_params":{"momentum":0.5,"affine":False,'

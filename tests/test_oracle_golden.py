@@ -293,6 +293,17 @@ def test_snowdar_attention_poolings_oracle_matches_reference(golden):
             assert rel(emb, g["{}_{}".format(cname, pos)]) < RTOL, (cname, pos)
 
 
+def test_snowdar_bn_relu_order_oracle_matches_reference(golden):
+    """tdnn_layer_params={"bn-relu": True}: affine -> BatchNorm -> ReLU (components.py:386-403)."""
+    g = golden("snowdar")
+    sd = onn.make_state_dict(onn.snowdar_xvector_spec(40, bn_affine=True), 317)
+    feats = onn.synthetic_feats(3, 120, 40, 1317)
+    for pos in ("far", "near_affine", "near"):
+        emb = np.stack([onn.extract_embedding(lambda x: onn.snowdar_xvector_forward(sd, x, pos, bn_relu=True), feats[i]).numpy()
+                        for i in range(3)])
+        assert rel(emb, g["bnrelu_{}".format(pos)]) < RTOL, pos
+
+
 def test_coral_adaptation_oracle_matches_reference(golden):
     from oracle import plda_train as opt
     g = golden("plda_train")
