@@ -77,6 +77,8 @@ struct xvb_ecapa {
   Planes in, X, Hh, R, Z, N, CAT, M, A1, gp, s1, zm, pp;
   float *MF = nullptr, *LOG = nullptr, *gate = nullptr, *ub = nullptr, *zmean = nullptr, *gstat = nullptr, *pstat = nullptr;
   float* s1f = nullptr;   // (B, se_dim) fp32: hidden vector of the SE gate
+  float* f1 = nullptr;    // (B, fc1_dim) fp32: output of fc1 when the model has one
+  int fc1_dim = 0;
   int last_launches = 0;
   float* h_feats = nullptr; float* h_emb = nullptr;   // device staging of xvb_ecapa_extract_host
   size_t h_feats_cap = 0, h_emb_cap = 0;
@@ -226,8 +228,22 @@ extern "C" int xvb_ecapa_finalize(xvb_ecapa_t* h) {
     }
   }
   if ((rc = need("mfa", 3 * C, h->D, 1)) || (rc = need("att_x", h->D, h->H, 1)) || (rc = need("att_gs", 2 * h->D, h->H, 1)) ||
-      (rc = need("att2", h->H, h->D, 1)) || (rc = need("fc2", 2 * h->D, h->E, 1)))
+      (rc = need("att2", h->H, h->D, 1)))
     return rc;
+  // segment level (ecapa_tdnn_xvector.py:412-422): [fc1 ->] [fc2]; "far" hands over fc1 alone, fc1=False fc2 alone
+  if (const ELayer* fc1 = find(h, "fc1")) {
+    XVB_CHECK_ARG(fc1->Cin == 2 * h->D && fc1->ntaps == 1 && fc1->w_f32, "xvb_ecapa_finalize: 'fc1' must be a one-tap layer over the %d pooled statistics", 2 * h->D);
+    if (find(h, "fc2")) {
+      rc = need("fc2", fc1->Cout, h->E, 1);
+      if (rc) return rc;
+    } else {
+      XVB_CHECK_ARG(fc1->Cout == h->E, "xvb_ecapa_finalize: 'fc1' alone must produce the %d-d embedding", h->E);
+    }
+    h->fc1_dim = fc1->Cout;
+  } else {
+    rc = need("fc2", 2 * h->D, h->E, 1);
+    if (rc) return rc;
+  }
   {
     const ELayer* L0 = find(h, "layer1");
     bool consecutive = L0->ntaps > 1 && L0->ctx[0] <= 0 && L0->ctx[L0->ntaps - 1] >= 0;
@@ -259,7 +275,8 @@ static int reserve(xvb_ecapa* h, int B, int T) {
       (rc = h->planes(&h->gp, nb, 2 * D)) || (rc = h->planes(&h->s1, nb, h->se_dim)) || (rc = h->planes(&h->zm, nb, C)) ||
       (rc = h->planes(&h->pp, nb, 2 * D)) || (rc = h->f32(&h->MF, nf * D)) || (rc = h->f32(&h->LOG, nf * D)) ||
       (rc = h->f32(&h->gate, nb * C)) || (rc = h->f32(&h->ub, nb * h->H)) || (rc = h->f32(&h->zmean, nb * C)) ||
-      (rc = h->f32(&h->gstat, nb * 2 * D)) || (rc = h->f32(&h->pstat, nb * 2 * D)) || (rc = h->f32(&h->s1f, nb * (size_t)h->se_dim)))
+      (rc = h->f32(&h->gstat, nb * 2 * D)) || (rc = h->f32(&h->pstat, nb * 2 * D)) || (rc = h->f32(&h->s1f, nb * (size_t)h->se_dim)) ||
+      (h->fc1_dim && (rc = h->f32(&h->f1, nb * (size_t)h->fc1_dim))))
     return rc;
   h->cap_frames = (long long)nf;
   h->cap_B = (int)nb;
@@ -373,7 +390,16 @@ extern "C" int xvb_ecapa_extract(xvb_ecapa_t* h, const float* feats, int B, int 
   r = Run{}; r.B = B; r.T = T; r.L = L("att2"); r.x = h->A1; r.y_f32 = h->LOG; r.ldyf = D;
   if ((rc = launch(r, stream))) return rc;
   if ((rc = xvb_attn_stats_pool(h->LOG, D, h->MF, D, B, T, D, 1e-5f, h->pstat, h->pp.hi, h->pp.lo, 2 * D, stream))) return rc;
-  if (small_ok(L("fc2"))) {
+  if (const ELayer* fc1 = L("fc1")) {              // fc1 [-> fc2] on CUDA cores (fp32)
+    const ELayer* fc2 = L("fc2");
+    rc = small_layer(fc1, h->pstat, 2 * D, B, fc2 ? h->f1 : emb, fc1->Cout, 0, stream);
+    if (rc) return rc;
+    if (fc2) {
+      XVB_CHECK_ARG(fc2->w_f32, "xvb_ecapa_extract: 'fc2' after 'fc1' needs an input width that is a multiple of 4");
+      rc = small_layer(fc2, h->f1, fc1->Cout, B, emb, h->E, 0, stream);
+      if (rc) return rc;
+    }
+  } else if (small_ok(L("fc2"))) {
     rc = small_layer(L("fc2"), h->pstat, 2 * D, B, emb, h->E, 0, stream);
       if (rc) return rc;
   } else {
@@ -434,7 +460,7 @@ static int ecapa_ensure_lanes(xvb_ecapa* h) {
   XVB_CUDA(cudaEventCreateWithFlags(&h->ev_lane_start, cudaEventDisableTiming));
   xvb_ecapa* c = new xvb_ecapa();
   c->feat_dim = h->feat_dim; c->ldf = h->ldf; c->C = h->C; c->D = h->D; c->H = h->H; c->E = h->E; c->scale = h->scale;
-  c->se_dim = h->se_dim; c->finalized = true;
+  c->se_dim = h->se_dim; c->fc1_dim = h->fc1_dim; c->finalized = true;
   for (int b = 0; b < 3; ++b) {
     c->dilation[b] = h->dilation[b];
     c->res_w_hi[b] = h->res_w_hi[b]; c->res_w_lo[b] = h->res_w_lo[b]; c->res_bias[b] = h->res_bias[b];

@@ -104,10 +104,9 @@ class ECAPA_TDNN(TopVirtualNnet):
                       "bn_params": {"momentum": 0.5, "affine": True, "track_running_stats": True}}
         if pooling != "ecpa-attentive":
             raise NotImplementedError("B200 ECAPA implements pooling='ecpa-attentive' (the reference default)")
-        if fc1:
-            raise NotImplementedError("B200 ECAPA implements fc1=False (the c1024 recipe)")
         ecapa_params = _merge(default_ecapa, ecapa_params)
         pooling_params = _merge(default_pool, pooling_params)
+        fc1_params = _merge(default_fc, fc1_params)
         fc2_params = _merge(default_fc, fc2_params)
         self.inputs_dim = inputs_dim
         self.use_step, self.step_params = use_step, step_params
@@ -121,16 +120,16 @@ class ECAPA_TDNN(TopVirtualNnet):
         self.mfa = ReluBatchNormTdnnLayer(channels * 3, mfa_conv, **ecapa_params)
         self.stats = AttentiveStatsPool(mfa_conv, pooling_params["hidden_size"], pooling_params["time_attention"])
         self.bn_stats = nn.BatchNorm1d(mfa_conv * 2, **ecapa_params["bn_params"])
-        self.fc1 = None
-        self.fc2 = ReluBatchNormTdnnLayer(mfa_conv * 2, self.embd_dim, **fc2_params)
+        self.fc1 = ReluBatchNormTdnnLayer(mfa_conv * 2, self.embd_dim, **fc1_params) if fc1 else None      # :286-287
+        self.fc2 = ReluBatchNormTdnnLayer(self.embd_dim if fc1 else mfa_conv * 2, self.embd_dim, **fc2_params)   # :326-333
         self.transform_keys = ["layer1", "layer2", "layer3", "layer4", "stats", "mfa", "bn_stats", "fc1", "fc2", "loss"]
         if margin_loss and transfer_from == "softmax_loss":
             self.rename_transform_keys = {"loss.affine.weight": "loss.weight"}
 
     def build_extractor(self):
-        if self.extracted_embedding not in ("near", "near_affine"):
-            if self.extracted_embedding == "far":
-                raise AssertionError("extracted_embedding='far' needs fc1 (ecapa_tdnn_xvector.py:415-416)")
+        if self.extracted_embedding == "far":
+            assert self.fc1 is not None, "extracted_embedding='far' needs fc1 (ecapa_tdnn_xvector.py:415-416)"
+        elif self.extracted_embedding not in ("near", "near_affine"):
             raise TypeError("Expected far or near position, but got {}".format(self.extracted_embedding))
         dev = self.device_for_extraction()
         if os.environ.get("XVB_ECAPA_NATIVE", "1") == "0" or self.layer1.affine.output_dim != 1024:
@@ -203,14 +202,30 @@ def _named_layers(m):
     out.append(("att_x", np.ascontiguousarray(w0[:, :c]), None, [0], s, t, True))
     out.append(("att_gs", np.ascontiguousarray(w0[:, c:]), f(att[0].bias), [0], None, None, False))
     out.append(("att2", f(att[4].weight), f(att[4].bias), [0], None, None, False))
+    out += _segment_layers(m)
+    return out
+
+
+def _segment_layers(m):
+    """[fc1 ->] [fc2] of ECAPA_TDNN.extract_embedding (:412-422) as (name, w, b, [0], scale, shift, relu) records: "far" =
+    fc1.affine alone, "near_affine" = [fc1 full ->] fc2.affine, "near" = [fc1 full ->] fc2 full; bn_stats (eval BatchNorm on
+    the pooled statistics, :412) is folded into whichever layer reads them: W' = W diag(s), b' = W t + b, in float64."""
+    pos = m.extracted_embedding
+    chain = ([("fc1", m.fc1, pos != "far")] if m.fc1 is not None else []) + \
+            ([("fc2", m.fc2, pos == "near")] if pos != "far" else [])
     s, t = fold_batchnorm(m.bn_stats)
-    w = m.fc2.affine.weight.detach().double().cpu().numpy()[:, :, 0]
-    b = m.fc2.affine.bias.detach().double().cpu().numpy()
-    w2 = (w * s.astype(np.float64)[None, :]).astype(np.float32)[:, :, None]
-    b2 = (w @ t.astype(np.float64) + b).astype(np.float32)
-    full = m.extracted_embedding == "near"
-    fs, ft = fold_batchnorm(m.fc2.batchnorm) if full else (None, None)
-    out.append(("fc2", w2, b2, [0], fs, ft, full and m.fc2.relu))
+    out = []
+    for i, (name, layer, full) in enumerate(chain):
+        if full:
+            w, b, scale, shift, relu = layer.export()
+        else:
+            w, b, scale, shift, relu = layer.affine.dense_weight(), layer.affine.bias.detach().float(), None, None, False
+        w = w.double().cpu().numpy()[:, :, 0]
+        b = b.double().cpu().numpy()
+        if i == 0:
+            b = w @ t.astype(np.float64) + b
+            w = w * s.astype(np.float64)[None, :]
+        out.append((name, w.astype(np.float32)[:, :, None], b.astype(np.float32), [0], scale, shift, relu))
     return out
 
 
@@ -357,15 +372,9 @@ class EcapaExtractor:
         self.att_gs = _Layer(w0[:, c:].contiguous(), att[0].bias, [0], device=device)  # [mean | std] columns
         self.att2 = _Layer(att[4].weight, att[4].bias, [0], device=device)
         self.mfa_dim = c
-        # bn_stats folded into fc2: W' = W diag(s), b' = W t + b
-        s, t = fold_batchnorm(m.bn_stats)
-        w = m.fc2.affine.weight.detach().double().cpu().numpy()[:, :, 0]
-        b = m.fc2.affine.bias.detach().double().cpu().numpy()
-        w2 = torch.from_numpy((w * s.astype(np.float64)[None, :]).astype(np.float32)).unsqueeze(2)
-        b2 = torch.from_numpy((w @ t.astype(np.float64) + b).astype(np.float32))
-        full = m.extracted_embedding == "near"
-        self.fc2 = _Layer(w2, b2, [0], relu=full and m.fc2.relu, device=device,
-                          scale_shift=fold_batchnorm(m.fc2.batchnorm) if full else (None, None))
+        # segment level: [fc1 ->] [fc2], bn_stats folded into the first (same records as the native extractor gets)
+        self.segment = [_Layer(torch.from_numpy(w), torch.from_numpy(b), ctx, relu=relu, device=device, scale_shift=(scale, shift))
+                        for _, w, b, ctx, scale, shift, relu in _segment_layers(m)]
         self.embed_dim = m.embd_dim
 
     def extract(self, feats):
@@ -428,10 +437,13 @@ class EcapaExtractor:
         self.att2.run(A1, y_f32=LOG)
         pstat, pp = ops.attn_stats_pool(LOG, MF, 1e-5, planes=True)
         _mark("attn_stats_pool")
-        if SMALL_ROWS:
-            return self.fc2.run_rows(pstat)
+        if SMALL_ROWS or len(self.segment) > 1:
+            x = pstat
+            for layer in self.segment:
+                x = layer.run_rows(x)
+            return x
         emb = torch.empty(B, 1, self.embed_dim, dtype=torch.float32, device=dev)
-        self.fc2.run(pp, y_f32=emb)
+        self.segment[0].run(pp, y_f32=emb)
         return emb.view(B, self.embed_dim)
 
     def close(self):

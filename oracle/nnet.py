@@ -420,7 +420,7 @@ def attentive_stats_pool(x, sd, prefix="stats"):
     return torch.cat([mean, std], dim=1)
 
 
-def ecapa_forward(sd, x, extracted_embedding="near", fc2_relu=False, return_intermediates=False):
+def ecapa_forward(sd, x, extracted_embedding="near", fc2_relu=False, return_intermediates=False, fc1=False):
     """ECAPA_TDNN.extract_embedding body, ecapa_tdnn_xvector.py:403-426 with the canonical
     c1024 parameters of pytorch/launcher/runEcapaXvector_online.py:221-263 (fc1=False; fc2
     nonlinearity '' and BN affine=False -> ``fc2_relu=False`` and no fc2.batchnorm.weight
@@ -439,10 +439,16 @@ def ecapa_forward(sd, x, extracted_embedding="near", fc2_relu=False, return_inte
     inter["stats"] = x
     x = batchnorm_eval(x, sd, "bn_stats")
     x = x.unsqueeze(2)
-    if extracted_embedding == "near_affine":
-        x = tdnn_affine(x, sd["fc2.affine.weight"], sd["fc2.affine.bias"], [0])
-    elif extracted_embedding == "near":
-        x = relu_bn_tdnn_layer(x, sd, "fc2", [0], relu=fc2_relu)
+    if extracted_embedding == "far":                     # :414-416 (fc1=True models only; fc1 with the constructor defaults)
+        assert fc1
+        x = tdnn_affine(x, sd["fc1.affine.weight"], sd["fc1.affine.bias"], [0])
+    elif extracted_embedding in ("near_affine", "near"):
+        if fc1:
+            x = relu_bn_tdnn_layer(x, sd, "fc1", [0])
+        if extracted_embedding == "near_affine":
+            x = tdnn_affine(x, sd["fc2.affine.weight"], sd["fc2.affine.bias"], [0])
+        else:
+            x = relu_bn_tdnn_layer(x, sd, "fc2", [0], relu=fc2_relu)
     else:
         raise TypeError("Expected far or near position, but got {}".format(extracted_embedding))
     return (x, inter) if return_intermediates else x
@@ -505,7 +511,7 @@ def xvector_spec(inputs_dim):
 
 
 def ecapa_spec(inputs_dim, channels=1024, embd_dim=192, mfa_conv=1536, hidden=128,
-               fc2_bn_affine=False, scale=8, se_bottleneck=128):
+               fc2_bn_affine=False, scale=8, se_bottleneck=128, fc1=False):
     """Keys/shapes of ECAPA_TDNN(inputs_dim, N, training=False, <canonical params>).state_dict()
     (ecapa_tdnn_xvector.py:259-332)."""
     spec = _affine_entries("layer1", inputs_dim, channels, [-2, -1, 0, 1, 2]) + \
@@ -526,7 +532,9 @@ def ecapa_spec(inputs_dim, channels=1024, embd_dim=192, mfa_conv=1536, hidden=12
         _bn_entries("stats.attention.2", hidden) + \
         _affine_entries("stats.attention.4", hidden, mfa_conv, [0], "conv")
     spec += _bn_entries("bn_stats", 2 * mfa_conv)
-    spec += _affine_entries("fc2", 2 * mfa_conv, embd_dim, [0]) + \
+    if fc1:       # ReluBatchNormTdnnLayer(2 * mfa_conv, embd_dim) with the constructor's default fc params (BN affine=True)
+        spec += _affine_entries("fc1", 2 * mfa_conv, embd_dim, [0]) + _bn_entries("fc1.batchnorm", embd_dim)
+    spec += _affine_entries("fc2", embd_dim if fc1 else 2 * mfa_conv, embd_dim, [0]) + \
         _bn_entries("fc2.batchnorm", embd_dim, affine=fc2_bn_affine)
     return spec
 
