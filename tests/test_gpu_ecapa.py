@@ -207,6 +207,26 @@ def test_ecapa_default_fc2_and_short_utterances(golden):
         assert rel(m.extract_embedding(f).numpy(), g["ecapa80_default_T{}".format(T)]) < EMB_TOL
 
 
+@pytest.mark.parametrize("native", ["1", "0"])
+def test_ecapa_with_fc1_matches_reference_golden(golden, monkeypatch, native):
+    """ECAPA_TDNN(fc1=True) in the three positions (far = fc1.affine, near_affine = fc1 -> fc2.affine, near = fc1 -> fc2;
+    ecapa_tdnn_xvector.py:412-422) against the reference's own outputs, native extractor and Python twin."""
+    from asv_subtools_b200.model.ecapa_tdnn_xvector import ECAPA_TDNN
+    monkeypatch.setenv("XVB_ECAPA_NATIVE", native)
+    g = golden("ecapa_fc1")
+    sd = onn.make_state_dict(onn.ecapa_spec(80, fc1=True, fc2_bn_affine=True), 203)
+    feats = onn.synthetic_feats(2, 120, 80, 1203)
+    for pos in ("far", "near_affine", "near"):
+        m = ECAPA_TDNN(80, 10, training=False, fc1=True, extracted_embedding=pos)
+        m.load_state_dict(sd, strict=True)
+        m.cuda().eval()
+        assert rel(m.extract_embedding_batch(feats).cpu().numpy(), g["fc1_" + pos]) < EMB_TOL, pos
+        assert rel(m.extract_embedding(feats[1]).numpy(), g["fc1_" + pos][1]) < EMB_TOL, pos
+        m.invalidate()
+    with pytest.raises(AssertionError):
+        ECAPA_TDNN(80, 10, training=False, extracted_embedding="far").cuda().eval().extractor()
+
+
 def test_ecapa_vs_oracle_batch():
     """A batch shape with ragged tiles (B=5, T=83) straight against the oracle."""
     m, sd = _model("near")

@@ -304,6 +304,17 @@ def test_snowdar_bn_relu_order_oracle_matches_reference(golden):
         assert rel(emb, g["bnrelu_{}".format(pos)]) < RTOL, pos
 
 
+def test_ecapa_with_fc1_oracle_matches_reference(golden):
+    """ECAPA_TDNN(fc1=True): far = fc1.affine, near_affine = fc1 -> fc2.affine, near = fc1 -> fc2 (ecapa_tdnn_xvector.py:412-422)."""
+    g = golden("ecapa_fc1")
+    sd = onn.make_state_dict(onn.ecapa_spec(80, fc1=True, fc2_bn_affine=True), 203)
+    feats = onn.synthetic_feats(2, 120, 80, 1203)
+    for pos in ("far", "near_affine", "near"):
+        fwd = lambda x: onn.ecapa_forward(sd, x, pos, fc2_relu=True, fc1=True)  # noqa: E731
+        emb = np.stack([onn.extract_embedding(fwd, feats[i]).numpy() for i in range(2)])
+        assert rel(emb, g["fc1_" + pos]) < RTOL, pos
+
+
 def test_coral_adaptation_oracle_matches_reference(golden):
     from oracle import plda_train as opt
     g = golden("plda_train")
