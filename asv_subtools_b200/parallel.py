@@ -47,7 +47,7 @@ class PeerTable:
     Same-node ranks only (CUDA IPC + peer access).  Raises RuntimeError if the driver refuses the mapping -- the caller
     falls back to `all_gather_blocks`."""
 
-    def __init__(self, rows_per_rank, dim, group=None, device=None):
+    def __init__(self, rows_per_rank, dim, group=None, device=None, total_rows=None):
         import ctypes as C
 
         from ._lib import check, lib
@@ -58,7 +58,8 @@ class PeerTable:
             raise ValueError("PeerTable maps at most 16 peers (XVB_MAX_PEERS)")
         self.n, self.dim = int(rows_per_rank), int(dim)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        nbytes = self.world * self.n * self.dim * 4
+        self.rows = int(total_rows) if total_rows is not None else self.world * self.n
+        nbytes = self.rows * self.dim * 4
         base = C.c_void_p()
         check(lib.xvb_ipc_alloc(C.byref(base), nbytes), "xvb_ipc_alloc")
         self._base = base.value
@@ -87,7 +88,7 @@ class PeerTable:
         if int(ok.item()) == 0:
             self.close()
             raise RuntimeError("CUDA IPC peer mapping is not available between these ranks")
-        self.tensor = self._view(self._base, (self.world * self.n, self.dim))
+        self.tensor = self._view(self._base, (self.rows, self.dim))
 
     def _view(self, ptr, shape):
         holder = type("_CudaBuffer", (), {})()
@@ -97,9 +98,10 @@ class PeerTable:
         t._xvb_keepalive = self          # the allocation lives as long as the table object
         return t
 
-    def attach(self, extractor):
-        """Make `extractor`'s shard calls (x-vector `ops.Extractor` or the ECAPA extractor) store into every copy."""
-        extractor.set_gather(self.pointers, self.world, self.rank * self.n, self.dim)
+    def attach(self, extractor, row0=None):
+        """Make `extractor`'s shard calls (x-vector `ops.Extractor` or the ECAPA extractor) store into every copy, this
+        rank's rows starting at `row0` (default rank * rows_per_rank; unequal shards pass their own offsets)."""
+        extractor.set_gather(self.pointers, self.world, self.rank * self.n if row0 is None else int(row0), self.dim)
 
     @staticmethod
     def detach(extractor):

@@ -580,8 +580,11 @@ def run_native(args, rank, world, local_rank):
     n = SHARD_UTTS
     n_total = n * world
     n_spk = max(2, n_total // UTTS_PER_SPK)
-    feats, spk = synthetic_shard(n, T, F, rank * n, n_spk, dev, 2048 + rank)
-    emb = torch.empty(n, D, device=dev)
+    # N > 1: room for a shard up to 8 % larger than nominal -- after the warm-up the shard sizes follow the measured speeds
+    cap = n if world == 1 else n + ((n * 8 // 100 + B - 1) // B) * B
+    feats_cap, spk_cap = synthetic_shard(cap, T, F, rank * cap, n_spk, dev, 2048 + rank)
+    emb_cap = torch.empty(cap, D, device=dev)
+    feats, spk, emb = feats_cap[:n], spk_cap[:n], emb_cap[:n]
     # The path's one exchange: every GPU needs the whole (N x n, 512) table.  Default: the table's copies are mapped
     # into one another over NVLink (CUDA IPC) and every batch's embeddings are stored into all of them while the next
     # batches run (csrc/peer.cu); a step then ends with a one-word all-reduce as the rendezvous.  XVB_BENCH_GATHER=nccl
@@ -592,7 +595,7 @@ def run_native(args, rank, world, local_rank):
         if os.environ.get("XVB_BENCH_GATHER", "p2p") != "nccl":
             try:
                 from asv_subtools_b200.parallel import PeerTable
-                table = PeerTable(n, D)
+                table = PeerTable(n, D, total_rows=n_total)
                 gather_kind = "p2p"
             except RuntimeError as err:
                 if rank == 0:
@@ -616,8 +619,50 @@ def run_native(args, rank, world, local_rank):
         exchange()
 
     # ---- device-resident throughput (sustained) --------------------------------------------------
+    warm_ms = []
     for _ in range(args.warmup):
-        step()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        ex.extract_shard(feats, B, out=emb)
+        w1.record()
+        exchange()
+        warm_ms.append((w0, w1))
+    # Shard sizes by measured speed (N > 1, peer table only: its rows need not be equal per rank).  Under the power cap the
+    # GPUs of a box settle at different clocks (1447-1522 MHz in profiles/r04k) and a step ends when the slowest is done;
+    # the reference balances its jobs the same way, by length (splitDataByLength.sh).  The total stays N x SHARD_UTTS.
+    n_rank, row0, balance = [n] * world, rank * n, None
+    if table is not None and os.environ.get("XVB_BENCH_BALANCE", "1") != "0":
+        torch.cuda.synchronize()
+        mine = statistics.mean(a.elapsed_time(b) for a, b in warm_ms[-2:])
+        times = torch.zeros(world, dtype=torch.float64, device=dev)
+        times[rank] = mine
+        dist.all_reduce(times)
+        speed = 1.0 / times.cpu().numpy()
+        want = n_total * speed / speed.sum()
+        n_rank = [int(min(cap, max(B, round(w / B) * B))) for w in want]
+        k = 0
+        while sum(n_rank) != n_total and k < 64 * world:          # put the rounding remainder where there is room
+            r = k % world
+            step_ = B if sum(n_rank) < n_total else -B
+            if B <= n_rank[r] + step_ <= cap:
+                n_rank[r] += step_
+            k += 1
+        if sum(n_rank) == n_total:
+            row0 = sum(n_rank[:rank])
+            n_mine = n_rank[rank]
+            feats, spk, emb = feats_cap[:n_mine], spk_cap[:n_mine], emb_cap[:n_mine]
+            table.attach(ex, row0)
+            balance = {"kind": "static: shard sizes proportional to each rank's measured shard rate over the last two warm-up steps, "
+                               "in whole batches, total unchanged", "utts_per_rank": n_rank,
+                       "warmup_shard_ms_per_rank": [float(x) for x in times.cpu().numpy()]}
+            step()                                                  # one more warm-up step at the new sizes
+        else:
+            n_rank = [n] * world
+    n_mine = n_rank[rank]
+    if world > 1:                                                   # speaker ids in table order (shards may be unequal now)
+        pad = torch.full((world * cap,), -1, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(pad, spk_cap)
+        spk_full = torch.cat([pad[r * cap:r * cap + n_rank[r]] for r in range(world)]).contiguous()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     tm.barrier()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
@@ -638,17 +683,19 @@ def run_native(args, rank, world, local_rank):
     # the collective alone: inside a step its CUDA-event span also holds the wait for the slowest rank's shard
     gather_alone_ms, p2p_equals_nccl = 0.0, None
     if world > 1:
-        check = torch.empty(n_total, D, device=dev)
+        check = torch.empty(world * cap, D, device=dev)
         tm.barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
         for _ in range(5):
-            dist.all_gather_into_tensor(check, emb)
+            dist.all_gather_into_tensor(check[:n_total], emb_cap[:n])      # the nominal (N x n, 512) collective
         g1.record()
         tm.barrier()
         gather_alone_ms = tm.max_over_ranks(g0.elapsed_time(g1) / 5)
-        if table is not None:                              # the peer-stored table must be the all-gathered one, bit for bit
-            same = torch.tensor([1 if torch.equal(check, full) else 0], device=dev)
+        if table is not None:              # the peer-stored table must be what NCCL gathers (padded shards), bit for bit
+            dist.all_gather_into_tensor(check, emb_cap)
+            ok = all(torch.equal(check[r * cap:r * cap + n_rank[r]], full[sum(n_rank[:r]):sum(n_rank[:r + 1])]) for r in range(world))
+            same = torch.tensor([1 if ok else 0], device=dev)
             dist.all_reduce(same, op=dist.ReduceOp.MIN)
             p2p_equals_nccl = bool(same.item())
         del check
@@ -658,14 +705,14 @@ def run_native(args, rank, world, local_rank):
     if table is not None:
         table.detach(ex)                                   # the end-to-end leg below measures the plain host-buffer call
     host = pinned_copy(feats)
-    host_out = torch.empty(n, D, dtype=torch.float32, pin_memory=True)
-    ex.extract_shard_host(host.data_ptr(), min(n, 8 * B), T, host_out.data_ptr(), B)      # warm: slots, copy stream
+    host_out = torch.empty(n_mine, D, dtype=torch.float32, pin_memory=True)
+    ex.extract_shard_host(host.data_ptr(), min(n_mine, 8 * B), T, host_out.data_ptr(), B)      # warm: slots, copy stream
     e2e_steps = max(3, min(args.steps, 10))
     tm.barrier()
     wall2 = time.time()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        ex.extract_shard_host(host.data_ptr(), n, T, host_out.data_ptr(), B)   # returns with the embeddings on the host
+        ex.extract_shard_host(host.data_ptr(), n_mine, T, host_out.data_ptr(), B)   # returns with the embeddings on the host
     e2e_host_ms = (time.perf_counter() - t0) * 1e3
     tm.barrier()
     wall3 = time.time()
@@ -673,7 +720,7 @@ def run_native(args, rank, world, local_rank):
     e2e_equal = bool(torch.equal(host_out, emb.cpu()))
     clocks_e2e = sampler.window(wall2, wall3) if sampler else None
     # what bounds e2e: the host->device link.  Same pinned buffer, copy alone, CUDA events.
-    nb_link = min(n, 64 * B)
+    nb_link = min(n_mine, 64 * B)
     dst = torch.empty(nb_link, T, F, device=dev)
     dst.copy_(host[:nb_link], non_blocking=True)
     torch.cuda.synchronize()
@@ -700,12 +747,12 @@ def run_native(args, rank, world, local_rank):
     if world > 1 and table is None:
         dist.all_gather_into_tensor(full, emb)
     if table is not None:                                  # refill through the peer path (the e2e leg ran detached)
-        table.attach(ex)
+        table.attach(ex, row0)
         ex.extract_shard(feats, B, out=emb)
         table.detach(ex)
         table.barrier()
     c4 = config4_block(tm, full, spk_full, rank, world, verify_single=True)
-    del feats
+    del feats, feats_cap
     torch.cuda.empty_cache()
     c3, c5 = ecapa_blocks(tm, dev, rank, world, pk, args.steps)
     if table is not None:
@@ -728,6 +775,7 @@ def run_native(args, rank, world, local_rank):
         "dtype": "f32 (bf16x3 split operands on tcgen05, fp32 accumulate in TMEM)", "data": "synthetic",
         "config": workload_config(world),
         "timed_region_s": ms * 1e-3,
+        "balance": balance,
         "exchange": {"kind": gather_kind, "p2p_equals_nccl": p2p_equals_nccl,
                      "what": "p2p: every batch's embeddings are stored into all N table copies over NVLink peer mappings (CUDA IPC) "
                              "while the next batches run, a one-word all-reduce ends the step; nccl: one all-gather after the shard"},
@@ -740,7 +788,7 @@ def run_native(args, rank, world, local_rank):
                               "by itself after a barrier (5 back to back), which is what the bus bandwidth is quoted on" % n},
         "shard_pipeline": "two lanes: batches alternate between twin workspaces on two streams (XVB_LANES=%s)" % os.environ.get("XVB_LANES", "1"),
         "e2e": {"value": frames_per_step * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / e2e_steps,
-                "steps": e2e_steps, "h2d_bytes_per_step": n * T * F * 4, "d2h_bytes_per_step": n * D * 4,
+                "steps": e2e_steps, "h2d_bytes_per_step": n_mine * T * F * 4, "d2h_bytes_per_step": n_mine * D * 4,
                 "api": "xvb_extractor_extract_shard_host (pinned host features in, host embeddings out; the H2D of batch k+1 "
                        "on a copy stream overlaps the kernels of batch k; host clock, max over ranks)",
                 "equals_device_path": e2e_equal, "h2d_link_gbs_measured": h2d_gbs,
