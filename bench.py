@@ -638,16 +638,14 @@ def run_native(args, rank, world, local_rank):
         times[rank] = mine
         dist.all_reduce(times)
         speed = 1.0 / times.cpu().numpy()
-        want = n_total * speed / speed.sum()
-        n_rank = [int(min(cap, max(B, round(w / B) * B))) for w in want]
-        k = 0
-        while sum(n_rank) != n_total and k < 64 * world:          # put the rounding remainder where there is room
-            r = k % world
-            step_ = B if sum(n_rank) < n_total else -B
-            if B <= n_rank[r] + step_ <= cap:
-                n_rank[r] += step_
-            k += 1
-        if sum(n_rank) == n_total:
+        q, rem = divmod(n_total, B)                                 # whole batches by largest remainder, the odd tail to the fastest
+        share = q * speed / speed.sum()
+        batches = [int(x) for x in np.floor(share)]
+        for r in np.argsort(-(share - np.floor(share)))[: q - sum(batches)]:
+            batches[int(r)] += 1
+        n_rank = [b * B for b in batches]
+        n_rank[int(np.argmax(speed))] += rem
+        if sum(n_rank) == n_total and max(n_rank) <= cap and min(n_rank) >= B:
             row0 = sum(n_rank[:rank])
             n_mine = n_rank[rank]
             feats, spk, emb = feats_cap[:n_mine], spk_cap[:n_mine], emb_cap[:n_mine]
