@@ -638,6 +638,8 @@ def run_native(args, rank, world, local_rank):
         times[rank] = mine
         dist.all_reduce(times)
         speed = 1.0 / times.cpu().numpy()
+        if os.environ.get("XVB_BENCH_FAKE_SPEED"):                  # test knob: pretend the ranks differ (comma-separated factors)
+            speed = speed * np.array([float(v) for v in os.environ["XVB_BENCH_FAKE_SPEED"].split(",")][:world])
         q, rem = divmod(n_total, B)                                 # whole batches by largest remainder, the odd tail to the fastest
         share = q * speed / speed.sum()
         batches = [int(x) for x in np.floor(share)]
