@@ -429,9 +429,13 @@ struct OnlineU {
   float m, s0, s1, s2, u1, u2;
 };
 
+// xi-vector form (xivec_stdinit_softplus2_prec_pooling, pooling.py:165-212): the raw logit z becomes 2 log(softplus(z)) (a frame's
+// log-precision, :189-190) and the softmax runs over T + 1 elements, the extra one being the prior (logit prior_logit[c], value
+// prior_x[c], :194-202): it initialises the online-softmax state of warp 0.
 __global__ void __launch_bounds__(kApWarps * 32)
 attn_head_stats_pool_kernel(const float* __restrict__ logits, long long ldl, const float* __restrict__ x, long long ldx,
-                            int T, int C, int O, int gdiv, float floor_, int unweighted_var, float* __restrict__ out,
+                            int T, int C, int O, int gdiv, float floor_, int unweighted_var, const float* __restrict__ prior_logit,
+                            const float* __restrict__ prior_x, int softplus2log, float* __restrict__ out,
                             __nv_bfloat16* __restrict__ oh, __nv_bfloat16* __restrict__ ol, long long ldo) {
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -445,6 +449,13 @@ attn_head_stats_pool_kernel(const float* __restrict__ logits, long long ldl, con
     int g[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) g[k] = (o + k) / gdiv;
+    if (prior_logit && warp == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float px = __ldg(prior_x + c + k);
+        st[k] = {__ldg(prior_logit + c + k), 1.f, px, px * px, 0.f, 0.f};
+      }
+    }
     const float* lb = logits + (long long)b * T * ldl;
     const float* xb = x + (long long)b * T * ldx + c;
     for (int t = warp; t < T; t += kApWarps) {
@@ -453,7 +464,11 @@ attn_head_stats_pool_kernel(const float* __restrict__ logits, long long ldl, con
       const float* lr = lb + (long long)t * ldl;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float l = __ldg(lr + g[k]);
+        float l = __ldg(lr + g[k]);
+        if (softplus2log) {
+          l = 2.f * logf(l > 20.f ? l : log1pf(expf(l)));    // Softplus(beta=1, threshold=20), then 2 log
+          if (l == -INFINITY) continue;                      // zero precision: weight exactly 0, like exp(-inf) in the softmax
+        }
         OnlineU& s = st[k];
         const float mn = fmaxf(s.m, l);
         const float sc = expf(s.m - mn), e = expf(l - mn);
@@ -557,8 +572,18 @@ extern "C" int xvb_small_affine(const float* x, int64_t ldx, const float* w, int
 extern "C" int xvb_attn_head_stats_pool(const float* logits, int64_t ldl, int G, const float* x, int64_t ldx, int B, int T,
                                         int C, int O, int gdiv, float floor_, int unweighted_var, float* out,
                                         uint16_t* out_hi, uint16_t* out_lo, int64_t ldo, void* stream) {
+  return xvb_attn_head_stats_pool_prior(logits, ldl, G, x, ldx, B, T, C, O, gdiv, floor_, unweighted_var, nullptr, nullptr, 0, out,
+                                        out_hi, out_lo, ldo, stream);
+}
+
+extern "C" int xvb_attn_head_stats_pool_prior(const float* logits, int64_t ldl, int G, const float* x, int64_t ldx, int B, int T,
+                                              int C, int O, int gdiv, float floor_, int unweighted_var, const float* prior_logit,
+                                              const float* prior_x, int softplus2log, float* out, uint16_t* out_hi,
+                                              uint16_t* out_lo, int64_t ldo, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
+  XVB_CHECK_ARG((prior_logit != nullptr) == (prior_x != nullptr) && (!prior_logit || (O == C && !unweighted_var)),
+                "xvb_attn_head_stats_pool: the prior element needs both arrays, O == C and weighted moments");
   XVB_CHECK_ARG(logits && x && out, "xvb_attn_head_stats_pool: null pointer");
   XVB_CHECK_ARG(B > 0 && T > 0 && C > 0 && C % 4 == 0 && O > 0 && O % C == 0 && ldx % 4 == 0 && ldx >= C && B <= 65535,
                 "xvb_attn_head_stats_pool: need C%%4==0, O a multiple of C, ldx%%4==0");
@@ -568,8 +593,8 @@ extern "C" int xvb_attn_head_stats_pool(const float* logits, int64_t ldl, int G,
   if (out_hi) XVB_CHECK_ARG(ldo % 4 == 0 && ldo >= 2 * (int64_t)O, "xvb_attn_head_stats_pool: ldo too small / unaligned");
   dim3 grid((O + 127) / 128, B);
   attn_head_stats_pool_kernel<<<grid, kApWarps * 32, 0, (cudaStream_t)stream>>>(
-      logits, ldl, x, ldx, T, C, O, gdiv, floor_, unweighted_var, out, reinterpret_cast<__nv_bfloat16*>(out_hi),
-      reinterpret_cast<__nv_bfloat16*>(out_lo), ldo);
+      logits, ldl, x, ldx, T, C, O, gdiv, floor_, unweighted_var, prior_logit, prior_x, softplus2log, out,
+      reinterpret_cast<__nv_bfloat16*>(out_hi), reinterpret_cast<__nv_bfloat16*>(out_lo), ldo);
   XVB_LAUNCH_CHECK();
   return XVB_OK;
 }

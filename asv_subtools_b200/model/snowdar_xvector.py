@@ -2,9 +2,10 @@
 """Snowdar x-vector blueprint for the B200 path -- drop-in for pytorch/model/snowdar_xvector.py (Xvector.init
 :15-152, extract_embedding :262-294) in its TDNN configurations: standard or `extend=True` stack,
 `tdnn_layer_params` (default BatchNorm affine=False, momentum 0.5), pooling = statistics | attentive | multi-head |
-multi-resolution | lde (pooling.py:15-76, :130-162, :322-440, :518-587; the blueprint's switch :119-136), positions
+multi-resolution | lde | xi-postmean-softplus2 | xi-postdist-softplus2 (pooling.py:15-76, :130-212, :322-440, :518-587; the
+blueprint's switch :119-136 in full), positions
 far / near_affine / near.  Same constructor keywords and state_dict keys.  The options that add other
-operators (SE blocks, skip connection, xi-vector pooling) raise NotImplementedError;
+operators (SE blocks, skip connection) raise NotImplementedError;
 training-only keywords (mixup, specaugment, dropouts, margin loss, step params) are accepted and ignored,
 as the launchers rewrite the creation string with training=False for extraction."""
 import os
@@ -14,6 +15,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 
 from asv_subtools_b200.nnet import (AttentionPoolingExtractor, AttentiveStatisticsPooling, LDEPooling,  # noqa: E402
                                     MultiHeadAttentionPooling, MultiResolutionMultiHeadAttentionPooling,
+                                    xivec_stdinit_softplus2_prec_pooling,
                                     ReluBatchNormTdnnLayer, StatisticsPooling, TopVirtualNnet, build_tdnn_extractor)
 
 
@@ -27,9 +29,9 @@ class Xvector(TopVirtualNnet):
              step_params={}, transfer_from="softmax_loss", training=True, extracted_embedding="far"):
         if SE or skip_connection:
             raise NotImplementedError("SE blocks / skip connection are not on the B200 path")
-        if pooling not in ("statistics", "lde", "attentive", "multi-head", "multi-resolution"):
-            raise NotImplementedError("pooling={!r}: statistics / lde / attentive / multi-head / multi-resolution are on the "
-                                      "B200 path".format(pooling))
+        if pooling not in ("statistics", "lde", "attentive", "multi-head", "multi-resolution", "xi-postmean-softplus2",
+                           "xi-postdist-softplus2"):
+            raise NotImplementedError("pooling={!r} is not one of the reference's options (snowdar_xvector.py:119-136)".format(pooling))
         if not tdnn6:
             raise NotImplementedError("tdnn6=False is not on the B200 path")
         layer = {"nonlinearity": "relu", "nonlinearity_params": {"inplace": True}, "bn-relu": False, "bn": True,
@@ -67,6 +69,9 @@ class Xvector(TopVirtualNnet):
             self.stats = MultiHeadAttentionPooling(num_nodes, stddev=True, **pool)
         elif pooling == "multi-resolution":                                                                 # :129-130
             self.stats = MultiResolutionMultiHeadAttentionPooling(num_nodes, **pool)
+        elif pooling in ("xi-postmean-softplus2", "xi-postdist-softplus2"):                                 # :131-134
+            self.stats = xivec_stdinit_softplus2_prec_pooling(num_nodes, hidden_size=pool["hidden_size"],
+                                                              stddev=pooling == "xi-postdist-softplus2")
         else:
             self.stats = StatisticsPooling(num_nodes, stddev=True)
         self.tdnn6 = L(self.stats.get_output_dim(), 512, **layer)

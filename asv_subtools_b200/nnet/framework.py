@@ -256,7 +256,16 @@ class AttentionPoolingExtractor:
         dev = model.device_for_extraction()
         self.feat_dim = inputs_dim
         self.frames = [_PackedAffine.from_layer(l, dev) for l in frame_layers]
-        self.lde = None
+        self.lde = self.xi = None
+        if hasattr(stats, "prior_logprec"):                      # xi-vector: precision network + prior element
+            self.first = _PackedAffine.from_layer(stats.lin1_relu_bn, dev)
+            self.last = _PackedAffine(stats.lin2, dev)
+            self.xi = (stats.prior_logprec.detach().float().reshape(-1).to(dev).contiguous(),
+                       stats.prior_mean.detach().float().reshape(-1).to(dev).contiguous(), bool(stats.stddev))
+            self.channels, self.pooled, self.gdiv = stats.input_dim, stats.input_dim, 1
+            self.eps, self.unweighted = 1.0e-10, False           # clamp(sigma2 - phi^2, min=1e-10), pooling.py:205
+            self._segments(dev, tdnn6, tdnn7, position)
+            return
         if hasattr(stats, "mu"):                                 # LDEPooling: no attention network
             self.lde = (stats.mu.detach().float().to(dev).contiguous(), stats.neg_beta().to(dev).contiguous())
             self.first = self.last = None
@@ -310,8 +319,14 @@ class AttentionPoolingExtractor:
                 self.first.run(xp, y=y)
             logits = torch.empty(B, T, self.last.cout, dtype=torch.float32, device=dev)
             self.last.run(h, y_f32=logits)
-            _, x = ops.attn_head_stats_pool(logits[..., :self.last.cout_real], xf[..., :top.cout_real], self.pooled, self.gdiv,
-                                            floor=self.eps, unweighted_var=self.unweighted, planes=True)
+            if self.xi is not None:
+                _, x = ops.attn_head_stats_pool(logits[..., :self.last.cout_real], xf[..., :top.cout_real], self.pooled, 1, floor=self.eps,
+                                                planes=True, prior_logit=self.xi[0], prior_x=self.xi[1], softplus2log=True)
+                if not self.xi[2]:                               # post-mean variant: phi alone
+                    x = x.slice(0, self.pooled)
+            else:
+                _, x = ops.attn_head_stats_pool(logits[..., :self.last.cout_real], xf[..., :top.cout_real], self.pooled, self.gdiv,
+                                                floor=self.eps, unweighted_var=self.unweighted, planes=True)
         for i, layer in enumerate(self.segment):
             if i + 1 == len(self.segment):
                 emb = torch.empty(B, 1, layer.cout, dtype=torch.float32, device=dev)

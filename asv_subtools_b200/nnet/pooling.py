@@ -47,6 +47,26 @@ class LDEPooling(torch.nn.Module):
         return -(self.s.detach().float() ** 2 + self.eps)
 
 
+class xivec_stdinit_softplus2_prec_pooling(torch.nn.Module):
+    """Xi-vector pooling (pooling.py:165-212): a frame-wise precision network lin1_relu_bn -> lin2 -> softplus, Gaussian
+    posterior inference against a learnt prior (prior_mean, prior_logprec): phi = sum over the T frames AND the prior of
+    softmax(2 log precision) * value; `stddev=True` adds the posterior spread.  Same parameter names as the reference; the
+    arithmetic runs on the layer kernel (lin1, lin2) and `xvb_attn_head_stats_pool_prior`."""
+
+    def __init__(self, input_dim, hidden_size=256, context=[0], stddev=False, train_mean=True, train_prec=True):
+        super().__init__()
+        from .components import ReluBatchNormTdnnLayer
+        self.input_dim, self.stddev = input_dim, stddev
+        self.output_dim = 2 * input_dim if stddev else input_dim
+        self.prior_mean = torch.nn.Parameter(torch.zeros(1, input_dim), requires_grad=train_mean)
+        self.prior_logprec = torch.nn.Parameter(torch.zeros(1, input_dim), requires_grad=train_prec)
+        self.lin1_relu_bn = ReluBatchNormTdnnLayer(input_dim, hidden_size, context)
+        self.lin2 = TdnnAffine(hidden_size, input_dim, context=context)
+
+    def get_output_dim(self):
+        return self.output_dim
+
+
 class AttentionAlphaComponent(torch.nn.Module):
     """alpha = softmax_T(last_affine(relu(first_affine(x)))) -- same constructor, same parameter / buffer names and
     shapes as the reference (pooling.py:226-298): grouped affines for split heads, `t` the per-head temperature

@@ -253,9 +253,11 @@ def small_affine(x, w, bias=None, bn_scale=None, bn_shift=None, relu=False, sigm
     return (y, op) if planes else y
 
 
-def attn_head_stats_pool(logits, x, out_channels, gdiv, floor=1e-10, unweighted_var=False, planes=False):
+def attn_head_stats_pool(logits, x, out_channels, gdiv, floor=1e-10, unweighted_var=False, planes=False, prior_logit=None,
+                         prior_x=None, softplus2log=False):
     """Attention pooling with a head map (xvb_attn_head_stats_pool): logits (B,T,G) fp32 (any row pitch >= G), x (B,T,C)
-    fp32; output channel o pools x[..., o % C] with softmax_T(logits[..., o // gdiv]).  -> (B, 2*out_channels)."""
+    fp32; output channel o pools x[..., o % C] with softmax_T(logits[..., o // gdiv]).  -> (B, 2*out_channels).
+    prior_logit / prior_x (C,) + softplus2log: the xi-vector form (a prior element in the softmax, logits = 2 log softplus)."""
     for name, v in (("logits", logits), ("x", x)):       # channel-slice views of wider buffers are fine: rows stay contiguous
         if v.dtype != torch.float32 or not v.is_cuda or v.dim() != 3 or v.stride(-1) != 1 or v.stride(0) != v.shape[1] * v.stride(1):
             raise TypeError("{} must be a (B,T,*) CUDA float32 tensor with contiguous rows".format(name))
@@ -263,9 +265,10 @@ def attn_head_stats_pool(logits, x, out_channels, gdiv, floor=1e-10, unweighted_
     g = logits.shape[-1]
     out = torch.empty(b, 2 * out_channels, dtype=torch.float32, device=x.device)
     op = SplitPlanes.empty((b, 1, 2 * out_channels), x.device) if planes else None
-    check(lib.xvb_attn_head_stats_pool(_ptr(logits), logits.stride(-2), g, _ptr(x), x.stride(-2), b, t, c, out_channels, int(gdiv),
-                                       floor, 1 if unweighted_var else 0, _ptr(out), op.hi.data_ptr() if op else None,
-                                       op.lo.data_ptr() if op else None, 2 * out_channels, _stream()),
+    check(lib.xvb_attn_head_stats_pool_prior(_ptr(logits), logits.stride(-2), g, _ptr(x), x.stride(-2), b, t, c, out_channels,
+                                             int(gdiv), floor, 1 if unweighted_var else 0, _ptr(prior_logit), _ptr(prior_x),
+                                             1 if softplus2log else 0, _ptr(out), op.hi.data_ptr() if op else None,
+                                             op.lo.data_ptr() if op else None, 2 * out_channels, _stream()),
           "xvb_attn_head_stats_pool")
     return (out, op) if planes else out
 

@@ -222,6 +222,14 @@ int xvb_small_affine(const float* x, int64_t ldx, const float* w, int B, int K, 
 int xvb_attn_head_stats_pool(const float* logits, int64_t ldl, int G, const float* x, int64_t ldx, int B, int T, int C,
                              int O, int gdiv, float floor_, int unweighted_var, float* out, uint16_t* out_hi,
                              uint16_t* out_lo, int64_t ldo, void* stream);
+/* The xi-vector pooling (xivec_stdinit_softplus2_prec_pooling, pooling.py:165-212) on the same kernel: softplus2log = 1
+ * turns the raw logit z (output of `lin2`) into a frame log-precision 2 log(softplus(z)) (:189-190); prior_logit / prior_x
+ * (C each, may be NULL) add the prior as a (T+1)-th element of the softmax and of the weighted sums (:194-202).  out =
+ * [phi | sqrt(max(sum w x^2 - phi^2, floor))]: the post-mean variant uses the first half. */
+int xvb_attn_head_stats_pool_prior(const float* logits, int64_t ldl, int G, const float* x, int64_t ldx, int B, int T, int C,
+                                   int O, int gdiv, float floor_, int unweighted_var, const float* prior_logit,
+                                   const float* prior_x, int softplus2log, float* out, uint16_t* out_hi, uint16_t* out_lo,
+                                   int64_t ldo, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Feature-side front-end on a ragged batch: utterance u owns rows

@@ -226,6 +226,23 @@ def lde_pooling(x, mu, s, eps=1.0e-10):
     return e.reshape(-1, mu.shape[0] * mu.shape[1], 1)
 
 
+def xi_vector_pooling(x, sd, prefix, stddev):
+    """xivec_stdinit_softplus2_prec_pooling.forward, pooling.py:188-207."""
+    h = relu_bn_tdnn_layer(x, sd, prefix + ".lin1_relu_bn", [0])
+    logprec = F.softplus(tdnn_affine(h, sd[prefix + ".lin2.weight"], sd[prefix + ".lin2.bias"], [0]), beta=1, threshold=20)
+    logprec = 2.0 * torch.log(logprec)
+    b = x.shape[0]
+    pl = sd[prefix + ".prior_logprec"].repeat(b, 1).unsqueeze(2)
+    pm = sd[prefix + ".prior_mean"].repeat(b, 1).unsqueeze(2)
+    w = torch.softmax(torch.cat((logprec, pl), 2), dim=2)
+    xx = torch.cat((x, pm), 2)
+    phi = torch.sum(xx * w, dim=2)
+    if not stddev:
+        return phi.unsqueeze(2)
+    sigma = torch.sqrt(torch.clamp(torch.sum(xx.pow(2) * w, dim=2) - phi ** 2, min=1.0e-10))
+    return torch.cat((phi, sigma), dim=1).unsqueeze(2)
+
+
 def snowdar_pooling(x, sd, pooling, params, num_nodes):
     """Xvector.init's pooling switch, snowdar_xvector.py:119-136, for statistics / attentive / multi-head /
     multi-resolution."""
@@ -233,6 +250,8 @@ def snowdar_pooling(x, sd, pooling, params, num_nodes):
         return statistics_pooling(x)
     if pooling == "lde":             # :121-122 -> LDEPooling(num_nodes, c_num=num_head)
         return lde_pooling(x, sd["stats.mu"], sd["stats.s"])
+    if pooling.startswith("xi-"):    # :131-134
+        return xi_vector_pooling(x, sd, "stats", pooling == "xi-postdist-softplus2")
     p = dict(ATTENTION_DEFAULTS)
     p.update(params)
     if pooling == "attentive":       # :124-126 -> AttentiveStatisticsPooling(:327-337): one head, shared weight, bias
@@ -271,6 +290,12 @@ def snowdar_pooling_spec(pooling, params, num_nodes=1500):   # num_nodes may als
         return [], 2 * num_nodes
     p = dict(ATTENTION_DEFAULTS)
     p.update(params)
+    if pooling.startswith("xi-"):    # prior_mean, prior_logprec, lin1_relu_bn (BN affine=True default), lin2 -- pooling.py:179-186
+        h = p["hidden_size"]
+        spec = [("stats.prior_mean", (1, num_nodes), ("b", 0)), ("stats.prior_logprec", (1, num_nodes), ("b", 0))]
+        spec += _affine_entries("stats.lin1_relu_bn", num_nodes, h, [0]) + _bn_entries("stats.lin1_relu_bn.batchnorm", h)
+        spec += _affine_entries("stats.lin2", h, num_nodes, [0], "conv")
+        return spec, num_nodes * (2 if pooling == "xi-postdist-softplus2" else 1)
     if pooling == "lde":             # parameters mu (C, c_num) ~ randn, s (c_num,) ~ ones (pooling.py:143-144)
         return [("stats.mu", (num_nodes, p["num_head"]), ("lde_mu", 0)), ("stats.s", (p["num_head"],), ("lde_s", 0))], \
             num_nodes * p["num_head"]

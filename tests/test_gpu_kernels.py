@@ -419,6 +419,8 @@ SNOWDAR_POOLING_CASES = {
     "mha_full": ("multi-head", {"num_head": 4, "share": False, "affine_layers": 2}, 314),
     "mres": ("multi-resolution", {"num_head": 4, "temperature": True, "affine_layers": 2}, 315),
     "lde": ("lde", {"num_head": 12, "num_nodes": 200}, 316),                        # LDEPooling(200, c_num=12): 2400-d encoding
+    "xi_mean": ("xi-postmean-softplus2", {"hidden_size": 64, "num_nodes": 200}, 319),  # xi-vector, posterior mean
+    "xi_dist": ("xi-postdist-softplus2", {"hidden_size": 64, "num_nodes": 200}, 320),  # ... mean | spread
 }
 
 
@@ -440,7 +442,7 @@ def test_snowdar_attention_poolings_match_reference_golden(golden, cname):
         assert rel(m.extract_embedding_batch(feats).cpu().numpy(), want) < EMB_TOL, (cname, pos)
         assert rel(m.extract_embedding(feats[1]).numpy(), want[1]) < EMB_TOL, (cname, pos)
     with pytest.raises(NotImplementedError):
-        Xvector(40, 10, pooling="xi-postmean-softplus2")
+        Xvector(40, 10, pooling="no-such-pooling")
 
 
 def test_snowdar_bn_relu_order_and_weight_normalisation(golden):

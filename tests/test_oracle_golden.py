@@ -277,6 +277,8 @@ SNOWDAR_POOLING_CASES = {
     "mha_full": ("multi-head", {"num_head": 4, "share": False, "affine_layers": 2}, 314),
     "mres": ("multi-resolution", {"num_head": 4, "temperature": True, "affine_layers": 2}, 315),
     "lde": ("lde", {"num_head": 12, "num_nodes": 200}, 316),                        # LDEPooling(200, c_num=12): 2400-d encoding
+    "xi_mean": ("xi-postmean-softplus2", {"hidden_size": 64, "num_nodes": 200}, 319),  # xi-vector, posterior mean
+    "xi_dist": ("xi-postdist-softplus2", {"hidden_size": 64, "num_nodes": 200}, 320),  # ... mean | spread
 }
 
 
