@@ -809,8 +809,11 @@ def run_native(args, rank, world, local_rank):
                      "note": "3 bf16 MMAs per algorithmic MAC (hi*hi + lo*hi + hi*lo) to hold 1e-4 parity: the algorithmic "
                              "fraction is capped at 1/3 by construction",
                      "traffic": None,
-                     "traffic_static": {"bytes_per_launch_avg": 121383333, "source": "profiles/r02h_gemm_ncu_summary.txt "
-                                        "(builder-run ncu --set full of round 1; not measured by this run)"}},
+                     "traffic_static": {"bytes_per_launch_avg": 122224000, "algorithmic_bytes_note": "42 MB per batch must move "
+                                        "(features in, embeddings out, weights); the rest is the hi/lo activation planes between layers",
+                                        "source": "profiles/r05_gemm_ncu_summary.txt: dram__bytes_read + dram__bytes_write summed "
+                                        "over the six GEMM launches of one batch / 6 (builder-run ncu --set full; not measured by "
+                                        "this run)"}},
         "kernel_ms": dict({k: float(v) for k, v in zip(XV_KERNELS, kern_ms)}, inter_batch_gap=gap_ms,
                           regime="sustained pass, mean per batch"),
         "burst": burst,
