@@ -261,6 +261,22 @@ def pinned_copy(x):
     return h
 
 
+def balance_shards(speed, n_total, batch, cap):
+    """Shard sizes proportional to `speed` (one entry per rank) in whole batches by largest remainder, the odd tail of
+    n_total to the fastest rank; None if that would exceed `cap` utterances on a rank or leave one without a batch."""
+    speed = np.asarray(speed, dtype=np.float64)
+    q, rem = divmod(int(n_total), int(batch))
+    share = q * speed / speed.sum()
+    batches = [int(x) for x in np.floor(share)]
+    for r in np.argsort(-(share - np.floor(share)), kind="stable")[: q - sum(batches)]:
+        batches[int(r)] += 1
+    n_rank = [b * batch for b in batches]
+    n_rank[int(np.argmax(speed))] += rem
+    if sum(n_rank) != n_total or max(n_rank) > cap or min(n_rank) < batch:
+        return None
+    return n_rank
+
+
 class Timer:
     def __init__(self, world, dev):
         self.world, self.dev = world, dev
@@ -640,14 +656,9 @@ def run_native(args, rank, world, local_rank):
         speed = 1.0 / times.cpu().numpy()
         if os.environ.get("XVB_BENCH_FAKE_SPEED"):                  # test knob: pretend the ranks differ (comma-separated factors)
             speed = speed * np.array([float(v) for v in os.environ["XVB_BENCH_FAKE_SPEED"].split(",")][:world])
-        q, rem = divmod(n_total, B)                                 # whole batches by largest remainder, the odd tail to the fastest
-        share = q * speed / speed.sum()
-        batches = [int(x) for x in np.floor(share)]
-        for r in np.argsort(-(share - np.floor(share)))[: q - sum(batches)]:
-            batches[int(r)] += 1
-        n_rank = [b * B for b in batches]
-        n_rank[int(np.argmax(speed))] += rem
-        if sum(n_rank) == n_total and max(n_rank) <= cap and min(n_rank) >= B:
+        cut = balance_shards(speed, n_total, B, cap)
+        if cut is not None:
+            n_rank = cut
             row0 = sum(n_rank[:rank])
             n_mine = n_rank[rank]
             feats, spk, emb = feats_cap[:n_mine], spk_cap[:n_mine], emb_cap[:n_mine]

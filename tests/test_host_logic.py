@@ -294,3 +294,23 @@ def test_backend_transform_host_algebra_matches_oracle_and_reference(golden):
     got, want = proc.pca_from_statistics(mean, total), osc.pca_transform(emb)
     sign = np.sign(np.sum(got[:, :16] * want[:, :16], axis=1))[:, None]
     assert np.max(np.abs(got * sign - want)) < 1e-8
+
+
+def test_bench_shard_balancing_keeps_the_total_and_whole_batches():
+    """bench.balance_shards: sizes follow the measured speeds in whole batches, the total is exact, the odd tail goes to the
+    fastest rank, and an impossible cut (over the per-rank capacity) is refused rather than approximated."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    n, B = 125000, 256
+    cap = n + ((n * 8 // 100 + B - 1) // B) * B
+    for speed in ([1.0, 1.0], [1.0, 0.96], [1, 0.97, 1.02, 0.99, 1.0, 0.95, 1.03, 1.0]):
+        cut = bench.balance_shards(speed, n * len(speed), B, cap)
+        assert cut is not None and sum(cut) == n * len(speed) and max(cut) <= cap
+        fastest = int(np.argmax(speed))
+        assert all(c % B == 0 for i, c in enumerate(cut) if i != fastest)
+        order = np.argsort(speed)
+        assert all(cut[order[i]] <= cut[order[i + 1]] + B for i in range(len(speed) - 1))      # monotone in speed up to one batch
+    assert bench.balance_shards([1.0, 0.5], 2 * n, B, cap) is None                               # would need 167 k on one rank
+    assert bench.balance_shards([1.0, 1.0], 2 * n, B, cap) == [125072, 124928]
