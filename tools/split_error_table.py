@@ -20,7 +20,6 @@ float64 too, and the embedding is compared with the unrounded float64 forward.  
 import os
 import sys
 
-import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
