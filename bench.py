@@ -6,14 +6,20 @@
 One process per GPU (torchrun for N > 1).  A STEP is one pass of the hot path over one rank's shard of
 BASELINE.json configs[3]: 125 000 utterances (1 M over 8 GPUs) x 200 frames x 80-d, resident in HBM, through
 `xvb_extractor_extract_shard` in configs[1] batches (256 x 200) -- split -> tdnn1..5 (statistics pooling fused
-into tdnn5's epilogue) -> Chan merge -> tdnn6.affine -- and, for N > 1, the one collective of the path: the NCCL
-all-gather of the (N x 125 000, 512) embedding table.  A step lasts ~0.35 s, K steps several seconds: the timed
-region runs at SUSTAINED clocks; the `burst` block repeats round 1's measurement (one batch timed alone).
+into tdnn5's epilogue) -> Chan merge -> tdnn6.affine, batches alternating between two lanes -- and, for N > 1, the
+one exchange of the path: every GPU ends the step holding the whole (N x 125 000, 512) embedding table.  By default
+the table's copies are mapped into one another over NVLink (CUDA IPC) and every batch's embeddings are stored into
+all of them while the next batches run (csrc/peer.cu), a one-word all-reduce being the step's rendezvous; with
+XVB_BENCH_GATHER=nccl (or if the mapping is refused) it is one NCCL all-gather after the shard.  After the warm-up the
+shard sizes follow each rank's measured speed (whole batches, total unchanged; XVB_BENCH_BALANCE=0: equal shards).
+A step lasts ~0.36 s, K steps several seconds: the timed region runs at SUSTAINED clocks; the `burst` block repeats
+round 1's measurement (one batch timed alone).
 
   value        whole-job frames/s, inputs resident in HBM (CUDA events on the launching stream, barrier +
                synchronize both sides, max over ranks); weak scaling: per-GPU work is fixed
   e2e          the same shard through the C-ABI host-buffer call `xvb_extractor_extract_shard_host`: pinned host
-               features -> H2D (copy stream, overlapped) -> stack -> D2H of the embeddings, host clock
+               features -> H2D (copy stream, four device slots: the copies run ahead of both lanes) -> stack -> D2H of
+               the embeddings, host clock
   roofline     the tcgen05 TDNN GEMM: algorithmic FLOPs (5 630 976 FLOP/frame) / summed per-launch
                CUDA-event durations taken inside a sustained pass, against MEASURED_PEAKS' sustained bf16 peak;
                `burst` carries the isolated-batch figures against the burst peak.  The kernel executes 3 bf16
