@@ -224,60 +224,80 @@ attn_stats_pool_kernel(const float* __restrict__ logits, long long ldl, const fl
 // memory in channel chunks) and the weighted residual mean (a block = one utterance x 32 channels, w rows staged in
 // shared memory in time chunks).  K <= 64, K % 4 == 0 (pad the dictionary with zero-weight columns: beta = +inf is
 // not needed, the caller passes neg_beta = -inf for padded clusters so that their softmax weight is exactly 0).
-constexpr int kLdeFrames = 32, kLdeChunk = 64, kLdeMaxK = 64;
+constexpr int kLdeFr = 4;                      // frames per thread (weights kernel) / channels per thread (encode kernel)
+constexpr int kLdeFrames = 32 * kLdeFr, kLdeChunk = 32, kLdeMaxK = 64;
+
+// this thread's (up to 8) dictionary entries of one row: two 16-byte loads when the thread owns 8 consecutive ones
+__device__ __forceinline__ void lde_row8(const float* row, int g, int kq, int K, float (&m)[8]) {
+  if (kq == 8) {
+    const float4 a = *reinterpret_cast<const float4*>(row + g * 8), b = *reinterpret_cast<const float4*>(row + g * 8 + 4);
+    m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = (i < kq && g * kq + i < K) ? row[g * kq + i] : 0.f;
+  }
+}
 
 __global__ void __launch_bounds__(256)
 lde_weights_kernel(const float* __restrict__ x, long long ldx, long long rows, int C, const float* __restrict__ mu, int K,
                    const float* __restrict__ neg_beta, float* __restrict__ w) {
   __shared__ float xs[kLdeFrames][kLdeChunk + 1];
-  __shared__ float ms[kLdeChunk][kLdeMaxK];
-  const int f = threadIdx.x >> 3, g = threadIdx.x & 7;       // frame within the tile, cluster group: clusters g*kq .. +kq
+  __shared__ __align__(16) float ms[kLdeChunk][kLdeMaxK];
+  const int fq = threadIdx.x >> 3, g = threadIdx.x & 7;      // frames fq*4 .. fq*4+3 of the tile, clusters g*kq .. +kq
   const int kq = (K + 7) >> 3;                               // clusters per thread (<= 8)
   const long long row0 = (long long)blockIdx.x * kLdeFrames;
-  float d[8];
+  float d[kLdeFr][8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) d[i] = 0.f;
+  for (int r = 0; r < kLdeFr; ++r)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[r][i] = 0.f;
   for (int c0 = 0; c0 < C; c0 += kLdeChunk) {
     const int cc = min(kLdeChunk, C - c0);
     for (int e = threadIdx.x; e < kLdeFrames * kLdeChunk; e += 256) {
       const int ff = e / kLdeChunk, c = e - ff * kLdeChunk;
       xs[ff][c] = (row0 + ff < rows && c < cc) ? __ldg(x + (row0 + ff) * ldx + c0 + c) : 0.f;
     }
-    for (int e = threadIdx.x; e < kLdeChunk * K; e += 256) {
-      const int c = e / K, k = e - c * K;
-      ms[c][k] = c < cc ? __ldg(mu + (long long)(c0 + c) * K + k) : 0.f;   // padded channels: x = mu = 0
+    for (int e = threadIdx.x; e < kLdeChunk * kLdeMaxK; e += 256) {
+      const int c = e / kLdeMaxK, k = e - c * kLdeMaxK;
+      ms[c][k] = (c < cc && k < K) ? __ldg(mu + (long long)(c0 + c) * K + k) : 0.f;   // padded channels: x = mu = 0
     }
     __syncthreads();
     for (int c = 0; c < cc; ++c) {
-      const float xv = xs[f][c];
+      float m[8];
+      lde_row8(ms[c], g, kq, K, m);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int k = g * kq + i;
-        if (i < kq && k < K) { const float r = xv - ms[c][k]; d[i] = fmaf(r, r, d[i]); }
+      for (int r = 0; r < kLdeFr; ++r) {
+        const float xv = xs[fq * kLdeFr + r][c];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float q = xv - m[i]; d[r][i] = fmaf(q, q, d[r][i]); }   // absent clusters: unused
       }
     }
     __syncthreads();
   }
-  // softmax over the K clusters of this frame: the 8 threads of a frame are 8 consecutive lanes
-  float l[8], mx = -INFINITY;
+  float nb[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int k = g * kq + i;
-    l[i] = (i < kq && k < K) ? __ldg(neg_beta + k) * d[i] : -INFINITY;
-    mx = fmaxf(mx, l[i]);
-  }
+  for (int i = 0; i < 8; ++i) nb[i] = (i < kq && g * kq + i < K) ? __ldg(neg_beta + g * kq + i) : 0.f;
 #pragma unroll
-  for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  float sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { l[i] = expf(l[i] - mx); sum += l[i]; }   // exp(-inf) = 0 for absent clusters
-#pragma unroll
-  for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  if (row0 + f < rows) {
+  for (int r = 0; r < kLdeFr; ++r) {
+    // softmax over the K clusters of this frame: the 8 threads of a frame are 8 consecutive lanes
+    float l[8], mx = -INFINITY;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int k = g * kq + i;
-      if (i < kq && k < K) w[(row0 + f) * K + k] = l[i] / sum;
+      l[i] = (i < kq && g * kq + i < K) ? nb[i] * d[r][i] : -INFINITY;
+      mx = fmaxf(mx, l[i]);
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { l[i] = expf(l[i] - mx); sum += l[i]; }   // exp(-inf) = 0 for absent clusters
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const long long row = row0 + fq * kLdeFr + r;
+    if (row < rows) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < kq && g * kq + i < K) w[row * K + g * kq + i] = l[i] / sum;
     }
   }
 }
@@ -286,44 +306,53 @@ __global__ void __launch_bounds__(256)
 lde_encode_kernel(const float* __restrict__ x, long long ldx, int T, int C, const float* __restrict__ mu, int K,
                   const float* __restrict__ w, float* __restrict__ out, __nv_bfloat16* __restrict__ oh,
                   __nv_bfloat16* __restrict__ ol, long long ldo) {
-  __shared__ float ws[64][kLdeMaxK];                          // 64 frames of weights at a time
+  __shared__ __align__(16) float ws[64][kLdeMaxK];           // 64 frames of weights at a time
   const int b = blockIdx.y;
-  const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;      // channel within the tile, cluster group
-  const int c = blockIdx.x * 32 + cl;
+  const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;      // channels blockIdx.x*128 + i*32 + cl, cluster group g
   const int kq = (K + 7) >> 3;
-  float acc[8], m[8];
+  float acc[kLdeFr][8], m[kLdeFr][8];
+  int ch[kLdeFr];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int k = g * kq + i;
-    acc[i] = 0.f;
-    m[i] = (i < kq && k < K && c < C) ? __ldg(mu + (long long)c * K + k) : 0.f;
+  for (int r = 0; r < kLdeFr; ++r) {
+    ch[r] = blockIdx.x * (32 * kLdeFr) + r * 32 + cl;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = g * kq + i;
+      acc[r][i] = 0.f;
+      m[r][i] = (i < kq && k < K && ch[r] < C) ? __ldg(mu + (long long)ch[r] * K + k) : 0.f;
+    }
   }
   const float* xb = x + (long long)b * T * ldx;
   const float* wb = w + (long long)b * T * K;
   for (int t0 = 0; t0 < T; t0 += 64) {
     const int tn = min(64, T - t0);
-    for (int e = threadIdx.x; e < tn * K; e += 256) ws[e / K][e % K] = __ldg(wb + (long long)t0 * K + e);
+    for (int e = threadIdx.x; e < tn * kLdeMaxK; e += 256) {
+      const int t = e / kLdeMaxK, k = e - t * kLdeMaxK;
+      ws[t][k] = k < K ? __ldg(wb + (long long)(t0 + t) * K + k) : 0.f;
+    }
     __syncthreads();
-    if (c < C) {
-      for (int t = 0; t < tn; ++t) {
-        const float xv = __ldg(xb + (long long)(t0 + t) * ldx + c);
+    for (int t = 0; t < tn; ++t) {
+      float wv[8];
+      lde_row8(ws[t], g, kq, K, wv);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int k = g * kq + i;
-          if (i < kq && k < K) acc[i] = fmaf(ws[t][k], xv - m[i], acc[i]);
-        }
+      for (int r = 0; r < kLdeFr; ++r) {
+        const float xv = ch[r] < C ? __ldg(xb + (long long)(t0 + t) * ldx + ch[r]) : 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[r][i] = fmaf(wv[i], xv - m[r][i], acc[r][i]);   // absent clusters: weight 0
       }
     }
     __syncthreads();
   }
-  if (c < C) {
-    const float inv = 1.f / (float)T;
+  const float inv = 1.f / (float)T;
+#pragma unroll
+  for (int r = 0; r < kLdeFr; ++r) {
+    if (ch[r] >= C) continue;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int k = g * kq + i;
       if (i < kq && k < K) {
-        const float v = acc[i] * inv;
-        const long long o = (long long)c * K + k;
+        const float v = acc[r][i] * inv;
+        const long long o = (long long)ch[r] * K + k;
         out[(long long)b * C * K + o] = v;
         if (oh) {
           __nv_bfloat16 h, l;
@@ -458,26 +487,41 @@ attn_head_stats_pool_kernel(const float* __restrict__ logits, long long ldl, con
     }
     const float* lb = logits + (long long)b * T * ldl;
     const float* xb = x + (long long)b * T * ldx + c;
-    for (int t = warp; t < T; t += kApWarps) {
-      const float4 xv = __ldg(reinterpret_cast<const float4*>(xb + (long long)t * ldx));
-      const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-      const float* lr = lb + (long long)t * ldl;
+    const bool vec_logits = gdiv == 1 && (ldl & 3) == 0 && ((uintptr_t)lb & 15) == 0;   // per-channel logits: 16-byte loads
+    for (int t0 = warp; t0 < T; t0 += kApWarps * kApRows) {
+      float4 xv[kApRows], lv[kApRows];                       // kApRows frames in flight per thread before any is consumed
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float l = __ldg(lr + g[k]);
-        if (softplus2log) {
-          l = 2.f * logf(l > 20.f ? l : log1pf(expf(l)));    // Softplus(beta=1, threshold=20), then 2 log
-          if (l == -INFINITY) continue;                      // zero precision: weight exactly 0, like exp(-inf) in the softmax
+      for (int r = 0; r < kApRows; ++r) {
+        const int t = t0 + r * kApWarps;
+        if (t < T) {
+          xv[r] = __ldcs(reinterpret_cast<const float4*>(xb + (long long)t * ldx));
+          const float* lr = lb + (long long)t * ldl;
+          if (vec_logits) lv[r] = __ldcs(reinterpret_cast<const float4*>(lr + o));
+          else lv[r] = make_float4(__ldg(lr + g[0]), __ldg(lr + g[1]), __ldg(lr + g[2]), __ldg(lr + g[3]));
         }
-        OnlineU& s = st[k];
-        const float mn = fmaxf(s.m, l);
-        const float sc = expf(s.m - mn), e = expf(l - mn);
-        s.s0 = fmaf(s.s0, sc, e);
-        s.s1 = fmaf(s.s1, sc, e * xs[k]);
-        s.s2 = fmaf(s.s2, sc, e * xs[k] * xs[k]);
-        s.m = mn;
-        s.u1 += xs[k];
-        s.u2 = fmaf(xs[k], xs[k], s.u2);
+      }
+#pragma unroll
+      for (int r = 0; r < kApRows; ++r) {
+        if (t0 + r * kApWarps >= T) continue;
+        const float xs[4] = {xv[r].x, xv[r].y, xv[r].z, xv[r].w};
+        const float ls[4] = {lv[r].x, lv[r].y, lv[r].z, lv[r].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float l = ls[k];
+          if (softplus2log) {
+            l = 2.f * logf(l > 20.f ? l : log1pf(expf(l)));  // Softplus(beta=1, threshold=20), then 2 log
+            if (l == -INFINITY) continue;                    // zero precision: weight exactly 0, like exp(-inf) in the softmax
+          }
+          OnlineU& s = st[k];
+          const float mn = fmaxf(s.m, l);
+          const float sc = expf(s.m - mn), e = expf(l - mn);
+          s.s0 = fmaf(s.s0, sc, e);
+          s.s1 = fmaf(s.s1, sc, e * xs[k]);
+          s.s2 = fmaf(s.s2, sc, e * xs[k] * xs[k]);
+          s.m = mn;
+          s.u1 += xs[k];
+          s.u2 = fmaf(xs[k], xs[k], s.u2);
+        }
       }
     }
   }
@@ -541,7 +585,7 @@ extern "C" int xvb_lde_pool(const float* x, int64_t ldx, int B, int T, int C, co
   lde_weights_kernel<<<(unsigned)((rows + kLdeFrames - 1) / kLdeFrames), 256, 0, (cudaStream_t)stream>>>(x, ldx, rows, C, mu, K,
                                                                                                         neg_beta, w_scratch);
   XVB_LAUNCH_CHECK();
-  dim3 grid((C + 31) / 32, B);
+  dim3 grid((C + 32 * kLdeFr - 1) / (32 * kLdeFr), B);
   lde_encode_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, T, C, mu, K, w_scratch, out,
                                                            reinterpret_cast<__nv_bfloat16*>(out_hi),
                                                            reinterpret_cast<__nv_bfloat16*>(out_lo), ldo);
