@@ -461,6 +461,7 @@ struct OnlineU {
 // xi-vector form (xivec_stdinit_softplus2_prec_pooling, pooling.py:165-212): the raw logit z becomes 2 log(softplus(z)) (a frame's
 // log-precision, :189-190) and the softmax runs over T + 1 elements, the extra one being the prior (logit prior_logit[c], value
 // prior_x[c], :194-202): it initialises the online-softmax state of warp 0.
+template <int kRows>
 __global__ void __launch_bounds__(kApWarps * 32)
 attn_head_stats_pool_kernel(const float* __restrict__ logits, long long ldl, const float* __restrict__ x, long long ldx,
                             int T, int C, int O, int gdiv, float floor_, int unweighted_var, const float* __restrict__ prior_logit,
@@ -488,10 +489,10 @@ attn_head_stats_pool_kernel(const float* __restrict__ logits, long long ldl, con
     const float* lb = logits + (long long)b * T * ldl;
     const float* xb = x + (long long)b * T * ldx + c;
     const bool vec_logits = gdiv == 1 && (ldl & 3) == 0 && ((uintptr_t)lb & 15) == 0;   // per-channel logits: 16-byte loads
-    for (int t0 = warp; t0 < T; t0 += kApWarps * kApRows) {
-      float4 xv[kApRows], lv[kApRows];                       // kApRows frames in flight per thread before any is consumed
+    for (int t0 = warp; t0 < T; t0 += kApWarps * kRows) {
+      float4 xv[kRows], lv[kRows];                       // kRows frames in flight per thread before any is consumed
 #pragma unroll
-      for (int r = 0; r < kApRows; ++r) {
+      for (int r = 0; r < kRows; ++r) {
         const int t = t0 + r * kApWarps;
         if (t < T) {
           xv[r] = __ldcs(reinterpret_cast<const float4*>(xb + (long long)t * ldx));
@@ -501,7 +502,7 @@ attn_head_stats_pool_kernel(const float* __restrict__ logits, long long ldl, con
         }
       }
 #pragma unroll
-      for (int r = 0; r < kApRows; ++r) {
+      for (int r = 0; r < kRows; ++r) {
         if (t0 + r * kApWarps >= T) continue;
         const float xs[4] = {xv[r].x, xv[r].y, xv[r].z, xv[r].w};
         const float ls[4] = {lv[r].x, lv[r].y, lv[r].z, lv[r].w};
@@ -636,7 +637,11 @@ extern "C" int xvb_attn_head_stats_pool_prior(const float* logits, int64_t ldl, 
   XVB_CHECK_ARG((out_hi != nullptr) == (out_lo != nullptr), "xvb_attn_head_stats_pool: out_hi/out_lo must both be set or both NULL");
   if (out_hi) XVB_CHECK_ARG(ldo % 4 == 0 && ldo >= 2 * (int64_t)O, "xvb_attn_head_stats_pool: ldo too small / unaligned");
   dim3 grid((O + 127) / 128, B);
-  attn_head_stats_pool_kernel<<<grid, kApWarps * 32, 0, (cudaStream_t)stream>>>(
+  // frames in flight per thread: 1 measured fastest (0.150 / 0.167 / 0.190 ms for 1 / 2 / 4 on the 256 x 200 x 1500 tensor,
+  // same box, profiles/README.md r05c): the extra registers of the unrolled forms cost more occupancy than they hide latency
+  static const int rows_knob = getenv("XVB_ATTN_ROWS") ? atoi(getenv("XVB_ATTN_ROWS")) : 1;
+  auto* kern = rows_knob == 1 ? attn_head_stats_pool_kernel<1> : rows_knob == 2 ? attn_head_stats_pool_kernel<2> : attn_head_stats_pool_kernel<4>;
+  kern<<<grid, kApWarps * 32, 0, (cudaStream_t)stream>>>(
       logits, ldl, x, ldx, T, C, O, gdiv, floor_, unweighted_var, prior_logit, prior_x, softplus2log, out,
       reinterpret_cast<__nv_bfloat16*>(out_hi), reinterpret_cast<__nv_bfloat16*>(out_lo), ldo);
   XVB_LAUNCH_CHECK();
