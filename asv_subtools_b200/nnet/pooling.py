@@ -86,25 +86,18 @@ class AttentionAlphaComponent(torch.nn.Module):
                     self.t = torch.nn.Parameter(torch.zeros(1, num_head, 1, 1))
         self.input_dim, self.num_head, self.split_input, self.share = input_dim, num_head, split_input, share
         self.temperature, self.fixed = temperature, fixed
-        final_dim = 1 if share else (input_dim // num_head if split_input else input_dim)
-        first_groups = last_groups = 1
-        if affine_layers == 1:
-            last_in = input_dim
-            if num_head > 1 and split_input:
-                last_groups = num_head
-            self.relu_affine = False
-        elif affine_layers == 2:
-            last_in = hidden_size * num_head
-            if num_head > 1:
-                last_groups = num_head
-                if split_input:
-                    first_groups = num_head
-            self.relu_affine = True
-            self.first_affine = TdnnAffine(input_dim, last_in, context=context, bias=bias, groups=first_groups)
-        else:
+        if affine_layers not in (1, 2):
             raise ValueError("Expected 1 or 2 affine layers, but got {}.".format(affine_layers))
-        self.final_dim = final_dim
-        self.last_affine = TdnnAffine(last_in, final_dim * num_head, context=context, bias=bias, groups=last_groups)
+        multi = num_head > 1
+        # one logit per head when the weight is shared, else one per pooled channel of the head
+        self.final_dim = 1 if share else (input_dim // num_head if split_input else input_dim)
+        self.relu_affine = affine_layers == 2
+        hidden = hidden_size * num_head
+        if self.relu_affine:     # hidden layer: per-head blocks; its input is split too only for split heads
+            self.first_affine = TdnnAffine(input_dim, hidden, context=context, bias=bias, groups=num_head if multi and split_input else 1)
+        last_in = hidden if self.relu_affine else input_dim
+        last_groups = num_head if multi and (self.relu_affine or split_input) else 1
+        self.last_affine = TdnnAffine(last_in, self.final_dim * num_head, context=context, bias=bias, groups=last_groups)
 
     def head_temperatures(self):
         """(num_head,) divisors of the logits, or None: fixed buffer as stored, learnt as 1 + t^2 (:308-313)."""

@@ -96,3 +96,28 @@ def test_extraction_wrapper_rewrites_only_the_hard_coded_extractor_command(tmp_p
     for l in lines:
         assert "-m asv_subtools_b200.pipeline.extract_embeddings --batch-size 256 --blueprint-dir" in l
         assert "--use-gpu" in l and "onestep/extract_embeddings.py" not in l
+
+
+@pytest.mark.parametrize("pooling,pp", [
+    ("multi-head", {"num_head": 4, "share": False}),
+    ("multi-head", {"num_head": 2, "affine_layers": 2, "hidden_size": 32}),
+    ("multi-resolution", {"num_head": 4, "temperature": True, "affine_layers": 1, "share": False}),
+    ("multi-resolution", {"num_head": 3, "temperature": True, "affine_layers": 2, "share": False, "fixed": False}),
+    ("attentive", {"affine_layers": 2, "context": [-1, 0, 1]}),
+    ("lde", {"num_head": 5, "num_nodes": 64}),
+    ("xi-postdist-softplus2", {"hidden_size": 32, "num_nodes": 64}),
+])
+def test_snowdar_pooling_variants_register_the_reference_parameters(ref_utils, pooling, pp):
+    """Every pooling option of the snowdar blueprint's switch (snowdar_xvector.py:119-136): the B200 blueprint registers the
+    same parameter / buffer names and shapes as the reference's (grouped attention affines, temperatures, LDE dictionary,
+    xi-vector prior), so reference checkpoints of those configurations load with strict=True."""
+    creation = 'Xvector(40,10,training=False,pooling="{}",pooling_params={!r})'.format(pooling, pp)
+    ref = ref_utils.create_model_from_py(os.path.join(REF, "pytorch/model/snowdar_xvector.py"), creation)
+    want = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    for name in [m for m in sys.modules if m == "snowdar_xvector"]:
+        del sys.modules[name]
+    ours = ref_utils.create_model_from_py(os.path.join(ROOT, "asv_subtools_b200/model/snowdar_xvector.py"), creation)
+    assert {k: tuple(v.shape) for k, v in ours.state_dict().items()} == want
+    assert not ours.load_state_dict(ref.state_dict(), strict=True).missing_keys
+    for name in [m for m in sys.modules if m == "snowdar_xvector"]:
+        del sys.modules[name]
