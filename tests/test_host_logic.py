@@ -314,3 +314,26 @@ def test_bench_shard_balancing_keeps_the_total_and_whole_batches():
         assert all(cut[order[i]] <= cut[order[i + 1]] + B for i in range(len(speed) - 1))      # monotone in speed up to one batch
     assert bench.balance_shards([1.0, 0.5], 2 * n, B, cap) is None                               # would need 167 k on one rank
     assert bench.balance_shards([1.0, 1.0], 2 * n, B, cap) == [125072, 124928]
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the native one): one JSON line with the contract's keys,
+    `impl` = reference, the same metric / unit / config keys as the native arm, an `e2e` block without copies, no GPU needed;
+    and without a GPU the native arm refuses to run instead of falling back."""
+    import json
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3"],
+                       capture_output=True, text=True, env=env, cwd=ROOT, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches", "impl"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["higher_is_better"] is True and line["vs_baseline"] is None
+    assert line["config"]["batch"] == 256 and line["config"]["frames_per_utt"] == 200 and "workload" in line["config"]
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["gpu_launches"] == 0
+    if not torch.cuda.is_available():
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, env=env, cwd=ROOT,
+                           timeout=300)
+        assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
